@@ -1,0 +1,554 @@
+// kr_attn.cu — tcgen05 flash attention, forward + backward, head_dim 64
+// (reference: MultiHeadAttentionImproved.forward, model/transformers.py:299-316,393-398 — SDPA with an
+//  additive causal(-inf) + key-padding(-inf) mask and scale 1/sqrt(d_k)).
+//
+// Q/K/V/O/dO live token-major as [batch, seq, heads, 64] bf16 (arbitrary seq/batch strides) and are
+// reached through 4-D TMA maps (d, head, seq, batch), so the projections' [tokens, H*64] GEMM
+// outputs are consumed in place.  The T x T mask is never materialised: causality and the per-key
+// padding byte-mask are predicates on the S tile.
+//
+// forward : one CTA per (128-query tile, head, batch).  S = Q K^T lands in TMEM (128 lanes x 128
+//           cols), each of the 128 threads owns one query row: online softmax in registers, P is
+//           written to swizzled smem as the bf16 A operand of O_tile = P V (V is the MN-major B
+//           operand straight from its natural [kv, d] tile), O accumulates in registers.
+// backward: one CTA per (128-key tile, head, batch) looping over query tiles: S and dP = dO V^T in
+//           TMEM, P / dS rebuilt per row, then dV += P^T dO, dK += dS^T Q (P, dS as MN-major A
+//           operands, dO / Q as MN-major B operands — no transposed copies) and dQ_tile = dS K,
+//           which is reduced into the fp32 dQ buffer with vector atomics.
+#include "kr_common.cuh"
+
+namespace {
+using namespace kr;
+
+constexpr int TQ = 128, TK = 128, HD = 64;
+constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: 128 rows x 128 B
+
+struct AttnParams {
+  int B, H, Sq, Sk;
+  float scale, scale_log2;
+  const uint8_t* key_mask;  // [B, Sk] 1 = masked key, or null
+  bf16* O; long long o_ss, o_bs;
+  float* lse;               // [B, H, Sq], log2 domain
+  const float* delta;       // [B, H, Sq]
+  float* dQ; long long dq_ss, dq_bs;
+  bf16* dK; long long dk_ss, dk_bs;
+  bf16* dV; long long dv_ss, dv_bs;
+};
+
+// [128 rows x 64 K] bf16 tile, K-major, SW128: k-th UMMA_K slice.
+__device__ __forceinline__ uint64_t desc_k64(uint32_t base, int k) {
+  return make_smem_desc_sw128(base + k * 32, 16, 1024);
+}
+// [128 rows x 128 K] bf16 tile stored as two 64-wide K chunks (16 KB each), K-major.
+__device__ __forceinline__ uint64_t desc_k128(uint32_t base, int k) {
+  return make_smem_desc_sw128(base + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024);
+}
+// Same two-chunk tile read as an MN-major operand: MN = the 128 contiguous columns (two 64-chunks,
+// LBO apart), K = the rows (8-row groups SBO apart); k-th slice = rows [16k, 16k+16).
+__device__ __forceinline__ uint64_t desc_mn128(uint32_t base, int k) {
+  return make_smem_desc_sw128(base + k * 2048, TILE_BYTES, 1024);
+}
+// [rows x 64] tile read as MN-major operand with MN = the 64 columns, K = rows.
+__device__ __forceinline__ uint64_t desc_mn64(uint32_t base, int k) {
+  return make_smem_desc_sw128(base + k * 2048, 2048, 1024);
+}
+
+// store 32 packed-bf16 columns [32c, 32c+32) of `row` into a two-chunk [128 x 128] SW128 tile
+__device__ __forceinline__ void store_chunk_sw128(uint8_t* tile, int row, int c, const uint32_t* pk) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int u = c * 4 + q;
+    uint8_t* dst = tile + (u >> 3) * TILE_BYTES + row * 128 + (((u & 7) ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+constexpr int FWD_SMEM = 7 * TILE_BYTES + 256 + 1024;
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TILE_BYTES;       // 2 stages
+  uint8_t* sV = smem + 3 * TILE_BYTES;   // 2 stages
+  uint8_t* sP = smem + 5 * TILE_BYTES;   // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * TILE_BYTES);
+  uint64_t* q_bar = bars;
+  uint64_t* k_bar = bars + 1;
+  uint64_t* v_bar = bars + 3;
+  uint64_t* s_bar = bars + 5;
+  uint64_t* o_bar = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint32_t* mask_words = tmem_slot + 2;  // [2][4]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+  int n_tiles = (p.Sk + TK - 1) / TK;
+  if (CAUSAL) n_tiles = min(n_tiles, (int)blockIdx.x + 1);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(q_bar, TILE_BYTES);
+    tma_load_4d(sQ, &tmQ, q_bar, 0, h, q0, b);
+    mbar_arrive_expect_tx(&k_bar[0], TILE_BYTES);
+    tma_load_4d(sK, &tmK, &k_bar[0], 0, h, 0, b);
+    mbar_arrive_expect_tx(&v_bar[0], TILE_BYTES);
+    tma_load_4d(sV, &tmV, &v_bar[0], 0, h, 0, b);
+  }
+
+  float o_acc[HD];
+#pragma unroll
+  for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+  const int qi = q0 + tid;
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+
+  for (int j = 0; j < n_tiles; ++j) {
+    const int st = j & 1;
+    {
+      const int key = j * TK + tid;
+      bool masked = key >= p.Sk;
+      if (!masked && p.key_mask != nullptr) masked = p.key_mask[(long long)b * p.Sk + key] != 0;
+      const unsigned w = __ballot_sync(0xffffffffu, masked);
+      if (lane == 0) mask_words[st * 4 + warp] = w;
+    }
+    if (tid == 0) {
+      if (j + 1 < n_tiles) {
+        const int ns = st ^ 1;
+        mbar_arrive_expect_tx(&k_bar[ns], TILE_BYTES);
+        tma_load_4d(sK + ns * TILE_BYTES, &tmK, &k_bar[ns], 0, h, (j + 1) * TK, b);
+        mbar_arrive_expect_tx(&v_bar[ns], TILE_BYTES);
+        tma_load_4d(sV + ns * TILE_BYTES, &tmV, &v_bar[ns], 0, h, (j + 1) * TK, b);
+      }
+      if (j == 0) mbar_wait(q_bar, 0);
+      mbar_wait(&k_bar[st], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + st * TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k)
+        umma_bf16_ss(tmem_S, desc_k64(aQ, k), desc_k64(aK, k), idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(s_bar);
+    }
+    __syncthreads();
+    mbar_wait(s_bar, j & 1);
+    tc_fence_after();
+    uint32_t mw[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mw[c] = mask_words[st * 4 + c];
+
+    // pass 1: row max (log2 domain)
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_S + t_lane + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int key = j * TK + c * 32 + i;
+        const bool masked = ((mw[c] >> i) & 1u) || (CAUSAL && key > qi);
+        const float s = masked ? -INFINITY : __uint_as_float(r[i]) * p.scale_log2;
+        mx = fmaxf(mx, s);
+      }
+    }
+    const float m_new = fmaxf(m_run, mx);
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float alpha = fast_exp2(m_run - m_use);
+    // pass 2: probabilities -> bf16 A operand in smem
+    float rowsum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_S + t_lane + c * 32, r);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float pv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = j * TK + c * 32 + i + e;
+          const bool masked = ((mw[c] >> (i + e)) & 1u) || (CAUSAL && key > qi);
+          pv[e] = masked ? 0.f : fast_exp2(__uint_as_float(r[i + e]) * p.scale_log2 - m_use);
+        }
+        // accumulate the row sum from the bf16-rounded values the MMA will actually see
+        const uint32_t u = pack_bf16(pv[0], pv[1]);
+        const float2 rb = unpack_bf16(u);
+        rowsum += rb.x + rb.y;
+        pk[i >> 1] = u;
+      }
+      store_chunk_sw128(sP, tid, c, pk);
+    }
+    l_run = l_run * alpha + rowsum;
+    m_run = m_new;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(&v_bar[st], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t aP = smem_u32(sP), aV = smem_u32(sV + st * TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < TK / 16; ++k)
+        umma_bf16_ss(tmem_O, desc_k128(aP, k), desc_mn64(aV, k), idesc_o, k > 0 ? 1u : 0u);
+      umma_commit(o_bar);
+    }
+    __syncwarp();
+    mbar_wait(o_bar, j & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_O + t_lane + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(r[i]);
+    }
+    tc_fence_before();
+  }
+
+  if (qi < p.Sq) {
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    bf16* orow = p.O + (long long)b * p.o_bs + (long long)qi * p.o_ss + h * HD;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint4 q;
+      q.x = pack_bf16(o_acc[8 * i] * inv, o_acc[8 * i + 1] * inv);
+      q.y = pack_bf16(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv);
+      q.z = pack_bf16(o_acc[8 * i + 4] * inv, o_acc[8 * i + 5] * inv);
+      q.w = pack_bf16(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv);
+      *reinterpret_cast<uint4*>(orow + 8 * i) = q;
+    }
+    p.lse[((long long)b * p.H + h) * p.Sq + qi] = l_run > 0.f ? m_run + log2f(l_run) : 0.f;
+  }
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward prep: delta[b,h,q] = sum_d dO * O   (one warp per token row of H*64 elements)
+// ---------------------------------------------------------------------------------------------
+__global__ void attn_bwd_prep_kernel(const bf16* __restrict__ O, long long o_ss, long long o_bs,
+                                     const bf16* __restrict__ dO, long long do_ss, long long do_bs,
+                                     float* __restrict__ delta, int B, int H, int Sq) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * Sq) return;
+  const int b = row / Sq, q = row % Sq;
+  const bf16* o = O + (long long)b * o_bs + (long long)q * o_ss;
+  const bf16* d = dO + (long long)b * do_bs + (long long)q * do_ss;
+  // H*64 elements, 8 per 16-byte vector -> H*8 vectors; vector v belongs to head v/8
+  for (int v0 = 0; v0 < H * 8; v0 += 32) {
+    const int v = v0 + lane;
+    float acc = 0.f;
+    if (v < H * 8) {
+      const uint4 a = *reinterpret_cast<const uint4*>(o + v * 8);
+      const uint4 g = *reinterpret_cast<const uint4*>(d + v * 8);
+      const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = unpack_bf16(aa[i]), y = unpack_bf16(gg[i]);
+        acc += x.x * y.x + x.y * y.y;
+      }
+    }
+    // reduce groups of 8 lanes (one head)
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if ((lane & 7) == 0 && v < H * 8) delta[((long long)b * H + (v >> 3)) * Sq + q] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+constexpr int BWD_SMEM = 8 * TILE_BYTES + 256 + 1024;
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(128, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + TILE_BYTES;
+  uint8_t* sQ = smem + 2 * TILE_BYTES;
+  uint8_t* sdO = smem + 3 * TILE_BYTES;
+  uint8_t* sP = smem + 4 * TILE_BYTES;   // 32 KB
+  uint8_t* sdS = smem + 6 * TILE_BYTES;  // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * TILE_BYTES);
+  uint64_t* kv_bar = bars;
+  uint64_t* qdo_bar = bars + 1;
+  uint64_t* sdp_bar = bars + 2;
+  uint64_t* out_bar = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* mask_words = tmem_slot + 2;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kv0 = blockIdx.x * TK, h = blockIdx.y, b = blockIdx.z;
+  const int n_q_tiles = (p.Sq + TQ - 1) / TQ;
+  const int i_begin = CAUSAL ? (int)blockIdx.x : 0;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  {
+    const int key = kv0 + tid;
+    bool masked = key >= p.Sk;
+    if (!masked && p.key_mask != nullptr) masked = p.key_mask[(long long)b * p.Sk + key] != 0;
+    const unsigned w = __ballot_sync(0xffffffffu, masked);
+    if (lane == 0) mask_words[warp] = w;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dV = tmem_base + 256,
+                 tmem_dK = tmem_base + 320, tmem_dQ = tmem_base + 384;
+  const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+  uint32_t mw[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) mw[c] = mask_words[c];
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(kv_bar, 2 * TILE_BYTES);
+    tma_load_4d(sK, &tmK, kv_bar, 0, h, kv0, b);
+    tma_load_4d(sV, &tmV, kv_bar, 0, h, kv0, b);
+  }
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);    // S, dP
+  constexpr uint32_t idesc_tt = make_idesc_bf16(128, 64, 1, 1);    // dV, dK
+  constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);    // dQ
+  const long long bh = (long long)b * p.H + h;
+
+  int it = 0;
+  for (int i = i_begin; i < n_q_tiles; ++i, ++it) {
+    const int q0 = i * TQ;
+    const int qi = q0 + tid;
+    const bool row_ok = qi < p.Sq;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(qdo_bar, 2 * TILE_BYTES);
+      tma_load_4d(sQ, &tmQ, qdo_bar, 0, h, q0, b);
+      tma_load_4d(sdO, &tmdO, qdo_bar, 0, h, q0, b);
+      if (it == 0) mbar_wait(kv_bar, 0);
+      mbar_wait(qdo_bar, it & 1);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), adO = smem_u32(sdO), aV = smem_u32(sV);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k)
+        umma_bf16_ss(tmem_S, desc_k64(aQ, k), desc_k64(aK, k), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k)
+        umma_bf16_ss(tmem_dP, desc_k64(adO, k), desc_k64(aV, k), idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(sdp_bar);
+    }
+    __syncwarp();
+    const float lse_i = row_ok ? p.lse[bh * p.Sq + qi] : 0.f;
+    const float delta_i = row_ok ? p.delta[bh * p.Sq + qi] : 0.f;
+    mbar_wait(sdp_bar, it & 1);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t rs[32], rp[32];
+      tmem_ld_32x32(tmem_S + t_lane + c * 32, rs);
+      tmem_ld_32x32(tmem_dP + t_lane + c * 32, rp);
+      tmem_ld_wait();
+      uint32_t pkP[16], pkS[16];
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        float pv[2], ds[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int key = kv0 + c * 32 + e + u;
+          const bool masked = !row_ok || ((mw[c] >> (e + u)) & 1u) || (CAUSAL && key > qi);
+          pv[u] = masked ? 0.f : fast_exp2(__uint_as_float(rs[e + u]) * p.scale_log2 - lse_i);
+          ds[u] = pv[u] * (__uint_as_float(rp[e + u]) - delta_i) * p.scale;
+        }
+        pkP[e >> 1] = pack_bf16(pv[0], pv[1]);
+        pkS[e >> 1] = pack_bf16(ds[0], ds[1]);
+      }
+      store_chunk_sw128(sP, tid, c, pkP);
+      store_chunk_sw128(sdS, tid, c, pkS);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS), aQ = smem_u32(sQ), adO = smem_u32(sdO),
+                     aK = smem_u32(sK);
+#pragma unroll
+      for (int k = 0; k < TQ / 16; ++k)   // dV[kv,d] += P^T dO, contraction over the 128 query rows
+        umma_bf16_ss(tmem_dV, desc_mn128(aP, k), desc_mn64(adO, k), idesc_tt, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < TQ / 16; ++k)   // dK[kv,d] += dS^T Q
+        umma_bf16_ss(tmem_dK, desc_mn128(adS, k), desc_mn64(aQ, k), idesc_tt, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < TK / 16; ++k)   // dQ[q,d] = dS K, contraction over the 128 keys
+        umma_bf16_ss(tmem_dQ, desc_k128(adS, k), desc_mn64(aK, k), idesc_dq, k > 0 ? 1u : 0u);
+      umma_commit(out_bar);
+    }
+    __syncwarp();
+    mbar_wait(out_bar, it & 1);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_dQ + t_lane + c * 32, r);
+      tmem_ld_wait();
+      if (row_ok) {
+        float* dq = p.dQ + (long long)b * p.dq_bs + (long long)qi * p.dq_ss + h * HD + c * 32;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          atomicAdd(reinterpret_cast<float4*>(dq + 4 * e),
+                    make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]),
+                                __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3])));
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+
+  // dK / dV: thread tid owns key row kv0 + tid
+  {
+    const int kv = kv0 + tid;
+    const bool ok = kv < p.Sk;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      bf16* base = which == 0 ? p.dV : p.dK;
+      const long long ss = which == 0 ? p.dv_ss : p.dk_ss, bs = which == 0 ? p.dv_bs : p.dk_bs;
+      const uint32_t tm = which == 0 ? tmem_dV : tmem_dK;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        if (it > 0) {
+          tmem_ld_32x32(tm + t_lane + c * 32, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) r[e] = 0u;
+        }
+        if (ok) {
+          bf16* row = base + (long long)b * bs + (long long)kv * ss + h * HD + c * 32;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint4 q;
+            q.x = pack_bf16(__uint_as_float(r[8 * e]), __uint_as_float(r[8 * e + 1]));
+            q.y = pack_bf16(__uint_as_float(r[8 * e + 2]), __uint_as_float(r[8 * e + 3]));
+            q.z = pack_bf16(__uint_as_float(r[8 * e + 4]), __uint_as_float(r[8 * e + 5]));
+            q.w = pack_bf16(__uint_as_float(r[8 * e + 6]), __uint_as_float(r[8 * e + 7]));
+            *reinterpret_cast<uint4*>(row + 8 * e) = q;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+int make_head_map(CUtensorMap* m, const void* ptr, int H, int S, int B, long long ss, long long bs) {
+  return kr_make_tmap_bf16_heads(m, ptr, H, S, B, HD, ss, bs, 128);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int kr_attn_fwd(const void* q, long long q_ss, long long q_bs, const void* k, long long k_ss,
+                           long long k_bs, const void* v, long long v_ss, long long v_bs, void* o,
+                           long long o_ss, long long o_bs, float* lse, const unsigned char* key_mask,
+                           int B, int H, int Sq, int Sk, int causal, float scale, void* stream) {
+  if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) { kr_set_error("kr_attn_fwd: empty problem"); return KR_ERR_ARG; }
+  if (causal && Sq != Sk) { kr_set_error("kr_attn_fwd: causal needs Sq == Sk"); return KR_ERR_ARG; }
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_head_map(&tq, q, H, Sq, B, q_ss, q_bs)) != KR_OK) return rc;
+  if ((rc = make_head_map(&tk, k, H, Sk, B, k_ss, k_bs)) != KR_OK) return rc;
+  if ((rc = make_head_map(&tv, v, H, Sk, B, v_ss, v_bs)) != KR_OK) return rc;
+  AttnParams p{};
+  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.key_mask = key_mask; p.O = reinterpret_cast<bf16*>(o); p.o_ss = o_ss; p.o_bs = o_bs; p.lse = lse;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    attr = true;
+  }
+  dim3 grid((Sq + TQ - 1) / TQ, H, B);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (causal) attn_fwd_kernel<true><<<grid, 128, FWD_SMEM, st>>>(tq, tk, tv, p);
+  else        attn_fwd_kernel<false><<<grid, 128, FWD_SMEM, st>>>(tq, tk, tv, p);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+extern "C" int kr_attn_bwd(const void* q, long long q_ss, long long q_bs, const void* k, long long k_ss,
+                           long long k_bs, const void* v, long long v_ss, long long v_bs, const void* o,
+                           long long o_ss, long long o_bs, const void* d_o, long long do_ss,
+                           long long do_bs, const float* lse, float* delta, float* dq, long long dq_ss,
+                           long long dq_bs, void* dk, long long dk_ss, long long dk_bs, void* dv,
+                           long long dv_ss, long long dv_bs, const unsigned char* key_mask, int B, int H,
+                           int Sq, int Sk, int causal, float scale, void* stream) {
+  if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) { kr_set_error("kr_attn_bwd: empty problem"); return KR_ERR_ARG; }
+  if (causal && Sq != Sk) { kr_set_error("kr_attn_bwd: causal needs Sq == Sk"); return KR_ERR_ARG; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    const int rows = B * Sq, wpb = 8;
+    attn_bwd_prep_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+        reinterpret_cast<const bf16*>(o), o_ss, o_bs, reinterpret_cast<const bf16*>(d_o), do_ss, do_bs,
+        delta, B, H, Sq);
+    KR_CHECK_LAUNCH();
+  }
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  if ((rc = make_head_map(&tq, q, H, Sq, B, q_ss, q_bs)) != KR_OK) return rc;
+  if ((rc = make_head_map(&tk, k, H, Sk, B, k_ss, k_bs)) != KR_OK) return rc;
+  if ((rc = make_head_map(&tv, v, H, Sk, B, v_ss, v_bs)) != KR_OK) return rc;
+  if ((rc = make_head_map(&tdo, d_o, H, Sq, B, do_ss, do_bs)) != KR_OK) return rc;
+  AttnParams p{};
+  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.key_mask = key_mask; p.lse = const_cast<float*>(lse); p.delta = delta;
+  p.dQ = dq; p.dq_ss = dq_ss; p.dq_bs = dq_bs;
+  p.dK = reinterpret_cast<bf16*>(dk); p.dk_ss = dk_ss; p.dk_bs = dk_bs;
+  p.dV = reinterpret_cast<bf16*>(dv); p.dv_ss = dv_ss; p.dv_bs = dv_bs;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    attr = true;
+  }
+  dim3 grid((Sk + TK - 1) / TK, H, B);
+  if (causal) attn_bwd_kernel<true><<<grid, 128, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
+  else        attn_bwd_kernel<false><<<grid, 128, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}

@@ -1,0 +1,490 @@
+// kr_norm.cu — HBM-bound normalisation kernels of the transformer blocks (warp-per-row, float4
+// loads, warp-shuffle reductions; column gradients reduced per block then one atomic per column).
+//   * LayerNorm fwd/bwd            (reference model/transformers.py:478,485,564,572,581,660; eps 1e-5)
+//   * FFN output RMSNorm + residual (transformers.py:94,105-111; nn.RMSNorm(eps=None) -> finfo.eps)
+//   * per-head Q/K/V RMSNorm with learned gain + rotate-half RoPE, fwd/bwd
+//     (transformers.py:145-148,260-272; positional_encoding.py:196-209)
+#include "kr_common.cuh"
+#include <float.h>
+
+namespace {
+using namespace kr;
+
+constexpr int WARPS = 8;  // warps per block for the row kernels
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st_bf16x4(bf16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16(v.x, v.y);
+  u.y = pack_bf16(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm forward: x f32 [N,D] -> y bf16 [N,D] (+ optional f32 copy), mean/rstd [N]
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, bf16* __restrict__ y,
+                              float* __restrict__ y32, float* __restrict__ mean_out,
+                              float* __restrict__ rstd_out, int N, float eps) {
+  constexpr int D = NV * 128;
+  const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* xr = x + (long long)row * D;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = ld4(xr + i * 128 + lane * 4);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = i * 128 + lane * 4;
+    const float4 g = ld4(gamma + c0), b = ld4(beta + c0);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (y != nullptr) st_bf16x4(y + (long long)row * D + c0, o);
+    if (y32 != nullptr) st4(y32 + (long long)row * D + c0, o);
+  }
+  if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward: dx = dres + rstd*(g*dy - mean(g*dy) - xhat*mean(g*dy*xhat))
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                              const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                              const float* __restrict__ gamma, const float* dres, float* dx,
+                              bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta, int N) {
+  constexpr int D = NV * 128;
+  __shared__ float sm[WARPS][D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 ag[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  for (int row = blockIdx.x * WARPS + warp; row < N; row += gridDim.x * WARPS) {
+    const long long off = (long long)row * D;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float4 xh[NV], g[NV];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = i * 128 + lane * 4;
+      const float4 xv = ld4(x + off + c0), d = ld4(dy + off + c0), gm = ld4(gamma + c0);
+      xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+      g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      c1 += g[i].x + g[i].y + g[i].z + g[i].w;
+      c2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+      ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+      ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+    }
+    c1 = warp_sum(c1) * (1.f / D);
+    c2 = warp_sum(c2) * (1.f / D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = i * 128 + lane * 4;
+      float4 o;
+      o.x = rstd * (g[i].x - c1 - xh[i].x * c2);
+      o.y = rstd * (g[i].y - c1 - xh[i].y * c2);
+      o.z = rstd * (g[i].z - c1 - xh[i].z * c2);
+      o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
+      if (dres != nullptr) {
+        const float4 r = ld4(dres + off + c0);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      st4(dx + off + c0, o);
+      if (dx_bf16 != nullptr) st_bf16x4(dx_bf16 + off + c0, o);
+    }
+  }
+  // column gradients: warps -> smem -> one atomic per column per block
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) st4(&sm[warp][i * 128 + lane * 4], pass == 0 ? ag[i] : ab[i]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) t += sm[w][c];
+      atomicAdd((pass == 0 ? dgamma : dbeta) + c, t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FFN output RMSNorm + residual: out = resid + y * rsqrt(mean(y^2)+eps) * g
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void rms_resid_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gain,
+                                     const float* resid, float* out, int N, float eps) {
+  constexpr int D = NV * 128;
+  const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const long long off = (long long)row * D;
+  float4 v[NV];
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = ld4(y + off + i * 128 + lane * 4);
+    q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = i * 128 + lane * 4;
+    const float4 g = ld4(gain + c0), r = ld4(resid + off + c0);
+    st4(out + off + c0, make_float4(r.x + v[i].x * rstd * g.x, r.y + v[i].y * rstd * g.y,
+                                    r.z + v[i].z * rstd * g.z, r.w + v[i].w * rstd * g.w));
+  }
+}
+
+template <int NV>
+__global__ void rms_resid_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y,
+                                     const float* __restrict__ gain, bf16* __restrict__ dy,
+                                     float* __restrict__ dgain, int N, float eps) {
+  constexpr int D = NV * 128;
+  __shared__ float sm[WARPS][D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 ag[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ag[i] = make_float4(0, 0, 0, 0);
+  for (int row = blockIdx.x * WARPS + warp; row < N; row += gridDim.x * WARPS) {
+    const long long off = (long long)row * D;
+    float4 v[NV], d[NV];
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i] = ld4(y + off + i * 128 + lane * 4);
+      q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+    float c = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = i * 128 + lane * 4;
+      const float4 g = ld4(gain + c0), o = ld4(dout + off + c0);
+      v[i] = make_float4(v[i].x * rstd, v[i].y * rstd, v[i].z * rstd, v[i].w * rstd);  // yhat
+      ag[i].x += o.x * v[i].x; ag[i].y += o.y * v[i].y; ag[i].z += o.z * v[i].z; ag[i].w += o.w * v[i].w;
+      d[i] = make_float4(o.x * g.x, o.y * g.y, o.z * g.z, o.w * g.w);
+      c += d[i].x * v[i].x + d[i].y * v[i].y + d[i].z * v[i].z + d[i].w * v[i].w;
+    }
+    c = warp_sum(c) * (1.f / D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = i * 128 + lane * 4;
+      st_bf16x4(dy + off + c0, make_float4(rstd * (d[i].x - v[i].x * c), rstd * (d[i].y - v[i].y * c),
+                                           rstd * (d[i].z - v[i].z * c), rstd * (d[i].w - v[i].w * c)));
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) st4(&sm[warp][i * 128 + lane * 4], ag[i]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) t += sm[w][c];
+    atomicAdd(dgain + c, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q/K/V head prep: per-head RMSNorm (d_k = 64, learned gain shared by the heads) + optional RoPE.
+// One warp handles one (token, part) = 8 heads x 64 per iteration; 4 lanes per head, 16 elements
+// per lane; the rotate-half partner (i, i+32) lives in lane^2.
+// ---------------------------------------------------------------------------------------------
+struct PrepPart {
+  const void* in;     // raw projection output (bf16) — fwd input / bwd saved input
+  void* out;          // fwd: normalised bf16; bwd: d(raw) bf16
+  const void* grad;   // bwd: incoming gradient (f32 if grad_f32 else bf16)
+  const float* gain;  // [64]
+  float* dgain;       // [64] atomics (bwd)
+  long long ld_in, ld_out, ld_grad;
+  int rope, grad_f32;
+};
+struct PrepParams {
+  PrepPart part[3];
+  int n_parts, N, S, H;
+  const float* cos_t;  // [S_max, 32]
+  const float* sin_t;
+  float eps;
+};
+
+__device__ __forceinline__ void load16_bf16(const bf16* p, float* v) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 8);
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float2 f = unpack_bf16(w[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void store16_bf16(bf16* p, const float* v) {
+  uint4 a, b;
+  a.x = pack_bf16(v[0], v[1]); a.y = pack_bf16(v[2], v[3]); a.z = pack_bf16(v[4], v[5]); a.w = pack_bf16(v[6], v[7]);
+  b.x = pack_bf16(v[8], v[9]); b.y = pack_bf16(v[10], v[11]); b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
+  *reinterpret_cast<uint4*>(p) = a;
+  *reinterpret_cast<uint4*>(p + 8) = b;
+}
+
+// unit = (row, part, head); a warp handles 8 consecutive units per iteration (4 lanes each).
+struct PrepUnit { int row, part, col; bool valid; };
+__device__ __forceinline__ PrepUnit prep_unit(const PrepParams& p, long long w, int lane, long long total) {
+  long long u = w * 8 + (lane >> 2);
+  PrepUnit r;
+  r.valid = u < total;
+  if (!r.valid) u = total - 1;
+  const int head = (int)(u % p.H);
+  const long long t = u / p.H;
+  r.part = (int)(t % p.n_parts);
+  r.row = (int)(t / p.n_parts);
+  r.col = head * 64 + (lane & 3) * 16;
+  return r;
+}
+
+__global__ void qkv_prep_fwd_kernel(const PrepParams p) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 3;                // 16-element slice of the head
+  const long long total = (long long)p.N * p.n_parts * p.H;
+  const long long n_iter = (total + 7) / 8;
+  for (long long w = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); w < n_iter;
+       w += (long long)gridDim.x * WARPS) {
+    const PrepUnit un = prep_unit(p, w, lane, total);
+    const PrepPart& pp = p.part[un.part];
+    float v[16];
+    load16_bf16(reinterpret_cast<const bf16*>(pp.in) + (long long)un.row * pp.ld_in + un.col, v);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) q += v[i] * v[i];
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    const float rstd = rsqrtf(q * (1.f / 64.f) + p.eps);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = v[i] * rstd * __ldg(pp.gain + sub * 16 + i);
+    const int pos = un.row % p.S;
+    const float* ct = p.cos_t + (long long)pos * 32 + (sub & 1) * 16;
+    const float* st = p.sin_t + (long long)pos * 32 + (sub & 1) * 16;
+    const float sgn = (sub < 2) ? -1.f : 1.f;   // rot(x)[i] = -x[i+32] (i<32), +x[i-32] (i>=32)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float other = __shfl_xor_sync(0xffffffffu, v[i], 2);
+      if (pp.rope) v[i] = v[i] * __ldg(ct + i) + sgn * other * __ldg(st + i);
+    }
+    if (un.valid)
+      store16_bf16(reinterpret_cast<bf16*>(pp.out) + (long long)un.row * pp.ld_out + un.col, v);
+  }
+}
+
+__global__ void qkv_prep_bwd_kernel(const PrepParams p) {
+  __shared__ float sm[3][64];
+  for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) (&sm[0][0])[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 3;
+  float dg[3][16];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dg[a][i] = 0.f;
+  const long long total = (long long)p.N * p.n_parts * p.H;
+  const long long n_iter = (total + 7) / 8;
+  for (long long w = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); w < n_iter;
+       w += (long long)gridDim.x * WARPS) {
+    const PrepUnit un = prep_unit(p, w, lane, total);
+    const PrepPart& pp = p.part[un.part];
+    float x[16], g[16];
+    load16_bf16(reinterpret_cast<const bf16*>(pp.in) + (long long)un.row * pp.ld_in + un.col, x);
+    if (pp.grad_f32) {
+      const float* gp = reinterpret_cast<const float*>(pp.grad) + (long long)un.row * pp.ld_grad + un.col;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 f = ld4(gp + 4 * i);
+        g[4 * i] = f.x; g[4 * i + 1] = f.y; g[4 * i + 2] = f.z; g[4 * i + 3] = f.w;
+      }
+    } else {
+      load16_bf16(reinterpret_cast<const bf16*>(pp.grad) + (long long)un.row * pp.ld_grad + un.col, g);
+    }
+    {  // transpose of the rotation: dz[i] = dy[i] cos_i + (i<32 ? +dy[i+32] : -dy[i-32]) sin_i
+      const int pos = un.row % p.S;
+      const float* ct = p.cos_t + (long long)pos * 32 + (sub & 1) * 16;
+      const float* st = p.sin_t + (long long)pos * 32 + (sub & 1) * 16;
+      const float sgn = (sub < 2) ? 1.f : -1.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float other = __shfl_xor_sync(0xffffffffu, g[i], 2);
+        if (pp.rope) g[i] = g[i] * __ldg(ct + i) + sgn * other * __ldg(st + i);
+      }
+    }
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) q += x[i] * x[i];
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    const float rstd = rsqrtf(q * (1.f / 64.f) + p.eps);
+    float c = 0.f;
+    const float vf = un.valid ? 1.f : 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float xh = x[i] * rstd;
+      const float dgi = g[i] * xh * vf;                // d gain
+      dg[0][i] += (un.part == 0) ? dgi : 0.f;
+      dg[1][i] += (un.part == 1) ? dgi : 0.f;
+      dg[2][i] += (un.part == 2) ? dgi : 0.f;
+      g[i] *= __ldg(pp.gain + sub * 16 + i);           // d xhat
+      c += g[i] * xh;
+      x[i] = xh;
+    }
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c *= (1.f / 64.f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) g[i] = rstd * (g[i] - x[i] * c);
+    if (un.valid)
+      store16_bf16(reinterpret_cast<bf16*>(pp.out) + (long long)un.row * pp.ld_out + un.col, g);
+  }
+  // lanes with equal `sub` hold the same 16 gain slots: fold across the 8 units, then block, then global
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float t = dg[a][i];
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 8);
+      t += __shfl_xor_sync(0xffffffffu, t, 16);
+      if (lane < 4 && a < p.n_parts) atomicAdd(&sm[a][sub * 16 + i], t);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.n_parts * 64; i += blockDim.x) {
+    const int part = i / 64;
+    if (p.part[part].dgain != nullptr) atomicAdd(p.part[part].dgain + (i & 63), sm[part][i & 63]);
+  }
+}
+
+int row_blocks(int N) { return (N + WARPS - 1) / WARPS; }
+int persistent_blocks(int N) { return min(row_blocks(N), kNumSMs * 4); }
+
+}  // namespace
+
+#define DISPATCH_NV(D, CALL)                                          \
+  switch (D) {                                                        \
+    case 128: { constexpr int NV = 1; CALL; break; }                  \
+    case 256: { constexpr int NV = 2; CALL; break; }                  \
+    case 512: { constexpr int NV = 4; CALL; break; }                  \
+    default: kr_set_error("hidden dim must be 128, 256 or 512"); return KR_ERR_UNSUPPORTED; \
+  }
+
+extern "C" int kr_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                                float* y_f32, float* mean, float* rstd, int N, int D, float eps,
+                                void* stream) {
+  if (N <= 0) return KR_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_NV(D, (ln_fwd_kernel<NV><<<row_blocks(N), WARPS * 32, 0, st>>>(
+                     x, gamma, beta, reinterpret_cast<bf16*>(y_bf16), y_f32, mean, rstd, N, eps)));
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+extern "C" int kr_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                                const float* gamma, const float* dres, float* dx, void* dx_bf16,
+                                float* dgamma, float* dbeta, int N, int D, void* stream) {
+  if (N <= 0) return KR_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_NV(D, (ln_bwd_kernel<NV><<<persistent_blocks(N), WARPS * 32, 0, st>>>(
+                     dy, x, mean, rstd, gamma, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dgamma,
+                     dbeta, N)));
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+extern "C" int kr_rmsnorm_resid_fwd(const float* y, const float* gain, const float* resid, float* out,
+                                    int N, int D, void* stream) {
+  if (N <= 0) return KR_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_NV(D, (rms_resid_fwd_kernel<NV><<<row_blocks(N), WARPS * 32, 0, st>>>(y, gain, resid, out, N,
+                                                                                FLT_EPSILON)));
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+extern "C" int kr_rmsnorm_resid_bwd(const float* dout, const float* y, const float* gain, void* dy_bf16,
+                                    float* dgain, int N, int D, void* stream) {
+  if (N <= 0) return KR_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_NV(D, (rms_resid_bwd_kernel<NV><<<persistent_blocks(N), WARPS * 32, 0, st>>>(
+                     dout, y, gain, reinterpret_cast<bf16*>(dy_bf16), dgain, N, FLT_EPSILON)));
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+// parts: up to 3 column blocks of H*64 each (e.g. q|k|v of one fused projection output).
+// in/out/grad pointers and leading dimensions per part; rope_mask bit i = apply RoPE to part i;
+// grad_f32_mask bit i = incoming gradient of part i is fp32 (else bf16).  Position = row % S.
+extern "C" int kr_qkv_prep_fwd(const void* in0, const void* in1, const void* in2, void* out0, void* out1,
+                               void* out2, long long ld_in, long long ld_out, const float* gain0,
+                               const float* gain1, const float* gain2, int n_parts, int rope_mask,
+                               const float* cos_t, const float* sin_t, int N, int S, int H,
+                               void* stream) {
+  if (N <= 0) return KR_OK;
+  PrepParams p{};
+  const void* ins[3] = {in0, in1, in2};
+  void* outs[3] = {out0, out1, out2};
+  const float* gains[3] = {gain0, gain1, gain2};
+  for (int i = 0; i < n_parts; ++i) {
+    p.part[i].in = ins[i]; p.part[i].out = outs[i]; p.part[i].gain = gains[i];
+    p.part[i].ld_in = ld_in; p.part[i].ld_out = ld_out; p.part[i].rope = (rope_mask >> i) & 1;
+  }
+  p.n_parts = n_parts; p.N = N; p.S = S; p.H = H; p.cos_t = cos_t; p.sin_t = sin_t; p.eps = FLT_EPSILON;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = ((long long)N * n_parts * H + 7) / 8;
+  const long long nb_ = (total + WARPS - 1) / WARPS;
+  const int blocks = (int)(nb_ < kNumSMs * 8 ? nb_ : kNumSMs * 8);
+  qkv_prep_fwd_kernel<<<blocks, WARPS * 32, 0, st>>>(p);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+extern "C" int kr_qkv_prep_bwd(const void* in0, const void* in1, const void* in2, const void* grad0,
+                               const void* grad1, const void* grad2, long long ld_grad0,
+                               long long ld_grad1, long long ld_grad2, void* out0, void* out1, void* out2,
+                               long long ld_in, long long ld_out, const float* gain0, const float* gain1,
+                               const float* gain2, float* dgain0, float* dgain1, float* dgain2,
+                               int n_parts, int rope_mask, int grad_f32_mask, const float* cos_t,
+                               const float* sin_t, int N, int S, int H, void* stream) {
+  if (N <= 0) return KR_OK;
+  PrepParams p{};
+  const void* ins[3] = {in0, in1, in2};
+  const void* grads[3] = {grad0, grad1, grad2};
+  const long long ldg[3] = {ld_grad0, ld_grad1, ld_grad2};
+  void* outs[3] = {out0, out1, out2};
+  const float* gains[3] = {gain0, gain1, gain2};
+  float* dgains[3] = {dgain0, dgain1, dgain2};
+  for (int i = 0; i < n_parts; ++i) {
+    p.part[i].in = ins[i]; p.part[i].out = outs[i]; p.part[i].grad = grads[i]; p.part[i].gain = gains[i];
+    p.part[i].dgain = dgains[i]; p.part[i].ld_in = ld_in; p.part[i].ld_out = ld_out;
+    p.part[i].ld_grad = ldg[i]; p.part[i].rope = (rope_mask >> i) & 1;
+    p.part[i].grad_f32 = (grad_f32_mask >> i) & 1;
+  }
+  p.n_parts = n_parts; p.N = N; p.S = S; p.H = H; p.cos_t = cos_t; p.sin_t = sin_t; p.eps = FLT_EPSILON;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = ((long long)N * n_parts * H + 7) / 8;
+  const long long nb_ = (total + WARPS - 1) / WARPS;
+  const int blocks = (int)(nb_ < kNumSMs * 4 ? nb_ : kNumSMs * 4);
+  qkv_prep_bwd_kernel<<<blocks, WARPS * 32, 0, st>>>(p);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}

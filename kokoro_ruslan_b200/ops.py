@@ -84,3 +84,40 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major: boo
                             _stream())
     check(rc, "kr_gemm_bf16")
     return out
+
+
+def _heads_strides(t: torch.Tensor):
+    """t is a [B, S, H, 64] bf16 view with unit inner stride and head stride 64."""
+    assert t.dtype == torch.bfloat16 and t.dim() == 4 and t.shape[3] == 64
+    assert t.stride(3) == 1 and t.stride(2) == 64, t.stride()
+    return c_ll(t.stride(1)), c_ll(t.stride(0))
+
+
+def attn_fwd(q, k, v, o, lse, key_mask: Optional[torch.Tensor], causal: bool, scale: float):
+    """Flash attention forward (tcgen05).  q,o: [B,Sq,H,64]; k,v: [B,Sk,H,64]; lse: [B,H,Sq] f32
+    (log2 domain); key_mask: [B,Sk] uint8 (1 = masked) or None."""
+    B, Sq, H, _ = q.shape
+    Sk = k.shape[1]
+    if key_mask is not None:
+        assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.shape == (B, Sk)
+    assert lse.dtype == torch.float32 and lse.is_contiguous()
+    rc = lib().kr_attn_fwd(_ptr(q), *_heads_strides(q), _ptr(k), *_heads_strides(k), _ptr(v),
+                           *_heads_strides(v), _ptr(o), *_heads_strides(o), _ptr(lse),
+                           _ptr(key_mask), c_int(B), c_int(H), c_int(Sq), c_int(Sk),
+                           c_int(int(causal)), c_float(scale), _stream())
+    check(rc, "kr_attn_fwd")
+
+
+def attn_bwd(q, k, v, o, d_o, lse, delta, dq, dk, dv, key_mask, causal: bool, scale: float):
+    """Flash attention backward.  dq: fp32 [B,Sq,H,64] and must be ZEROED by the caller (atomic
+    accumulation); dk, dv: bf16 [B,Sk,H,64]; delta: fp32 scratch [B,H,Sq]."""
+    B, Sq, H, _ = q.shape
+    Sk = k.shape[1]
+    assert dq.dtype == torch.float32 and dq.stride(3) == 1 and dq.stride(2) == 64
+    rc = lib().kr_attn_bwd(_ptr(q), *_heads_strides(q), _ptr(k), *_heads_strides(k), _ptr(v),
+                           *_heads_strides(v), _ptr(o), *_heads_strides(o), _ptr(d_o),
+                           *_heads_strides(d_o), _ptr(lse), _ptr(delta), _ptr(dq),
+                           c_ll(dq.stride(1)), c_ll(dq.stride(0)), _ptr(dk), *_heads_strides(dk),
+                           _ptr(dv), *_heads_strides(dv), _ptr(key_mask), c_int(B), c_int(H),
+                           c_int(Sq), c_int(Sk), c_int(int(causal)), c_float(scale), _stream())
+    check(rc, "kr_attn_bwd")
