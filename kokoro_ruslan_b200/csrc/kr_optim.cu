@@ -1,0 +1,269 @@
+// kr_optim.cu — optimizer step over the flat fp32 parameter / gradient buffers (HBM-bound; one pass
+// reads p,g,m,v,ema and writes p,m,v,ema + the bf16 GEMM shadow: 9 streams).
+//   reference semantics reproduced, in order (SURVEY.md §8 "Step algorithm" 4-5):
+//     per-tensor spike pre-clip  (training/trainer.py:1332-1407, scale = thr/(norm+1e-12))
+//     total grad norm + explosion detector (trainer.py:1315-1330, 2355-2405: threshold =
+//       max(floor, 3*EMA_0.95) once the EMA has 100 steps, floor decays 8000->1000 over 400
+//       steps; exploding => clip = min(clip, 0.3)); non-finite gradients skip the step (:2407-2463)
+//     clip_grad_norm_ (coef = min(1, clip/(norm+1e-6)))  (training/runtime_policies.py:33-79)
+//     AdamW, per-group lr / weight decay (trainer.py:446-689), bias-corrected, eps 1e-8
+//     EMA of the weights (trainer.py:1491-1517)
+//     post-step FFN weight-norm projection ||W||_2 <= 95 (trainer.py:883-912)
+// Everything stays on the device: the step-control block below replaces ~1.2k host syncs.
+#include "kr_common.cuh"
+
+namespace {
+using namespace kr;
+
+constexpr int CHUNK = 4096;  // elements per block; chunks never straddle tensors
+
+struct Ctrl {           // device-resident optimizer control block (mirrored layout in optim.py)
+  float total_norm;     // 0  post-preclip total gradient norm
+  float clip_coef;      // 1
+  int skip;             // 2  1 => non-finite gradients, step skipped
+  int step;             // 3  successful optimizer steps (bias correction exponent)
+  float bc1;            // 4
+  float bc2_sqrt;       // 5
+  float ema_norm;       // 6  explosion-detector EMA of the grad norm
+  int ema_steps;        // 7
+  int exploding;        // 8
+  float threshold;      // 9
+  int nonfinite;        // 10 set by the norm kernel
+  float clip_used;      // 11
+  int skipped_total;    // 12
+  int reserved[3];
+};
+
+__global__ void sqnorm_kernel(const float* __restrict__ g, const int* __restrict__ chunk_tensor,
+                              const long long* __restrict__ chunk_start, const int* __restrict__ chunk_len,
+                              float* __restrict__ sq, Ctrl* ctrl) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const float* p = g + chunk_start[c];
+  const int n = chunk_len[c];
+  float s = 0.f;
+  for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(p + i);
+      s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    } else {
+      for (int k = i; k < n; ++k) s += p[k] * p[k];
+    }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    if (!isfinite(s)) atomicExch(&ctrl->nonfinite, 1);
+    atomicAdd(sq + chunk_tensor[c], s);
+  }
+}
+
+struct CtrlCfg {
+  float clip_norm;         // adaptive clip for this step (host: 1.5 or the long-sequence value)
+  float beta1, beta2;
+  float abs_floor, warmup_floor;   // 1000, 8000
+  int warmup_steps;                // 400
+  float ema_alpha, multiplier;     // 0.95, 3.0
+  int min_ema_steps;               // 100
+  float emergency_clip;            // 0.3
+};
+
+__global__ void step_control_kernel(const float* __restrict__ sq, const float* __restrict__ preclip,
+                                    float* __restrict__ tscale, int n_tensors, Ctrl* ctrl,
+                                    const CtrlCfg cfg, const float* clip_override) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int t = threadIdx.x; t < n_tensors; t += blockDim.x) {
+    const float nrm = sqrtf(sq[t]);
+    float sc = 1.f;
+    const float thr = preclip[t];
+    if (thr > 0.f && isfinite(nrm) && nrm > thr) sc = thr / (nrm + 1e-12f);
+    tscale[t] = sc;
+    s += (nrm * sc) * (nrm * sc);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const float total = sqrtf(s);
+    const bool bad = ctrl->nonfinite != 0 || !isfinite(total);
+    float clip = clip_override != nullptr ? *clip_override : cfg.clip_norm;
+    // explosion threshold
+    float floor_ = cfg.abs_floor;
+    if (cfg.warmup_steps > 0 && ctrl->step < cfg.warmup_steps) {
+      const float prog = (float)ctrl->step / (float)cfg.warmup_steps;
+      floor_ = cfg.warmup_floor - (cfg.warmup_floor - cfg.abs_floor) * prog;
+    }
+    const bool ema_ready = ctrl->ema_steps >= cfg.min_ema_steps;
+    const float ema_thr = ctrl->ema_steps > 0 ? ctrl->ema_norm * cfg.multiplier : 0.f;
+    const float thr = ema_ready ? fmaxf(floor_, ema_thr) : floor_;
+    const bool exploding = !bad && total > thr;
+    if (exploding) clip = fminf(clip, cfg.emergency_clip);
+    if (!bad) {
+      ctrl->ema_norm = ctrl->ema_steps == 0 ? total : cfg.ema_alpha * ctrl->ema_norm + (1.f - cfg.ema_alpha) * total;
+      ctrl->ema_steps += 1;
+    }
+    ctrl->total_norm = total;
+    ctrl->threshold = thr;
+    ctrl->exploding = exploding ? 1 : 0;
+    ctrl->clip_used = clip;
+    ctrl->clip_coef = bad ? 0.f : fminf(1.f, clip / (total + 1e-6f));
+    ctrl->skip = bad ? 1 : 0;
+    if (bad) {
+      ctrl->skipped_total += 1;
+    } else {
+      ctrl->step += 1;
+      ctrl->bc1 = 1.f - powf(cfg.beta1, (float)ctrl->step);
+      ctrl->bc2_sqrt = sqrtf(1.f - powf(cfg.beta2, (float)ctrl->step));
+    }
+    ctrl->nonfinite = 0;
+  }
+}
+
+struct AdamParams {
+  float* p; const float* g; float* m; float* v; float* ema; bf16* shadow;
+  const int* chunk_tensor; const long long* chunk_start; const int* chunk_len;
+  const int* t_group; const float* tscale; const float* g_lr; const float* g_wd;
+  const float* t_wnmax; float* wsq;
+  const Ctrl* ctrl;
+  float beta1, beta2, eps, ema_decay;
+};
+
+__global__ void adamw_kernel(const AdamParams a) {
+  __shared__ float red[32];
+  if (a.ctrl->skip) return;
+  const int c = blockIdx.x;
+  const int t = a.chunk_tensor[c];
+  const long long off = a.chunk_start[c];
+  const int n = a.chunk_len[c];
+  const int grp = a.t_group[t];
+  const float lr = a.g_lr[grp], wd = a.g_wd[grp];
+  const float gs = a.tscale[t] * a.ctrl->clip_coef;
+  const float step_size = lr / a.ctrl->bc1;
+  const float inv_bc2 = 1.f / a.ctrl->bc2_sqrt;
+  const float decay = 1.f - lr * wd;
+  const bool want_wsq = a.t_wnmax[t] > 0.f;
+  float wacc = 0.f;
+  for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) {
+    float pv[4], gv[4], mv[4], vv[4], ev[4] = {0, 0, 0, 0};
+    const int cnt = min(4, n - i);
+    if (cnt == 4) {
+      const float4 P = *reinterpret_cast<const float4*>(a.p + off + i), G = *reinterpret_cast<const float4*>(a.g + off + i);
+      const float4 M = *reinterpret_cast<const float4*>(a.m + off + i), V = *reinterpret_cast<const float4*>(a.v + off + i);
+      pv[0] = P.x; pv[1] = P.y; pv[2] = P.z; pv[3] = P.w; gv[0] = G.x; gv[1] = G.y; gv[2] = G.z; gv[3] = G.w;
+      mv[0] = M.x; mv[1] = M.y; mv[2] = M.z; mv[3] = M.w; vv[0] = V.x; vv[1] = V.y; vv[2] = V.z; vv[3] = V.w;
+      if (a.ema != nullptr) {
+        const float4 E = *reinterpret_cast<const float4*>(a.ema + off + i);
+        ev[0] = E.x; ev[1] = E.y; ev[2] = E.z; ev[3] = E.w;
+      }
+    } else {
+      for (int k = 0; k < cnt; ++k) {
+        pv[k] = a.p[off + i + k]; gv[k] = a.g[off + i + k]; mv[k] = a.m[off + i + k]; vv[k] = a.v[off + i + k];
+        if (a.ema != nullptr) ev[k] = a.ema[off + i + k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < cnt) {
+        const float g = gv[k] * gs;
+        mv[k] = a.beta1 * mv[k] + (1.f - a.beta1) * g;
+        vv[k] = a.beta2 * vv[k] + (1.f - a.beta2) * g * g;
+        const float denom = sqrtf(vv[k]) * inv_bc2 + a.eps;
+        pv[k] = pv[k] * decay - step_size * (mv[k] / denom);
+        ev[k] = a.ema_decay * ev[k] + (1.f - a.ema_decay) * pv[k];
+        wacc += pv[k] * pv[k];
+      }
+    }
+    if (cnt == 4) {
+      *reinterpret_cast<float4*>(a.p + off + i) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      *reinterpret_cast<float4*>(a.m + off + i) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+      *reinterpret_cast<float4*>(a.v + off + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      if (a.ema != nullptr) *reinterpret_cast<float4*>(a.ema + off + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+      uint2 u; u.x = pack_bf16(pv[0], pv[1]); u.y = pack_bf16(pv[2], pv[3]);
+      *reinterpret_cast<uint2*>(a.shadow + off + i) = u;
+    } else {
+      for (int k = 0; k < cnt; ++k) {
+        a.p[off + i + k] = pv[k]; a.m[off + i + k] = mv[k]; a.v[off + i + k] = vv[k];
+        if (a.ema != nullptr) a.ema[off + i + k] = ev[k];
+        a.shadow[off + i + k] = __float2bfloat16(pv[k]);
+      }
+    }
+  }
+  if (want_wsq) {
+    wacc = block_sum(wacc, red);
+    if (threadIdx.x == 0) atomicAdd(a.wsq + t, wacc);
+  }
+}
+
+__global__ void wn_project_kernel(float* __restrict__ p, bf16* __restrict__ shadow,
+                                  const int* __restrict__ chunk_ids, const int* __restrict__ chunk_tensor,
+                                  const long long* __restrict__ chunk_start, const int* __restrict__ chunk_len,
+                                  const float* __restrict__ t_wnmax, const float* __restrict__ wsq,
+                                  const Ctrl* ctrl) {
+  if (ctrl->skip) return;
+  const int c = chunk_ids[blockIdx.x];
+  const int t = chunk_tensor[c];
+  const float nrm = sqrtf(wsq[t]), mx = t_wnmax[t];
+  if (!(nrm > mx)) return;
+  const float sc = mx / nrm;
+  const long long off = chunk_start[c];
+  const int n = chunk_len[c];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = p[off + i] * sc;
+    p[off + i] = v;
+    shadow[off + i] = __float2bfloat16(v);
+  }
+}
+
+}  // namespace
+
+extern "C" int kr_optim_ctrl_size(void) { return (int)sizeof(Ctrl); }
+
+// Phase 1: per-tensor squared gradient norms (sq must be zeroed by the caller) + non-finite flag.
+extern "C" int kr_grad_sqnorm(const float* grads, const int* chunk_tensor, const long long* chunk_start,
+                              const int* chunk_len, int n_chunks, float* sq, void* ctrl, void* stream) {
+  if (n_chunks <= 0) return KR_OK;
+  sqnorm_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(grads, chunk_tensor, chunk_start, chunk_len, sq, (Ctrl*)ctrl);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+// Phase 2: per-tensor pre-clip scales, total norm, explosion detector, clip coefficient, step count.
+extern "C" int kr_step_control(const float* sq, const float* preclip, float* tscale, int n_tensors,
+                               void* ctrl, float clip_norm, const float* clip_override, float beta1,
+                               float beta2, float abs_floor, float warmup_floor, int warmup_steps,
+                               float ema_alpha, float multiplier, int min_ema_steps,
+                               float emergency_clip, void* stream) {
+  CtrlCfg cfg;
+  cfg.clip_norm = clip_norm; cfg.beta1 = beta1; cfg.beta2 = beta2; cfg.abs_floor = abs_floor;
+  cfg.warmup_floor = warmup_floor; cfg.warmup_steps = warmup_steps; cfg.ema_alpha = ema_alpha;
+  cfg.multiplier = multiplier; cfg.min_ema_steps = min_ema_steps; cfg.emergency_clip = emergency_clip;
+  step_control_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sq, preclip, tscale, n_tensors, (Ctrl*)ctrl, cfg, clip_override);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+// Phase 3: fused clip + AdamW + EMA + bf16 shadow (+ squared weight norms of the projected tensors;
+// wsq must be zeroed by the caller).
+extern "C" int kr_adamw_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow,
+                             const int* chunk_tensor, const long long* chunk_start, const int* chunk_len,
+                             int n_chunks, const int* t_group, const float* tscale, const float* g_lr,
+                             const float* g_wd, const float* t_wnmax, float* wsq, const void* ctrl,
+                             float beta1, float beta2, float eps, float ema_decay, void* stream) {
+  if (n_chunks <= 0) return KR_OK;
+  AdamParams a;
+  a.p = p; a.g = g; a.m = m; a.v = v; a.ema = ema; a.shadow = (bf16*)shadow;
+  a.chunk_tensor = chunk_tensor; a.chunk_start = chunk_start; a.chunk_len = chunk_len;
+  a.t_group = t_group; a.tscale = tscale; a.g_lr = g_lr; a.g_wd = g_wd; a.t_wnmax = t_wnmax; a.wsq = wsq;
+  a.ctrl = (const Ctrl*)ctrl; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.ema_decay = ema_decay;
+  adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(a);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+// Phase 4: scale the flagged tensors whose updated norm exceeds their limit.
+extern "C" int kr_wn_project(float* p, void* shadow, const int* wn_chunk_ids, int n_wn_chunks,
+                             const int* chunk_tensor, const long long* chunk_start, const int* chunk_len,
+                             const float* t_wnmax, const float* wsq, const void* ctrl, void* stream) {
+  if (n_wn_chunks <= 0) return KR_OK;
+  wn_project_kernel<<<n_wn_chunks, 256, 0, (cudaStream_t)stream>>>(p, (bf16*)shadow, wn_chunk_ids, chunk_tensor, chunk_start, chunk_len, t_wnmax, wsq, (const Ctrl*)ctrl);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}

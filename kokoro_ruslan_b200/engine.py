@@ -1,0 +1,474 @@
+"""Acoustic-model training forward / backward as a sequence of libkokoro_b200 kernel launches.
+
+Mirrors the data flow of the reference ``KokoroModel.forward_training``
+(src/kokoro/model/model.py:565-673 and SURVEY.md §9 S1-S9): embedding -> 6 pre-norm encoder
+blocks -> variance adaptor (duration predictor, detached length regulation, pitch/energy
+predictors and embeddings) -> teacher-forced 6-block decoder -> mel / stop heads; then the fused
+losses and a hand-scheduled backward over the four disjoint sub-graphs the reference's two
+``detach()`` cuts create.  Host code only allocates tensors and orders launches; all arithmetic is
+in the CUDA library (tcgen05 GEMM / flash attention + HBM kernels).  Dropout / stochastic depth
+are not applied (p = 0, the parity configuration).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .params import ModelConfig, ParamStore
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+@dataclass
+class LossConfig:
+    """Loss weights / criteria constants (reference training/config.py:133-141, trainer.py:410-444)."""
+    w_dur: float = 0.35
+    w_stop: float = 0.010
+    w_pitch: float = 1.0
+    w_energy: float = 1.0
+    stop_pos_weight: float = 17.0
+    huber_delta_var: float = 0.05
+
+
+class PadGeom:
+    """Row tables of the predictor 'padded layout' for B sequences of length L split into
+    independent chunks (reference model/variance_predictor.py:77-87): every chunk is surrounded by
+    one zero row on each side (= the conv's zero padding)."""
+
+    def __init__(self, B: int, L: int, chunk: int, device):
+        self.B, self.L, self.chunk = B, L, chunk
+        row_group: List[int] = []
+        tok_of_row: List[int] = []
+        row_of_tok = [0] * (B * L)
+        group_rows: List[int] = []
+        for b in range(B):
+            for s in range(0, L, chunk):
+                n = min(chunk, L - s)
+                gid = len(group_rows)
+                group_rows.append(n)
+                row_group.append(-1)
+                tok_of_row.append(-1)
+                for t in range(s, s + n):
+                    row_of_tok[b * L + t] = len(row_group)
+                    row_group.append(gid)
+                    tok_of_row.append(b * L + t)
+                row_group.append(-1)
+                tok_of_row.append(-1)
+        self.R = len(row_group)
+        self.G = len(group_rows)
+        i32 = dict(dtype=torch.int32, device=device)
+        self.row_group = torch.tensor(row_group, **i32)
+        self.tok_of_row = torch.tensor(tok_of_row, **i32)
+        self.row_of_tok = torch.tensor(row_of_tok, **i32)
+        self.group_rows = torch.tensor(group_rows, **i32)
+
+
+def _auto_splits(tiles: int, k_blocks: int, target: int = 296) -> int:
+    return max(1, min(k_blocks, (target + tiles - 1) // tiles))
+
+
+class AcousticEngine:
+    def __init__(self, cfg: ModelConfig, device=None, with_ema: bool = True,
+                 loss_cfg: Optional[LossConfig] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("AcousticEngine needs a CUDA device: the hot path has no CPU fallback")
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else "cuda")
+        self.loss_cfg = loss_cfg or LossConfig()
+        self.store = ParamStore(cfg, self.device, with_ema=with_ema)
+        self.H = cfg.n_heads
+        self.D = cfg.hidden_dim
+        assert self.D == self.H * 64, "head_dim must be 64 (tcgen05 attention tiles)"
+        self._geoms: Dict[Tuple[int, int], PadGeom] = {}
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _geom(self, B: int, L: int) -> PadGeom:
+        key = (B, L)
+        if key not in self._geoms:
+            self._geoms[key] = PadGeom(B, L, self.cfg.vp_chunk, self.device)
+        return self._geoms[key]
+
+    def _empty(self, *shape, dtype=F32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def _zeros(self, *shape, dtype=F32):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------------------------------
+    # linear helpers
+    # ------------------------------------------------------------------------------------------
+    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, gw: torch.Tensor):
+        """gw[N_out, K_in] += dy[tok, N_out]^T x[tok, K_in] (split-K, fp32 atomics)."""
+        n_out, k_in = gw.shape
+        tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128)
+        kb = (dy.shape[0] + 63) // 64
+        ops.gemm(dy, x, gw, a_mn_major=True, b_mn_major=True, accumulate=True,
+                 splits=_auto_splits(tiles, kb))
+
+    # ------------------------------------------------------------------------------------------
+    # attention sub-layer
+    # ------------------------------------------------------------------------------------------
+    def _attn_fwd(self, pre: str, x: torch.Tensor, B: int, S: int, norm: str, causal: bool,
+                  key_mask: Optional[torch.Tensor], mem: Optional[torch.Tensor], Sk: int, sv: dict):
+        st, D, H = self.store, self.D, self.H
+        N = B * S
+        cross = mem is not None
+        h = self._empty(N, D, dtype=BF16)
+        mean, rstd = self._empty(N), self._empty(N)
+        ops.layernorm_fwd(x, st.p(norm + "weight"), st.p(norm + "bias"), h, None, mean, rstd)
+        gq, gk, gv = st.p(pre + "q_norm.weight"), st.p(pre + "k_norm.weight"), st.p(pre + "v_norm.weight")
+        if not cross:
+            raw = self._empty(N, 3 * D, dtype=BF16)
+            ops.gemm(h, st.span(st.shadow, pre + "w_q.weight", 3 * D, D), raw)
+            nrm = self._empty(N, 3 * D, dtype=BF16)
+            parts_in = [raw[:, :D], raw[:, D:2 * D], raw[:, 2 * D:]]
+            parts_out = [nrm[:, :D], nrm[:, D:2 * D], nrm[:, 2 * D:]]
+            ops.qkv_prep_fwd(parts_in, parts_out, [gq, gk, gv], 0b011, st.rope_cos, st.rope_sin, N, S, H)
+            q, k, v = (t.view(B, S, H, 64) for t in parts_out)
+            sv.update(raw=raw, nrm=nrm)
+        else:
+            Nk = B * Sk
+            raw_q = self._empty(N, D, dtype=BF16)
+            ops.gemm(h, st.w(pre + "w_q.weight"), raw_q)
+            raw_kv = self._empty(Nk, 2 * D, dtype=BF16)
+            ops.gemm(mem, st.span(st.shadow, pre + "w_k.weight", 2 * D, D), raw_kv)
+            nq = self._empty(N, D, dtype=BF16)
+            nkv = self._empty(Nk, 2 * D, dtype=BF16)
+            ops.qkv_prep_fwd([raw_q], [nq], [gq], 0, st.rope_cos, st.rope_sin, N, S, H)
+            ops.qkv_prep_fwd([raw_kv[:, :D], raw_kv[:, D:]], [nkv[:, :D], nkv[:, D:]], [gk, gv], 0,
+                             st.rope_cos, st.rope_sin, Nk, Sk, H)
+            q = nq.view(B, S, H, 64)
+            k, v = nkv[:, :D].view(B, Sk, H, 64), nkv[:, D:].view(B, Sk, H, 64)
+            sv.update(raw_q=raw_q, raw_kv=raw_kv, nq=nq, nkv=nkv)
+        o = self._empty(N, D, dtype=BF16)
+        lse = self._empty(B, H, S)
+        ops.attn_fwd(q, k, v, o.view(B, S, H, 64), lse, key_mask, causal, 1.0 / 8.0)
+        out = self._empty(N, D)
+        ops.gemm(o, st.w(pre + "w_o.weight"), out, bias=st.p(pre + "w_o.bias"), resid=x)
+        sv.update(x=x, h=h, mean=mean, rstd=rstd, o=o, lse=lse, q=q, k=k, v=v)
+        return out
+
+    def _attn_bwd(self, pre: str, dout: torch.Tensor, dout_bf: torch.Tensor, B: int, S: int, norm: str,
+                  causal: bool, key_mask, mem, Sk: int, sv: dict, dmem: Optional[torch.Tensor],
+                  dmem_first: bool):
+        st, D, H = self.store, self.D, self.H
+        N = B * S
+        cross = mem is not None
+        self._wgrad(dout_bf, sv["o"], st.g(pre + "w_o.weight"))
+        ops.colsum_bf16(dout_bf, st.g(pre + "w_o.bias"))
+        d_o = self._empty(N, D, dtype=BF16)
+        ops.gemm(dout_bf, st.w(pre + "w_o.weight"), d_o, b_mn_major=True)
+        dq = self._zeros(N, D)
+        Nk = B * Sk
+        dkv = self._empty(Nk, 2 * D, dtype=BF16)
+        delta = self._empty(B, H, S)
+        ops.attn_bwd(sv["q"], sv["k"], sv["v"], sv["o"].view(B, S, H, 64), d_o.view(B, S, H, 64), sv["lse"],
+                     delta, dq.view(B, S, H, 64), dkv[:, :D].view(B, Sk, H, 64), dkv[:, D:].view(B, Sk, H, 64),
+                     key_mask, causal, 1.0 / 8.0)
+        gq, gk, gv = st.p(pre + "q_norm.weight"), st.p(pre + "k_norm.weight"), st.p(pre + "v_norm.weight")
+        dgq, dgk, dgv = st.g(pre + "q_norm.weight"), st.g(pre + "k_norm.weight"), st.g(pre + "v_norm.weight")
+        dh = self._empty(N, D)
+        if not cross:
+            raw = sv["raw"]
+            draw = self._empty(N, 3 * D, dtype=BF16)
+            ops.qkv_prep_bwd([raw[:, :D], raw[:, D:2 * D], raw[:, 2 * D:]], [dq, dkv[:, :D], dkv[:, D:]],
+                             [draw[:, :D], draw[:, D:2 * D], draw[:, 2 * D:]], [gq, gk, gv], [dgq, dgk, dgv],
+                             0b011, st.rope_cos, st.rope_sin, N, S, H)
+            self._wgrad(draw, sv["h"], st.span(st.grads, pre + "w_q.weight", 3 * D, D))
+            ops.gemm(draw, st.span(st.shadow, pre + "w_q.weight", 3 * D, D), dh, b_mn_major=True)
+        else:
+            dq_raw = self._empty(N, D, dtype=BF16)
+            ops.qkv_prep_bwd([sv["raw_q"]], [dq], [dq_raw], [gq], [dgq], 0, st.rope_cos, st.rope_sin, N, S, H)
+            raw_kv = sv["raw_kv"]
+            dkv_raw = self._empty(Nk, 2 * D, dtype=BF16)
+            ops.qkv_prep_bwd([raw_kv[:, :D], raw_kv[:, D:]], [dkv[:, :D], dkv[:, D:]],
+                             [dkv_raw[:, :D], dkv_raw[:, D:]], [gk, gv], [dgk, dgv], 0, st.rope_cos,
+                             st.rope_sin, Nk, Sk, H)
+            self._wgrad(dq_raw, sv["h"], st.g(pre + "w_q.weight"))
+            self._wgrad(dkv_raw, mem, st.span(st.grads, pre + "w_k.weight", 2 * D, D))
+            ops.gemm(dq_raw, st.w(pre + "w_q.weight"), dh, b_mn_major=True)
+            ops.gemm(dkv_raw, st.span(st.shadow, pre + "w_k.weight", 2 * D, D), dmem, b_mn_major=True,
+                     resid=None if dmem_first else dmem)
+        dx = self._empty(N, D)
+        dx_bf = self._empty(N, D, dtype=BF16)
+        ops.layernorm_bwd(dh, sv["x"], sv["mean"], sv["rstd"], st.p(norm + "weight"), dout, dx, dx_bf,
+                          st.g(norm + "weight"), st.g(norm + "bias"))
+        return dx, dx_bf
+
+    # ------------------------------------------------------------------------------------------
+    # GLU feed-forward sub-layer
+    # ------------------------------------------------------------------------------------------
+    def _ffn_fwd(self, pre: str, x: torch.Tensor, norm: str, ff: int, sv: dict):
+        st, D = self.store, self.D
+        N = x.shape[0]
+        h = self._empty(N, D, dtype=BF16)
+        mean, rstd = self._empty(N), self._empty(N)
+        ops.layernorm_fwd(x, st.p(norm + "weight"), st.p(norm + "bias"), h, None, mean, rstd)
+        hff = self._empty(N, 2 * ff, dtype=BF16)
+        ops.gemm(h, st.w(pre + "linear1.weight"), hff, bias=st.p(pre + "linear1.bias"))
+        u = self._empty(N, ff, dtype=BF16)
+        ops.glu_fwd(hff, u)
+        y = self._empty(N, D)
+        ops.gemm(u, st.w(pre + "linear2.weight"), y, bias=st.p(pre + "linear2.bias"))
+        out = self._empty(N, D)
+        ops.rmsnorm_resid_fwd(y, st.p(pre + "output_norm.weight"), x, out)
+        sv.update(x=x, h=h, mean=mean, rstd=rstd, hff=hff, u=u, y=y)
+        return out
+
+    def _ffn_bwd(self, pre: str, dout: torch.Tensor, norm: str, ff: int, sv: dict):
+        st, D = self.store, self.D
+        N = dout.shape[0]
+        dy = self._empty(N, D, dtype=BF16)
+        ops.rmsnorm_resid_bwd(dout, sv["y"], st.p(pre + "output_norm.weight"), dy, st.g(pre + "output_norm.weight"))
+        self._wgrad(dy, sv["u"], st.g(pre + "linear2.weight"))
+        ops.colsum_bf16(dy, st.g(pre + "linear2.bias"))
+        du = self._empty(N, ff, dtype=BF16)
+        ops.gemm(dy, st.w(pre + "linear2.weight"), du, b_mn_major=True)
+        dhff = self._empty(N, 2 * ff, dtype=BF16)
+        ops.glu_bwd(du, sv["hff"], dhff)
+        self._wgrad(dhff, sv["h"], st.g(pre + "linear1.weight"))
+        ops.colsum_bf16(dhff, st.g(pre + "linear1.bias"))
+        dh = self._empty(N, D)
+        ops.gemm(dhff, st.w(pre + "linear1.weight"), dh, b_mn_major=True)
+        dx = self._empty(N, D)
+        dx_bf = self._empty(N, D, dtype=BF16)
+        ops.layernorm_bwd(dh, sv["x"], sv["mean"], sv["rstd"], st.p(norm + "weight"), dout, dx, dx_bf,
+                          st.g(norm + "weight"), st.g(norm + "bias"))
+        return dx, dx_bf
+
+    # ------------------------------------------------------------------------------------------
+    # variance predictor (two k=3 convs as overlapping-row GEMMs + GroupNorm/ReLU + linear head)
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _conv_view(buf_guarded: torch.Tensor, R: int, C: int) -> torch.Tensor:
+        """[R, 3C] view whose row r spans guarded rows r..r+2 (= padded rows r-1, r, r+1)."""
+        return torch.as_strided(buf_guarded, (R, 3 * C), (C, 1))
+
+    def _vp_fwd(self, pre: str, xg: torch.Tensor, geom: PadGeom, mask: Optional[torch.Tensor], sv: dict):
+        st, Fv = self.store, self.cfg.variance_filter_size
+        R, Cin = geom.R, xg.shape[1]
+        a1 = self._conv_view(xg, R, Cin)
+        c1 = self._empty(R, Fv)
+        ops.gemm(a1, st.w(pre + "conv_layers.0.weight"), c1, bias=st.p(pre + "conv_layers.0.bias"))
+        h1g = self._zeros(R + 2, Fv, dtype=BF16)
+        stats1 = self._empty(geom.G, 2, dtype=torch.float64)
+        ops.gn_fwd(c1, geom.row_group, geom.group_rows, stats1, st.p(pre + "norms.0.weight"),
+                   st.p(pre + "norms.0.bias"), h1g[1:R + 1])
+        a2 = self._conv_view(h1g, R, Fv)
+        c2 = self._empty(R, Fv)
+        ops.gemm(a2, st.w(pre + "conv_layers.1.weight"), c2, bias=st.p(pre + "conv_layers.1.bias"))
+        h2 = self._empty(R, Fv, dtype=BF16)
+        stats2 = self._empty(geom.G, 2, dtype=torch.float64)
+        ops.gn_fwd(c2, geom.row_group, geom.group_rows, stats2, st.p(pre + "norms.1.weight"),
+                   st.p(pre + "norms.1.bias"), h2)
+        out = self._empty(geom.B, geom.L)
+        ops.vp_head_fwd(h2, geom.row_of_tok, st.p(pre + "linear.weight"), st.p(pre + "linear.bias"), mask, out,
+                        geom.L, self.cfg.vp_chunk)
+        sv.update(xg=xg, c1=c1, h1g=h1g, stats1=stats1, c2=c2, h2=h2, stats2=stats2, mask=mask)
+        return out
+
+    def _vp_bwd(self, pre: str, dout: torch.Tensor, geom: PadGeom, sv: dict, need_dx: bool):
+        st, Fv = self.store, self.cfg.variance_filter_size
+        R, Cin = geom.R, sv["xg"].shape[1]
+        dh2 = self._empty(R, Fv, dtype=BF16)
+        ops.vp_head_bwd(dout, sv["h2"], geom.tok_of_row, st.p(pre + "linear.weight"), sv["mask"], dh2,
+                        st.g(pre + "linear.weight"), st.g(pre + "linear.bias"), geom.L, self.cfg.vp_chunk)
+        gsum = self._empty(geom.G, 2, dtype=torch.float64)
+        dc2g = self._zeros(R + 2, Fv, dtype=BF16)
+        ops.gn_bwd(dh2, sv["c2"], geom.row_group, geom.group_rows, sv["stats2"], gsum, st.p(pre + "norms.1.weight"),
+                   st.p(pre + "norms.1.bias"), dc2g[1:R + 1], st.g(pre + "norms.1.weight"), st.g(pre + "norms.1.bias"))
+        self._wgrad(dc2g[1:R + 1], self._conv_view(sv["h1g"], R, Fv), st.g(pre + "conv_layers.1.weight"))
+        ops.colsum_bf16(dc2g[1:R + 1], st.g(pre + "conv_layers.1.bias"))
+        dh1 = self._empty(R, Fv, dtype=BF16)
+        ops.gemm(self._conv_view(dc2g, R, Fv), st.conv_dgrad[pre + "conv_layers.1.weight"], dh1)
+        dc1g = self._zeros(R + 2, Fv, dtype=BF16)
+        ops.gn_bwd(dh1, sv["c1"], geom.row_group, geom.group_rows, sv["stats1"], gsum, st.p(pre + "norms.0.weight"),
+                   st.p(pre + "norms.0.bias"), dc1g[1:R + 1], st.g(pre + "norms.0.weight"), st.g(pre + "norms.0.bias"))
+        self._wgrad(dc1g[1:R + 1], self._conv_view(sv["xg"], R, Cin), st.g(pre + "conv_layers.0.weight"))
+        ops.colsum_bf16(dc1g[1:R + 1], st.g(pre + "conv_layers.0.bias"))
+        if not need_dx:
+            return None
+        dxp = self._empty(R, Cin)
+        ops.gemm(self._conv_view(dc1g, R, Fv), st.conv_dgrad[pre + "conv_layers.0.weight"], dxp)
+        dx = self._empty(geom.B * geom.L, Cin)
+        ops.gather_rows(dxp, geom.row_of_tok, dx)
+        return dx
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def forward(self, phoneme_indices, mel_specs, phoneme_durations, pitch_targets, energy_targets,
+                stress_indices=None, expanded_len: Optional[int] = None):
+        """Training forward.  Returns ((mel, log_dur, stop, pitch, energy), ctx)."""
+        cfg, st, D, H = self.cfg, self.store, self.D, self.H
+        B, P = phoneme_indices.shape
+        T = mel_specs.shape[1]
+        Ne, Nd = B * P, B * T
+        va = "duration_adaptor.variance_adaptor."
+        ctx: dict = {"B": B, "P": P, "T": T}
+        if expanded_len is None:
+            # T' = max_b sum(d) (reference utils/lengths.py:44-47 also synchronises here)
+            expanded_len = max(1, int(phoneme_durations.clamp(min=0).sum(dim=1).max().item()))
+        Tp = int(expanded_len)
+        if Tp < 3:
+            raise RuntimeError("expanded length < 3 frames is not supported")
+        ctx["Tp"] = Tp
+
+        # ---- encoder -------------------------------------------------------------------------
+        idx = phoneme_indices.contiguous()
+        stress = stress_indices.contiguous() if stress_indices is not None else None
+        x = self._empty(Ne, D)
+        ops.embed_fwd(idx, stress, st.p("text_embedding.weight"), st.p("stress_embedding.weight"), st.pe, x, P)
+        text_pad = self._empty(B, P, dtype=torch.uint8)
+        ops.eq_mask(idx, 0, text_pad)
+        enc_saved = []
+        for i in range(cfg.n_encoder_layers):
+            pre = f"transformer_encoder_layers.{i}."
+            s1, s2 = {}, {}
+            x = self._attn_fwd(pre + "self_attn.", x, B, P, pre + "norm1.", False, text_pad, None, P, s1)
+            x = self._ffn_fwd(pre + "ff.", x, pre + "norm2.", cfg.encoder_ff_dim, s2)
+            enc_saved.append((s1, s2))
+        enc = self._empty(Ne, D)
+        enc_mean, enc_rstd = self._empty(Ne), self._empty(Ne)
+        ops.layernorm_fwd(x, st.p("encoder_norm.weight"), st.p("encoder_norm.bias"), None, enc, enc_mean, enc_rstd)
+        ctx.update(idx=idx, stress=stress, text_pad=text_pad, enc_saved=enc_saved, enc_in=x,
+                   enc_mean=enc_mean, enc_rstd=enc_rstd)
+
+        # ---- variance adaptor ------------------------------------------------------------------
+        gt = self._geom(B, P)
+        xg_tok = self._zeros(gt.R + 2, D, dtype=BF16)
+        ops.scatter_rows(enc, gt.row_of_tok, xg_tok[1:])
+        sv_dur: dict = {}
+        log_dur = self._vp_fwd(va + "duration_predictor.", xg_tok, gt, text_pad, sv_dur)
+
+        dur = phoneme_durations.contiguous()
+        lr_idx = self._empty(B, Tp, dtype=torch.int32)
+        lengths = self._empty(B, dtype=torch.int32)
+        ops.lr_index(dur, lr_idx, lengths)
+        flags = self._zeros(2, dtype=torch.int32)
+        pitch_t, energy_t = pitch_targets.contiguous(), energy_targets.contiguous()
+        ops.range_flag(pitch_t, flags[0:1])
+        ops.range_flag(energy_t, flags[1:2])
+        gf = self._geom(B, Tp)
+        xg_frm = self._zeros(gf.R + 2, D, dtype=BF16)
+        mem = self._empty(Nd, D, dtype=BF16)
+        p_idx = self._empty(B, T, dtype=torch.int32)
+        e_idx = self._empty(B, T, dtype=torch.int32)
+        fmask_t = self._empty(B, T, dtype=torch.uint8)
+        fmask_p = self._empty(B, Tp, dtype=torch.uint8)
+        ops.expand_adapt(enc, lr_idx, lengths, pitch_t, energy_t, flags, st.pitch_bins, st.energy_bins,
+                         st.p(va + "pitch_embedding.weight"), st.p(va + "energy_embedding.weight"),
+                         gf.row_of_tok, xg_frm[1:], mem, p_idx, e_idx, fmask_t, fmask_p, B, P, D, Tp, T)
+        sv_pitch, sv_energy = {}, {}
+        pitch_pred = self._vp_fwd(va + "pitch_predictor.", xg_frm, gf, fmask_p, sv_pitch)
+        energy_pred = self._vp_fwd(va + "energy_predictor.", xg_frm, gf, fmask_p, sv_energy)
+        ctx.update(sv_dur=sv_dur, sv_pitch=sv_pitch, sv_energy=sv_energy, lr_idx=lr_idx, lengths=lengths,
+                   mem=mem, p_idx=p_idx, e_idx=e_idx, fmask_t=fmask_t, fmask_p=fmask_p)
+
+        # ---- decoder ---------------------------------------------------------------------------
+        mel = mel_specs.contiguous()
+        melshift = self._empty(Nd, cfg.mel_dim, dtype=BF16)
+        ops.shift_cast(mel, melshift.view(B, T, cfg.mel_dim))
+        y = self._empty(Nd, D)
+        ops.gemm(melshift, st.w("mel_projection_in.weight"), y, bias=st.p("mel_projection_in.bias"),
+                 resid=st.pe[:T], resid_mod=T)
+        dec_saved = []
+        for i in range(cfg.n_decoder_layers):
+            pre = f"decoder.layers.{i}."
+            s1, s2, s3 = {}, {}, {}
+            y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, None, None, T, s1)
+            y = self._attn_fwd(pre + "cross_attn.", y, B, T, pre + "norm2.", False, fmask_t, mem, T, s2)
+            y = self._ffn_fwd(pre + "ff.", y, pre + "norm3.", cfg.decoder_ff_dim, s3)
+            dec_saved.append((s1, s2, s3))
+        yn = self._empty(Nd, D, dtype=BF16)
+        dn_mean, dn_rstd = self._empty(Nd), self._empty(Nd)
+        ops.layernorm_fwd(y, st.p("decoder.norm.weight"), st.p("decoder.norm.bias"), yn, None, dn_mean, dn_rstd)
+        mel_pred = self._empty(Nd, cfg.mel_dim)
+        ops.gemm(yn, st.w("mel_projection_out.weight"), mel_pred, bias=st.p("mel_projection_out.bias"))
+        stop = self._empty(Nd)
+        ops.stop_head_fwd(yn, st.p("stop_token_predictor.weight"), st.p("stop_token_predictor.bias"), stop)
+        ctx.update(melshift=melshift, dec_saved=dec_saved, dec_in=y, dn_mean=dn_mean, dn_rstd=dn_rstd, yn=yn)
+        outs = (mel_pred.view(B, T, cfg.mel_dim), log_dur, stop.view(B, T), pitch_pred, energy_pred)
+        return outs, ctx
+
+    # ------------------------------------------------------------------------------------------
+    # losses (+ gradients wrt the five outputs)
+    # ------------------------------------------------------------------------------------------
+    def losses(self, outs, mel_specs, phoneme_durations, stop_targets, pitch_targets, energy_targets,
+               mel_lengths, phoneme_lengths, loss_scale: Optional[torch.Tensor] = None):
+        mel_pred, log_dur, stop, pitch_pred, energy_pred = outs
+        B, T, C = mel_specs.shape
+        P = phoneme_durations.shape[1]
+        Tp = pitch_pred.shape[1]
+        lc = self.loss_cfg
+        acc = self._empty(10, dtype=torch.float64)
+        losses = self._empty(6)
+        g = {"mel": self._empty(B * T, C, dtype=BF16), "dur": self._empty(B, P), "stop": self._empty(B * T),
+             "pitch": self._empty(B, Tp), "energy": self._empty(B, Tp)}
+        ops.losses_fwd_bwd(mel_pred, mel_specs.contiguous(), log_dur, phoneme_durations.contiguous(), stop,
+                           stop_targets.contiguous(), pitch_pred, pitch_targets.contiguous(), energy_pred,
+                           energy_targets.contiguous(), mel_lengths.contiguous(), phoneme_lengths.contiguous(),
+                           (lc.w_dur, lc.w_stop, lc.w_pitch, lc.w_energy), lc.stop_pos_weight,
+                           lc.huber_delta_var, loss_scale, acc, losses, g["mel"], g["dur"], g["stop"],
+                           g["pitch"], g["energy"])
+        return losses, g
+
+    # ------------------------------------------------------------------------------------------
+    # backward: accumulates into store.grads
+    # ------------------------------------------------------------------------------------------
+    def backward(self, ctx: dict, g: dict):
+        cfg, st, D = self.cfg, self.store, self.D
+        B, P, T, Tp = ctx["B"], ctx["P"], ctx["T"], ctx["Tp"]
+        Ne, Nd = B * P, B * T
+        va = "duration_adaptor.variance_adaptor."
+        dmel = g["mel"]                                     # [Nd, mel] bf16
+        # heads (the stop head reads a detached decoder output: weights only)
+        ops.stop_head_bwd(g["stop"], ctx["yn"], st.g("stop_token_predictor.weight"), st.g("stop_token_predictor.bias"))
+        self._wgrad(dmel, ctx["yn"], st.g("mel_projection_out.weight"))
+        ops.colsum_bf16(dmel, st.g("mel_projection_out.bias"))
+        dyn = self._empty(Nd, D)
+        ops.gemm(dmel, st.w("mel_projection_out.weight"), dyn, b_mn_major=True)
+        dy = self._empty(Nd, D)
+        dy_bf = self._empty(Nd, D, dtype=BF16)
+        ops.layernorm_bwd(dyn, ctx["dec_in"], ctx["dn_mean"], ctx["dn_rstd"], st.p("decoder.norm.weight"), None,
+                          dy, dy_bf, st.g("decoder.norm.weight"), st.g("decoder.norm.bias"))
+        dmem = self._empty(Nd, D)
+        first = True
+        for i in reversed(range(cfg.n_decoder_layers)):
+            pre = f"decoder.layers.{i}."
+            s1, s2, s3 = ctx["dec_saved"][i]
+            dy, dy_bf = self._ffn_bwd(pre + "ff.", dy, pre + "norm3.", cfg.decoder_ff_dim, s3)
+            dy, dy_bf = self._attn_bwd(pre + "cross_attn.", dy, dy_bf, B, T, pre + "norm2.", False, ctx["fmask_t"],
+                                       ctx["mem"], T, s2, dmem, first)
+            first = False
+            dy, dy_bf = self._attn_bwd(pre + "self_attn.", dy, dy_bf, B, T, pre + "norm1.", True, None, None, T,
+                                       s1, None, False)
+        self._wgrad(dy_bf, ctx["melshift"], st.g("mel_projection_in.weight"))
+        ops.colsum_bf16(dy_bf, st.g("mel_projection_in.bias"))
+        # memory gradient reaches only the pitch / energy embedding rows (detached expansion)
+        ops.adapt_bwd(dmem, ctx["p_idx"].view(-1), ctx["e_idx"].view(-1), st.g(va + "pitch_embedding.weight"),
+                      st.g(va + "energy_embedding.weight"))
+        gf, gt = self._geom(B, Tp), self._geom(B, P)
+        self._vp_bwd(va + "pitch_predictor.", g["pitch"], gf, ctx["sv_pitch"], need_dx=False)
+        self._vp_bwd(va + "energy_predictor.", g["energy"], gf, ctx["sv_energy"], need_dx=False)
+        denc = self._vp_bwd(va + "duration_predictor.", g["dur"], gt, ctx["sv_dur"], need_dx=True)
+        # encoder: gradient from the duration loss only
+        dx = self._empty(Ne, D)
+        dx_bf = self._empty(Ne, D, dtype=BF16)
+        ops.layernorm_bwd(denc, ctx["enc_in"], ctx["enc_mean"], ctx["enc_rstd"], st.p("encoder_norm.weight"), None,
+                          dx, dx_bf, st.g("encoder_norm.weight"), st.g("encoder_norm.bias"))
+        for i in reversed(range(cfg.n_encoder_layers)):
+            pre = f"transformer_encoder_layers.{i}."
+            s1, s2 = ctx["enc_saved"][i]
+            dx, dx_bf = self._ffn_bwd(pre + "ff.", dx, pre + "norm2.", cfg.encoder_ff_dim, s2)
+            dx, dx_bf = self._attn_bwd(pre + "self_attn.", dx, dx_bf, B, P, pre + "norm1.", False, ctx["text_pad"],
+                                       None, P, s1, None, False)
+        ops.embed_bwd(dx, ctx["idx"], ctx["stress"], st.g("text_embedding.weight"), st.g("stress_embedding.weight"))
+
+    def zero_grad(self):
+        self.store.grads.zero_()

@@ -121,3 +121,204 @@ def attn_bwd(q, k, v, o, d_o, lse, delta, dq, dk, dv, key_mask, causal: bool, sc
                            _ptr(dv), *_heads_strides(dv), _ptr(key_mask), c_int(B), c_int(H),
                            c_int(Sq), c_int(Sk), c_int(int(causal)), c_float(scale), _stream())
     check(rc, "kr_attn_bwd")
+
+
+# ---------------------------------------------------------------------------------------------
+# HBM kernels
+# ---------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, y_bf16, y_f32, mean, rstd, eps: float = 1e-5):
+    N, D = x.shape
+    check(lib().kr_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y_bf16), _ptr(y_f32), _ptr(mean),
+                                 _ptr(rstd), c_int(N), c_int(D), c_float(eps), _stream()), "kr_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, dx_bf16, dgamma, dbeta):
+    N, D = x.shape
+    check(lib().kr_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres), _ptr(dx),
+                                 _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), c_int(N), c_int(D), _stream()),
+          "kr_layernorm_bwd")
+
+
+def rmsnorm_resid_fwd(y, gain, resid, out):
+    N, D = y.shape
+    check(lib().kr_rmsnorm_resid_fwd(_ptr(y), _ptr(gain), _ptr(resid), _ptr(out), c_int(N), c_int(D), _stream()),
+          "kr_rmsnorm_resid_fwd")
+
+
+def rmsnorm_resid_bwd(dout, y, gain, dy_bf16, dgain):
+    N, D = y.shape
+    check(lib().kr_rmsnorm_resid_bwd(_ptr(dout), _ptr(y), _ptr(gain), _ptr(dy_bf16), _ptr(dgain), c_int(N),
+                                     c_int(D), _stream()), "kr_rmsnorm_resid_bwd")
+
+
+def _parts3(ts):
+    ts = list(ts) + [None] * (3 - len(ts))
+    return ts
+
+
+def qkv_prep_fwd(ins, outs, gains, rope_mask: int, cos_t, sin_t, N: int, S: int, H: int):
+    """ins/outs: lists (1..3) of [N, H*64] bf16 column-block views sharing one leading dimension."""
+    n = len(ins)
+    ld_in, ld_out = ins[0].stride(0), outs[0].stride(0)
+    i3, o3, g3 = _parts3(ins), _parts3(outs), _parts3(gains)
+    check(lib().kr_qkv_prep_fwd(_ptr(i3[0]), _ptr(i3[1]), _ptr(i3[2]), _ptr(o3[0]), _ptr(o3[1]), _ptr(o3[2]),
+                                c_ll(ld_in), c_ll(ld_out), _ptr(g3[0]), _ptr(g3[1]), _ptr(g3[2]), c_int(n),
+                                c_int(rope_mask), _ptr(cos_t), _ptr(sin_t), c_int(N), c_int(S), c_int(H),
+                                _stream()), "kr_qkv_prep_fwd")
+
+
+def qkv_prep_bwd(ins, grads, outs, gains, dgains, rope_mask: int, cos_t, sin_t, N: int, S: int, H: int):
+    n = len(ins)
+    ld_in, ld_out = ins[0].stride(0), outs[0].stride(0)
+    f32_mask = 0
+    for i, g in enumerate(grads):
+        if g.dtype == torch.float32:
+            f32_mask |= 1 << i
+    i3, g3, o3, w3, d3 = _parts3(ins), _parts3(grads), _parts3(outs), _parts3(gains), _parts3(dgains)
+    ldg = [g.stride(0) if g is not None else 0 for g in g3]
+    check(lib().kr_qkv_prep_bwd(_ptr(i3[0]), _ptr(i3[1]), _ptr(i3[2]), _ptr(g3[0]), _ptr(g3[1]), _ptr(g3[2]),
+                                c_ll(ldg[0]), c_ll(ldg[1]), c_ll(ldg[2]), _ptr(o3[0]), _ptr(o3[1]), _ptr(o3[2]),
+                                c_ll(ld_in), c_ll(ld_out), _ptr(w3[0]), _ptr(w3[1]), _ptr(w3[2]), _ptr(d3[0]),
+                                _ptr(d3[1]), _ptr(d3[2]), c_int(n), c_int(rope_mask), c_int(f32_mask),
+                                _ptr(cos_t), _ptr(sin_t), c_int(N), c_int(S), c_int(H), _stream()),
+          "kr_qkv_prep_bwd")
+
+
+def glu_fwd(h, u):
+    N, FF = u.shape
+    check(lib().kr_glu_fwd(_ptr(h), _ptr(u), c_int(N), c_int(FF), _stream()), "kr_glu_fwd")
+
+
+def glu_bwd(du, h, dh):
+    N, FF = du.shape
+    check(lib().kr_glu_bwd(_ptr(du), _ptr(h), _ptr(dh), c_int(N), c_int(FF), _stream()), "kr_glu_bwd")
+
+
+def colsum_bf16(x, out):
+    N, C = x.shape
+    check(lib().kr_colsum_bf16(_ptr(x), c_ll(x.stride(0)), _ptr(out), c_int(N), c_int(C), _stream()),
+          "kr_colsum_bf16")
+
+
+def embed_fwd(idx, stress, emb, semb, pe, x, P: int):
+    N, D = x.shape
+    check(lib().kr_embed_fwd(_ptr(idx), _ptr(stress), _ptr(emb), _ptr(semb), _ptr(pe), _ptr(x), c_int(N),
+                             c_int(P), c_int(D), _stream()), "kr_embed_fwd")
+
+
+def embed_bwd(dx, idx, stress, demb, dsemb):
+    N, D = dx.shape
+    check(lib().kr_embed_bwd(_ptr(dx), _ptr(idx), _ptr(stress), _ptr(demb), _ptr(dsemb), c_int(N), c_int(D),
+                             _stream()), "kr_embed_bwd")
+
+
+def shift_cast(mel, out):
+    B, T, C = mel.shape
+    check(lib().kr_shift_cast(_ptr(mel), _ptr(out), c_int(B), c_int(T), c_int(C), _stream()), "kr_shift_cast")
+
+
+def cast_bf16(src, dst):
+    check(lib().kr_cast_bf16(_ptr(src), _ptr(dst), c_ll(src.numel()), _stream()), "kr_cast_bf16")
+
+
+def scatter_rows(src, row_map, dst):
+    R, C = src.shape
+    check(lib().kr_scatter_rows(_ptr(src), _ptr(row_map), _ptr(dst), c_int(R), c_int(C),
+                                c_int(int(dst.dtype == torch.bfloat16)), _stream()), "kr_scatter_rows")
+
+
+def gather_rows(src, row_map, dst):
+    R, C = dst.shape
+    check(lib().kr_gather_rows(_ptr(src), _ptr(row_map), _ptr(dst), c_int(R), c_int(C), _stream()),
+          "kr_gather_rows")
+
+
+def eq_mask(idx, value: int, out):
+    check(lib().kr_eq_mask_i64(_ptr(idx), c_ll(value), _ptr(out), c_ll(idx.numel()), _stream()), "kr_eq_mask_i64")
+
+
+def nonfinite_flag(x, flag, bit: int):
+    check(lib().kr_nonfinite_flag(_ptr(x), c_ll(x.numel()), _ptr(flag), c_int(bit), _stream()), "kr_nonfinite_flag")
+
+
+def lr_index(dur, idx, lengths):
+    B, P = dur.shape
+    check(lib().kr_lr_index(_ptr(dur), _ptr(idx), _ptr(lengths), c_int(B), c_int(P), c_int(idx.shape[1]),
+                            _stream()), "kr_lr_index")
+
+
+def range_flag(x, flag):
+    check(lib().kr_range_flag(_ptr(x), c_ll(x.numel()), _ptr(flag), _stream()), "kr_range_flag")
+
+
+def expand_adapt(enc, idx, lengths, pitch, energy, flags, pbins, ebins, pemb, eemb, row_of_tok, xpad, mem,
+                 p_idx, e_idx, fmask_t, fmask_p, B, P, D, Tp, T):
+    check(lib().kr_expand_adapt(_ptr(enc), _ptr(idx), _ptr(lengths), _ptr(pitch), _ptr(energy), _ptr(flags),
+                                _ptr(pbins), _ptr(ebins), _ptr(pemb), _ptr(eemb), _ptr(row_of_tok), _ptr(xpad),
+                                _ptr(mem), _ptr(p_idx), _ptr(e_idx), _ptr(fmask_t), _ptr(fmask_p), c_int(B),
+                                c_int(P), c_int(D), c_int(Tp), c_int(T), c_int(pitch.shape[1]),
+                                c_int(pbins.numel()), _stream()), "kr_expand_adapt")
+
+
+def adapt_bwd(dmem, p_idx, e_idx, dpemb, deemb):
+    rows, D = dmem.shape
+    check(lib().kr_adapt_bwd(_ptr(dmem), _ptr(p_idx), _ptr(e_idx), _ptr(dpemb), _ptr(deemb), c_ll(rows), c_int(D),
+                             _stream()), "kr_adapt_bwd")
+
+
+def gn_fwd(x, row_group, group_rows, stats, gamma, beta, out):
+    R, C = x.shape
+    check(lib().kr_gn_fwd(_ptr(x), _ptr(row_group), _ptr(group_rows), _ptr(stats), _ptr(gamma), _ptr(beta),
+                          _ptr(out), c_int(R), c_int(C), c_int(group_rows.numel()), _stream()), "kr_gn_fwd")
+
+
+def gn_bwd(dy, x, row_group, group_rows, stats, gsum, gamma, beta, dx, dgamma, dbeta):
+    R, C = x.shape
+    check(lib().kr_gn_bwd(_ptr(dy), _ptr(x), _ptr(row_group), _ptr(group_rows), _ptr(stats), _ptr(gsum),
+                          _ptr(gamma), _ptr(beta), _ptr(dx), _ptr(dgamma), _ptr(dbeta), c_int(R), c_int(C),
+                          c_int(group_rows.numel()), _stream()), "kr_gn_bwd")
+
+
+def vp_head_fwd(h, row_of_tok, w, b, mask, out, L: int, chunk: int):
+    F = h.shape[1]
+    check(lib().kr_vp_head_fwd(_ptr(h), _ptr(row_of_tok), _ptr(w), _ptr(b), _ptr(mask), _ptr(out),
+                               c_int(out.numel()), c_int(L), c_int(F), c_int(chunk), _stream()), "kr_vp_head_fwd")
+
+
+def vp_head_bwd(dout, h, tok_of_row, w, mask, dh, dw, db, L: int, chunk: int):
+    R, F = h.shape
+    check(lib().kr_vp_head_bwd(_ptr(dout), _ptr(h), _ptr(tok_of_row), _ptr(w), _ptr(mask), _ptr(dh), _ptr(dw),
+                               _ptr(db), c_int(R), c_int(L), c_int(F), c_int(chunk), _stream()), "kr_vp_head_bwd")
+
+
+def conv_dgrad_shadow(w2, wd, Co: int, Ci: int):
+    check(lib().kr_conv_dgrad_shadow(_ptr(w2), _ptr(wd), c_int(Co), c_int(Ci), _stream()), "kr_conv_dgrad_shadow")
+
+
+def stop_head_fwd(x, w, b, z):
+    N, D = x.shape
+    check(lib().kr_stop_head_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(z), c_int(N), c_int(D), _stream()),
+          "kr_stop_head_fwd")
+
+
+def stop_head_bwd(dz, x, dw, db):
+    N, D = x.shape
+    check(lib().kr_stop_head_bwd(_ptr(dz), _ptr(x), _ptr(dw), _ptr(db), c_int(N), c_int(D), _stream()),
+          "kr_stop_head_bwd")
+
+
+def losses_fwd_bwd(mel_pred, mel_tgt, dur_pred, dur_tgt, stop_pred, stop_tgt, pitch_pred, pitch_tgt,
+                   energy_pred, energy_tgt, mel_len, ph_len, weights, pos_weight, delta_var, loss_scale, acc,
+                   losses, dmel, ddur, dstop, dpitch, denergy):
+    B, T, C = mel_tgt.shape
+    P = dur_tgt.shape[1]
+    Tp = pitch_pred.shape[1] if pitch_pred is not None else 0
+    Tt = pitch_tgt.shape[1] if pitch_tgt is not None else 0
+    w_dur, w_stop, w_pitch, w_energy = weights
+    check(lib().kr_losses_fwd_bwd(_ptr(mel_pred), _ptr(mel_tgt), _ptr(dur_pred), _ptr(dur_tgt), _ptr(stop_pred),
+                                  _ptr(stop_tgt), _ptr(pitch_pred), _ptr(pitch_tgt), _ptr(energy_pred),
+                                  _ptr(energy_tgt), _ptr(mel_len), _ptr(ph_len), c_int(B), c_int(T), c_int(P),
+                                  c_int(C), c_int(Tp), c_int(Tt), c_float(w_dur), c_float(w_stop),
+                                  c_float(w_pitch), c_float(w_energy), c_float(pos_weight), c_float(delta_var),
+                                  _ptr(loss_scale), _ptr(acc), _ptr(losses), _ptr(dmel), _ptr(ddur), _ptr(dstop),
+                                  _ptr(dpitch), _ptr(denergy), _stream()), "kr_losses_fwd_bwd")

@@ -1,0 +1,139 @@
+"""Acoustic engine (CUDA, bf16 tensor-core GEMMs, fp32 residual stream) vs the fp32 oracle and the
+golden fixtures generated from the live reference.
+
+Tolerance (BASELINE.json north_star): bf16 path within 1e-2 of the fp32 reference, metric
+max|a-b| / max|b| (SURVEY.md §8(c) parity recipe); LengthRegulator indices bit-exact.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+TOL_OUT = 1e-2
+TOL_GRAD = 3e-2   # per-tensor ||a-b|| / ||b||
+
+
+def _cases():
+    from oracle import acoustic as oa
+    return {
+        "tiny": (oa.AcousticConfig(hidden_dim=128, n_heads=2, n_encoder_layers=2, n_decoder_layers=2,
+                                   ff_dim=256, variance_filter=64, max_len=1200),
+                 dict(B=3, P=24, T=150, seed=11, ragged=True)),
+        "chunked": (oa.AcousticConfig(hidden_dim=128, n_heads=2, n_encoder_layers=1, n_decoder_layers=1,
+                                      ff_dim=128, variance_filter=64, max_len=1200),
+                    dict(B=2, P=40, T=600, seed=12, ragged=True)),
+        "full_width": (oa.AcousticConfig(max_len=1200), dict(B=2, P=32, T=200, seed=13, ragged=True)),
+    }
+
+
+def _engine_for(ocfg):
+    from kokoro_ruslan_b200.engine import AcousticEngine
+    from kokoro_ruslan_b200.params import ModelConfig
+    cfg = ModelConfig(vocab_size=ocfg.vocab_size, mel_dim=ocfg.mel_dim, hidden_dim=ocfg.hidden_dim,
+                      n_encoder_layers=ocfg.n_encoder_layers, n_heads=ocfg.n_heads, encoder_ff_dim=ocfg.ff_dim,
+                      n_decoder_layers=ocfg.n_decoder_layers, decoder_ff_dim=ocfg.ff_dim,
+                      max_decoder_seq_len=ocfg.max_len, variance_filter_size=ocfg.variance_filter,
+                      n_variance_bins=ocfg.n_bins)
+    return AcousticEngine(cfg, "cuda")
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("name", ["tiny", "chunked", "full_width"])
+def test_forward_backward_parity(name):
+    from oracle import acoustic as oa
+    ocfg, bk = _cases()[name]
+    batch = oa.synthetic_batch(n_mels=ocfg.mel_dim, vocab=ocfg.vocab_size, **bk)
+    sd = oa.seeded_state_dict(ocfg, seed=0)
+    eng = _engine_for(ocfg)
+    eng.store.load_state_dict(sd)
+    cb = {k: v.cuda() for k, v in batch.items()}
+    outs, ctx = eng.forward(cb["phoneme_indices"], cb["mel_specs"], cb["phoneme_durations"], cb["pitches"],
+                            cb["energies"], cb["stress_indices"])
+    losses, g = eng.losses(outs, cb["mel_specs"], cb["phoneme_durations"], cb["stop_token_targets"],
+                           cb["pitches"], cb["energies"], cb["mel_lengths"], cb["phoneme_lengths"])
+    eng.zero_grad()
+    eng.backward(ctx, g)
+    torch.cuda.synchronize()
+
+    # oracle (fp32, CPU) on the same inputs
+    sdr = {k: v.clone().requires_grad_(k not in oa.BUFFER_KEYS) for k, v in sd.items()}
+    o_outs = oa.forward_training(sdr, ocfg, batch["phoneme_indices"], batch["mel_specs"], batch["phoneme_durations"],
+                                 batch["pitches"], batch["energies"], batch["stress_indices"])
+    o_losses = oa.training_losses(ocfg, o_outs, batch["mel_specs"], batch["phoneme_durations"],
+                                  batch["stop_token_targets"], batch["pitches"], batch["energies"],
+                                  batch["mel_lengths"], batch["phoneme_lengths"])
+    o_losses[0].backward()
+
+    fix = np.load(os.path.join(HERE, "golden", f"acoustic_{name}.npz"))
+    for key, got, want in zip(("mel", "log_dur", "stop", "pitch", "energy"), outs, o_outs):
+        r = _rel(got.float().cpu(), want.detach())
+        rg = _rel(got.float().cpu(), torch.from_numpy(fix[f"out_{key}"]))
+        assert r < TOL_OUT and rg < TOL_OUT, f"{name}:{key} rel err vs oracle {r:.3e}, vs golden {rg:.3e}"
+    got_l = losses.cpu().double().numpy()
+    want_l = np.array([float(x) for x in o_losses])
+    assert np.allclose(got_l, want_l, rtol=1e-2, atol=1e-4), (got_l, want_l)
+    assert np.allclose(got_l, fix["losses"], rtol=1e-2, atol=1e-4), (got_l, fix["losses"])
+
+    worst = []
+    gsd = eng.store.state_dict(eng.store.grads)
+    for n in eng.store.order:
+        og = sdr[n].grad
+        mine = gsd[n].float().cpu()
+        if og is None:
+            assert float(mine.abs().max()) == 0.0, n
+            continue
+        denom = float(og.norm()) + 1e-12
+        err = float((mine - og).norm()) / denom
+        worst.append((err, n, denom))
+    worst.sort(reverse=True)
+    bad = [(e, n, d) for e, n, d in worst if e > TOL_GRAD and d > 1e-7]
+    assert not bad, f"{name}: gradient mismatches (rel L2): {bad[:8]}"
+
+
+def test_length_regulator_bit_exact():
+    from oracle import acoustic as oa
+    from kokoro_ruslan_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    dur = torch.randint(0, 30, (5, 256), generator=g)
+    dur[1] = 0                      # all-zero row
+    dur[2, 100:] = 0                # padded tail
+    dur[3, ::3] = -2                # negative durations clamp to 0
+    for max_len in (None, 1000, 4500):
+        want, L = oa.length_regulate_index(dur, max_len)
+        Tp = want.shape[1]
+        idx = torch.empty(5, Tp, dtype=torch.int32, device="cuda")
+        lens = torch.empty(5, dtype=torch.int32, device="cuda")
+        ops.lr_index(dur.cuda(), idx, lens)
+        assert torch.equal(idx.cpu().long(), want), f"index mismatch (max_len={max_len})"
+        assert torch.equal(lens.cpu().long(), L)
+
+
+def test_expand_matches_reference_semantics():
+    """expanded memory / masks / bucket indices vs the oracle's aux outputs (bit-exact integers)."""
+    from oracle import acoustic as oa
+    ocfg, bk = _cases()["tiny"]
+    batch = oa.synthetic_batch(n_mels=ocfg.mel_dim, vocab=ocfg.vocab_size, **bk)
+    sd = oa.seeded_state_dict(ocfg, seed=0)
+    eng = _engine_for(ocfg)
+    eng.store.load_state_dict(sd)
+    cb = {k: v.cuda() for k, v in batch.items()}
+    outs, ctx = eng.forward(cb["phoneme_indices"], cb["mel_specs"], cb["phoneme_durations"], cb["pitches"],
+                            cb["energies"], cb["stress_indices"])
+    _, aux = oa.forward_training(sd, ocfg, batch["phoneme_indices"], batch["mel_specs"], batch["phoneme_durations"],
+                                 batch["pitches"], batch["energies"], batch["stress_indices"], return_aux=True)
+    assert torch.equal(ctx["fmask_t"].cpu().bool(), aux["frame_mask"])
+    valid = ~aux["frame_mask"]
+    assert torch.equal(ctx["p_idx"].cpu().long()[valid], aux["pitch_idx"][:, :valid.shape[1]][valid])
+    assert torch.equal(ctx["e_idx"].cpu().long()[valid], aux["energy_idx"][:, :valid.shape[1]][valid])
+    B, T = valid.shape
+    r = _rel(ctx["mem"].float().cpu().view(B, T, -1), aux["memory"])
+    assert r < 1e-2, r

@@ -1,0 +1,127 @@
+"""CPU-side checks: oracle pinned to the golden fixtures, parameter table, groups, C-ABI exports."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _cases():
+    from oracle import acoustic as oa
+    return {
+        "tiny": (oa.AcousticConfig(hidden_dim=128, n_heads=2, n_encoder_layers=2, n_decoder_layers=2,
+                                   ff_dim=256, variance_filter=64, max_len=1200),
+                 dict(B=3, P=24, T=150, seed=11, ragged=True)),
+        "chunked": (oa.AcousticConfig(hidden_dim=128, n_heads=2, n_encoder_layers=1, n_decoder_layers=1,
+                                      ff_dim=128, variance_filter=64, max_len=1200),
+                    dict(B=2, P=40, T=600, seed=12, ragged=True)),
+        "full_width": (oa.AcousticConfig(max_len=1200), dict(B=2, P=32, T=200, seed=13, ragged=True)),
+    }
+
+
+@pytest.mark.parametrize("name", ["tiny", "chunked", "full_width"])
+def test_oracle_matches_reference_golden(name):
+    """The fp32 oracle reproduces the live reference's outputs, losses and gradients (fixtures made
+    by tests/golden/make_golden.py from /root/reference)."""
+    from oracle import acoustic as oa
+    ocfg, bk = _cases()[name]
+    batch = oa.synthetic_batch(n_mels=ocfg.mel_dim, vocab=ocfg.vocab_size, **bk)
+    sd = oa.seeded_state_dict(ocfg, seed=0)
+    sdr = {k: v.clone().requires_grad_(k not in oa.BUFFER_KEYS) for k, v in sd.items()}
+    outs = oa.forward_training(sdr, ocfg, batch["phoneme_indices"], batch["mel_specs"], batch["phoneme_durations"],
+                               batch["pitches"], batch["energies"], batch["stress_indices"])
+    losses = oa.training_losses(ocfg, outs, batch["mel_specs"], batch["phoneme_durations"],
+                                batch["stop_token_targets"], batch["pitches"], batch["energies"],
+                                batch["mel_lengths"], batch["phoneme_lengths"])
+    losses[0].backward()
+    fix = np.load(os.path.join(HERE, "golden", f"acoustic_{name}.npz"))
+    for key, got in zip(("mel", "log_dur", "stop", "pitch", "energy"), outs):
+        want = torch.from_numpy(fix[f"out_{key}"])
+        assert torch.allclose(got.detach(), want, rtol=1e-4, atol=2e-5), key
+    assert np.allclose([float(x) for x in losses], fix["losses"], rtol=1e-5, atol=1e-6)
+    for n, norm, samp in zip(fix["grad_names"], fix["grad_norms"], fix["grad_samples"]):
+        g = sdr[str(n)].grad
+        if norm < 0:
+            assert g is None or float(g.abs().max()) == 0.0
+            continue
+        assert abs(float(g.double().norm()) - norm) <= 1e-4 * norm + 1e-7, n
+        flat = g.reshape(-1)
+        idx = torch.linspace(0, flat.numel() - 1, 4).long()
+        assert np.allclose(flat[idx].numpy(), samp, rtol=1e-3, atol=1e-6), n
+
+
+def test_length_regulator_reference_vectors():
+    """Exact expansion values the reference's own tests pin (tests/unit/test_utils_lengths.py:11-43)."""
+    from oracle import acoustic as oa
+    tokens = torch.tensor([[1.0, 2.0, 3.0]])
+    out = oa.expand_tokens(tokens, torch.tensor([[2, 0, 3]]))
+    assert out.tolist() == [[1.0, 1.0, 3.0, 3.0, 3.0]]
+    out = oa.expand_tokens(tokens, torch.tensor([[1, 1, 1]]), max_len=5)
+    assert out.tolist() == [[1.0, 2.0, 3.0, 0.0, 0.0]]
+    out = oa.expand_tokens(tokens, torch.tensor([[3, 3, 3]]), max_len=4)
+    assert out.tolist() == [[1.0, 1.0, 1.0, 2.0]]
+    out = oa.expand_tokens(tokens, torch.tensor([[0, 0, 0]]))
+    assert out.tolist() == [[0.0]]
+
+
+def test_param_table_matches_reference_names():
+    from kokoro_ruslan_b200.params import ModelConfig, param_specs
+    fix = np.load(os.path.join(HERE, "golden", "acoustic_full_width.npz"))
+    names = [n for n, _ in param_specs(ModelConfig())]
+    assert names == [str(n) for n in fix["grad_names"]]
+    assert len(names) == 308
+    total = 0
+    for _, shape in param_specs(ModelConfig()):
+        n = 1
+        for s in shape:
+            n *= s
+        total += n
+    assert total == 49432276
+
+
+def test_optimizer_groups_match_reference_counts():
+    """SURVEY.md §8 A13': 94/12/52/20/48/48/12/18/2/2 tensors in the ten AdamW groups."""
+    from kokoro_ruslan_b200.optim import OptimConfig, group_of, preclip_of
+    from kokoro_ruslan_b200.params import ModelConfig, param_specs
+    counts = [0] * 10
+    elems = [0] * 10
+    n_pre = 0
+    for name, shape in param_specs(ModelConfig()):
+        g = group_of(name)
+        counts[g] += 1
+        n = 1
+        for s in shape:
+            n *= s
+        elems[g] += n
+        n_pre += preclip_of(name, OptimConfig()) > 0
+    assert counts == [94, 12, 52, 20, 48, 48, 12, 18, 2, 2]
+    assert elems == [6365312, 14155776, 1785683, 91136, 12582912, 8448, 14155776, 24576, 262144, 513]
+    assert n_pre == 126
+
+
+def test_c_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "kokoro_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(kr_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) > 30
+    so = os.path.join(ROOT, "kokoro_ruslan_b200", "libkokoro_b200.so")
+    if not os.path.exists(so):
+        from kokoro_ruslan_b200.build import build
+        build()
+    lib = ctypes.CDLL(so)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    lib.kr_abi_version.restype = ctypes.c_int
+    assert lib.kr_abi_version() == 1
+
+
+def test_ops_refuse_cpu_tensors():
+    from kokoro_ruslan_b200 import ops
+    a = torch.zeros(128, 64, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, a, torch.zeros(128, 128))

@@ -1,0 +1,124 @@
+"""Regenerates include/kokoro_b200.h from the extern "C" definitions in kokoro_ruslan_b200/csrc.
+
+The prototypes are copied verbatim from the sources (single source of truth); the per-function
+comment (what it replaces in the reference, file:line) comes from DOCS below.  A function without a
+DOCS entry fails the generation so the header can never silently lose its citations.
+"""
+import glob
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+DOCS = {
+    "kr_last_error": "Thread-local message of the last failing call (every entry point returns 0 or a negative KR_ERR_* code; the Python side maps non-zero to RuntimeError, which the reference trainer's per-batch handler expects: training/trainer.py:2679-2686).",
+    "kr_abi_version": "ABI version of this header (1).",
+    "kr_device_cc": "Compute capability (major*10+minor) of the current device; 100 on B200.",
+    "kr_gemm_bf16": "tcgen05 GEMM C[M,N] (+)= alpha*A[M,K]*B[N,K]^T (+bias[n]) (+resid[m % resid_mod, n]); bf16 operands staged by TMA, fp32 accumulation in TMEM. a_mn_major / b_mn_major select the [K,rows] storage that weight- and data-gradient GEMMs read in place. epi_mode 0 = bf16 store, 1 = fp32 store, 2 = fp32 atomic accumulate (split-K). Replaces every nn.Linear on the path: model/transformers.py:228,258-259,434 (Q/K/V/out projections), transformers.py:105-111 (GLU FFN), model/model.py:519-531,561 (mel in/out projections), and — through an overlapping-row view — the k=3 nn.Conv1d of model/variance_predictor.py:46.",
+    "kr_attn_fwd": "tcgen05 flash attention forward, head_dim 64, on token-major [B,S,H,64] bf16 tensors (q_ss/q_bs = seq/batch strides in elements). Causal and per-key padding (key_mask[B,Sk], 1 = masked) are predicates; lse[B,H,Sq] is the log2-domain log-sum-exp kept for the backward. Replaces F.scaled_dot_product_attention with the dense additive mask, model/transformers.py:299-316,393-398.",
+    "kr_attn_bwd": "Flash attention backward: dq (fp32 [B,Sq,H,64], zeroed by the caller, atomically accumulated), dk/dv (bf16). delta[B,H,Sq] is scratch. Autograd of model/transformers.py:393-398.",
+    "kr_stop_head_fwd": "Stop-token logits z[n] = x[n,:].w + b on the (detached) decoder output, model/model.py:562.",
+    "kr_stop_head_bwd": "Weight/bias gradient of the stop head (no data gradient: the input is detached, model/model.py:562).",
+    "kr_losses_fwd_bwd": "Fused masked losses + gradients w.r.t. the five model outputs: L1 mel, Huber(1) log1p-duration, BCE-with-logits(pos_weight) stop, Huber(delta_var) pitch/energy, clamps 100/100/100/10/10, weighted total; losses[6] = total, mel, dur, stop, pitch, energy. training/losses.py:9-216, criteria training/trainer.py:410-444.",
+    "kr_layernorm_fwd": "LayerNorm over the last dim (D in {128,256,512}), fp32 in, bf16 and/or fp32 out, saves mean/rstd. model/transformers.py:478,485,564,572,581,660; model/model.py:122.",
+    "kr_layernorm_bwd": "LayerNorm backward fused with the residual-gradient add (dx = dres + ...), optional bf16 copy of dx, dgamma/dbeta accumulated with atomics.",
+    "kr_rmsnorm_resid_fwd": "FFN output RMSNorm(eps = fp32 finfo.eps) + residual add, model/transformers.py:94,109-111.",
+    "kr_rmsnorm_resid_bwd": "Backward of kr_rmsnorm_resid_fwd w.r.t. y (bf16) and the gain.",
+    "kr_qkv_prep_fwd": "Per-head RMSNorm(64) with learned gain on up to three column blocks (q|k|v) + rotate-half RoPE on the blocks selected by rope_mask; position = row % S. model/transformers.py:145-148,260-272; model/positional_encoding.py:196-209.",
+    "kr_qkv_prep_bwd": "Backward of kr_qkv_prep_fwd: incoming gradients may be fp32 (grad_f32_mask) or bf16; writes d(raw projection) bf16 and accumulates the gain gradients.",
+    "kr_optim_ctrl_size": "sizeof the device-resident optimizer control block (64 bytes; layout in kokoro_ruslan_b200/optim.py CTRL_FIELDS).",
+    "kr_grad_sqnorm": "Per-tensor squared L2 norms of the flat gradient buffer + non-finite flag. Replaces the 308 `.norm().item()` + 2x308 `isfinite().all()` host syncs of training/trainer.py:2355-2362,1308-1313.",
+    "kr_step_control": "Device-side step control: per-tensor spike pre-clip scales (training/trainer.py:1332-1407), total norm, explosion detector (trainer.py:1315-1330,2367-2405), clip coefficient (clip_grad_norm_, training/runtime_policies.py:33-79), skip-on-non-finite (trainer.py:2407-2463), bias corrections.",
+    "kr_adamw_step": "Fused clip + AdamW (per-group lr / weight decay, trainer.py:446-689) + EMA (trainer.py:1491-1517) + bf16 shadow write over the flat buffers; accumulates squared norms of the tensors subject to the weight-norm projection.",
+    "kr_wn_project": "Post-step projection ||W||_2 <= limit of the decoder FFN matrices, training/trainer.py:883-912.",
+    "kr_glu_fwd": "u = gelu_erf(gate) * lin over h = [gate | lin], model/transformers.py:105-108.",
+    "kr_glu_bwd": "Backward of kr_glu_fwd.",
+    "kr_colsum_bf16": "out[c] += sum_n x[n,c] (bias gradients).",
+    "kr_embed_fwd": "Encoder input emb[idx]*sqrt(D) + stress_emb[s] + PE[n % P], model/model.py:375-378, model/positional_encoding.py:66-74.",
+    "kr_embed_bwd": "Scatter-add into the token / stress embedding gradients (stress row 0 = padding_idx gets none, model/model.py:92).",
+    "kr_shift_cast": "Teacher-forcing shift-right of the mel target + bf16 cast, model/model.py:519.",
+    "kr_cast_bf16": "fp32 -> bf16 copy (initial shadow of the master weights).",
+    "kr_scatter_rows": "dst[map[r]] = src[r] row copy (fp32 -> bf16/fp32): token order -> predictor padded layout.",
+    "kr_gather_rows": "dst[r] = src[map[r]] row copy (fp32), zero rows where map[r] < 0.",
+    "kr_eq_mask_i64": "Byte mask idx == value: the reference text padding mask `phoneme_indices == 0`, model/model.py:586-587.",
+    "kr_nonfinite_flag": "Sets `bit` in *flag if x holds a NaN/Inf — the finite-output guard of training/trainer.py:3233-3256 without host syncs.",
+    "kr_lr_index": "LengthRegulator index tensor: idx[b,f] = min{j : cumsum(max(0,d))[b,j] > f} for f < L[b], else -1; lengths[b] = L[b]. Bit-exact restatement of utils/lengths.py:16-96 (repeat_interleave + scatter on the CPU in the reference).",
+    "kr_range_flag": "flag |= any(x > 1 or x < 0): the data-dependent normalisation test of model/variance_predictor.py:244,268.",
+    "kr_expand_adapt": "Duration-expand gather + pitch/energy bucketize(255 bins) + embedding add + frame masks; writes the predictor input (padded layout) and the decoder memory aligned to the mel length. model/variance_predictor.py:345-437, model/model.py:607-628.",
+    "kr_adapt_bwd": "Memory gradient -> pitch/energy embedding rows (the only path through the detached expansion, utils/lengths.py:30).",
+    "kr_gn_fwd": "GroupNorm(1 group, eps 1e-5) + ReLU per independent (sample, 512-frame chunk) on the padded layout, model/variance_predictor.py:55,70-115.",
+    "kr_gn_bwd": "Backward of kr_gn_fwd (ReLU mask recomputed), dgamma/dbeta accumulated.",
+    "kr_vp_head_fwd": "Predictor head Linear(F->1) + masked_fill(mask, 0); a chunk of length 1 yields zeros, model/variance_predictor.py:95-115.",
+    "kr_vp_head_bwd": "Backward of kr_vp_head_fwd.",
+    "kr_conv_dgrad_shadow": "bf16 tap-reversed transpose of a tap-major conv weight: the B operand of the conv data-gradient GEMM.",
+}
+
+TYPES = """typedef struct CUstream_st* kr_stream_t; /* passed as void*: a cudaStream_t */"""
+
+
+def main():
+    protos = []
+    for f in sorted(glob.glob(os.path.join(ROOT, "kokoro_ruslan_b200", "csrc", "*.cu"))):
+        s = open(f).read()
+        group = []
+        for m in re.finditer(r'extern "C"\s+((?:const\s+)?\w+\*?)\s+(kr_\w+)\s*\(([^)]*)\)', s):
+            ret, name, args = m.groups()
+            args = re.sub(r"\s+", " ", args.strip())
+            if name not in DOCS:
+                sys.exit(f"gen_header: no DOCS entry for {name}")
+            group.append((ret, name, args))
+        if group:
+            protos.append((os.path.basename(f), group))
+    out = ["/* kokoro_b200.h — C ABI of libkokoro_b200.so (GENERATED by tools/gen_header.py; do not edit).",
+           " *",
+           " * Drop-in boundary of the Blackwell-native hot path of igorshmukler/kokoro-ruslan.  The reference",
+           " * has no FFI of its own (it is pure PyTorch); each entry point below replaces the ATen/torch call",
+           " * sites cited in its comment (paths relative to the reference's src/kokoro/).",
+           " *",
+           " * Conventions: plain pointers and sizes only (no torch types); all pointers are DEVICE pointers",
+           " * unless noted; the caller allocates every output / workspace; every launch goes to the",
+           " * cudaStream_t passed as `stream` (graph-capturable, no allocation, no synchronisation);",
+           " * return 0 on success or a negative KR_ERR_* code with a message in kr_last_error().",
+           " */",
+           "#ifndef KOKORO_B200_H", "#define KOKORO_B200_H", "", "#ifdef __cplusplus", 'extern "C" {', "#endif", "",
+           "#define KR_OK 0", "#define KR_ERR_ARG (-1)", "#define KR_ERR_CUDA (-2)", "#define KR_ERR_TMAP (-3)",
+           "#define KR_ERR_UNSUPPORTED (-4)", ""]
+    for fname, group in protos:
+        out.append(f"/* ---- {fname} " + "-" * max(4, 88 - len(fname)) + " */")
+        for ret, name, args in group:
+            doc = DOCS[name]
+            words, line, lines = doc.split(), "", []
+            for w in words:
+                if len(line) + len(w) + 1 > 96:
+                    lines.append(line)
+                    line = w
+                else:
+                    line = (line + " " + w).strip()
+            lines.append(line)
+            out.append("/* " + ("\n * ".join(lines)) + " */")
+            proto = f"{ret} {name}({args});"
+            # wrap long prototypes
+            if len(proto) > 100:
+                parts = args.split(", ")
+                cur = f"{ret} {name}("
+                wrapped = []
+                for i, p in enumerate(parts):
+                    piece = p + (", " if i < len(parts) - 1 else ");")
+                    if len(cur) + len(piece) > 100:
+                        wrapped.append(cur.rstrip())
+                        cur = "    " + piece
+                    else:
+                        cur += piece
+                wrapped.append(cur)
+                proto = "\n".join(wrapped)
+            out.append(proto)
+            out.append("")
+    out += ["#ifdef __cplusplus", "}", "#endif", "#endif /* KOKORO_B200_H */", ""]
+    path = os.path.join(ROOT, "include", "kokoro_b200.h")
+    open(path, "w").write("\n".join(out))
+    print(f"wrote {path}: {sum(len(g) for _, g in protos)} entry points")
+
+
+if __name__ == "__main__":
+    main()
