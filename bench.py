@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — acoustic-model training step throughput (mel-frames/s) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json north_star / SURVEY.md §8(d)): synthetic batch B=8 utterances per GPU,
+phoneme_len 128, mel_frames 800, n_mels 80, default 49.4 M-parameter model, bf16 tensor-core GEMMs
+with fp32 residual stream / accumulation / optimizer.  One "step" = H2D-resident batch ->
+forward -> fused losses -> backward -> (all-reduce) -> clip + AdamW + EMA (one optimizer step).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident whole-job throughput; `e2e` = the same
+through TrainStep.train_step() with pinned HOST batches (H2D inside the timed region) and a D2H
+read of the losses every step.  `roofline` = the tcgen05 GEMM family (dominant kernel) timed per
+launch with CUDA events in an instrumented eager step right after the timed region;
+`cpu_baseline` = the oracle port of the same step on the host cores (bounded sample).
+`--impl reference` times the CPU oracle port only (the reference is pure Python/PyTorch and its
+algorithm is restated in oracle/).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B_PER_GPU, P_LEN, T_LEN, N_MELS = 8, 128, 800, 80
+METRIC = "mel_frames_per_sec_train_step"
+UNIT = "mel-frames/s"
+WORKLOAD = "acoustic train step: B=8/GPU, phoneme_len=128, mel_frames=800, n_mels=80 (configs[1]/[2] synthetic point)"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        return {"hbm_gbs": float(pk["hbm_gbs"]), "tf_burst": float(pk["bf16_tflops"]),
+                "tf_sustained": float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"])), "src": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def synthetic_batch(B, P, T, n_mels, vocab, seed):
+    """Seeded synthetic batch of SURVEY.md §8(d) (same recipe as oracle.acoustic.synthetic_batch,
+    restated here so the product arm never imports oracle/)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    ph = torch.randint(1, vocab, (B, P), generator=g)
+    stress = torch.randint(0, 3, (B, P), generator=g)
+    base, extra = T // P, T - (T // P) * P
+    dur = torch.full((B, P), base, dtype=torch.long)
+    dur[:, :extra] += 1
+    mel = torch.randn(B, T, n_mels, generator=g) * 2.0 - 5.0
+    pitch = torch.rand(B, T, generator=g)
+    energy = torch.rand(B, T, generator=g)
+    stop = torch.zeros(B, T)
+    for k in range(7):
+        stop[:, T - 1 - k] = 0.5 ** k
+    return {"phoneme_indices": ph, "stress_indices": stress, "phoneme_durations": dur, "mel_specs": mel,
+            "pitches": pitch, "energies": energy, "stop_token_targets": stop,
+            "mel_lengths": torch.full((B,), T, dtype=torch.long), "phoneme_lengths": torch.full((B,), P, dtype=torch.long)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline and --impl reference)
+# ----------------------------------------------------------------------------------------------
+def cpu_oracle_run(steps: int, warmup: int, budget_s: float):
+    """Times the oracle port of the training step (fwd + losses + bwd + pre-clip + clip + AdamW +
+    EMA, fp32, dropout 0) on the host cores.  Returns (frames/s, ms/step, cores, sample text)."""
+    import torch
+    from oracle import acoustic as oa
+    from oracle.train_step import CpuTrainStep
+    cores = torch.get_num_threads()
+    cfg = oa.AcousticConfig()
+    step = CpuTrainStep(cfg, oa.seeded_state_dict(cfg, seed=0))
+    B = B_PER_GPU
+    batch = oa.synthetic_batch(B=B, P=P_LEN, T=T_LEN, seed=1)
+    t0 = time.perf_counter()
+    step.train_step(batch)
+    t_first = time.perf_counter() - t0
+    done_warm = 1
+    if (steps + max(0, warmup - 1)) * t_first > budget_s and B > 1:
+        B = max(1, int(B * budget_s / ((steps + max(0, warmup - 1)) * t_first)))
+        batch = {k: (v[:B].clone() if hasattr(v, "shape") else v) for k, v in batch.items()}
+    while done_warm < warmup:
+        step.train_step(batch)
+        done_warm += 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step.train_step(batch)
+    dt = time.perf_counter() - t0
+    frames = steps * B * T_LEN
+    sample = (f"{steps} full optimizer steps (fwd+losses+bwd+pre-clip+clip+AdamW+EMA, fp32, dropout 0) of "
+              f"B={B} utterances x P={P_LEN} x T={T_LEN}, torch {torch.__version__} CPU, {cores} threads")
+    return frames / dt, dt / steps * 1e3, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, ms, cores, sample = cpu_oracle_run(args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# product arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from kokoro_ruslan_b200.build import build
+    build()
+    from kokoro_ruslan_b200 import _lib
+    from kokoro_ruslan_b200.kprof import OpTimer
+    from kokoro_ruslan_b200.params import ModelConfig
+    from kokoro_ruslan_b200.train_step import ScheduleConfig, TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    if args.gpus != world and rank == 0 and world > 1:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+
+    cfg = ModelConfig()
+    ts = TrainStep(cfg, sched_cfg=ScheduleConfig(total_steps=100000), device=dev, use_graphs=True, process_group=pg)
+    ts.store.init_default(seed=0)          # same weights on every rank
+    host = synthetic_batch(B_PER_GPU, P_LEN, T_LEN, N_MELS, cfg.vocab_size, seed=1 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    frames_per_step = B_PER_GPU * T_LEN * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up through the public API (eager pass, graph capture, replays) --------------------
+    W = max(3, args.warmup)
+    for _ in range(W):
+        losses = ts.train_step(host)
+    torch.cuda.synchronize(dev)
+    first_losses = losses.cpu().tolist()
+    launches_per_step = ts.launches_last_step
+    # device-resident copy of the batch for the `value` leg (same static buffers: no copies at all)
+    st, key = ts.stage(host)
+    resident = st.dev
+
+    # ---- e2e leg: host batches in, losses out, every step ---------------------------------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        l = ts.train_step(host)
+        l_host = l.cpu()                      # D2H read of the step's result (synchronises)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
+    # ---- value leg: inputs resident in HBM --------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ts.train_step(resident)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    clocks = sampler.stop()
+    final_losses = ts._staged[key].losses.cpu().tolist() if ts._staged[key].losses is not None else None
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier(device_ids=[local])
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: instrumented eager step (per-launch CUDA events) ---------------------------------
+    peaks = _peaks()
+    roof, top_ops = None, []
+    try:
+        ts_use_graphs = ts.use_graphs
+        ts.use_graphs = False
+        world_saved = ts.world
+        ts.world = 1                              # rank-0-only pass: no collective
+        with OpTimer() as tm:
+            ts.stage(resident)
+            ts.opt.set_lrs(ts.sched.lrs())
+            ts._run_fwd_bwd(st, key)
+            with tm.region("optimizer(sqnorm+control+adamw_ema+wn_project)", byts=9 * 4.0 * ts.store.total):
+                ts._run_optimizer()
+        ts.use_graphs, ts.world = ts_use_graphs, world_saved
+        rows = tm.summary()
+        step_ms_eager = sum(r["ms"] for r in rows)
+        gemm = [r for r in rows if r["op"].startswith("gemm")]
+        g_ms, g_fl = sum(r["ms"] for r in gemm), sum(r["flops"] for r in gemm)
+        g_n = sum(r["launches"] for r in gemm)
+        all_fl = sum(r["flops"] for r in rows)
+        achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "kr_gemm_kernel (tcgen05 bf16 GEMM, all %d launches of a step)" % g_n,
+                "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
+                "share_of_step": g_ms / step_ms_eager if step_ms_eager else None,
+                "algorithmic_flops_per_step": all_fl,
+                "step_tensor_frac": all_fl / (ms * 1e-3) / 1e12 / peaks["tf_sustained"],
+                "how": "CUDA events around every C-ABI launch of one eager step after the timed region"}
+        top_ops = [{"op": r["op"], "n": r["launches"], "ms": round(r["ms"], 4), "share": round(r["share"], 4),
+                    "tflops": round(r["tflops"], 1), "gbs": round(r["gbs"], 1)} for r in rows[:14]]
+    except Exception as exc:  # the bench line must still be printed
+        roof = {"bound": "tensor", "error": repr(exc)}
+
+    # ---- CPU baseline (oracle port, bounded sample) ---------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, _, cores, sample = cpu_oracle_run(steps=2, warmup=1, budget_s=40.0)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        except Exception as exc:
+            cpu = {"error": repr(exc)}
+
+    line = {"metric": METRIC, "value": frames_per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "params": 49432276,
+                       "precision": "bf16 tcgen05 GEMM/attention operands, fp32 accumulate/residual/optimizer",
+                       "dropout": 0.0, "grad_accum": 1, "parallelism": f"dp{world}",
+                       "l2": "no flush: a step streams >1 GB of weights/optimizer state/activations (> 126 MB L2)",
+                       "cuda_graphs": True},
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": frames_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d_bytes + 8 + 40, "d2h_bytes_per_step": 24},
+            "gpu_launches": launches_per_step * args.steps * 2, "launches_per_step": launches_per_step,
+            "clocks": clocks, "losses_first": first_losses, "losses_last": final_losses, "top_ops": top_ops,
+            "lib": str(_lib.LIB_PATH)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

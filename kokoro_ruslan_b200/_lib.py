@@ -22,6 +22,7 @@ def lib() -> ctypes.CDLL:
                 "(there is no CPU / PyTorch fallback for the hot path)")
         _LIB = ctypes.CDLL(str(LIB_PATH))
         _LIB.kr_last_error.restype = ctypes.c_char_p
+        _LIB.kr_launch_count.restype = ctypes.c_longlong
     return _LIB
 
 
@@ -29,3 +30,8 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib().kr_last_error().decode(errors="replace")
         raise RuntimeError(f"libkokoro_b200 {what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    """Kernels launched by libkokoro_b200 so far (graph replays are not re-counted)."""
+    return int(lib().kr_launch_count())

@@ -24,9 +24,11 @@
   do {                                                      \
     cudaError_t e__ = cudaGetLastError();                   \
     if (e__ != cudaSuccess) { kr_set_error(cudaGetErrorString(e__)); return KR_ERR_CUDA; } \
+    kr_count_launch();                                      \
   } while (0)
 
 void kr_set_error(const char* msg);
+void kr_count_launch();
 
 typedef __nv_bfloat16 bf16;
 

@@ -361,7 +361,8 @@ extern "C" int kr_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
                             long long stride_r, int resid_mod, float alpha, int splits,
                             void* stream) {
   if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) { kr_set_error("kr_gemm_bf16: empty problem"); return KR_ERR_ARG; }
-  if ((K & 7) != 0) { kr_set_error("kr_gemm_bf16: K must be a multiple of 8"); return KR_ERR_ARG; }
+  // K needs no alignment: TMA zero-fills the out-of-bounds tail of the last K block (row strides
+  // are validated when the tensor maps are encoded).
   const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
   if (splits < 1) splits = 1;
   if (splits > total_kb) splits = total_kb;

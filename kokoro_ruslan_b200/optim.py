@@ -160,16 +160,19 @@ class FusedAdamW:
         self.lr_mult = [m for m, _ in hp]
         self.g_wd = torch.tensor([w for _, w in hp], dtype=torch.float32, device=dev)
         self.g_lr = torch.tensor([self.cfg.learning_rate * m for m in self.lr_mult], dtype=torch.float32, device=dev)
-        self._lr_host = torch.empty(len(hp), dtype=torch.float32).pin_memory() if torch.cuda.is_available() else None
+        # pinned ring: the async H2D of step n must not observe the host write of step n+1
+        self._lr_ring = torch.empty(64, len(hp), dtype=torch.float32).pin_memory() if torch.cuda.is_available() else None
+        self._lr_i = 0
         assert lib().kr_optim_ctrl_size() == 64
         self.ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
 
     # ------------------------------------------------------------------------------------------
     def set_lrs(self, lrs: List[float]) -> None:
         """Per-group learning rates for the next step (scheduler output)."""
-        for i, v in enumerate(lrs):
-            self._lr_host[i] = v
-        self.g_lr.copy_(self._lr_host, non_blocking=True)
+        slot = self._lr_ring[self._lr_i % self._lr_ring.shape[0]]
+        self._lr_i += 1
+        slot.copy_(torch.tensor(lrs, dtype=torch.float32))
+        self.g_lr.copy_(slot, non_blocking=True)
 
     def set_base_lr(self, base_lr: float) -> None:
         self.set_lrs([base_lr * m for m in self.lr_mult])

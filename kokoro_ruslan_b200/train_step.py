@@ -1,0 +1,304 @@
+"""One optimizer step of the acoustic model on one GPU (or one rank of a data-parallel job).
+
+Restates the reference's per-step order of operations (SURVEY.md §8 "Step algorithm";
+reference src/kokoro/training/trainer.py:2218-2294 adaptive stabilisation, :3181-3315
+``_execute_training_step``, training/runtime_policies.py:14-87 optimizer step, trainer.py:1519-1575
+scheduler) around the CUDA engine:
+
+    host batch (pinned) --H2D--> static device buffers
+      -> [CUDA graph A]  zero_grad, forward, fused losses (+ grads of the outputs), backward
+      -> [NCCL]          one all-reduce(SUM) of the flat gradient buffer      (world_size > 1 only)
+      -> [CUDA graph B]  grad norms -> step control -> fused clip+AdamW+EMA -> weight-norm projection
+      -> losses[6] stay on the device; the caller decides when to read them.
+
+There are no host synchronisations inside a step: the expanded length T' = max_b sum(d) and the
+long-sequence stabiliser are computed from the HOST copy of the batch before the H2D copy, the
+finite guards live in the device-side step control (non-finite gradients skip the step).
+Graphs are cached per (B, P, T, T') shape; unseen shapes run eagerly once (warm-up) and are then
+captured.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from ._lib import launch_count
+from .engine import AcousticEngine, LossConfig
+from .optim import FusedAdamW, OptimConfig
+from .params import ModelConfig
+
+BATCH_KEYS = ("phoneme_indices", "stress_indices", "phoneme_durations", "mel_specs", "pitches", "energies",
+              "stop_token_targets", "mel_lengths", "phoneme_lengths")
+
+
+@dataclass
+class ScheduleConfig:
+    """reference training/config.py:34-35,79-81 + trainer.py:691-775"""
+    total_steps: int = 100000          # optimizer steps in the run (epochs * steps/epoch)
+    use_warmup: bool = True
+    warmup_steps: int = 1200
+    warmup_start_lr_ratio: float = 0.01
+    max_lr_multiplier: float = 1.0
+    pct_start: float = 0.20
+    final_div_factor: float = 1.0e4
+
+
+class WarmupOneCycle:
+    """Per-group learning rate for optimizer step k, reproducing the reference's hand-rolled linear
+    warm-up followed by torch OneCycleLR(cos, two-phase) (trainer.py:691-775, 1519-1575).
+
+    Reference quirk kept: the LR the optimizer holds *before* the first scheduler call is
+    OneCycleLR's initial LR (max_lr / div_factor), so optimizer step 0 runs at the full base LR and
+    the warm-up ramp only starts with step 1.
+    """
+
+    def __init__(self, base_lr: float, mults: List[float], cfg: ScheduleConfig):
+        self.cfg = cfg
+        self.base_lr = base_lr
+        self.mults = list(mults)
+        total = max(1, int(cfg.total_steps))
+        warm = int(cfg.warmup_steps) if cfg.use_warmup else 0
+        if warm >= total:                       # _apply_warmup_guard, trainer.py:1638-1651
+            warm = max(0, total - 1)
+        self.warmup_steps = warm
+        self.onecycle_steps = max(1, total - warm)
+        self.max_lr = base_lr * cfg.max_lr_multiplier
+        self.div_factor = max(1.0, float(cfg.max_lr_multiplier)) if cfg.use_warmup else 25.0
+        self.warmup_start = base_lr * cfg.warmup_start_lr_ratio
+        self.warmup_target = min(base_lr, self.max_lr)
+        self.current_optimizer_step = 0         # scheduler calls made so far
+        self.sched_step = 0                     # OneCycleLR.last_epoch
+
+    def _onecycle(self, step: int) -> float:
+        """Base (mult = 1) OneCycleLR value at `step` (torch two-phase cosine)."""
+        total, pct = self.onecycle_steps, self.cfg.pct_start
+        initial = self.max_lr / self.div_factor
+        min_lr = initial / self.cfg.final_div_factor
+        end1 = float(pct * total) - 1.0
+        end2 = float(total) - 1.0
+
+        def cos_anneal(start, end, p):
+            return end + (start - end) / 2.0 * (math.cos(math.pi * p) + 1.0)
+
+        if step <= end1 or end1 >= end2:
+            p = step / end1 if end1 > 0 else 1.0
+            return cos_anneal(initial, self.max_lr, min(1.0, p))
+        p = (step - end1) / (end2 - end1)
+        return cos_anneal(self.max_lr, min_lr, min(1.0, p))
+
+    def lrs(self) -> List[float]:
+        """LR per group for the NEXT optimizer step."""
+        k = self.current_optimizer_step
+        if k == 0:
+            base = self._onecycle(0)
+        elif self.cfg.use_warmup and (k - 1) < self.warmup_steps:
+            prog = (k - 1) / self.warmup_steps
+            base = self.warmup_start + (self.warmup_target - self.warmup_start) * prog
+        else:
+            base = self._onecycle(self.sched_step)
+        return [base * m for m in self.mults]
+
+    def advance(self) -> None:
+        """Called after a successful optimizer step (runtime_policies.py:81-85)."""
+        k = self.current_optimizer_step
+        if self.cfg.use_warmup and k < self.warmup_steps:
+            pass
+        elif self.sched_step < self.onecycle_steps - 1:
+            self.sched_step += 1
+        self.current_optimizer_step += 1
+
+    def state_dict(self):
+        return {"current_optimizer_step": self.current_optimizer_step, "sched_step": self.sched_step}
+
+    def load_state_dict(self, sd):
+        self.current_optimizer_step = int(sd["current_optimizer_step"])
+        self.sched_step = int(sd["sched_step"])
+
+
+def adaptive_stabilisation(T: int, max_dur: int, base_clip: float, frame_thr: float = 1400.0,
+                           dur_thr: float = 150.0) -> Tuple[float, float]:
+    """(loss scale, clip norm) for long utterances, reference trainer.py:2218-2255: with
+    r = max(T/1400, max(d)/150) > 1 the loss is scaled by max(0.25, 1/r) and the clip becomes
+    max(0.05, 0.5/sqrt(r)) (never above the configured clip)."""
+    r = max(T / frame_thr, max_dur / dur_thr)
+    if r <= 1.0:
+        return 1.0, base_clip
+    return max(0.25, 1.0 / r), min(base_clip, max(0.05, 0.5 / math.sqrt(r)))
+
+
+@dataclass
+class _Staged:
+    """Static device buffers + graph for one batch shape."""
+    dev: Dict[str, torch.Tensor]
+    graph: Optional[torch.cuda.CUDAGraph] = None
+    losses: Optional[torch.Tensor] = None
+    launches: int = 0
+    warm: int = 0
+
+
+class TrainStep:
+    def __init__(self, model_cfg: Optional[ModelConfig] = None, optim_cfg: Optional[OptimConfig] = None,
+                 sched_cfg: Optional[ScheduleConfig] = None, loss_cfg: Optional[LossConfig] = None,
+                 device=None, use_graphs: bool = True, process_group=None, max_seq_cap: int = 2000):
+        self.engine = AcousticEngine(model_cfg or ModelConfig(), device, with_ema=True, loss_cfg=loss_cfg)
+        self.device = self.engine.device
+        self.opt = FusedAdamW(self.engine.store, optim_cfg or OptimConfig())
+        self.sched = WarmupOneCycle(self.opt.cfg.learning_rate, self.opt.lr_mult, sched_cfg or ScheduleConfig())
+        self.use_graphs = use_graphs
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self.max_seq_cap = max_seq_cap
+        self._staged: Dict[Tuple[int, int, int, int], _Staged] = {}
+        self._opt_graph: Optional[torch.cuda.CUDAGraph] = None
+        self._opt_warm = 0
+        self._opt_launches = 0
+        # [loss scale / world, clip norm] for the current step: one pinned ring slot -> one H2D copy
+        self._scal_ring = torch.empty(64, 2, dtype=torch.float32).pin_memory()
+        self._scal_i = 0
+        self._scal_dev = torch.tensor([1.0, self.opt.cfg.max_grad_norm], dtype=torch.float32, device=self.device)
+        self.loss_scale = self._scal_dev[0:1]
+        self.clip = self._scal_dev[1:2]
+        self.launches_last_step = 0
+        self.h2d_bytes_last_step = 0
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def store(self):
+        return self.engine.store
+
+    def load_state_dict(self, sd, strict: bool = True):
+        self.engine.store.load_state_dict(sd, strict=strict)
+
+    def state_dict(self):
+        return self.engine.store.ordered_state_dict()
+
+    # ------------------------------------------------------------------------------------------
+    def _cap(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """_cap_batch_sequence_dimensions, trainer.py:3365-3411 (cap T and P to 2000)."""
+        cap = self.max_seq_cap
+        T = batch["mel_specs"].shape[1]
+        P = batch["phoneme_indices"].shape[1]
+        if T <= cap and P <= cap:
+            return batch
+        out = dict(batch)
+        if T > cap:
+            for k in ("mel_specs", "pitches", "energies", "stop_token_targets"):
+                out[k] = batch[k][:, :cap].contiguous()
+            out["mel_lengths"] = batch["mel_lengths"].clamp(max=cap)
+        if P > cap:
+            for k in ("phoneme_indices", "stress_indices", "phoneme_durations"):
+                out[k] = batch[k][:, :cap].contiguous()
+            out["phoneme_lengths"] = batch["phoneme_lengths"].clamp(max=cap)
+        return out
+
+    def stage(self, batch: Dict[str, torch.Tensor]) -> Tuple[_Staged, Tuple[int, int, int, int]]:
+        """Host-side prologue: shape key, stabiliser scalars, async H2D into the static buffers."""
+        batch = self._cap(batch)
+        for k in BATCH_KEYS:
+            if k not in batch:
+                raise KeyError(f"batch is missing required key '{k}' (reference trainer.py:1262-1297)")
+        dur = batch["phoneme_durations"]
+        B, P = dur.shape
+        T = batch["mel_specs"].shape[1]
+        on_host = not dur.is_cuda
+        if on_host:
+            dsum = dur.clamp(min=0).sum(dim=1)
+            Tp = max(1, int(dsum.max()))
+            max_d = int(dur.max()) if dur.numel() else 0
+        else:   # device-resident batch (bench `value` leg): caller guarantees sum(d) == T
+            Tp, max_d = T, 0
+        Tp = max(Tp, 3)
+        key = (B, P, T, Tp)
+        st = self._staged.get(key)
+        if st is None:
+            dev = {}
+            for k in BATCH_KEYS:
+                src = batch[k]
+                dev[k] = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+            st = _Staged(dev=dev)
+            self._staged[key] = st
+        nbytes = 0
+        for k in BATCH_KEYS:
+            src = batch[k]
+            if src.data_ptr() != st.dev[k].data_ptr():
+                st.dev[k].copy_(src, non_blocking=True)
+                if not src.is_cuda:
+                    nbytes += src.numel() * src.element_size()
+        scale, clip = adaptive_stabilisation(T, max_d, self.opt.cfg.max_grad_norm)
+        slot = self._scal_ring[self._scal_i % self._scal_ring.shape[0]]
+        self._scal_i += 1
+        slot[0] = scale / self.world
+        slot[1] = clip
+        self._scal_dev.copy_(slot, non_blocking=True)
+        self.h2d_bytes_last_step = nbytes + 8
+        return st, key
+
+    # ------------------------------------------------------------------------------------------
+    def _fwd_bwd(self, d: Dict[str, torch.Tensor], Tp: int) -> torch.Tensor:
+        eng = self.engine
+        eng.zero_grad()
+        outs, ctx = eng.forward(d["phoneme_indices"], d["mel_specs"], d["phoneme_durations"], d["pitches"],
+                                d["energies"], d["stress_indices"], expanded_len=Tp)
+        losses, g = eng.losses(outs, d["mel_specs"], d["phoneme_durations"], d["stop_token_targets"],
+                               d["pitches"], d["energies"], d["mel_lengths"], d["phoneme_lengths"],
+                               loss_scale=self.loss_scale)
+        eng.backward(ctx, g)
+        return losses
+
+    def _run_fwd_bwd(self, st: _Staged, key) -> torch.Tensor:
+        Tp = key[3]
+        if not self.use_graphs:
+            n0 = launch_count()
+            losses = self._fwd_bwd(st.dev, Tp)
+            st.launches = launch_count() - n0
+            return losses
+        if st.graph is None:
+            if st.warm < 1:                       # eager warm-up (builds geometry tables, sets func attrs)
+                st.warm += 1
+                n0 = launch_count()
+                losses = self._fwd_bwd(st.dev, Tp)
+                st.launches = launch_count() - n0
+                return losses
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st.losses = self._fwd_bwd(st.dev, Tp)
+            st.graph = g
+        st.graph.replay()
+        return st.losses
+
+    def _run_optimizer(self) -> None:
+        if not self.use_graphs or (self._opt_graph is None and self._opt_warm < 1):
+            self._opt_warm += 1
+            n0 = launch_count()
+            self.opt.step(clip_override=self.clip)
+            self._opt_launches = launch_count() - n0
+            return
+        if self._opt_graph is None:
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.opt.step(clip_override=self.clip)
+            self._opt_graph = g
+        self._opt_graph.replay()
+
+    # ------------------------------------------------------------------------------------------
+    def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Full optimizer step on one micro-batch.  Returns the device tensor
+        losses[6] = (total, mel, duration, stop, pitch, energy), un-scaled."""
+        st, key = self.stage(batch)
+        self.opt.set_lrs(self.sched.lrs())
+        losses = self._run_fwd_bwd(st, key)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.engine.store.grads, op=dist.ReduceOp.SUM, group=self.pg)
+        self._run_optimizer()
+        self.sched.advance()
+        self.launches_last_step = st.launches + self._opt_launches + (1 if self.world > 1 else 0)
+        return losses

@@ -125,3 +125,52 @@ def test_ops_refuse_cpu_tensors():
     a = torch.zeros(128, 64, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError):
         ops.gemm(a, a, torch.zeros(128, 128))
+
+
+def test_warmup_onecycle_matches_reference_stepping():
+    """WarmupOneCycle == the reference's hand-rolled warm-up + torch OneCycleLR driven exactly as
+    trainer.py:1519-1575 drives it (incl. the full-LR first step)."""
+    import warnings
+    from kokoro_ruslan_b200.train_step import ScheduleConfig, WarmupOneCycle
+    total, warm, lr = 3000, 1200, 5e-5
+    p = [torch.nn.Parameter(torch.zeros(1))]
+    opt = torch.optim.SGD(p, lr=lr)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        s = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=lr, total_steps=total - warm, pct_start=0.2,
+                                                anneal_strategy="cos", cycle_momentum=False, div_factor=1.0,
+                                                final_div_factor=1e4)
+        w = WarmupOneCycle(lr, [1.0, 0.65], ScheduleConfig(total_steps=total))
+        cur = 0
+        for k in range(total + 20):
+            ref = opt.param_groups[0]["lr"]
+            got = w.lrs()
+            assert abs(got[0] - ref) <= 1e-12 + 1e-6 * ref, (k, got, ref)
+            assert abs(got[1] - 0.65 * ref) <= 1e-12 + 1e-6 * ref
+            if cur < warm:
+                opt.param_groups[0]["lr"] = lr * 0.01 + (lr - lr * 0.01) * cur / warm
+            elif s.last_epoch < total - warm - 1:
+                s.step()
+            cur += 1
+            w.advance()
+
+
+def test_oracle_and_product_agree_on_groups_and_preclip():
+    from kokoro_ruslan_b200.optim import OptimConfig, group_hparams, group_of, preclip_of
+    from kokoro_ruslan_b200.params import ModelConfig, param_specs
+    from oracle.train_step import GROUPS, param_group, spike_clip
+    hp = group_hparams(OptimConfig())
+    for (_, m, wd), (m2, wd2) in zip(GROUPS, hp):
+        assert (m, wd) == (m2, wd2)
+    for name, _ in param_specs(ModelConfig()):
+        assert group_of(name) == param_group(name), name
+        assert preclip_of(name, OptimConfig()) == spike_clip(name), name
+
+
+def test_adaptive_stabilisation_values():
+    from kokoro_ruslan_b200.train_step import adaptive_stabilisation
+    assert adaptive_stabilisation(800, 20, 1.5) == (1.0, 1.5)
+    s, c = adaptive_stabilisation(2000, 20, 1.5)          # SURVEY §8(d) config-4: 0.70 / 0.418
+    assert abs(s - 0.7) < 1e-6 and abs(c - 0.5 / (2000 / 1400) ** 0.5) < 1e-9
+    s, c = adaptive_stabilisation(800, 1200, 1.5)
+    assert s == 0.25 and abs(c - 0.5 / 8 ** 0.5) < 1e-9
