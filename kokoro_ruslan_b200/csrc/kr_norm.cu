@@ -242,30 +242,40 @@ __device__ __forceinline__ void store16_bf16(bf16* p, const float* v) {
   *reinterpret_cast<uint4*>(p + 8) = b;
 }
 
-// unit = (row, part, head); a warp handles 8 consecutive units per iteration (4 lanes each).
-struct PrepUnit { int row, part, col; bool valid; };
+// unit = (row, head) of ONE part (blockIdx.y); a warp handles 8 consecutive units per iteration
+// (4 lanes each) = one full 512-wide row when H = 8, i.e. 1 KB coalesced bf16 per warp access.
+struct PrepUnit { int row, col; bool valid; };
 __device__ __forceinline__ PrepUnit prep_unit(const PrepParams& p, long long w, int lane, long long total) {
   long long u = w * 8 + (lane >> 2);
   PrepUnit r;
   r.valid = u < total;
   if (!r.valid) u = total - 1;
   const int head = (int)(u % p.H);
-  const long long t = u / p.H;
-  r.part = (int)(t % p.n_parts);
-  r.row = (int)(t / p.n_parts);
+  r.row = (int)(u / p.H);
   r.col = head * 64 + (lane & 3) * 16;
   return r;
 }
 
-__global__ void qkv_prep_fwd_kernel(const PrepParams p) {
+__device__ __forceinline__ void load16_f32(const float* p, float* v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(p) + i);
+    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+  }
+}
+
+__global__ void __launch_bounds__(WARPS * 32) qkv_prep_fwd_kernel(const PrepParams p) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & 3;                // 16-element slice of the head
-  const long long total = (long long)p.N * p.n_parts * p.H;
+  const PrepPart& pp = p.part[blockIdx.y];
+  const long long total = (long long)p.N * p.H;
   const long long n_iter = (total + 7) / 8;
+  float gn[16];
+  load16_f32(pp.gain + sub * 16, gn);
+  const float sgn = (sub < 2) ? -1.f : 1.f;   // rot(x)[i] = -x[i+32] (i<32), +x[i-32] (i>=32)
   for (long long w = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); w < n_iter;
        w += (long long)gridDim.x * WARPS) {
     const PrepUnit un = prep_unit(p, w, lane, total);
-    const PrepPart& pp = p.part[un.part];
     float v[16];
     load16_bf16(reinterpret_cast<const bf16*>(pp.in) + (long long)un.row * pp.ld_in + un.col, v);
     float q = 0.f;
@@ -275,59 +285,55 @@ __global__ void qkv_prep_fwd_kernel(const PrepParams p) {
     q += __shfl_xor_sync(0xffffffffu, q, 2);
     const float rstd = rsqrtf(q * (1.f / 64.f) + p.eps);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = v[i] * rstd * __ldg(pp.gain + sub * 16 + i);
-    const int pos = un.row % p.S;
-    const float* ct = p.cos_t + (long long)pos * 32 + (sub & 1) * 16;
-    const float* st = p.sin_t + (long long)pos * 32 + (sub & 1) * 16;
-    const float sgn = (sub < 2) ? -1.f : 1.f;   // rot(x)[i] = -x[i+32] (i<32), +x[i-32] (i>=32)
+    for (int i = 0; i < 16; ++i) v[i] = v[i] * rstd * gn[i];
+    if (pp.rope) {
+      const int pos = un.row % p.S;
+      float ct[16], st[16];
+      load16_f32(p.cos_t + (long long)pos * 32 + (sub & 1) * 16, ct);
+      load16_f32(p.sin_t + (long long)pos * 32 + (sub & 1) * 16, st);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float other = __shfl_xor_sync(0xffffffffu, v[i], 2);
-      if (pp.rope) v[i] = v[i] * __ldg(ct + i) + sgn * other * __ldg(st + i);
+      for (int i = 0; i < 16; ++i) {
+        const float other = __shfl_xor_sync(0xffffffffu, v[i], 2);
+        v[i] = v[i] * ct[i] + sgn * other * st[i];
+      }
     }
     if (un.valid)
       store16_bf16(reinterpret_cast<bf16*>(pp.out) + (long long)un.row * pp.ld_out + un.col, v);
   }
 }
 
-__global__ void qkv_prep_bwd_kernel(const PrepParams p) {
-  __shared__ float sm[3][64];
-  for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) (&sm[0][0])[i] = 0.f;
+__global__ void __launch_bounds__(WARPS * 32) qkv_prep_bwd_kernel(const PrepParams p) {
+  __shared__ float sm[64];
+  if (threadIdx.x < 64) sm[threadIdx.x] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int sub = lane & 3;
-  float dg[3][16];
+  const PrepPart& pp = p.part[blockIdx.y];
+  float dg[16], gn[16];
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) dg[a][i] = 0.f;
-  const long long total = (long long)p.N * p.n_parts * p.H;
+  for (int i = 0; i < 16; ++i) dg[i] = 0.f;
+  load16_f32(pp.gain + sub * 16, gn);
+  const float sgn = (sub < 2) ? 1.f : -1.f;
+  const long long total = (long long)p.N * p.H;
   const long long n_iter = (total + 7) / 8;
   for (long long w = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); w < n_iter;
        w += (long long)gridDim.x * WARPS) {
     const PrepUnit un = prep_unit(p, w, lane, total);
-    const PrepPart& pp = p.part[un.part];
     float x[16], g[16];
     load16_bf16(reinterpret_cast<const bf16*>(pp.in) + (long long)un.row * pp.ld_in + un.col, x);
-    if (pp.grad_f32) {
-      const float* gp = reinterpret_cast<const float*>(pp.grad) + (long long)un.row * pp.ld_grad + un.col;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 f = ld4(gp + 4 * i);
-        g[4 * i] = f.x; g[4 * i + 1] = f.y; g[4 * i + 2] = f.z; g[4 * i + 3] = f.w;
-      }
-    } else {
+    if (pp.grad_f32)
+      load16_f32(reinterpret_cast<const float*>(pp.grad) + (long long)un.row * pp.ld_grad + un.col, g);
+    else
       load16_bf16(reinterpret_cast<const bf16*>(pp.grad) + (long long)un.row * pp.ld_grad + un.col, g);
-    }
-    {  // transpose of the rotation: dz[i] = dy[i] cos_i + (i<32 ? +dy[i+32] : -dy[i-32]) sin_i
+    if (pp.rope) {  // transpose of the rotation: dz[i] = dy[i] cos_i + (i<32 ? +dy[i+32] : -dy[i-32]) sin_i
       const int pos = un.row % p.S;
-      const float* ct = p.cos_t + (long long)pos * 32 + (sub & 1) * 16;
-      const float* st = p.sin_t + (long long)pos * 32 + (sub & 1) * 16;
-      const float sgn = (sub < 2) ? 1.f : -1.f;
+      float ct[16], st[16];
+      load16_f32(p.cos_t + (long long)pos * 32 + (sub & 1) * 16, ct);
+      load16_f32(p.sin_t + (long long)pos * 32 + (sub & 1) * 16, st);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float other = __shfl_xor_sync(0xffffffffu, g[i], 2);
-        if (pp.rope) g[i] = g[i] * __ldg(ct + i) + sgn * other * __ldg(st + i);
+        g[i] = g[i] * ct[i] + sgn * other * st[i];
       }
     }
     float q = 0.f;
@@ -341,11 +347,8 @@ __global__ void qkv_prep_bwd_kernel(const PrepParams p) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const float xh = x[i] * rstd;
-      const float dgi = g[i] * xh * vf;                // d gain
-      dg[0][i] += (un.part == 0) ? dgi : 0.f;
-      dg[1][i] += (un.part == 1) ? dgi : 0.f;
-      dg[2][i] += (un.part == 2) ? dgi : 0.f;
-      g[i] *= __ldg(pp.gain + sub * 16 + i);           // d xhat
+      dg[i] += g[i] * xh * vf;                         // d gain
+      g[i] *= gn[i];                                   // d xhat
       c += g[i] * xh;
       x[i] = xh;
     }
@@ -359,20 +362,15 @@ __global__ void qkv_prep_bwd_kernel(const PrepParams p) {
   }
   // lanes with equal `sub` hold the same 16 gain slots: fold across the 8 units, then block, then global
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float t = dg[a][i];
-      t += __shfl_xor_sync(0xffffffffu, t, 4);
-      t += __shfl_xor_sync(0xffffffffu, t, 8);
-      t += __shfl_xor_sync(0xffffffffu, t, 16);
-      if (lane < 4 && a < p.n_parts) atomicAdd(&sm[a][sub * 16 + i], t);
-    }
-  __syncthreads();
-  for (int i = threadIdx.x; i < p.n_parts * 64; i += blockDim.x) {
-    const int part = i / 64;
-    if (p.part[part].dgain != nullptr) atomicAdd(p.part[part].dgain + (i & 63), sm[part][i & 63]);
+  for (int i = 0; i < 16; ++i) {
+    float t = dg[i];
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 8);
+    t += __shfl_xor_sync(0xffffffffu, t, 16);
+    if (lane < 4) atomicAdd(&sm[sub * 16 + i], t);
   }
+  __syncthreads();
+  if (threadIdx.x < 64 && pp.dgain != nullptr) atomicAdd(pp.dgain + threadIdx.x, sm[threadIdx.x]);
 }
 
 int row_blocks(int N) { return (N + WARPS - 1) / WARPS; }
@@ -450,10 +448,11 @@ extern "C" int kr_qkv_prep_fwd(const void* in0, const void* in1, const void* in2
   }
   p.n_parts = n_parts; p.N = N; p.S = S; p.H = H; p.cos_t = cos_t; p.sin_t = sin_t; p.eps = FLT_EPSILON;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const long long total = ((long long)N * n_parts * H + 7) / 8;
+  const long long total = ((long long)N * H + 7) / 8;
   const long long nb_ = (total + WARPS - 1) / WARPS;
-  const int blocks = (int)(nb_ < kNumSMs * 8 ? nb_ : kNumSMs * 8);
-  qkv_prep_fwd_kernel<<<blocks, WARPS * 32, 0, st>>>(p);
+  const int per_part = kNumSMs * 8 / n_parts;
+  const int blocks = (int)(nb_ < per_part ? nb_ : per_part);
+  qkv_prep_fwd_kernel<<<dim3(blocks, n_parts), WARPS * 32, 0, st>>>(p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -481,10 +480,11 @@ extern "C" int kr_qkv_prep_bwd(const void* in0, const void* in1, const void* in2
   }
   p.n_parts = n_parts; p.N = N; p.S = S; p.H = H; p.cos_t = cos_t; p.sin_t = sin_t; p.eps = FLT_EPSILON;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const long long total = ((long long)N * n_parts * H + 7) / 8;
+  const long long total = ((long long)N * H + 7) / 8;
   const long long nb_ = (total + WARPS - 1) / WARPS;
-  const int blocks = (int)(nb_ < kNumSMs * 4 ? nb_ : kNumSMs * 4);
-  qkv_prep_bwd_kernel<<<blocks, WARPS * 32, 0, st>>>(p);
+  const int per_part = kNumSMs * 6 / n_parts;
+  const int blocks = (int)(nb_ < per_part ? nb_ : per_part);
+  qkv_prep_bwd_kernel<<<dim3(blocks, n_parts), WARPS * 32, 0, st>>>(p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -73,7 +73,7 @@ def _auto_splits(tiles: int, k_blocks: int, target: int = 296) -> int:
 
 class AcousticEngine:
     def __init__(self, cfg: ModelConfig, device=None, with_ema: bool = True,
-                 loss_cfg: Optional[LossConfig] = None):
+                 loss_cfg: Optional[LossConfig] = None, multi_stream: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("AcousticEngine needs a CUDA device: the hot path has no CPU fallback")
         self.cfg = cfg
@@ -84,7 +84,17 @@ class AcousticEngine:
         self.D = cfg.hidden_dim
         assert self.D == self.H * 64, "head_dim must be 64 (tcgen05 attention tiles)"
         self._geoms: Dict[Tuple[int, int], PadGeom] = {}
-        self.launches = 0
+        # Independent sub-graphs run on side streams (fork/join from the caller's stream, so the
+        # whole step is still one capturable DAG): weight-gradient GEMMs + bias column sums (off
+        # the critical path), the variance predictors, and the encoder backward, which is disjoint
+        # from the decoder backward because the length regulator detaches (utils/lengths.py:30).
+        self.multi_stream = multi_stream
+        self._side = {k: torch.cuda.Stream(device=self.device) for k in ("w0", "w1", "vp", "enc")} if multi_stream else {}
+        self._w_rr = 0
+        self._forked: List[torch.cuda.Stream] = []
+        # every tensor of a step stays referenced until the next step starts: memory is never
+        # recycled across streams inside a step (the caching allocator is per-stream ordered).
+        self._live: List[torch.Tensor] = []
 
     # ------------------------------------------------------------------------------------------
     def _geom(self, B: int, L: int) -> PadGeom:
@@ -94,21 +104,70 @@ class AcousticEngine:
         return self._geoms[key]
 
     def _empty(self, *shape, dtype=F32):
-        return torch.empty(*shape, dtype=dtype, device=self.device)
+        t = torch.empty(*shape, dtype=dtype, device=self.device)
+        self._live.append(t)
+        return t
 
     def _zeros(self, *shape, dtype=F32):
-        return torch.zeros(*shape, dtype=dtype, device=self.device)
+        t = torch.zeros(*shape, dtype=dtype, device=self.device)
+        self._live.append(t)
+        return t
+
+    # ------------------------------------------------------------------------------------------
+    # stream fork / join
+    # ------------------------------------------------------------------------------------------
+    class _On:
+        """`with eng._on("vp"):` runs the body on a side stream that first waits for everything
+        enqueued so far on the current stream; _join_all() makes the current stream wait for it."""
+
+        def __init__(self, eng, name):
+            self.eng, self.name, self.ctx = eng, name, None
+
+        def __enter__(self):
+            eng = self.eng
+            if not eng.multi_stream:
+                return self
+            side = eng._side[self.name]
+            side.wait_stream(torch.cuda.current_stream(eng.device))
+            if side not in eng._forked:
+                eng._forked.append(side)
+            self.ctx = torch.cuda.stream(side)
+            self.ctx.__enter__()
+            return self
+
+        def __exit__(self, *exc):
+            if self.ctx is not None:
+                self.ctx.__exit__(*exc)
+            return False
+
+    def _on(self, name: str):
+        return AcousticEngine._On(self, name)
+
+    def _on_w(self):
+        """Round-robin over the two weight-gradient streams."""
+        self._w_rr ^= 1
+        return self._on("w1" if self._w_rr else "w0")
+
+    def _join_all(self):
+        cur = torch.cuda.current_stream(self.device)
+        for side in self._forked:
+            cur.wait_stream(side)
+        self._forked = []
 
     # ------------------------------------------------------------------------------------------
     # linear helpers
     # ------------------------------------------------------------------------------------------
-    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, gw: torch.Tensor):
-        """gw[N_out, K_in] += dy[tok, N_out]^T x[tok, K_in] (split-K, fp32 atomics)."""
+    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, gw: torch.Tensor, gb: Optional[torch.Tensor] = None):
+        """gw[N_out, K_in] += dy[tok, N_out]^T x[tok, K_in] (split-K, fp32 atomics) and, when gb is
+        given, gb[N_out] += column sums of dy (bias gradient) — both on a weight-gradient stream."""
         n_out, k_in = gw.shape
         tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128)
         kb = (dy.shape[0] + 63) // 64
-        ops.gemm(dy, x, gw, a_mn_major=True, b_mn_major=True, accumulate=True,
-                 splits=_auto_splits(tiles, kb))
+        with self._on_w():
+            ops.gemm(dy, x, gw, a_mn_major=True, b_mn_major=True, accumulate=True,
+                     splits=_auto_splits(tiles, kb))
+            if gb is not None:
+                ops.colsum_bf16(dy, gb)
 
     # ------------------------------------------------------------------------------------------
     # attention sub-layer
@@ -159,8 +218,7 @@ class AcousticEngine:
         st, D, H = self.store, self.D, self.H
         N = B * S
         cross = mem is not None
-        self._wgrad(dout_bf, sv["o"], st.g(pre + "w_o.weight"))
-        ops.colsum_bf16(dout_bf, st.g(pre + "w_o.bias"))
+        self._wgrad(dout_bf, sv["o"], st.g(pre + "w_o.weight"), st.g(pre + "w_o.bias"))
         d_o = self._empty(N, D, dtype=BF16)
         ops.gemm(dout_bf, st.w(pre + "w_o.weight"), d_o, b_mn_major=True)
         dq = self._zeros(N, D)
@@ -225,14 +283,12 @@ class AcousticEngine:
         N = dout.shape[0]
         dy = self._empty(N, D, dtype=BF16)
         ops.rmsnorm_resid_bwd(dout, sv["y"], st.p(pre + "output_norm.weight"), dy, st.g(pre + "output_norm.weight"))
-        self._wgrad(dy, sv["u"], st.g(pre + "linear2.weight"))
-        ops.colsum_bf16(dy, st.g(pre + "linear2.bias"))
+        self._wgrad(dy, sv["u"], st.g(pre + "linear2.weight"), st.g(pre + "linear2.bias"))
         du = self._empty(N, ff, dtype=BF16)
         ops.gemm(dy, st.w(pre + "linear2.weight"), du, b_mn_major=True)
         dhff = self._empty(N, 2 * ff, dtype=BF16)
         ops.glu_bwd(du, sv["hff"], dhff)
-        self._wgrad(dhff, sv["h"], st.g(pre + "linear1.weight"))
-        ops.colsum_bf16(dhff, st.g(pre + "linear1.bias"))
+        self._wgrad(dhff, sv["h"], st.g(pre + "linear1.weight"), st.g(pre + "linear1.bias"))
         dh = self._empty(N, D)
         ops.gemm(dhff, st.w(pre + "linear1.weight"), dh, b_mn_major=True)
         dx = self._empty(N, D)
@@ -282,15 +338,15 @@ class AcousticEngine:
         dc2g = self._zeros(R + 2, Fv, dtype=BF16)
         ops.gn_bwd(dh2, sv["c2"], geom.row_group, geom.group_rows, sv["stats2"], gsum, st.p(pre + "norms.1.weight"),
                    st.p(pre + "norms.1.bias"), dc2g[1:R + 1], st.g(pre + "norms.1.weight"), st.g(pre + "norms.1.bias"))
-        self._wgrad(dc2g[1:R + 1], self._conv_view(sv["h1g"], R, Fv), st.g(pre + "conv_layers.1.weight"))
-        ops.colsum_bf16(dc2g[1:R + 1], st.g(pre + "conv_layers.1.bias"))
+        self._wgrad(dc2g[1:R + 1], self._conv_view(sv["h1g"], R, Fv), st.g(pre + "conv_layers.1.weight"),
+                    st.g(pre + "conv_layers.1.bias"))
         dh1 = self._empty(R, Fv, dtype=BF16)
         ops.gemm(self._conv_view(dc2g, R, Fv), st.conv_dgrad[pre + "conv_layers.1.weight"], dh1)
         dc1g = self._zeros(R + 2, Fv, dtype=BF16)
         ops.gn_bwd(dh1, sv["c1"], geom.row_group, geom.group_rows, sv["stats1"], gsum, st.p(pre + "norms.0.weight"),
                    st.p(pre + "norms.0.bias"), dc1g[1:R + 1], st.g(pre + "norms.0.weight"), st.g(pre + "norms.0.bias"))
-        self._wgrad(dc1g[1:R + 1], self._conv_view(sv["xg"], R, Cin), st.g(pre + "conv_layers.0.weight"))
-        ops.colsum_bf16(dc1g[1:R + 1], st.g(pre + "conv_layers.0.bias"))
+        self._wgrad(dc1g[1:R + 1], self._conv_view(sv["xg"], R, Cin), st.g(pre + "conv_layers.0.weight"),
+                    st.g(pre + "conv_layers.0.bias"))
         if not need_dx:
             return None
         dxp = self._empty(R, Cin)
@@ -311,6 +367,7 @@ class AcousticEngine:
         Ne, Nd = B * P, B * T
         va = "duration_adaptor.variance_adaptor."
         ctx: dict = {"B": B, "P": P, "T": T}
+        self._live = []          # previous step's tensors may be recycled from here on
         if expanded_len is None:
             # T' = max_b sum(d) (reference utils/lengths.py:44-47 also synchronises here)
             expanded_len = max(1, int(phoneme_durations.clamp(min=0).sum(dim=1).max().item()))
@@ -341,10 +398,11 @@ class AcousticEngine:
 
         # ---- variance adaptor ------------------------------------------------------------------
         gt = self._geom(B, P)
-        xg_tok = self._zeros(gt.R + 2, D, dtype=BF16)
-        ops.scatter_rows(enc, gt.row_of_tok, xg_tok[1:])
         sv_dur: dict = {}
-        log_dur = self._vp_fwd(va + "duration_predictor.", xg_tok, gt, text_pad, sv_dur)
+        with self._on("vp"):
+            xg_tok = self._zeros(gt.R + 2, D, dtype=BF16)
+            ops.scatter_rows(enc, gt.row_of_tok, xg_tok[1:])
+            log_dur = self._vp_fwd(va + "duration_predictor.", xg_tok, gt, text_pad, sv_dur)
 
         dur = phoneme_durations.contiguous()
         lr_idx = self._empty(B, Tp, dtype=torch.int32)
@@ -365,8 +423,10 @@ class AcousticEngine:
                          st.p(va + "pitch_embedding.weight"), st.p(va + "energy_embedding.weight"),
                          gf.row_of_tok, xg_frm[1:], mem, p_idx, e_idx, fmask_t, fmask_p, B, P, D, Tp, T)
         sv_pitch, sv_energy = {}, {}
-        pitch_pred = self._vp_fwd(va + "pitch_predictor.", xg_frm, gf, fmask_p, sv_pitch)
-        energy_pred = self._vp_fwd(va + "energy_predictor.", xg_frm, gf, fmask_p, sv_energy)
+        with self._on("vp"):
+            pitch_pred = self._vp_fwd(va + "pitch_predictor.", xg_frm, gf, fmask_p, sv_pitch)
+        with self._on("enc"):
+            energy_pred = self._vp_fwd(va + "energy_predictor.", xg_frm, gf, fmask_p, sv_energy)
         ctx.update(sv_dur=sv_dur, sv_pitch=sv_pitch, sv_energy=sv_energy, lr_idx=lr_idx, lengths=lengths,
                    mem=mem, p_idx=p_idx, e_idx=e_idx, fmask_t=fmask_t, fmask_p=fmask_p)
 
@@ -393,6 +453,7 @@ class AcousticEngine:
         stop = self._empty(Nd)
         ops.stop_head_fwd(yn, st.p("stop_token_predictor.weight"), st.p("stop_token_predictor.bias"), stop)
         ctx.update(melshift=melshift, dec_saved=dec_saved, dec_in=y, dn_mean=dn_mean, dn_rstd=dn_rstd, yn=yn)
+        self._join_all()
         outs = (mel_pred.view(B, T, cfg.mel_dim), log_dur, stop.view(B, T), pitch_pred, energy_pred)
         return outs, ctx
 
@@ -427,10 +488,32 @@ class AcousticEngine:
         Ne, Nd = B * P, B * T
         va = "duration_adaptor.variance_adaptor."
         dmel = g["mel"]                                     # [Nd, mel] bf16
-        # heads (the stop head reads a detached decoder output: weights only)
-        ops.stop_head_bwd(g["stop"], ctx["yn"], st.g("stop_token_predictor.weight"), st.g("stop_token_predictor.bias"))
-        self._wgrad(dmel, ctx["yn"], st.g("mel_projection_out.weight"))
-        ops.colsum_bf16(dmel, st.g("mel_projection_out.bias"))
+        gf, gt = self._geom(B, Tp), self._geom(B, P)
+        # (iv) duration loss -> duration predictor -> encoder -> embeddings: disjoint from the decoder
+        # backward (the expansion is detached), so it runs on its own stream.
+        with self._on("enc"):
+            denc = self._vp_bwd(va + "duration_predictor.", g["dur"], gt, ctx["sv_dur"], need_dx=True)
+            dx = self._empty(Ne, D)
+            dx_bf = self._empty(Ne, D, dtype=BF16)
+            ops.layernorm_bwd(denc, ctx["enc_in"], ctx["enc_mean"], ctx["enc_rstd"], st.p("encoder_norm.weight"),
+                              None, dx, dx_bf, st.g("encoder_norm.weight"), st.g("encoder_norm.bias"))
+            for i in reversed(range(cfg.n_encoder_layers)):
+                pre = f"transformer_encoder_layers.{i}."
+                s1, s2 = ctx["enc_saved"][i]
+                dx, dx_bf = self._ffn_bwd(pre + "ff.", dx, pre + "norm2.", cfg.encoder_ff_dim, s2)
+                dx, dx_bf = self._attn_bwd(pre + "self_attn.", dx, dx_bf, B, P, pre + "norm1.", False,
+                                           ctx["text_pad"], None, P, s1, None, False)
+            ops.embed_bwd(dx, ctx["idx"], ctx["stress"], st.g("text_embedding.weight"),
+                          st.g("stress_embedding.weight"))
+        # (iii) pitch / energy losses -> their predictors only (input is the detached expansion)
+        with self._on("vp"):
+            self._vp_bwd(va + "pitch_predictor.", g["pitch"], gf, ctx["sv_pitch"], need_dx=False)
+            self._vp_bwd(va + "energy_predictor.", g["energy"], gf, ctx["sv_energy"], need_dx=False)
+            # (ii) stop loss -> stop head only (it reads a detached decoder output)
+            ops.stop_head_bwd(g["stop"], ctx["yn"], st.g("stop_token_predictor.weight"),
+                              st.g("stop_token_predictor.bias"))
+        # (i) mel loss -> mel head -> decoder -> mel_projection_in and the pitch/energy embedding rows
+        self._wgrad(dmel, ctx["yn"], st.g("mel_projection_out.weight"), st.g("mel_projection_out.bias"))
         dyn = self._empty(Nd, D)
         ops.gemm(dmel, st.w("mel_projection_out.weight"), dyn, b_mn_major=True)
         dy = self._empty(Nd, D)
@@ -448,27 +531,11 @@ class AcousticEngine:
             first = False
             dy, dy_bf = self._attn_bwd(pre + "self_attn.", dy, dy_bf, B, T, pre + "norm1.", True, None, None, T,
                                        s1, None, False)
-        self._wgrad(dy_bf, ctx["melshift"], st.g("mel_projection_in.weight"))
-        ops.colsum_bf16(dy_bf, st.g("mel_projection_in.bias"))
+        self._wgrad(dy_bf, ctx["melshift"], st.g("mel_projection_in.weight"), st.g("mel_projection_in.bias"))
         # memory gradient reaches only the pitch / energy embedding rows (detached expansion)
         ops.adapt_bwd(dmem, ctx["p_idx"].view(-1), ctx["e_idx"].view(-1), st.g(va + "pitch_embedding.weight"),
                       st.g(va + "energy_embedding.weight"))
-        gf, gt = self._geom(B, Tp), self._geom(B, P)
-        self._vp_bwd(va + "pitch_predictor.", g["pitch"], gf, ctx["sv_pitch"], need_dx=False)
-        self._vp_bwd(va + "energy_predictor.", g["energy"], gf, ctx["sv_energy"], need_dx=False)
-        denc = self._vp_bwd(va + "duration_predictor.", g["dur"], gt, ctx["sv_dur"], need_dx=True)
-        # encoder: gradient from the duration loss only
-        dx = self._empty(Ne, D)
-        dx_bf = self._empty(Ne, D, dtype=BF16)
-        ops.layernorm_bwd(denc, ctx["enc_in"], ctx["enc_mean"], ctx["enc_rstd"], st.p("encoder_norm.weight"), None,
-                          dx, dx_bf, st.g("encoder_norm.weight"), st.g("encoder_norm.bias"))
-        for i in reversed(range(cfg.n_encoder_layers)):
-            pre = f"transformer_encoder_layers.{i}."
-            s1, s2 = ctx["enc_saved"][i]
-            dx, dx_bf = self._ffn_bwd(pre + "ff.", dx, pre + "norm2.", cfg.encoder_ff_dim, s2)
-            dx, dx_bf = self._attn_bwd(pre + "self_attn.", dx, dx_bf, B, P, pre + "norm1.", False, ctx["text_pad"],
-                                       None, P, s1, None, False)
-        ops.embed_bwd(dx, ctx["idx"], ctx["stress"], st.g("text_embedding.weight"), st.g("stress_embedding.weight"))
+        self._join_all()
 
     def zero_grad(self):
         self.store.grads.zero_()
