@@ -1,18 +1,28 @@
-// kr_gemm.cu — tcgen05 bf16 GEMM for every Linear on the acoustic-model hot path
-// (reference call sites: model/transformers.py:228,258-259,434 Q/K/V/out projections;
-//  transformers.py:105-111 GLU feed-forward; model/model.py:519-531,561 mel in/out projections).
+// kr_gemm.cu — persistent tcgen05 bf16 GEMM / implicit-GEMM conv1d for every dense contraction on
+// the hot path.
+//   acoustic model: model/transformers.py:228,258-259,434 (Q/K/V/out projections), :105-111 (GLU FFN),
+//                   model/model.py:519-531,561 (mel in/out projections), model/variance_predictor.py:46
+//                   (k=3 Conv1d) and all of their weight- / data-gradient GEMMs;
+//   vocoder:        inference/hifigan_vocoder.py:31-133 (dilated Conv1d / polyphase ConvTranspose1d).
 //
-//   C[b][M,N] (+)= alpha * sum_k A[b][m,k] * B[b][n,k]  (+ bias[n]) (+ resid[m % resid_mod, n])
+//   v      = alpha * sum_k A[b][m,k] * B[b][n,k] + bias[n] + resid[b][m % resid_mod, n]
+//   v      = v * beta + resid2[b][m, n]
+//   C [b][m,n] = v                      (bf16 | fp32 | fp32 atomic-add | not stored)
+//   C2[b][m,n] = bf16(leaky_relu(v, act_slope))          (optional second output)
 //
-// One CTA computes one 128 x BLOCK_N tile: warp 0 = TMA producer, warp 1 = single-thread
-// tcgen05.mma issuer (accumulator in TMEM), warps 2..5 = epilogue (tcgen05.ld -> registers ->
-// global).  Operands are staged by TMA into 128B-swizzled shared-memory tiles through a
-// KR_GEMM_STAGES-deep mbarrier ring.  A and B may each be K-major ([rows, K], K contiguous) or
-// MN-major ([K, rows], rows contiguous): the second form is what the weight-gradient
-// (dW = dY^T X) and data-gradient GEMMs read, so no transposed copies are materialised.
-// Split-K (grid.z) with an fp32 vector-atomic epilogue serves the weight gradients, which are
-// accumulated into the flat gradient buffer anyway.
+// Design (one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer: A/B tiles -> 128B-swizzled smem ring (STAGES deep, runs ahead across
+//               tile boundaries);
+//   warp 1      single-thread tcgen05.mma issuer; the fp32 accumulator lives in TMEM and is
+//               DOUBLE-BUFFERED (2 x BLOCK_N columns) so the MMAs of tile i+1 overlap the epilogue
+//               of tile i;
+//   warps 2..5  epilogue: tcgen05.ld -> registers -> fused bias / residual / activation -> global.
+// Operands may be K-major ([rows, K]) or MN-major ([K, rows]); the latter is what the weight- and
+// data-gradient GEMMs read in place.  Split-K uses the fp32 atomic epilogue.  In conv mode the A
+// operand is a channels-last activation [batch, rows(+zero halos), C_in]: K-block kb = (tap, 64-ch
+// chunk) is fetched at row offset tap*dilation — the im2col matrix is never materialised.
 #include "kr_common.cuh"
+#include "kokoro_b200.h"
 #include <stdio.h>
 
 namespace {
@@ -22,20 +32,25 @@ using namespace kr;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane group, alternating column chunks
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // producer warp + MMA warp + epilogue warps
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;         // per-warp 32x32 fp32 transpose buffer
+constexpr int SMEM_BUDGET = 192 * 1024;
 
-enum EpiMode { EPI_BF16 = 0, EPI_F32 = 1, EPI_ATOMIC_F32 = 2 };
+enum CMode { C_BF16 = 0, C_F32 = 1, C_ATOMIC_F32 = 2, C_NONE = 3 };
 
 struct GemmParams {
   int M, N, K;
-  int batch, splits, kb_per_split;
-  void* C;
-  long long ldc, c_batch_stride;
+  int batch, splits, kb_per_split, total_kb;
+  int m_tiles, n_tiles, total_tiles;
+  int conv_taps, conv_dil, conv_row0, conv_cin_blocks;
+  void* C; long long ldc, c_batch_stride; int c_mode;
+  bf16* C2; long long ldc2, c2_batch_stride; float act_slope;
   const float* bias;
-  const float* resid;
-  long long ldr, r_batch_stride;
-  int resid_mod;
-  float alpha;
+  const void* resid; int resid_bf16; long long ldr, r_batch_stride; int resid_mod;
+  const void* resid2; int resid2_bf16; long long ldr2, r2_batch_stride;
+  float alpha, beta;
+  int b_shared;   // B has no batch dimension (weights shared by every batch item)
 };
 
 template <int BLOCK_N>
@@ -43,13 +58,72 @@ struct SmemLayout {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N >= 128) ? 3 : 4;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int EPI_OFFSET = BAR_OFFSET + 512;
+  static constexpr int TOTAL = EPI_OFFSET + EPI_WARPS * EPI_STAGE_BYTES + 1024;  // + alignment slack
+  static constexpr int TMEM_COLS = BLOCK_N <= 64 ? 128 : (BLOCK_N <= 128 ? 256 : 512);  // power of two >= 2*BLOCK_N
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+struct TileCoord { int m_blk, n_blk, bz, split; };
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+  TileCoord t;
+  t.m_blk = tile % p.m_tiles;
+  int r = tile / p.m_tiles;
+  t.n_blk = r % p.n_tiles;
+  r /= p.n_tiles;
+  t.split = r % p.splits;
+  t.bz = r / p.splits;
+  return t;
+}
+
+__device__ __forceinline__ float4 add4(float4 v, const void* base, int is_bf16, long long off) {
+  if (is_bf16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(base) + off);
+    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
+    v.x += f0.x; v.y += f0.y; v.z += f1.x; v.w += f1.y;
+  } else {
+    const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    v.x += f.x; v.y += f.y; v.z += f.z; v.w += f.w;
+  }
+  return v;
+}
+
+// Rare path (N or a leading dimension not a multiple of 4, e.g. N = 80 with ld 80 is fine but N = 1
+// or odd strides are not): one element at a time, deliberately not inlined / unrolled so that it does
+// not bloat the instruction footprint of the hot epilogue.
+__device__ __noinline__ void epi_chunk_scalar(const GemmParams& p, const float* stg, int bz, int mw0, int nb,
+                                              int lane, bool use_bias, bool use_resid) {
+#pragma unroll 1
+  for (int e = lane; e < 32 * 32; e += 32) {
+    const int rr = e >> 5, cc = e & 31;
+    const int m = mw0 + rr, n = nb + cc;
+    if (m >= p.M || n >= p.N) continue;
+    float v = stg[rr * 32 + ((((cc >> 2) ^ (rr & 7)) << 2) | (cc & 3))] * p.alpha;
+    if (use_bias) v += __ldg(p.bias + n);
+    if (use_resid) {
+      const int rm = p.resid_mod > 0 ? (m % p.resid_mod) : m;
+      const long long off = (long long)bz * p.r_batch_stride + (long long)rm * p.ldr + n;
+      v += p.resid_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(p.resid)[off])
+                        : reinterpret_cast<const float*>(p.resid)[off];
+    }
+    if (p.resid2 != nullptr) {
+      const long long off = (long long)bz * p.r2_batch_stride + (long long)m * p.ldr2 + n;
+      v = v * p.beta + (p.resid2_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(p.resid2)[off])
+                                      : reinterpret_cast<const float*>(p.resid2)[off]);
+    }
+    const long long c_off = (long long)bz * p.c_batch_stride + (long long)m * p.ldc + n;
+    if (p.c_mode == C_BF16) reinterpret_cast<bf16*>(p.C)[c_off] = __float2bfloat16(v);
+    else if (p.c_mode == C_F32) reinterpret_cast<float*>(p.C)[c_off] = v;
+    else if (p.c_mode == C_ATOMIC_F32) atomicAdd(reinterpret_cast<float*>(p.C) + c_off, v);
+    if (p.C2 != nullptr)
+      p.C2[(long long)bz * p.c2_batch_stride + (long long)m * p.ldc2 + n] =
+          __float2bfloat16(v > 0.f ? v : v * p.act_slope);
+  }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
   using L = SmemLayout<BLOCK_N>;
@@ -60,19 +134,12 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BLOCK_M;
-  const int n0 = blockIdx.y * BLOCK_N;
-  const int bz = blockIdx.z / p.splits;
-  const int split = blockIdx.z % p.splits;
-  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int kb0 = split * p.kb_per_split;
-  const int kb1 = min(kb0 + p.kb_per_split, total_kb);
-  const int num_kb = kb1 - kb0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -81,11 +148,14 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], EPI_WARPS);   // one arrive per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BLOCK_N);
+    tmem_alloc(tmem_slot, L::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -96,27 +166,38 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * L::STAGE_BYTES;
-        uint8_t* sb = sa + L::A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        const int k = (kb0 + i) * BLOCK_K;
-        if (A_MN) {
+      int it = 0;  // global k-block counter (ring position)
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BLOCK_N;
+        const int kb0 = tc.split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
+        const int bzb = p.b_shared ? 0 : tc.bz;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          const int k = kb * BLOCK_K;
+          if (A_MN) {
 #pragma unroll
-          for (int j = 0; j < BLOCK_M / 64; ++j)
-            tma_load_3d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[s], m0 + j * 64, k, bz);
-        } else {
-          tma_load_3d(sa, &tmap_a, &full_bar[s], k, m0, bz);
-        }
-        if (B_MN) {
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_3d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[s], m0 + j * 64, k, tc.bz);
+          } else if (p.conv_taps > 0) {
+            const int tap = kb / p.conv_cin_blocks, cb = kb - tap * p.conv_cin_blocks;
+            tma_load_3d(sa, &tmap_a, &full_bar[s], cb * BLOCK_K, p.conv_row0 + m0 + tap * p.conv_dil, tc.bz);
+          } else {
+            tma_load_3d(sa, &tmap_a, &full_bar[s], k, m0, tc.bz);
+          }
+          if (B_MN) {
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_3d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[s], n0 + j * 64, k, bz);
-        } else {
-          tma_load_3d(sb, &tmap_b, &full_bar[s], k, n0, bz);
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_3d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[s], n0 + j * 64, k, bzb);
+          } else {
+            tma_load_3d(sb, &tmap_b, &full_bar[s], k, n0, bzb);
+          }
         }
       }
     }
@@ -128,151 +209,150 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // 64-wide MN chunks BLOCK_K*128 B apart, +2048 B per UMMA_K.
       constexpr uint32_t a_lbo = A_MN ? BLOCK_K * 128 : 16, b_lbo = B_MN ? BLOCK_K * 128 : 16;
       constexpr uint32_t a_kstep = A_MN ? 2048 : 32, b_kstep = B_MN ? 2048 : 32;
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, lt = 0;  // k-block counter, local tile counter
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int kb0 = tc.split * p.kb_per_split;
+        const int num_kb = min(kb0 + p.kb_per_split, p.total_kb) - kb0;
+        const int buf = lt & 1;
+        const uint32_t use = (uint32_t)(lt >> 1);
+        mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t sb = sa + L::A_BYTES;
+        const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
+        for (int i = 0; i < num_kb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint64_t da = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-          umma_bf16_ss(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+        umma_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
-    // ===== epilogue: warps 2..5 -> TMEM lane groups (warp % 4) =====
+    // ===== epilogue: warps 2..9; TMEM lane group = warp % 4, two warps per group split the column chunks =====
+    // Accumulator rows live one per thread (TMEM lane); every chunk of 32 columns is transposed through a
+    // per-warp swizzled smem buffer so that ALL global traffic (residual loads, output stores) is issued
+    // as 4 rows x 128 contiguous bytes per warp instruction.
     const int lg = warp & 3;
-    const int row = lg * 32 + lane;
-    const int m = m0 + row;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const bool row_ok = (m < p.M) && (num_kb > 0);
-    const long long c_off = (long long)bz * p.c_batch_stride + (long long)m * p.ldc;
-    const float* rrow = nullptr;
-    if (p.resid != nullptr && row_ok) {
-      const int rm = p.resid_mod > 0 ? (m % p.resid_mod) : m;
-      rrow = p.resid + (long long)bz * p.r_batch_stride + (long long)rm * p.ldr;
-    }
+    const int half = (warp - 2) >> 2;
+    float* stg = reinterpret_cast<float*>(smem + L::EPI_OFFSET + (warp - 2) * EPI_STAGE_BYTES);
+    const int crow = lane >> 3;          // coalesced layout: this lane handles row 4*i + crow ...
+    const int ccol = (lane & 7) * 4;     // ... columns [ccol, ccol + 4) of the chunk
+    const bool vec_ok = ((p.N & 3) == 0) && ((p.ldc & 3) == 0) && ((p.ldr & 3) == 0) && ((p.ldr2 & 3) == 0) &&
+                        ((p.ldc2 & 3) == 0);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int mw0 = tc.m_blk * BLOCK_M + lg * 32;   // first row of this warp's 32-row slab
+      const int n0 = tc.n_blk * BLOCK_N;
+      const int buf = lt & 1;
+      const uint32_t use = (uint32_t)(lt >> 1);
+      mbar_wait(&tmem_full_bar[buf], use & 1);
+      tc_fence_after();
+      const bool first_split = (tc.split == 0);
+      const bool use_bias = p.bias != nullptr && first_split;
+      const bool use_resid = p.resid != nullptr && first_split;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c * 32, r);
-      tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (row_ok && nb < p.N) {
-      float v[32];
+      for (int c = half; c < BLOCK_N / 32; c += 2) {
+        const int nb = n0 + c * 32;
+        if (nb >= p.N) break;                          // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + buf * BLOCK_N + (static_cast<uint32_t>(lg * 32) << 16) + c * 32, r);
+        tmem_ld_wait();
+        // row layout -> smem (16-byte slots XOR-swizzled by row: conflict-free both ways)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-      const bool full = (nb + 32 <= p.N);
-      if (p.bias != nullptr && (EPI != EPI_ATOMIC_F32 || split == 0)) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (full || nb + i < p.N) v[i] += __ldg(p.bias + nb + i);
-      }
-      if (rrow != nullptr) {
-        if (full) {
-#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+              make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        __syncwarp();
+        if (vec_ok) {
+          const int n = nb + ccol;
+          const bool col_ok = n < p.N;          // N % 4 == 0: a 4-group is all in or all out
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (use_bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll 4
           for (int i = 0; i < 8; ++i) {
-            const float4 q = *reinterpret_cast<const float4*>(rrow + nb + 4 * i);
-            v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            const int rr = 4 * i + crow;
+            const int m = mw0 + rr;
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+            if (m < p.M && col_ok) {
+              float4 v = make_float4(a4.x * p.alpha + b4.x, a4.y * p.alpha + b4.y, a4.z * p.alpha + b4.z,
+                                     a4.w * p.alpha + b4.w);
+              if (use_resid) {
+                const int rm = p.resid_mod > 0 ? (m % p.resid_mod) : m;
+                v = add4(v, p.resid, p.resid_bf16, (long long)tc.bz * p.r_batch_stride + (long long)rm * p.ldr + n);
+              }
+              if (p.resid2 != nullptr) {
+                v.x *= p.beta; v.y *= p.beta; v.z *= p.beta; v.w *= p.beta;
+                v = add4(v, p.resid2, p.resid2_bf16, (long long)tc.bz * p.r2_batch_stride + (long long)m * p.ldr2 + n);
+              }
+              const long long c_off = (long long)tc.bz * p.c_batch_stride + (long long)m * p.ldc + n;
+              if (p.c_mode == C_BF16)
+                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.C) + c_off) =
+                    make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+              else if (p.c_mode == C_F32)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + c_off) = v;
+              else if (p.c_mode == C_ATOMIC_F32)
+                atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + c_off), v);
+              if (p.C2 != nullptr) {
+                const float sl = p.act_slope;
+                v.x = v.x > 0.f ? v.x : v.x * sl; v.y = v.y > 0.f ? v.y : v.y * sl;
+                v.z = v.z > 0.f ? v.z : v.z * sl; v.w = v.w > 0.f ? v.w : v.w * sl;
+                *reinterpret_cast<uint2*>(p.C2 + (long long)tc.bz * p.c2_batch_stride + (long long)m * p.ldc2 + n) =
+                    make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+              }
+            }
           }
         } else {
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < p.N) v[i] += rrow[nb + i];
+          epi_chunk_scalar(p, stg, tc.bz, mw0, nb, lane, use_bias, use_resid);
         }
+        __syncwarp();  // staging buffer is reused by the next chunk; also reconverges for tcgen05.ld
       }
-      if (EPI == EPI_BF16) {
-        bf16* crow = reinterpret_cast<bf16*>(p.C) + c_off + nb;
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 q;
-            q.x = pack_bf16(v[8 * i], v[8 * i + 1]);
-            q.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-            q.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-            q.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-            *reinterpret_cast<uint4*>(crow + 8 * i) = q;
-          }
-        } else {
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < p.N) crow[i] = __float2bfloat16(v[i]);
-        }
-      } else if (EPI == EPI_F32) {
-        float* crow = reinterpret_cast<float*>(p.C) + c_off + nb;
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(crow + 4 * i) =
-                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < p.N) crow[i] = v[i];
-        }
-      } else {
-        float* crow = reinterpret_cast<float*>(p.C) + c_off + nb;
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            atomicAdd(reinterpret_cast<float4*>(crow + 4 * i),
-                      make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-        } else {
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < p.N) atomicAdd(crow + i, v[i]);
-        }
-      }
-      }
-      __syncwarp();  // reconverge before the next warp-aligned tcgen05.ld
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BLOCK_N);
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+template <int BLOCK_N, bool A_MN, bool B_MN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
   using L = SmemLayout<BLOCK_N>;
-  auto kern = kr_gemm_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+  auto kern = kr_gemm_kernel<BLOCK_N, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) { kr_set_error(cudaGetErrorString(e)); return KR_ERR_CUDA; }
     attr_set = true;
   }
-  dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, (p.N + BLOCK_N - 1) / BLOCK_N, p.batch * p.splits);
+  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
   kern<<<grid, GEMM_THREADS, L::TOTAL, st>>>(ta, tb, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
-int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                 cudaStream_t st) {
-  switch (epi) {
-    case EPI_BF16: return launch_gemm<BLOCK_N, A_MN, B_MN, EPI_BF16>(ta, tb, p, st);
-    case EPI_F32: return launch_gemm<BLOCK_N, A_MN, B_MN, EPI_F32>(ta, tb, p, st);
-    case EPI_ATOMIC_F32: return launch_gemm<BLOCK_N, A_MN, B_MN, EPI_ATOMIC_F32>(ta, tb, p, st);
-  }
-  kr_set_error("kr_gemm_bf16: bad epilogue mode");
-  return KR_ERR_ARG;
-}
-
 template <int BLOCK_N>
-int dispatch_major(int a_mn, int b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
-                   const GemmParams& p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return dispatch_epi<BLOCK_N, false, false>(epi, ta, tb, p, st);
-  if (!a_mn && b_mn) return dispatch_epi<BLOCK_N, false, true>(epi, ta, tb, p, st);
-  if (a_mn && !b_mn) return dispatch_epi<BLOCK_N, true, false>(epi, ta, tb, p, st);
-  return dispatch_epi<BLOCK_N, true, true>(epi, ta, tb, p, st);
+int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                   cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_gemm<BLOCK_N, false, false>(ta, tb, p, st);
+  if (!a_mn && b_mn) return launch_gemm<BLOCK_N, false, true>(ta, tb, p, st);
+  if (a_mn && !b_mn) return launch_gemm<BLOCK_N, true, false>(ta, tb, p, st);
+  return launch_gemm<BLOCK_N, true, true>(ta, tb, p, st);
 }
 
 }  // namespace
@@ -354,40 +434,93 @@ int kr_make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t heads, 
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
+extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
+  if (a == nullptr) { kr_set_error("kr_gemm_ex: null args"); return KR_ERR_ARG; }
+  const int M = a->M, N = a->N, K = a->K, batch = a->batch;
+  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) { kr_set_error("kr_gemm_ex: empty problem"); return KR_ERR_ARG; }
+  const bool conv = a->conv_taps > 0;
+  if (conv && (a->a_mn_major || (a->conv_cin % BLOCK_K) != 0 || K != a->conv_taps * a->conv_cin)) {
+    kr_set_error("kr_gemm_ex: conv mode needs K-major A, C_in % 64 == 0 and K == taps * C_in");
+    return KR_ERR_ARG;
+  }
+  const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  int splits = a->splits < 1 ? 1 : a->splits;
+  if (splits > total_kb) splits = total_kb;
+  if (splits > 1 && a->c_mode != C_ATOMIC_F32) { kr_set_error("kr_gemm_ex: split-K needs the atomic epilogue"); return KR_ERR_ARG; }
+  if (splits > 1 && (a->resid2 != nullptr || a->C2 != nullptr)) { kr_set_error("kr_gemm_ex: split-K cannot use resid2 / C2"); return KR_ERR_ARG; }
+  const int kb_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + kb_per_split - 1) / kb_per_split;  // no empty splits
+
+  // tile width: maximise (wave quantisation efficiency) x (MMA feed efficiency: narrow tiles re-read
+  // the 128-row A tile from shared memory more often per flop)
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  int block_n = 64;
+  {
+    const int cand[4] = {64, 128, 192, 256};
+    const double feed[4] = {0.67, 0.92, 0.97, 1.0};
+    double best = -1.0;
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cand[i];
+      if (bn > 64 && bn - 64 >= N) continue;                 // more than one empty 64-column group
+      const long long tiles = (long long)m_tiles * ((N + bn - 1) / bn) * batch * splits;
+      const long long rounds = (tiles + kNumSMs - 1) / kNumSMs;
+      const double used = (double)N / (double)(((N + bn - 1) / bn) * bn);
+      const double eff = (double)tiles / (double)(rounds * kNumSMs) * feed[i] * used;
+      if (eff > best + 1e-9) { best = eff; block_n = bn; }
+    }
+  }
+  if (a->force_block_n == 64 || a->force_block_n == 128 || a->force_block_n == 192 || a->force_block_n == 256)
+    block_n = a->force_block_n;
+
+  const bool b_shared = batch > 1 && a->stride_b == 0;
+  const uint64_t bstride_a = batch > 1 ? (uint64_t)a->stride_a
+                                       : (uint64_t)a->lda * (a->a_mn_major ? K : (conv ? a->a_rows : M));
+  const uint64_t bstride_b = (batch > 1 && !b_shared) ? (uint64_t)a->stride_b
+                                                      : (uint64_t)a->ldb * (a->b_mn_major ? K : N);
+  const int b_batch = b_shared ? 1 : batch;
+  CUtensorMap ta, tb;
+  int rc;
+  if (a->a_mn_major) rc = kr_make_tmap_bf16_3d(&ta, a->A, M, K, batch, a->lda, bstride_a, 64, BLOCK_K);
+  else if (conv)     rc = kr_make_tmap_bf16_3d(&ta, a->A, a->conv_cin, a->a_rows, batch, a->lda, bstride_a, BLOCK_K, BLOCK_M);
+  else               rc = kr_make_tmap_bf16_3d(&ta, a->A, K, M, batch, a->lda, bstride_a, BLOCK_K, BLOCK_M);
+  if (rc != KR_OK) return rc;
+  if (a->b_mn_major) rc = kr_make_tmap_bf16_3d(&tb, a->B, N, K, b_batch, a->ldb, bstride_b, 64, BLOCK_K);
+  else               rc = kr_make_tmap_bf16_3d(&tb, a->B, K, N, b_batch, a->ldb, bstride_b, BLOCK_K, block_n);
+  if (rc != KR_OK) return rc;
+
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.batch = batch; p.splits = splits; p.kb_per_split = kb_per_split;
+  p.total_kb = total_kb; p.m_tiles = m_tiles; p.n_tiles = (N + block_n - 1) / block_n;
+  p.total_tiles = p.m_tiles * p.n_tiles * batch * splits;
+  p.conv_taps = a->conv_taps; p.conv_dil = a->conv_dil; p.conv_row0 = a->conv_row0;
+  p.conv_cin_blocks = conv ? a->conv_cin / BLOCK_K : 0;
+  p.C = a->C; p.ldc = a->ldc; p.c_batch_stride = a->stride_c; p.c_mode = a->C != nullptr ? a->c_mode : C_NONE;
+  p.C2 = reinterpret_cast<bf16*>(a->C2); p.ldc2 = a->ldc2; p.c2_batch_stride = a->stride_c2; p.act_slope = a->act_slope;
+  p.bias = a->bias;
+  p.resid = a->resid; p.resid_bf16 = a->resid_dtype; p.ldr = a->ldr; p.r_batch_stride = a->stride_r; p.resid_mod = a->resid_mod;
+  p.resid2 = a->resid2; p.resid2_bf16 = a->resid2_dtype; p.ldr2 = a->ldr2; p.r2_batch_stride = a->stride_r2;
+  p.alpha = a->alpha; p.beta = a->beta;
+  p.b_shared = b_shared ? 1 : 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (block_n == 256) return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ta, tb, p, st);
+  if (block_n == 192) return dispatch_major<192>(a->a_mn_major, a->b_mn_major, ta, tb, p, st);
+  if (block_n == 128) return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ta, tb, p, st);
+  return dispatch_major<64>(a->a_mn_major, a->b_mn_major, ta, tb, p, st);
+}
+
 extern "C" int kr_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int batch,
                             long long lda, long long ldb, long long ldc, long long stride_a,
                             long long stride_b, long long stride_c, int a_mn_major, int b_mn_major,
                             int epi_mode, const float* bias, const float* resid, long long ldr,
                             long long stride_r, int resid_mod, float alpha, int splits,
                             void* stream) {
-  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) { kr_set_error("kr_gemm_bf16: empty problem"); return KR_ERR_ARG; }
-  // K needs no alignment: TMA zero-fills the out-of-bounds tail of the last K block (row strides
-  // are validated when the tensor maps are encoded).
-  const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
-  if (splits < 1) splits = 1;
-  if (splits > total_kb) splits = total_kb;
-  if (splits > 1 && epi_mode != EPI_ATOMIC_F32) { kr_set_error("kr_gemm_bf16: split-K needs the atomic epilogue"); return KR_ERR_ARG; }
-  int kb_per_split = (total_kb + splits - 1) / splits;
-  splits = (total_kb + kb_per_split - 1) / kb_per_split;  // no empty splits
-
-  const int block_n = (N > 64) ? 128 : 64;
-  const uint64_t bstride_a = batch > 1 ? (uint64_t)stride_a : (uint64_t)lda * (a_mn_major ? K : M);
-  const uint64_t bstride_b = batch > 1 ? (uint64_t)stride_b : (uint64_t)ldb * (b_mn_major ? K : N);
-  CUtensorMap ta, tb;
-  int rc;
-  if (a_mn_major) rc = kr_make_tmap_bf16_3d(&ta, A, M, K, batch, lda, bstride_a, 64, BLOCK_K);
-  else            rc = kr_make_tmap_bf16_3d(&ta, A, K, M, batch, lda, bstride_a, BLOCK_K, BLOCK_M);
-  if (rc != KR_OK) return rc;
-  if (b_mn_major) rc = kr_make_tmap_bf16_3d(&tb, B, N, K, batch, ldb, bstride_b, 64, BLOCK_K);
-  else            rc = kr_make_tmap_bf16_3d(&tb, B, K, N, batch, ldb, bstride_b, BLOCK_K, block_n);
-  if (rc != KR_OK) return rc;
-
-  GemmParams p;
-  p.M = M; p.N = N; p.K = K; p.batch = batch; p.splits = splits; p.kb_per_split = kb_per_split;
-  p.C = C; p.ldc = ldc; p.c_batch_stride = stride_c;
-  p.bias = bias; p.resid = resid; p.ldr = ldr; p.r_batch_stride = stride_r; p.resid_mod = resid_mod;
-  p.alpha = alpha;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 128) return dispatch_major<128>(a_mn_major, b_mn_major, epi_mode, ta, tb, p, st);
-  return dispatch_major<64>(a_mn_major, b_mn_major, epi_mode, ta, tb, p, st);
+  kr_gemm_args a{};
+  a.A = A; a.B = B; a.M = M; a.N = N; a.K = K; a.batch = batch;
+  a.lda = lda; a.ldb = ldb; a.stride_a = stride_a; a.stride_b = stride_b;
+  a.a_mn_major = a_mn_major; a.b_mn_major = b_mn_major;
+  a.alpha = alpha; a.beta = 1.f; a.bias = bias;
+  a.resid = resid; a.resid_dtype = 0; a.ldr = ldr; a.stride_r = stride_r; a.resid_mod = resid_mod;
+  a.C = C; a.c_mode = epi_mode; a.ldc = ldc; a.stride_c = stride_c;
+  a.splits = splits;
+  return kr_gemm_ex(&a, stream);
 }

@@ -86,6 +86,80 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major: boo
     return out
 
 
+class GemmArgs(ctypes.Structure):
+    """ctypes mirror of kr_gemm_args (include/kokoro_b200.h)."""
+    _fields_ = [("A", c_void_p), ("B", c_void_p),
+                ("M", c_int), ("N", c_int), ("K", c_int), ("batch", c_int),
+                ("lda", c_ll), ("ldb", c_ll), ("stride_a", c_ll), ("stride_b", c_ll),
+                ("a_mn_major", c_int), ("b_mn_major", c_int),
+                ("conv_taps", c_int), ("conv_dil", c_int), ("conv_row0", c_int), ("conv_cin", c_int),
+                ("a_rows", c_int),
+                ("alpha", c_float), ("beta", c_float),
+                ("bias", c_void_p),
+                ("resid", c_void_p), ("resid_dtype", c_int), ("ldr", c_ll), ("stride_r", c_ll), ("resid_mod", c_int),
+                ("resid2", c_void_p), ("resid2_dtype", c_int), ("ldr2", c_ll), ("stride_r2", c_ll),
+                ("C", c_void_p), ("c_mode", c_int), ("ldc", c_ll), ("stride_c", c_ll),
+                ("C2", c_void_p), ("ldc2", c_ll), ("stride_c2", c_ll), ("act_slope", c_float),
+                ("splits", c_int), ("force_block_n", c_int)]
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("kokoro_ruslan_b200 ops need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def conv1d_cl(x: torch.Tensor, w: torch.Tensor, *, rows: int, row0: int, taps: int, dil: int,
+              bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              out_act: Optional[torch.Tensor] = None, act_slope: float = 0.1,
+              resid: Optional[torch.Tensor] = None, resid2: Optional[torch.Tensor] = None,
+              beta: float = 1.0, block_n: int = 0) -> None:
+    """Implicit-GEMM conv1d on channels-last bf16 activations (tcgen05).
+
+    x: [B, rows_phys, C_in] bf16 with zero halos; output row m (0 <= m < rows) of item b reads
+    x[b, row0 + m + tap*dil, :] for tap in range(taps).  w: [N, taps*C_in] bf16 (tap-major K).
+    out / out_act / resid / resid2: [B, rows, N]-shaped *views* (any row / batch strides, unit
+    inner stride): v = acc + bias + resid; v = v*beta + resid2; out = v; out_act = lrelu(v).
+    """
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.dim() == 3 and w.dim() == 2
+    Bn, rows_phys, cin = x.shape
+    N, K = w.shape
+    assert K == taps * cin and x.stride(2) == 1 and w.stride(1) == 1
+    a = GemmArgs()
+    a.A, a.B = _p(x), _p(w)
+    a.M, a.N, a.K, a.batch = rows, N, K, Bn
+    a.lda, a.ldb, a.stride_a, a.stride_b = x.stride(1), w.stride(0), x.stride(0), 0
+    a.conv_taps, a.conv_dil, a.conv_row0, a.conv_cin, a.a_rows = taps, dil, row0, cin, rows_phys
+    a.alpha, a.beta = 1.0, beta
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+        a.bias = _p(bias)
+
+    def _view(t):
+        assert t.dim() == 3 and t.shape[0] == Bn and t.shape[1] >= rows and t.shape[2] == N and t.stride(2) == 1, \
+            (t.shape, t.stride(), rows, N)
+        return _p(t), t.stride(1), t.stride(0)
+    if resid is not None:
+        a.resid, a.ldr, a.stride_r = _view(resid)
+        a.resid_dtype = int(resid.dtype == torch.bfloat16)
+    if resid2 is not None:
+        a.resid2, a.ldr2, a.stride_r2 = _view(resid2)
+        a.resid2_dtype = int(resid2.dtype == torch.bfloat16)
+    if out is not None:
+        a.C, a.ldc, a.stride_c = _view(out)
+        a.c_mode = EPI_BF16 if out.dtype == torch.bfloat16 else EPI_F32
+    else:
+        a.c_mode = 3
+    if out_act is not None:
+        assert out_act.dtype == torch.bfloat16
+        a.C2, a.ldc2, a.stride_c2 = _view(out_act)
+        a.act_slope = act_slope
+    a.splits, a.force_block_n = 1, block_n
+    check(lib().kr_gemm_ex(ctypes.byref(a), _stream()), "kr_gemm_ex")
+
+
 def _heads_strides(t: torch.Tensor):
     """t is a [B, S, H, 64] bf16 view with unit inner stride and head stride 64."""
     assert t.dtype == torch.bfloat16 and t.dim() == 4 and t.shape[3] == 64

@@ -61,3 +61,58 @@ def test_gemm_batched():
     ops.gemm(A, B, out)
     ref = torch.einsum("bmk,bnk->bmn", A.float(), B.float())
     assert torch.allclose(out, ref, atol=2e-2, rtol=2e-3)
+
+
+@pytest.mark.parametrize("block_n", [0, 64, 128, 192, 256])
+def test_gemm_block_n_variants_persistent(block_n):
+    """Every tile width, many tiles per CTA (persistent loop + double-buffered TMEM accumulator)."""
+    import ctypes
+    from kokoro_ruslan_b200 import ops
+    from kokoro_ruslan_b200._lib import check, lib
+    M, N, K = 128 * 41 + 77, 1000, 704
+    A, B = _mk((M, K), 11), _mk((N, K), 12)
+    bias = torch.randn(N, device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    a = ops.GemmArgs()
+    a.A, a.B, a.M, a.N, a.K, a.batch = A.data_ptr(), B.data_ptr(), M, N, K, 1
+    a.lda, a.ldb, a.alpha, a.beta, a.bias = K, K, 1.0, 1.0, bias.data_ptr()
+    a.C, a.c_mode, a.ldc, a.splits, a.force_block_n = out.data_ptr(), 1, N, 1, block_n
+    check(lib().kr_gemm_ex(ctypes.byref(a), ops._stream()), "kr_gemm_ex")
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t() + bias
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-3, err
+
+
+@pytest.mark.parametrize("cin,cout,k,dil", [(128, 128, 3, 1), (128, 128, 7, 3), (64, 64, 11, 5), (512, 256, 7, 1),
+                                            (64, 200, 3, 1)])
+def test_conv1d_channels_last_implicit_gemm(cin, cout, k, dil):
+    """conv mode of the GEMM kernel vs torch conv1d (same bf16-rounded operands), with the fused
+    bias + bf16 residual + 1/3 scaling + second leaky-relu output used by the HiFi-GAN MRF."""
+    from kokoro_ruslan_b200 import ops
+    Bn, L, halo = 3, 1000, 32
+    pad = dil * (k - 1) // 2
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(Bn, cin, L, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(cout, generator=g)
+    res = (torch.randn(Bn, cout, L, generator=g)).to(torch.bfloat16)
+    acc = (torch.randn(Bn, cout, L, generator=g)).to(torch.bfloat16)
+    ref = torch.nn.functional.conv1d(x.float(), w.float(), bias, padding=pad, dilation=dil) + res.float()
+    ref2 = ref / 3.0 + acc.float()
+    xcl = torch.zeros(Bn, L + 2 * halo, cin, dtype=torch.bfloat16, device="cuda")
+    xcl[:, halo:halo + L] = x.permute(0, 2, 1).cuda()
+    wt = w.permute(0, 2, 1).reshape(cout, k * cin).contiguous().cuda()          # tap-major K
+    out = torch.zeros(Bn, L + 2 * halo, cout, dtype=torch.bfloat16, device="cuda")
+    act = torch.zeros_like(out)
+    rcl = res.permute(0, 2, 1).contiguous().cuda()
+    acl = acc.permute(0, 2, 1).contiguous().cuda()
+    ops.conv1d_cl(xcl, wt, rows=L, row0=halo - pad, taps=k, dil=dil, bias=bias.cuda(), out=out[:, halo:halo + L],
+                  out_act=act[:, halo:halo + L], act_slope=0.1, resid=rcl, resid2=acl, beta=1.0 / 3.0)
+    torch.cuda.synchronize()
+    got = out[:, halo:halo + L].float().cpu().permute(0, 2, 1)
+    scale = ref2.abs().max().item()
+    assert (got - ref2).abs().max().item() / scale < 1e-2
+    got_act = act[:, halo:halo + L].float().cpu().permute(0, 2, 1)
+    assert (got_act - torch.nn.functional.leaky_relu(ref2, 0.1)).abs().max().item() / scale < 1e-2
+    assert float(out[:, :halo].abs().max()) == 0.0 and float(out[:, halo + L:].abs().max()) == 0.0   # halos untouched

@@ -17,6 +17,7 @@ DOCS = {
     "kr_launch_count": "Number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches evidence).",
     "kr_device_cc": "Compute capability (major*10+minor) of the current device; 100 on B200.",
     "kr_gemm_bf16": "tcgen05 GEMM C[M,N] (+)= alpha*A[M,K]*B[N,K]^T (+bias[n]) (+resid[m % resid_mod, n]); bf16 operands staged by TMA, fp32 accumulation in TMEM. a_mn_major / b_mn_major select the [K,rows] storage that weight- and data-gradient GEMMs read in place. epi_mode 0 = bf16 store, 1 = fp32 store, 2 = fp32 atomic accumulate (split-K). Replaces every nn.Linear on the path: model/transformers.py:228,258-259,434 (Q/K/V/out projections), transformers.py:105-111 (GLU FFN), model/model.py:519-531,561 (mel in/out projections), and — through an overlapping-row view — the k=3 nn.Conv1d of model/variance_predictor.py:46.",
+    "kr_gemm_ex": "Persistent tcgen05 GEMM / implicit-GEMM conv1d with the full fused epilogue (see kr_gemm_args). kr_gemm_bf16 is the plain-argument subset. The conv mode replaces nn.Conv1d / nn.ConvTranspose1d (polyphase) of inference/hifigan_vocoder.py:31-133.",
     "kr_attn_fwd": "tcgen05 flash attention forward, head_dim 64, on token-major [B,S,H,64] bf16 tensors (q_ss/q_bs = seq/batch strides in elements). Causal and per-key padding (key_mask[B,Sk], 1 = masked) are predicates; lse[B,H,Sq] is the log2-domain log-sum-exp kept for the backward. Replaces F.scaled_dot_product_attention with the dense additive mask, model/transformers.py:299-316,393-398.",
     "kr_attn_bwd": "Flash attention backward: dq (fp32 [B,Sq,H,64], zeroed by the caller, atomically accumulated), dk/dv (bf16). delta[B,H,Sq] is scratch. Autograd of model/transformers.py:393-398.",
     "kr_stop_head_fwd": "Stop-token logits z[n] = x[n,:].w + b on the (detached) decoder output, model/model.py:562.",
@@ -55,7 +56,28 @@ DOCS = {
     "kr_conv_dgrad_shadow": "bf16 tap-reversed transpose of a tap-major conv weight: the B operand of the conv data-gradient GEMM.",
 }
 
-TYPES = """typedef struct CUstream_st* kr_stream_t; /* passed as void*: a cudaStream_t */"""
+STRUCTS = """/* Argument block of kr_gemm_ex (plain C, zero-initialise then fill what you need). */
+typedef struct kr_gemm_args {
+  const void* A;            /* bf16; logical [M,K]: stored [M,K] (K-major) or [K,M] if a_mn_major */
+  const void* B;            /* bf16; logical [N,K]: stored [N,K] (K-major) or [K,N] if b_mn_major */
+  int M, N, K, batch;       /* per batch item; stride_b == 0 with batch > 1 = weights shared */
+  long long lda, ldb, stride_a, stride_b;
+  int a_mn_major, b_mn_major;
+  /* implicit-GEMM conv1d on A: channels-last activation [batch, a_rows, conv_cin] that already
+   * contains its zero halos; K = conv_taps * conv_cin, K-block (tap, chunk) is read at row
+   * conv_row0 + m + tap * conv_dil.  conv_taps == 0: plain GEMM. */
+  int conv_taps, conv_dil, conv_row0, conv_cin, a_rows;
+  /* epilogue: v = alpha*acc + bias[n] + resid[m % resid_mod, n];  v = v*beta + resid2[m, n] */
+  float alpha, beta;
+  const float* bias;
+  const void* resid;  int resid_dtype;  long long ldr, stride_r;  int resid_mod;   /* dtype 0 f32, 1 bf16 */
+  const void* resid2; int resid2_dtype; long long ldr2, stride_r2;
+  void* C;  int c_mode; long long ldc, stride_c;    /* 0 bf16, 1 f32, 2 f32 atomic add, 3 none */
+  void* C2; long long ldc2, stride_c2; float act_slope;   /* optional bf16 leaky_relu(v, act_slope) */
+  int splits;               /* split-K (c_mode 2 only) */
+  int force_block_n;        /* 0 = heuristic, else 64 / 128 / 192 / 256 */
+} kr_gemm_args;
+"""
 
 
 def main():
@@ -84,7 +106,7 @@ def main():
            " */",
            "#ifndef KOKORO_B200_H", "#define KOKORO_B200_H", "", "#ifdef __cplusplus", 'extern "C" {', "#endif", "",
            "#define KR_OK 0", "#define KR_ERR_ARG (-1)", "#define KR_ERR_CUDA (-2)", "#define KR_ERR_TMAP (-3)",
-           "#define KR_ERR_UNSUPPORTED (-4)", ""]
+           "#define KR_ERR_UNSUPPORTED (-4)", "", STRUCTS]
     for fname, group in protos:
         out.append(f"/* ---- {fname} " + "-" * max(4, 88 - len(fname)) + " */")
         for ret, name, args in group:
