@@ -6,7 +6,7 @@
 //   vocoder:        inference/hifigan_vocoder.py:31-133 (dilated Conv1d / polyphase ConvTranspose1d).
 //
 //   v      = alpha * sum_k A[b][m,k] * B[b][n,k] + bias[n] + resid[b][m % resid_mod, n]
-//   v      = v * beta + resid2[b][m, n]
+//   v      = v * beta + resid2[b][m, n]        (beta is applied with or without resid2)
 //   C [b][m,n] = v                      (bf16 | fp32 | fp32 atomic-add | not stored)
 //   C2[b][m,n] = bf16(leaky_relu(v, act_slope))          (optional second output)
 //
@@ -107,10 +107,11 @@ __device__ __noinline__ void epi_chunk_scalar(const GemmParams& p, const float* 
       v += p.resid_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(p.resid)[off])
                         : reinterpret_cast<const float*>(p.resid)[off];
     }
+    v *= p.beta;
     if (p.resid2 != nullptr) {
       const long long off = (long long)bz * p.r2_batch_stride + (long long)m * p.ldr2 + n;
-      v = v * p.beta + (p.resid2_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(p.resid2)[off])
-                                      : reinterpret_cast<const float*>(p.resid2)[off]);
+      v += p.resid2_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(p.resid2)[off])
+                         : reinterpret_cast<const float*>(p.resid2)[off];
     }
     const long long c_off = (long long)bz * p.c_batch_stride + (long long)m * p.ldc + n;
     if (p.c_mode == C_BF16) reinterpret_cast<bf16*>(p.C)[c_off] = __float2bfloat16(v);
@@ -291,10 +292,9 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int rm = p.resid_mod > 0 ? (m % p.resid_mod) : m;
                 v = add4(v, p.resid, p.resid_bf16, (long long)tc.bz * p.r_batch_stride + (long long)rm * p.ldr + n);
               }
-              if (p.resid2 != nullptr) {
-                v.x *= p.beta; v.y *= p.beta; v.z *= p.beta; v.w *= p.beta;
+              v.x *= p.beta; v.y *= p.beta; v.z *= p.beta; v.w *= p.beta;
+              if (p.resid2 != nullptr)
                 v = add4(v, p.resid2, p.resid2_bf16, (long long)tc.bz * p.r2_batch_stride + (long long)m * p.ldr2 + n);
-              }
               const long long c_off = (long long)tc.bz * p.c_batch_stride + (long long)m * p.ldc + n;
               if (p.c_mode == C_BF16)
                 *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.C) + c_off) =

@@ -1,0 +1,39 @@
+"""HiFi-GAN oracle pinned to the golden audio generated from the live reference module."""
+import os
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_oracle_matches_reference_golden_audio():
+    from oracle import hifigan as oh
+    fix = np.load(os.path.join(HERE, "golden", "hifigan_small.npz"))
+    cfg = oh.HifiConfig()
+    sd = oh.seeded_state_dict(cfg, seed=0)
+    for case in ("a", "b"):
+        B, T, seed = [int(v) for v in fix[f"shape_{case}"]]
+        got = oh.generator_forward(sd, cfg, oh.synthetic_mel(B, T, seed))
+        want = torch.from_numpy(fix[f"audio_{case}"])
+        assert got.shape == want.shape == (B, 1, T * 256)
+        assert float((got - want).abs().max()) < 2e-6
+        assert float(want.abs().max()) < 0.99          # the fixture is not tanh-saturated
+
+
+def test_oracle_input_layouts():
+    from oracle import hifigan as oh
+    cfg = oh.HifiConfig()
+    sd = oh.seeded_state_dict(cfg, seed=0)
+    mel = oh.synthetic_mel(1, 12, 4)
+    a = oh.generator_forward(sd, cfg, mel)
+    assert torch.equal(a, oh.generator_forward(sd, cfg, mel.transpose(1, 2)))
+    assert torch.equal(a, oh.generator_forward(sd, cfg, mel[0].t()))
+
+
+def test_state_dict_layout():
+    from oracle import hifigan as oh
+    keys = oh.state_dict_keys(oh.HifiConfig())
+    assert len(keys) == 78 * 3                     # 78 weight-normed convs: bias, g, v
+    n = sum(int(np.prod(s)) for k, s in keys if not k.endswith("original0"))
+    assert n == 13926017                           # v + biases (g adds one scalar per out/in channel)

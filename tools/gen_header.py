@@ -18,6 +18,8 @@ DOCS = {
     "kr_device_cc": "Compute capability (major*10+minor) of the current device; 100 on B200.",
     "kr_gemm_bf16": "tcgen05 GEMM C[M,N] (+)= alpha*A[M,K]*B[N,K]^T (+bias[n]) (+resid[m % resid_mod, n]); bf16 operands staged by TMA, fp32 accumulation in TMEM. a_mn_major / b_mn_major select the [K,rows] storage that weight- and data-gradient GEMMs read in place. epi_mode 0 = bf16 store, 1 = fp32 store, 2 = fp32 atomic accumulate (split-K). Replaces every nn.Linear on the path: model/transformers.py:228,258-259,434 (Q/K/V/out projections), transformers.py:105-111 (GLU FFN), model/model.py:519-531,561 (mel in/out projections), and — through an overlapping-row view — the k=3 nn.Conv1d of model/variance_predictor.py:46.",
     "kr_gemm_ex": "Persistent tcgen05 GEMM / implicit-GEMM conv1d with the full fused epilogue (see kr_gemm_args). kr_gemm_bf16 is the plain-argument subset. The conv mode replaces nn.Conv1d / nn.ConvTranspose1d (polyphase) of inference/hifigan_vocoder.py:31-133.",
+    "kr_hifi_pack_mel": "Mel (B,80,T) [time_major=0] or (B,T,80) [1] fp32 -> channels-last bf16 [B, T+2*halo, c_phys] (interior rows; halos and padded channels stay zero): the input-layout handling of inference/hifigan_vocoder.py:112-117 fused with the bf16 cast.",
+    "kr_hifi_post_tanh": "conv_post (C -> 1, k=7, pad 3) + tanh on the channels-last activation, inference/hifigan_vocoder.py:131-132.",
     "kr_attn_fwd": "tcgen05 flash attention forward, head_dim 64, on token-major [B,S,H,64] bf16 tensors (q_ss/q_bs = seq/batch strides in elements). Causal and per-key padding (key_mask[B,Sk], 1 = masked) are predicates; lse[B,H,Sq] is the log2-domain log-sum-exp kept for the backward. Replaces F.scaled_dot_product_attention with the dense additive mask, model/transformers.py:299-316,393-398.",
     "kr_attn_bwd": "Flash attention backward: dq (fp32 [B,Sq,H,64], zeroed by the caller, atomically accumulated), dk/dv (bf16). delta[B,H,Sq] is scratch. Autograd of model/transformers.py:393-398.",
     "kr_stop_head_fwd": "Stop-token logits z[n] = x[n,:].w + b on the (detached) decoder output, model/model.py:562.",
