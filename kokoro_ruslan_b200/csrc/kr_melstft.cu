@@ -1,0 +1,124 @@
+// kr_melstft.cu — log-mel feature extraction (reference data/dataset.py:162-178, 672, 694-697:
+// torchaudio MelSpectrogram(sr 22050, n_fft 1024, win 1024, hop 256, f 0-8000, 80 mels, power 2,
+// periodic Hann, center=True / reflect pad, HTK scale, norm=None) followed by log(x + 1e-9);
+// SURVEY.md §9 S6).  HBM-bound: 1 KB of unique waveform in, 320 B out per frame.
+//
+// One CTA per frame: windowed, reflect-padded samples -> 1024-point Stockham radix-2 FFT in shared
+// memory (fp32, exact-table twiddles) -> |X|^2 for the 513 one-sided bins -> HTK triangular
+// filterbank (dense [n_mels, 513] weights, each warp reduces its filters with shuffles) -> log.
+#include "kr_common.cuh"
+#include <math_constants.h>
+
+namespace {
+using namespace kr;
+
+constexpr int NFFT = 1024, HOP = 256, NBINS = NFFT / 2 + 1, THREADS = 256;
+
+__global__ void wave_peak_kernel(const float* __restrict__ wav, const long long* __restrict__ lengths, long long n_max,
+                                 unsigned int* __restrict__ peak_bits) {
+  __shared__ float red[32];
+  const int b = blockIdx.y;
+  const long long n = lengths != nullptr ? lengths[b] : n_max;
+  const float* x = wav + (long long)b * n_max;
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  m = warp_max(m);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) red[w] = m;
+  __syncthreads();
+  if (w == 0) {
+    m = l < (blockDim.x >> 5) ? red[l] : 0.f;
+    m = warp_max(m);
+    if (l == 0) atomicMax(peak_bits + b, __float_as_uint(m));   // non-negative floats order like uints
+  }
+}
+
+__global__ void __launch_bounds__(THREADS)
+mel_stft_kernel(const float* __restrict__ wav, const long long* __restrict__ lengths, const float* __restrict__ peak,
+                const float* __restrict__ fb_t, float* __restrict__ out, long long n_max, int frames_max, int n_mels,
+                float log_eps) {
+  __shared__ float2 buf[2][NFFT];
+  __shared__ float2 tw[NFFT / 2];
+  __shared__ float pw[NBINS + 3];
+  const int f = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const long long n = lengths != nullptr ? lengths[b] : n_max;
+  const int n_frames = 1 + (int)(n / HOP);
+  float* orow = out + ((long long)b * n_mels) * frames_max + f;
+  if (f >= n_frames) {                       // padding frames of a ragged batch
+    for (int m = tid; m < n_mels; m += THREADS) orow[(long long)m * frames_max] = 0.f;
+    return;
+  }
+  const float* x = wav + (long long)b * n_max;
+  const float gain = peak != nullptr ? 1.f / (peak[b] + 1e-9f) : 1.f;
+  for (int i = tid; i < NFFT / 2; i += THREADS) {
+    float s, c;
+    sincospif(-2.f * (float)i / (float)NFFT, &s, &c);
+    tw[i] = make_float2(c, s);
+  }
+  // frame f covers padded samples [f*HOP, f*HOP + NFFT) = original [f*HOP - 512, ...) with reflection
+  for (int i = tid; i < NFFT; i += THREADS) {
+    long long j = (long long)f * HOP + i - NFFT / 2;
+    if (j < 0) j = -j;
+    if (j >= n) j = 2 * (n - 1) - j;
+    j = j < 0 ? 0 : j;
+    const float w = 0.5f - 0.5f * cospif(2.f * (float)i / (float)NFFT);     // periodic Hann
+    buf[0][i] = make_float2(x[j] * gain * w, 0.f);
+  }
+  __syncthreads();
+  int cur = 0;
+#pragma unroll 1
+  for (int p = 1; p < NFFT; p <<= 1) {       // Stockham autosort radix-2, natural order in and out
+    const int tw_stride = (NFFT / 2) / p;
+    for (int i = tid; i < NFFT / 2; i += THREADS) {
+      const int k = i & (p - 1);
+      const int j = ((i - k) << 1) + k;
+      const float2 w = tw[k * tw_stride];
+      const float2 u0 = buf[cur][i];
+      const float2 v = buf[cur][i + NFFT / 2];
+      const float2 u1 = make_float2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+      buf[cur ^ 1][j] = make_float2(u0.x + u1.x, u0.y + u1.y);
+      buf[cur ^ 1][j + p] = make_float2(u0.x - u1.x, u0.y - u1.y);
+    }
+    cur ^= 1;
+    __syncthreads();
+  }
+  for (int i = tid; i < NBINS; i += THREADS) {
+    const float2 z = buf[cur][i];
+    pw[i] = z.x * z.x + z.y * z.y;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int m = warp; m < n_mels; m += THREADS / 32) {
+    const float* frow = fb_t + (long long)m * NBINS;
+    float acc = 0.f;
+    for (int i = lane; i < NBINS; i += 32) acc = fmaf(pw[i], __ldg(frow + i), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) orow[(long long)m * frames_max] = logf(acc + log_eps);
+  }
+}
+
+}  // namespace
+
+extern "C" int kr_wave_peak(const float* wav, const long long* lengths, float* peak, int B, long long n_max, void* stream) {
+  if (B <= 0 || n_max <= 0) return KR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(peak, 0, sizeof(float) * B, st);
+  int bx = (int)((n_max + 256 * 8 - 1) / (256 * 8));
+  if (bx > 64) bx = 64;
+  wave_peak_kernel<<<dim3(bx, B), 256, 0, st>>>(wav, lengths, n_max, reinterpret_cast<unsigned int*>(peak));
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+extern "C" int kr_mel_stft(const float* wav, const long long* lengths, const float* peak, const float* fb_t, float* out,
+                           int B, long long n_max, int frames_max, int n_mels, int n_fft, int hop, float log_eps,
+                           void* stream) {
+  if (n_fft != NFFT || hop != HOP) { kr_set_error("kr_mel_stft: built for n_fft 1024 / hop 256"); return KR_ERR_UNSUPPORTED; }
+  if (B <= 0 || frames_max <= 0) return KR_OK;
+  if (n_max < NFFT / 2 + 1) { kr_set_error("kr_mel_stft: waveform shorter than the reflect padding"); return KR_ERR_ARG; }
+  mel_stft_kernel<<<dim3(frames_max, B), THREADS, 0, (cudaStream_t)stream>>>(wav, lengths, peak, fb_t, out, n_max,
+                                                                              frames_max, n_mels, log_eps);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}

@@ -461,3 +461,50 @@ extern "C" int kr_conv_dgrad_shadow(const float* w2, void* wd, int Co, int Ci, v
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// SpecAugment on the cross-attention memory (reference training/trainer.py:1578-1604, hooked in at
+// model/model.py:636-639): per sample, n_time spans of frames and n_feat spans of hidden dims are
+// zeroed.  The spans are drawn on the host (same torch.randint sequence as the reference) and live in
+// a small device table spans[B, n_time + n_feat, 2] = (start, length); the same call masks the memory
+// gradient in the backward pass (is_f32 = 1).
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <typename T>
+__global__ void spec_augment_kernel(T* __restrict__ x, const int* __restrict__ spans, int B, int Tn, int D, int n_time,
+                                    int n_feat) {
+  const int b = blockIdx.y;
+  const int* sp = spans + (long long)b * (n_time + n_feat) * 2;
+  T* xb = x + (long long)b * Tn * D;
+  const T zero = T(0.f);
+  // time spans: whole rows
+  for (int k = 0; k < n_time; ++k) {
+    const int t0 = sp[2 * k], tl = sp[2 * k + 1];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)tl * D;
+         e += (long long)gridDim.x * blockDim.x) {
+      const int t = t0 + (int)(e / D);
+      if (t < Tn) xb[(long long)t * D + (e % D)] = zero;
+    }
+  }
+  // feature spans: a few columns of every row
+  for (int k = 0; k < n_feat; ++k) {
+    const int f0 = sp[2 * (n_time + k)], fl = sp[2 * (n_time + k) + 1];
+    if (fl <= 0) continue;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)Tn * fl;
+         e += (long long)gridDim.x * blockDim.x) {
+      const int t = (int)(e / fl), f = f0 + (int)(e % fl);
+      if (f < D) xb[(long long)t * D + f] = zero;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int kr_spec_augment(void* x, int is_f32, const int* spans, int B, int T, int D, int n_time, int n_feat,
+                               void* stream) {
+  if (B <= 0 || T <= 0 || (n_time + n_feat) <= 0) return KR_OK;
+  dim3 grid(8, B);
+  if (is_f32) spec_augment_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, spans, B, T, D, n_time, n_feat);
+  else spec_augment_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((bf16*)x, spans, B, T, D, n_time, n_feat);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}

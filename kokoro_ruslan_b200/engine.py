@@ -95,6 +95,9 @@ class AcousticEngine:
         # every tensor of a step stays referenced until the next step starts: memory is never
         # recycled across streams inside a step (the caching allocator is per-stream ordered).
         self._live: List[torch.Tensor] = []
+        # SpecAugment span table (device int32 [B, n_time + n_feat, 2]) or None; see set_spec_augment()
+        self.spec_spans: Optional[torch.Tensor] = None
+        self.spec_n_time = self.spec_n_feat = 0
 
     # ------------------------------------------------------------------------------------------
     def _geom(self, B: int, L: int) -> PadGeom:
@@ -422,6 +425,8 @@ class AcousticEngine:
         ops.expand_adapt(enc, lr_idx, lengths, pitch_t, energy_t, flags, st.pitch_bins, st.energy_bins,
                          st.p(va + "pitch_embedding.weight"), st.p(va + "energy_embedding.weight"),
                          gf.row_of_tok, xg_frm[1:], mem, p_idx, e_idx, fmask_t, fmask_p, B, P, D, Tp, T)
+        if self.spec_spans is not None:      # SpecAugment on the decoder's cross-attention memory only
+            ops.spec_augment(mem.view(B, T, D), self.spec_spans, self.spec_n_time, self.spec_n_feat)
         sv_pitch, sv_energy = {}, {}
         with self._on("vp"):
             pitch_pred = self._vp_fwd(va + "pitch_predictor.", xg_frm, gf, fmask_p, sv_pitch)
@@ -533,9 +538,39 @@ class AcousticEngine:
                                        s1, None, False)
         self._wgrad(dy_bf, ctx["melshift"], st.g("mel_projection_in.weight"), st.g("mel_projection_in.bias"))
         # memory gradient reaches only the pitch / energy embedding rows (detached expansion)
+        if self.spec_spans is not None:
+            ops.spec_augment(dmem.view(B, T, D), self.spec_spans, self.spec_n_time, self.spec_n_feat)
         ops.adapt_bwd(dmem, ctx["p_idx"].view(-1), ctx["e_idx"].view(-1), st.g(va + "pitch_embedding.weight"),
                       st.g(va + "energy_embedding.weight"))
         self._join_all()
+
+    @staticmethod
+    def draw_spec_spans(B: int, T: int, D: int, time_mask_max: int = 5, freq_mask_max: int = 3,
+                        num_time_masks: int = 1, num_freq_masks: int = 2) -> torch.Tensor:
+        """Host-side span sampling with the SAME torch.randint call sequence as the reference's
+        KokoroTrainer._apply_spec_augment (trainer.py:1594-1603): int32 [B, nt + nf, 2] = (start, length)."""
+        spans = torch.zeros(B, num_time_masks + num_freq_masks, 2, dtype=torch.int32)
+        time_limit = max(1, min(time_mask_max, T // 4))
+        for b in range(B):
+            for k in range(num_time_masks):
+                t = int(torch.randint(0, time_limit, (1,)).item())
+                t0 = int(torch.randint(0, max(1, T - t), (1,)).item())
+                spans[b, k, 0], spans[b, k, 1] = t0, t
+            for k in range(num_freq_masks):
+                f = int(torch.randint(0, max(1, freq_mask_max), (1,)).item())
+                f0 = int(torch.randint(0, max(1, D - f), (1,)).item())
+                spans[b, num_time_masks + k, 0], spans[b, num_time_masks + k, 1] = f0, f
+        return spans
+
+    def set_spec_augment(self, spans: Optional[torch.Tensor], n_time: int = 1, n_feat: int = 2) -> None:
+        """spans: host or device int32 [B, n_time + n_feat, 2], or None to disable."""
+        if spans is None:
+            self.spec_spans = None
+            return
+        if self.spec_spans is None or self.spec_spans.shape != spans.shape:
+            self.spec_spans = torch.empty(spans.shape, dtype=torch.int32, device=self.device)
+        self.spec_spans.copy_(spans, non_blocking=True)
+        self.spec_n_time, self.spec_n_feat = n_time, n_feat
 
     def zero_grad(self):
         self.store.grads.zero_()

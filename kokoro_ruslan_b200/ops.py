@@ -396,3 +396,10 @@ def losses_fwd_bwd(mel_pred, mel_tgt, dur_pred, dur_tgt, stop_pred, stop_tgt, pi
                                   c_float(w_pitch), c_float(w_energy), c_float(pos_weight), c_float(delta_var),
                                   _ptr(loss_scale), _ptr(acc), _ptr(losses), _ptr(dmel), _ptr(ddur), _ptr(dstop),
                                   _ptr(dpitch), _ptr(denergy), _stream()), "kr_losses_fwd_bwd")
+
+
+def spec_augment(x, spans, n_time: int, n_feat: int):
+    """x: [B, T, D] bf16 or fp32 (in place); spans: int32 [B, n_time + n_feat, 2]."""
+    B, T, D = x.shape
+    check(lib().kr_spec_augment(_ptr(x), c_int(int(x.dtype == torch.float32)), _ptr(spans), c_int(B), c_int(T),
+                                c_int(D), c_int(n_time), c_int(n_feat), _stream()), "kr_spec_augment")

@@ -296,8 +296,8 @@ class TrainStep:
         self.opt.set_lrs(self.sched.lrs())
         losses = self._run_fwd_bwd(st, key)
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.engine.store.grads, op=dist.ReduceOp.SUM, group=self.pg)
+            from .parallel import all_reduce_gradients
+            all_reduce_gradients(self.engine.store.grads, self.pg)
         self._run_optimizer()
         self.sched.advance()
         self.launches_last_step = st.launches + self._opt_launches + (1 if self.world > 1 else 0)

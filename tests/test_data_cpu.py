@@ -1,0 +1,112 @@
+"""collate_fn / batch samplers vs the reference's own outputs (golden) and its unit-test properties
+(reference tests/unit/test_dynamic_frame_batch_sampler.py: budget :37, coverage :58-79, heavy-batch
+spreading :127-213)."""
+import json
+import os
+import random
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class DummyDataset:
+    def __init__(self, lengths):
+        self.samples = [{"audio_length": int(v)} for v in lengths]
+
+    def __len__(self):
+        return len(self.samples)
+
+
+def _fix():
+    return json.load(open(os.path.join(HERE, "golden", "sampler.json")))["cases"]
+
+
+def test_samplers_reproduce_reference_batches():
+    from kokoro_ruslan_b200.data import DynamicFrameBatchSampler, LengthBasedBatchSampler
+    for case in _fix():
+        random.seed(case["seed"])
+        ds = DummyDataset(case["lengths"])
+        if case["kind"] == "dynamic":
+            s = DynamicFrameBatchSampler(ds, **case["kwargs"])
+            assert s.batches == case["init"]
+            assert list(iter(s)) == case["epoch"]
+            assert len(s) == len(case["epoch"])
+        else:
+            s = LengthBasedBatchSampler(ds, **case["kwargs"])
+            assert list(iter(s)) == case["epoch"]
+
+
+def test_frame_budget_and_coverage():
+    from kokoro_ruslan_b200.data import DynamicFrameBatchSampler
+    case = _fix()[0]
+    random.seed(5)
+    ds = DummyDataset(case["lengths"])
+    s = DynamicFrameBatchSampler(ds, max_frames=8000, min_batch_size=1, max_batch_size=32, drop_last=False, shuffle=True)
+    seen = []
+    for b in s:
+        longest = max(case["lengths"][i] for i in b)
+        assert len(b) == 1 or len(b) * longest <= 8000
+        assert len(b) <= 32
+        seen += b
+    assert sorted(seen) == list(range(len(ds)))
+    costs = [max(case["lengths"][i] for i in b) * len(b) for b in s.batches]
+    assert costs[0] == max(costs)                       # heaviest batch first, anchors spread out
+    n_anchor = max(2, int(len(costs) ** 0.5))
+    heavy_pos = sorted(sorted(range(len(costs)), key=costs.__getitem__, reverse=True)[:n_anchor])
+    gaps = [b - a for a, b in zip(heavy_pos, heavy_pos[1:])]
+    assert min(gaps) >= len(costs) // n_anchor - 1
+
+
+def test_distributed_sampler_partitions_identically_on_all_ranks():
+    from kokoro_ruslan_b200.data import DistributedBatchSampler, DynamicFrameBatchSampler
+    lens = _fix()[0]["lengths"]
+    per_rank = []
+    for rank in range(4):
+        random.seed(1000 + rank)                         # ranks start from DIFFERENT global RNG states
+        base = DynamicFrameBatchSampler(DummyDataset(lens), max_frames=8000, min_batch_size=1, shuffle=True)
+        d = DistributedBatchSampler(base, rank, 4, seed=42)
+        d.set_epoch(3)
+        per_rank.append(list(iter(d)))
+        assert len(per_rank[-1]) == len(d)
+    assert len({len(p) for p in per_rank}) == 1          # equal step counts
+    flat = [tuple(b) for p in per_rank for b in p]
+    assert len(set(flat)) == len(flat)                   # disjoint batches
+    random.seed(42 + 3)
+    ref = list(iter(DynamicFrameBatchSampler(DummyDataset(lens), max_frames=8000, min_batch_size=1, shuffle=True)))
+    # NB the constructor already consumed randomness once: rebuild exactly as the wrapper does
+    base = DynamicFrameBatchSampler(DummyDataset(lens), max_frames=8000, min_batch_size=1, shuffle=True)
+    random.seed(42 + 3)
+    ref = list(iter(base))
+    usable = len(ref) // 4 * 4
+    for rank in range(4):
+        assert per_rank[rank] == ref[rank:usable:4]
+
+
+def test_collate_contract():
+    from kokoro_ruslan_b200.data import build_stop_token_targets, collate_fn
+    g = torch.Generator().manual_seed(0)
+    items = []
+    for T, P in [(50, 7), (31, 12), (64, 3)]:
+        items.append({"mel_spec": torch.randn(80, T, generator=g), "pitch": torch.rand(T, generator=g),
+                      "energy": torch.rand(T, generator=g), "stop_token_targets": build_stop_token_targets(T, 6),
+                      "phoneme_indices": torch.randint(1, 59, (P,), generator=g),
+                      "phoneme_durations": torch.randint(1, 9, (P,), generator=g),
+                      "stress_indices": torch.randint(0, 3, (P,), generator=g), "mel_length": T, "phoneme_length": P,
+                      "text": f"t{T}", "audio_file": f"a{T}.wav"})
+    out = collate_fn(items, pin_memory=False)
+    assert set(out) == {"mel_specs", "phoneme_indices", "stress_indices", "phoneme_durations", "stop_token_targets",
+                        "pitches", "energies", "mel_lengths", "phoneme_lengths", "texts", "audio_files"}
+    assert out["mel_specs"].shape == (3, 64, 80) and out["mel_specs"].dtype == torch.float32
+    assert out["phoneme_indices"].shape == (3, 12) and out["phoneme_indices"].dtype == torch.long
+    assert out["mel_lengths"].tolist() == [50, 31, 64] and out["phoneme_lengths"].tolist() == [7, 12, 3]
+    for i, it in enumerate(items):
+        T, P = it["mel_length"], it["phoneme_length"]
+        assert torch.equal(out["mel_specs"][i, :T], it["mel_spec"].t())
+        assert float(out["mel_specs"][i, T:].abs().sum()) == 0.0
+        assert torch.equal(out["phoneme_durations"][i, :P], it["phoneme_durations"])
+        assert int(out["phoneme_durations"][i, P:].sum()) == 0
+        assert torch.equal(out["stop_token_targets"][i, :T], it["stop_token_targets"])
+    assert out["texts"] == ["t50", "t31", "t64"]
+    assert build_stop_token_targets(5, 2).tolist() == [0.0, 0.0, 0.25, 0.5, 1.0]

@@ -20,6 +20,9 @@ DOCS = {
     "kr_gemm_ex": "Persistent tcgen05 GEMM / implicit-GEMM conv1d with the full fused epilogue (see kr_gemm_args). kr_gemm_bf16 is the plain-argument subset. The conv mode replaces nn.Conv1d / nn.ConvTranspose1d (polyphase) of inference/hifigan_vocoder.py:31-133.",
     "kr_hifi_pack_mel": "Mel (B,80,T) [time_major=0] or (B,T,80) [1] fp32 -> channels-last bf16 [B, T+2*halo, c_phys] (interior rows; halos and padded channels stay zero): the input-layout handling of inference/hifigan_vocoder.py:112-117 fused with the bf16 cast.",
     "kr_hifi_post_tanh": "conv_post (C -> 1, k=7, pad 3) + tanh on the channels-last activation, inference/hifigan_vocoder.py:131-132.",
+    "kr_wave_peak": "peak[b] = max |wav[b, :len[b]]| — the peak normalisation x / (max|x| + 1e-9) of data/dataset.py:672 is applied inside kr_mel_stft.",
+    "kr_mel_stft": "Log-mel features out[B, n_mels, frames_max] = log(melfb(|STFT|^2) + log_eps): reflect pad 512, periodic Hann 1024, hop 256, 513 bins, dense filterbank fb_t[n_mels, 513] (HTK, norm=None); frames beyond 1 + len//256 are zero. Replaces torchaudio.transforms.MelSpectrogram + log of data/dataset.py:162-178,694-697.",
+    "kr_spec_augment": "SpecAugment on the cross-attention memory (bf16) or its gradient (fp32): zeroes the per-sample frame / hidden-dim spans in spans[B, n_time+n_feat, 2] = (start, length). training/trainer.py:1578-1604, applied at model/model.py:636-639.",
     "kr_attn_fwd": "tcgen05 flash attention forward, head_dim 64, on token-major [B,S,H,64] bf16 tensors (q_ss/q_bs = seq/batch strides in elements). Causal and per-key padding (key_mask[B,Sk], 1 = masked) are predicates; lse[B,H,Sq] is the log2-domain log-sum-exp kept for the backward. Replaces F.scaled_dot_product_attention with the dense additive mask, model/transformers.py:299-316,393-398.",
     "kr_attn_bwd": "Flash attention backward: dq (fp32 [B,Sq,H,64], zeroed by the caller, atomically accumulated), dk/dv (bf16). delta[B,H,Sq] is scratch. Autograd of model/transformers.py:393-398.",
     "kr_stop_head_fwd": "Stop-token logits z[n] = x[n,:].w + b on the (detached) decoder output, model/model.py:562.",
