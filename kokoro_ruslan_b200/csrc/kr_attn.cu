@@ -156,9 +156,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
     for (int c = 0; c < 4; ++c) mw[c] = mask_words[st * 4 + c];
 
-    // pass 1: row max (log2 domain)
-    float mx = -INFINITY;
-#pragma unroll 1
+    // S row (128 keys) is read from TMEM ONCE into registers (TMEM read bandwidth, 64 B/clk/SM, is the
+    // scarce resource of this loop); masking folded in as -inf
+    float sv[128];
+#pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_S + t_lane + c * 32, r);
@@ -167,32 +168,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int i = 0; i < 32; ++i) {
         const int key = j * TK + c * 32 + i;
         const bool masked = ((mw[c] >> i) & 1u) || (CAUSAL && key > qi);
-        const float s = masked ? -INFINITY : __uint_as_float(r[i]) * p.scale_log2;
-        mx = fmaxf(mx, s);
+        sv[c * 32 + i] = masked ? -INFINITY : __uint_as_float(r[i]) * p.scale_log2;
       }
     }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 128; ++i) mx = fmaxf(mx, sv[i]);
     const float m_new = fmaxf(m_run, mx);
     const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
     const float alpha = fast_exp2(m_run - m_use);
-    // pass 2: probabilities -> bf16 A operand in smem
     float rowsum = 0.f;
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_S + t_lane + c * 32, r);
-      tmem_ld_wait();
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        float pv[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int key = j * TK + c * 32 + i + e;
-          const bool masked = ((mw[c] >> (i + e)) & 1u) || (CAUSAL && key > qi);
-          pv[e] = masked ? 0.f : fast_exp2(__uint_as_float(r[i + e]) * p.scale_log2 - m_use);
-        }
-        // accumulate the row sum from the bf16-rounded values the MMA will actually see
-        const uint32_t u = pack_bf16(pv[0], pv[1]);
+        // exp2(-inf) = 0 handles the masked entries; the row sum uses the bf16-rounded values the MMA sees
+        const uint32_t u = pack_bf16(fast_exp2(sv[c * 32 + i] - m_use), fast_exp2(sv[c * 32 + i + 1] - m_use));
         const float2 rb = unpack_bf16(u);
         rowsum += rb.x + rb.y;
         pk[i >> 1] = u;
@@ -282,11 +274,23 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ O, long long o_ss,
 
 // ---------------------------------------------------------------------------------------------
 // backward
+//
+// One CTA per (128-key tile, head, batch), looping over query tiles i.  Per iteration:
+//   MMA1(i): S = Q K^T, dP = dO V^T                     -> TMEM (128 cols each)
+//   soft(i): P = exp2(S*scale - lse), dS = P*(dP - delta)*scale  -> bf16 smem tiles (8 warps: lane group =
+//            warp % 4 = 32 query rows, column half = warp / 4 = 64 keys)
+//   MMA2(i): dV += P^T dO, dK += dS^T Q (TMEM, accumulated over i), dQ_i = dS K (TMEM, fresh)
+//   dQ_i is read back by the 8 warps and reduced into the fp32 dQ buffer with vector atomics.
+// A 9th CONTROL warp issues all TMA loads and tcgen05.mma; the issue order "MMA1(i+1), then MMA2(i)"
+// lets soft(i+1) run on the CUDA cores while the tensor pipe executes MMA2(i).  Q/dO and P/dS tiles are
+// double-buffered in shared memory (224 KB), S/dP/dQ are single-buffered in TMEM and handed over with
+// mbarriers (sdp: MMA1 done, out: MMA2 done, soft: the 256 compute threads are done with iteration i).
 // ---------------------------------------------------------------------------------------------
-constexpr int BWD_SMEM = 8 * TILE_BYTES + 256 + 1024;
+constexpr int BWD_SMEM = 14 * TILE_BYTES + 256 + 1024;
+constexpr int BWD_THREADS = 288;
 
 template <bool CAUSAL>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                 const AttnParams p) {
@@ -295,30 +299,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sK = smem;
   uint8_t* sV = smem + TILE_BYTES;
-  uint8_t* sQ = smem + 2 * TILE_BYTES;
-  uint8_t* sdO = smem + 3 * TILE_BYTES;
-  uint8_t* sP = smem + 4 * TILE_BYTES;   // 32 KB
-  uint8_t* sdS = smem + 6 * TILE_BYTES;  // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * TILE_BYTES);
+  uint8_t* sQ = smem + 2 * TILE_BYTES;    // [2] buffers
+  uint8_t* sdO = smem + 4 * TILE_BYTES;   // [2]
+  uint8_t* sP = smem + 6 * TILE_BYTES;    // [2] x 32 KB
+  uint8_t* sdS = smem + 10 * TILE_BYTES;  // [2] x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 14 * TILE_BYTES);
   uint64_t* kv_bar = bars;
-  uint64_t* qdo_bar = bars + 1;
-  uint64_t* sdp_bar = bars + 2;
-  uint64_t* out_bar = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* qdo_bar = bars + 1;   // [2]
+  uint64_t* sdp_bar = bars + 3;
+  uint64_t* out_bar = bars + 4;
+  uint64_t* soft_bar = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   uint32_t* mask_words = tmem_slot + 2;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kv0 = blockIdx.x * TK, h = blockIdx.y, b = blockIdx.z;
   const int n_q_tiles = (p.Sq + TQ - 1) / TQ;
   const int i_begin = CAUSAL ? (int)blockIdx.x : 0;
+  const int n_it = n_q_tiles - i_begin;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    mbar_init(kv_bar, 1); mbar_init(&qdo_bar[0], 1); mbar_init(&qdo_bar[1], 1);
+    mbar_init(sdp_bar, 1); mbar_init(out_bar, 1); mbar_init(soft_bar, 256);
     fence_barrier_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  {
+  if (tid < 128) {
     const int key = kv0 + tid;
     bool masked = key >= p.Sk;
     if (!masked && p.key_mask != nullptr) masked = p.key_mask[(long long)b * p.Sk + key] != 0;
@@ -331,98 +338,84 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dV = tmem_base + 256,
                  tmem_dK = tmem_base + 320, tmem_dQ = tmem_base + 384;
-  const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
-  uint32_t mw[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) mw[c] = mask_words[c];
-
-  if (tid == 0) {
-    mbar_arrive_expect_tx(kv_bar, 2 * TILE_BYTES);
-    tma_load_4d(sK, &tmK, kv_bar, 0, h, kv0, b);
-    tma_load_4d(sV, &tmV, kv_bar, 0, h, kv0, b);
-  }
   constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);    // S, dP
   constexpr uint32_t idesc_tt = make_idesc_bf16(128, 64, 1, 1);    // dV, dK
   constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);    // dQ
-  const long long bh = (long long)b * p.H + h;
 
-  int it = 0;
-  for (int i = i_begin; i < n_q_tiles; ++i, ++it) {
-    const int q0 = i * TQ;
-    const int qi = q0 + tid;
-    const bool row_ok = qi < p.Sq;
-    if (tid == 0) {
-      mbar_arrive_expect_tx(qdo_bar, 2 * TILE_BYTES);
-      tma_load_4d(sQ, &tmQ, qdo_bar, 0, h, q0, b);
-      tma_load_4d(sdO, &tmdO, qdo_bar, 0, h, q0, b);
-      if (it == 0) mbar_wait(kv_bar, 0);
-      mbar_wait(qdo_bar, it & 1);
-      tc_fence_after();
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), adO = smem_u32(sdO), aV = smem_u32(sV);
-#pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
-        umma_bf16_ss(tmem_S, desc_k64(aQ, k), desc_k64(aK, k), idesc_s, k > 0 ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
-        umma_bf16_ss(tmem_dP, desc_k64(adO, k), desc_k64(aV, k), idesc_s, k > 0 ? 1u : 0u);
-      umma_commit(sdp_bar);
-    }
-    __syncwarp();
-    const float lse_i = row_ok ? p.lse[bh * p.Sq + qi] : 0.f;
-    const float delta_i = row_ok ? p.delta[bh * p.Sq + qi] : 0.f;
-    mbar_wait(sdp_bar, it & 1);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t rs[32], rp[32];
-      tmem_ld_32x32(tmem_S + t_lane + c * 32, rs);
-      tmem_ld_32x32(tmem_dP + t_lane + c * 32, rp);
-      tmem_ld_wait();
-      uint32_t pkP[16], pkS[16];
-#pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        float pv[2], ds[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int key = kv0 + c * 32 + e + u;
-          const bool masked = !row_ok || ((mw[c] >> (e + u)) & 1u) || (CAUSAL && key > qi);
-          pv[u] = masked ? 0.f : fast_exp2(__uint_as_float(rs[e + u]) * p.scale_log2 - lse_i);
-          ds[u] = pv[u] * (__uint_as_float(rp[e + u]) - delta_i) * p.scale;
-        }
-        pkP[e >> 1] = pack_bf16(pv[0], pv[1]);
-        pkS[e >> 1] = pack_bf16(ds[0], ds[1]);
+  if (warp == 8) {
+    // ===================== control warp: TMA + MMA issue =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_bar, 2 * TILE_BYTES);
+      tma_load_4d(sK, &tmK, kv_bar, 0, h, kv0, b);
+      tma_load_4d(sV, &tmV, kv_bar, 0, h, kv0, b);
+      for (int j = 0; j < 2 && j < n_it; ++j) {
+        mbar_arrive_expect_tx(&qdo_bar[j], 2 * TILE_BYTES);
+        tma_load_4d(sQ + j * TILE_BYTES, &tmQ, &qdo_bar[j], 0, h, (i_begin + j) * TQ, b);
+        tma_load_4d(sdO + j * TILE_BYTES, &tmdO, &qdo_bar[j], 0, h, (i_begin + j) * TQ, b);
       }
-      store_chunk_sw128(sP, tid, c, pkP);
-      store_chunk_sw128(sdS, tid, c, pkS);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+      auto issue_mma1 = [&](int it) {
+        const uint32_t aQ = smem_u32(sQ + (it & 1) * TILE_BYTES), adO = smem_u32(sdO + (it & 1) * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_S, desc_k64(aQ, k), desc_k64(aK, k), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_dP, desc_k64(adO, k), desc_k64(aV, k), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(sdp_bar);
+      };
+      mbar_wait(kv_bar, 0);
+      mbar_wait(&qdo_bar[0], 0);
       tc_fence_after();
-      const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS), aQ = smem_u32(sQ), adO = smem_u32(sdO),
-                     aK = smem_u32(sK);
+      issue_mma1(0);
+      for (int it = 0; it < n_it; ++it) {
+        const int bsel = it & 1;
+        mbar_wait(soft_bar, it & 1);          // P/dS(it) in smem; S, dP and dQ TMEM regions are free again
+        tc_fence_after();
+        if (it + 1 < n_it) {
+          mbar_wait(&qdo_bar[bsel ^ 1], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_mma1(it + 1);                 // first in the tensor pipe: soft(it+1) can start early ...
+        }
+        {                                     // ... while MMA2(it) executes underneath it
+          const uint32_t aP = smem_u32(sP + bsel * 2 * TILE_BYTES), adS = smem_u32(sdS + bsel * 2 * TILE_BYTES);
+          const uint32_t aQ = smem_u32(sQ + bsel * TILE_BYTES), adO = smem_u32(sdO + bsel * TILE_BYTES);
 #pragma unroll
-      for (int k = 0; k < TQ / 16; ++k)   // dV[kv,d] += P^T dO, contraction over the 128 query rows
-        umma_bf16_ss(tmem_dV, desc_mn128(aP, k), desc_mn64(adO, k), idesc_tt, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TQ / 16; ++k)   // dV[kv,d] += P^T dO, contraction over the 128 query rows
+            umma_bf16_ss(tmem_dV, desc_mn128(aP, k), desc_mn64(adO, k), idesc_tt, (it > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < TQ / 16; ++k)   // dK[kv,d] += dS^T Q
-        umma_bf16_ss(tmem_dK, desc_mn128(adS, k), desc_mn64(aQ, k), idesc_tt, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TQ / 16; ++k)   // dK[kv,d] += dS^T Q
+            umma_bf16_ss(tmem_dK, desc_mn128(adS, k), desc_mn64(aQ, k), idesc_tt, (it > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < TK / 16; ++k)   // dQ[q,d] = dS K, contraction over the 128 keys
-        umma_bf16_ss(tmem_dQ, desc_k128(adS, k), desc_mn64(aK, k), idesc_dq, k > 0 ? 1u : 0u);
-      umma_commit(out_bar);
+          for (int k = 0; k < TK / 16; ++k)   // dQ[q,d] = dS K, contraction over the 128 keys
+            umma_bf16_ss(tmem_dQ, desc_k128(adS, k), desc_mn64(aK, k), idesc_dq, k > 0 ? 1u : 0u);
+          umma_commit(out_bar);
+        }
+        if (it + 2 < n_it) {                  // refill this Q/dO buffer once MMA2(it) has drained it
+          mbar_wait(out_bar, it & 1);
+          mbar_arrive_expect_tx(&qdo_bar[bsel], 2 * TILE_BYTES);
+          tma_load_4d(sQ + bsel * TILE_BYTES, &tmQ, &qdo_bar[bsel], 0, h, (i_begin + it + 2) * TQ, b);
+          tma_load_4d(sdO + bsel * TILE_BYTES, &tmdO, &qdo_bar[bsel], 0, h, (i_begin + it + 2) * TQ, b);
+        }
+      }
     }
-    __syncwarp();
-    mbar_wait(out_bar, it & 1);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+  } else {
+    // ===================== compute warps =====================
+    const int lg = warp & 3, ch = warp >> 2;
+    const int row = lg * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>(lg * 32) << 16;
+    uint32_t mw[2];
+    mw[0] = mask_words[2 * ch];
+    mw[1] = mask_words[2 * ch + 1];
+    const long long bh = (long long)b * p.H + h;
+
+    auto dq_flush = [&](int it_done) {       // dQ tile of iteration it_done: this thread owns 32 columns of one row
+      const int qi = (i_begin + it_done) * TQ + row;
       uint32_t r[32];
-      tmem_ld_32x32(tmem_dQ + t_lane + c * 32, r);
+      tmem_ld_32x32(tmem_dQ + t_lane + ch * 32, r);
       tmem_ld_wait();
-      if (row_ok) {
-        float* dq = p.dQ + (long long)b * p.dq_bs + (long long)qi * p.dq_ss + h * HD + c * 32;
+      if (qi < p.Sq && p.dQ != nullptr) {
+        float* dq = p.dQ + (long long)b * p.dq_bs + (long long)qi * p.dq_ss + h * HD + ch * 32;
 #pragma unroll
         for (int e = 0; e < 8; ++e)
           atomicAdd(reinterpret_cast<float4*>(dq + 4 * e),
@@ -430,43 +423,79 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                 __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3])));
       }
       __syncwarp();
-    }
-    tc_fence_before();
-  }
+    };
 
-  // dK / dV: thread tid owns key row kv0 + tid
-  {
-    const int kv = kv0 + tid;
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (i_begin + it) * TQ;
+      const int qi = q0 + row;
+      const bool row_ok = qi < p.Sq;
+      const float lse_i = row_ok ? p.lse[bh * p.Sq + qi] : 0.f;
+      const float delta_i = row_ok ? p.delta[bh * p.Sq + qi] : 0.f;
+      uint8_t* tP = sP + (it & 1) * 2 * TILE_BYTES;
+      uint8_t* tdS = sdS + (it & 1) * 2 * TILE_BYTES;
+      mbar_wait(sdp_bar, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * ch + cc;            // 32-column chunk of the 128-key tile
+        uint32_t rs[32], rp[32];
+        tmem_ld_32x32(tmem_S + t_lane + c * 32, rs);
+        tmem_ld_32x32(tmem_dP + t_lane + c * 32, rp);
+        tmem_ld_wait();
+        uint32_t pkP[16], pkS[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float pv[2], ds[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int key = kv0 + c * 32 + e + u;
+            const bool masked = !row_ok || ((mw[cc] >> (e + u)) & 1u) || (CAUSAL && key > qi);
+            pv[u] = masked ? 0.f : fast_exp2(__uint_as_float(rs[e + u]) * p.scale_log2 - lse_i);
+            ds[u] = pv[u] * (__uint_as_float(rp[e + u]) - delta_i) * p.scale;
+          }
+          pkP[e >> 1] = pack_bf16(pv[0], pv[1]);
+          pkS[e >> 1] = pack_bf16(ds[0], ds[1]);
+        }
+        store_chunk_sw128(tP, row, c, pkP);
+        store_chunk_sw128(tdS, row, c, pkS);
+      }
+      if (it > 0) {
+        mbar_wait(out_bar, (it - 1) & 1);     // MMA2(it-1) done: its dQ tile is complete
+        tc_fence_after();
+        dq_flush(it - 1);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(soft_bar);
+    }
+    mbar_wait(out_bar, (n_it - 1) & 1);
+    tc_fence_after();
+    dq_flush(n_it - 1);
+
+    // dK / dV: this thread owns key row kv0 + row, 32 of the 64 columns
+    const int kv = kv0 + row;
     const bool ok = kv < p.Sk;
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       bf16* base = which == 0 ? p.dV : p.dK;
       const long long ss = which == 0 ? p.dv_ss : p.dk_ss, bs = which == 0 ? p.dv_bs : p.dk_bs;
       const uint32_t tm = which == 0 ? tmem_dV : tmem_dK;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        if (it > 0) {
-          tmem_ld_32x32(tm + t_lane + c * 32, r);
-          tmem_ld_wait();
-        } else {
+      uint32_t r[32];
+      tmem_ld_32x32(tm + t_lane + ch * 32, r);
+      tmem_ld_wait();
+      if (ok) {
+        bf16* orow = base + (long long)b * bs + (long long)kv * ss + h * HD + ch * 32;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) r[e] = 0u;
+        for (int e = 0; e < 4; ++e) {
+          uint4 q;
+          q.x = pack_bf16(__uint_as_float(r[8 * e]), __uint_as_float(r[8 * e + 1]));
+          q.y = pack_bf16(__uint_as_float(r[8 * e + 2]), __uint_as_float(r[8 * e + 3]));
+          q.z = pack_bf16(__uint_as_float(r[8 * e + 4]), __uint_as_float(r[8 * e + 5]));
+          q.w = pack_bf16(__uint_as_float(r[8 * e + 6]), __uint_as_float(r[8 * e + 7]));
+          *reinterpret_cast<uint4*>(orow + 8 * e) = q;
         }
-        if (ok) {
-          bf16* row = base + (long long)b * bs + (long long)kv * ss + h * HD + c * 32;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            uint4 q;
-            q.x = pack_bf16(__uint_as_float(r[8 * e]), __uint_as_float(r[8 * e + 1]));
-            q.y = pack_bf16(__uint_as_float(r[8 * e + 2]), __uint_as_float(r[8 * e + 3]));
-            q.z = pack_bf16(__uint_as_float(r[8 * e + 4]), __uint_as_float(r[8 * e + 5]));
-            q.w = pack_bf16(__uint_as_float(r[8 * e + 6]), __uint_as_float(r[8 * e + 7]));
-            *reinterpret_cast<uint4*>(row + 8 * e) = q;
-          }
-        }
-        __syncwarp();
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -547,8 +576,8 @@ extern "C" int kr_attn_bwd(const void* q, long long q_ss, long long q_bs, const 
     attr = true;
   }
   dim3 grid((Sk + TK - 1) / TK, H, B);
-  if (causal) attn_bwd_kernel<true><<<grid, 128, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
-  else        attn_bwd_kernel<false><<<grid, 128, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
+  if (causal) attn_bwd_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
+  else        attn_bwd_kernel<false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -68,7 +68,7 @@ __global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restri
 // LayerNorm backward: dx = dres + rstd*(g*dy - mean(g*dy) - xhat*mean(g*dy*xhat))
 // ---------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(WARPS * 32, 3) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                               const float* __restrict__ gamma, const float* dres, float* dx,
                               bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
@@ -82,8 +82,11 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restr
   for (int row = blockIdx.x * WARPS + warp; row < N; row += gridDim.x * WARPS) {
     const long long off = (long long)row * D;
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float4 xh[NV], g[NV];
+    float4 xh[NV], g[NV], rs[NV];
     float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)          // residual gradient: issue its loads together with x / dy
+      rs[i] = dres != nullptr ? ld4(dres + off + i * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c0 = i * 128 + lane * 4;
@@ -105,10 +108,7 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restr
       o.y = rstd * (g[i].y - c1 - xh[i].y * c2);
       o.z = rstd * (g[i].z - c1 - xh[i].z * c2);
       o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
-      if (dres != nullptr) {
-        const float4 r = ld4(dres + off + c0);
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      }
+      o.x += rs[i].x; o.y += rs[i].y; o.z += rs[i].z; o.w += rs[i].w;
       st4(dx + off + c0, o);
       if (dx_bf16 != nullptr) st_bf16x4(dx_bf16 + off + c0, o);
     }
@@ -157,7 +157,7 @@ __global__ void rms_resid_fwd_kernel(const float* __restrict__ y, const float* _
 }
 
 template <int NV>
-__global__ void rms_resid_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y,
+__global__ void __launch_bounds__(WARPS * 32, 3) rms_resid_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y,
                                      const float* __restrict__ gain, bf16* __restrict__ dy,
                                      float* __restrict__ dgain, int N, float eps) {
   constexpr int D = NV * 128;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(WARPS * 32) qkv_prep_fwd_kernel(const PrepPara
   }
 }
 
-__global__ void __launch_bounds__(WARPS * 32) qkv_prep_bwd_kernel(const PrepParams p) {
+__global__ void __launch_bounds__(WARPS * 32, 3) qkv_prep_bwd_kernel(const PrepParams p) {
   __shared__ float sm[64];
   if (threadIdx.x < 64) sm[threadIdx.x] = 0.f;
   __syncthreads();

@@ -89,7 +89,7 @@ class AcousticEngine:
         # the critical path), the variance predictors, and the encoder backward, which is disjoint
         # from the decoder backward because the length regulator detaches (utils/lengths.py:30).
         self.multi_stream = multi_stream
-        self._side = {k: torch.cuda.Stream(device=self.device) for k in ("w0", "w1", "vp", "enc")} if multi_stream else {}
+        self._side = {k: torch.cuda.Stream(device=self.device) for k in ("w0", "w1", "vp", "enc", "kv")} if multi_stream else {}
         self._w_rr = 0
         self._forked: List[torch.cuda.Stream] = []
         # every tensor of a step stays referenced until the next step starts: memory is never
@@ -175,8 +175,18 @@ class AcousticEngine:
     # ------------------------------------------------------------------------------------------
     # attention sub-layer
     # ------------------------------------------------------------------------------------------
+    def _cross_kv(self, pre: str, mem: torch.Tensor, Nk: int, Sk: int):
+        """K/V projection + per-head RMSNorm of the cross-attention memory (no RoPE on cross-attention)."""
+        st, D, H = self.store, self.D, self.H
+        raw_kv = self._empty(Nk, 2 * D, dtype=BF16)
+        ops.gemm(mem, st.span(st.shadow, pre + "w_k.weight", 2 * D, D), raw_kv)
+        nkv = self._empty(Nk, 2 * D, dtype=BF16)
+        ops.qkv_prep_fwd([raw_kv[:, :D], raw_kv[:, D:]], [nkv[:, :D], nkv[:, D:]],
+                         [st.p(pre + "k_norm.weight"), st.p(pre + "v_norm.weight")], 0, st.rope_cos, st.rope_sin, Nk, Sk, H)
+        return raw_kv, nkv
+
     def _attn_fwd(self, pre: str, x: torch.Tensor, B: int, S: int, norm: str, causal: bool,
-                  key_mask: Optional[torch.Tensor], mem: Optional[torch.Tensor], Sk: int, sv: dict):
+                  key_mask: Optional[torch.Tensor], mem: Optional[torch.Tensor], Sk: int, sv: dict, kv_pre=None):
         st, D, H = self.store, self.D, self.H
         N = B * S
         cross = mem is not None
@@ -197,13 +207,14 @@ class AcousticEngine:
             Nk = B * Sk
             raw_q = self._empty(N, D, dtype=BF16)
             ops.gemm(h, st.w(pre + "w_q.weight"), raw_q)
-            raw_kv = self._empty(Nk, 2 * D, dtype=BF16)
-            ops.gemm(mem, st.span(st.shadow, pre + "w_k.weight", 2 * D, D), raw_kv)
             nq = self._empty(N, D, dtype=BF16)
-            nkv = self._empty(Nk, 2 * D, dtype=BF16)
             ops.qkv_prep_fwd([raw_q], [nq], [gq], 0, st.rope_cos, st.rope_sin, N, S, H)
-            ops.qkv_prep_fwd([raw_kv[:, :D], raw_kv[:, D:]], [nkv[:, :D], nkv[:, D:]], [gk, gv], 0,
-                             st.rope_cos, st.rope_sin, Nk, Sk, H)
+            if kv_pre is not None:            # K/V of the memory were projected ahead of time on the "kv" stream
+                raw_kv, nkv, ev = kv_pre
+                if ev is not None:
+                    torch.cuda.current_stream(self.device).wait_event(ev)
+            else:
+                raw_kv, nkv = self._cross_kv(pre, mem, Nk, Sk)
             q = nq.view(B, S, H, 64)
             k, v = nkv[:, :D].view(B, Sk, H, 64), nkv[:, D:].view(B, Sk, H, 64)
             sv.update(raw_q=raw_q, raw_kv=raw_kv, nq=nq, nkv=nkv)
@@ -243,18 +254,21 @@ class AcousticEngine:
             self._wgrad(draw, sv["h"], st.span(st.grads, pre + "w_q.weight", 3 * D, D))
             ops.gemm(draw, st.span(st.shadow, pre + "w_q.weight", 3 * D, D), dh, b_mn_major=True)
         else:
+            # K/V side of the cross-attention: only feeds weight gradients and the memory gradient, which is
+            # consumed after the last layer -> off the critical path, serialised on the "kv" stream
+            with self._on("kv"):
+                raw_kv = sv["raw_kv"]
+                dkv_raw = self._empty(Nk, 2 * D, dtype=BF16)
+                ops.qkv_prep_bwd([raw_kv[:, :D], raw_kv[:, D:]], [dkv[:, :D], dkv[:, D:]],
+                                 [dkv_raw[:, :D], dkv_raw[:, D:]], [gk, gv], [dgk, dgv], 0, st.rope_cos,
+                                 st.rope_sin, Nk, Sk, H)
+                self._wgrad(dkv_raw, mem, st.span(st.grads, pre + "w_k.weight", 2 * D, D))
+                ops.gemm(dkv_raw, st.span(st.shadow, pre + "w_k.weight", 2 * D, D), dmem, b_mn_major=True,
+                         resid=None if dmem_first else dmem)
             dq_raw = self._empty(N, D, dtype=BF16)
             ops.qkv_prep_bwd([sv["raw_q"]], [dq], [dq_raw], [gq], [dgq], 0, st.rope_cos, st.rope_sin, N, S, H)
-            raw_kv = sv["raw_kv"]
-            dkv_raw = self._empty(Nk, 2 * D, dtype=BF16)
-            ops.qkv_prep_bwd([raw_kv[:, :D], raw_kv[:, D:]], [dkv[:, :D], dkv[:, D:]],
-                             [dkv_raw[:, :D], dkv_raw[:, D:]], [gk, gv], [dgk, dgv], 0, st.rope_cos,
-                             st.rope_sin, Nk, Sk, H)
             self._wgrad(dq_raw, sv["h"], st.g(pre + "w_q.weight"))
-            self._wgrad(dkv_raw, mem, st.span(st.grads, pre + "w_k.weight", 2 * D, D))
             ops.gemm(dq_raw, st.w(pre + "w_q.weight"), dh, b_mn_major=True)
-            ops.gemm(dkv_raw, st.span(st.shadow, pre + "w_k.weight", 2 * D, D), dmem, b_mn_major=True,
-                     resid=None if dmem_first else dmem)
         dx = self._empty(N, D)
         dx_bf = self._empty(N, D, dtype=BF16)
         ops.layernorm_bwd(dh, sv["x"], sv["mean"], sv["rstd"], st.p(norm + "weight"), dout, dx, dx_bf,
@@ -443,11 +457,20 @@ class AcousticEngine:
         ops.gemm(melshift, st.w("mel_projection_in.weight"), y, bias=st.p("mel_projection_in.bias"),
                  resid=st.pe[:T], resid_mod=T)
         dec_saved = []
+        kv_pre = [None] * cfg.n_decoder_layers
+        if self.multi_stream:                 # all six cross-attention K/V projections depend on `mem` only
+            with self._on("kv"):
+                for i in range(cfg.n_decoder_layers):
+                    raw_kv, nkv = self._cross_kv(f"decoder.layers.{i}.cross_attn.", mem, Nd, T)
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(self.device))
+                    kv_pre[i] = (raw_kv, nkv, ev)
         for i in range(cfg.n_decoder_layers):
             pre = f"decoder.layers.{i}."
             s1, s2, s3 = {}, {}, {}
             y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, None, None, T, s1)
-            y = self._attn_fwd(pre + "cross_attn.", y, B, T, pre + "norm2.", False, fmask_t, mem, T, s2)
+            y = self._attn_fwd(pre + "cross_attn.", y, B, T, pre + "norm2.", False, fmask_t, mem, T, s2,
+                               kv_pre=kv_pre[i])
             y = self._ffn_fwd(pre + "ff.", y, pre + "norm3.", cfg.decoder_ff_dim, s3)
             dec_saved.append((s1, s2, s3))
         yn = self._empty(Nd, D, dtype=BF16)
@@ -537,12 +560,12 @@ class AcousticEngine:
             dy, dy_bf = self._attn_bwd(pre + "self_attn.", dy, dy_bf, B, T, pre + "norm1.", True, None, None, T,
                                        s1, None, False)
         self._wgrad(dy_bf, ctx["melshift"], st.g("mel_projection_in.weight"), st.g("mel_projection_in.bias"))
-        # memory gradient reaches only the pitch / energy embedding rows (detached expansion)
+        self._join_all()
+        # memory gradient (accumulated on the "kv" stream) reaches only the pitch / energy embedding rows
         if self.spec_spans is not None:
             ops.spec_augment(dmem.view(B, T, D), self.spec_spans, self.spec_n_time, self.spec_n_feat)
         ops.adapt_bwd(dmem, ctx["p_idx"].view(-1), ctx["e_idx"].view(-1), st.g(va + "pitch_embedding.weight"),
                       st.g(va + "energy_embedding.weight"))
-        self._join_all()
 
     @staticmethod
     def draw_spec_spans(B: int, T: int, D: int, time_mask_max: int = 5, freq_mask_max: int = 3,
