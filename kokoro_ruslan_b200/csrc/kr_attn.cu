@@ -63,6 +63,17 @@ __device__ __forceinline__ void store_chunk_sw128(uint8_t* tile, int row, int c,
   }
 }
 
+// Bit e of the result is set iff key (key0 + e) may be attended by query row qi: not padded (pad_bits bit e
+// clear) and, if causal, key <= qi.  All-ones is the common case and takes a predicate-free fast path.
+__device__ __forceinline__ uint32_t allowed_bits(uint32_t pad_bits, bool causal, int key0, int qi) {
+  uint32_t a = ~pad_bits;
+  if (causal) {
+    const int n = qi - key0 + 1;                       // number of leading keys of this chunk that are <= qi
+    a &= n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
+  }
+  return a;
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -89,9 +100,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t* mask_words = tmem_slot + 2;  // [2][4]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+  // causal: the last query tile attends to the most keys -> schedule the heavy tiles first
+  const int qt = CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int q0 = qt * TQ, h = blockIdx.y, b = blockIdx.z;
   int n_tiles = (p.Sk + TK - 1) / TK;
-  if (CAUSAL) n_tiles = min(n_tiles, (int)blockIdx.x + 1);
+  if (CAUSAL) n_tiles = min(n_tiles, qt + 1);
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -164,11 +177,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t r[32];
       tmem_ld_32x32(tmem_S + t_lane + c * 32, r);
       tmem_ld_wait();
+      const uint32_t ok = allowed_bits(mw[c], CAUSAL, j * TK + c * 32, qi);
+      if (__all_sync(0xffffffffu, ok == 0xffffffffu)) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int key = j * TK + c * 32 + i;
-        const bool masked = ((mw[c] >> i) & 1u) || (CAUSAL && key > qi);
-        sv[c * 32 + i] = masked ? -INFINITY : __uint_as_float(r[i]) * p.scale_log2;
+        for (int i = 0; i < 32; ++i) sv[c * 32 + i] = __uint_as_float(r[i]) * p.scale_log2;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          sv[c * 32 + i] = ((ok >> i) & 1u) ? __uint_as_float(r[i]) * p.scale_log2 : -INFINITY;
       }
     }
     float mx = -INFINITY;
@@ -306,10 +322,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 14 * TILE_BYTES);
   uint64_t* kv_bar = bars;
   uint64_t* qdo_bar = bars + 1;   // [2]
-  uint64_t* sdp_bar = bars + 3;
-  uint64_t* out_bar = bars + 4;
-  uint64_t* soft_bar = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* sdp_bar = bars + 3;   // [2] one per 64-key half of the S / dP tiles
+  uint64_t* out_bar = bars + 5;
+  uint64_t* soft_bar = bars + 6;  // [2] one per half (128 threads each)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   uint32_t* mask_words = tmem_slot + 2;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -321,7 +337,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     mbar_init(kv_bar, 1); mbar_init(&qdo_bar[0], 1); mbar_init(&qdo_bar[1], 1);
-    mbar_init(sdp_bar, 1); mbar_init(out_bar, 1); mbar_init(soft_bar, 256);
+    mbar_init(&sdp_bar[0], 1); mbar_init(&sdp_bar[1], 1); mbar_init(out_bar, 1);
+    mbar_init(&soft_bar[0], 128); mbar_init(&soft_bar[1], 128);
     fence_barrier_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -338,7 +355,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dV = tmem_base + 256,
                  tmem_dK = tmem_base + 320, tmem_dQ = tmem_base + 384;
-  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);    // S, dP
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);     // one 64-key half of S / dP
   constexpr uint32_t idesc_tt = make_idesc_bf16(128, 64, 1, 1);    // dV, dK
   constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);    // dQ
 
@@ -354,28 +371,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_load_4d(sdO + j * TILE_BYTES, &tmdO, &qdo_bar[j], 0, h, (i_begin + j) * TQ, b);
       }
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-      auto issue_mma1 = [&](int it) {
+      // MMA1 for one 64-key half hf: S[:, hf] = Q K[hf]^T, dP[:, hf] = dO V[hf]^T  (K/V rows 64*hf.. start 8 KB in)
+      auto issue_mma1 = [&](int it, int hf) {
         const uint32_t aQ = smem_u32(sQ + (it & 1) * TILE_BYTES), adO = smem_u32(sdO + (it & 1) * TILE_BYTES);
+        const uint32_t kOff = hf * 64 * 128;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_S, desc_k64(aQ, k), desc_k64(aK, k), idesc_s, k > 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_S + hf * 64, desc_k64(aQ, k), desc_k64(aK + kOff, k), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_dP, desc_k64(adO, k), desc_k64(aV, k), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(sdp_bar);
+          umma_bf16_ss(tmem_dP + hf * 64, desc_k64(adO, k), desc_k64(aV + kOff, k), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&sdp_bar[hf]);
       };
       mbar_wait(kv_bar, 0);
       mbar_wait(&qdo_bar[0], 0);
       tc_fence_after();
-      issue_mma1(0);
+      issue_mma1(0, 0);
+      issue_mma1(0, 1);
       for (int it = 0; it < n_it; ++it) {
         const int bsel = it & 1;
-        mbar_wait(soft_bar, it & 1);          // P/dS(it) in smem; S, dP and dQ TMEM regions are free again
-        tc_fence_after();
-        if (it + 1 < n_it) {
-          mbar_wait(&qdo_bar[bsel ^ 1], ((it + 1) >> 1) & 1);
+        // half hf of S/dP is free again as soon as ITS 4 warps are done with it: refill it right away so the
+        // warps of that half never wait for more than one MMA1 latency
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&soft_bar[hf], it & 1);
           tc_fence_after();
-          issue_mma1(it + 1);                 // first in the tensor pipe: soft(it+1) can start early ...
+          if (it + 1 < n_it) {
+            if (hf == 0) { mbar_wait(&qdo_bar[bsel ^ 1], ((it + 1) >> 1) & 1); tc_fence_after(); }
+            issue_mma1(it + 1, hf);
+          }
         }
         {                                     // ... while MMA2(it) executes underneath it
           const uint32_t aP = smem_u32(sP + bsel * 2 * TILE_BYTES), adS = smem_u32(sdS + bsel * 2 * TILE_BYTES);
@@ -404,9 +427,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int lg = warp & 3, ch = warp >> 2;
     const int row = lg * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(lg * 32) << 16;
-    uint32_t mw[2];
-    mw[0] = mask_words[2 * ch];
-    mw[1] = mask_words[2 * ch + 1];
+    const uint32_t mw0 = mask_words[2 * ch], mw1 = mask_words[2 * ch + 1];
     const long long bh = (long long)b * p.H + h;
 
     auto dq_flush = [&](int it_done) {       // dQ tile of iteration it_done: this thread owns 32 columns of one row
@@ -433,7 +454,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float delta_i = row_ok ? p.delta[bh * p.Sq + qi] : 0.f;
       uint8_t* tP = sP + (it & 1) * 2 * TILE_BYTES;
       uint8_t* tdS = sdS + (it & 1) * 2 * TILE_BYTES;
-      mbar_wait(sdp_bar, it & 1);
+      mbar_wait(&sdp_bar[ch], it & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
@@ -442,19 +463,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_32x32(tmem_S + t_lane + c * 32, rs);
         tmem_ld_32x32(tmem_dP + t_lane + c * 32, rp);
         tmem_ld_wait();
+        uint32_t ok = allowed_bits(cc == 0 ? mw0 : mw1, CAUSAL, kv0 + c * 32, qi);
+        if (!row_ok) ok = 0u;
+        const float nds = -delta_i * p.scale;
         uint32_t pkP[16], pkS[16];
+        if (__all_sync(0xffffffffu, ok == 0xffffffffu)) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float pv[2], ds[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int key = kv0 + c * 32 + e + u;
-            const bool masked = !row_ok || ((mw[cc] >> (e + u)) & 1u) || (CAUSAL && key > qi);
-            pv[u] = masked ? 0.f : fast_exp2(__uint_as_float(rs[e + u]) * p.scale_log2 - lse_i);
-            ds[u] = pv[u] * (__uint_as_float(rp[e + u]) - delta_i) * p.scale;
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse_i));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse_i));
+            pkP[e >> 1] = pack_bf16(p0, p1);
+            pkS[e >> 1] = pack_bf16(p0 * fmaf(__uint_as_float(rp[e]), p.scale, nds),
+                                    p1 * fmaf(__uint_as_float(rp[e + 1]), p.scale, nds));
           }
-          pkP[e >> 1] = pack_bf16(pv[0], pv[1]);
-          pkS[e >> 1] = pack_bf16(ds[0], ds[1]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse_i));
+            float p1 = fast_exp2(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse_i));
+            p0 = ((ok >> e) & 1u) ? p0 : 0.f;
+            p1 = ((ok >> (e + 1)) & 1u) ? p1 : 0.f;
+            pkP[e >> 1] = pack_bf16(p0, p1);
+            pkS[e >> 1] = pack_bf16(p0 * fmaf(__uint_as_float(rp[e]), p.scale, nds),
+                                    p1 * fmaf(__uint_as_float(rp[e + 1]), p.scale, nds));
+          }
         }
         store_chunk_sw128(tP, row, c, pkP);
         store_chunk_sw128(tdS, row, c, pkS);
@@ -466,7 +498,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(soft_bar);
+      mbar_arrive(&soft_bar[ch]);
     }
     mbar_wait(out_bar, (n_it - 1) & 1);
     tc_fence_after();
