@@ -1,6 +1,9 @@
 // kr_api.cu — error reporting + version for the C ABI (include/kokoro_b200.h).
 #include "kr_common.cuh"
 #include <string.h>
+#include <stdlib.h>
+#include <mutex>
+#include <unordered_set>
 
 static thread_local char g_err[512] = "";
 
@@ -11,6 +14,26 @@ void kr_set_error(const char* msg) {
 
 static unsigned long long g_launches = 0;
 void kr_count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+namespace kr {
+void kr_prefer_max_smem(const void* kernel) {
+  static std::mutex mu;
+  static std::unordered_set<const void*> seen;
+  static int enabled = -1;
+  std::lock_guard<std::mutex> lock(mu);
+  if (enabled < 0) { const char* e = getenv("KR_CARVEOUT"); enabled = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  if (!enabled || !seen.insert(kernel).second) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaGetLastError();   // best effort
+}
+}  // namespace kr
+
+int kr_pdl_enabled() {
+  static int v = -1;
+  // measured: no gain inside CUDA graphs on B200 -> opt-in
+  if (v < 0) { const char* e = getenv("KR_PDL"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  return v;
+}
 
 extern "C" const char* kr_last_error(void) { return g_err; }
 // Kernels launched by this library since it was loaded (every launch site counts itself).
@@ -26,4 +49,13 @@ extern "C" int kr_device_cc(void) {
     return KR_ERR_CUDA;
   }
   return prop.major * 10 + prop.minor;
+}
+
+// Zero-fill on the stream through the copy/memset engine (a memset node inside CUDA graphs): unlike a
+// fill kernel it does not touch the SMs' shared-memory configuration.
+extern "C" int kr_memset_zero(void* ptr, long long bytes, void* stream) {
+  if (bytes <= 0) return KR_OK;
+  cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) { kr_set_error(cudaGetErrorString(e)); return KR_ERR_CUDA; }
+  return KR_OK;
 }

@@ -106,6 +106,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   int n_tiles = (p.Sk + TK - 1) / TK;
   if (CAUSAL) n_tiles = min(n_tiles, qt + 1);
 
+  pdl_launch_dependents();
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
@@ -115,6 +116,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
   const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
@@ -260,6 +262,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ O, long long o_ss, long long o_bs,
                                      const bf16* __restrict__ dO, long long do_ss, long long do_bs,
                                      float* __restrict__ delta, int B, int H, int Sq) {
+  pdl_entry();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B * Sq) return;
@@ -333,6 +336,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int n_q_tiles = (p.Sq + TQ - 1) / TQ;
   const int i_begin = CAUSAL ? (int)blockIdx.x : 0;
   const int n_it = n_q_tiles - i_begin;
+  pdl_launch_dependents();
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
@@ -342,6 +346,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  pdl_wait();
   if (tid < 128) {
     const int key = kv0 + tid;
     bool masked = key >= p.Sk;
@@ -566,8 +571,8 @@ extern "C" int kr_attn_fwd(const void* q, long long q_ss, long long q_bs, const 
   }
   dim3 grid((Sq + TQ - 1) / TQ, H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (causal) attn_fwd_kernel<true><<<grid, 128, FWD_SMEM, st>>>(tq, tk, tv, p);
-  else        attn_fwd_kernel<false><<<grid, 128, FWD_SMEM, st>>>(tq, tk, tv, p);
+  if (causal) kr::launch(attn_fwd_kernel<true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
+  else        kr::launch(attn_fwd_kernel<false>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -584,7 +589,7 @@ extern "C" int kr_attn_bwd(const void* q, long long q_ss, long long q_bs, const 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   {
     const int rows = B * Sq, wpb = 8;
-    attn_bwd_prep_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+    kr::launch(attn_bwd_prep_kernel, (rows + wpb - 1) / wpb, wpb * 32, 0, st, 
         reinterpret_cast<const bf16*>(o), o_ss, o_bs, reinterpret_cast<const bf16*>(d_o), do_ss, do_bs,
         delta, B, H, Sq);
     KR_CHECK_LAUNCH();
@@ -608,8 +613,8 @@ extern "C" int kr_attn_bwd(const void* q, long long q_ss, long long q_bs, const 
     attr = true;
   }
   dim3 grid((Sk + TK - 1) / TK, H, B);
-  if (causal) attn_bwd_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
-  else        attn_bwd_kernel<false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tdo, p);
+  if (causal) kr::launch(attn_bwd_kernel<true>, grid, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, p);
+  else        kr::launch(attn_bwd_kernel<false>, grid, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -29,12 +29,47 @@
 
 void kr_set_error(const char* msg);
 void kr_count_launch();
+int kr_pdl_enabled();   // programmatic dependent launch: opt-in with env KR_PDL=1
 
 typedef __nv_bfloat16 bf16;
 
 namespace kr {
 
 constexpr int kNumSMs = 148;
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library starts with
+//   pdl_launch_dependents();  ... prologue that touches no global memory ...  pdl_wait();
+// and is launched with programmaticStreamSerialization, so the launch latency and the prologue
+// (barrier init, TMEM allocation, tensor-map prefetch) of kernel N+1 overlap the tail of kernel N.
+// griddepcontrol.wait returns only when the preceding grid has COMPLETED and flushed its memory, so
+// ordering is exactly that of a normal stream; a step is ~540 short dependent kernels, which makes the
+// per-launch bubble (~2 us) a first-order cost.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_launch_dependents(); pdl_wait(); }
+
+// Every kernel of the library asks for the MAXIMUM shared-memory carve-out, including the HBM kernels
+// that use no shared memory at all: the tcgen05 GEMM / attention CTAs need ~200 KB, and an SM has to
+// drain before it can change its L1/shared split, so alternating small-smem and large-smem kernels
+// (which is what a training step is) would otherwise pay a reconfiguration bubble on every GEMM launch.
+void kr_prefer_max_smem(const void* kernel);
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  kr_prefer_max_smem(reinterpret_cast<const void*>(kernel));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = kr_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---------------------------------------------------------------------------------------------
 // generic helpers

@@ -35,7 +35,6 @@ constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane group, alternating column chunks
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // producer warp + MMA warp + epilogue warps
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;         // per-warp 32x32 fp32 transpose buffer
-constexpr int SMEM_BUDGET = 192 * 1024;
 
 enum CMode { C_BF16 = 0, C_F32 = 1, C_ATOMIC_F32 = 2, C_NONE = 3 };
 
@@ -50,18 +49,24 @@ struct GemmParams {
   const void* resid; int resid_bf16; long long ldr, r_batch_stride; int resid_mod;
   const void* resid2; int resid2_bf16; long long ldr2, r2_batch_stride;
   float alpha, beta;
+  int stages, stage_bytes, b_resident, b_res_bytes;   // smem ring geometry (host-chosen)
   int b_shared;   // B has no batch dimension (weights shared by every batch item)
 };
+
+// Dynamic shared memory map (offsets from the 1024-aligned base):
+//   [0, 1024)                      mbarriers + TMEM slot
+//   [1024, 1024 + 32 KB)           epilogue transpose buffers (one 32x32 fp32 tile per epilogue warp)
+//   [.., + b_res_bytes)            RESIDENT B operand (all K blocks) when p.b_resident, else empty
+//   [.., + stages * stage_bytes)   TMA ring: A tile (+ B tile unless resident) per stage
+constexpr int MAX_STAGES = 12;
+constexpr int BAR_BYTES = 1024;
+constexpr int RING_OFFSET0 = BAR_BYTES + EPI_WARPS * EPI_STAGE_BYTES;   // 33 KB, 1024-aligned
+constexpr int SMEM_TOTAL = 227 * 1024 - 1024;                            // leave slack for the base alignment
 
 template <int BLOCK_N>
 struct SmemLayout {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int EPI_OFFSET = BAR_OFFSET + 512;
-  static constexpr int TOTAL = EPI_OFFSET + EPI_WARPS * EPI_STAGE_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = BLOCK_N <= 64 ? 128 : (BLOCK_N <= 128 ? 256 : 512);  // power of two >= 2*BLOCK_N
 };
 
@@ -75,6 +80,15 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   t.split = r % p.splits;
   t.bz = r / p.splits;
   return t;
+}
+
+__device__ __forceinline__ float4 ld4any(const void* base, int is_bf16, long long off) {
+  if (is_bf16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(base) + off);
+    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
+    return make_float4(f0.x, f0.y, f1.x, f1.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
 }
 
 __device__ __forceinline__ float4 add4(float4 v, const void* base, int is_bf16, long long off) {
@@ -128,19 +142,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
   using L = SmemLayout<BLOCK_N>;
-  constexpr int STAGES = L::STAGES;
+  const int STAGES = p.stages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+  uint64_t* bres_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  uint8_t* b_res = smem + RING_OFFSET0;
+  uint8_t* ring = b_res + p.b_res_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();   // the next kernel may start its own prologue now
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -149,6 +167,7 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    mbar_init(bres_bar, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], EPI_WARPS);   // one arrive per epilogue warp
@@ -163,24 +182,38 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // everything below reads / writes global memory of the preceding kernels
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      int it = 0;  // global k-block counter (ring position)
+      int ring_s = 0; uint32_t ring_ph = 0;  // ring position (stage, phase) — no runtime division
+      if (p.b_resident) {     // the whole [N, K] weight operand stays in smem for the life of the CTA
+        mbar_arrive_expect_tx(bres_bar, (uint32_t)p.b_res_bytes);
+        for (int kb = 0; kb < p.total_kb; ++kb) {
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_3d(b_res + kb * L::B_BYTES + j * (BLOCK_K * 128), &tmap_b, bres_bar, j * 64, kb * BLOCK_K, 0);
+          } else {
+            tma_load_3d(b_res + kb * L::B_BYTES, &tmap_b, bres_bar, kb * BLOCK_K, 0, 0);
+          }
+        }
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BLOCK_N;
         const int kb0 = tc.split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
         const int bzb = p.b_shared ? 0 : tc.bz;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int s = ring_s;
+          const uint32_t ph = ring_ph;
+          if (++ring_s == STAGES) { ring_s = 0; ring_ph ^= 1u; }
           mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sa = ring + s * p.stage_bytes;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
           const int k = kb * BLOCK_K;
           if (A_MN) {
 #pragma unroll
@@ -192,7 +225,9 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           } else {
             tma_load_3d(sa, &tmap_a, &full_bar[s], k, m0, tc.bz);
           }
-          if (B_MN) {
+          if (p.b_resident) {
+            // nothing: B is already in smem
+          } else if (B_MN) {
 #pragma unroll
             for (int j = 0; j < BLOCK_N / 64; ++j)
               tma_load_3d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[s], n0 + j * 64, k, bzb);
@@ -210,7 +245,9 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // 64-wide MN chunks BLOCK_K*128 B apart, +2048 B per UMMA_K.
       constexpr uint32_t a_lbo = A_MN ? BLOCK_K * 128 : 16, b_lbo = B_MN ? BLOCK_K * 128 : 16;
       constexpr uint32_t a_kstep = A_MN ? 2048 : 32, b_kstep = B_MN ? 2048 : 32;
-      int it = 0, lt = 0;  // k-block counter, local tile counter
+      int ring_s = 0, lt = 0;  // ring stage, local tile counter
+      uint32_t ring_ph = 0;
+      if (p.b_resident) { mbar_wait(bres_bar, 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
         const TileCoord tc = decode_tile(p, tile);
         const int kb0 = tc.split * p.kb_per_split;
@@ -220,13 +257,14 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
-        for (int i = 0; i < num_kb; ++i, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+        for (int i = 0; i < num_kb; ++i) {
+          const int s = ring_s;
+          const uint32_t ph = ring_ph;
+          if (++ring_s == STAGES) { ring_s = 0; ring_ph ^= 1u; }
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t sb = sa + L::A_BYTES;
+          const uint32_t sa = smem_u32(ring + s * p.stage_bytes);
+          const uint32_t sb = p.b_resident ? smem_u32(b_res + (kb0 + i) * L::B_BYTES) : sa + L::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
@@ -245,7 +283,7 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // as 4 rows x 128 contiguous bytes per warp instruction.
     const int lg = warp & 3;
     const int half = (warp - 2) >> 2;
-    float* stg = reinterpret_cast<float*>(smem + L::EPI_OFFSET + (warp - 2) * EPI_STAGE_BYTES);
+    float* stg = reinterpret_cast<float*>(smem + BAR_BYTES + (warp - 2) * EPI_STAGE_BYTES);
     const int crow = lane >> 3;          // coalesced layout: this lane handles row 4*i + crow ...
     const int ccol = (lane & 7) * 4;     // ... columns [ccol, ccol + 4) of the chunk
     const bool vec_ok = ((p.N & 3) == 0) && ((p.ldc & 3) == 0) && ((p.ldr & 3) == 0) && ((p.ldr2 & 3) == 0) &&
@@ -266,21 +304,48 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int c = half; c < BLOCK_N / 32; c += 2) {
         const int nb = n0 + c * 32;
         if (nb >= p.N) break;                          // warp-uniform
+        // (1) residual operands of this chunk are requested FIRST, in the coalesced layout, so that their
+        //     HBM/L2 latency overlaps the TMEM load and the smem transpose (the epilogue was latency-bound on
+        //     exactly these loads: 1.7 TB/s on the HiFi-GAN residual convs)
+        const int n = nb + ccol;
+        const bool col_ok = n < p.N;          // N % 4 == 0 on this path: a 4-group is all in or all out
+        float4 r1[8], r2[8];
+        if (vec_ok) {
+          if (use_resid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m = mw0 + 4 * i + crow;
+              r1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (m < p.M && col_ok) {
+                const int rm = p.resid_mod > 0 ? (m % p.resid_mod) : m;
+                r1[i] = ld4any(p.resid, p.resid_bf16, (long long)tc.bz * p.r_batch_stride + (long long)rm * p.ldr + n);
+              }
+            }
+          }
+          if (p.resid2 != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m = mw0 + 4 * i + crow;
+              r2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (m < p.M && col_ok)
+                r2[i] = ld4any(p.resid2, p.resid2_bf16, (long long)tc.bz * p.r2_batch_stride + (long long)m * p.ldr2 + n);
+            }
+          }
+        }
+        // (2) accumulator chunk: TMEM -> registers (row layout) -> smem (16-byte slots XOR-swizzled by row:
+        //     conflict-free both ways)
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + buf * BLOCK_N + (static_cast<uint32_t>(lg * 32) << 16) + c * 32, r);
         tmem_ld_wait();
-        // row layout -> smem (16-byte slots XOR-swizzled by row: conflict-free both ways)
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<uint4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) =
               make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
         __syncwarp();
         if (vec_ok) {
-          const int n = nb + ccol;
-          const bool col_ok = n < p.N;          // N % 4 == 0: a 4-group is all in or all out
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (use_bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-#pragma unroll 4
+#pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = 4 * i + crow;
             const int m = mw0 + rr;
@@ -288,13 +353,9 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (m < p.M && col_ok) {
               float4 v = make_float4(a4.x * p.alpha + b4.x, a4.y * p.alpha + b4.y, a4.z * p.alpha + b4.z,
                                      a4.w * p.alpha + b4.w);
-              if (use_resid) {
-                const int rm = p.resid_mod > 0 ? (m % p.resid_mod) : m;
-                v = add4(v, p.resid, p.resid_bf16, (long long)tc.bz * p.r_batch_stride + (long long)rm * p.ldr + n);
-              }
+              if (use_resid) { v.x += r1[i].x; v.y += r1[i].y; v.z += r1[i].z; v.w += r1[i].w; }
               v.x *= p.beta; v.y *= p.beta; v.z *= p.beta; v.w *= p.beta;
-              if (p.resid2 != nullptr)
-                v = add4(v, p.resid2, p.resid2_bf16, (long long)tc.bz * p.r2_batch_stride + (long long)m * p.ldr2 + n);
+              if (p.resid2 != nullptr) { v.x += r2[i].x; v.y += r2[i].y; v.z += r2[i].z; v.w += r2[i].w; }
               const long long c_off = (long long)tc.bz * p.c_batch_stride + (long long)m * p.ldc + n;
               if (p.c_mode == C_BF16)
                 *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.C) + c_off) =
@@ -331,28 +392,40 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, bool want_resident, cudaStream_t st) {
   using L = SmemLayout<BLOCK_N>;
   auto kern = kr_gemm_kernel<BLOCK_N, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL + 1024);
     if (e != cudaSuccess) { kr_set_error(cudaGetErrorString(e)); return KR_ERR_CUDA; }
     attr_set = true;
   }
+  // ring geometry: keep the weight operand resident when it fits next to >= 4 A-only stages
+  const int avail = SMEM_TOTAL - RING_OFFSET0;
+  p.b_resident = 0; p.b_res_bytes = 0; p.stage_bytes = L::A_BYTES + L::B_BYTES;
+  const long long bres = (long long)p.total_kb * L::B_BYTES;
+  if (want_resident && bres + 4LL * L::A_BYTES <= avail) {
+    p.b_resident = 1; p.b_res_bytes = (int)bres; p.stage_bytes = L::A_BYTES;
+  }
+  int stages = (avail - p.b_res_bytes) / p.stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > 8 && !p.b_resident) stages = 8;
+  p.stages = stages;
+  const int smem_bytes = RING_OFFSET0 + p.b_res_bytes + stages * p.stage_bytes + 1024;
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  kern<<<grid, GEMM_THREADS, L::TOTAL, st>>>(ta, tb, p);
+  kr::launch(kern, grid, GEMM_THREADS, smem_bytes, st, ta, tb, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 
 template <int BLOCK_N>
-int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, bool res,
                    cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_gemm<BLOCK_N, false, false>(ta, tb, p, st);
-  if (!a_mn && b_mn) return launch_gemm<BLOCK_N, false, true>(ta, tb, p, st);
-  if (a_mn && !b_mn) return launch_gemm<BLOCK_N, true, false>(ta, tb, p, st);
-  return launch_gemm<BLOCK_N, true, true>(ta, tb, p, st);
+  if (!a_mn && !b_mn) return launch_gemm<BLOCK_N, false, false>(ta, tb, p, res, st);
+  if (!a_mn && b_mn) return launch_gemm<BLOCK_N, false, true>(ta, tb, p, res, st);
+  if (a_mn && !b_mn) return launch_gemm<BLOCK_N, true, false>(ta, tb, p, res, st);
+  return launch_gemm<BLOCK_N, true, true>(ta, tb, p, res, st);
 }
 
 }  // namespace
@@ -502,10 +575,12 @@ extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
   p.alpha = a->alpha; p.beta = a->beta;
   p.b_shared = b_shared ? 1 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ta, tb, p, st);
-  if (block_n == 192) return dispatch_major<192>(a->a_mn_major, a->b_mn_major, ta, tb, p, st);
-  if (block_n == 128) return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ta, tb, p, st);
-  return dispatch_major<64>(a->a_mn_major, a->b_mn_major, ta, tb, p, st);
+  // resident weights: one N tile, no split-K, weights shared by the batch, and enough tiles per CTA to pay off
+  const bool res = p.n_tiles == 1 && splits == 1 && (batch == 1 || b_shared) && p.total_tiles >= 2 * kNumSMs;
+  if (block_n == 256) return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ta, tb, p, res, st);
+  if (block_n == 192) return dispatch_major<192>(a->a_mn_major, a->b_mn_major, ta, tb, p, res, st);
+  if (block_n == 128) return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ta, tb, p, res, st);
+  return dispatch_major<64>(a->a_mn_major, a->b_mn_major, ta, tb, p, res, st);
 }
 
 extern "C" int kr_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int batch,

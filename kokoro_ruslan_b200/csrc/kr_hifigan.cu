@@ -13,6 +13,7 @@ using namespace kr;
 // block = 32 time steps of one item; smem tile [c][33]
 __global__ void pack_mel_kernel(const float* __restrict__ mel, int time_major, bf16* __restrict__ out, int B, int T,
                                 int n_mels, int halo, int c_phys) {
+  kr::pdl_entry();
   extern __shared__ float tile[];  // [n_mels][33]
   const int b = blockIdx.y, t0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -44,6 +45,7 @@ __global__ void pack_mel_kernel(const float* __restrict__ mel, int time_major, b
 template <int TAPS>
 __global__ void post_tanh_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                  float* __restrict__ out, int B, long long L, int halo, int C, int c_phys) {
+  kr::pdl_entry();
   extern __shared__ float sw[];  // [TAPS][C]
   for (int i = threadIdx.x; i < TAPS * C; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -78,7 +80,7 @@ extern "C" int kr_hifi_pack_mel(const float* mel, int time_major, void* out, int
   if (B <= 0 || T <= 0) { kr_set_error("kr_hifi_pack_mel: empty input"); return KR_ERR_ARG; }
   if (c_phys < n_mels || (c_phys & 1)) { kr_set_error("kr_hifi_pack_mel: c_phys must be even and >= n_mels"); return KR_ERR_ARG; }
   dim3 grid((T + 31) / 32, B);
-  pack_mel_kernel<<<grid, 256, n_mels * 33 * sizeof(float), (cudaStream_t)stream>>>(
+  kr::launch(pack_mel_kernel, grid, 256, n_mels * 33 * sizeof(float), (cudaStream_t)stream, 
       mel, time_major, reinterpret_cast<bf16*>(out), B, T, n_mels, halo, c_phys);
   KR_CHECK_LAUNCH();
   return KR_OK;
@@ -90,7 +92,7 @@ extern "C" int kr_hifi_post_tanh(const void* x, const float* w, const float* bia
   const long long n = (long long)B * L;
   if (n <= 0) return KR_OK;
   const int threads = 256;
-  post_tanh_kernel<7><<<(unsigned)((n + threads - 1) / threads), threads, 7 * C * sizeof(float), (cudaStream_t)stream>>>(
+  kr::launch(post_tanh_kernel<7>, (unsigned)((n + threads - 1) / threads), threads, 7 * C * sizeof(float), (cudaStream_t)stream, 
       reinterpret_cast<const bf16*>(x), w, bias, out, B, L, halo, C, c_phys);
   KR_CHECK_LAUNCH();
   return KR_OK;

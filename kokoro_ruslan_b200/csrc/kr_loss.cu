@@ -52,6 +52,7 @@ __device__ __forceinline__ void block_accumulate(float s, float n, double* dst) 
 }
 
 __global__ void loss_reduce_kernel(const LossParams p) {
+  kr::pdl_entry();
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nth = (long long)gridDim.x * blockDim.x;
   float s = 0.f, n = 0.f;
@@ -91,6 +92,7 @@ __global__ void loss_reduce_kernel(const LossParams p) {
 }
 
 __global__ void loss_grad_kernel(const LossParams p) {
+  kr::pdl_entry();
   // every thread derives the five means / clamp gates from the 10 accumulators
   float L[5], f[5];
   const float cl[5] = {100.f, 100.f, 100.f, 10.f, 10.f};
@@ -149,6 +151,7 @@ __global__ void loss_grad_kernel(const LossParams p) {
 // z[n] = x[n,:] . w + b   (x bf16 [N,D])
 __global__ void stop_head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                      const float* __restrict__ bias, float* __restrict__ z, int N, int D) {
+  kr::pdl_entry();
   const int lane = threadIdx.x & 31;
   for (int n = blockIdx.x * WARPS + (threadIdx.x >> 5); n < N; n += gridDim.x * WARPS) {
     float s = 0.f;
@@ -169,6 +172,7 @@ __global__ void stop_head_fwd_kernel(const bf16* __restrict__ x, const float* __
 // dw += sum_n dz[n] x[n,:], db += sum_n dz[n]   (D <= 1024)
 __global__ void stop_head_bwd_kernel(const float* __restrict__ dz, const bf16* __restrict__ x,
                                      float* __restrict__ dw, float* __restrict__ db, int N, int D) {
+  kr::pdl_entry();
   __shared__ float sm[WARPS][1024];
   __shared__ float sb[WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,7 +224,7 @@ extern "C" int kr_stop_head_fwd(const void* x, const float* w, const float* bias
   if (N <= 0) return KR_OK;
   if (D % 8) { kr_set_error("kr_stop_head: D % 8 != 0"); return KR_ERR_ARG; }
   const int blocks = min((N + WARPS - 1) / WARPS, kNumSMs * 8);
-  stop_head_fwd_kernel<<<blocks, WARPS * 32, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, z, N, D);
+  kr::launch(stop_head_fwd_kernel, blocks, WARPS * 32, 0, (cudaStream_t)stream, (const bf16*)x, w, bias, z, N, D);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -230,7 +234,7 @@ extern "C" int kr_stop_head_bwd(const float* dz, const void* x, float* dw, float
   if (N <= 0) return KR_OK;
   if ((D % 8) || D > 1024) { kr_set_error("kr_stop_head: D % 8 != 0 or D > 1024"); return KR_ERR_ARG; }
   const int blocks = min((N + WARPS - 1) / WARPS, kNumSMs);
-  stop_head_bwd_kernel<<<blocks, WARPS * 32, 0, (cudaStream_t)stream>>>(dz, (const bf16*)x, dw, db, N, D);
+  kr::launch(stop_head_bwd_kernel, blocks, WARPS * 32, 0, (cudaStream_t)stream, dz, (const bf16*)x, dw, db, N, D);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -263,9 +267,9 @@ extern "C" int kr_losses_fwd_bwd(const float* mel_pred, const float* mel_tgt, co
   if (cudaMemsetAsync(acc, 0, 10 * sizeof(double), st) != cudaSuccess) { kr_set_error("memset failed"); return KR_ERR_CUDA; }
   const long long n = (long long)B * T * C;
   const int blocks = (int)((n + 255) / 256 < kNumSMs * 4 ? (n + 255) / 256 : kNumSMs * 4);
-  loss_reduce_kernel<<<blocks, 256, 0, st>>>(p);
+  kr::launch(loss_reduce_kernel, blocks, 256, 0, st, p);
   KR_CHECK_LAUNCH();
-  loss_grad_kernel<<<blocks, 256, 0, st>>>(p);
+  kr::launch(loss_grad_kernel, blocks, 256, 0, st, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -16,6 +16,7 @@ constexpr int NFFT = 1024, HOP = 256, NBINS = NFFT / 2 + 1, THREADS = 256;
 
 __global__ void wave_peak_kernel(const float* __restrict__ wav, const long long* __restrict__ lengths, long long n_max,
                                  unsigned int* __restrict__ peak_bits) {
+  kr::pdl_entry();
   __shared__ float red[32];
   const int b = blockIdx.y;
   const long long n = lengths != nullptr ? lengths[b] : n_max;
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(THREADS)
 mel_stft_kernel(const float* __restrict__ wav, const long long* __restrict__ lengths, const float* __restrict__ peak,
                 const float* __restrict__ fb_t, float* __restrict__ out, long long n_max, int frames_max, int n_mels,
                 float log_eps) {
+  kr::pdl_entry();
   __shared__ float2 buf[2][NFFT];
   __shared__ float2 tw[NFFT / 2];
   __shared__ float pw[NBINS + 3];
@@ -106,7 +108,7 @@ extern "C" int kr_wave_peak(const float* wav, const long long* lengths, float* p
   cudaMemsetAsync(peak, 0, sizeof(float) * B, st);
   int bx = (int)((n_max + 256 * 8 - 1) / (256 * 8));
   if (bx > 64) bx = 64;
-  wave_peak_kernel<<<dim3(bx, B), 256, 0, st>>>(wav, lengths, n_max, reinterpret_cast<unsigned int*>(peak));
+  kr::launch(wave_peak_kernel, dim3(bx, B), 256, 0, st, wav, lengths, n_max, reinterpret_cast<unsigned int*>(peak));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -117,7 +119,7 @@ extern "C" int kr_mel_stft(const float* wav, const long long* lengths, const flo
   if (n_fft != NFFT || hop != HOP) { kr_set_error("kr_mel_stft: built for n_fft 1024 / hop 256"); return KR_ERR_UNSUPPORTED; }
   if (B <= 0 || frames_max <= 0) return KR_OK;
   if (n_max < NFFT / 2 + 1) { kr_set_error("kr_mel_stft: waveform shorter than the reflect padding"); return KR_ERR_ARG; }
-  mel_stft_kernel<<<dim3(frames_max, B), THREADS, 0, (cudaStream_t)stream>>>(wav, lengths, peak, fb_t, out, n_max,
+  kr::launch(mel_stft_kernel, dim3(frames_max, B), THREADS, 0, (cudaStream_t)stream, wav, lengths, peak, fb_t, out, n_max,
                                                                               frames_max, n_mels, log_eps);
   KR_CHECK_LAUNCH();
   return KR_OK;

@@ -29,6 +29,7 @@ __global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restri
                               const float* __restrict__ beta, bf16* __restrict__ y,
                               float* __restrict__ y32, float* __restrict__ mean_out,
                               float* __restrict__ rstd_out, int N, float eps) {
+  kr::pdl_entry();
   constexpr int D = NV * 128;
   const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) ln_bwd_kernel(const float* __re
                               const float* __restrict__ gamma, const float* dres, float* dx,
                               bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
                               float* __restrict__ dbeta, int N) {
+  kr::pdl_entry();
   constexpr int D = NV * 128;
   __shared__ float sm[WARPS][D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) ln_bwd_kernel(const float* __re
 template <int NV>
 __global__ void rms_resid_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gain,
                                      const float* resid, float* out, int N, float eps) {
+  kr::pdl_entry();
   constexpr int D = NV * 128;
   const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -160,6 +163,7 @@ template <int NV>
 __global__ void __launch_bounds__(WARPS * 32, 3) rms_resid_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y,
                                      const float* __restrict__ gain, bf16* __restrict__ dy,
                                      float* __restrict__ dgain, int N, float eps) {
+  kr::pdl_entry();
   constexpr int D = NV * 128;
   __shared__ float sm[WARPS][D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -265,6 +269,7 @@ __device__ __forceinline__ void load16_f32(const float* p, float* v) {
 }
 
 __global__ void __launch_bounds__(WARPS * 32) qkv_prep_fwd_kernel(const PrepParams p) {
+  kr::pdl_entry();
   const int lane = threadIdx.x & 31;
   const int sub = lane & 3;                // 16-element slice of the head
   const PrepPart& pp = p.part[blockIdx.y];
@@ -303,6 +308,7 @@ __global__ void __launch_bounds__(WARPS * 32) qkv_prep_fwd_kernel(const PrepPara
 }
 
 __global__ void __launch_bounds__(WARPS * 32, 3) qkv_prep_bwd_kernel(const PrepParams p) {
+  kr::pdl_entry();
   __shared__ float sm[64];
   if (threadIdx.x < 64) sm[threadIdx.x] = 0.f;
   __syncthreads();
@@ -391,7 +397,7 @@ extern "C" int kr_layernorm_fwd(const float* x, const float* gamma, const float*
                                 void* stream) {
   if (N <= 0) return KR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  DISPATCH_NV(D, (ln_fwd_kernel<NV><<<row_blocks(N), WARPS * 32, 0, st>>>(
+  DISPATCH_NV(D, (kr::launch(ln_fwd_kernel<NV>, row_blocks(N), WARPS * 32, 0, st, 
                      x, gamma, beta, reinterpret_cast<bf16*>(y_bf16), y_f32, mean, rstd, N, eps)));
   KR_CHECK_LAUNCH();
   return KR_OK;
@@ -402,7 +408,7 @@ extern "C" int kr_layernorm_bwd(const float* dy, const float* x, const float* me
                                 float* dgamma, float* dbeta, int N, int D, void* stream) {
   if (N <= 0) return KR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  DISPATCH_NV(D, (ln_bwd_kernel<NV><<<persistent_blocks(N), WARPS * 32, 0, st>>>(
+  DISPATCH_NV(D, (kr::launch(ln_bwd_kernel<NV>, persistent_blocks(N), WARPS * 32, 0, st, 
                      dy, x, mean, rstd, gamma, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dgamma,
                      dbeta, N)));
   KR_CHECK_LAUNCH();
@@ -413,7 +419,7 @@ extern "C" int kr_rmsnorm_resid_fwd(const float* y, const float* gain, const flo
                                     int N, int D, void* stream) {
   if (N <= 0) return KR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  DISPATCH_NV(D, (rms_resid_fwd_kernel<NV><<<row_blocks(N), WARPS * 32, 0, st>>>(y, gain, resid, out, N,
+  DISPATCH_NV(D, (kr::launch(rms_resid_fwd_kernel<NV>, row_blocks(N), WARPS * 32, 0, st, y, gain, resid, out, N,
                                                                                 FLT_EPSILON)));
   KR_CHECK_LAUNCH();
   return KR_OK;
@@ -423,7 +429,7 @@ extern "C" int kr_rmsnorm_resid_bwd(const float* dout, const float* y, const flo
                                     float* dgain, int N, int D, void* stream) {
   if (N <= 0) return KR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  DISPATCH_NV(D, (rms_resid_bwd_kernel<NV><<<persistent_blocks(N), WARPS * 32, 0, st>>>(
+  DISPATCH_NV(D, (kr::launch(rms_resid_bwd_kernel<NV>, persistent_blocks(N), WARPS * 32, 0, st, 
                      dout, y, gain, reinterpret_cast<bf16*>(dy_bf16), dgain, N, FLT_EPSILON)));
   KR_CHECK_LAUNCH();
   return KR_OK;
@@ -452,7 +458,7 @@ extern "C" int kr_qkv_prep_fwd(const void* in0, const void* in1, const void* in2
   const long long nb_ = (total + WARPS - 1) / WARPS;
   const int per_part = kNumSMs * 8 / n_parts;
   const int blocks = (int)(nb_ < per_part ? nb_ : per_part);
-  qkv_prep_fwd_kernel<<<dim3(blocks, n_parts), WARPS * 32, 0, st>>>(p);
+  kr::launch(qkv_prep_fwd_kernel, dim3(blocks, n_parts), WARPS * 32, 0, st, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -484,7 +490,7 @@ extern "C" int kr_qkv_prep_bwd(const void* in0, const void* in1, const void* in2
   const long long nb_ = (total + WARPS - 1) / WARPS;
   const int per_part = kNumSMs * 6 / n_parts;
   const int blocks = (int)(nb_ < per_part ? nb_ : per_part);
-  qkv_prep_bwd_kernel<<<dim3(blocks, n_parts), WARPS * 32, 0, st>>>(p);
+  kr::launch(qkv_prep_bwd_kernel, dim3(blocks, n_parts), WARPS * 32, 0, st, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -37,6 +37,7 @@ struct Ctrl {           // device-resident optimizer control block (mirrored lay
 __global__ void sqnorm_kernel(const float* __restrict__ g, const int* __restrict__ chunk_tensor,
                               const long long* __restrict__ chunk_start, const int* __restrict__ chunk_len,
                               float* __restrict__ sq, Ctrl* ctrl) {
+  kr::pdl_entry();
   __shared__ float red[32];
   const int c = blockIdx.x;
   const float* p = g + chunk_start[c];
@@ -70,6 +71,7 @@ struct CtrlCfg {
 __global__ void step_control_kernel(const float* __restrict__ sq, const float* __restrict__ preclip,
                                     float* __restrict__ tscale, int n_tensors, Ctrl* ctrl,
                                     const CtrlCfg cfg, const float* clip_override) {
+  kr::pdl_entry();
   __shared__ float red[32];
   float s = 0.f;
   for (int t = threadIdx.x; t < n_tensors; t += blockDim.x) {
@@ -127,6 +129,7 @@ struct AdamParams {
 };
 
 __global__ void adamw_kernel(const AdamParams a) {
+  kr::pdl_entry();
   __shared__ float red[32];
   if (a.ctrl->skip) return;
   const int c = blockIdx.x;
@@ -197,6 +200,7 @@ __global__ void wn_project_kernel(float* __restrict__ p, bf16* __restrict__ shad
                                   const long long* __restrict__ chunk_start, const int* __restrict__ chunk_len,
                                   const float* __restrict__ t_wnmax, const float* __restrict__ wsq,
                                   const Ctrl* ctrl) {
+  kr::pdl_entry();
   if (ctrl->skip) return;
   const int c = chunk_ids[blockIdx.x];
   const int t = chunk_tensor[c];
@@ -220,7 +224,7 @@ extern "C" int kr_optim_ctrl_size(void) { return (int)sizeof(Ctrl); }
 extern "C" int kr_grad_sqnorm(const float* grads, const int* chunk_tensor, const long long* chunk_start,
                               const int* chunk_len, int n_chunks, float* sq, void* ctrl, void* stream) {
   if (n_chunks <= 0) return KR_OK;
-  sqnorm_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(grads, chunk_tensor, chunk_start, chunk_len, sq, (Ctrl*)ctrl);
+  kr::launch(sqnorm_kernel, n_chunks, 256, 0, (cudaStream_t)stream, grads, chunk_tensor, chunk_start, chunk_len, sq, (Ctrl*)ctrl);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -235,7 +239,7 @@ extern "C" int kr_step_control(const float* sq, const float* preclip, float* tsc
   cfg.clip_norm = clip_norm; cfg.beta1 = beta1; cfg.beta2 = beta2; cfg.abs_floor = abs_floor;
   cfg.warmup_floor = warmup_floor; cfg.warmup_steps = warmup_steps; cfg.ema_alpha = ema_alpha;
   cfg.multiplier = multiplier; cfg.min_ema_steps = min_ema_steps; cfg.emergency_clip = emergency_clip;
-  step_control_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sq, preclip, tscale, n_tensors, (Ctrl*)ctrl, cfg, clip_override);
+  kr::launch(step_control_kernel, 1, 256, 0, (cudaStream_t)stream, sq, preclip, tscale, n_tensors, (Ctrl*)ctrl, cfg, clip_override);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -253,7 +257,7 @@ extern "C" int kr_adamw_step(float* p, const float* g, float* m, float* v, float
   a.chunk_tensor = chunk_tensor; a.chunk_start = chunk_start; a.chunk_len = chunk_len;
   a.t_group = t_group; a.tscale = tscale; a.g_lr = g_lr; a.g_wd = g_wd; a.t_wnmax = t_wnmax; a.wsq = wsq;
   a.ctrl = (const Ctrl*)ctrl; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.ema_decay = ema_decay;
-  adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(a);
+  kr::launch(adamw_kernel, n_chunks, 256, 0, (cudaStream_t)stream, a);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -263,7 +267,7 @@ extern "C" int kr_wn_project(float* p, void* shadow, const int* wn_chunk_ids, in
                              const int* chunk_tensor, const long long* chunk_start, const int* chunk_len,
                              const float* t_wnmax, const float* wsq, const void* ctrl, void* stream) {
   if (n_wn_chunks <= 0) return KR_OK;
-  wn_project_kernel<<<n_wn_chunks, 256, 0, (cudaStream_t)stream>>>(p, (bf16*)shadow, wn_chunk_ids, chunk_tensor, chunk_start, chunk_len, t_wnmax, wsq, (const Ctrl*)ctrl);
+  kr::launch(wn_project_kernel, n_wn_chunks, 256, 0, (cudaStream_t)stream, p, (bf16*)shadow, wn_chunk_ids, chunk_tensor, chunk_start, chunk_len, t_wnmax, wsq, (const Ctrl*)ctrl);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -17,6 +17,7 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 __global__ void glu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ u, long long n_vec, int FF) {
+  kr::pdl_entry();
   // one thread = 8 consecutive output columns
   const int vec_per_row = FF / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
@@ -38,6 +39,7 @@ __global__ void glu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ u,
 
 __global__ void glu_bwd_kernel(const bf16* __restrict__ du, const bf16* __restrict__ h,
                                bf16* __restrict__ dh, long long n_vec, int FF) {
+  kr::pdl_entry();
   const int vec_per_row = FF / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -63,6 +65,7 @@ __global__ void glu_bwd_kernel(const bf16* __restrict__ du, const bf16* __restri
 constexpr int CS_ROWS = 128;
 __global__ void colsum_bf16_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out,
                                    int N, int C) {
+  kr::pdl_entry();
   __shared__ float sm[8][256 + 8];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c0 = blockIdx.x * 256 + tx * 8;
@@ -97,6 +100,7 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ idx, const long l
                                  const float* __restrict__ emb, const float* __restrict__ semb,
                                  const float* __restrict__ pe, float* __restrict__ x, int N, int P, int D,
                                  float scale) {
+  kr::pdl_entry();
   const int vec_per_row = D / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)N * vec_per_row;
        i += (long long)gridDim.x * blockDim.x) {
@@ -115,6 +119,7 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ idx, const long l
 __global__ void embed_bwd_kernel(const float* __restrict__ dx, const long long* __restrict__ idx,
                                  const long long* __restrict__ stress, float* __restrict__ demb,
                                  float* __restrict__ dsemb, int N, int D, float scale) {
+  kr::pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)N * D;
        i += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(i / D), c = (int)(i % D);
@@ -125,6 +130,7 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dx, const long long* 
 }
 
 __global__ void shift_cast_kernel(const float* __restrict__ mel, bf16* __restrict__ out, int B, int T, int C) {
+  kr::pdl_entry();
   const long long total = (long long)B * T * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -134,6 +140,7 @@ __global__ void shift_cast_kernel(const float* __restrict__ mel, bf16* __restric
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  kr::pdl_entry();
   const long long n4 = n / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -150,6 +157,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict_
 template <typename TO>
 __global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ map,
                                     TO* __restrict__ dst, int R, int C) {
+  kr::pdl_entry();
   const int vec = C / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)R * vec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -170,6 +178,7 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __
 // dst_row[r] = src_row[map[r]]  (f32 -> f32); map[r] < 0 writes zeros.
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ map,
                                    float* __restrict__ dst, int R, int C) {
+  kr::pdl_entry();
   const int vec = C / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)R * vec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -193,7 +202,7 @@ extern "C" int kr_glu_fwd(const void* h, void* u, int N, int FF, void* stream) {
   if (N <= 0) return KR_OK;
   if (FF % 8) { kr_set_error("kr_glu: FF must be a multiple of 8"); return KR_ERR_ARG; }
   const long long n_vec = (long long)N * FF / 8;
-  glu_fwd_kernel<<<ew_blocks(n_vec), 256, 0, (cudaStream_t)stream>>>((const bf16*)h, (bf16*)u, n_vec, FF);
+  kr::launch(glu_fwd_kernel, ew_blocks(n_vec), 256, 0, (cudaStream_t)stream, (const bf16*)h, (bf16*)u, n_vec, FF);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -201,7 +210,7 @@ extern "C" int kr_glu_bwd(const void* du, const void* h, void* dh, int N, int FF
   if (N <= 0) return KR_OK;
   if (FF % 8) { kr_set_error("kr_glu: FF must be a multiple of 8"); return KR_ERR_ARG; }
   const long long n_vec = (long long)N * FF / 8;
-  glu_bwd_kernel<<<ew_blocks(n_vec), 256, 0, (cudaStream_t)stream>>>((const bf16*)du, (const bf16*)h, (bf16*)dh, n_vec, FF);
+  kr::launch(glu_bwd_kernel, ew_blocks(n_vec), 256, 0, (cudaStream_t)stream, (const bf16*)du, (const bf16*)h, (bf16*)dh, n_vec, FF);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -209,7 +218,7 @@ extern "C" int kr_colsum_bf16(const void* x, long long ld, float* out, int N, in
   if (N <= 0 || C <= 0) return KR_OK;
   if ((C % 8) || (ld % 8)) { kr_set_error("kr_colsum_bf16: C and ld must be multiples of 8"); return KR_ERR_ARG; }
   dim3 grid((C + 255) / 256, (N + CS_ROWS - 1) / CS_ROWS), block(32, 8);
-  colsum_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, N, C);
+  kr::launch(colsum_bf16_kernel, grid, block, 0, (cudaStream_t)stream, (const bf16*)x, ld, out, N, C);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -217,7 +226,7 @@ extern "C" int kr_embed_fwd(const long long* idx, const long long* stress, const
                             const float* stress_emb, const float* pe, float* x, int N, int P, int D,
                             void* stream) {
   if (N <= 0) return KR_OK;
-  embed_fwd_kernel<<<ew_blocks((long long)N * D / 4), 256, 0, (cudaStream_t)stream>>>(
+  kr::launch(embed_fwd_kernel, ew_blocks((long long)N * D / 4), 256, 0, (cudaStream_t)stream, 
       idx, stress, emb, stress_emb, pe, x, N, P, D, sqrtf((float)D));
   KR_CHECK_LAUNCH();
   return KR_OK;
@@ -225,20 +234,20 @@ extern "C" int kr_embed_fwd(const long long* idx, const long long* stress, const
 extern "C" int kr_embed_bwd(const float* dx, const long long* idx, const long long* stress, float* demb,
                             float* dstress_emb, int N, int D, void* stream) {
   if (N <= 0) return KR_OK;
-  embed_bwd_kernel<<<ew_blocks((long long)N * D), 256, 0, (cudaStream_t)stream>>>(
+  kr::launch(embed_bwd_kernel, ew_blocks((long long)N * D), 256, 0, (cudaStream_t)stream, 
       dx, idx, stress, demb, dstress_emb, N, D, sqrtf((float)D));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 extern "C" int kr_shift_cast(const float* mel, void* out, int B, int T, int C, void* stream) {
   if (B <= 0 || T <= 0) return KR_OK;
-  shift_cast_kernel<<<ew_blocks((long long)B * T * C), 256, 0, (cudaStream_t)stream>>>(mel, (bf16*)out, B, T, C);
+  kr::launch(shift_cast_kernel, ew_blocks((long long)B * T * C), 256, 0, (cudaStream_t)stream, mel, (bf16*)out, B, T, C);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 extern "C" int kr_cast_bf16(const float* in, void* out, long long n, void* stream) {
   if (n <= 0) return KR_OK;
-  cast_bf16_kernel<<<ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(in, (bf16*)out, n);
+  kr::launch(cast_bf16_kernel, ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream, in, (bf16*)out, n);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -247,26 +256,28 @@ extern "C" int kr_scatter_rows(const float* src, const int* map, void* dst, int 
   if (R <= 0) return KR_OK;
   if (C % 4) { kr_set_error("kr_scatter_rows: C must be a multiple of 4"); return KR_ERR_ARG; }
   const int blocks = ew_blocks((long long)R * C / 4);
-  if (dst_bf16) scatter_rows_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, map, (bf16*)dst, R, C);
-  else          scatter_rows_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, map, (float*)dst, R, C);
+  if (dst_bf16) kr::launch(scatter_rows_kernel<bf16>, blocks, 256, 0, (cudaStream_t)stream, src, map, (bf16*)dst, R, C);
+  else          kr::launch(scatter_rows_kernel<float>, blocks, 256, 0, (cudaStream_t)stream, src, map, (float*)dst, R, C);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 extern "C" int kr_gather_rows(const float* src, const int* map, float* dst, int R, int C, void* stream) {
   if (R <= 0) return KR_OK;
   if (C % 4) { kr_set_error("kr_gather_rows: C must be a multiple of 4"); return KR_ERR_ARG; }
-  gather_rows_kernel<<<ew_blocks((long long)R * C / 4), 256, 0, (cudaStream_t)stream>>>(src, map, dst, R, C);
+  kr::launch(gather_rows_kernel, ew_blocks((long long)R * C / 4), 256, 0, (cudaStream_t)stream, src, map, dst, R, C);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 
 namespace {
 __global__ void eq_mask_kernel(const long long* __restrict__ idx, long long value, unsigned char* __restrict__ out, long long n) {
+  kr::pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = idx[i] == value ? 1 : 0;
 }
 // any non-finite value in x -> flag |= bit
 __global__ void nonfinite_flag_kernel(const float* __restrict__ x, long long n, int* flag, int bit) {
+  kr::pdl_entry();
   bool bad = false;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     bad |= !isfinite(x[i]);
@@ -277,14 +288,14 @@ __global__ void nonfinite_flag_kernel(const float* __restrict__ x, long long n, 
 // out[i] = (idx[i] == value)  — the reference's text padding mask `phoneme_indices == 0` (model/model.py:587)
 extern "C" int kr_eq_mask_i64(const long long* idx, long long value, unsigned char* out, long long n, void* stream) {
   if (n <= 0) return KR_OK;
-  eq_mask_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(idx, value, out, n);
+  kr::launch(eq_mask_kernel, ew_blocks(n), 256, 0, (cudaStream_t)stream, idx, value, out, n);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 // finite-output guard without a host sync per tensor (reference training/trainer.py:3233-3256)
 extern "C" int kr_nonfinite_flag(const float* x, long long n, int* flag, int bit, void* stream) {
   if (n <= 0) return KR_OK;
-  nonfinite_flag_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, n, flag, bit);
+  kr::launch(nonfinite_flag_kernel, ew_blocks(n), 256, 0, (cudaStream_t)stream, x, n, flag, bit);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -23,6 +23,7 @@ constexpr int WARPS = 8;
 // ---------------------------------------------------------------------------------------------
 __global__ void lr_index_kernel(const long long* __restrict__ dur, int* __restrict__ idx,
                                 int* __restrict__ lengths, int P, int Tp) {
+  kr::pdl_entry();
   extern __shared__ int cs[];  // P ints (double-buffered scan: 2*P)
   const int b = blockIdx.x;
   int* a = cs;
@@ -54,6 +55,7 @@ __global__ void lr_index_kernel(const long long* __restrict__ dur, int* __restri
 }
 
 __global__ void range_flag_kernel(const float* __restrict__ x, long long n, int* flag) {
+  kr::pdl_entry();
   bool bad = false;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -91,6 +93,7 @@ struct AdaptParams {
 };
 
 __global__ void expand_adapt_kernel(const AdaptParams p) {
+  kr::pdl_entry();
   __shared__ float sb[2][256];
   for (int i = threadIdx.x; i < p.nb; i += blockDim.x) { sb[0][i] = p.pbins[i]; sb[1][i] = p.ebins[i]; }
   __syncthreads();
@@ -149,6 +152,7 @@ __global__ void expand_adapt_kernel(const AdaptParams p) {
 __global__ void adapt_bwd_kernel(const float* __restrict__ dmem, const int* __restrict__ p_idx,
                                  const int* __restrict__ e_idx, float* __restrict__ dpemb,
                                  float* __restrict__ deemb, long long rows, int D) {
+  kr::pdl_entry();
   const int lane = threadIdx.x & 31;
   for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows;
        r += (long long)gridDim.x * WARPS) {
@@ -167,6 +171,7 @@ __global__ void adapt_bwd_kernel(const float* __restrict__ dmem, const int* __re
 // ---------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const float* __restrict__ x, const int* __restrict__ row_group,
                                 double* __restrict__ stats, int R, int C) {
+  kr::pdl_entry();
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * WARPS + (threadIdx.x >> 5); r < R; r += gridDim.x * WARPS) {
     const int g = row_group[r];
@@ -192,6 +197,7 @@ __global__ void gn_apply_relu_kernel(const float* __restrict__ x, const int* __r
                                      const double* __restrict__ stats, const int* __restrict__ group_rows,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      bf16* __restrict__ out, int R, int C) {
+  kr::pdl_entry();
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * WARPS + (threadIdx.x >> 5); r < R; r += gridDim.x * WARPS) {
     const int g = row_group[r];
@@ -211,6 +217,7 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const float* __
                                     const int* __restrict__ group_rows, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, double* __restrict__ gsum,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int C) {
+  kr::pdl_entry();
   __shared__ float sm[2][WARPS][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float ag[8], ab[8];
@@ -253,6 +260,7 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const float* __
                                     const int* __restrict__ group_rows, const double* __restrict__ gsum,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     bf16* __restrict__ dx, int R, int C) {
+  kr::pdl_entry();
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * WARPS + (threadIdx.x >> 5); r < R; r += gridDim.x * WARPS) {
     const int g = row_group[r];
@@ -283,6 +291,7 @@ __global__ void vp_head_fwd_kernel(const bf16* __restrict__ h, const int* __rest
                                    const float* __restrict__ w, const float* __restrict__ bias,
                                    const unsigned char* __restrict__ mask, float* __restrict__ out,
                                    int n_tok, int L, int F, int chunk) {
+  kr::pdl_entry();
   const int lane = threadIdx.x & 31;
   for (int t = blockIdx.x * WARPS + (threadIdx.x >> 5); t < n_tok; t += gridDim.x * WARPS) {
     const int pos = t % L;
@@ -302,6 +311,7 @@ __global__ void vp_head_bwd_kernel(const float* __restrict__ dout, const bf16* _
                                    const unsigned char* __restrict__ mask, bf16* __restrict__ dh,
                                    float* __restrict__ dw, float* __restrict__ dbias, int R, int L, int F,
                                    int chunk) {
+  kr::pdl_entry();
   __shared__ float sm[WARPS][256];
   __shared__ float sb[WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -346,6 +356,7 @@ __global__ void vp_head_bwd_kernel(const float* __restrict__ dout, const bf16* _
 
 // Wd[c, j*Co + o] = W2[o, (2-j)*Ci + c]  (W2 = master conv weight in [Co, 3, Ci] layout)
 __global__ void conv_dgrad_shadow_kernel(const float* __restrict__ w2, bf16* __restrict__ wd, int Co, int Ci) {
+  kr::pdl_entry();
   const long long total = (long long)Ci * 3 * Co;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -367,7 +378,7 @@ inline int warp_blocks(long long rows, int cap_mult = 8) {
 extern "C" int kr_lr_index(const long long* dur, int* idx, int* lengths, int B, int P, int Tp, void* stream) {
   if (B <= 0) return KR_OK;
   if (P > 4096) { kr_set_error("kr_lr_index: P > 4096 unsupported"); return KR_ERR_UNSUPPORTED; }
-  lr_index_kernel<<<B, 256, 2 * P * sizeof(int), (cudaStream_t)stream>>>(dur, idx, lengths, P, Tp);
+  kr::launch(lr_index_kernel, B, 256, 2 * P * sizeof(int), (cudaStream_t)stream, dur, idx, lengths, P, Tp);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -375,7 +386,7 @@ extern "C" int kr_lr_index(const long long* dur, int* idx, int* lengths, int B, 
 extern "C" int kr_range_flag(const float* x, long long n, int* flag, void* stream) {
   if (n <= 0) return KR_OK;
   long long b = (n + 255) / 256;
-  range_flag_kernel<<<(int)(b < 592 ? b : 592), 256, 0, (cudaStream_t)stream>>>(x, n, flag);
+  kr::launch(range_flag_kernel, (int)(b < 592 ? b : 592), 256, 0, (cudaStream_t)stream, x, n, flag);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -394,7 +405,7 @@ extern "C" int kr_expand_adapt(const float* enc, const int* idx, const int* leng
   p.xpad = (bf16*)xpad; p.mem = (bf16*)mem; p.p_idx = p_idx; p.e_idx = e_idx; p.fmask_t = fmask_t;
   p.fmask_p = fmask_p; p.B = B; p.P = P; p.D = D; p.Tp = Tp; p.T = T; p.Tt = Tt; p.nb = nb;
   const long long rows = (long long)B * (Tp > T ? Tp : T);
-  expand_adapt_kernel<<<warp_blocks(rows, 16), WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  kr::launch(expand_adapt_kernel, warp_blocks(rows, 16), WARPS * 32, 0, (cudaStream_t)stream, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -402,7 +413,7 @@ extern "C" int kr_expand_adapt(const float* enc, const int* idx, const int* leng
 extern "C" int kr_adapt_bwd(const float* dmem, const int* p_idx, const int* e_idx, float* dpemb,
                             float* deemb, long long rows, int D, void* stream) {
   if (rows <= 0) return KR_OK;
-  adapt_bwd_kernel<<<warp_blocks(rows, 16), WARPS * 32, 0, (cudaStream_t)stream>>>(dmem, p_idx, e_idx, dpemb, deemb, rows, D);
+  kr::launch(adapt_bwd_kernel, warp_blocks(rows, 16), WARPS * 32, 0, (cudaStream_t)stream, dmem, p_idx, e_idx, dpemb, deemb, rows, D);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -414,9 +425,9 @@ extern "C" int kr_gn_fwd(const float* x, const int* row_group, const int* group_
   if (C > 256 || (C % 32)) { kr_set_error("kr_gn: C must be a multiple of 32, <= 256"); return KR_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * G, st) != cudaSuccess) { kr_set_error("memset failed"); return KR_ERR_CUDA; }
-  gn_stats_kernel<<<warp_blocks(R), WARPS * 32, 0, st>>>(x, row_group, stats, R, C);
+  kr::launch(gn_stats_kernel, warp_blocks(R), WARPS * 32, 0, st, x, row_group, stats, R, C);
   KR_CHECK_LAUNCH();
-  gn_apply_relu_kernel<<<warp_blocks(R), WARPS * 32, 0, st>>>(x, row_group, stats, group_rows, gamma, beta, (bf16*)out_bf16, R, C);
+  kr::launch(gn_apply_relu_kernel, warp_blocks(R), WARPS * 32, 0, st, x, row_group, stats, group_rows, gamma, beta, (bf16*)out_bf16, R, C);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -428,9 +439,9 @@ extern "C" int kr_gn_bwd(const void* dy_bf16, const float* x, const int* row_gro
   if (C > 256 || (C % 32)) { kr_set_error("kr_gn: C must be a multiple of 32, <= 256"); return KR_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(gsum, 0, sizeof(double) * 2 * G, st) != cudaSuccess) { kr_set_error("memset failed"); return KR_ERR_CUDA; }
-  gn_bwd_stats_kernel<<<warp_blocks(R, 2), WARPS * 32, 0, st>>>((const bf16*)dy_bf16, x, row_group, stats, group_rows, gamma, beta, gsum, dgamma, dbeta, R, C);
+  kr::launch(gn_bwd_stats_kernel, warp_blocks(R, 2), WARPS * 32, 0, st, (const bf16*)dy_bf16, x, row_group, stats, group_rows, gamma, beta, gsum, dgamma, dbeta, R, C);
   KR_CHECK_LAUNCH();
-  gn_bwd_apply_kernel<<<warp_blocks(R), WARPS * 32, 0, st>>>((const bf16*)dy_bf16, x, row_group, stats, group_rows, gsum, gamma, beta, (bf16*)dx_bf16, R, C);
+  kr::launch(gn_bwd_apply_kernel, warp_blocks(R), WARPS * 32, 0, st, (const bf16*)dy_bf16, x, row_group, stats, group_rows, gsum, gamma, beta, (bf16*)dx_bf16, R, C);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -439,7 +450,7 @@ extern "C" int kr_vp_head_fwd(const void* h, const int* row_of_tok, const float*
                               const unsigned char* mask, float* out, int n_tok, int L, int F, int chunk,
                               void* stream) {
   if (n_tok <= 0) return KR_OK;
-  vp_head_fwd_kernel<<<warp_blocks(n_tok), WARPS * 32, 0, (cudaStream_t)stream>>>((const bf16*)h, row_of_tok, w, bias, mask, out, n_tok, L, F, chunk);
+  kr::launch(vp_head_fwd_kernel, warp_blocks(n_tok), WARPS * 32, 0, (cudaStream_t)stream, (const bf16*)h, row_of_tok, w, bias, mask, out, n_tok, L, F, chunk);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -449,7 +460,7 @@ extern "C" int kr_vp_head_bwd(const float* dout, const void* h, const int* tok_o
                               int F, int chunk, void* stream) {
   if (R <= 0) return KR_OK;
   if (F > 256) { kr_set_error("kr_vp_head: F <= 256 required"); return KR_ERR_ARG; }
-  vp_head_bwd_kernel<<<warp_blocks(R, 2), WARPS * 32, 0, (cudaStream_t)stream>>>(dout, (const bf16*)h, tok_of_row, w, mask, (bf16*)dh, dw, dbias, R, L, F, chunk);
+  kr::launch(vp_head_bwd_kernel, warp_blocks(R, 2), WARPS * 32, 0, (cudaStream_t)stream, dout, (const bf16*)h, tok_of_row, w, mask, (bf16*)dh, dw, dbias, R, L, F, chunk);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -457,7 +468,7 @@ extern "C" int kr_vp_head_bwd(const float* dout, const void* h, const int* tok_o
 extern "C" int kr_conv_dgrad_shadow(const float* w2, void* wd, int Co, int Ci, void* stream) {
   const long long total = (long long)Ci * 3 * Co;
   long long b = (total + 255) / 256;
-  conv_dgrad_shadow_kernel<<<(int)(b < 1184 ? b : 1184), 256, 0, (cudaStream_t)stream>>>(w2, (bf16*)wd, Co, Ci);
+  kr::launch(conv_dgrad_shadow_kernel, (int)(b < 1184 ? b : 1184), 256, 0, (cudaStream_t)stream, w2, (bf16*)wd, Co, Ci);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -473,6 +484,7 @@ namespace {
 template <typename T>
 __global__ void spec_augment_kernel(T* __restrict__ x, const int* __restrict__ spans, int B, int Tn, int D, int n_time,
                                     int n_feat) {
+  kr::pdl_entry();
   const int b = blockIdx.y;
   const int* sp = spans + (long long)b * (n_time + n_feat) * 2;
   T* xb = x + (long long)b * Tn * D;
@@ -503,8 +515,8 @@ extern "C" int kr_spec_augment(void* x, int is_f32, const int* spans, int B, int
                                void* stream) {
   if (B <= 0 || T <= 0 || (n_time + n_feat) <= 0) return KR_OK;
   dim3 grid(8, B);
-  if (is_f32) spec_augment_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, spans, B, T, D, n_time, n_feat);
-  else spec_augment_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((bf16*)x, spans, B, T, D, n_time, n_feat);
+  if (is_f32) kr::launch(spec_augment_kernel<float>, grid, 256, 0, (cudaStream_t)stream, (float*)x, spans, B, T, D, n_time, n_feat);
+  else kr::launch(spec_augment_kernel<bf16>, grid, 256, 0, (cudaStream_t)stream, (bf16*)x, spans, B, T, D, n_time, n_feat);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -88,6 +88,9 @@ class AcousticEngine:
         # whole step is still one capturable DAG): weight-gradient GEMMs + bias column sums (off
         # the critical path), the variance predictors, and the encoder backward, which is disjoint
         # from the decoder backward because the length regulator detaches (utils/lengths.py:30).
+        import os
+        if os.environ.get("KR_STREAMS", "1") == "0":
+            multi_stream = False
         self.multi_stream = multi_stream
         self._side = {k: torch.cuda.Stream(device=self.device) for k in ("w0", "w1", "vp", "enc", "kv")} if multi_stream else {}
         self._w_rr = 0
@@ -112,7 +115,7 @@ class AcousticEngine:
         return t
 
     def _zeros(self, *shape, dtype=F32):
-        t = torch.zeros(*shape, dtype=dtype, device=self.device)
+        t = ops.zero_(torch.empty(*shape, dtype=dtype, device=self.device))
         self._live.append(t)
         return t
 
@@ -596,4 +599,4 @@ class AcousticEngine:
         self.spec_n_time, self.spec_n_feat = n_time, n_feat
 
     def zero_grad(self):
-        self.store.grads.zero_()
+        ops.zero_(self.store.grads)

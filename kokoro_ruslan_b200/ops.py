@@ -403,3 +403,10 @@ def spec_augment(x, spans, n_time: int, n_feat: int):
     B, T, D = x.shape
     check(lib().kr_spec_augment(_ptr(x), c_int(int(x.dtype == torch.float32)), _ptr(spans), c_int(B), c_int(T),
                                 c_int(D), c_int(n_time), c_int(n_feat), _stream()), "kr_spec_augment")
+
+
+def zero_(t: torch.Tensor) -> torch.Tensor:
+    """In-place zero fill of a contiguous tensor through cudaMemsetAsync (no fill kernel)."""
+    assert t.is_contiguous()
+    check(lib().kr_memset_zero(_ptr(t), c_ll(t.numel() * t.element_size()), _stream()), "kr_memset_zero")
+    return t

@@ -181,8 +181,9 @@ class FusedAdamW:
         """One optimizer step on store.grads (already all-reduced when data-parallel)."""
         c, s = self.cfg, self.store
         L = lib()
-        self.sq.zero_()
-        self.wsq.zero_()
+        from .ops import zero_
+        zero_(self.sq)
+        zero_(self.wsq)
         check(L.kr_grad_sqnorm(_ptr(s.grads), _ptr(self.chunk_tensor), _ptr(self.chunk_start), _ptr(self.chunk_len),
                                c_int(self.n_chunks), _ptr(self.sq), _ptr(self.ctrl), _stream()), "kr_grad_sqnorm")
         check(L.kr_step_control(_ptr(self.sq), _ptr(self.t_preclip), _ptr(self.tscale), c_int(self.n_tensors),

@@ -15,6 +15,7 @@ DOCS = {
     "kr_last_error": "Thread-local message of the last failing call (every entry point returns 0 or a negative KR_ERR_* code; the Python side maps non-zero to RuntimeError, which the reference trainer's per-batch handler expects: training/trainer.py:2679-2686).",
     "kr_abi_version": "ABI version of this header (1).",
     "kr_launch_count": "Number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches evidence).",
+    "kr_memset_zero": "Asynchronous zero fill (memset node under graph capture) — replaces the torch fill kernels for gradient / scratch buffers.",
     "kr_device_cc": "Compute capability (major*10+minor) of the current device; 100 on B200.",
     "kr_gemm_bf16": "tcgen05 GEMM C[M,N] (+)= alpha*A[M,K]*B[N,K]^T (+bias[n]) (+resid[m % resid_mod, n]); bf16 operands staged by TMA, fp32 accumulation in TMEM. a_mn_major / b_mn_major select the [K,rows] storage that weight- and data-gradient GEMMs read in place. epi_mode 0 = bf16 store, 1 = fp32 store, 2 = fp32 atomic accumulate (split-K). Replaces every nn.Linear on the path: model/transformers.py:228,258-259,434 (Q/K/V/out projections), transformers.py:105-111 (GLU FFN), model/model.py:519-531,561 (mel in/out projections), and — through an overlapping-row view — the k=3 nn.Conv1d of model/variance_predictor.py:46.",
     "kr_gemm_ex": "Persistent tcgen05 GEMM / implicit-GEMM conv1d with the full fused epilogue (see kr_gemm_args). kr_gemm_bf16 is the plain-argument subset. The conv mode replaces nn.Conv1d / nn.ConvTranspose1d (polyphase) of inference/hifigan_vocoder.py:31-133.",
