@@ -49,7 +49,7 @@ def _peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period: float = 0.1):
+    def __init__(self, index: int, period: float = 0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -162,6 +162,59 @@ def run_reference(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# HiFi-GAN vocoder leg (second half of BASELINE.json's metric): 16 mels x 800 frames -> 22.05 kHz audio
+# ----------------------------------------------------------------------------------------------
+def hifigan_leg(peaks, steps: int = 10, B: int = 16, T: int = 800):
+    import torch
+    from kokoro_ruslan_b200 import _lib
+    from kokoro_ruslan_b200.hifigan import HiFiGANConfig, HiFiGANGenerator
+    gen = HiFiGANGenerator(HiFiGANConfig.get_default_config(), device="cuda")
+    g = torch.Generator().manual_seed(0)
+    mel_host = (torch.randn(B, 80, T, generator=g) * 2.0 - 5.0).pin_memory()
+    mel_dev = mel_host.cuda()
+    out_host = torch.empty(B, 1, T * 256).pin_memory()
+    for _ in range(3):
+        gen(mel_dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        gen(mel_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    e0.record()
+    for _ in range(steps):
+        out_host.copy_(gen(mel_host), non_blocking=True)      # H2D of the mels + D2H of the audio, every call
+        torch.cuda.synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / steps
+    samples = B * T * 256
+    flops = 614.1e6 * B * T                                   # 614.1 MFLOP per mel frame
+    alg_bytes = 2.03e6 * B * T                                # ... and 2.03 MB (bf16) of activation traffic
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_hifigan_traffic.json")) as f:
+            tr = json.load(f)["kr_gemm_kernel"]
+        traffic = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / 2.0    # the capture holds two forwards
+    except Exception:
+        pass
+    return {"metric": "hifigan_audio_samples_per_sec", "value": samples / (ms * 1e-3), "unit": "samples/s",
+            "ms_per_batch": ms, "config": {"workload": "HiFi-GAN v1 generator, batch=16 mels x 800 frames -> 204800 samples each",
+                                           "dtype": "bf16 tcgen05 implicit-GEMM convs, fp32 residual stream"},
+            "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_batch": ms_e2e,
+                    "h2d_bytes_per_step": mel_host.numel() * 4, "d2h_bytes_per_step": samples * 4},
+            "roofline": {"bound": "hbm", "kernel": "kr_gemm_kernel conv mode (77 launches per forward)",
+                         "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": alg_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
+                         "tensor_frac": flops / (ms * 1e-3) / 1e12 / peaks["tf_sustained"],
+                         "note": "algorithmic bytes = 2.03 MB/frame (bf16, each conv reads its input and writes its output "
+                                 "once); traffic = ncu dram bytes of the conv kernels per forward"},
+            "gpu_launches": gen.launches_last_forward * steps * 2}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -288,6 +341,26 @@ def run_ours(args):
     except Exception as exc:  # the bench line must still be printed
         roof = {"bound": "tensor", "error": repr(exc)}
 
+    # ---- measured DRAM traffic of the dominant kernel (ncu capture of this command, profiles/) -------------
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_step_traffic.json")) as f:
+            tr = json.load(f)["kr_gemm_kernel"]
+        if roof is not None and "error" not in roof:
+            roof["traffic"] = tr["traffic_per_launch"]
+            roof["traffic_note"] = ("mean dram__bytes_read+write per kr_gemm_kernel launch, ncu --clock-control none on "
+                                    "tools/one_step.py (profiles/r01_step_traffic.txt); algorithmic bytes per launch = "
+                                    "%.1f MB" % (sum(r["bytes"] for r in rows if r["op"].startswith("gemm")) / max(1, g_n) / 1e6))
+    except Exception:
+        pass
+
+    # ---- second headline metric: HiFi-GAN vocoder inference (BASELINE config 5) ----------------------------
+    hifi = None
+    if world == 1 and not args.no_hifigan:
+        try:
+            hifi = hifigan_leg(peaks, steps=max(5, args.steps // 2))
+        except Exception as exc:
+            hifi = {"error": repr(exc)}
+
     # ---- CPU baseline (oracle port, bounded sample) ---------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -309,7 +382,7 @@ def run_ours(args):
             "e2e": {"value": frames_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d_bytes + 8 + 40, "d2h_bytes_per_step": 24},
             "gpu_launches": launches_per_step * args.steps * 2, "launches_per_step": launches_per_step,
-            "clocks": clocks, "losses_first": first_losses, "losses_last": final_losses, "top_ops": top_ops,
+            "hifigan": hifi, "clocks": clocks, "losses_first": first_losses, "losses_last": final_losses, "top_ops": top_ops,
             "lib": str(_lib.LIB_PATH)}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -324,6 +397,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hifigan", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
