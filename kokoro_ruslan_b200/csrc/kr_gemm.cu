@@ -24,6 +24,7 @@
 #include "kr_common.cuh"
 #include "kokoro_b200.h"
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -43,6 +44,7 @@ struct GemmParams {
   int batch, splits, kb_per_split, total_kb;
   int m_tiles, n_tiles, total_tiles;
   int conv_taps, conv_dil, conv_row0, conv_cin_blocks;
+  int conv_slab, slab_rows;   // slab mode: one [slab_rows x 64ch] load per (tile, chunk); taps = row offsets into it
   void* C; long long ldc, c_batch_stride; int c_mode;
   bf16* C2; long long ldc2, c2_batch_stride; float act_slope;
   const float* bias;
@@ -206,6 +208,19 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int kb0 = tc.split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
         const int bzb = p.b_shared ? 0 : tc.bz;
+        if (p.conv_slab) {
+          // implicit GEMM proper: every activation row of the tile (+ the (taps-1)*dil halo rows) is fetched
+          // ONCE per 64-channel chunk; the taps are row-shifted views of the same smem slab.
+          const int s = ring_s;
+          const uint32_t ph = ring_ph;
+          if (++ring_s == STAGES) { ring_s = 0; ring_ph ^= 1u; }
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = ring + s * p.stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
+          for (int cb = 0; cb < p.conv_cin_blocks; ++cb)
+            tma_load_3d(sa + cb * p.slab_rows * 128, &tmap_a, &full_bar[s], cb * BLOCK_K, p.conv_row0 + m0, tc.bz);
+          continue;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           const int s = ring_s;
           const uint32_t ph = ring_ph;
@@ -257,6 +272,35 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
+        if (p.conv_slab) {
+          const int s = ring_s;
+          const uint32_t ph = ring_ph;
+          if (++ring_s == STAGES) { ring_s = 0; ring_ph ^= 1u; }
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t slab = smem_u32(ring + s * p.stage_bytes);
+          bool first = true;
+          for (int tap = 0; tap < p.conv_taps; ++tap) {
+            for (int cb = 0; cb < p.conv_cin_blocks; ++cb) {
+              // rows [tap*dil, tap*dil + 128) of chunk cb's slab.  The start address is row-shifted (not 1024-byte
+              // aligned); the 128B swizzle is a function of the absolute smem address on sm_100a, so TMA's
+              // placement and the UMMA read agree with the descriptor's base-offset field left at 0 (measured:
+              // bit-identical to re-fetching every tap; setting base_offset = (addr >> 7) & 7 is WRONG here)
+              const uint32_t sa = slab + cb * p.slab_rows * 128 + tap * p.conv_dil * 128;
+              const uint32_t sb = smem_u32(b_res + (tap * p.conv_cin_blocks + cb) * L::B_BYTES);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+                const uint64_t db = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+                umma_bf16_ss(tmem_d, da, db, idesc, first ? 0u : 1u);
+                first = false;
+              }
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          umma_commit(&tmem_full_bar[buf]);
+          continue;
+        }
         for (int i = 0; i < num_kb; ++i) {
           const int s = ring_s;
           const uint32_t ph = ring_ph;
@@ -392,7 +436,8 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, bool want_resident, cudaStream_t st) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta_slab, const CUtensorMap& tb, GemmParams p, bool want_resident,
+                int want_slab_rows, cudaStream_t st) {
   using L = SmemLayout<BLOCK_N>;
   auto kern = kr_gemm_kernel<BLOCK_N, A_MN, B_MN>;
   static bool attr_set = false;
@@ -408,24 +453,31 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, bool
   if (want_resident && bres + 4LL * L::A_BYTES <= avail) {
     p.b_resident = 1; p.b_res_bytes = (int)bres; p.stage_bytes = L::A_BYTES;
   }
+  p.conv_slab = 0; p.slab_rows = 0;
+  if (p.b_resident && !A_MN && p.conv_taps > 1 && want_slab_rows > 0) {
+    const int slab_bytes = p.conv_cin_blocks * want_slab_rows * 128;
+    if (p.b_res_bytes + 2LL * slab_bytes <= avail) {
+      p.conv_slab = 1; p.slab_rows = want_slab_rows; p.stage_bytes = slab_bytes;
+    }
+  }
   int stages = (avail - p.b_res_bytes) / p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > 8 && !p.b_resident) stages = 8;
   p.stages = stages;
   const int smem_bytes = RING_OFFSET0 + p.b_res_bytes + stages * p.stage_bytes + 1024;
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  kr::launch(kern, grid, GEMM_THREADS, smem_bytes, st, ta, tb, p);
+  kr::launch(kern, grid, GEMM_THREADS, smem_bytes, st, p.conv_slab ? ta_slab : ta, tb, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 
 template <int BLOCK_N>
-int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, bool res,
-                   cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_gemm<BLOCK_N, false, false>(ta, tb, p, res, st);
-  if (!a_mn && b_mn) return launch_gemm<BLOCK_N, false, true>(ta, tb, p, res, st);
-  if (a_mn && !b_mn) return launch_gemm<BLOCK_N, true, false>(ta, tb, p, res, st);
-  return launch_gemm<BLOCK_N, true, true>(ta, tb, p, res, st);
+int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& ta_slab, const CUtensorMap& tb,
+                   const GemmParams& p, bool res, int slab_rows, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_gemm<BLOCK_N, false, false>(ta, ta_slab, tb, p, res, slab_rows, st);
+  if (!a_mn && b_mn) return launch_gemm<BLOCK_N, false, true>(ta, ta_slab, tb, p, res, 0, st);
+  if (a_mn && !b_mn) return launch_gemm<BLOCK_N, true, false>(ta, ta_slab, tb, p, res, 0, st);
+  return launch_gemm<BLOCK_N, true, true>(ta, ta_slab, tb, p, res, 0, st);
 }
 
 }  // namespace
@@ -577,10 +629,22 @@ extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // resident weights: one N tile, no split-K, weights shared by the batch, and enough tiles per CTA to pay off
   const bool res = p.n_tiles == 1 && splits == 1 && (batch == 1 || b_shared) && p.total_tiles >= 2 * kNumSMs;
-  if (block_n == 256) return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ta, tb, p, res, st);
-  if (block_n == 192) return dispatch_major<192>(a->a_mn_major, a->b_mn_major, ta, tb, p, res, st);
-  if (block_n == 128) return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ta, tb, p, res, st);
-  return dispatch_major<64>(a->a_mn_major, a->b_mn_major, ta, tb, p, res, st);
+  // slab tensor map: same tensor, box = all rows a tile touches (128 + (taps-1)*dil, rounded up to 8)
+  CUtensorMap ta_slab = ta;
+  int slab_rows = 0;
+  if (conv && res && a->conv_taps > 1 && !a->no_slab) {
+    slab_rows = (BLOCK_M + (a->conv_taps - 1) * a->conv_dil + 7) / 8 * 8;
+    if (slab_rows <= 256) {
+      rc = kr_make_tmap_bf16_3d(&ta_slab, a->A, a->conv_cin, a->a_rows, batch, a->lda, bstride_a, BLOCK_K, slab_rows);
+      if (rc != KR_OK) return rc;
+    } else {
+      slab_rows = 0;
+    }
+  }
+  if (block_n == 256) return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ta, ta_slab, tb, p, res, slab_rows, st);
+  if (block_n == 192) return dispatch_major<192>(a->a_mn_major, a->b_mn_major, ta, ta_slab, tb, p, res, slab_rows, st);
+  if (block_n == 128) return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ta, ta_slab, tb, p, res, slab_rows, st);
+  return dispatch_major<64>(a->a_mn_major, a->b_mn_major, ta, ta_slab, tb, p, res, slab_rows, st);
 }
 
 extern "C" int kr_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int batch,

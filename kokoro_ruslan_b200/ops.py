@@ -100,7 +100,7 @@ class GemmArgs(ctypes.Structure):
                 ("resid2", c_void_p), ("resid2_dtype", c_int), ("ldr2", c_ll), ("stride_r2", c_ll),
                 ("C", c_void_p), ("c_mode", c_int), ("ldc", c_ll), ("stride_c", c_ll),
                 ("C2", c_void_p), ("ldc2", c_ll), ("stride_c2", c_ll), ("act_slope", c_float),
-                ("splits", c_int), ("force_block_n", c_int)]
+                ("splits", c_int), ("force_block_n", c_int), ("no_slab", c_int)]
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -115,7 +115,7 @@ def conv1d_cl(x: torch.Tensor, w: torch.Tensor, *, rows: int, row0: int, taps: i
               bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
               out_act: Optional[torch.Tensor] = None, act_slope: float = 0.1,
               resid: Optional[torch.Tensor] = None, resid2: Optional[torch.Tensor] = None,
-              beta: float = 1.0, block_n: int = 0) -> None:
+              beta: float = 1.0, block_n: int = 0, no_slab: bool = False) -> None:
     """Implicit-GEMM conv1d on channels-last bf16 activations (tcgen05).
 
     x: [B, rows_phys, C_in] bf16 with zero halos; output row m (0 <= m < rows) of item b reads
@@ -156,7 +156,7 @@ def conv1d_cl(x: torch.Tensor, w: torch.Tensor, *, rows: int, row0: int, taps: i
         assert out_act.dtype == torch.bfloat16
         a.C2, a.ldc2, a.stride_c2 = _view(out_act)
         a.act_slope = act_slope
-    a.splits, a.force_block_n = 1, block_n
+    a.splits, a.force_block_n, a.no_slab = 1, block_n, int(no_slab)
     check(lib().kr_gemm_ex(ctypes.byref(a), _stream()), "kr_gemm_ex")
 
 

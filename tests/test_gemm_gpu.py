@@ -116,3 +116,30 @@ def test_conv1d_channels_last_implicit_gemm(cin, cout, k, dil):
     got_act = act[:, halo:halo + L].float().cpu().permute(0, 2, 1)
     assert (got_act - torch.nn.functional.leaky_relu(ref2, 0.1)).abs().max().item() / scale < 1e-2
     assert float(out[:, :halo].abs().max()) == 0.0 and float(out[:, halo + L:].abs().max()) == 0.0   # halos untouched
+
+
+@pytest.mark.parametrize("cin,cout,k,dil", [(64, 64, 3, 1), (64, 64, 7, 3), (64, 64, 11, 5), (128, 128, 3, 1), (64, 128, 3, 1)])
+def test_conv1d_slab_mode_matches_tap_refetch(cin, cout, k, dil):
+    """Large-M conv (enough tiles for the resident-weight + slab path): one activation slab per tile with the
+    taps as row-shifted UMMA descriptors must give the same result as re-fetching every tap, and match torch."""
+    from kokoro_ruslan_b200 import ops
+    Bn, L, halo = 4, 128 * 90 + 37, 32
+    pad = dil * (k - 1) // 2
+    g = torch.Generator().manual_seed(9)
+    x = (torch.randn(Bn, cin, L, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(cout, generator=g)
+    ref = torch.nn.functional.conv1d(x.float(), w.float(), bias, padding=pad, dilation=dil)
+    xcl = torch.zeros(Bn, L + 2 * halo, cin, dtype=torch.bfloat16, device="cuda")
+    xcl[:, halo:halo + L] = x.permute(0, 2, 1).cuda()
+    wt = w.permute(0, 2, 1).reshape(cout, k * cin).contiguous().cuda()
+    outs = []
+    for no_slab in (True, False):
+        out = torch.zeros(Bn, L, cout, dtype=torch.float32, device="cuda")
+        ops.conv1d_cl(xcl, wt, rows=L, row0=halo - pad, taps=k, dil=dil, bias=bias.cuda(), out=out, no_slab=no_slab)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().permute(0, 2, 1))
+    scale = ref.abs().max().item()
+    assert (outs[0] - ref).abs().max().item() / scale < 5e-3
+    assert (outs[1] - ref).abs().max().item() / scale < 5e-3, "slab mode differs from torch"
+    assert torch.equal(outs[0], outs[1]), "slab mode is not bit-identical to the tap re-fetch path"

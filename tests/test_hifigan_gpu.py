@@ -89,3 +89,16 @@ def test_weight_update_refolds():
     gen.load_state_dict(sd1)
     a1 = gen(mel.cuda()).float().cpu()
     assert _rel(a1, oh.generator_forward(sd1, cfg, mel)) < TOL
+
+
+def test_slab_path_parity_mid_size():
+    """T = 320 frames, B = 1: stages 3 and 4 have >= 296 tiles, so the resident-weight + activation-slab
+    conv path is the one that runs; audio still within 1e-2 of the fp32 oracle."""
+    from oracle import hifigan as oh
+    cfg = oh.HifiConfig()
+    sd = oh.seeded_state_dict(cfg, seed=0)
+    gen = _gen(sd)
+    mel = oh.synthetic_mel(1, 320, 6)
+    got = gen(mel.cuda()).float().cpu()
+    want = oh.generator_forward(sd, cfg, mel)
+    assert _rel(got, want) < TOL

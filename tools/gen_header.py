@@ -82,6 +82,7 @@ typedef struct kr_gemm_args {
   void* C2; long long ldc2, stride_c2; float act_slope;   /* optional bf16 leaky_relu(v, act_slope) */
   int splits;               /* split-K (c_mode 2 only) */
   int force_block_n;        /* 0 = heuristic, else 64 / 128 / 192 / 256 */
+  int no_slab;              /* 1 = conv mode re-fetches every tap (debug / A-B comparison) */
 } kr_gemm_args;
 """
 
