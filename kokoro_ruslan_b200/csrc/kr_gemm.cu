@@ -348,33 +348,47 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int c = half; c < BLOCK_N / 32; c += 2) {
         const int nb = n0 + c * 32;
         if (nb >= p.N) break;                          // warp-uniform
-        // (1) residual operands of this chunk are requested FIRST, in the coalesced layout, so that their
-        //     HBM/L2 latency overlaps the TMEM load and the smem transpose (the epilogue was latency-bound on
-        //     exactly these loads: 1.7 TB/s on the HiFi-GAN residual convs)
+        // The epilogue is ISSUE-bound for the short-K GEMMs / convs of this model (it was ~870 warp instructions
+        // per 32x32 chunk = 3500 issue cycles per 128x128 tile vs ~2000 MMA cycles), so everything below keeps
+        // the per-row work to a handful of instructions: row pointers advance by a constant stride, optional
+        // operands are handled by warp-uniform branches OUTSIDE the row loops, interior tiles skip predicates.
         const int n = nb + ccol;
         const bool col_ok = n < p.N;          // N % 4 == 0 on this path: a 4-group is all in or all out
+        const int m_first = mw0 + crow;       // this lane's rows: m_first + 4*i
+        const bool interior = (mw0 + 32 <= p.M) && (nb + 32 <= p.N);      // warp-uniform
+        uint32_t okm = 0;                     // bit i: row i of this lane is inside the matrix
+        if (col_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) okm |= (m_first + 4 * i < p.M) ? (1u << i) : 0u;
+        }
+        // (1) residual operands are requested FIRST, in the coalesced layout, so that their HBM / L2 latency
+        //     overlaps the TMEM load and the smem transpose
         float4 r1[8], r2[8];
-        if (vec_ok) {
-          if (use_resid) {
+        if (vec_ok && use_resid) {
+          if (p.resid_mod > 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int m = mw0 + 4 * i + crow;
-              r1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (m < p.M && col_ok) {
-                const int rm = p.resid_mod > 0 ? (m % p.resid_mod) : m;
-                r1[i] = ld4any(p.resid, p.resid_bf16, (long long)tc.bz * p.r_batch_stride + (long long)rm * p.ldr + n);
-              }
+              const int m = m_first + 4 * i;
+              r1[i] = (okm >> i) & 1u ? ld4any(p.resid, p.resid_bf16, (long long)tc.bz * p.r_batch_stride +
+                                                                      (long long)(m % p.resid_mod) * p.ldr + n)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-          }
-          if (p.resid2 != nullptr) {
+          } else {
+            const long long off0 = (long long)tc.bz * p.r_batch_stride + (long long)m_first * p.ldr + n;
+            const long long step = 4 * p.ldr;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int m = mw0 + 4 * i + crow;
-              r2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (m < p.M && col_ok)
-                r2[i] = ld4any(p.resid2, p.resid2_bf16, (long long)tc.bz * p.r2_batch_stride + (long long)m * p.ldr2 + n);
-            }
+            for (int i = 0; i < 8; ++i)
+              r1[i] = (interior || ((okm >> i) & 1u)) ? ld4any(p.resid, p.resid_bf16, off0 + i * step)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+        }
+        if (vec_ok && p.resid2 != nullptr) {
+          const long long off0 = (long long)tc.bz * p.r2_batch_stride + (long long)m_first * p.ldr2 + n;
+          const long long step = 4 * p.ldr2;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            r2[i] = (interior || ((okm >> i) & 1u)) ? ld4any(p.resid2, p.resid2_bf16, off0 + i * step)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         // (2) accumulator chunk: TMEM -> registers (row layout) -> smem (16-byte slots XOR-swizzled by row:
         //     conflict-free both ways)
@@ -387,34 +401,66 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
         __syncwarp();
         if (vec_ok) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (use_bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          // (3) back in the coalesced layout: v[i] = row m_first + 4*i, columns [n, n+4)
+          float4 v[8];
+          const float* sp = stg + crow * 32;
+          const int xs = lane & 7;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + crow;
-            const int m = mw0 + rr;
-            const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
-            if (m < p.M && col_ok) {
-              float4 v = make_float4(a4.x * p.alpha + b4.x, a4.y * p.alpha + b4.y, a4.z * p.alpha + b4.z,
-                                     a4.w * p.alpha + b4.w);
-              if (use_resid) { v.x += r1[i].x; v.y += r1[i].y; v.z += r1[i].z; v.w += r1[i].w; }
-              v.x *= p.beta; v.y *= p.beta; v.z *= p.beta; v.w *= p.beta;
-              if (p.resid2 != nullptr) { v.x += r2[i].x; v.y += r2[i].y; v.z += r2[i].z; v.w += r2[i].w; }
-              const long long c_off = (long long)tc.bz * p.c_batch_stride + (long long)m * p.ldc + n;
-              if (p.c_mode == C_BF16)
-                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.C) + c_off) =
-                    make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-              else if (p.c_mode == C_F32)
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + c_off) = v;
-              else if (p.c_mode == C_ATOMIC_F32)
-                atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + c_off), v);
-              if (p.C2 != nullptr) {
-                const float sl = p.act_slope;
-                v.x = v.x > 0.f ? v.x : v.x * sl; v.y = v.y > 0.f ? v.y : v.y * sl;
-                v.z = v.z > 0.f ? v.z : v.z * sl; v.w = v.w > 0.f ? v.w : v.w * sl;
-                *reinterpret_cast<uint2*>(p.C2 + (long long)tc.bz * p.c2_batch_stride + (long long)m * p.ldc2 + n) =
-                    make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-              }
+          for (int i = 0; i < 8; ++i)   // row 4*i + crow: (row & 7) = ((i & 1) << 2) | crow
+            v[i] = *reinterpret_cast<const float4*>(sp + i * 128 + ((xs ^ (((i & 1) << 2) | crow)) << 2));
+          if (p.alpha != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i].x *= p.alpha; v[i].y *= p.alpha; v[i].z *= p.alpha; v[i].w *= p.alpha; }
+          }
+          if (use_bias) {
+            const float4 b4 = col_ok ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i].x += b4.x; v[i].y += b4.y; v[i].z += b4.z; v[i].w += b4.w; }
+          }
+          if (use_resid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i].x += r1[i].x; v[i].y += r1[i].y; v[i].z += r1[i].z; v[i].w += r1[i].w; }
+          }
+          if (p.beta != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i].x *= p.beta; v[i].y *= p.beta; v[i].z *= p.beta; v[i].w *= p.beta; }
+          }
+          if (p.resid2 != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i].x += r2[i].x; v[i].y += r2[i].y; v[i].z += r2[i].z; v[i].w += r2[i].w; }
+          }
+          const uint32_t okw = interior ? 0xffu : okm;
+          if (p.c_mode == C_BF16) {
+            bf16* cp = reinterpret_cast<bf16*>(p.C) + (long long)tc.bz * p.c_batch_stride + (long long)m_first * p.ldc + n;
+            const long long step = 4 * p.ldc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if ((okw >> i) & 1u)
+                *reinterpret_cast<uint2*>(cp + i * step) = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+          } else if (p.c_mode == C_F32) {
+            float* cp = reinterpret_cast<float*>(p.C) + (long long)tc.bz * p.c_batch_stride + (long long)m_first * p.ldc + n;
+            const long long step = 4 * p.ldc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if ((okw >> i) & 1u) *reinterpret_cast<float4*>(cp + i * step) = v[i];
+          } else if (p.c_mode == C_ATOMIC_F32) {
+            float* cp = reinterpret_cast<float*>(p.C) + (long long)tc.bz * p.c_batch_stride + (long long)m_first * p.ldc + n;
+            const long long step = 4 * p.ldc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if ((okw >> i) & 1u) atomicAdd(reinterpret_cast<float4*>(cp + i * step), v[i]);
+          }
+          if (p.C2 != nullptr) {
+            const float sl = p.act_slope;
+            bf16* cp = p.C2 + (long long)tc.bz * p.c2_batch_stride + (long long)m_first * p.ldc2 + n;
+            const long long step = 4 * p.ldc2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 a = v[i];
+              if ((okw >> i) & 1u)
+                *reinterpret_cast<uint2*>(cp + i * step) =
+                    make_uint2(pack_bf16(fmaxf(a.x, a.x * sl), fmaxf(a.y, a.y * sl)),
+                               pack_bf16(fmaxf(a.z, a.z * sl), fmaxf(a.w, a.w * sl)));
             }
           }
         } else {
