@@ -261,6 +261,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
+// Same with an explicit swizzle layout: 2 = 128-byte swizzle (64-element bf16 K blocks), 4 = 64-byte swizzle
+// (32-element K blocks: rows are 64 B, the pattern repeats every 8 rows = 512 B).
+__device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                      uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives TMEM lane
 // (32*(warp_id%4) + i), columns [col, col+32).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -289,7 +302,7 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // (box_inner, box_rows, 1), 128-byte swizzle (box_inner must be 64 bf16 = 128 B).
 int kr_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows,
                          uint64_t batch, uint64_t row_stride_elems, uint64_t batch_stride_elems,
-                         uint32_t box_inner, uint32_t box_rows);
+                         uint32_t box_inner, uint32_t box_rows, int swizzle64 = 0);
 // 4-D bf16 tensor map over a [batch, seq, heads, 64] token-major activation viewed as
 // (d=64, head, seq, batch); strides in ELEMENTS; box (64, 1, box_seq, 1), 128-byte swizzle.
 int kr_make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t heads, uint64_t seq,

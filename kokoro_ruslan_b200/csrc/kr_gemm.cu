@@ -65,10 +65,10 @@ constexpr int BAR_BYTES = 1024;
 constexpr int RING_OFFSET0 = BAR_BYTES + EPI_WARPS * EPI_STAGE_BYTES;   // 33 KB, 1024-aligned
 constexpr int SMEM_TOTAL = 227 * 1024 - 1024;                            // leave slack for the base alignment
 
-template <int BLOCK_N>
+template <int BLOCK_N, int BK = BLOCK_K>
 struct SmemLayout {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int A_BYTES = BLOCK_M * BK * 2;
+  static constexpr int B_BYTES = BLOCK_N * BK * 2;
   static constexpr int TMEM_COLS = BLOCK_N <= 64 ? 128 : (BLOCK_N <= 128 ? 256 : 512);  // power of two >= 2*BLOCK_N
 };
 
@@ -139,11 +139,17 @@ __device__ __noinline__ void epi_chunk_scalar(const GemmParams& p, const float* 
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+// BK = 64: 128-byte swizzled K blocks (everything).  BK = 32: 64-byte swizzled K blocks, K-major operands only —
+// the 32-channel HiFi-GAN stage, whose K blocks would otherwise be half zero padding.
+template <int BLOCK_N, bool A_MN, bool B_MN, int BK = BLOCK_K>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
-  using L = SmemLayout<BLOCK_N>;
+  static_assert(BK == 64 || (BK == 32 && !A_MN && !B_MN), "32-wide K blocks are K-major only");
+  using L = SmemLayout<BLOCK_N, BK>;
+  constexpr uint32_t ROWB = BK * 2;                 // bytes per K-major smem row
+  constexpr uint32_t SBO = 8 * ROWB;                // 8-row swizzle atom
+  constexpr uint32_t LAYOUT = BK == 64 ? 2u : 4u;   // SWIZZLE_128B / SWIZZLE_64B
   const int STAGES = p.stages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -196,9 +202,9 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (B_MN) {
 #pragma unroll
             for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_3d(b_res + kb * L::B_BYTES + j * (BLOCK_K * 128), &tmap_b, bres_bar, j * 64, kb * BLOCK_K, 0);
+              tma_load_3d(b_res + kb * L::B_BYTES + j * (BLOCK_K * 128), &tmap_b, bres_bar, j * 64, kb * BK, 0);
           } else {
-            tma_load_3d(b_res + kb * L::B_BYTES, &tmap_b, bres_bar, kb * BLOCK_K, 0, 0);
+            tma_load_3d(b_res + kb * L::B_BYTES, &tmap_b, bres_bar, kb * BK, 0, 0);
           }
         }
       }
@@ -218,7 +224,7 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint8_t* sa = ring + s * p.stage_bytes;
           mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
           for (int cb = 0; cb < p.conv_cin_blocks; ++cb)
-            tma_load_3d(sa + cb * p.slab_rows * 128, &tmap_a, &full_bar[s], cb * BLOCK_K, p.conv_row0 + m0, tc.bz);
+            tma_load_3d(sa + cb * p.slab_rows * ROWB, &tmap_a, &full_bar[s], cb * BK, p.conv_row0 + m0, tc.bz);
           continue;
         }
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -229,14 +235,14 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint8_t* sa = ring + s * p.stage_bytes;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
-          const int k = kb * BLOCK_K;
+          const int k = kb * BK;
           if (A_MN) {
 #pragma unroll
             for (int j = 0; j < BLOCK_M / 64; ++j)
               tma_load_3d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[s], m0 + j * 64, k, tc.bz);
           } else if (p.conv_taps > 0) {
             const int tap = kb / p.conv_cin_blocks, cb = kb - tap * p.conv_cin_blocks;
-            tma_load_3d(sa, &tmap_a, &full_bar[s], cb * BLOCK_K, p.conv_row0 + m0 + tap * p.conv_dil, tc.bz);
+            tma_load_3d(sa, &tmap_a, &full_bar[s], cb * BK, p.conv_row0 + m0 + tap * p.conv_dil, tc.bz);
           } else {
             tma_load_3d(sa, &tmap_a, &full_bar[s], k, m0, tc.bz);
           }
@@ -286,12 +292,12 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               // aligned); the 128B swizzle is a function of the absolute smem address on sm_100a, so TMA's
               // placement and the UMMA read agree with the descriptor's base-offset field left at 0 (measured:
               // bit-identical to re-fetching every tap; setting base_offset = (addr >> 7) & 7 is WRONG here)
-              const uint32_t sa = slab + cb * p.slab_rows * 128 + tap * p.conv_dil * 128;
+              const uint32_t sa = slab + cb * p.slab_rows * ROWB + tap * p.conv_dil * ROWB;
               const uint32_t sb = smem_u32(b_res + (tap * p.conv_cin_blocks + cb) * L::B_BYTES);
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
-                const uint64_t db = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t da = make_smem_desc_sw(sa + k * 32, 16, SBO, LAYOUT);
+                const uint64_t db = make_smem_desc_sw(sb + k * b_kstep, b_lbo, SBO, LAYOUT);
                 umma_bf16_ss(tmem_d, da, db, idesc, first ? 0u : 1u);
                 first = false;
               }
@@ -310,9 +316,9 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t sa = smem_u32(ring + s * p.stage_bytes);
           const uint32_t sb = p.b_resident ? smem_u32(b_res + (kb0 + i) * L::B_BYTES) : sa + L::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
-            const uint64_t db = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc_sw(sa + k * a_kstep, a_lbo, A_MN ? 1024u : SBO, LAYOUT);
+            const uint64_t db = make_smem_desc_sw(sb + k * b_kstep, b_lbo, B_MN ? 1024u : SBO, LAYOUT);
             umma_bf16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
@@ -481,11 +487,11 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int BK = BLOCK_K>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta_slab, const CUtensorMap& tb, GemmParams p, bool want_resident,
                 int want_slab_rows, cudaStream_t st) {
-  using L = SmemLayout<BLOCK_N>;
-  auto kern = kr_gemm_kernel<BLOCK_N, A_MN, B_MN>;
+  using L = SmemLayout<BLOCK_N, BK>;
+  auto kern = kr_gemm_kernel<BLOCK_N, A_MN, B_MN, BK>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL + 1024);
@@ -501,7 +507,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta_slab, const CUtenso
   }
   p.conv_slab = 0; p.slab_rows = 0;
   if (p.b_resident && !A_MN && p.conv_taps > 1 && want_slab_rows > 0) {
-    const int slab_bytes = p.conv_cin_blocks * want_slab_rows * 128;
+    const int slab_bytes = p.conv_cin_blocks * want_slab_rows * BK * 2;
     if (p.b_res_bytes + 2LL * slab_bytes <= avail) {
       p.conv_slab = 1; p.slab_rows = want_slab_rows; p.stage_bytes = slab_bytes;
     }
@@ -550,7 +556,7 @@ static PFN_encodeTiled get_encode_fn() {
 
 int kr_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows,
                          uint64_t batch, uint64_t row_stride_elems, uint64_t batch_stride_elems,
-                         uint32_t box_inner, uint32_t box_rows) {
+                         uint32_t box_inner, uint32_t box_rows, int swizzle64) {
   PFN_encodeTiled fn = get_encode_fn();
   if (fn == nullptr) { kr_set_error("cuTensorMapEncodeTiled entry point unavailable"); return KR_ERR_TMAP; }
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_stride_elems & 7) || (batch_stride_elems & 7)) {
@@ -562,7 +568,8 @@ int kr_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uin
   cuuint32_t box[3] = {box_inner, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[160];
@@ -610,11 +617,12 @@ extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
   const int M = a->M, N = a->N, K = a->K, batch = a->batch;
   if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) { kr_set_error("kr_gemm_ex: empty problem"); return KR_ERR_ARG; }
   const bool conv = a->conv_taps > 0;
-  if (conv && (a->a_mn_major || (a->conv_cin % BLOCK_K) != 0 || K != a->conv_taps * a->conv_cin)) {
-    kr_set_error("kr_gemm_ex: conv mode needs K-major A, C_in % 64 == 0 and K == taps * C_in");
+  const int bk = (conv && a->conv_cin == 32 && !a->a_mn_major && !a->b_mn_major && N <= 64) ? 32 : BLOCK_K;
+  if (conv && (a->a_mn_major || (a->conv_cin % bk) != 0 || K != a->conv_taps * a->conv_cin)) {
+    kr_set_error("kr_gemm_ex: conv mode needs K-major A, K == taps * C_in and C_in % 64 == 0 (or C_in == 32 with N <= 64)");
     return KR_ERR_ARG;
   }
-  const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int total_kb = (K + bk - 1) / bk;
   int splits = a->splits < 1 ? 1 : a->splits;
   if (splits > total_kb) splits = total_kb;
   if (splits > 1 && a->c_mode != C_ATOMIC_F32) { kr_set_error("kr_gemm_ex: split-K needs the atomic epilogue"); return KR_ERR_ARG; }
@@ -652,11 +660,11 @@ extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
   CUtensorMap ta, tb;
   int rc;
   if (a->a_mn_major) rc = kr_make_tmap_bf16_3d(&ta, a->A, M, K, batch, a->lda, bstride_a, 64, BLOCK_K);
-  else if (conv)     rc = kr_make_tmap_bf16_3d(&ta, a->A, a->conv_cin, a->a_rows, batch, a->lda, bstride_a, BLOCK_K, BLOCK_M);
+  else if (conv)     rc = kr_make_tmap_bf16_3d(&ta, a->A, a->conv_cin, a->a_rows, batch, a->lda, bstride_a, bk, BLOCK_M, bk == 32);
   else               rc = kr_make_tmap_bf16_3d(&ta, a->A, K, M, batch, a->lda, bstride_a, BLOCK_K, BLOCK_M);
   if (rc != KR_OK) return rc;
   if (a->b_mn_major) rc = kr_make_tmap_bf16_3d(&tb, a->B, N, K, b_batch, a->ldb, bstride_b, 64, BLOCK_K);
-  else               rc = kr_make_tmap_bf16_3d(&tb, a->B, K, N, b_batch, a->ldb, bstride_b, BLOCK_K, block_n);
+  else               rc = kr_make_tmap_bf16_3d(&tb, a->B, K, N, b_batch, a->ldb, bstride_b, bk, block_n, bk == 32);
   if (rc != KR_OK) return rc;
 
   GemmParams p{};
@@ -664,7 +672,7 @@ extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
   p.total_kb = total_kb; p.m_tiles = m_tiles; p.n_tiles = (N + block_n - 1) / block_n;
   p.total_tiles = p.m_tiles * p.n_tiles * batch * splits;
   p.conv_taps = a->conv_taps; p.conv_dil = a->conv_dil; p.conv_row0 = a->conv_row0;
-  p.conv_cin_blocks = conv ? a->conv_cin / BLOCK_K : 0;
+  p.conv_cin_blocks = conv ? a->conv_cin / bk : 0;
   p.C = a->C; p.ldc = a->ldc; p.c_batch_stride = a->stride_c; p.c_mode = a->C != nullptr ? a->c_mode : C_NONE;
   p.C2 = reinterpret_cast<bf16*>(a->C2); p.ldc2 = a->ldc2; p.c2_batch_stride = a->stride_c2; p.act_slope = a->act_slope;
   p.bias = a->bias;
@@ -681,12 +689,13 @@ extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
   if (conv && res && a->conv_taps > 1 && !a->no_slab) {
     slab_rows = (BLOCK_M + (a->conv_taps - 1) * a->conv_dil + 7) / 8 * 8;
     if (slab_rows <= 256) {
-      rc = kr_make_tmap_bf16_3d(&ta_slab, a->A, a->conv_cin, a->a_rows, batch, a->lda, bstride_a, BLOCK_K, slab_rows);
+      rc = kr_make_tmap_bf16_3d(&ta_slab, a->A, a->conv_cin, a->a_rows, batch, a->lda, bstride_a, bk, slab_rows, bk == 32);
       if (rc != KR_OK) return rc;
     } else {
       slab_rows = 0;
     }
   }
+  if (bk == 32) return launch_gemm<64, false, false, 32>(ta, ta_slab, tb, p, res, slab_rows, st);
   if (block_n == 256) return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ta, ta_slab, tb, p, res, slab_rows, st);
   if (block_n == 192) return dispatch_major<192>(a->a_mn_major, a->b_mn_major, ta, ta_slab, tb, p, res, slab_rows, st);
   if (block_n == 128) return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ta, ta_slab, tb, p, res, slab_rows, st);

@@ -65,8 +65,9 @@ class HiFiGANConfig:
 
 
 def _cpad(c: int) -> int:
-    """Physical channel count of an activation: the implicit-GEMM K chunk is 64 channels."""
-    return (c + 63) // 64 * 64
+    """Physical channel count of an activation: the implicit-GEMM K block is 64 channels (128-byte swizzle),
+    or exactly 32 channels (64-byte swizzled K blocks, last HiFi-GAN stage)."""
+    return 32 if c == 32 else (c + 63) // 64 * 64
 
 
 class _Plan:

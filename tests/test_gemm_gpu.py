@@ -85,7 +85,7 @@ def test_gemm_block_n_variants_persistent(block_n):
 
 
 @pytest.mark.parametrize("cin,cout,k,dil", [(128, 128, 3, 1), (128, 128, 7, 3), (64, 64, 11, 5), (512, 256, 7, 1),
-                                            (64, 200, 3, 1)])
+                                            (64, 200, 3, 1), (32, 32, 3, 1), (32, 32, 7, 3), (32, 32, 11, 5), (32, 64, 7, 1)])
 def test_conv1d_channels_last_implicit_gemm(cin, cout, k, dil):
     """conv mode of the GEMM kernel vs torch conv1d (same bf16-rounded operands), with the fused
     bias + bf16 residual + 1/3 scaling + second leaky-relu output used by the HiFi-GAN MRF."""
@@ -118,7 +118,8 @@ def test_conv1d_channels_last_implicit_gemm(cin, cout, k, dil):
     assert float(out[:, :halo].abs().max()) == 0.0 and float(out[:, halo + L:].abs().max()) == 0.0   # halos untouched
 
 
-@pytest.mark.parametrize("cin,cout,k,dil", [(64, 64, 3, 1), (64, 64, 7, 3), (64, 64, 11, 5), (128, 128, 3, 1), (64, 128, 3, 1)])
+@pytest.mark.parametrize("cin,cout,k,dil", [(64, 64, 3, 1), (64, 64, 7, 3), (64, 64, 11, 5), (128, 128, 3, 1), (64, 128, 3, 1),
+                                            (32, 32, 3, 1), (32, 32, 7, 3), (32, 32, 11, 5)])
 def test_conv1d_slab_mode_matches_tap_refetch(cin, cout, k, dil):
     """Large-M conv (enough tiles for the resident-weight + slab path): one activation slab per tile with the
     taps as row-shifted UMMA descriptors must give the same result as re-fetching every tap, and match torch."""
