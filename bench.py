@@ -124,6 +124,19 @@ def cpu_oracle_run(steps: int, warmup: int, budget_s: float):
     import torch
     from oracle import acoustic as oa
     from oracle.train_step import CpuTrainStep
+    # all the host cores the box has: torchrun exports OMP_NUM_THREADS=1, which would make the CPU arm
+    # single-threaded under N > 1 launches
+    try:
+        import psutil
+        want = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+    except Exception:
+        want = os.cpu_count() or 1
+    try:
+        want = min(want, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    if torch.get_num_threads() < want:
+        torch.set_num_threads(want)
     cores = torch.get_num_threads()
     cfg = oa.AcousticConfig()
     step = CpuTrainStep(cfg, oa.seeded_state_dict(cfg, seed=0))

@@ -137,12 +137,14 @@ class _Staged:
     losses: Optional[torch.Tensor] = None
     launches: int = 0
     warm: int = 0
+    last_used: int = 0
 
 
 class TrainStep:
     def __init__(self, model_cfg: Optional[ModelConfig] = None, optim_cfg: Optional[OptimConfig] = None,
                  sched_cfg: Optional[ScheduleConfig] = None, loss_cfg: Optional[LossConfig] = None,
-                 device=None, use_graphs: bool = True, process_group=None, max_seq_cap: int = 2000):
+                 device=None, use_graphs: bool = True, process_group=None, max_seq_cap: int = 2000,
+                 max_cached_shapes: int = 16):
         self.engine = AcousticEngine(model_cfg or ModelConfig(), device, with_ema=True, loss_cfg=loss_cfg)
         self.device = self.engine.device
         self.opt = FusedAdamW(self.engine.store, optim_cfg or OptimConfig())
@@ -154,6 +156,10 @@ class TrainStep:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
         self.max_seq_cap = max_seq_cap
+        # every cached batch shape pins its static input buffers and (once captured) a graph with ~4 GB of
+        # activations at the bench shape: dynamic batching produces many shapes, so the cache is LRU-bounded
+        self.max_cached_shapes = max_cached_shapes
+        self._tick = 0
         self._staged: Dict[Tuple[int, int, int, int], _Staged] = {}
         self._opt_graph: Optional[torch.cuda.CUDAGraph] = None
         self._opt_warm = 0
@@ -216,13 +222,18 @@ class TrainStep:
         Tp = max(Tp, 3)
         key = (B, P, T, Tp)
         st = self._staged.get(key)
+        self._tick += 1
         if st is None:
+            if len(self._staged) >= self.max_cached_shapes:
+                victim = min(self._staged, key=lambda k: self._staged[k].last_used)
+                del self._staged[victim]          # drops the graph and its private memory pool
             dev = {}
             for k in BATCH_KEYS:
                 src = batch[k]
                 dev[k] = torch.empty(src.shape, dtype=src.dtype, device=self.device)
             st = _Staged(dev=dev)
             self._staged[key] = st
+        st.last_used = self._tick
         nbytes = 0
         for k in BATCH_KEYS:
             src = batch[k]
