@@ -360,7 +360,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dV = tmem_base + 256,
                  tmem_dK = tmem_base + 320, tmem_dQ = tmem_base + 384;
-  constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);     // one 64-key half of S / dP
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);    // S, dP
   constexpr uint32_t idesc_tt = make_idesc_bf16(128, 64, 1, 1);    // dV, dK
   constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);    // dQ
 
@@ -376,34 +376,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_load_4d(sdO + j * TILE_BYTES, &tmdO, &qdo_bar[j], 0, h, (i_begin + j) * TQ, b);
       }
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-      // MMA1 for one 64-key half hf: S[:, hf] = Q K[hf]^T, dP[:, hf] = dO V[hf]^T  (K/V rows 64*hf.. start 8 KB in)
-      auto issue_mma1 = [&](int it, int hf) {
+      // MMA1: S = Q K^T, dP = dO V^T as full 128-key MMAs (every tcgen05.mma re-reads its 128-row A operand from
+      // shared memory, and smem operand bandwidth is what bounds these d = 64 shapes: N = 128 halves the A traffic
+      // of the two-half variant); both half barriers are signalled by the same completion.
+      auto issue_mma1 = [&](int it) {
         const uint32_t aQ = smem_u32(sQ + (it & 1) * TILE_BYTES), adO = smem_u32(sdO + (it & 1) * TILE_BYTES);
-        const uint32_t kOff = hf * 64 * 128;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_S + hf * 64, desc_k64(aQ, k), desc_k64(aK + kOff, k), idesc_s, k > 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_S, desc_k64(aQ, k), desc_k64(aK, k), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_dP + hf * 64, desc_k64(adO, k), desc_k64(aV + kOff, k), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&sdp_bar[hf]);
+          umma_bf16_ss(tmem_dP, desc_k64(adO, k), desc_k64(aV, k), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&sdp_bar[0]);
+        umma_commit(&sdp_bar[1]);
       };
       mbar_wait(kv_bar, 0);
       mbar_wait(&qdo_bar[0], 0);
       tc_fence_after();
-      issue_mma1(0, 0);
-      issue_mma1(0, 1);
+      issue_mma1(0);
       for (int it = 0; it < n_it; ++it) {
         const int bsel = it & 1;
-        // half hf of S/dP is free again as soon as ITS 4 warps are done with it: refill it right away so the
-        // warps of that half never wait for more than one MMA1 latency
-        for (int hf = 0; hf < 2; ++hf) {
-          mbar_wait(&soft_bar[hf], it & 1);
+        mbar_wait(&soft_bar[0], it & 1);      // P/dS(it) in smem; S, dP and dQ TMEM regions are free again
+        mbar_wait(&soft_bar[1], it & 1);
+        tc_fence_after();
+        if (it + 1 < n_it) {
+          mbar_wait(&qdo_bar[bsel ^ 1], ((it + 1) >> 1) & 1);
           tc_fence_after();
-          if (it + 1 < n_it) {
-            if (hf == 0) { mbar_wait(&qdo_bar[bsel ^ 1], ((it + 1) >> 1) & 1); tc_fence_after(); }
-            issue_mma1(it + 1, hf);
-          }
+          issue_mma1(it + 1);                 // first in the tensor pipe: soft(it+1) can start early ...
         }
         {                                     // ... while MMA2(it) executes underneath it
           const uint32_t aP = smem_u32(sP + bsel * 2 * TILE_BYTES), adS = smem_u32(sdS + bsel * 2 * TILE_BYTES);
