@@ -195,33 +195,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float m_new = fmaxf(m_run, mx);
     const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
     const float alpha = fast_exp2(m_run - m_use);
+    // P (bf16) goes back into TENSOR MEMORY, over the S columns this thread has already consumed: the P V MMA
+    // then reads its A operand from TMEM, which removes a 32 KB smem write + 32 KB smem read per tile from the
+    // loop (shared-memory operand bandwidth is what bounds these d = 64 MMAs).  Packed layout: lane = query row,
+    // 32-bit column c holds keys (2c, 2c+1).
     float rowsum = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t pk[16];
+    for (int hcol = 0; hcol < 2; ++hcol) {
+      uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
+      for (int i = 0; i < 64; i += 2) {
         // exp2(-inf) = 0 handles the masked entries; the row sum uses the bf16-rounded values the MMA sees
-        const uint32_t u = pack_bf16(fast_exp2(sv[c * 32 + i] - m_use), fast_exp2(sv[c * 32 + i + 1] - m_use));
+        const uint32_t u = pack_bf16(fast_exp2(sv[hcol * 64 + i] - m_use), fast_exp2(sv[hcol * 64 + i + 1] - m_use));
         const float2 rb = unpack_bf16(u);
         rowsum += rb.x + rb.y;
         pk[i >> 1] = u;
       }
-      store_chunk_sw128(sP, tid, c, pk);
+      tmem_st_32x32(tmem_S + t_lane + hcol * 32, pk);
     }
+    tmem_st_wait();
     l_run = l_run * alpha + rowsum;
     m_run = m_new;
-    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
       mbar_wait(&v_bar[st], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t aP = smem_u32(sP), aV = smem_u32(sV + st * TILE_BYTES);
+      const uint32_t aV = smem_u32(sV + st * TILE_BYTES);
 #pragma unroll
-      for (int k = 0; k < TK / 16; ++k)
-        umma_bf16_ss(tmem_O, desc_k128(aP, k), desc_mn64(aV, k), idesc_o, k > 0 ? 1u : 0u);
+      for (int k = 0; k < TK / 16; ++k)       // 16 keys = 8 packed TMEM columns per MMA
+        umma_bf16_ts(tmem_O, tmem_S + k * 8, desc_mn64(aV, k), idesc_o, k > 0 ? 1u : 0u);
       umma_commit(o_bar);
     }
     __syncwarp();
