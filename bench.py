@@ -118,9 +118,15 @@ def synthetic_batch(B, P, T, n_mels, vocab, seed):
 # ----------------------------------------------------------------------------------------------
 # CPU oracle leg (cpu_baseline and --impl reference)
 # ----------------------------------------------------------------------------------------------
-def cpu_oracle_run(steps: int, warmup: int, budget_s: float):
+DROPOUT_DESC = {"reference": "reference training defaults: encoder 0.15, decoder 0.20, decoder input 0.15, "
+                             "variance 0.1, stochastic depth 0.1 (training/config.py:108-121,195)",
+                "off": "0.0 (deterministic parity configuration)"}
+
+
+def cpu_oracle_run(steps: int, warmup: int, budget_s: float, dropout: str = "reference"):
     """Times the oracle port of the training step (fwd + losses + bwd + pre-clip + clip + AdamW +
-    EMA, fp32, dropout 0) on the host cores.  Returns (frames/s, ms/step, cores, sample text)."""
+    EMA, fp32; dropout / stochastic depth at the reference's training defaults unless dropout == "off")
+    on the host cores.  Returns (frames/s, ms/step, cores, sample text)."""
     import torch
     from oracle import acoustic as oa
     from oracle.train_step import CpuTrainStep
@@ -139,7 +145,11 @@ def cpu_oracle_run(steps: int, warmup: int, budget_s: float):
         torch.set_num_threads(want)
     cores = torch.get_num_threads()
     cfg = oa.AcousticConfig()
-    step = CpuTrainStep(cfg, oa.seeded_state_dict(cfg, seed=0))
+    drop = None
+    if dropout != "off":      # training/config.py:108-121,195
+        drop = oa.TorchDropout(p_enc=0.15, p_dec=0.20, p_in=0.15, p_var=0.1, sd_rate=0.1,
+                               n_enc=cfg.n_encoder_layers, n_dec=cfg.n_decoder_layers)
+    step = CpuTrainStep(cfg, oa.seeded_state_dict(cfg, seed=0), drop=drop)
     B = B_PER_GPU
     batch = oa.synthetic_batch(B=B, P=P_LEN, T=T_LEN, seed=1)
     t0 = time.perf_counter()
@@ -157,7 +167,8 @@ def cpu_oracle_run(steps: int, warmup: int, budget_s: float):
         step.train_step(batch)
     dt = time.perf_counter() - t0
     frames = steps * B * T_LEN
-    sample = (f"{steps} full optimizer steps (fwd+losses+bwd+pre-clip+clip+AdamW+EMA, fp32, dropout 0) of "
+    sample = (f"{steps} full optimizer steps (fwd+losses+bwd+pre-clip+clip+AdamW+EMA, fp32, dropout "
+              f"{'0' if drop is None else 'at the reference training defaults'}) of "
               f"B={B} utterances x P={P_LEN} x T={T_LEN}, torch {torch.__version__} CPU, {cores} threads")
     return frames / dt, dt / steps * 1e3, cores, sample
 
@@ -166,11 +177,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, cores, sample = cpu_oracle_run(args.steps, args.warmup, budget_s=150.0)
+    value, ms, cores, sample = cpu_oracle_run(args.steps, args.warmup, budget_s=150.0, dropout=args.dropout)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD},
+            "config": {"workload": WORKLOAD, "dropout": DROPOUT_DESC[args.dropout]},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -239,6 +250,7 @@ def run_ours(args):
     from kokoro_ruslan_b200.build import build
     build()
     from kokoro_ruslan_b200 import _lib
+    from kokoro_ruslan_b200.engine import DropoutConfig
     from kokoro_ruslan_b200.kprof import OpTimer
     from kokoro_ruslan_b200.params import ModelConfig
     from kokoro_ruslan_b200.train_step import ScheduleConfig, TrainStep
@@ -258,7 +270,11 @@ def run_ours(args):
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
 
     cfg = ModelConfig()
-    ts = TrainStep(cfg, sched_cfg=ScheduleConfig(total_steps=100000), device=dev, use_graphs=True, process_group=pg)
+    dropout = DropoutConfig.reference_training() if args.dropout != "off" else None
+    if dropout is not None:
+        dropout.seed = 1234 + rank      # data-parallel ranks draw independent masks
+    ts = TrainStep(cfg, sched_cfg=ScheduleConfig(total_steps=100000), device=dev, use_graphs=True, process_group=pg,
+                   dropout=dropout)
     ts.store.init_default(seed=0)          # same weights on every rank
     host = synthetic_batch(B_PER_GPU, P_LEN, T_LEN, N_MELS, cfg.vocab_size, seed=1 + rank)
     host = {k: v.pin_memory() for k, v in host.items()}
@@ -378,7 +394,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            v, _, cores, sample = cpu_oracle_run(steps=2, warmup=1, budget_s=40.0)
+            v, _, cores, sample = cpu_oracle_run(steps=2, warmup=1, budget_s=40.0, dropout=args.dropout)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         except Exception as exc:
             cpu = {"error": repr(exc)}
@@ -388,7 +404,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "params": 49432276,
                        "precision": "bf16 tcgen05 GEMM/attention operands, fp32 accumulate/residual/optimizer",
-                       "dropout": 0.0, "grad_accum": 1, "parallelism": f"dp{world}",
+                       "dropout": DROPOUT_DESC[args.dropout], "grad_accum": 1, "parallelism": f"dp{world}",
                        "l2": "no flush: a step streams >1 GB of weights/optimizer state/activations (> 126 MB L2)",
                        "cuda_graphs": True},
             "roofline": roof, "cpu_baseline": cpu,
@@ -409,6 +425,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dropout", default="reference", choices=["reference", "off"],
+                    help="reference = the trainer's dropout / stochastic-depth defaults (the real training step); "
+                         "off = the deterministic parity configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hifigan", action="store_true")
     args = ap.parse_args()

@@ -16,6 +16,7 @@
 //           operands, dO / Q as MN-major B operands — no transposed copies) and dQ_tile = dS K,
 //           which is reduced into the fp32 dQ buffer with vector atomics.
 #include "kr_common.cuh"
+#include "kokoro_b200.h"
 
 namespace {
 using namespace kr;
@@ -33,7 +34,17 @@ struct AttnParams {
   float* dQ; long long dq_ss, dq_bs;
   bf16* dK; long long dk_ss, dk_bs;
   bf16* dV; long long dv_ss, dv_bs;
+  // attention-probability dropout (F.scaled_dot_product_attention(dropout_p), transformers.py:393-398): element
+  // index of P[b, h, q, k] = ((b*H + h)*Sq + q) * sk_pad + k, sk_pad = Sk rounded up to the 128-key tile
+  DropSpec drop;
+  uint32_t sk_pad_half;
 };
+
+// packed-bf16 AND mask of one key pair: 0xffff per kept half
+__device__ __forceinline__ uint32_t drop_pair_bits(uint32_t pair, uint2 key, uint32_t thr) {
+  const uint32_t x = drop_hash(pair, key);
+  return ((x & 0xffffu) >= thr ? 0x0000ffffu : 0u) | ((x >> 16) >= thr ? 0xffff0000u : 0u);
+}
 
 // [128 rows x 64 K] bf16 tile, K-major, SW128: k-th UMMA_K slice.
 __device__ __forceinline__ uint64_t desc_k64(uint32_t base, int k) {
@@ -79,7 +90,7 @@ __device__ __forceinline__ uint32_t allowed_bits(uint32_t pad_bits, bool causal,
 // ---------------------------------------------------------------------------------------------
 constexpr int FWD_SMEM = 7 * TILE_BYTES + 256 + 1024;
 
-template <bool CAUSAL>
+template <bool CAUSAL, bool DROP>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -135,6 +146,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
   const int qi = q0 + tid;
+  uint2 dkey = make_uint2(0u, 0u);
+  uint32_t drow = 0;
+  if (DROP) {
+    dkey = drop_key(p.drop.state, p.drop.site_a);
+    drow = (uint32_t)(((long long)b * p.H + h) * p.Sq + min(qi, p.Sq - 1)) * p.sk_pad_half;
+  }
   constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
   constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
 
@@ -206,9 +223,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int i = 0; i < 64; i += 2) {
         // exp2(-inf) = 0 handles the masked entries; the row sum uses the bf16-rounded values the MMA sees
-        const uint32_t u = pack_bf16(fast_exp2(sv[hcol * 64 + i] - m_use), fast_exp2(sv[hcol * 64 + i + 1] - m_use));
+        uint32_t u = pack_bf16(fast_exp2(sv[hcol * 64 + i] - m_use), fast_exp2(sv[hcol * 64 + i + 1] - m_use));
         const float2 rb = unpack_bf16(u);
-        rowsum += rb.x + rb.y;
+        rowsum += rb.x + rb.y;          // the softmax denominator is that of the un-dropped probabilities
+        if (DROP) u &= drop_pair_bits(drow + j * (TK / 2) + hcol * 32 + (i >> 1), dkey, p.drop.thr_a);
         pk[i >> 1] = u;
       }
       tmem_st_32x32(tmem_S + t_lane + hcol * 32, pk);
@@ -243,7 +261,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 
   if (qi < p.Sq) {
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    if (DROP) inv *= p.drop.scale;
     bf16* orow = p.O + (long long)b * p.o_bs + (long long)qi * p.o_ss + h * HD;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -312,7 +331,7 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ O, long long o_ss,
 constexpr int BWD_SMEM = 14 * TILE_BYTES + 256 + 1024;
 constexpr int BWD_THREADS = 288;
 
-template <bool CAUSAL>
+template <bool CAUSAL, bool DROP>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -437,6 +456,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t t_lane = static_cast<uint32_t>(lg * 32) << 16;
     const uint32_t mw0 = mask_words[2 * ch], mw1 = mask_words[2 * ch + 1];
     const long long bh = (long long)b * p.H + h;
+    uint2 dkey = make_uint2(0u, 0u);
+    if (DROP) dkey = drop_key(p.drop.state, p.drop.site_a);
+    const float dp_scale = DROP ? p.scale * p.drop.scale : p.scale;   // dP_eff = mask * dP / keep
 
     auto dq_flush = [&](int it_done) {       // dQ tile of iteration it_done: this thread owns 32 columns of one row
       const int qi = (i_begin + it_done) * TQ + row;
@@ -475,7 +497,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (!row_ok) ok = 0u;
         const float nds = -delta_i * p.scale;
         uint32_t pkP[16], pkS[16];
-        if (__all_sync(0xffffffffu, ok == 0xffffffffu)) {
+        if (DROP) {
+          const uint32_t prow = (uint32_t)(bh * p.Sq + min(qi, p.Sq - 1)) * p.sk_pad_half + ((kv0 + c * 32) >> 1);
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse_i));
+            float p1 = fast_exp2(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse_i));
+            p0 = ((ok >> e) & 1u) ? p0 : 0.f;
+            p1 = ((ok >> (e + 1)) & 1u) ? p1 : 0.f;
+            const uint32_t keep = drop_pair_bits(prow + (e >> 1), dkey, p.drop.thr_a);
+            const float g0 = (keep & 0xffffu) ? __uint_as_float(rp[e]) : 0.f;
+            const float g1 = (keep >> 16) ? __uint_as_float(rp[e + 1]) : 0.f;
+            pkP[e >> 1] = pack_bf16(p0, p1) & keep;                    // dV += (mask P)^T dO  (1/keep at the store)
+            pkS[e >> 1] = pack_bf16(p0 * fmaf(g0, dp_scale, nds), p1 * fmaf(g1, dp_scale, nds));
+          }
+        } else if (__all_sync(0xffffffffu, ok == 0xffffffffu)) {
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             const float p0 = fast_exp2(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse_i));
@@ -523,6 +559,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t r[32];
       tmem_ld_32x32(tm + t_lane + ch * 32, r);
       tmem_ld_wait();
+      if (DROP && which == 0) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * p.drop.scale);
+      }
       if (ok) {
         bf16* orow = base + (long long)b * bs + (long long)kv * ss + h * HD + ch * 32;
 #pragma unroll
@@ -547,6 +587,18 @@ int make_head_map(CUtensorMap* m, const void* ptr, int H, int S, int B, long lon
   return kr_make_tmap_bf16_heads(m, ptr, H, S, B, HD, ss, bs, 128);
 }
 
+int set_drop(AttnParams& p, const kr_drop_spec* drop, const char* who) {
+  p.drop = kr_drop_to_device(drop);
+  const long long sk_pad = (long long)((p.Sk + TK - 1) / TK) * TK;
+  p.sk_pad_half = (uint32_t)(sk_pad / 2);
+  if (p.drop.state != nullptr) {
+    if (p.drop.thr_b != 0 || p.drop.row_scale != nullptr) { kr_set_error("attention dropout takes a single-mask spec"); return KR_ERR_ARG; }
+    if ((long long)p.B * p.H * p.Sq * (sk_pad / 2) >= (1LL << 32)) { kr_set_error(who); return KR_ERR_UNSUPPORTED; }
+    if (p.drop.thr_a == 0) p.drop.state = nullptr;     // p = 0: plain kernels
+  }
+  return KR_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -555,7 +607,8 @@ int make_head_map(CUtensorMap* m, const void* ptr, int H, int S, int B, long lon
 extern "C" int kr_attn_fwd(const void* q, long long q_ss, long long q_bs, const void* k, long long k_ss,
                            long long k_bs, const void* v, long long v_ss, long long v_bs, void* o,
                            long long o_ss, long long o_bs, float* lse, const unsigned char* key_mask,
-                           int B, int H, int Sq, int Sk, int causal, float scale, void* stream) {
+                           int B, int H, int Sq, int Sk, int causal, float scale, const kr_drop_spec* drop,
+                           void* stream) {
   if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) { kr_set_error("kr_attn_fwd: empty problem"); return KR_ERR_ARG; }
   if (causal && Sq != Sk) { kr_set_error("kr_attn_fwd: causal needs Sq == Sk"); return KR_ERR_ARG; }
   CUtensorMap tq, tk, tv;
@@ -566,16 +619,22 @@ extern "C" int kr_attn_fwd(const void* q, long long q_ss, long long q_bs, const 
   AttnParams p{};
   p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.key_mask = key_mask; p.O = reinterpret_cast<bf16*>(o); p.o_ss = o_ss; p.o_bs = o_bs; p.lse = lse;
+  if ((rc = set_drop(p, drop, "kr_attn_fwd")) != KR_OK) return rc;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
-    cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
     attr = true;
   }
   dim3 grid((Sq + TQ - 1) / TQ, H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (causal) kr::launch(attn_fwd_kernel<true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
-  else        kr::launch(attn_fwd_kernel<false>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
+  const bool dr = p.drop.state != nullptr;
+  if (causal && dr)  kr::launch(attn_fwd_kernel<true, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
+  else if (causal)   kr::launch(attn_fwd_kernel<true, false>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
+  else if (dr)       kr::launch(attn_fwd_kernel<false, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
+  else               kr::launch(attn_fwd_kernel<false, false>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -586,7 +645,7 @@ extern "C" int kr_attn_bwd(const void* q, long long q_ss, long long q_bs, const 
                            long long do_bs, const float* lse, float* delta, float* dq, long long dq_ss,
                            long long dq_bs, void* dk, long long dk_ss, long long dk_bs, void* dv,
                            long long dv_ss, long long dv_bs, const unsigned char* key_mask, int B, int H,
-                           int Sq, int Sk, int causal, float scale, void* stream) {
+                           int Sq, int Sk, int causal, float scale, const kr_drop_spec* drop, void* stream) {
   if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) { kr_set_error("kr_attn_bwd: empty problem"); return KR_ERR_ARG; }
   if (causal && Sq != Sk) { kr_set_error("kr_attn_bwd: causal needs Sq == Sk"); return KR_ERR_ARG; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -609,15 +668,21 @@ extern "C" int kr_attn_bwd(const void* q, long long q_ss, long long q_bs, const 
   p.dQ = dq; p.dq_ss = dq_ss; p.dq_bs = dq_bs;
   p.dK = reinterpret_cast<bf16*>(dk); p.dk_ss = dk_ss; p.dk_bs = dk_bs;
   p.dV = reinterpret_cast<bf16*>(dv); p.dv_ss = dv_ss; p.dv_bs = dv_bs;
+  if ((rc = set_drop(p, drop, "kr_attn_bwd")) != KR_OK) return rc;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-    cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    cudaFuncSetAttribute(attn_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    cudaFuncSetAttribute(attn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    cudaFuncSetAttribute(attn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    cudaFuncSetAttribute(attn_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
     attr = true;
   }
   dim3 grid((Sk + TK - 1) / TK, H, B);
-  if (causal) kr::launch(attn_bwd_kernel<true>, grid, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, p);
-  else        kr::launch(attn_bwd_kernel<false>, grid, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, p);
+  const bool dr = p.drop.state != nullptr;
+  if (causal && dr)  kr::launch(attn_bwd_kernel<true, true>, grid, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, p);
+  else if (causal)   kr::launch(attn_bwd_kernel<true, false>, grid, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, p);
+  else if (dr)       kr::launch(attn_bwd_kernel<false, true>, grid, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, p);
+  else               kr::launch(attn_bwd_kernel<false, false>, grid, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

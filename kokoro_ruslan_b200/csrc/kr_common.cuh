@@ -121,6 +121,79 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dropout / stochastic depth (reference nn.Dropout sites of model/transformers.py:108-111,396,482-487,
+// 569-581, model/positional_encoding.py:74, model/model.py:525, model/variance_predictor.py:106 and
+// drop_path :16-40).  Counter-based: the keep decision of element e at dropout site s in optimizer
+// step t is a pure function of (seed, t, s, e), so the backward kernels REGENERATE the masks instead
+// of storing them, and tests can export exactly the mask a fused kernel used (kr_drop_export_mask).
+//   key(seed, t, s)   = splitmix64 finaliser -> two 32-bit words
+//   hash(pair, key)   = two multiply-xorshift rounds keyed before each multiply; 32 bits serve the
+//                       element pair (2*pair, 2*pair + 1) as two 16-bit lanes
+//   keep(e)           = lane16 >= thr,   thr = round(p * 65536)      (P(keep) = 1 - thr / 65536)
+// A spec can carry a second independent mask (site_b / thr_b: consecutive reference dropouts) and a
+// per-sample factor table (stochastic depth: 0 or 1 / (1 - p_path)), see kr_drop_spec.
+// ---------------------------------------------------------------------------------------------
+struct DropSpec {               // device-side copy of kr_drop_spec (include/kokoro_b200.h)
+  const unsigned long long* state;   // {seed, step}; nullptr = dropout disabled
+  uint32_t site_a, thr_a, site_b, thr_b;
+  float scale;                       // factor of kept elements
+  const float* row_scale;            // optional [n_samples]
+  int rows_per_sample;
+};
+struct DropCtx { uint2 ka, kb; uint32_t thr_a, thr_b; float scale; };
+
+__device__ __forceinline__ uint2 drop_key(const unsigned long long* state, uint32_t site) {
+  unsigned long long z = state[0] + 0x9E3779B97F4A7C15ull * (state[1] + 1ull) + 0xD1B54A32D192ED03ull * (site + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return make_uint2(static_cast<uint32_t>(z), static_cast<uint32_t>(z >> 32));
+}
+__device__ __forceinline__ uint32_t drop_hash(uint32_t pair, uint2 k) {
+  uint32_t x = pair ^ k.x;
+  x *= 0x7feb352du; x ^= x >> 15;
+  x ^= k.y;
+  x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ DropCtx drop_ctx(const DropSpec& d) {
+  DropCtx c;
+  c.ka = drop_key(d.state, d.site_a);
+  c.kb = d.thr_b ? drop_key(d.state, d.site_b) : make_uint2(0u, 0u);
+  c.thr_a = d.thr_a; c.thr_b = d.thr_b; c.scale = d.scale;
+  return c;
+}
+// factors (0 or scale) of elements 2*pair and 2*pair + 1
+__device__ __forceinline__ void drop_pair(const DropCtx& c, uint32_t pair, float& f0, float& f1) {
+  const uint32_t x = drop_hash(pair, c.ka);
+  bool k0 = (x & 0xffffu) >= c.thr_a, k1 = (x >> 16) >= c.thr_a;
+  if (c.thr_b) {
+    const uint32_t y = drop_hash(pair, c.kb);
+    k0 = k0 && (y & 0xffffu) >= c.thr_b;
+    k1 = k1 && (y >> 16) >= c.thr_b;
+  }
+  f0 = k0 ? c.scale : 0.f;
+  f1 = k1 ? c.scale : 0.f;
+}
+// factors of the four consecutive elements starting at e0 (e0 % 4 == 0)
+__device__ __forceinline__ float4 drop_quad(const DropCtx& c, long long e0) {
+  float4 f;
+  const uint32_t pr = static_cast<uint32_t>(e0 >> 1);
+  drop_pair(c, pr, f.x, f.y);
+  drop_pair(c, pr + 1u, f.z, f.w);
+  return f;
+}
+// factor of the single element e
+__device__ __forceinline__ float drop_one(const DropCtx& c, long long e) {
+  float f0, f1;
+  drop_pair(c, static_cast<uint32_t>(e >> 1), f0, f1);
+  return (e & 1) ? f1 : f0;
+}
+__device__ __forceinline__ float drop_row_scale(const DropSpec& d, int row) {
+  return d.row_scale != nullptr ? d.row_scale[row / d.rows_per_sample] : 1.f;
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -330,6 +403,10 @@ __device__ __forceinline__ void tmem_ld_wait() {
 }
 
 }  // namespace kr
+
+// host: kr_drop_spec (include/kokoro_b200.h) -> kernel parameter; NULL / disabled -> state == nullptr
+struct kr_drop_spec;
+kr::DropSpec kr_drop_to_device(const kr_drop_spec* s);
 
 // ---------------------------------------------------------------------------------------------
 // host: tensor-map encoding through the driver entry point (no link-time libcuda dependency, so

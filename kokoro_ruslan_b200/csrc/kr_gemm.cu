@@ -53,6 +53,7 @@ struct GemmParams {
   float alpha, beta;
   int stages, stage_bytes, b_resident, b_res_bytes;   // smem ring geometry (host-chosen)
   int b_shared;   // B has no batch dimension (weights shared by every batch item)
+  DropSpec drop;  // dropout / stochastic depth on v = alpha*acc + bias, before the residual adds (state == nullptr: off)
 };
 
 // Dynamic shared memory map (offsets from the 1024-aligned base):
@@ -350,6 +351,15 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool first_split = (tc.split == 0);
       const bool use_bias = p.bias != nullptr && first_split;
       const bool use_resid = p.resid != nullptr && first_split;
+      // dropout epilogue (attention out-projection): per-row stochastic-depth factors of this lane's 8 rows
+      const bool use_drop = p.drop.state != nullptr;
+      DropCtx dc{};
+      float rowf[8];
+      if (use_drop) {
+        dc = drop_ctx(p.drop);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rowf[i] = drop_row_scale(p.drop, min(mw0 + (lane >> 3) + 4 * i, p.M - 1));
+      }
 #pragma unroll 1
       for (int c = half; c < BLOCK_N / 32; c += 2) {
         const int nb = n0 + c * 32;
@@ -422,6 +432,14 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const float4 b4 = col_ok ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) { v[i].x += b4.x; v[i].y += b4.y; v[i].z += b4.z; v[i].w += b4.w; }
+          }
+          if (use_drop) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 f = drop_quad(dc, (long long)(m_first + 4 * i) * p.N + n);
+              const float rf = rowf[i];
+              v[i].x *= f.x * rf; v[i].y *= f.y * rf; v[i].z *= f.z * rf; v[i].w *= f.w * rf;
+            }
           }
           if (use_resid) {
 #pragma unroll
@@ -680,6 +698,11 @@ extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
   p.resid2 = a->resid2; p.resid2_bf16 = a->resid2_dtype; p.ldr2 = a->ldr2; p.r2_batch_stride = a->stride_r2;
   p.alpha = a->alpha; p.beta = a->beta;
   p.b_shared = b_shared ? 1 : 0;
+  p.drop = kr_drop_to_device(a->drop);
+  if (p.drop.state != nullptr && (batch != 1 || splits != 1 || (N & 3) || (a->ldc & 3) || (a->ldr & 3))) {
+    kr_set_error("kr_gemm_ex: the dropout epilogue needs batch == 1, no split-K and N / leading dimensions % 4 == 0");
+    return KR_ERR_ARG;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // resident weights: one N tile, no split-K, weights shared by the batch, and enough tiles per CTA to pay off
   const bool res = p.n_tiles == 1 && splits == 1 && (batch == 1 || b_shared) && p.total_tiles >= 2 * kNumSMs;

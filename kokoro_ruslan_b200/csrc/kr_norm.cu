@@ -5,6 +5,7 @@
 //   * per-head Q/K/V RMSNorm with learned gain + rotate-half RoPE, fwd/bwd
 //     (transformers.py:145-148,260-272; positional_encoding.py:196-209)
 #include "kr_common.cuh"
+#include "kokoro_b200.h"
 #include <float.h>
 
 namespace {
@@ -73,10 +74,12 @@ __global__ void __launch_bounds__(WARPS * 32, 3) ln_bwd_kernel(const float* __re
                               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                               const float* __restrict__ gamma, const float* dres, float* dx,
                               bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-                              float* __restrict__ dbeta, int N) {
+                              float* __restrict__ dbeta, int N, const DropSpec drop) {
   kr::pdl_entry();
   constexpr int D = NV * 128;
   __shared__ float sm[WARPS][D];
+  DropCtx dc{};
+  if (drop.state != nullptr) dc = drop_ctx(drop);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 ag[NV], ab[NV];
 #pragma unroll
@@ -112,7 +115,14 @@ __global__ void __launch_bounds__(WARPS * 32, 3) ln_bwd_kernel(const float* __re
       o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
       o.x += rs[i].x; o.y += rs[i].y; o.z += rs[i].z; o.w += rs[i].w;
       st4(dx + off + c0, o);
-      if (dx_bf16 != nullptr) st_bf16x4(dx_bf16 + off + c0, o);
+      if (dx_bf16 != nullptr) {
+        if (drop.state != nullptr) {   // the bf16 copy feeds the backward of a dropped residual branch
+          const float rsf = drop_row_scale(drop, row);
+          const float4 f = drop_quad(dc, off + c0);
+          o.x *= f.x * rsf; o.y *= f.y * rsf; o.z *= f.z * rsf; o.w *= f.w * rsf;
+        }
+        st_bf16x4(dx_bf16 + off + c0, o);
+      }
     }
   }
   // column gradients: warps -> smem -> one atomic per column per block
@@ -135,13 +145,16 @@ __global__ void __launch_bounds__(WARPS * 32, 3) ln_bwd_kernel(const float* __re
 // ---------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void rms_resid_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gain,
-                                     const float* resid, float* out, int N, float eps) {
+                                     const float* resid, float* out, int N, float eps, const DropSpec drop) {
   kr::pdl_entry();
   constexpr int D = NV * 128;
   const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
   const long long off = (long long)row * D;
+  DropCtx dc{};
+  float rsf = 1.f;
+  if (drop.state != nullptr) { dc = drop_ctx(drop); rsf = drop_row_scale(drop, row); }
   float4 v[NV];
   float q = 0.f;
 #pragma unroll
@@ -154,18 +167,25 @@ __global__ void rms_resid_fwd_kernel(const float* __restrict__ y, const float* _
   for (int i = 0; i < NV; ++i) {
     const int c0 = i * 128 + lane * 4;
     const float4 g = ld4(gain + c0), r = ld4(resid + off + c0);
-    st4(out + off + c0, make_float4(r.x + v[i].x * rstd * g.x, r.y + v[i].y * rstd * g.y,
-                                    r.z + v[i].z * rstd * g.z, r.w + v[i].w * rstd * g.w));
+    float4 f = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (drop.state != nullptr) {     // dropout(s) + stochastic depth on the branch, transformers.py:111,486-487,581
+      f = drop_quad(dc, off + c0);
+      f.x *= rsf; f.y *= rsf; f.z *= rsf; f.w *= rsf;
+    }
+    st4(out + off + c0, make_float4(r.x + v[i].x * rstd * g.x * f.x, r.y + v[i].y * rstd * g.y * f.y,
+                                    r.z + v[i].z * rstd * g.z * f.z, r.w + v[i].w * rstd * g.w * f.w));
   }
 }
 
 template <int NV>
 __global__ void __launch_bounds__(WARPS * 32, 3) rms_resid_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y,
                                      const float* __restrict__ gain, bf16* __restrict__ dy,
-                                     float* __restrict__ dgain, int N, float eps) {
+                                     float* __restrict__ dgain, int N, float eps, const DropSpec drop) {
   kr::pdl_entry();
   constexpr int D = NV * 128;
   __shared__ float sm[WARPS][D];
+  DropCtx dc{};
+  if (drop.state != nullptr) dc = drop_ctx(drop);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 ag[NV];
 #pragma unroll
@@ -184,7 +204,13 @@ __global__ void __launch_bounds__(WARPS * 32, 3) rms_resid_bwd_kernel(const floa
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c0 = i * 128 + lane * 4;
-      const float4 g = ld4(gain + c0), o = ld4(dout + off + c0);
+      const float4 g = ld4(gain + c0);
+      float4 o = ld4(dout + off + c0);
+      if (drop.state != nullptr) {
+        const float rsf = drop_row_scale(drop, row);
+        const float4 f = drop_quad(dc, off + c0);
+        o.x *= f.x * rsf; o.y *= f.y * rsf; o.z *= f.z * rsf; o.w *= f.w * rsf;
+      }
       v[i] = make_float4(v[i].x * rstd, v[i].y * rstd, v[i].z * rstd, v[i].w * rstd);  // yhat
       ag[i].x += o.x * v[i].x; ag[i].y += o.y * v[i].y; ag[i].z += o.z * v[i].z; ag[i].w += o.w * v[i].w;
       d[i] = make_float4(o.x * g.x, o.y * g.y, o.z * g.z, o.w * g.w);
@@ -405,32 +431,34 @@ extern "C" int kr_layernorm_fwd(const float* x, const float* gamma, const float*
 
 extern "C" int kr_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                 const float* gamma, const float* dres, float* dx, void* dx_bf16,
-                                float* dgamma, float* dbeta, int N, int D, void* stream) {
+                                float* dgamma, float* dbeta, int N, int D, const kr_drop_spec* drop_bf16,
+                                void* stream) {
   if (N <= 0) return KR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DISPATCH_NV(D, (kr::launch(ln_bwd_kernel<NV>, persistent_blocks(N), WARPS * 32, 0, st, 
                      dy, x, mean, rstd, gamma, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dgamma,
-                     dbeta, N)));
+                     dbeta, N, kr_drop_to_device(drop_bf16))));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 
 extern "C" int kr_rmsnorm_resid_fwd(const float* y, const float* gain, const float* resid, float* out,
-                                    int N, int D, void* stream) {
+                                    int N, int D, const kr_drop_spec* drop, void* stream) {
   if (N <= 0) return KR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DISPATCH_NV(D, (kr::launch(rms_resid_fwd_kernel<NV>, row_blocks(N), WARPS * 32, 0, st, y, gain, resid, out, N,
-                                                                                FLT_EPSILON)));
+                                                                                FLT_EPSILON, kr_drop_to_device(drop))));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 
 extern "C" int kr_rmsnorm_resid_bwd(const float* dout, const float* y, const float* gain, void* dy_bf16,
-                                    float* dgain, int N, int D, void* stream) {
+                                    float* dgain, int N, int D, const kr_drop_spec* drop, void* stream) {
   if (N <= 0) return KR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DISPATCH_NV(D, (kr::launch(rms_resid_bwd_kernel<NV>, persistent_blocks(N), WARPS * 32, 0, st, 
-                     dout, y, gain, reinterpret_cast<bf16*>(dy_bf16), dgain, N, FLT_EPSILON)));
+                     dout, y, gain, reinterpret_cast<bf16*>(dy_bf16), dgain, N, FLT_EPSILON,
+                     kr_drop_to_device(drop))));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -5,6 +5,7 @@
 //   * decoder input shift-right + cast                     (model/model.py:519)
 //   * column sums (bias gradients), f32->bf16 casts, row gather/scatter helpers
 #include "kr_common.cuh"
+#include "kokoro_b200.h"
 
 namespace {
 using namespace kr;
@@ -16,8 +17,22 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-__global__ void glu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ u, long long n_vec, int FF) {
+// dropout factors of the 8 consecutive elements starting at e0 (all 1 when disabled)
+__device__ __forceinline__ void drop8(const DropSpec& d, const DropCtx& c, long long e0, float* f) {
+  if (d.state != nullptr) {
+    const float4 a = drop_quad(c, e0), b = drop_quad(c, e0 + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = 1.f;
+  }
+}
+
+__global__ void glu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ u, long long n_vec, int FF,
+                               const DropSpec d) {
   kr::pdl_entry();
+  DropCtx dc{};
+  if (d.state != nullptr) dc = drop_ctx(d);
   // one thread = 8 consecutive output columns
   const int vec_per_row = FF / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
@@ -28,18 +43,22 @@ __global__ void glu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ u,
     const uint4 l = *reinterpret_cast<const uint4*>(h + row * 2 * FF + FF + c);
     const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, lw[4] = {l.x, l.y, l.z, l.w};
     uint32_t o[4];
+    float f[8];
+    drop8(d, dc, 8 * i, f);          // dropout on the gated product, transformers.py:108
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 a = unpack_bf16(gw[k]), b = unpack_bf16(lw[k]);
-      o[k] = pack_bf16(gelu_erf(a.x) * b.x, gelu_erf(a.y) * b.y);
+      o[k] = pack_bf16(gelu_erf(a.x) * b.x * f[2 * k], gelu_erf(a.y) * b.y * f[2 * k + 1]);
     }
     *reinterpret_cast<uint4*>(u + row * FF + c) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
 __global__ void glu_bwd_kernel(const bf16* __restrict__ du, const bf16* __restrict__ h,
-                               bf16* __restrict__ dh, long long n_vec, int FF) {
+                               bf16* __restrict__ dh, long long n_vec, int FF, const DropSpec drop) {
   kr::pdl_entry();
+  DropCtx dc{};
+  if (drop.state != nullptr) dc = drop_ctx(drop);
   const int vec_per_row = FF / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -50,9 +69,13 @@ __global__ void glu_bwd_kernel(const bf16* __restrict__ du, const bf16* __restri
     const uint4 d = *reinterpret_cast<const uint4*>(du + row * FF + c);
     const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, lw[4] = {l.x, l.y, l.z, l.w}, dw[4] = {d.x, d.y, d.z, d.w};
     uint32_t og[4], ol[4];
+    float f[8];
+    drop8(drop, dc, 8 * i, f);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float2 a = unpack_bf16(gw[k]), b = unpack_bf16(lw[k]), e = unpack_bf16(dw[k]);
+      const float2 a = unpack_bf16(gw[k]), b = unpack_bf16(lw[k]);
+      float2 e = unpack_bf16(dw[k]);
+      e.x *= f[2 * k]; e.y *= f[2 * k + 1];
       og[k] = pack_bf16(e.x * b.x * gelu_erf_grad(a.x), e.y * b.y * gelu_erf_grad(a.y));
       ol[k] = pack_bf16(e.x * gelu_erf(a.x), e.y * gelu_erf(a.y));
     }
@@ -99,8 +122,10 @@ __global__ void colsum_bf16_kernel(const bf16* __restrict__ x, long long ld, flo
 __global__ void embed_fwd_kernel(const long long* __restrict__ idx, const long long* __restrict__ stress,
                                  const float* __restrict__ emb, const float* __restrict__ semb,
                                  const float* __restrict__ pe, float* __restrict__ x, int N, int P, int D,
-                                 float scale) {
+                                 float scale, const DropSpec d) {
   kr::pdl_entry();
+  DropCtx dc{};
+  if (d.state != nullptr) dc = drop_ctx(d);
   const int vec_per_row = D / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)N * vec_per_row;
        i += (long long)gridDim.x * blockDim.x) {
@@ -112,18 +137,29 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ idx, const long l
       const float4 s = *reinterpret_cast<const float4*>(semb + stress[n] * D + c);
       o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
     }
+    if (d.state != nullptr) {          // PositionalEncoding's dropout, positional_encoding.py:74
+      const float4 f = drop_quad(dc, 4 * i);
+      o.x *= f.x; o.y *= f.y; o.z *= f.z; o.w *= f.w;
+    }
     *reinterpret_cast<float4*>(x + (long long)n * D + c) = o;
   }
 }
 
 __global__ void embed_bwd_kernel(const float* __restrict__ dx, const long long* __restrict__ idx,
                                  const long long* __restrict__ stress, float* __restrict__ demb,
-                                 float* __restrict__ dsemb, int N, int D, float scale) {
+                                 float* __restrict__ dsemb, int N, int D, float scale, const DropSpec d) {
   kr::pdl_entry();
+  DropCtx dc{};
+  if (d.state != nullptr) dc = drop_ctx(d);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)N * D;
        i += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(i / D), c = (int)(i % D);
-    const float g = dx[i];
+    float g = dx[i];
+    if (d.state != nullptr) {
+      float f0, f1;
+      drop_pair(dc, (uint32_t)(i >> 1), f0, f1);
+      g *= (i & 1) ? f1 : f0;
+    }
     atomicAdd(demb + idx[n] * D + c, g * scale);
     if (stress != nullptr && stress[n] != 0) atomicAdd(dsemb + stress[n] * D + c, g);
   }
@@ -198,19 +234,22 @@ inline int ew_blocks(long long n, int threads = 256) {
 
 }  // namespace
 
-extern "C" int kr_glu_fwd(const void* h, void* u, int N, int FF, void* stream) {
+extern "C" int kr_glu_fwd(const void* h, void* u, int N, int FF, const kr_drop_spec* drop, void* stream) {
   if (N <= 0) return KR_OK;
   if (FF % 8) { kr_set_error("kr_glu: FF must be a multiple of 8"); return KR_ERR_ARG; }
   const long long n_vec = (long long)N * FF / 8;
-  kr::launch(glu_fwd_kernel, ew_blocks(n_vec), 256, 0, (cudaStream_t)stream, (const bf16*)h, (bf16*)u, n_vec, FF);
+  kr::launch(glu_fwd_kernel, ew_blocks(n_vec), 256, 0, (cudaStream_t)stream, (const bf16*)h, (bf16*)u, n_vec, FF,
+             kr_drop_to_device(drop));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
-extern "C" int kr_glu_bwd(const void* du, const void* h, void* dh, int N, int FF, void* stream) {
+extern "C" int kr_glu_bwd(const void* du, const void* h, void* dh, int N, int FF, const kr_drop_spec* drop,
+                          void* stream) {
   if (N <= 0) return KR_OK;
   if (FF % 8) { kr_set_error("kr_glu: FF must be a multiple of 8"); return KR_ERR_ARG; }
   const long long n_vec = (long long)N * FF / 8;
-  kr::launch(glu_bwd_kernel, ew_blocks(n_vec), 256, 0, (cudaStream_t)stream, (const bf16*)du, (const bf16*)h, (bf16*)dh, n_vec, FF);
+  kr::launch(glu_bwd_kernel, ew_blocks(n_vec), 256, 0, (cudaStream_t)stream, (const bf16*)du, (const bf16*)h, (bf16*)dh, n_vec, FF,
+             kr_drop_to_device(drop));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -224,18 +263,18 @@ extern "C" int kr_colsum_bf16(const void* x, long long ld, float* out, int N, in
 }
 extern "C" int kr_embed_fwd(const long long* idx, const long long* stress, const float* emb,
                             const float* stress_emb, const float* pe, float* x, int N, int P, int D,
-                            void* stream) {
+                            const kr_drop_spec* drop, void* stream) {
   if (N <= 0) return KR_OK;
   kr::launch(embed_fwd_kernel, ew_blocks((long long)N * D / 4), 256, 0, (cudaStream_t)stream, 
-      idx, stress, emb, stress_emb, pe, x, N, P, D, sqrtf((float)D));
+      idx, stress, emb, stress_emb, pe, x, N, P, D, sqrtf((float)D), kr_drop_to_device(drop));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 extern "C" int kr_embed_bwd(const float* dx, const long long* idx, const long long* stress, float* demb,
-                            float* dstress_emb, int N, int D, void* stream) {
+                            float* dstress_emb, int N, int D, const kr_drop_spec* drop, void* stream) {
   if (N <= 0) return KR_OK;
   kr::launch(embed_bwd_kernel, ew_blocks((long long)N * D), 256, 0, (cudaStream_t)stream, 
-      dx, idx, stress, demb, dstress_emb, N, D, sqrtf((float)D));
+      dx, idx, stress, demb, dstress_emb, N, D, sqrtf((float)D), kr_drop_to_device(drop));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

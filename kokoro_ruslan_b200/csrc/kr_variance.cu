@@ -13,6 +13,7 @@
 // before and after every chunk (the conv's zero padding), plus one guard row at each end of the
 // buffer.  row_group[r] = (sample, chunk) id of padded row r or -1 for a zero row.
 #include "kr_common.cuh"
+#include "kokoro_b200.h"
 
 namespace {
 using namespace kr;
@@ -196,9 +197,11 @@ __device__ __forceinline__ void gn_mean_rstd(const double* stats, const int* gro
 __global__ void gn_apply_relu_kernel(const float* __restrict__ x, const int* __restrict__ row_group,
                                      const double* __restrict__ stats, const int* __restrict__ group_rows,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     bf16* __restrict__ out, int R, int C) {
+                                     bf16* __restrict__ out, int R, int C, const DropSpec drop) {
   kr::pdl_entry();
   const int lane = threadIdx.x & 31;
+  DropCtx dc{};
+  if (drop.state != nullptr) dc = drop_ctx(drop);
   for (int r = blockIdx.x * WARPS + (threadIdx.x >> 5); r < R; r += gridDim.x * WARPS) {
     const int g = row_group[r];
     float mean = 0.f, rstd = 0.f;
@@ -206,6 +209,7 @@ __global__ void gn_apply_relu_kernel(const float* __restrict__ x, const int* __r
     for (int c = lane; c < C; c += 32) {
       float y = 0.f;
       if (g >= 0) y = fmaxf((x[(long long)r * C + c] - mean) * rstd * gamma[c] + beta[c], 0.f);
+      if (drop.state != nullptr) y *= drop_one(dc, (long long)r * C + c);   // variance_predictor.py:106
       out[(long long)r * C + c] = __float2bfloat16(y);
     }
   }
@@ -216,9 +220,12 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const float* __
                                     const int* __restrict__ row_group, const double* __restrict__ stats,
                                     const int* __restrict__ group_rows, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, double* __restrict__ gsum,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int C) {
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int C,
+                                    const DropSpec drop) {
   kr::pdl_entry();
   __shared__ float sm[2][WARPS][256];
+  DropCtx dc{};
+  if (drop.state != nullptr) dc = drop_ctx(drop);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float ag[8], ab[8];
 #pragma unroll
@@ -235,7 +242,8 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const float* __
       if (c < C) {
         const float xh = (x[(long long)r * C + c] - mean) * rstd;
         const float y = xh * gamma[c] + beta[c];
-        const float d = y > 0.f ? __bfloat162float(dy[(long long)r * C + c]) : 0.f;
+        float d = y > 0.f ? __bfloat162float(dy[(long long)r * C + c]) : 0.f;
+        if (drop.state != nullptr) d *= drop_one(dc, (long long)r * C + c);
         ag[i] += d * xh; ab[i] += d;
         s1 += d * gamma[c]; s2 += d * gamma[c] * xh;
       }
@@ -259,9 +267,11 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const float* __
                                     const int* __restrict__ row_group, const double* __restrict__ stats,
                                     const int* __restrict__ group_rows, const double* __restrict__ gsum,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                    bf16* __restrict__ dx, int R, int C) {
+                                    bf16* __restrict__ dx, int R, int C, const DropSpec drop) {
   kr::pdl_entry();
   const int lane = threadIdx.x & 31;
+  DropCtx dc{};
+  if (drop.state != nullptr) dc = drop_ctx(drop);
   for (int r = blockIdx.x * WARPS + (threadIdx.x >> 5); r < R; r += gridDim.x * WARPS) {
     const int g = row_group[r];
     float mean = 0.f, rstd = 0.f, m1 = 0.f, m2 = 0.f;
@@ -276,7 +286,8 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const float* __
       if (g >= 0) {
         const float xh = (x[(long long)r * C + c] - mean) * rstd;
         const float y = xh * gamma[c] + beta[c];
-        const float d = y > 0.f ? __bfloat162float(dy[(long long)r * C + c]) : 0.f;
+        float d = y > 0.f ? __bfloat162float(dy[(long long)r * C + c]) : 0.f;
+        if (drop.state != nullptr) d *= drop_one(dc, (long long)r * C + c);
         o = rstd * (d * gamma[c] - m1 - xh * m2);
       }
       dx[(long long)r * C + c] = __float2bfloat16(o);
@@ -420,28 +431,32 @@ extern "C" int kr_adapt_bwd(const float* dmem, const int* p_idx, const int* e_id
 
 extern "C" int kr_gn_fwd(const float* x, const int* row_group, const int* group_rows, double* stats,
                          const float* gamma, const float* beta, void* out_bf16, int R, int C, int G,
-                         void* stream) {
+                         const kr_drop_spec* drop, void* stream) {
   if (R <= 0) return KR_OK;
   if (C > 256 || (C % 32)) { kr_set_error("kr_gn: C must be a multiple of 32, <= 256"); return KR_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * G, st) != cudaSuccess) { kr_set_error("memset failed"); return KR_ERR_CUDA; }
   kr::launch(gn_stats_kernel, warp_blocks(R), WARPS * 32, 0, st, x, row_group, stats, R, C);
   KR_CHECK_LAUNCH();
-  kr::launch(gn_apply_relu_kernel, warp_blocks(R), WARPS * 32, 0, st, x, row_group, stats, group_rows, gamma, beta, (bf16*)out_bf16, R, C);
+  kr::launch(gn_apply_relu_kernel, warp_blocks(R), WARPS * 32, 0, st, x, row_group, stats, group_rows, gamma, beta, (bf16*)out_bf16, R, C,
+             kr_drop_to_device(drop));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 
 extern "C" int kr_gn_bwd(const void* dy_bf16, const float* x, const int* row_group, const int* group_rows,
                          const double* stats, double* gsum, const float* gamma, const float* beta,
-                         void* dx_bf16, float* dgamma, float* dbeta, int R, int C, int G, void* stream) {
+                         void* dx_bf16, float* dgamma, float* dbeta, int R, int C, int G,
+                         const kr_drop_spec* drop, void* stream) {
   if (R <= 0) return KR_OK;
   if (C > 256 || (C % 32)) { kr_set_error("kr_gn: C must be a multiple of 32, <= 256"); return KR_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(gsum, 0, sizeof(double) * 2 * G, st) != cudaSuccess) { kr_set_error("memset failed"); return KR_ERR_CUDA; }
-  kr::launch(gn_bwd_stats_kernel, warp_blocks(R, 2), WARPS * 32, 0, st, (const bf16*)dy_bf16, x, row_group, stats, group_rows, gamma, beta, gsum, dgamma, dbeta, R, C);
+  kr::launch(gn_bwd_stats_kernel, warp_blocks(R, 2), WARPS * 32, 0, st, (const bf16*)dy_bf16, x, row_group, stats, group_rows, gamma, beta, gsum, dgamma, dbeta, R, C,
+             kr_drop_to_device(drop));
   KR_CHECK_LAUNCH();
-  kr::launch(gn_bwd_apply_kernel, warp_blocks(R), WARPS * 32, 0, st, (const bf16*)dy_bf16, x, row_group, stats, group_rows, gsum, gamma, beta, (bf16*)dx_bf16, R, C);
+  kr::launch(gn_bwd_apply_kernel, warp_blocks(R), WARPS * 32, 0, st, (const bf16*)dy_bf16, x, row_group, stats, group_rows, gsum, gamma, beta, (bf16*)dx_bf16, R, C,
+             kr_drop_to_device(drop));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -6,8 +6,9 @@ blocks -> variance adaptor (duration predictor, detached length regulation, pitc
 predictors and embeddings) -> teacher-forced 6-block decoder -> mel / stop heads; then the fused
 losses and a hand-scheduled backward over the four disjoint sub-graphs the reference's two
 ``detach()`` cuts create.  Host code only allocates tensors and orders launches; all arithmetic is
-in the CUDA library (tcgen05 GEMM / flash attention + HBM kernels).  Dropout / stochastic depth
-are not applied (p = 0, the parity configuration).
+in the CUDA library (tcgen05 GEMM / flash attention + HBM kernels).  Dropout and stochastic depth
+(``DropoutConfig``) are fused into those kernels through a counter-based RNG: masks are functions of
+(seed, step, site, element) and are regenerated, never stored (csrc/kr_common.cuh).
 """
 from __future__ import annotations
 
@@ -32,6 +33,27 @@ class LossConfig:
     w_energy: float = 1.0
     stop_pos_weight: float = 17.0
     huber_delta_var: float = 0.05
+
+
+@dataclass
+class DropoutConfig:
+    """Drop probabilities of the reference model (KokoroModel ctor, model/model.py:35-47,78; the
+    trainer's values are training/config.py:108-121,195).  All zeros = the deterministic parity
+    configuration."""
+    encoder: float = 0.0            # encoder attention / FFN / residual dropouts AND both positional-encoding dropouts
+    decoder: float = 0.0            # decoder attention / FFN / residual dropouts
+    decoder_input: float = 0.0      # F.dropout on the projected, shifted mel (model.py:525)
+    variance: float = 0.0           # VariancePredictor conv stack (variance_predictor.py:106)
+    stochastic_depth: float = 0.0   # max drop-path rate, linear over the layers (model.py:99-107)
+    seed: int = 0
+
+    @staticmethod
+    def reference_training() -> "DropoutConfig":
+        """TrainingConfig defaults: encoder 0.15, decoder 0.20, decoder input 0.15, variance 0.1, stochastic depth 0.1."""
+        return DropoutConfig(encoder=0.15, decoder=0.20, decoder_input=0.15, variance=0.1, stochastic_depth=0.1)
+
+    def any(self) -> bool:
+        return any(v > 0 for v in (self.encoder, self.decoder, self.decoder_input, self.variance, self.stochastic_depth))
 
 
 class PadGeom:
@@ -73,7 +95,8 @@ def _auto_splits(tiles: int, k_blocks: int, target: int = 296) -> int:
 
 class AcousticEngine:
     def __init__(self, cfg: ModelConfig, device=None, with_ema: bool = True,
-                 loss_cfg: Optional[LossConfig] = None, multi_stream: bool = True):
+                 loss_cfg: Optional[LossConfig] = None, multi_stream: bool = True,
+                 dropout: Optional[DropoutConfig] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("AcousticEngine needs a CUDA device: the hot path has no CPU fallback")
         self.cfg = cfg
@@ -101,6 +124,73 @@ class AcousticEngine:
         # SpecAugment span table (device int32 [B, n_time + n_feat, 2]) or None; see set_spec_augment()
         self.spec_spans: Optional[torch.Tensor] = None
         self.spec_n_time = self.spec_n_feat = 0
+        self.training = True
+        self._init_dropout(dropout)
+
+    # ------------------------------------------------------------------------------------------
+    # dropout / stochastic depth
+    # ------------------------------------------------------------------------------------------
+    def _init_dropout(self, dropout: Optional[DropoutConfig]) -> None:
+        """Site table: every dropout of the reference forward gets a fixed integer id (the RNG stream
+        selector); residual branches additionally get a row of the per-step stochastic-depth table."""
+        cfg = self.cfg
+        self.dropout = dropout if (dropout is not None and dropout.any()) else None
+        names: List[str] = ["enc.pe", "dec.in", "dec.pe"]
+        path: List[Tuple[str, float]] = []
+        sd = self.dropout.stochastic_depth if self.dropout is not None else 0.0
+        for i in range(cfg.n_encoder_layers):
+            rate = (i / max(cfg.n_encoder_layers - 1, 1)) * sd
+            for sub in ("attn", "ffn"):
+                names += [f"enc.{i}.{sub}.p", f"enc.{i}.{sub}.u", f"enc.{i}.{sub}.out", f"enc.{i}.{sub}.out2",
+                          f"enc.{i}.{sub}.path"]
+                path.append((f"enc.{i}.{sub}.path", rate))
+        for i in range(cfg.n_decoder_layers):
+            rate = (i / max(cfg.n_decoder_layers - 1, 1)) * sd
+            for sub in ("self", "cross", "ffn"):
+                names += [f"dec.{i}.{sub}.p", f"dec.{i}.{sub}.u", f"dec.{i}.{sub}.out", f"dec.{i}.{sub}.out2",
+                          f"dec.{i}.{sub}.path"]
+                path.append((f"dec.{i}.{sub}.path", rate))
+        for vp in ("duration", "pitch", "energy"):
+            names += [f"vp.{vp}.0", f"vp.{vp}.1"]
+        self.drop_sites: Dict[str, int] = {n: i + 1 for i, n in enumerate(names)}
+        self._path_rows: Dict[str, int] = {n: r for r, (n, _) in enumerate(path)}
+        self._path_rates = [r for _, r in path]
+        self._path_table: Optional[torch.Tensor] = None
+        if self.dropout is None:
+            self.drop_state = None
+            return
+        self.drop_state = torch.tensor([int(self.dropout.seed), 0], dtype=torch.int64, device=self.device)
+        self._path_site_dev = torch.tensor([self.drop_sites[n] for n, _ in path], dtype=torch.int32, device=self.device)
+        self._path_p_dev = torch.tensor(self._path_rates, dtype=torch.float32, device=self.device)
+
+    def set_dropout(self, dropout: Optional[DropoutConfig]) -> None:
+        self._init_dropout(dropout)
+
+    @property
+    def _drop_on(self) -> bool:
+        return self.training and self.dropout is not None
+
+    def _ds(self, site: Optional[str], p: float = 0.0, site_b: Optional[str] = None, p_b: float = 0.0,
+            path: Optional[str] = None, rows_per_sample: int = 1):
+        """Drop spec of one site (None when dropout is off or the site is a no-op)."""
+        if not self._drop_on:
+            return None
+        row = None
+        if path is not None and self._path_rates[self._path_rows[path]] > 0:
+            row = self._path_table[self._path_rows[path]]
+        return ops.make_drop_spec(self.drop_state, self.drop_sites[site] if site else 0, p,
+                                  self.drop_sites[site_b] if site_b else 0, p_b, row, rows_per_sample)
+
+    def _branch_specs(self, tag: str, p: float, S: int, ffn: bool) -> dict:
+        """Specs of one residual branch `tag` ('enc.3.attn', 'dec.0.ffn', ...) with rows_per_sample = S:
+        'p' attention probabilities, 'u' FFN inner dropout, 'out' branch output (the block's dropout, for an
+        FFN preceded by the FFN's own output dropout, and the stochastic-depth factor)."""
+        if not self._drop_on:
+            return {"p": None, "u": None, "out": None}
+        out = self._ds(f"{tag}.out", p, f"{tag}.out2" if ffn else None, p if ffn else 0.0, path=f"{tag}.path",
+                       rows_per_sample=S)
+        return {"p": None if ffn else self._ds(f"{tag}.p", p), "u": self._ds(f"{tag}.u", p) if ffn else None,
+                "out": out}
 
     # ------------------------------------------------------------------------------------------
     def _geom(self, B: int, L: int) -> PadGeom:
@@ -189,7 +279,8 @@ class AcousticEngine:
         return raw_kv, nkv
 
     def _attn_fwd(self, pre: str, x: torch.Tensor, B: int, S: int, norm: str, causal: bool,
-                  key_mask: Optional[torch.Tensor], mem: Optional[torch.Tensor], Sk: int, sv: dict, kv_pre=None):
+                  key_mask: Optional[torch.Tensor], mem: Optional[torch.Tensor], Sk: int, sv: dict, kv_pre=None,
+                  drop: Optional[dict] = None):
         st, D, H = self.store, self.D, self.H
         N = B * S
         cross = mem is not None
@@ -223,15 +314,19 @@ class AcousticEngine:
             sv.update(raw_q=raw_q, raw_kv=raw_kv, nq=nq, nkv=nkv)
         o = self._empty(N, D, dtype=BF16)
         lse = self._empty(B, H, S)
-        ops.attn_fwd(q, k, v, o.view(B, S, H, 64), lse, key_mask, causal, 1.0 / 8.0)
+        drop = drop or {"p": None, "out": None}
+        ops.attn_fwd(q, k, v, o.view(B, S, H, 64), lse, key_mask, causal, 1.0 / 8.0, drop=drop["p"])
         out = self._empty(N, D)
-        ops.gemm(o, st.w(pre + "w_o.weight"), out, bias=st.p(pre + "w_o.bias"), resid=x)
-        sv.update(x=x, h=h, mean=mean, rstd=rstd, o=o, lse=lse, q=q, k=k, v=v)
+        ops.gemm(o, st.w(pre + "w_o.weight"), out, bias=st.p(pre + "w_o.bias"), resid=x, drop=drop["out"])
+        sv.update(x=x, h=h, mean=mean, rstd=rstd, o=o, lse=lse, q=q, k=k, v=v, drop=drop)
         return out
 
     def _attn_bwd(self, pre: str, dout: torch.Tensor, dout_bf: torch.Tensor, B: int, S: int, norm: str,
                   causal: bool, key_mask, mem, Sk: int, sv: dict, dmem: Optional[torch.Tensor],
-                  dmem_first: bool):
+                  dmem_first: bool, next_drop=None):
+        """dout_bf must already carry this branch's output dropout (sv['drop']['out']): it is produced by the
+        layernorm_bwd of the sub-layer that follows in the forward.  next_drop = the output-dropout spec of the
+        branch that PRECEDES this one in the forward, applied to the returned dx_bf."""
         st, D, H = self.store, self.D, self.H
         N = B * S
         cross = mem is not None
@@ -244,7 +339,7 @@ class AcousticEngine:
         delta = self._empty(B, H, S)
         ops.attn_bwd(sv["q"], sv["k"], sv["v"], sv["o"].view(B, S, H, 64), d_o.view(B, S, H, 64), sv["lse"],
                      delta, dq.view(B, S, H, 64), dkv[:, :D].view(B, Sk, H, 64), dkv[:, D:].view(B, Sk, H, 64),
-                     key_mask, causal, 1.0 / 8.0)
+                     key_mask, causal, 1.0 / 8.0, drop=sv["drop"]["p"])
         gq, gk, gv = st.p(pre + "q_norm.weight"), st.p(pre + "k_norm.weight"), st.p(pre + "v_norm.weight")
         dgq, dgk, dgv = st.g(pre + "q_norm.weight"), st.g(pre + "k_norm.weight"), st.g(pre + "v_norm.weight")
         dh = self._empty(N, D)
@@ -275,13 +370,13 @@ class AcousticEngine:
         dx = self._empty(N, D)
         dx_bf = self._empty(N, D, dtype=BF16)
         ops.layernorm_bwd(dh, sv["x"], sv["mean"], sv["rstd"], st.p(norm + "weight"), dout, dx, dx_bf,
-                          st.g(norm + "weight"), st.g(norm + "bias"))
+                          st.g(norm + "weight"), st.g(norm + "bias"), drop_bf16=next_drop)
         return dx, dx_bf
 
     # ------------------------------------------------------------------------------------------
     # GLU feed-forward sub-layer
     # ------------------------------------------------------------------------------------------
-    def _ffn_fwd(self, pre: str, x: torch.Tensor, norm: str, ff: int, sv: dict):
+    def _ffn_fwd(self, pre: str, x: torch.Tensor, norm: str, ff: int, sv: dict, drop: Optional[dict] = None):
         st, D = self.store, self.D
         N = x.shape[0]
         h = self._empty(N, D, dtype=BF16)
@@ -290,31 +385,33 @@ class AcousticEngine:
         hff = self._empty(N, 2 * ff, dtype=BF16)
         ops.gemm(h, st.w(pre + "linear1.weight"), hff, bias=st.p(pre + "linear1.bias"))
         u = self._empty(N, ff, dtype=BF16)
-        ops.glu_fwd(hff, u)
+        drop = drop or {"u": None, "out": None}
+        ops.glu_fwd(hff, u, drop=drop["u"])
         y = self._empty(N, D)
         ops.gemm(u, st.w(pre + "linear2.weight"), y, bias=st.p(pre + "linear2.bias"))
         out = self._empty(N, D)
-        ops.rmsnorm_resid_fwd(y, st.p(pre + "output_norm.weight"), x, out)
-        sv.update(x=x, h=h, mean=mean, rstd=rstd, hff=hff, u=u, y=y)
+        ops.rmsnorm_resid_fwd(y, st.p(pre + "output_norm.weight"), x, out, drop=drop["out"])
+        sv.update(x=x, h=h, mean=mean, rstd=rstd, hff=hff, u=u, y=y, drop=drop)
         return out
 
-    def _ffn_bwd(self, pre: str, dout: torch.Tensor, norm: str, ff: int, sv: dict):
+    def _ffn_bwd(self, pre: str, dout: torch.Tensor, norm: str, ff: int, sv: dict, next_drop=None):
         st, D = self.store, self.D
         N = dout.shape[0]
         dy = self._empty(N, D, dtype=BF16)
-        ops.rmsnorm_resid_bwd(dout, sv["y"], st.p(pre + "output_norm.weight"), dy, st.g(pre + "output_norm.weight"))
+        ops.rmsnorm_resid_bwd(dout, sv["y"], st.p(pre + "output_norm.weight"), dy, st.g(pre + "output_norm.weight"),
+                              drop=sv["drop"]["out"])
         self._wgrad(dy, sv["u"], st.g(pre + "linear2.weight"), st.g(pre + "linear2.bias"))
         du = self._empty(N, ff, dtype=BF16)
         ops.gemm(dy, st.w(pre + "linear2.weight"), du, b_mn_major=True)
         dhff = self._empty(N, 2 * ff, dtype=BF16)
-        ops.glu_bwd(du, sv["hff"], dhff)
+        ops.glu_bwd(du, sv["hff"], dhff, drop=sv["drop"]["u"])
         self._wgrad(dhff, sv["h"], st.g(pre + "linear1.weight"), st.g(pre + "linear1.bias"))
         dh = self._empty(N, D)
         ops.gemm(dhff, st.w(pre + "linear1.weight"), dh, b_mn_major=True)
         dx = self._empty(N, D)
         dx_bf = self._empty(N, D, dtype=BF16)
         ops.layernorm_bwd(dh, sv["x"], sv["mean"], sv["rstd"], st.p(norm + "weight"), dout, dx, dx_bf,
-                          st.g(norm + "weight"), st.g(norm + "bias"))
+                          st.g(norm + "weight"), st.g(norm + "bias"), drop_bf16=next_drop)
         return dx, dx_bf
 
     # ------------------------------------------------------------------------------------------
@@ -325,8 +422,11 @@ class AcousticEngine:
         """[R, 3C] view whose row r spans guarded rows r..r+2 (= padded rows r-1, r, r+1)."""
         return torch.as_strided(buf_guarded, (R, 3 * C), (C, 1))
 
-    def _vp_fwd(self, pre: str, xg: torch.Tensor, geom: PadGeom, mask: Optional[torch.Tensor], sv: dict):
+    def _vp_fwd(self, pre: str, xg: torch.Tensor, geom: PadGeom, mask: Optional[torch.Tensor], sv: dict,
+                tag: str = ""):
         st, Fv = self.store, self.cfg.variance_filter_size
+        pv = self.dropout.variance if self._drop_on else 0.0
+        d1, d2 = self._ds(f"vp.{tag}.0", pv), self._ds(f"vp.{tag}.1", pv)
         R, Cin = geom.R, xg.shape[1]
         a1 = self._conv_view(xg, R, Cin)
         c1 = self._empty(R, Fv)
@@ -334,18 +434,18 @@ class AcousticEngine:
         h1g = self._zeros(R + 2, Fv, dtype=BF16)
         stats1 = self._empty(geom.G, 2, dtype=torch.float64)
         ops.gn_fwd(c1, geom.row_group, geom.group_rows, stats1, st.p(pre + "norms.0.weight"),
-                   st.p(pre + "norms.0.bias"), h1g[1:R + 1])
+                   st.p(pre + "norms.0.bias"), h1g[1:R + 1], drop=d1)
         a2 = self._conv_view(h1g, R, Fv)
         c2 = self._empty(R, Fv)
         ops.gemm(a2, st.w(pre + "conv_layers.1.weight"), c2, bias=st.p(pre + "conv_layers.1.bias"))
         h2 = self._empty(R, Fv, dtype=BF16)
         stats2 = self._empty(geom.G, 2, dtype=torch.float64)
         ops.gn_fwd(c2, geom.row_group, geom.group_rows, stats2, st.p(pre + "norms.1.weight"),
-                   st.p(pre + "norms.1.bias"), h2)
+                   st.p(pre + "norms.1.bias"), h2, drop=d2)
         out = self._empty(geom.B, geom.L)
         ops.vp_head_fwd(h2, geom.row_of_tok, st.p(pre + "linear.weight"), st.p(pre + "linear.bias"), mask, out,
                         geom.L, self.cfg.vp_chunk)
-        sv.update(xg=xg, c1=c1, h1g=h1g, stats1=stats1, c2=c2, h2=h2, stats2=stats2, mask=mask)
+        sv.update(xg=xg, c1=c1, h1g=h1g, stats1=stats1, c2=c2, h2=h2, stats2=stats2, mask=mask, d1=d1, d2=d2)
         return out
 
     def _vp_bwd(self, pre: str, dout: torch.Tensor, geom: PadGeom, sv: dict, need_dx: bool):
@@ -357,14 +457,16 @@ class AcousticEngine:
         gsum = self._empty(geom.G, 2, dtype=torch.float64)
         dc2g = self._zeros(R + 2, Fv, dtype=BF16)
         ops.gn_bwd(dh2, sv["c2"], geom.row_group, geom.group_rows, sv["stats2"], gsum, st.p(pre + "norms.1.weight"),
-                   st.p(pre + "norms.1.bias"), dc2g[1:R + 1], st.g(pre + "norms.1.weight"), st.g(pre + "norms.1.bias"))
+                   st.p(pre + "norms.1.bias"), dc2g[1:R + 1], st.g(pre + "norms.1.weight"), st.g(pre + "norms.1.bias"),
+                   drop=sv["d2"])
         self._wgrad(dc2g[1:R + 1], self._conv_view(sv["h1g"], R, Fv), st.g(pre + "conv_layers.1.weight"),
                     st.g(pre + "conv_layers.1.bias"))
         dh1 = self._empty(R, Fv, dtype=BF16)
         ops.gemm(self._conv_view(dc2g, R, Fv), st.conv_dgrad[pre + "conv_layers.1.weight"], dh1)
         dc1g = self._zeros(R + 2, Fv, dtype=BF16)
         ops.gn_bwd(dh1, sv["c1"], geom.row_group, geom.group_rows, sv["stats1"], gsum, st.p(pre + "norms.0.weight"),
-                   st.p(pre + "norms.0.bias"), dc1g[1:R + 1], st.g(pre + "norms.0.weight"), st.g(pre + "norms.0.bias"))
+                   st.p(pre + "norms.0.bias"), dc1g[1:R + 1], st.g(pre + "norms.0.weight"), st.g(pre + "norms.0.bias"),
+                   drop=sv["d1"])
         self._wgrad(dc1g[1:R + 1], self._conv_view(sv["xg"], R, Cin), st.g(pre + "conv_layers.0.weight"),
                     st.g(pre + "conv_layers.0.bias"))
         if not need_dx:
@@ -395,20 +497,30 @@ class AcousticEngine:
         if Tp < 3:
             raise RuntimeError("expanded length < 3 frames is not supported")
         ctx["Tp"] = Tp
+        dcfg = self.dropout if self._drop_on else None
+        p_enc = dcfg.encoder if dcfg else 0.0
+        p_dec = dcfg.decoder if dcfg else 0.0
+        if dcfg is not None:      # new RNG step + this step's stochastic-depth factors
+            self._path_table = self._empty(len(self._path_rates), B)
+            ops.drop_begin(self.drop_state, self._path_site_dev, self._path_p_dev, self._path_table, B)
 
         # ---- encoder -------------------------------------------------------------------------
         idx = phoneme_indices.contiguous()
         stress = stress_indices.contiguous() if stress_indices is not None else None
         x = self._empty(Ne, D)
-        ops.embed_fwd(idx, stress, st.p("text_embedding.weight"), st.p("stress_embedding.weight"), st.pe, x, P)
+        ctx["drop_pe"] = self._ds("enc.pe", p_enc)
+        ops.embed_fwd(idx, stress, st.p("text_embedding.weight"), st.p("stress_embedding.weight"), st.pe, x, P,
+                      drop=ctx["drop_pe"])
         text_pad = self._empty(B, P, dtype=torch.uint8)
         ops.eq_mask(idx, 0, text_pad)
         enc_saved = []
         for i in range(cfg.n_encoder_layers):
             pre = f"transformer_encoder_layers.{i}."
             s1, s2 = {}, {}
-            x = self._attn_fwd(pre + "self_attn.", x, B, P, pre + "norm1.", False, text_pad, None, P, s1)
-            x = self._ffn_fwd(pre + "ff.", x, pre + "norm2.", cfg.encoder_ff_dim, s2)
+            x = self._attn_fwd(pre + "self_attn.", x, B, P, pre + "norm1.", False, text_pad, None, P, s1,
+                               drop=self._branch_specs(f"enc.{i}.attn", p_enc, P, False))
+            x = self._ffn_fwd(pre + "ff.", x, pre + "norm2.", cfg.encoder_ff_dim, s2,
+                              drop=self._branch_specs(f"enc.{i}.ffn", p_enc, P, True))
             enc_saved.append((s1, s2))
         enc = self._empty(Ne, D)
         enc_mean, enc_rstd = self._empty(Ne), self._empty(Ne)
@@ -422,7 +534,7 @@ class AcousticEngine:
         with self._on("vp"):
             xg_tok = self._zeros(gt.R + 2, D, dtype=BF16)
             ops.scatter_rows(enc, gt.row_of_tok, xg_tok[1:])
-            log_dur = self._vp_fwd(va + "duration_predictor.", xg_tok, gt, text_pad, sv_dur)
+            log_dur = self._vp_fwd(va + "duration_predictor.", xg_tok, gt, text_pad, sv_dur, "duration")
 
         dur = phoneme_durations.contiguous()
         lr_idx = self._empty(B, Tp, dtype=torch.int32)
@@ -446,9 +558,9 @@ class AcousticEngine:
             ops.spec_augment(mem.view(B, T, D), self.spec_spans, self.spec_n_time, self.spec_n_feat)
         sv_pitch, sv_energy = {}, {}
         with self._on("vp"):
-            pitch_pred = self._vp_fwd(va + "pitch_predictor.", xg_frm, gf, fmask_p, sv_pitch)
+            pitch_pred = self._vp_fwd(va + "pitch_predictor.", xg_frm, gf, fmask_p, sv_pitch, "pitch")
         with self._on("enc"):
-            energy_pred = self._vp_fwd(va + "energy_predictor.", xg_frm, gf, fmask_p, sv_energy)
+            energy_pred = self._vp_fwd(va + "energy_predictor.", xg_frm, gf, fmask_p, sv_energy, "energy")
         ctx.update(sv_dur=sv_dur, sv_pitch=sv_pitch, sv_energy=sv_energy, lr_idx=lr_idx, lengths=lengths,
                    mem=mem, p_idx=p_idx, e_idx=e_idx, fmask_t=fmask_t, fmask_p=fmask_p)
 
@@ -457,8 +569,23 @@ class AcousticEngine:
         melshift = self._empty(Nd, cfg.mel_dim, dtype=BF16)
         ops.shift_cast(mel, melshift.view(B, T, cfg.mel_dim))
         y = self._empty(Nd, D)
-        ops.gemm(melshift, st.w("mel_projection_in.weight"), y, bias=st.p("mel_projection_in.bias"),
-                 resid=st.pe[:T], resid_mod=T)
+        # dropout(dropout(proj, p_in) + PE, p_enc): model.py:525-531 (the PE module is shared with the encoder)
+        ctx["drop_in"] = self._ds("dec.in", dcfg.decoder_input if dcfg else 0.0, "dec.pe", p_enc)
+        if ctx["drop_in"] is None:
+            ops.gemm(melshift, st.w("mel_projection_in.weight"), y, bias=st.p("mel_projection_in.bias"),
+                     resid=st.pe[:T], resid_mod=T)
+        else:
+            t_in = self._empty(Nd, D)
+            ops.gemm(melshift, st.w("mel_projection_in.weight"), t_in, bias=st.p("mel_projection_in.bias"))
+            # forward needs the two masks separately (the PE is added between them); ctx["drop_in"] (their
+            # product) is what the backward applies to the weight-gradient operand
+            spec = ops.DropSpec()
+            spec.state = self.drop_state.data_ptr()
+            spec.site_a, spec.thr_a = self.drop_sites["dec.in"], ops.drop_thr(dcfg.decoder_input)
+            spec.site_b, spec.thr_b = self.drop_sites["dec.pe"], ops.drop_thr(p_enc)
+            scale_a = 1.0 / ops.drop_keep(dcfg.decoder_input)
+            spec.scale = scale_a / ops.drop_keep(p_enc)
+            ops.dec_in_drop(t_in, st.pe[:T], y, T, spec, scale_a)
         dec_saved = []
         kv_pre = [None] * cfg.n_decoder_layers
         if self.multi_stream:                 # all six cross-attention K/V projections depend on `mem` only
@@ -471,10 +598,12 @@ class AcousticEngine:
         for i in range(cfg.n_decoder_layers):
             pre = f"decoder.layers.{i}."
             s1, s2, s3 = {}, {}, {}
-            y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, None, None, T, s1)
+            y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, None, None, T, s1,
+                               drop=self._branch_specs(f"dec.{i}.self", p_dec, T, False))
             y = self._attn_fwd(pre + "cross_attn.", y, B, T, pre + "norm2.", False, fmask_t, mem, T, s2,
-                               kv_pre=kv_pre[i])
-            y = self._ffn_fwd(pre + "ff.", y, pre + "norm3.", cfg.decoder_ff_dim, s3)
+                               kv_pre=kv_pre[i], drop=self._branch_specs(f"dec.{i}.cross", p_dec, T, False))
+            y = self._ffn_fwd(pre + "ff.", y, pre + "norm3.", cfg.decoder_ff_dim, s3,
+                              drop=self._branch_specs(f"dec.{i}.ffn", p_dec, T, True))
             dec_saved.append((s1, s2, s3))
         yn = self._empty(Nd, D, dtype=BF16)
         dn_mean, dn_rstd = self._empty(Nd), self._empty(Nd)
@@ -531,11 +660,12 @@ class AcousticEngine:
             for i in reversed(range(cfg.n_encoder_layers)):
                 pre = f"transformer_encoder_layers.{i}."
                 s1, s2 = ctx["enc_saved"][i]
-                dx, dx_bf = self._ffn_bwd(pre + "ff.", dx, pre + "norm2.", cfg.encoder_ff_dim, s2)
+                dx, dx_bf = self._ffn_bwd(pre + "ff.", dx, pre + "norm2.", cfg.encoder_ff_dim, s2,
+                                          next_drop=s1["drop"]["out"])
                 dx, dx_bf = self._attn_bwd(pre + "self_attn.", dx, dx_bf, B, P, pre + "norm1.", False,
                                            ctx["text_pad"], None, P, s1, None, False)
             ops.embed_bwd(dx, ctx["idx"], ctx["stress"], st.g("text_embedding.weight"),
-                          st.g("stress_embedding.weight"))
+                          st.g("stress_embedding.weight"), drop=ctx["drop_pe"])
         # (iii) pitch / energy losses -> their predictors only (input is the detached expansion)
         with self._on("vp"):
             self._vp_bwd(va + "pitch_predictor.", g["pitch"], gf, ctx["sv_pitch"], need_dx=False)
@@ -556,12 +686,14 @@ class AcousticEngine:
         for i in reversed(range(cfg.n_decoder_layers)):
             pre = f"decoder.layers.{i}."
             s1, s2, s3 = ctx["dec_saved"][i]
-            dy, dy_bf = self._ffn_bwd(pre + "ff.", dy, pre + "norm3.", cfg.decoder_ff_dim, s3)
+            dy, dy_bf = self._ffn_bwd(pre + "ff.", dy, pre + "norm3.", cfg.decoder_ff_dim, s3,
+                                      next_drop=s2["drop"]["out"])
             dy, dy_bf = self._attn_bwd(pre + "cross_attn.", dy, dy_bf, B, T, pre + "norm2.", False, ctx["fmask_t"],
-                                       ctx["mem"], T, s2, dmem, first)
+                                       ctx["mem"], T, s2, dmem, first, next_drop=s1["drop"]["out"])
             first = False
+            # layer 0: the bf16 copy feeds mel_projection_in's weight gradient through both input dropouts
             dy, dy_bf = self._attn_bwd(pre + "self_attn.", dy, dy_bf, B, T, pre + "norm1.", True, None, None, T,
-                                       s1, None, False)
+                                       s1, None, False, next_drop=ctx["drop_in"] if i == 0 else None)
         self._wgrad(dy_bf, ctx["melshift"], st.g("mel_projection_in.weight"), st.g("mel_projection_in.bias"))
         self._join_all()
         # memory gradient (accumulated on the "kv" stream) reaches only the pitch / energy embedding rows

@@ -93,6 +93,8 @@ class OpTimer:
             fn = getattr(ops, name)
             if name.startswith("_") or not callable(fn) or getattr(fn, "__module__", None) != ops.__name__:
                 continue
+            if isinstance(fn, type) or name in ("make_drop_spec", "drop_thr", "drop_keep"):
+                continue      # host-side helpers: no launch
             self._saved[name] = fn
             setattr(ops, name, self._wrap(name, fn))
         if self.spin_ms > 0:

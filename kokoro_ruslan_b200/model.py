@@ -10,9 +10,10 @@ tensors wired into autograd through ONE ``torch.autograd.Function``; ``loss.back
 the hand-scheduled CUDA backward, which accumulates into a flat gradient buffer that every
 parameter's ``.grad`` is a view of.  Nothing here computes on the CPU or through ATen math.
 
-Reference behaviours that are deliberately NOT reproduced on this path are listed in DESIGN.md
-("parity configuration"): dropout / stochastic depth are 0, inference (``mel_specs=None``) is the
-"next" row N2 and raises NotImplementedError.
+Dropout and stochastic depth follow the constructor arguments in ``train()`` mode (fused into the
+kernels, counter-based RNG) and are off in ``eval()``.  Reference behaviours that are deliberately
+NOT reproduced on this path are listed in DESIGN.md: inference (``mel_specs=None``) is the "next"
+row N2 and raises NotImplementedError.
 """
 from __future__ import annotations
 
@@ -20,7 +21,7 @@ from typing import Callable, Dict, Iterator, List, Optional, Tuple
 
 import torch
 
-from .engine import AcousticEngine, LossConfig
+from .engine import AcousticEngine, DropoutConfig, LossConfig
 from .params import ModelConfig
 
 
@@ -93,7 +94,10 @@ class KokoroModel:
                           n_decoder_layers=n_decoder_layers, decoder_ff_dim=decoder_ff_dim,
                           max_decoder_seq_len=max_decoder_seq_len, variance_filter_size=variance_filter_size,
                           n_variance_bins=n_variance_bins)
-        self.engine = AcousticEngine(cfg, device, with_ema=False)
+        dec_p = decoder_dropout if decoder_dropout is not None else encoder_dropout     # model.py:78
+        self.engine = AcousticEngine(cfg, device, with_ema=False, dropout=DropoutConfig(
+            encoder=encoder_dropout, decoder=dec_p, decoder_input=decoder_input_dropout, variance=variance_dropout,
+            stochastic_depth=stochastic_depth_rate if use_stochastic_depth else 0.0, seed=seed))
         self.engine.store.init_default(seed=seed)
         self.training = True
         self.external_optimizer = True
@@ -123,6 +127,7 @@ class KokoroModel:
 
     def train(self, mode: bool = True):
         self.training = bool(mode)
+        self.engine.training = self.training      # eval(): dropout / stochastic depth off (nn.Module semantics)
         return self
 
     def eval(self):
@@ -179,9 +184,6 @@ class KokoroModel:
         if text_padding_mask is not None or mel_padding_mask is not None:
             raise NotImplementedError("explicit padding masks: the trainer always passes None (text mask = "
                                       "indices == 0, no mel mask; trainer.py:3226-3230)")
-        if self.training and any(v for v in self.dropouts.values()):
-            # parity configuration: dropout / stochastic depth are not applied
-            pass
         outs = _TrainingForward.apply(self._hook, self, phoneme_indices, mel_specs, phoneme_durations, pitch_targets,
                                       energy_targets, stress_indices)
         return outs

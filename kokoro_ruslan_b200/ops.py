@@ -20,6 +20,45 @@ c_float = ctypes.c_float
 EPI_BF16, EPI_F32, EPI_ATOMIC_F32 = 0, 1, 2
 
 
+class DropSpec(ctypes.Structure):
+    """ctypes mirror of kr_drop_spec (include/kokoro_b200.h): one dropout / stochastic-depth site."""
+    _fields_ = [("state", c_void_p), ("site_a", ctypes.c_uint), ("thr_a", ctypes.c_uint),
+                ("site_b", ctypes.c_uint), ("thr_b", ctypes.c_uint), ("scale", c_float),
+                ("row_scale", c_void_p), ("rows_per_sample", c_int)]
+
+
+def drop_thr(p: float) -> int:
+    """16-bit keep threshold of drop probability p: keep iff lane16 >= thr."""
+    return max(0, min(65535, int(round(float(p) * 65536.0))))
+
+
+def drop_keep(p: float) -> float:
+    """Exact keep probability realised by drop_thr(p)."""
+    return 1.0 - drop_thr(p) / 65536.0
+
+
+def make_drop_spec(state: torch.Tensor, site_a: int = 0, p_a: float = 0.0, site_b: int = 0, p_b: float = 0.0,
+                   row_scale: Optional[torch.Tensor] = None, rows_per_sample: int = 1) -> Optional["DropSpec"]:
+    """None when the site is a no-op (both probabilities 0 and no per-sample factors)."""
+    ta, tb = drop_thr(p_a), drop_thr(p_b)
+    if ta == 0 and tb == 0 and row_scale is None:
+        return None
+    if ta == 0 and tb != 0:
+        site_a, ta, site_b, tb = site_b, tb, 0, 0
+    d = DropSpec()
+    d.state = state.data_ptr()
+    d.site_a, d.thr_a, d.site_b, d.thr_b = site_a, ta, site_b, tb
+    d.scale = 1.0 / ((1.0 - ta / 65536.0) * (1.0 - tb / 65536.0))
+    d.row_scale = row_scale.data_ptr() if row_scale is not None else None
+    d.rows_per_sample = rows_per_sample
+    d._keep = (state, row_scale)       # the spec borrows device memory
+    return d
+
+
+def _dref(d: Optional["DropSpec"]):
+    return ctypes.byref(d) if d is not None else None
+
+
 def _ptr(t: Optional[torch.Tensor]) -> c_void_p:
     if t is None:
         return c_void_p(0)
@@ -35,7 +74,7 @@ def _stream() -> c_void_p:
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major: bool = False,
          b_mn_major: bool = False, bias: Optional[torch.Tensor] = None,
          resid: Optional[torch.Tensor] = None, resid_mod: int = 0, alpha: float = 1.0,
-         accumulate: bool = False, splits: int = 1) -> torch.Tensor:
+         accumulate: bool = False, splits: int = 1, drop: Optional[DropSpec] = None) -> torch.Tensor:
     """out[M,N] (+)= alpha * A @ B^T (+bias) (+resid) on tcgen05 (bf16 in, fp32 accumulate).
 
     A logical [M,K]: stored [M,K] (K-major) or, if a_mn_major, stored [K,M].
@@ -76,6 +115,21 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major: boo
         sr = resid.stride(0) if (batched and resid.dim() == 3) else 0
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
+    if drop is not None:             # dropout epilogue: v = drop(alpha*acc + bias) + resid  (kr_gemm_ex only)
+        assert not batched and not accumulate and splits == 1
+        g = GemmArgs()
+        g.A, g.B, g.M, g.N, g.K, g.batch = _p(a), _p(b), M, N, K, 1
+        g.lda, g.ldb = a2.stride(0), b2.stride(0)
+        g.a_mn_major, g.b_mn_major = int(a_mn_major), int(b_mn_major)
+        g.alpha, g.beta = alpha, 1.0
+        g.bias = _p(bias)
+        if resid is not None:
+            g.resid, g.resid_dtype, g.ldr, g.resid_mod = _p(resid), 0, ldr, resid_mod
+        g.C, g.c_mode, g.ldc = _p(out), epi, o2.stride(0)
+        g.splits = 1
+        g.drop = ctypes.addressof(drop)
+        check(lib().kr_gemm_ex(ctypes.byref(g), _stream()), "kr_gemm_ex")
+        return out
     rc = lib().kr_gemm_bf16(_ptr(a), _ptr(b), _ptr(out), c_int(M), c_int(N), c_int(K), c_int(batch),
                             c_ll(a2.stride(0)), c_ll(b2.stride(0)), c_ll(o2.stride(0)),
                             c_ll(sa), c_ll(sb), c_ll(sc), c_int(int(a_mn_major)),
@@ -100,7 +154,7 @@ class GemmArgs(ctypes.Structure):
                 ("resid2", c_void_p), ("resid2_dtype", c_int), ("ldr2", c_ll), ("stride_r2", c_ll),
                 ("C", c_void_p), ("c_mode", c_int), ("ldc", c_ll), ("stride_c", c_ll),
                 ("C2", c_void_p), ("ldc2", c_ll), ("stride_c2", c_ll), ("act_slope", c_float),
-                ("splits", c_int), ("force_block_n", c_int), ("no_slab", c_int)]
+                ("splits", c_int), ("force_block_n", c_int), ("no_slab", c_int), ("drop", c_void_p)]
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -167,7 +221,8 @@ def _heads_strides(t: torch.Tensor):
     return c_ll(t.stride(1)), c_ll(t.stride(0))
 
 
-def attn_fwd(q, k, v, o, lse, key_mask: Optional[torch.Tensor], causal: bool, scale: float):
+def attn_fwd(q, k, v, o, lse, key_mask: Optional[torch.Tensor], causal: bool, scale: float,
+             drop: Optional[DropSpec] = None):
     """Flash attention forward (tcgen05).  q,o: [B,Sq,H,64]; k,v: [B,Sk,H,64]; lse: [B,H,Sq] f32
     (log2 domain); key_mask: [B,Sk] uint8 (1 = masked) or None."""
     B, Sq, H, _ = q.shape
@@ -178,11 +233,12 @@ def attn_fwd(q, k, v, o, lse, key_mask: Optional[torch.Tensor], causal: bool, sc
     rc = lib().kr_attn_fwd(_ptr(q), *_heads_strides(q), _ptr(k), *_heads_strides(k), _ptr(v),
                            *_heads_strides(v), _ptr(o), *_heads_strides(o), _ptr(lse),
                            _ptr(key_mask), c_int(B), c_int(H), c_int(Sq), c_int(Sk),
-                           c_int(int(causal)), c_float(scale), _stream())
+                           c_int(int(causal)), c_float(scale), _dref(drop), _stream())
     check(rc, "kr_attn_fwd")
 
 
-def attn_bwd(q, k, v, o, d_o, lse, delta, dq, dk, dv, key_mask, causal: bool, scale: float):
+def attn_bwd(q, k, v, o, d_o, lse, delta, dq, dk, dv, key_mask, causal: bool, scale: float,
+             drop: Optional[DropSpec] = None):
     """Flash attention backward.  dq: fp32 [B,Sq,H,64] and must be ZEROED by the caller (atomic
     accumulation); dk, dv: bf16 [B,Sk,H,64]; delta: fp32 scratch [B,H,Sq]."""
     B, Sq, H, _ = q.shape
@@ -193,7 +249,7 @@ def attn_bwd(q, k, v, o, d_o, lse, delta, dq, dk, dv, key_mask, causal: bool, sc
                            *_heads_strides(d_o), _ptr(lse), _ptr(delta), _ptr(dq),
                            c_ll(dq.stride(1)), c_ll(dq.stride(0)), _ptr(dk), *_heads_strides(dk),
                            _ptr(dv), *_heads_strides(dv), _ptr(key_mask), c_int(B), c_int(H),
-                           c_int(Sq), c_int(Sk), c_int(int(causal)), c_float(scale), _stream())
+                           c_int(Sq), c_int(Sk), c_int(int(causal)), c_float(scale), _dref(drop), _stream())
     check(rc, "kr_attn_bwd")
 
 
@@ -206,23 +262,27 @@ def layernorm_fwd(x, gamma, beta, y_bf16, y_f32, mean, rstd, eps: float = 1e-5):
                                  _ptr(rstd), c_int(N), c_int(D), c_float(eps), _stream()), "kr_layernorm_fwd")
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, dx_bf16, dgamma, dbeta):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, dx_bf16, dgamma, dbeta, drop_bf16: Optional[DropSpec] = None):
+    """drop_bf16: dropout / stochastic-depth factors applied to the bf16 copy only (it feeds the backward of
+    the dropped residual branch that precedes this norm; dx itself is the residual-stream gradient)."""
     N, D = x.shape
     check(lib().kr_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres), _ptr(dx),
-                                 _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), c_int(N), c_int(D), _stream()),
+                                 _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), c_int(N), c_int(D), _dref(drop_bf16),
+                                 _stream()),
           "kr_layernorm_bwd")
 
 
-def rmsnorm_resid_fwd(y, gain, resid, out):
+def rmsnorm_resid_fwd(y, gain, resid, out, drop: Optional[DropSpec] = None):
     N, D = y.shape
-    check(lib().kr_rmsnorm_resid_fwd(_ptr(y), _ptr(gain), _ptr(resid), _ptr(out), c_int(N), c_int(D), _stream()),
+    check(lib().kr_rmsnorm_resid_fwd(_ptr(y), _ptr(gain), _ptr(resid), _ptr(out), c_int(N), c_int(D), _dref(drop),
+                                     _stream()),
           "kr_rmsnorm_resid_fwd")
 
 
-def rmsnorm_resid_bwd(dout, y, gain, dy_bf16, dgain):
+def rmsnorm_resid_bwd(dout, y, gain, dy_bf16, dgain, drop: Optional[DropSpec] = None):
     N, D = y.shape
     check(lib().kr_rmsnorm_resid_bwd(_ptr(dout), _ptr(y), _ptr(gain), _ptr(dy_bf16), _ptr(dgain), c_int(N),
-                                     c_int(D), _stream()), "kr_rmsnorm_resid_bwd")
+                                     c_int(D), _dref(drop), _stream()), "kr_rmsnorm_resid_bwd")
 
 
 def _parts3(ts):
@@ -258,14 +318,14 @@ def qkv_prep_bwd(ins, grads, outs, gains, dgains, rope_mask: int, cos_t, sin_t, 
           "kr_qkv_prep_bwd")
 
 
-def glu_fwd(h, u):
+def glu_fwd(h, u, drop: Optional[DropSpec] = None):
     N, FF = u.shape
-    check(lib().kr_glu_fwd(_ptr(h), _ptr(u), c_int(N), c_int(FF), _stream()), "kr_glu_fwd")
+    check(lib().kr_glu_fwd(_ptr(h), _ptr(u), c_int(N), c_int(FF), _dref(drop), _stream()), "kr_glu_fwd")
 
 
-def glu_bwd(du, h, dh):
+def glu_bwd(du, h, dh, drop: Optional[DropSpec] = None):
     N, FF = du.shape
-    check(lib().kr_glu_bwd(_ptr(du), _ptr(h), _ptr(dh), c_int(N), c_int(FF), _stream()), "kr_glu_bwd")
+    check(lib().kr_glu_bwd(_ptr(du), _ptr(h), _ptr(dh), c_int(N), c_int(FF), _dref(drop), _stream()), "kr_glu_bwd")
 
 
 def colsum_bf16(x, out):
@@ -274,16 +334,16 @@ def colsum_bf16(x, out):
           "kr_colsum_bf16")
 
 
-def embed_fwd(idx, stress, emb, semb, pe, x, P: int):
+def embed_fwd(idx, stress, emb, semb, pe, x, P: int, drop: Optional[DropSpec] = None):
     N, D = x.shape
     check(lib().kr_embed_fwd(_ptr(idx), _ptr(stress), _ptr(emb), _ptr(semb), _ptr(pe), _ptr(x), c_int(N),
-                             c_int(P), c_int(D), _stream()), "kr_embed_fwd")
+                             c_int(P), c_int(D), _dref(drop), _stream()), "kr_embed_fwd")
 
 
-def embed_bwd(dx, idx, stress, demb, dsemb):
+def embed_bwd(dx, idx, stress, demb, dsemb, drop: Optional[DropSpec] = None):
     N, D = dx.shape
     check(lib().kr_embed_bwd(_ptr(dx), _ptr(idx), _ptr(stress), _ptr(demb), _ptr(dsemb), c_int(N), c_int(D),
-                             _stream()), "kr_embed_bwd")
+                             _dref(drop), _stream()), "kr_embed_bwd")
 
 
 def shift_cast(mel, out):
@@ -340,17 +400,39 @@ def adapt_bwd(dmem, p_idx, e_idx, dpemb, deemb):
                              _stream()), "kr_adapt_bwd")
 
 
-def gn_fwd(x, row_group, group_rows, stats, gamma, beta, out):
+def gn_fwd(x, row_group, group_rows, stats, gamma, beta, out, drop: Optional[DropSpec] = None):
     R, C = x.shape
     check(lib().kr_gn_fwd(_ptr(x), _ptr(row_group), _ptr(group_rows), _ptr(stats), _ptr(gamma), _ptr(beta),
-                          _ptr(out), c_int(R), c_int(C), c_int(group_rows.numel()), _stream()), "kr_gn_fwd")
+                          _ptr(out), c_int(R), c_int(C), c_int(group_rows.numel()), _dref(drop), _stream()),
+          "kr_gn_fwd")
 
 
-def gn_bwd(dy, x, row_group, group_rows, stats, gsum, gamma, beta, dx, dgamma, dbeta):
+def gn_bwd(dy, x, row_group, group_rows, stats, gsum, gamma, beta, dx, dgamma, dbeta,
+           drop: Optional[DropSpec] = None):
     R, C = x.shape
     check(lib().kr_gn_bwd(_ptr(dy), _ptr(x), _ptr(row_group), _ptr(group_rows), _ptr(stats), _ptr(gsum),
                           _ptr(gamma), _ptr(beta), _ptr(dx), _ptr(dgamma), _ptr(dbeta), c_int(R), c_int(C),
-                          c_int(group_rows.numel()), _stream()), "kr_gn_bwd")
+                          c_int(group_rows.numel()), _dref(drop), _stream()), "kr_gn_bwd")
+
+
+def drop_begin(state, path_site, path_p, table, B: int):
+    """New dropout step: state[1] += 1, table[s, b] = stochastic-depth factor of branch s / sample b."""
+    n = path_site.numel()
+    check(lib().kr_drop_begin(_ptr(state), _ptr(path_site), _ptr(path_p), _ptr(table), c_int(n), c_int(B), _stream()),
+          "kr_drop_begin")
+
+
+def dec_in_drop(t, pe, y, T: int, drop: DropSpec, scale_a: float):
+    N, D = t.shape
+    check(lib().kr_dec_in_drop(_ptr(t), _ptr(pe), _ptr(y), c_int(N), c_int(T), c_int(D), c_float(scale_a),
+                               _dref(drop), _stream()), "kr_dec_in_drop")
+
+
+def drop_export_mask(state, site: int, p: float, rows: int, cols: int, ld: int, out):
+    """out[rows, cols] uint8 = keep mask of `site` for elements r*ld + c (test aid)."""
+    assert out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == rows * cols
+    check(lib().kr_drop_export_mask(_ptr(state), ctypes.c_uint(site), ctypes.c_uint(drop_thr(p)), c_ll(rows),
+                                    c_int(cols), c_ll(ld), _ptr(out), _stream()), "kr_drop_export_mask")
 
 
 def vp_head_fwd(h, row_of_tok, w, b, mask, out, L: int, chunk: int):

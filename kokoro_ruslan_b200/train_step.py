@@ -26,7 +26,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from ._lib import launch_count
-from .engine import AcousticEngine, LossConfig
+from .engine import AcousticEngine, DropoutConfig, LossConfig
 from .optim import FusedAdamW, OptimConfig
 from .params import ModelConfig
 
@@ -144,8 +144,9 @@ class TrainStep:
     def __init__(self, model_cfg: Optional[ModelConfig] = None, optim_cfg: Optional[OptimConfig] = None,
                  sched_cfg: Optional[ScheduleConfig] = None, loss_cfg: Optional[LossConfig] = None,
                  device=None, use_graphs: bool = True, process_group=None, max_seq_cap: int = 2000,
-                 max_cached_shapes: int = 16):
-        self.engine = AcousticEngine(model_cfg or ModelConfig(), device, with_ema=True, loss_cfg=loss_cfg)
+                 max_cached_shapes: int = 16, dropout: Optional[DropoutConfig] = None):
+        self.engine = AcousticEngine(model_cfg or ModelConfig(), device, with_ema=True, loss_cfg=loss_cfg,
+                                     dropout=dropout)
         self.device = self.engine.device
         self.opt = FusedAdamW(self.engine.store, optim_cfg or OptimConfig())
         self.sched = WarmupOneCycle(self.opt.cfg.learning_rate, self.opt.lr_mult, sched_cfg or ScheduleConfig())

@@ -71,8 +71,9 @@ class CpuTrainStep:
     """fp32 CPU training step over a flat {name: tensor} state dict."""
 
     def __init__(self, cfg: oa.AcousticConfig, sd: Dict[str, torch.Tensor], lr: float = 5e-5,
-                 max_grad_norm: float = 1.5, ema_decay: float = 0.999, wn_max: float = 95.0):
+                 max_grad_norm: float = 1.5, ema_decay: float = 0.999, wn_max: float = 95.0, drop=None):
         self.cfg = cfg
+        self.drop = drop      # oracle.acoustic dropout callback (None = p 0)
         self.sd = {k: (v.clone().requires_grad_(True) if k not in oa.BUFFER_KEYS else v.clone())
                    for k, v in sd.items()}
         self.names = [k for k in self.sd if k not in oa.BUFFER_KEYS]
@@ -93,7 +94,7 @@ class CpuTrainStep:
             self.sd[n].grad = None
         outs = oa.forward_training(self.sd, self.cfg, batch["phoneme_indices"], batch["mel_specs"],
                                    batch["phoneme_durations"], batch["pitches"], batch["energies"],
-                                   batch["stress_indices"])
+                                   batch["stress_indices"], drop=self.drop)
         losses = oa.training_losses(self.cfg, outs, batch["mel_specs"], batch["phoneme_durations"],
                                     batch["stop_token_targets"], batch["pitches"], batch["energies"],
                                     batch["mel_lengths"], batch["phoneme_lengths"])

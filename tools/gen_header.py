@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 DOCS = {
     "kr_last_error": "Thread-local message of the last failing call (every entry point returns 0 or a negative KR_ERR_* code; the Python side maps non-zero to RuntimeError, which the reference trainer's per-batch handler expects: training/trainer.py:2679-2686).",
-    "kr_abi_version": "ABI version of this header (1).",
+    "kr_abi_version": "ABI version of this header (2: dropout specs).",
     "kr_launch_count": "Number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches evidence).",
     "kr_memset_zero": "Asynchronous zero fill (memset node under graph capture) — replaces the torch fill kernels for gradient / scratch buffers.",
     "kr_device_cc": "Compute capability (major*10+minor) of the current device; 100 on B200.",
@@ -59,10 +59,29 @@ DOCS = {
     "kr_gn_bwd": "Backward of kr_gn_fwd (ReLU mask recomputed), dgamma/dbeta accumulated.",
     "kr_vp_head_fwd": "Predictor head Linear(F->1) + masked_fill(mask, 0); a chunk of length 1 yields zeros, model/variance_predictor.py:95-115.",
     "kr_vp_head_bwd": "Backward of kr_vp_head_fwd.",
+    "kr_drop_begin": "Once per training forward: state[1] += 1 (new dropout step) and table[s, b] = stochastic-depth factor of residual branch s for sample b (0 with probability path_p[s], else 1/(1-p)): drop_path of model/transformers.py:16-40 with the per-layer rates of model/model.py:99-107.",
+    "kr_dec_in_drop": "Decoder input y = drop_b(drop_a(t) + PE[row % T]) for t = mel_projection_in(shifted mel): F.dropout(p = decoder_input_dropout) then PositionalEncoding's own dropout, model/model.py:525-531, model/positional_encoding.py:72-74. scale_a = 1/keep_a; drop->scale = 1/(keep_a*keep_b).",
+    "kr_drop_export_mask": "Test aid: out[r*cols + c] = keep(element r*ld + c) of one dropout site as bytes, so a CPU oracle can apply exactly the masks the fused kernels regenerate.",
     "kr_conv_dgrad_shadow": "bf16 tap-reversed transpose of a tap-major conv weight: the B operand of the conv data-gradient GEMM.",
 }
 
-STRUCTS = """/* Argument block of kr_gemm_ex (plain C, zero-initialise then fill what you need). */
+STRUCTS = """/* Dropout / stochastic-depth descriptor of ONE site (HOST struct, passed by pointer; NULL or
+ * state == NULL = disabled).  The keep decision of element e is a pure function of
+ * (state[0] = seed, state[1] = step, site, e): keep iff lane16(hash(e >> 1, key(seed, step, site)), e & 1) >= thr
+ * with thr = round(p * 65536), so backward kernels regenerate the mask instead of storing it
+ * (kr_common.cuh).  Kept elements are multiplied by `scale` (1 / keep probability, product over
+ * both masks) and, when row_scale != NULL, by row_scale[row / rows_per_sample] — the per-sample
+ * stochastic-depth factor (0 or 1 / (1 - p_path)) written by kr_drop_begin. */
+typedef struct kr_drop_spec {
+  const unsigned long long* state;   /* device {seed, step} */
+  unsigned int site_a, thr_a;        /* first mask (thr_a == 0: none) */
+  unsigned int site_b, thr_b;        /* optional second, independent mask (thr_b == 0: none) */
+  float scale;
+  const float* row_scale;            /* device [n_samples] or NULL */
+  int rows_per_sample;
+} kr_drop_spec;
+
+/* Argument block of kr_gemm_ex (plain C, zero-initialise then fill what you need). */
 typedef struct kr_gemm_args {
   const void* A;            /* bf16; logical [M,K]: stored [M,K] (K-major) or [K,M] if a_mn_major */
   const void* B;            /* bf16; logical [N,K]: stored [N,K] (K-major) or [K,N] if b_mn_major */
@@ -83,6 +102,9 @@ typedef struct kr_gemm_args {
   int splits;               /* split-K (c_mode 2 only) */
   int force_block_n;        /* 0 = heuristic, else 64 / 128 / 192 / 256 */
   int no_slab;              /* 1 = conv mode re-fetches every tap (debug / A-B comparison) */
+  /* dropout on the GEMM result BEFORE the residual adds: v = drop(alpha*acc + bias) + resid ...; element index
+   * m * N + n (single batch only).  transformers.py:482-483,569,578 (dropout(drop_path(attn_out)) + residual) */
+  const kr_drop_spec* drop;
 } kr_gemm_args;
 """
 
