@@ -133,10 +133,13 @@ def adaptive_stabilisation(T: int, max_dur: int, base_clip: float, frame_thr: fl
 class _Staged:
     """Static device buffers + graph for one batch shape."""
     dev: Dict[str, torch.Tensor]
-    graph: Optional[torch.cuda.CUDAGraph] = None
+    # one graph per variant: index 1 = zero the gradient buffer first (start of an accumulation window),
+    # index 0 = accumulate onto it
+    graph: List[Optional[torch.cuda.CUDAGraph]] = field(default_factory=lambda: [None, None])
+    graph_losses: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
     losses: Optional[torch.Tensor] = None
     launches: int = 0
-    warm: int = 0
+    warm: List[int] = field(default_factory=lambda: [0, 0])
     last_used: int = 0
 
 
@@ -204,8 +207,9 @@ class TrainStep:
             out["phoneme_lengths"] = batch["phoneme_lengths"].clamp(max=cap)
         return out
 
-    def stage(self, batch: Dict[str, torch.Tensor]) -> Tuple[_Staged, Tuple[int, int, int, int]]:
-        """Host-side prologue: shape key, stabiliser scalars, async H2D into the static buffers."""
+    def stage(self, batch: Dict[str, torch.Tensor], divisor: int = 1) -> Tuple[_Staged, Tuple[int, int, int, int]]:
+        """Host-side prologue: shape key, stabiliser scalars, async H2D into the static buffers.
+        divisor = the accumulation divisor of this micro-batch (trainer.py:2284-2294)."""
         batch = self._cap(batch)
         for k in BATCH_KEYS:
             if k not in batch:
@@ -245,16 +249,17 @@ class TrainStep:
         scale, clip = adaptive_stabilisation(T, max_d, self.opt.cfg.max_grad_norm)
         slot = self._scal_ring[self._scal_i % self._scal_ring.shape[0]]
         self._scal_i += 1
-        slot[0] = scale / self.world
+        slot[0] = scale / (self.world * max(1, divisor))
         slot[1] = clip
         self._scal_dev.copy_(slot, non_blocking=True)
         self.h2d_bytes_last_step = nbytes + 8
         return st, key
 
     # ------------------------------------------------------------------------------------------
-    def _fwd_bwd(self, d: Dict[str, torch.Tensor], Tp: int) -> torch.Tensor:
+    def _fwd_bwd(self, d: Dict[str, torch.Tensor], Tp: int, zero: bool = True) -> torch.Tensor:
         eng = self.engine
-        eng.zero_grad()
+        if zero:                                  # optimizer.zero_grad() at the start of a window, trainer.py:2258-2259
+            eng.zero_grad()
         outs, ctx = eng.forward(d["phoneme_indices"], d["mel_specs"], d["phoneme_durations"], d["pitches"],
                                 d["energies"], d["stress_indices"], expanded_len=Tp)
         losses, g = eng.losses(outs, d["mel_specs"], d["phoneme_durations"], d["stop_token_targets"],
@@ -263,26 +268,28 @@ class TrainStep:
         eng.backward(ctx, g)
         return losses
 
-    def _run_fwd_bwd(self, st: _Staged, key) -> torch.Tensor:
+    def _run_fwd_bwd(self, st: _Staged, key, zero: bool = True) -> torch.Tensor:
         Tp = key[3]
+        v = int(zero)
         if not self.use_graphs:
             n0 = launch_count()
-            losses = self._fwd_bwd(st.dev, Tp)
+            losses = self._fwd_bwd(st.dev, Tp, zero)
             st.launches = launch_count() - n0
             return losses
-        if st.graph is None:
-            if st.warm < 1:                       # eager warm-up (builds geometry tables, sets func attrs)
-                st.warm += 1
+        if st.graph[v] is None:
+            if st.warm[v] < 1:                    # eager warm-up (builds geometry tables, sets func attrs)
+                st.warm[v] += 1
                 n0 = launch_count()
-                losses = self._fwd_bwd(st.dev, Tp)
+                losses = self._fwd_bwd(st.dev, Tp, zero)
                 st.launches = launch_count() - n0
                 return losses
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                st.losses = self._fwd_bwd(st.dev, Tp)
-            st.graph = g
-        st.graph.replay()
+                st.graph_losses[v] = self._fwd_bwd(st.dev, Tp, zero)
+            st.graph[v] = g
+        st.graph[v].replay()
+        st.losses = st.graph_losses[v]
         return st.losses
 
     def _run_optimizer(self) -> None:
@@ -301,16 +308,36 @@ class TrainStep:
         self._opt_graph.replay()
 
     # ------------------------------------------------------------------------------------------
-    def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
-        """Full optimizer step on one micro-batch.  Returns the device tensor
+    def micro_step(self, batch: Dict[str, torch.Tensor], first: bool = True, last: bool = True,
+                   divisor: int = 1) -> torch.Tensor:
+        """One micro-batch of a gradient-accumulation window (reference trainer.py:2258-2294, 2341-2343):
+        `first` zeroes the gradient buffer, the loss is scaled by adaptive_scale / divisor, and `last` closes the
+        window: one all-reduce (world > 1), pre-clip / clip (with THIS micro-batch's adaptive clip, as the
+        reference does), AdamW, scheduler, EMA, projection.  Returns the device tensor
         losses[6] = (total, mel, duration, stop, pitch, energy), un-scaled."""
-        st, key = self.stage(batch)
-        self.opt.set_lrs(self.sched.lrs())
-        losses = self._run_fwd_bwd(st, key)
-        if self.world > 1:
-            from .parallel import all_reduce_gradients
-            all_reduce_gradients(self.engine.store.grads, self.pg)
-        self._run_optimizer()
-        self.sched.advance()
-        self.launches_last_step = st.launches + self._opt_launches + (1 if self.world > 1 else 0)
+        st, key = self.stage(batch, divisor)
+        if last:
+            self.opt.set_lrs(self.sched.lrs())
+        losses = self._run_fwd_bwd(st, key, zero=first)
+        self.launches_last_step = st.launches
+        if last:
+            if self.world > 1:
+                from .parallel import all_reduce_gradients
+                all_reduce_gradients(self.engine.store.grads, self.pg)
+            self._run_optimizer()
+            self.sched.advance()
+            self.launches_last_step += self._opt_launches + (1 if self.world > 1 else 0)
         return losses
+
+    def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Full optimizer step on one micro-batch (gradient_accumulation_steps = 1)."""
+        return self.micro_step(batch, True, True, 1)
+
+    def train_window(self, batches: List[Dict[str, torch.Tensor]]) -> List[torch.Tensor]:
+        """One optimizer step over an accumulation window of len(batches) micro-batches; the divisor is the
+        window length (= min(G, remaining) of trainer.py:3345-3362 when the caller cuts the windows)."""
+        n = len(batches)
+        out = []
+        for i, b in enumerate(batches):
+            out.append(self.micro_step(b, first=(i == 0), last=(i == n - 1), divisor=n).clone())
+        return out

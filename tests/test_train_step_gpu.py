@@ -77,3 +77,53 @@ def test_adaptive_long_sequence_scalars_reach_device():
     assert abs(scale - 1400 / 1600) < 1e-6 and abs(clip - 0.5 / (1600 / 1400) ** 0.5) < 1e-6
     assert abs(float(ts.loss_scale.cpu()) - scale) < 1e-6
     assert abs(ts.opt.read_ctrl()["clip_used"] - clip) < 1e-6
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_gradient_accumulation_window_matches_cpu_oracle(graphs):
+    """gradient_accumulation_steps = 2 (the reference default, training/config.py): zero_grad at the window
+    start, each micro-batch's loss scaled by 1/divisor, ONE optimizer step at the window end
+    (trainer.py:2258-2294, 2341-2343).  Two different batch shapes per window (two graph variants each)."""
+    from oracle import acoustic as oa
+    from oracle.train_step import CpuTrainStep
+    from kokoro_ruslan_b200.optim import OptimConfig
+    from kokoro_ruslan_b200.train_step import ScheduleConfig, TrainStep
+    ocfg, cfg = _tiny()
+    sd = oa.seeded_state_dict(ocfg, seed=0)
+    b0 = oa.synthetic_batch(B=3, P=24, T=150, seed=11, ragged=True)
+    b1 = oa.synthetic_batch(B=2, P=32, T=130, seed=12, ragged=True)
+    lr = 1e-3
+    ts = TrainStep(cfg, OptimConfig(learning_rate=lr, ema_decay=0.9),
+                   ScheduleConfig(total_steps=1000, use_warmup=False, pct_start=0.5), device="cuda", use_graphs=graphs)
+    ts.load_state_dict(sd)
+    ref = CpuTrainStep(ocfg, sd, lr=lr, ema_decay=0.9)
+    n_windows = 3
+    for k in range(n_windows):
+        ref.set_lr(ts.sched.lrs()[2])
+        want = []
+        for i, b in enumerate((b0, b1)):
+            # CpuTrainStep.fwd_bwd clears .grad: accumulate by hand like autograd would
+            saved = {n: (ref.sd[n].grad.clone() if ref.sd[n].grad is not None else None) for n in ref.names} if i else None
+            _, losses = ref.fwd_bwd(b, loss_scale=0.5)
+            if saved is not None:
+                for n in ref.names:
+                    if saved[n] is not None:
+                        ref.sd[n].grad = saved[n] if ref.sd[n].grad is None else ref.sd[n].grad + saved[n]
+            want.append([float(x.detach()) for x in losses])
+        ref.optimizer_step()
+        got = [l.cpu().tolist() for l in ts.train_window([b0, b1])]
+        for gw, ww in zip(got, want):
+            for g, w in zip(gw, ww):
+                assert abs(g - w) <= 1e-2 * abs(w) + 1e-4, (k, got, want)
+    torch.cuda.synchronize()
+    ctrl = ts.opt.read_ctrl()
+    assert ctrl["step"] == n_windows and ctrl["skip"] == 0
+    assert ts.sched.current_optimizer_step == n_windows
+    num = den = 0.0
+    mine = ts.store.state_dict()
+    for n in ts.store.order:
+        d_ref = ref.sd[n].detach() - sd[n]
+        d_got = mine[n].float().cpu() - sd[n]
+        num += float((d_got - d_ref).pow(2).sum())
+        den += float(d_ref.pow(2).sum())
+    assert (num / den) ** 0.5 < 0.15, (num / den) ** 0.5
