@@ -405,6 +405,9 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "params": 49432276,
                        "precision": "bf16 tcgen05 GEMM/attention operands, fp32 accumulate/residual/optimizer",
                        "dropout": DROPOUT_DESC[args.dropout], "grad_accum": 1, "parallelism": f"dp{world}",
+                       "comm": (None if world == 1 else ("fused all-reduce + grad-norm kernel over symmetric memory (%s)" %
+                                                         ("NVSwitch multicast" if ts.reducer.multicast else "peer loads/stores")
+                                                         if ts.reducer is not None else "NCCL all-reduce")),
                        "l2": "no flush: a step streams >1 GB of weights/optimizer state/activations (> 126 MB L2)",
                        "cuda_graphs": True},
             "roofline": roof, "cpu_baseline": cpu,

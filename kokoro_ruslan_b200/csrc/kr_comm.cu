@@ -1,0 +1,217 @@
+// kr_comm.cu — the data-parallel collective of a training step, fused with the first phase of the optimizer:
+// ONE kernel all-reduces the flat fp32 gradient buffer over NVLink 5 / NVSwitch peer memory AND produces the
+// per-chunk squared gradient norms the step control needs (the reference has no data-parallel path; this
+// replaces "NCCL all-reduce, then kr_grad_sqnorm re-reads 198 MB": SURVEY.md 8(e), trainer.py:2355-2362).
+//
+// The gradient buffer of every rank lives in symmetric memory (same virtual layout on all ranks, peers mapped,
+// plus an NVSwitch MULTICAST mapping when the fabric supports it).  4096-element chunk c — the optimizer's own
+// chunk table, chunks never straddle tensors — is owned by rank c % world.  The owner
+//   * multicast path: `multimem.ld_reduce.add.v4.f32` — the SWITCH sums the chunk over all ranks and returns it
+//     once (one pass of link traffic instead of a ring's two), `multimem.st.v4.f32` broadcasts the sum back;
+//   * peer path (no multicast): 16-byte loads from every rank in rank order, stores to every rank;
+//   * squares and sums what it just reduced (the data is in registers) and broadcasts the chunk's sum.
+// Every element is reduced exactly once and then replicated, and the per-tensor norms are later summed from the
+// chunk sums in a fixed order, so all replicas see bit-identical gradients and norms (NCCL + atomics gave
+// neither guarantee for the norms) and take identical clip / skip decisions without further communication.
+// Cross-GPU ordering: a per-block flag barrier (system-scope release / acquire CAS on flags in symmetric
+// memory) before the first load — the peer's backward has finished — and after the last store.
+#include "kr_common.cuh"
+
+namespace {
+using namespace kr;
+
+constexpr int MAX_RANKS = 8;
+constexpr int AR_THREADS = 256;
+
+struct ArParams {
+  float* mc;                      // multicast address of the gradient buffer, or nullptr
+  float* sq_mc;                   // multicast address of the per-chunk squared-sum buffer, or nullptr
+  float* grads[MAX_RANKS];        // every rank's gradient buffer (peer mappings)
+  float* sq[MAX_RANKS];           // every rank's per-chunk squared-sum buffer
+  unsigned* flags[MAX_RANKS];     // every rank's barrier flags [grid][world]
+  const long long* chunk_start;
+  const int* chunk_len;
+  int n_chunks, rank, world;
+};
+
+__device__ __forceinline__ float4 multimem_ld_reduce_f32x4(const float* addr) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f32x4(float* addr, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st_f32(float* addr, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_sys_f32x4(const float* addr) {      // peer memory: never through L1
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned cas_release_sys(unsigned* addr, unsigned cmp, unsigned val) {
+  unsigned old;
+  asm volatile("atom.release.sys.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned cas_acquire_sys(unsigned* addr, unsigned cmp, unsigned val) {
+  unsigned old;
+  asm volatile("atom.acquire.sys.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+
+// Block b of every rank meets block b of every other rank.  Slot [b][src] of rank dst's flags is raised by
+// rank src (0 -> 1) and lowered by rank dst (1 -> 0), so the flags are back at zero afterwards.  A watchdog
+// traps instead of hanging the box if a peer never arrives.
+__device__ __forceinline__ void cross_gpu_barrier(const ArParams& p) {
+  __syncthreads();
+  if ((int)threadIdx.x < p.world) {
+    const int q = threadIdx.x;
+    unsigned* put = p.flags[q] + (size_t)blockIdx.x * p.world + p.rank;
+    unsigned* wait = p.flags[p.rank] + (size_t)blockIdx.x * p.world + q;
+    const long long t0 = clock64();
+    while (cas_release_sys(put, 0u, 1u) != 0u) {
+      if (clock64() - t0 > 8000000000LL) { printf("kr_comm: barrier put watchdog (rank %d block %d)\n", p.rank, blockIdx.x); __trap(); }
+    }
+    while (cas_acquire_sys(wait, 1u, 0u) != 1u) {
+      if (clock64() - t0 > 8000000000LL) { printf("kr_comm: barrier wait watchdog (rank %d block %d)\n", p.rank, blockIdx.x); __trap(); }
+    }
+  }
+  __syncthreads();
+}
+
+// loads of one chunk: all issued before the first use (NVLink / switch latency: keep the link full)
+__device__ __forceinline__ void ar_load_chunk(const ArParams& p, int c, float4 (&v)[4]) {
+  const long long off = p.chunk_start[c];
+  const int n4 = (p.chunk_len[c] + 3) >> 2;      // tensors are 64-element aligned and zero padded: whole float4s are safe
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.x + k * AR_THREADS;
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+      if (p.mc != nullptr) {
+        v[k] = multimem_ld_reduce_f32x4(p.mc + off + 4 * i);
+      } else {
+        for (int q = 0; q < p.world; ++q) {
+          const float4 t = ld_sys_f32x4(p.grads[q] + off + 4 * i);
+          v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AR_THREADS) allreduce_sqnorm_kernel(const ArParams p) {
+  __shared__ float red[32];
+  cross_gpu_barrier(p);                          // every rank's gradients are final
+  const int stride = p.world * (int)gridDim.x;
+  int c = p.rank + p.world * (int)blockIdx.x;
+  float4 v[4], vn[4];
+  if (c < p.n_chunks) ar_load_chunk(p, c, vn);
+  for (; c < p.n_chunks; c += stride) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = vn[k];
+    if (c + stride < p.n_chunks) ar_load_chunk(p, c + stride, vn);   // next chunk's loads fly under this chunk's stores
+    const long long off = p.chunk_start[c];
+    const int n4 = (p.chunk_len[c] + 3) >> 2;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = threadIdx.x + k * AR_THREADS;
+      if (i < n4) {
+        s += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+        if (p.mc != nullptr) {
+          multimem_st_f32x4(p.mc + off + 4 * i, v[k]);
+        } else {
+          for (int q = 0; q < p.world; ++q) *reinterpret_cast<float4*>(p.grads[q] + off + 4 * i) = v[k];
+        }
+      }
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) {
+      if (p.sq_mc != nullptr) {
+        multimem_st_f32(p.sq_mc + c, s);
+      } else {
+        for (int q = 0; q < p.world; ++q) p.sq[q][c] = s;
+      }
+    }
+  }
+  __threadfence_system();
+  cross_gpu_barrier(p);                          // every rank's stores have landed everywhere
+}
+
+// single-GPU / after-NCCL variant of the same first optimizer phase: per-chunk squared sums, no atomics
+__global__ void __launch_bounds__(AR_THREADS) chunk_sqnorm_kernel(const float* __restrict__ g,
+                                                                 const long long* __restrict__ chunk_start,
+                                                                 const int* __restrict__ chunk_len,
+                                                                 float* __restrict__ sq_chunk) {
+  kr::pdl_entry();
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const float* p = g + chunk_start[c];
+  const int n4 = (chunk_len[c] + 3) >> 2;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(p + 4 * i);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) sq_chunk[c] = s;
+}
+
+// sq[t] = sum of the chunk sums of tensor t, in chunk order (deterministic, identical on every replica);
+// a non-finite sum raises the control block's non-finite flag (word `nonfinite_word`).
+__global__ void chunk_to_tensor_kernel(const float* __restrict__ sq_chunk, const int* __restrict__ first_chunk,
+                                       float* __restrict__ sq, int n_tensors, int* ctrl_nonfinite) {
+  kr::pdl_entry();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tensors) return;
+  float s = 0.f;
+  for (int c = first_chunk[t]; c < first_chunk[t + 1]; ++c) s += sq_chunk[c];
+  sq[t] = s;
+  if (!isfinite(s)) atomicExch(ctrl_nonfinite, 1);
+}
+
+}  // namespace
+
+extern "C" int kr_allreduce_sqnorm(void* mc_grads, void* mc_sq, void* const* grads, void* const* sq,
+                                   void* const* flags, int rank, int world, const long long* chunk_start,
+                                   const int* chunk_len, int n_chunks, int grid, void* stream) {
+  if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world) { kr_set_error("kr_allreduce_sqnorm: world must be 1..8"); return KR_ERR_ARG; }
+  if (grid < 1 || n_chunks <= 0) { kr_set_error("kr_allreduce_sqnorm: empty problem"); return KR_ERR_ARG; }
+  ArParams p{};
+  p.mc = reinterpret_cast<float*>(mc_grads);
+  p.sq_mc = reinterpret_cast<float*>(mc_sq);
+  for (int q = 0; q < world; ++q) {
+    p.grads[q] = reinterpret_cast<float*>(grads[q]);
+    p.sq[q] = reinterpret_cast<float*>(sq[q]);
+    p.flags[q] = reinterpret_cast<unsigned*>(flags[q]);
+  }
+  p.chunk_start = chunk_start; p.chunk_len = chunk_len; p.n_chunks = n_chunks; p.rank = rank; p.world = world;
+  // plain launch: every block spins on its peers, so the whole grid must not depend on a later grid
+  allreduce_sqnorm_kernel<<<grid, AR_THREADS, 0, (cudaStream_t)stream>>>(p);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+extern "C" int kr_chunk_sqnorm(const float* grads, const long long* chunk_start, const int* chunk_len, int n_chunks,
+                               float* sq_chunk, void* stream) {
+  if (n_chunks <= 0) return KR_OK;
+  kr::launch(chunk_sqnorm_kernel, n_chunks, AR_THREADS, 0, (cudaStream_t)stream, grads, chunk_start, chunk_len, sq_chunk);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+extern "C" int kr_chunk_to_tensor_sq(const float* sq_chunk, const int* first_chunk, float* sq, int n_tensors,
+                                     void* ctrl, void* stream) {
+  if (n_tensors <= 0) return KR_OK;
+  int* nonfinite = reinterpret_cast<int*>(ctrl) + 10;      // Ctrl::nonfinite (kr_optim.cu)
+  kr::launch(chunk_to_tensor_kernel, (n_tensors + 127) / 128, 128, 0, (cudaStream_t)stream, sq_chunk, first_chunk, sq,
+             n_tensors, nonfinite);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}

@@ -643,6 +643,22 @@ class AcousticEngine:
     # backward: accumulates into store.grads
     # ------------------------------------------------------------------------------------------
     def backward(self, ctx: dict, g: dict):
+        for _ in self.backward_parts(ctx, g, None):
+            pass
+
+    def early_grad_ranges(self, split_layer: int) -> List[Tuple[int, int]]:
+        """Element ranges of the flat gradient buffer that are FINAL when backward_parts(…, split_layer) yields:
+        embeddings + encoder + predictors (front of the buffer) and decoder layers >= split_layer + heads (tail).
+        The complement — pitch / energy embeddings, mel_projection_in, decoder layers < split_layer — is one range."""
+        st = self.store
+        a = st.entries["duration_adaptor.variance_adaptor.pitch_embedding.weight"].offset
+        b = st.entries[f"decoder.layers.{split_layer}.self_attn.w_q.weight"].offset
+        return [(0, a), (b, st.total)]
+
+    def backward_parts(self, ctx: dict, g: dict, split_layer: Optional[int]):
+        """Backward as a generator that yields ONCE (when split_layer is not None), after the encoder, the
+        predictors, the heads and decoder layers n-1 .. split_layer are done and every side stream has been
+        joined: the data-parallel step all-reduces early_grad_ranges() underneath the rest of the backward."""
         cfg, st, D = self.cfg, self.store, self.D
         B, P, T, Tp = ctx["B"], ctx["P"], ctx["T"], ctx["Tp"]
         Ne, Nd = B * P, B * T
@@ -694,6 +710,9 @@ class AcousticEngine:
             # layer 0: the bf16 copy feeds mel_projection_in's weight gradient through both input dropouts
             dy, dy_bf = self._attn_bwd(pre + "self_attn.", dy, dy_bf, B, T, pre + "norm1.", True, None, None, T,
                                        s1, None, False, next_drop=ctx["drop_in"] if i == 0 else None)
+            if split_layer is not None and i == split_layer and i > 0:
+                self._join_all()
+                yield
         self._wgrad(dy_bf, ctx["melshift"], st.g("mel_projection_in.weight"), st.g("mel_projection_in.bias"))
         self._join_all()
         # memory gradient (accumulated on the "kv" stream) reaches only the pitch / energy embedding rows

@@ -153,6 +153,15 @@ class FusedAdamW:
         self.n_chunks = len(chunk_tensor)
         self.t_preclip = torch.tensor([preclip_of(n, self.cfg) for n in names], dtype=torch.float32, device=dev)
         self.t_wnmax = torch.tensor(t_wn, dtype=torch.float32, device=dev)
+        first_chunk = [0] * (self.n_tensors + 1)
+        for ti in chunk_tensor:
+            first_chunk[ti + 1] += 1
+        for ti in range(self.n_tensors):
+            first_chunk[ti + 1] += first_chunk[ti]
+        self.first_chunk = torch.tensor(first_chunk, **i32)
+        # per-chunk squared gradient sums: written by kr_chunk_sqnorm, or — data parallel — by the fused
+        # all-reduce kernel, in which case the buffer lives in symmetric memory (parallel.SymmetricGradReducer)
+        self.sq_chunk = torch.zeros(self.n_chunks, dtype=torch.float32, device=dev)
         self.sq = torch.zeros(self.n_tensors, dtype=torch.float32, device=dev)
         self.wsq = torch.zeros(self.n_tensors, dtype=torch.float32, device=dev)
         self.tscale = torch.ones(self.n_tensors, dtype=torch.float32, device=dev)
@@ -177,15 +186,19 @@ class FusedAdamW:
     def set_base_lr(self, base_lr: float) -> None:
         self.set_lrs([base_lr * m for m in self.lr_mult])
 
-    def step(self, clip_norm: Optional[float] = None, clip_override: Optional[torch.Tensor] = None) -> None:
-        """One optimizer step on store.grads (already all-reduced when data-parallel)."""
+    def step(self, clip_norm: Optional[float] = None, clip_override: Optional[torch.Tensor] = None,
+             sq_chunk_ready: bool = False) -> None:
+        """One optimizer step on store.grads (already all-reduced when data-parallel).  sq_chunk_ready: the
+        per-chunk squared sums were already produced by the fused all-reduce kernel."""
         c, s = self.cfg, self.store
         L = lib()
         from .ops import zero_
-        zero_(self.sq)
         zero_(self.wsq)
-        check(L.kr_grad_sqnorm(_ptr(s.grads), _ptr(self.chunk_tensor), _ptr(self.chunk_start), _ptr(self.chunk_len),
-                               c_int(self.n_chunks), _ptr(self.sq), _ptr(self.ctrl), _stream()), "kr_grad_sqnorm")
+        if not sq_chunk_ready:
+            check(L.kr_chunk_sqnorm(_ptr(s.grads), _ptr(self.chunk_start), _ptr(self.chunk_len), c_int(self.n_chunks),
+                                    _ptr(self.sq_chunk), _stream()), "kr_chunk_sqnorm")
+        check(L.kr_chunk_to_tensor_sq(_ptr(self.sq_chunk), _ptr(self.first_chunk), _ptr(self.sq), c_int(self.n_tensors),
+                                      _ptr(self.ctrl), _stream()), "kr_chunk_to_tensor_sq")
         check(L.kr_step_control(_ptr(self.sq), _ptr(self.t_preclip), _ptr(self.tscale), c_int(self.n_tensors),
                                 _ptr(self.ctrl), c_float(clip_norm if clip_norm is not None else c.max_grad_norm),
                                 _ptr(clip_override), c_float(c.adam_betas[0]), c_float(c.adam_betas[1]),

@@ -7,7 +7,9 @@ scheduler) around the CUDA engine:
 
     host batch (pinned) --H2D--> static device buffers
       -> [CUDA graph A]  zero_grad, forward, fused losses (+ grads of the outputs), backward
-      -> [NCCL]          one all-reduce(SUM) of the flat gradient buffer      (world_size > 1 only)
+      -> [NCCL]          all-reduce(SUM) of the flat gradient buffer (world_size > 1 only): the ranges that
+                         are final after the upper half of the decoder backward are reduced underneath the
+                         lower half (graph A is cut in two there), the remainder right after it
       -> [CUDA graph B]  grad norms -> step control -> fused clip+AdamW+EMA -> weight-norm projection
       -> losses[6] stay on the device; the caller decides when to read them.
 
@@ -20,6 +22,7 @@ captured.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -136,6 +139,7 @@ class _Staged:
     # one graph per variant: index 1 = zero the gradient buffer first (start of an accumulation window),
     # index 0 = accumulate onto it
     graph: List[Optional[torch.cuda.CUDAGraph]] = field(default_factory=lambda: [None, None])
+    graph_tail: List[Optional[torch.cuda.CUDAGraph]] = field(default_factory=lambda: [None, None])
     graph_losses: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
     losses: Optional[torch.Tensor] = None
     launches: int = 0
@@ -159,6 +163,24 @@ class TrainStep:
         if process_group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
+        # data parallel: the backward is cut after decoder layer `split_layer` so that the all-reduce of everything
+        # that is final by then (~73 % of the gradient bytes) runs on NCCL's stream underneath the rest of it
+        n_dec = self.engine.cfg.n_decoder_layers
+        self.split_layer: Optional[int] = n_dec // 2 if (self.world > 1 and n_dec >= 2) else None
+        if os.environ.get("KR_DP_SPLIT", "0") == "0":   # measured on 2 x B200: NCCL's CTAs steal SMs from the persistent
+            # GEMM grids of the backward tail and the overlap loses more than it hides (8.40 vs 8.29 ms/step)
+            self.split_layer = None
+        self._pending: List = []
+        # the collective: "fused" = one hand-written kernel over NVSwitch peer / multicast memory that also
+        # produces the optimizer's gradient norms (parallel.SymmetricGradReducer); "nccl" = torch.distributed
+        self.reducer = None
+        self.comm = "none"
+        if self.world > 1:
+            self.comm = os.environ.get("KR_COMM", "fused")
+            if self.comm == "fused":
+                from .parallel import SymmetricGradReducer
+                self.reducer = SymmetricGradReducer(self.engine.store, self.opt, process_group)
+                self.split_layer = None           # nothing to overlap: the kernel needs the whole buffer
         self.max_seq_cap = max_seq_cap
         # every cached batch shape pins its static input buffers and (once captured) a graph with ~4 GB of
         # activations at the bench shape: dynamic batching produces many shapes, so the cache is LRU-bounded
@@ -256,7 +278,8 @@ class TrainStep:
         return st, key
 
     # ------------------------------------------------------------------------------------------
-    def _fwd_bwd(self, d: Dict[str, torch.Tensor], Tp: int, zero: bool = True) -> torch.Tensor:
+    def _fwd_bwd_parts(self, d: Dict[str, torch.Tensor], Tp: int, zero: bool, out: list):
+        """Generator over the (at most two) parts of zero-grad + forward + losses + backward; out[0] = losses."""
         eng = self.engine
         if zero:                                  # optimizer.zero_grad() at the start of a window, trainer.py:2258-2259
             eng.zero_grad()
@@ -265,45 +288,89 @@ class TrainStep:
         losses, g = eng.losses(outs, d["mel_specs"], d["phoneme_durations"], d["stop_token_targets"],
                                d["pitches"], d["energies"], d["mel_lengths"], d["phoneme_lengths"],
                                loss_scale=self.loss_scale)
-        eng.backward(ctx, g)
-        return losses
+        out.append(losses)
+        yield from eng.backward_parts(ctx, g, self.split_layer)
 
-    def _run_fwd_bwd(self, st: _Staged, key, zero: bool = True) -> torch.Tensor:
+    def _fwd_bwd(self, d: Dict[str, torch.Tensor], Tp: int, zero: bool = True, reduce_early: bool = False) -> torch.Tensor:
+        out: list = []
+        for _ in self._fwd_bwd_parts(d, Tp, zero, out):
+            if reduce_early:
+                self._reduce_early()
+        return out[0]
+
+    def _reduce_early(self) -> None:
+        """Async all-reduce of the gradient ranges that are final at the backward split (NCCL's own stream waits
+        for the work enqueued so far and then runs underneath what follows)."""
+        import torch.distributed as dist
+        grads = self.engine.store.grads
+        for a, b in self.engine.early_grad_ranges(self.split_layer):
+            self._pending.append(dist.all_reduce(grads[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def _reduce_rest(self) -> None:
+        import torch.distributed as dist
+        grads = self.engine.store.grads
+        if self.split_layer is None:
+            dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=self.pg)
+            return
+        (_, a), (b, _) = self.engine.early_grad_ranges(self.split_layer)
+        self._pending.append(dist.all_reduce(grads[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        for w in self._pending:
+            w.wait()                               # stream-level wait: no host synchronisation
+        self._pending = []
+
+    def _run_fwd_bwd(self, st: _Staged, key, zero: bool = True, reduce_early: bool = False) -> torch.Tensor:
+        """reduce_early (data parallel, closing micro-batch of a window): launch the all-reduce of the early
+        gradient ranges at the backward split.  With graphs the step is TWO graphs sharing one memory pool
+        (head: zero-grad, forward, losses, backward down to the split; tail: the rest)."""
         Tp = key[3]
         v = int(zero)
+        split = self.split_layer is not None
         if not self.use_graphs:
             n0 = launch_count()
-            losses = self._fwd_bwd(st.dev, Tp, zero)
+            losses = self._fwd_bwd(st.dev, Tp, zero, reduce_early)
             st.launches = launch_count() - n0
             return losses
         if st.graph[v] is None:
             if st.warm[v] < 1:                    # eager warm-up (builds geometry tables, sets func attrs)
                 st.warm[v] += 1
                 n0 = launch_count()
-                losses = self._fwd_bwd(st.dev, Tp, zero)
+                losses = self._fwd_bwd(st.dev, Tp, zero, reduce_early)
                 st.launches = launch_count() - n0
                 return losses
             torch.cuda.synchronize(self.device)
+            out: list = []
+            parts = self._fwd_bwd_parts(st.dev, Tp, zero, out)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                st.graph_losses[v] = self._fwd_bwd(st.dev, Tp, zero)
+                more = next(parts, "done") != "done"
             st.graph[v] = g
+            if more:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=g.pool()):
+                    assert next(parts, "done") == "done"
+                st.graph_tail[v] = g2
+            st.graph_losses[v] = out[0]
         st.graph[v].replay()
+        if split and st.graph_tail[v] is not None:
+            if reduce_early:
+                self._reduce_early()
+            st.graph_tail[v].replay()
         st.losses = st.graph_losses[v]
         return st.losses
 
     def _run_optimizer(self) -> None:
+        fused = self.reducer is not None and self.world > 1
         if not self.use_graphs or (self._opt_graph is None and self._opt_warm < 1):
             self._opt_warm += 1
             n0 = launch_count()
-            self.opt.step(clip_override=self.clip)
+            self.opt.step(clip_override=self.clip, sq_chunk_ready=fused)
             self._opt_launches = launch_count() - n0
             return
         if self._opt_graph is None:
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.opt.step(clip_override=self.clip)
+                self.opt.step(clip_override=self.clip, sq_chunk_ready=fused)
             self._opt_graph = g
         self._opt_graph.replay()
 
@@ -318,12 +385,15 @@ class TrainStep:
         st, key = self.stage(batch, divisor)
         if last:
             self.opt.set_lrs(self.sched.lrs())
-        losses = self._run_fwd_bwd(st, key, zero=first)
+        losses = self._run_fwd_bwd(st, key, zero=first, reduce_early=(last and self.world > 1 and
+                                                                      self.split_layer is not None))
         self.launches_last_step = st.launches
         if last:
             if self.world > 1:
-                from .parallel import all_reduce_gradients
-                all_reduce_gradients(self.engine.store.grads, self.pg)
+                if self.reducer is not None:
+                    self.reducer.reduce()
+                else:
+                    self._reduce_rest()
             self._run_optimizer()
             self.sched.advance()
             self.launches_last_step += self._opt_launches + (1 if self.world > 1 else 0)
