@@ -115,7 +115,7 @@ class AcousticEngine:
         if os.environ.get("KR_STREAMS", "1") == "0":
             multi_stream = False
         self.multi_stream = multi_stream
-        self._side = {k: torch.cuda.Stream(device=self.device) for k in ("w0", "w1", "vp", "enc", "kv")} if multi_stream else {}
+        self._side = {k: torch.cuda.Stream(device=self.device) for k in ("w0", "w1", "vp", "enc", "kv", "d0")} if multi_stream else {}
         self._w_rr = 0
         self._forked: List[torch.cuda.Stream] = []
         # every tensor of a step stays referenced until the next step starts: memory is never
@@ -243,6 +243,15 @@ class AcousticEngine:
         """Round-robin over the two weight-gradient streams."""
         self._w_rr ^= 1
         return self._on("w1" if self._w_rr else "w0")
+
+    def _join(self, name: str):
+        """The current stream waits for side stream `name` only."""
+        if not self.multi_stream:
+            return
+        side = self._side[name]
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        if side in self._forked:
+            self._forked.remove(side)
 
     def _join_all(self):
         cur = torch.cuda.current_stream(self.device)
@@ -477,6 +486,39 @@ class AcousticEngine:
         ops.gather_rows(dxp, geom.row_of_tok, dx)
         return dx
 
+    def _decoder_head(self, ctx: dict, mel_specs, B: int, T: int, dcfg, p_enc: float, p_dec: float):
+        """Decoder input (shift-right, mel_projection_in, dropouts, PE) and the self-attention sub-layer of decoder
+        layer 0: the only part of the decoder that does not depend on the encoder, so forward() runs it on a
+        side stream underneath the (latency-bound, 1024-token) encoder."""
+        cfg, st, D = self.cfg, self.store, self.D
+        Nd = B * T
+        mel = mel_specs.contiguous()
+        melshift = self._empty(Nd, cfg.mel_dim, dtype=BF16)
+        ops.shift_cast(mel, melshift.view(B, T, cfg.mel_dim))
+        y = self._empty(Nd, D)
+        # dropout(dropout(proj, p_in) + PE, p_enc): model.py:525-531 (the PE module is shared with the encoder)
+        ctx["drop_in"] = self._ds("dec.in", dcfg.decoder_input if dcfg else 0.0, "dec.pe", p_enc)
+        if ctx["drop_in"] is None:
+            ops.gemm(melshift, st.w("mel_projection_in.weight"), y, bias=st.p("mel_projection_in.bias"),
+                     resid=st.pe[:T], resid_mod=T)
+        else:
+            t_in = self._empty(Nd, D)
+            ops.gemm(melshift, st.w("mel_projection_in.weight"), t_in, bias=st.p("mel_projection_in.bias"))
+            # forward needs the two masks separately (the PE is added between them); ctx["drop_in"] (their
+            # product) is what the backward applies to the weight-gradient operand
+            spec = ops.DropSpec()
+            spec.state = self.drop_state.data_ptr()
+            spec.site_a, spec.thr_a = self.drop_sites["dec.in"], ops.drop_thr(dcfg.decoder_input)
+            spec.site_b, spec.thr_b = self.drop_sites["dec.pe"], ops.drop_thr(p_enc)
+            scale_a = 1.0 / ops.drop_keep(dcfg.decoder_input)
+            spec.scale = scale_a / ops.drop_keep(p_enc)
+            ops.dec_in_drop(t_in, st.pe[:T], y, T, spec, scale_a)
+        s1: dict = {}
+        pre = "decoder.layers.0."
+        y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, None, None, T, s1,
+                           drop=self._branch_specs("dec.0.self", p_dec, T, False))
+        return melshift, y, s1
+
     # ------------------------------------------------------------------------------------------
     # forward
     # ------------------------------------------------------------------------------------------
@@ -503,6 +545,11 @@ class AcousticEngine:
         if dcfg is not None:      # new RNG step + this step's stochastic-depth factors
             self._path_table = self._empty(len(self._path_rates), B)
             ops.drop_begin(self.drop_state, self._path_site_dev, self._path_p_dev, self._path_table, B)
+
+        dec_head = None
+        if self.multi_stream:                 # decoder input + layer-0 self-attention do not need the encoder
+            with self._on("d0"):
+                dec_head = self._decoder_head(ctx, mel_specs, B, T, dcfg, p_enc, p_dec)
 
         # ---- encoder -------------------------------------------------------------------------
         idx = phoneme_indices.contiguous()
@@ -565,27 +612,11 @@ class AcousticEngine:
                    mem=mem, p_idx=p_idx, e_idx=e_idx, fmask_t=fmask_t, fmask_p=fmask_p)
 
         # ---- decoder ---------------------------------------------------------------------------
-        mel = mel_specs.contiguous()
-        melshift = self._empty(Nd, cfg.mel_dim, dtype=BF16)
-        ops.shift_cast(mel, melshift.view(B, T, cfg.mel_dim))
-        y = self._empty(Nd, D)
-        # dropout(dropout(proj, p_in) + PE, p_enc): model.py:525-531 (the PE module is shared with the encoder)
-        ctx["drop_in"] = self._ds("dec.in", dcfg.decoder_input if dcfg else 0.0, "dec.pe", p_enc)
-        if ctx["drop_in"] is None:
-            ops.gemm(melshift, st.w("mel_projection_in.weight"), y, bias=st.p("mel_projection_in.bias"),
-                     resid=st.pe[:T], resid_mod=T)
+        if dec_head is None:
+            dec_head = self._decoder_head(ctx, mel_specs, B, T, dcfg, p_enc, p_dec)
         else:
-            t_in = self._empty(Nd, D)
-            ops.gemm(melshift, st.w("mel_projection_in.weight"), t_in, bias=st.p("mel_projection_in.bias"))
-            # forward needs the two masks separately (the PE is added between them); ctx["drop_in"] (their
-            # product) is what the backward applies to the weight-gradient operand
-            spec = ops.DropSpec()
-            spec.state = self.drop_state.data_ptr()
-            spec.site_a, spec.thr_a = self.drop_sites["dec.in"], ops.drop_thr(dcfg.decoder_input)
-            spec.site_b, spec.thr_b = self.drop_sites["dec.pe"], ops.drop_thr(p_enc)
-            scale_a = 1.0 / ops.drop_keep(dcfg.decoder_input)
-            spec.scale = scale_a / ops.drop_keep(p_enc)
-            ops.dec_in_drop(t_in, st.pe[:T], y, T, spec, scale_a)
+            self._join("d0")
+        melshift, y, s1_first = dec_head
         dec_saved = []
         kv_pre = [None] * cfg.n_decoder_layers
         if self.multi_stream:                 # all six cross-attention K/V projections depend on `mem` only
@@ -598,8 +629,11 @@ class AcousticEngine:
         for i in range(cfg.n_decoder_layers):
             pre = f"decoder.layers.{i}."
             s1, s2, s3 = {}, {}, {}
-            y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, None, None, T, s1,
-                               drop=self._branch_specs(f"dec.{i}.self", p_dec, T, False))
+            if i == 0:
+                s1 = s1_first                 # already computed by _decoder_head
+            else:
+                y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, None, None, T, s1,
+                                   drop=self._branch_specs(f"dec.{i}.self", p_dec, T, False))
             y = self._attn_fwd(pre + "cross_attn.", y, B, T, pre + "norm2.", False, fmask_t, mem, T, s2,
                                kv_pre=kv_pre[i], drop=self._branch_specs(f"dec.{i}.cross", p_dec, T, False))
             y = self._ffn_fwd(pre + "ff.", y, pre + "norm3.", cfg.decoder_ff_dim, s3,

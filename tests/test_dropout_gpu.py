@@ -217,3 +217,26 @@ def test_train_step_with_reference_dropout_under_graphs():
     assert torch.isfinite(hist[0]).all()
     assert torch.allclose(hist[0], hist[1], rtol=2e-2, atol=1e-3), (hist[0], hist[1])
     assert not torch.allclose(hist[0][0], hist[0][1], rtol=1e-4)      # masks / weights change between steps
+
+
+def test_masks_bit_exact_against_the_numpy_restatement():
+    """The exported CUDA masks equal oracle/dropmask.py bit for bit (integer work: exact), including a padded
+    leading dimension (the attention layout) and the stochastic-depth table written by kr_drop_begin."""
+    import numpy as np
+    from oracle import dropmask
+    from kokoro_ruslan_b200 import ops
+    state = torch.tensor([987654321, 41], dtype=torch.int64, device="cuda")
+    for site, p, rows, cols, ld in [(1, 0.1, 7, 513, 513), (9, 0.2, 33, 200, 256), (200, 0.15, 1, 100001, 100001)]:
+        got = _export(state, site, p, rows, cols, ld).cpu().numpy()
+        want = dropmask.keep_mask(987654321, 41, site, p, rows, cols, ld)
+        assert np.array_equal(got, want), (site, p)
+    # kr_drop_begin: advances the step and fills table[s, b] = keep(b) / (1 - p) from site path_site[s]
+    sites = torch.tensor([5, 6, 7], dtype=torch.int32, device="cuda")
+    probs = torch.tensor([0.0, 0.3, 0.5], dtype=torch.float32, device="cuda")
+    table = torch.empty(3, 16, device="cuda")
+    ops.drop_begin(state, sites, probs, table, 16)
+    assert state.cpu().tolist() == [987654321, 42]
+    for s, (site, p) in enumerate([(5, 0.0), (6, 0.3), (7, 0.5)]):
+        keep = dropmask.keep_mask(987654321, 42, site, p, 1, 16)[0].astype(np.float32)
+        want = keep / (1.0 - dropmask.drop_thr(p) / 65536.0) if p > 0 else np.ones(16, np.float32)
+        assert np.allclose(table[s].cpu().numpy(), want, rtol=1e-6), (s, table[s], want)
