@@ -35,16 +35,20 @@ struct AttnParams {
   bf16* dK; long long dk_ss, dk_bs;
   bf16* dV; long long dv_ss, dv_bs;
   // attention-probability dropout (F.scaled_dot_product_attention(dropout_p), transformers.py:393-398): element
-  // index of P[b, h, q, k] = ((b*H + h)*Sq + q) * sk_pad + k, sk_pad = Sk rounded up to the 128-key tile
+  // index of P[b, h, q, k] = ((b*H + h)*Sq + q) * sk_pad + k, sk_pad = Sk rounded up to the 128-key tile.
+  // This site uses the generator's BYTE-lane mode (one 32-bit hash serves 4 keys, thr quantised to 1/256): the
+  // softmax threads of these kernels are issue-bound and the 16-bit mode doubled the forward's time.
   DropSpec drop;
-  uint32_t sk_pad_half;
+  uint32_t sk_pad_quarter, thr4;     // thr4 = the 8-bit threshold replicated into 4 bytes
 };
 
-// packed-bf16 AND mask of one key pair: 0xffff per kept half
-__device__ __forceinline__ uint32_t drop_pair_bits(uint32_t pair, uint2 key, uint32_t thr) {
-  const uint32_t x = drop_hash(pair, key);
-  return ((x & 0xffffu) >= thr ? 0x0000ffffu : 0u) | ((x >> 16) >= thr ? 0xffff0000u : 0u);
+// keep bytes (0xff / 0x00) of the 4 keys served by hash `quad`
+__device__ __forceinline__ uint32_t drop_quad_bytes(uint32_t quad, uint2 key, uint32_t thr4) {
+  return __vcmpgeu4(drop_hash(quad, key), thr4);
 }
+// packed-bf16 AND masks of key pairs (0,1) and (2,3) of a quad from its keep bytes
+__device__ __forceinline__ uint32_t keep_lo_pair(uint32_t m) { return __byte_perm(m, 0u, 0x1100); }
+__device__ __forceinline__ uint32_t keep_hi_pair(uint32_t m) { return __byte_perm(m, 0u, 0x3322); }
 
 // [128 rows x 64 K] bf16 tile, K-major, SW128: k-th UMMA_K slice.
 __device__ __forceinline__ uint64_t desc_k64(uint32_t base, int k) {
@@ -150,7 +154,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t drow = 0;
   if (DROP) {
     dkey = drop_key(p.drop.state, p.drop.site_a);
-    drow = (uint32_t)(((long long)b * p.H + h) * p.Sq + min(qi, p.Sq - 1)) * p.sk_pad_half;
+    drow = (uint32_t)(((long long)b * p.H + h) * p.Sq + min(qi, p.Sq - 1)) * p.sk_pad_quarter;
   }
   constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
   constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
@@ -221,13 +225,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int hcol = 0; hcol < 2; ++hcol) {
       uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 64; i += 2) {
+      for (int i = 0; i < 64; i += 4) {
         // exp2(-inf) = 0 handles the masked entries; the row sum uses the bf16-rounded values the MMA sees
-        uint32_t u = pack_bf16(fast_exp2(sv[hcol * 64 + i] - m_use), fast_exp2(sv[hcol * 64 + i + 1] - m_use));
-        const float2 rb = unpack_bf16(u);
-        rowsum += rb.x + rb.y;          // the softmax denominator is that of the un-dropped probabilities
-        if (DROP) u &= drop_pair_bits(drow + j * (TK / 2) + hcol * 32 + (i >> 1), dkey, p.drop.thr_a);
-        pk[i >> 1] = u;
+        uint32_t u0 = pack_bf16(fast_exp2(sv[hcol * 64 + i] - m_use), fast_exp2(sv[hcol * 64 + i + 1] - m_use));
+        uint32_t u1 = pack_bf16(fast_exp2(sv[hcol * 64 + i + 2] - m_use), fast_exp2(sv[hcol * 64 + i + 3] - m_use));
+        const float2 ra = unpack_bf16(u0), rb = unpack_bf16(u1);
+        rowsum += (ra.x + ra.y) + (rb.x + rb.y);   // the softmax denominator is that of the un-dropped probabilities
+        if (DROP) {
+          const uint32_t m = drop_quad_bytes(drow + j * (TK / 4) + hcol * 16 + (i >> 2), dkey, p.thr4);
+          u0 &= keep_lo_pair(m);
+          u1 &= keep_hi_pair(m);
+        }
+        pk[i >> 1] = u0;
+        pk[(i >> 1) + 1] = u1;
       }
       tmem_st_32x32(tmem_S + t_lane + hcol * 32, pk);
     }
@@ -498,18 +508,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float nds = -delta_i * p.scale;
         uint32_t pkP[16], pkS[16];
         if (DROP) {
-          const uint32_t prow = (uint32_t)(bh * p.Sq + min(qi, p.Sq - 1)) * p.sk_pad_half + ((kv0 + c * 32) >> 1);
+          const uint32_t prow = (uint32_t)(bh * p.Sq + min(qi, p.Sq - 1)) * p.sk_pad_quarter + ((kv0 + c * 32) >> 2);
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float p0 = fast_exp2(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse_i));
-            float p1 = fast_exp2(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse_i));
-            p0 = ((ok >> e) & 1u) ? p0 : 0.f;
-            p1 = ((ok >> (e + 1)) & 1u) ? p1 : 0.f;
-            const uint32_t keep = drop_pair_bits(prow + (e >> 1), dkey, p.drop.thr_a);
-            const float g0 = (keep & 0xffffu) ? __uint_as_float(rp[e]) : 0.f;
-            const float g1 = (keep >> 16) ? __uint_as_float(rp[e + 1]) : 0.f;
-            pkP[e >> 1] = pack_bf16(p0, p1) & keep;                    // dV += (mask P)^T dO  (1/keep at the store)
-            pkS[e >> 1] = pack_bf16(p0 * fmaf(g0, dp_scale, nds), p1 * fmaf(g1, dp_scale, nds));
+          for (int e = 0; e < 32; e += 4) {
+            const uint32_t m = drop_quad_bytes(prow + (e >> 2), dkey, p.thr4);
+            float pv[4], gv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float pe = fast_exp2(fmaf(__uint_as_float(rs[e + t]), p.scale_log2, -lse_i));
+              pv[t] = ((ok >> (e + t)) & 1u) ? pe : 0.f;
+              gv[t] = ((m >> (8 * t)) & 1u) ? __uint_as_float(rp[e + t]) : 0.f;
+            }
+            pkP[e >> 1] = pack_bf16(pv[0], pv[1]) & keep_lo_pair(m);          // dV += (mask P)^T dO  (1/keep at the store)
+            pkP[(e >> 1) + 1] = pack_bf16(pv[2], pv[3]) & keep_hi_pair(m);
+            pkS[e >> 1] = pack_bf16(pv[0] * fmaf(gv[0], dp_scale, nds), pv[1] * fmaf(gv[1], dp_scale, nds));
+            pkS[(e >> 1) + 1] = pack_bf16(pv[2] * fmaf(gv[2], dp_scale, nds), pv[3] * fmaf(gv[3], dp_scale, nds));
           }
         } else if (__all_sync(0xffffffffu, ok == 0xffffffffu)) {
 #pragma unroll
@@ -590,10 +603,13 @@ int make_head_map(CUtensorMap* m, const void* ptr, int H, int S, int B, long lon
 int set_drop(AttnParams& p, const kr_drop_spec* drop, const char* who) {
   p.drop = kr_drop_to_device(drop);
   const long long sk_pad = (long long)((p.Sk + TK - 1) / TK) * TK;
-  p.sk_pad_half = (uint32_t)(sk_pad / 2);
+  p.sk_pad_quarter = (uint32_t)(sk_pad / 4);
   if (p.drop.state != nullptr) {
     if (p.drop.thr_b != 0 || p.drop.row_scale != nullptr) { kr_set_error("attention dropout takes a single-mask spec"); return KR_ERR_ARG; }
-    if ((long long)p.B * p.H * p.Sq * (sk_pad / 2) >= (1LL << 32)) { kr_set_error(who); return KR_ERR_UNSUPPORTED; }
+    if (p.drop.thr_a & 0xffu) { kr_set_error("attention dropout uses the byte-lane mode: thr must be a multiple of 256"); return KR_ERR_ARG; }
+    if ((long long)p.B * p.H * p.Sq * (sk_pad / 4) >= (1LL << 32)) { kr_set_error(who); return KR_ERR_UNSUPPORTED; }
+    const uint32_t t8 = p.drop.thr_a >> 8;
+    p.thr4 = t8 * 0x01010101u;
     if (p.drop.thr_a == 0) p.drop.state = nullptr;     // p = 0: plain kernels
   }
   return KR_OK;

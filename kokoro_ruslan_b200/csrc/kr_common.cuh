@@ -130,6 +130,8 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 //   hash(pair, key)   = two multiply-xorshift rounds keyed before each multiply; 32 bits serve the
 //                       element pair (2*pair, 2*pair + 1) as two 16-bit lanes
 //   keep(e)           = lane16 >= thr,   thr = round(p * 65536)      (P(keep) = 1 - thr / 65536)
+//   byte-lane mode (attention-probability sites only, kr_attn.cu): one hash serves the 4 elements 4*quad .. 4*quad+3
+//                       as 8-bit lanes, keep iff lane8 >= thr >> 8 with thr = round(p * 256) * 256
 // A spec can carry a second independent mask (site_b / thr_b: consecutive reference dropouts) and a
 // per-sample factor table (stochastic depth: 0 or 1 / (1 - p_path)), see kr_drop_spec.
 // ---------------------------------------------------------------------------------------------

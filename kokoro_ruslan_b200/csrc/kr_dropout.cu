@@ -53,16 +53,21 @@ __global__ void dec_in_drop_kernel(const float* __restrict__ t, const float* __r
 }
 
 __global__ void drop_export_kernel(const unsigned long long* state, uint32_t site, uint32_t thr, long long rows,
-                                   int cols, long long ld, unsigned char* __restrict__ out) {
+                                   int cols, long long ld, unsigned char* __restrict__ out, int byte_lanes) {
   kr::pdl_entry();
   const uint2 k = drop_key(state, site);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols, c = i % cols;
     const long long e = r * ld + c;
-    const uint32_t x = drop_hash((uint32_t)(e >> 1), k);
-    const uint32_t lane16 = (e & 1) ? (x >> 16) : (x & 0xffffu);
-    out[i] = lane16 >= thr ? 1 : 0;
+    if (byte_lanes) {      // attention sites: 4 elements per hash, 8-bit lanes, threshold thr >> 8
+      const uint32_t x = drop_hash((uint32_t)(e >> 2), k);
+      out[i] = ((x >> (8 * (e & 3))) & 0xffu) >= (thr >> 8) ? 1 : 0;
+    } else {
+      const uint32_t x = drop_hash((uint32_t)(e >> 1), k);
+      const uint32_t lane16 = (e & 1) ? (x >> 16) : (x & 0xffffu);
+      out[i] = lane16 >= thr ? 1 : 0;
+    }
   }
 }
 
@@ -99,11 +104,13 @@ extern "C" int kr_dec_in_drop(const float* t, const float* pe, float* y, int N, 
 }
 
 extern "C" int kr_drop_export_mask(const unsigned long long* state, unsigned int site, unsigned int thr,
-                                   long long rows, int cols, long long ld, unsigned char* out, void* stream) {
+                                   long long rows, int cols, long long ld, unsigned char* out, int byte_lanes,
+                                   void* stream) {
   if (rows <= 0 || cols <= 0) return KR_OK;
   long long b = (rows * cols + 255) / 256;
   const long long cap = (long long)kr::kNumSMs * 16;
-  kr::launch(drop_export_kernel, (int)(b < cap ? b : cap), 256, 0, (cudaStream_t)stream, state, site, thr, rows, cols, ld, out);
+  kr::launch(drop_export_kernel, (int)(b < cap ? b : cap), 256, 0, (cudaStream_t)stream, state, site, thr, rows, cols, ld, out,
+             byte_lanes);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -171,7 +171,7 @@ class AcousticEngine:
         return self.training and self.dropout is not None
 
     def _ds(self, site: Optional[str], p: float = 0.0, site_b: Optional[str] = None, p_b: float = 0.0,
-            path: Optional[str] = None, rows_per_sample: int = 1):
+            path: Optional[str] = None, rows_per_sample: int = 1, byte_lanes: bool = False):
         """Drop spec of one site (None when dropout is off or the site is a no-op)."""
         if not self._drop_on:
             return None
@@ -179,7 +179,7 @@ class AcousticEngine:
         if path is not None and self._path_rates[self._path_rows[path]] > 0:
             row = self._path_table[self._path_rows[path]]
         return ops.make_drop_spec(self.drop_state, self.drop_sites[site] if site else 0, p,
-                                  self.drop_sites[site_b] if site_b else 0, p_b, row, rows_per_sample)
+                                  self.drop_sites[site_b] if site_b else 0, p_b, row, rows_per_sample, byte_lanes)
 
     def _branch_specs(self, tag: str, p: float, S: int, ffn: bool) -> dict:
         """Specs of one residual branch `tag` ('enc.3.attn', 'dec.0.ffn', ...) with rows_per_sample = S:
@@ -189,7 +189,7 @@ class AcousticEngine:
             return {"p": None, "u": None, "out": None}
         out = self._ds(f"{tag}.out", p, f"{tag}.out2" if ffn else None, p if ffn else 0.0, path=f"{tag}.path",
                        rows_per_sample=S)
-        return {"p": None if ffn else self._ds(f"{tag}.p", p), "u": self._ds(f"{tag}.u", p) if ffn else None,
+        return {"p": None if ffn else self._ds(f"{tag}.p", p, byte_lanes=True), "u": self._ds(f"{tag}.u", p) if ffn else None,
                 "out": out}
 
     # ------------------------------------------------------------------------------------------

@@ -52,11 +52,15 @@ class OpTimer:
         self.records: List[Tuple[str, float, float, torch.cuda.Event, torch.cuda.Event]] = []
         self._saved: Dict[str, Callable] = {}
         self.spin_ms = spin_ms
+        # every GEMM call of the instrumented pass (original function, args, kwargs): lets the caller replay exactly
+        # those launches back to back inside a CUDA graph (replay_gemms) — kernel time without event-pair overhead
+        self.gemm_calls: List[Tuple[Callable, tuple, dict]] = []
 
     def _wrap(self, name: str, fn: Callable) -> Callable:
         def wrapper(*args, **kwargs):
             if name == "gemm":
                 label, flops, byts = _gemm_work(args, kwargs)
+                self.gemm_calls.append((fn, args, kwargs))
             elif name in ("attn_fwd", "attn_bwd"):
                 label, flops, byts = _attn_work(name, args)
             else:
@@ -105,6 +109,33 @@ class OpTimer:
         for name, fn in self._saved.items():
             setattr(ops, name, fn)
         torch.cuda.synchronize()
+
+    def replay_gemms(self, reps: int = 5) -> Tuple[float, int]:
+        """(ms per pass, launches): all recorded GEMM launches re-issued in order on one stream inside a CUDA graph
+        and timed with CUDA events over `reps` replays.  The operands are the step's own tensors (the caller keeps
+        them alive); outputs are simply rewritten (weight-gradient GEMMs accumulate once more, which nothing reads
+        before the next step zeroes the buffer)."""
+        if not self.gemm_calls:
+            return 0.0, 0
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for fn, a, kw in self.gemm_calls:          # warm (function attributes, tensor maps)
+                fn(*a, **kw)
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for fn, a, kw in self.gemm_calls:
+                    fn(*a, **kw)
+            g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            for _ in range(reps):
+                g.replay()
+            e1.record(side)
+            side.synchronize()
+        torch.cuda.current_stream().wait_stream(side)
+        return e0.elapsed_time(e1) / reps, len(self.gemm_calls)
 
     def summary(self) -> List[dict]:
         """Per-label totals sorted by device time."""

@@ -37,10 +37,17 @@ def drop_keep(p: float) -> float:
     return 1.0 - drop_thr(p) / 65536.0
 
 
+def drop_thr8(p: float) -> int:
+    """Threshold of the byte-lane mode (attention-probability sites): p quantised to 1/256, in 16-bit units."""
+    return max(0, min(255, int(round(float(p) * 256.0)))) * 256
+
+
 def make_drop_spec(state: torch.Tensor, site_a: int = 0, p_a: float = 0.0, site_b: int = 0, p_b: float = 0.0,
-                   row_scale: Optional[torch.Tensor] = None, rows_per_sample: int = 1) -> Optional["DropSpec"]:
-    """None when the site is a no-op (both probabilities 0 and no per-sample factors)."""
-    ta, tb = drop_thr(p_a), drop_thr(p_b)
+                   row_scale: Optional[torch.Tensor] = None, rows_per_sample: int = 1,
+                   byte_lanes: bool = False) -> Optional["DropSpec"]:
+    """None when the site is a no-op (both probabilities 0 and no per-sample factors).  byte_lanes: the
+    attention kernels' generator mode (threshold quantised to 1/256; the scale stays the exact 1 / keep)."""
+    ta, tb = (drop_thr8(p_a) if byte_lanes else drop_thr(p_a)), drop_thr(p_b)
     if ta == 0 and tb == 0 and row_scale is None:
         return None
     if ta == 0 and tb != 0:
@@ -428,11 +435,13 @@ def dec_in_drop(t, pe, y, T: int, drop: DropSpec, scale_a: float):
                                _dref(drop), _stream()), "kr_dec_in_drop")
 
 
-def drop_export_mask(state, site: int, p: float, rows: int, cols: int, ld: int, out):
+def drop_export_mask(state, site: int, p: float, rows: int, cols: int, ld: int, out, byte_lanes: bool = False):
     """out[rows, cols] uint8 = keep mask of `site` for elements r*ld + c (test aid)."""
     assert out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == rows * cols
-    check(lib().kr_drop_export_mask(_ptr(state), ctypes.c_uint(site), ctypes.c_uint(drop_thr(p)), c_ll(rows),
-                                    c_int(cols), c_ll(ld), _ptr(out), _stream()), "kr_drop_export_mask")
+    thr = drop_thr8(p) if byte_lanes else drop_thr(p)
+    check(lib().kr_drop_export_mask(_ptr(state), ctypes.c_uint(site), ctypes.c_uint(thr), c_ll(rows),
+                                    c_int(cols), c_ll(ld), _ptr(out), c_int(int(byte_lanes)), _stream()),
+          "kr_drop_export_mask")
 
 
 def vp_head_fwd(h, row_of_tok, w, b, mask, out, L: int, chunk: int):

@@ -25,17 +25,26 @@ def drop_thr(p: float) -> int:
     return max(0, min(65535, int(round(float(p) * 65536.0))))
 
 
-def keep_mask(seed: int, step: int, site: int, p: float, rows: int, cols: int, ld: int = None) -> np.ndarray:
-    """uint8 [rows, cols]: 1 = kept, for elements r * ld + c."""
+def drop_thr8(p: float) -> int:
+    return max(0, min(255, int(round(float(p) * 256.0)))) * 256
+
+
+def keep_mask(seed: int, step: int, site: int, p: float, rows: int, cols: int, ld: int = None,
+              byte_lanes: bool = False) -> np.ndarray:
+    """uint8 [rows, cols]: 1 = kept, for elements r * ld + c.  byte_lanes: the attention-probability sites'
+    mode (hash(e >> 2), 8-bit lane e & 3, threshold round(p * 256))."""
     ld = cols if ld is None else ld
     k0, k1 = drop_key(seed, step, site)
     e = (np.arange(rows, dtype=np.uint64)[:, None] * np.uint64(ld) + np.arange(cols, dtype=np.uint64)[None, :])
-    x = (e >> np.uint64(1)).astype(np.uint32) ^ k0
+    x = (e >> np.uint64(2 if byte_lanes else 1)).astype(np.uint32) ^ k0
     with np.errstate(over="ignore"):
         x = x * np.uint32(0x7FEB352D)
         x ^= x >> np.uint32(15)
         x ^= k1
         x = x * np.uint32(0x846CA68B)
         x ^= x >> np.uint32(16)
+    if byte_lanes:
+        lane = (x >> ((e & np.uint64(3)) * np.uint64(8)).astype(np.uint32)) & np.uint32(0xFF)
+        return (lane >= np.uint32(drop_thr8(p) >> 8)).astype(np.uint8)
     lane = np.where((e & np.uint64(1)) == 1, x >> np.uint32(16), x & np.uint32(0xFFFF))
     return (lane >= np.uint32(drop_thr(p))).astype(np.uint8)

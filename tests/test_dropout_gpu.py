@@ -19,10 +19,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 
 
-def _export(state, site, p, rows, cols, ld):
+def _export(state, site, p, rows, cols, ld, byte_lanes=False):
     from kokoro_ruslan_b200 import ops
     out = torch.empty(rows, cols, dtype=torch.uint8, device="cuda")
-    ops.drop_export_mask(state, site, p, rows, cols, ld, out)
+    ops.drop_export_mask(state, site, p, rows, cols, ld, out, byte_lanes)
     return out
 
 
@@ -60,7 +60,8 @@ def test_attention_dropout_matches_exported_mask(causal):
     key_mask = torch.zeros(B, Sk, dtype=torch.uint8, device="cuda")
     key_mask[1, 170:] = 1
     state = torch.tensor([5, 3], dtype=torch.int64, device="cuda")
-    spec = ops.make_drop_spec(state, 11, p)
+    spec = ops.make_drop_spec(state, 11, p, byte_lanes=True)
+    keep_p = 1.0 - ops.drop_thr8(p) / 65536.0
     o = torch.empty_like(q)
     lse = torch.empty(B, H, Sq, device="cuda")
     ops.attn_fwd(q, k, v, o, lse, key_mask, causal, 0.125, drop=spec)
@@ -71,13 +72,14 @@ def test_attention_dropout_matches_exported_mask(causal):
     torch.cuda.synchronize()
 
     sk_pad = (Sk + 127) // 128 * 128
-    keep = _export(state, 11, p, B * H * Sq, Sk, sk_pad).view(B, H, Sq, Sk).float()
+    keep = _export(state, 11, p, B * H * Sq, Sk, sk_pad, byte_lanes=True).view(B, H, Sq, Sk).float()
+    assert abs(float(keep.mean()) - keep_p) < 5e-3
     qf, kf, vf = (t.float().transpose(1, 2).detach().requires_grad_(True) for t in (q, k, v))
     s = (qf @ kf.transpose(-1, -2)) * 0.125
     if causal:
         s = s + torch.triu(torch.full((Sq, Sk), float("-inf"), device="cuda"), diagonal=1)
     s = s.masked_fill(key_mask.bool().view(B, 1, 1, Sk), float("-inf"))
-    pr = torch.softmax(s, dim=-1) * keep / ops.drop_keep(p)
+    pr = torch.softmax(s, dim=-1) * keep / keep_p
     want = pr @ vf
     want.backward(d_o.float().transpose(1, 2))
 
@@ -103,12 +105,13 @@ class _MaskOracle:
         self.table = eng._path_table.float().cpu()
         self.seen = set()
 
-    def _mask(self, site, p, rows, cols, ld=None):
+    def _mask(self, site, p, rows, cols, ld=None, byte_lanes=False):
         from kokoro_ruslan_b200 import ops
-        if ops.drop_thr(p) == 0:
+        thr = ops.drop_thr8(p) if byte_lanes else ops.drop_thr(p)
+        if thr == 0:
             return torch.ones(rows, cols)
-        m = _export(self.state, self.eng.drop_sites[site], p, rows, cols, ld or cols).float().cpu()
-        return m / ops.drop_keep(p)
+        m = _export(self.state, self.eng.drop_sites[site], p, rows, cols, ld or cols, byte_lanes).float().cpu()
+        return m / (1.0 - thr / 65536.0)
 
     def __call__(self, site, t, **info):
         d = self.d
@@ -128,7 +131,7 @@ class _MaskOracle:
         p = d.encoder if parts[0] == "enc" else d.decoder
         if parts[-1] == "p":
             Bh, Sq, Sk = t.shape[0] * t.shape[1], t.shape[2], t.shape[3]
-            return t * self._mask(site, p, Bh * Sq, Sk, (Sk + 127) // 128 * 128).view_as(t)
+            return t * self._mask(site, p, Bh * Sq, Sk, (Sk + 127) // 128 * 128, byte_lanes=True).view_as(t)
         if parts[-1] == "u":
             return t * self._mask(site, p, t.shape[0] * t.shape[1], t.shape[2]).view_as(t)
         assert parts[-1] == "out"
@@ -227,9 +230,10 @@ def test_masks_bit_exact_against_the_numpy_restatement():
     from kokoro_ruslan_b200 import ops
     state = torch.tensor([987654321, 41], dtype=torch.int64, device="cuda")
     for site, p, rows, cols, ld in [(1, 0.1, 7, 513, 513), (9, 0.2, 33, 200, 256), (200, 0.15, 1, 100001, 100001)]:
-        got = _export(state, site, p, rows, cols, ld).cpu().numpy()
-        want = dropmask.keep_mask(987654321, 41, site, p, rows, cols, ld)
-        assert np.array_equal(got, want), (site, p)
+        for byte_lanes in (False, True):
+            got = _export(state, site, p, rows, cols, ld, byte_lanes).cpu().numpy()
+            want = dropmask.keep_mask(987654321, 41, site, p, rows, cols, ld, byte_lanes)
+            assert np.array_equal(got, want), (site, p, byte_lanes)
     # kr_drop_begin: advances the step and fills table[s, b] = keep(b) / (1 - p) from site path_site[s]
     sites = torch.tensor([5, 6, 7], dtype=torch.int32, device="cuda")
     probs = torch.tensor([0.0, 0.3, 0.5], dtype=torch.float32, device="cuda")

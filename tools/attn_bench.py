@@ -35,9 +35,14 @@ def run(B, H, S, causal):
                           ops._ptr(lse), ops._ptr(delta), None, ctypes.c_longlong(dq.stride(1)), ctypes.c_longlong(dq.stride(0)),
                           ops._ptr(dk), *ops._heads_strides(dk), ops._ptr(dv), *ops._heads_strides(dv), None,
                           ctypes.c_int(B), ctypes.c_int(H), ctypes.c_int(S), ctypes.c_int(S), ctypes.c_int(int(causal)),
-                          ctypes.c_float(0.125), ops._stream())
+                          ctypes.c_float(0.125), None, ops._stream())
     b2 = bench(bwd_nodq)
     print(f"   bwd without dQ atomics: {b2:7.1f} us")
+    state = torch.tensor([1, 1], dtype=torch.int64, device="cuda")
+    spec = ops.make_drop_spec(state, 5, 0.2, byte_lanes=True)
+    fd = bench(lambda: ops.attn_fwd(q, k, v, o, lse, None, causal, 0.125, drop=spec))
+    bd = bench(lambda: ops.attn_bwd(q, k, v, o, d_o, lse, delta, dq, dk, dv, None, causal, 0.125, drop=spec))
+    print(f"   with dropout 0.2: fwd {fd:7.1f} us | bwd {bd:7.1f} us")
     mm = 2.0 * B * H * S * S * 64 * (0.5 if causal else 1.0)
     print(f"B{B} H{H} S{S} causal={int(causal)}: fwd {f:7.1f} us {2*mm/f/1e6:6.1f} TF/s | bwd {b:7.1f} us {5*mm/b/1e6:6.1f} TF/s")
 
