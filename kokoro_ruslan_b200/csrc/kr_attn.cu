@@ -294,12 +294,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ O, long long o_ss, long long o_bs,
                                      const bf16* __restrict__ dO, long long do_ss, long long do_bs,
-                                     float* __restrict__ delta, int B, int H, int Sq) {
+                                     float* __restrict__ delta, int B, int H, int Sq,
+                                     float* __restrict__ dq, long long dq_ss, long long dq_bs) {
   pdl_entry();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B * Sq) return;
   const int b = row / Sq, q = row % Sq;
+  if (dq != nullptr) {      // the main kernel accumulates dQ with atomics: zero it here instead of a separate memset
+    float4* z = reinterpret_cast<float4*>(dq + (long long)b * dq_bs + (long long)q * dq_ss);
+    for (int v = lane; v < H * 16; v += 32) z[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const bf16* o = O + (long long)b * o_bs + (long long)q * o_ss;
   const bf16* d = dO + (long long)b * do_bs + (long long)q * do_ss;
   // H*64 elements, 8 per 16-byte vector -> H*8 vectors; vector v belongs to head v/8
@@ -669,7 +674,7 @@ extern "C" int kr_attn_bwd(const void* q, long long q_ss, long long q_bs, const 
     const int rows = B * Sq, wpb = 8;
     kr::launch(attn_bwd_prep_kernel, (rows + wpb - 1) / wpb, wpb * 32, 0, st, 
         reinterpret_cast<const bf16*>(o), o_ss, o_bs, reinterpret_cast<const bf16*>(d_o), do_ss, do_bs,
-        delta, B, H, Sq);
+        delta, B, H, Sq, dq, dq_ss, dq_bs);
     KR_CHECK_LAUNCH();
   }
   CUtensorMap tq, tk, tv, tdo;

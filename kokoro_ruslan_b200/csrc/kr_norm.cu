@@ -7,6 +7,7 @@
 #include "kr_common.cuh"
 #include "kokoro_b200.h"
 #include <float.h>
+#include <stdlib.h>
 
 namespace {
 using namespace kr;
@@ -69,17 +70,21 @@ __global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restri
 // ---------------------------------------------------------------------------------------------
 // LayerNorm backward: dx = dres + rstd*(g*dy - mean(g*dy) - xhat*mean(g*dy*xhat))
 // ---------------------------------------------------------------------------------------------
-template <int NV>
-__global__ void __launch_bounds__(WARPS * 32, 3) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+template <int NV, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                               const float* __restrict__ gamma, const float* dres, float* dx,
                               bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-                              float* __restrict__ dbeta, int N, const DropSpec drop) {
+                              float* __restrict__ dbeta, int N, const DropSpec drop,
+                              float* __restrict__ dcol_bf16) {
   kr::pdl_entry();
   constexpr int D = NV * 128;
   __shared__ float sm[WARPS][D];
   DropCtx dc{};
   if (drop.state != nullptr) dc = drop_ctx(drop);
+  float4 ao[NV];      // column sums of what is written to dx_bf16 (= the bias gradient of the Linear it feeds)
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ao[i] = make_float4(0, 0, 0, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 ag[NV], ab[NV];
 #pragma unroll
@@ -122,20 +127,22 @@ __global__ void __launch_bounds__(WARPS * 32, 3) ln_bwd_kernel(const float* __re
           o.x *= f.x * rsf; o.y *= f.y * rsf; o.z *= f.z * rsf; o.w *= f.w * rsf;
         }
         st_bf16x4(dx_bf16 + off + c0, o);
+        ao[i].x += o.x; ao[i].y += o.y; ao[i].z += o.z; ao[i].w += o.w;
       }
     }
   }
   // column gradients: warps -> smem -> one atomic per column per block
-  for (int pass = 0; pass < 2; ++pass) {
+  const int n_pass = dcol_bf16 != nullptr ? 3 : 2;
+  for (int pass = 0; pass < n_pass; ++pass) {
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NV; ++i) st4(&sm[warp][i * 128 + lane * 4], pass == 0 ? ag[i] : ab[i]);
+    for (int i = 0; i < NV; ++i) st4(&sm[warp][i * 128 + lane * 4], pass == 0 ? ag[i] : (pass == 1 ? ab[i] : ao[i]));
     __syncthreads();
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < WARPS; ++w) t += sm[w][c];
-      atomicAdd((pass == 0 ? dgamma : dbeta) + c, t);
+      atomicAdd((pass == 0 ? dgamma : (pass == 1 ? dbeta : dcol_bf16)) + c, t);
     }
   }
 }
@@ -180,12 +187,16 @@ __global__ void rms_resid_fwd_kernel(const float* __restrict__ y, const float* _
 template <int NV>
 __global__ void __launch_bounds__(WARPS * 32, 3) rms_resid_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y,
                                      const float* __restrict__ gain, bf16* __restrict__ dy,
-                                     float* __restrict__ dgain, int N, float eps, const DropSpec drop) {
+                                     float* __restrict__ dgain, int N, float eps, const DropSpec drop,
+                                     float* __restrict__ dcol) {
   kr::pdl_entry();
   constexpr int D = NV * 128;
   __shared__ float sm[WARPS][D];
   DropCtx dc{};
   if (drop.state != nullptr) dc = drop_ctx(drop);
+  float4 ao[NV];      // column sums of dy (= the bias gradient of linear2)
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ao[i] = make_float4(0, 0, 0, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 ag[NV];
 #pragma unroll
@@ -220,19 +231,24 @@ __global__ void __launch_bounds__(WARPS * 32, 3) rms_resid_bwd_kernel(const floa
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c0 = i * 128 + lane * 4;
-      st_bf16x4(dy + off + c0, make_float4(rstd * (d[i].x - v[i].x * c), rstd * (d[i].y - v[i].y * c),
-                                           rstd * (d[i].z - v[i].z * c), rstd * (d[i].w - v[i].w * c)));
+      const float4 o = make_float4(rstd * (d[i].x - v[i].x * c), rstd * (d[i].y - v[i].y * c),
+                                   rstd * (d[i].z - v[i].z * c), rstd * (d[i].w - v[i].w * c));
+      st_bf16x4(dy + off + c0, o);
+      ao[i].x += o.x; ao[i].y += o.y; ao[i].z += o.z; ao[i].w += o.w;
     }
   }
-  __syncthreads();
+  const int n_pass = dcol != nullptr ? 2 : 1;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < NV; ++i) st4(&sm[warp][i * 128 + lane * 4], ag[i]);
-  __syncthreads();
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float t = 0.f;
+    for (int i = 0; i < NV; ++i) st4(&sm[warp][i * 128 + lane * 4], pass == 0 ? ag[i] : ao[i]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) t += sm[w][c];
-    atomicAdd(dgain + c, t);
+      for (int w = 0; w < WARPS; ++w) t += sm[w][c];
+      atomicAdd((pass == 0 ? dgain : dcol) + c, t);
+    }
   }
 }
 
@@ -333,7 +349,8 @@ __global__ void __launch_bounds__(WARPS * 32) qkv_prep_fwd_kernel(const PrepPara
   }
 }
 
-__global__ void __launch_bounds__(WARPS * 32, 3) qkv_prep_bwd_kernel(const PrepParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) qkv_prep_bwd_kernel(const PrepParams p) {
   kr::pdl_entry();
   __shared__ float sm[64];
   if (threadIdx.x < 64) sm[threadIdx.x] = 0.f;
@@ -405,6 +422,13 @@ __global__ void __launch_bounds__(WARPS * 32, 3) qkv_prep_bwd_kernel(const PrepP
   if (threadIdx.x < 64 && pp.dgain != nullptr) atomicAdd(pp.dgain + threadIdx.x, sm[threadIdx.x]);
 }
 
+// occupancy variant of the two register-heavy backward kernels: 3 blocks / SM caps them at 80 registers (they
+// spill ~260 bytes since the dropout specs were added), 2 blocks / SM lets them keep everything in registers
+int norm_minb() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("KR_NORM_MINB"); v = (e != nullptr && e[0] == '3') ? 3 : 2; }
+  return v;
+}
 int row_blocks(int N) { return (N + WARPS - 1) / WARPS; }
 int persistent_blocks(int N) { return min(row_blocks(N), kNumSMs * 4); }
 
@@ -432,12 +456,18 @@ extern "C" int kr_layernorm_fwd(const float* x, const float* gamma, const float*
 extern "C" int kr_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                 const float* gamma, const float* dres, float* dx, void* dx_bf16,
                                 float* dgamma, float* dbeta, int N, int D, const kr_drop_spec* drop_bf16,
-                                void* stream) {
+                                float* dcol_bf16, void* stream) {
   if (N <= 0) return KR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  DISPATCH_NV(D, (kr::launch(ln_bwd_kernel<NV>, persistent_blocks(N), WARPS * 32, 0, st, 
-                     dy, x, mean, rstd, gamma, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dgamma,
-                     dbeta, N, kr_drop_to_device(drop_bf16))));
+  if (norm_minb() == 3) {
+    DISPATCH_NV(D, (kr::launch(ln_bwd_kernel<NV, 3>, persistent_blocks(N), WARPS * 32, 0, st,
+                       dy, x, mean, rstd, gamma, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dgamma,
+                       dbeta, N, kr_drop_to_device(drop_bf16), dcol_bf16)));
+  } else {
+    DISPATCH_NV(D, (kr::launch(ln_bwd_kernel<NV, 2>, persistent_blocks(N), WARPS * 32, 0, st,
+                       dy, x, mean, rstd, gamma, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dgamma,
+                       dbeta, N, kr_drop_to_device(drop_bf16), dcol_bf16)));
+  }
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -453,12 +483,13 @@ extern "C" int kr_rmsnorm_resid_fwd(const float* y, const float* gain, const flo
 }
 
 extern "C" int kr_rmsnorm_resid_bwd(const float* dout, const float* y, const float* gain, void* dy_bf16,
-                                    float* dgain, int N, int D, const kr_drop_spec* drop, void* stream) {
+                                    float* dgain, int N, int D, const kr_drop_spec* drop, float* dcol,
+                                    void* stream) {
   if (N <= 0) return KR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DISPATCH_NV(D, (kr::launch(rms_resid_bwd_kernel<NV>, persistent_blocks(N), WARPS * 32, 0, st, 
                      dout, y, gain, reinterpret_cast<bf16*>(dy_bf16), dgain, N, FLT_EPSILON,
-                     kr_drop_to_device(drop))));
+                     kr_drop_to_device(drop), dcol)));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -518,7 +549,8 @@ extern "C" int kr_qkv_prep_bwd(const void* in0, const void* in1, const void* in2
   const long long nb_ = (total + WARPS - 1) / WARPS;
   const int per_part = kNumSMs * 6 / n_parts;
   const int blocks = (int)(nb_ < per_part ? nb_ : per_part);
-  kr::launch(qkv_prep_bwd_kernel, dim3(blocks, n_parts), WARPS * 32, 0, st, p);
+  if (norm_minb() == 3) kr::launch(qkv_prep_bwd_kernel<3>, dim3(blocks, n_parts), WARPS * 32, 0, st, p);
+  else                  kr::launch(qkv_prep_bwd_kernel<2>, dim3(blocks, n_parts), WARPS * 32, 0, st, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -332,17 +332,18 @@ class AcousticEngine:
 
     def _attn_bwd(self, pre: str, dout: torch.Tensor, dout_bf: torch.Tensor, B: int, S: int, norm: str,
                   causal: bool, key_mask, mem, Sk: int, sv: dict, dmem: Optional[torch.Tensor],
-                  dmem_first: bool, next_drop=None):
+                  dmem_first: bool, next_drop=None, next_dbias=None, bias_done: bool = False):
         """dout_bf must already carry this branch's output dropout (sv['drop']['out']): it is produced by the
         layernorm_bwd of the sub-layer that follows in the forward.  next_drop = the output-dropout spec of the
         branch that PRECEDES this one in the forward, applied to the returned dx_bf."""
         st, D, H = self.store, self.D, self.H
         N = B * S
         cross = mem is not None
-        self._wgrad(dout_bf, sv["o"], st.g(pre + "w_o.weight"), st.g(pre + "w_o.bias"))
+        # bias_done: the layernorm_bwd that produced dout_bf already accumulated its column sums into w_o.bias
+        self._wgrad(dout_bf, sv["o"], st.g(pre + "w_o.weight"), None if bias_done else st.g(pre + "w_o.bias"))
         d_o = self._empty(N, D, dtype=BF16)
         ops.gemm(dout_bf, st.w(pre + "w_o.weight"), d_o, b_mn_major=True)
-        dq = self._zeros(N, D)
+        dq = self._empty(N, D)            # zeroed by kr_attn_bwd's prep kernel
         Nk = B * Sk
         dkv = self._empty(Nk, 2 * D, dtype=BF16)
         delta = self._empty(B, H, S)
@@ -379,7 +380,7 @@ class AcousticEngine:
         dx = self._empty(N, D)
         dx_bf = self._empty(N, D, dtype=BF16)
         ops.layernorm_bwd(dh, sv["x"], sv["mean"], sv["rstd"], st.p(norm + "weight"), dout, dx, dx_bf,
-                          st.g(norm + "weight"), st.g(norm + "bias"), drop_bf16=next_drop)
+                          st.g(norm + "weight"), st.g(norm + "bias"), drop_bf16=next_drop, dcol_bf16=next_dbias)
         return dx, dx_bf
 
     # ------------------------------------------------------------------------------------------
@@ -403,13 +404,13 @@ class AcousticEngine:
         sv.update(x=x, h=h, mean=mean, rstd=rstd, hff=hff, u=u, y=y, drop=drop)
         return out
 
-    def _ffn_bwd(self, pre: str, dout: torch.Tensor, norm: str, ff: int, sv: dict, next_drop=None):
+    def _ffn_bwd(self, pre: str, dout: torch.Tensor, norm: str, ff: int, sv: dict, next_drop=None, next_dbias=None):
         st, D = self.store, self.D
         N = dout.shape[0]
         dy = self._empty(N, D, dtype=BF16)
         ops.rmsnorm_resid_bwd(dout, sv["y"], st.p(pre + "output_norm.weight"), dy, st.g(pre + "output_norm.weight"),
-                              drop=sv["drop"]["out"])
-        self._wgrad(dy, sv["u"], st.g(pre + "linear2.weight"), st.g(pre + "linear2.bias"))
+                              drop=sv["drop"]["out"], dcol=st.g(pre + "linear2.bias"))
+        self._wgrad(dy, sv["u"], st.g(pre + "linear2.weight"), None)
         du = self._empty(N, ff, dtype=BF16)
         ops.gemm(dy, st.w(pre + "linear2.weight"), du, b_mn_major=True)
         dhff = self._empty(N, 2 * ff, dtype=BF16)
@@ -420,7 +421,7 @@ class AcousticEngine:
         dx = self._empty(N, D)
         dx_bf = self._empty(N, D, dtype=BF16)
         ops.layernorm_bwd(dh, sv["x"], sv["mean"], sv["rstd"], st.p(norm + "weight"), dout, dx, dx_bf,
-                          st.g(norm + "weight"), st.g(norm + "bias"), drop_bf16=next_drop)
+                          st.g(norm + "weight"), st.g(norm + "bias"), drop_bf16=next_drop, dcol_bf16=next_dbias)
         return dx, dx_bf
 
     # ------------------------------------------------------------------------------------------
@@ -711,9 +712,9 @@ class AcousticEngine:
                 pre = f"transformer_encoder_layers.{i}."
                 s1, s2 = ctx["enc_saved"][i]
                 dx, dx_bf = self._ffn_bwd(pre + "ff.", dx, pre + "norm2.", cfg.encoder_ff_dim, s2,
-                                          next_drop=s1["drop"]["out"])
+                                          next_drop=s1["drop"]["out"], next_dbias=st.g(pre + "self_attn.w_o.bias"))
                 dx, dx_bf = self._attn_bwd(pre + "self_attn.", dx, dx_bf, B, P, pre + "norm1.", False,
-                                           ctx["text_pad"], None, P, s1, None, False)
+                                           ctx["text_pad"], None, P, s1, None, False, bias_done=True)
             ops.embed_bwd(dx, ctx["idx"], ctx["stress"], st.g("text_embedding.weight"),
                           st.g("stress_embedding.weight"), drop=ctx["drop_pe"])
         # (iii) pitch / energy losses -> their predictors only (input is the detached expansion)
@@ -737,17 +738,19 @@ class AcousticEngine:
             pre = f"decoder.layers.{i}."
             s1, s2, s3 = ctx["dec_saved"][i]
             dy, dy_bf = self._ffn_bwd(pre + "ff.", dy, pre + "norm3.", cfg.decoder_ff_dim, s3,
-                                      next_drop=s2["drop"]["out"])
+                                      next_drop=s2["drop"]["out"], next_dbias=st.g(pre + "cross_attn.w_o.bias"))
             dy, dy_bf = self._attn_bwd(pre + "cross_attn.", dy, dy_bf, B, T, pre + "norm2.", False, ctx["fmask_t"],
-                                       ctx["mem"], T, s2, dmem, first, next_drop=s1["drop"]["out"])
+                                       ctx["mem"], T, s2, dmem, first, next_drop=s1["drop"]["out"],
+                                       next_dbias=st.g(pre + "self_attn.w_o.bias"), bias_done=True)
             first = False
             # layer 0: the bf16 copy feeds mel_projection_in's weight gradient through both input dropouts
             dy, dy_bf = self._attn_bwd(pre + "self_attn.", dy, dy_bf, B, T, pre + "norm1.", True, None, None, T,
-                                       s1, None, False, next_drop=ctx["drop_in"] if i == 0 else None)
+                                       s1, None, False, next_drop=ctx["drop_in"] if i == 0 else None,
+                                       next_dbias=st.g("mel_projection_in.bias") if i == 0 else None, bias_done=True)
             if split_layer is not None and i == split_layer and i > 0:
                 self._join_all()
                 yield
-        self._wgrad(dy_bf, ctx["melshift"], st.g("mel_projection_in.weight"), st.g("mel_projection_in.bias"))
+        self._wgrad(dy_bf, ctx["melshift"], st.g("mel_projection_in.weight"), None)   # bias: layer 0's layernorm_bwd
         self._join_all()
         # memory gradient (accumulated on the "kv" stream) reaches only the pitch / energy embedding rows
         if self.spec_spans is not None:

@@ -246,8 +246,8 @@ def attn_fwd(q, k, v, o, lse, key_mask: Optional[torch.Tensor], causal: bool, sc
 
 def attn_bwd(q, k, v, o, d_o, lse, delta, dq, dk, dv, key_mask, causal: bool, scale: float,
              drop: Optional[DropSpec] = None):
-    """Flash attention backward.  dq: fp32 [B,Sq,H,64] and must be ZEROED by the caller (atomic
-    accumulation); dk, dv: bf16 [B,Sk,H,64]; delta: fp32 scratch [B,H,Sq]."""
+    """Flash attention backward.  dq: fp32 [B,Sq,H,64] (zeroed by the call's own prep kernel, then atomically
+    accumulated); dk, dv: bf16 [B,Sk,H,64]; delta: fp32 scratch [B,H,Sq]."""
     B, Sq, H, _ = q.shape
     Sk = k.shape[1]
     assert dq.dtype == torch.float32 and dq.stride(3) == 1 and dq.stride(2) == 64
@@ -269,13 +269,15 @@ def layernorm_fwd(x, gamma, beta, y_bf16, y_f32, mean, rstd, eps: float = 1e-5):
                                  _ptr(rstd), c_int(N), c_int(D), c_float(eps), _stream()), "kr_layernorm_fwd")
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, dx_bf16, dgamma, dbeta, drop_bf16: Optional[DropSpec] = None):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, dx_bf16, dgamma, dbeta, drop_bf16: Optional[DropSpec] = None,
+                  dcol_bf16: Optional[torch.Tensor] = None):
     """drop_bf16: dropout / stochastic-depth factors applied to the bf16 copy only (it feeds the backward of
-    the dropped residual branch that precedes this norm; dx itself is the residual-stream gradient)."""
+    the dropped residual branch that precedes this norm; dx itself is the residual-stream gradient).
+    dcol_bf16 [D] += column sums of that bf16 copy: the bias gradient of the Linear whose backward it enters."""
     N, D = x.shape
     check(lib().kr_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres), _ptr(dx),
                                  _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), c_int(N), c_int(D), _dref(drop_bf16),
-                                 _stream()),
+                                 _ptr(dcol_bf16), _stream()),
           "kr_layernorm_bwd")
 
 
@@ -286,10 +288,12 @@ def rmsnorm_resid_fwd(y, gain, resid, out, drop: Optional[DropSpec] = None):
           "kr_rmsnorm_resid_fwd")
 
 
-def rmsnorm_resid_bwd(dout, y, gain, dy_bf16, dgain, drop: Optional[DropSpec] = None):
+def rmsnorm_resid_bwd(dout, y, gain, dy_bf16, dgain, drop: Optional[DropSpec] = None,
+                      dcol: Optional[torch.Tensor] = None):
+    """dcol [D] += column sums of dy (the bias gradient of the Linear that produced y)."""
     N, D = y.shape
     check(lib().kr_rmsnorm_resid_bwd(_ptr(dout), _ptr(y), _ptr(gain), _ptr(dy_bf16), _ptr(dgain), c_int(N),
-                                     c_int(D), _dref(drop), _stream()), "kr_rmsnorm_resid_bwd")
+                                     c_int(D), _dref(drop), _ptr(dcol), _stream()), "kr_rmsnorm_resid_bwd")
 
 
 def _parts3(ts):

@@ -50,7 +50,7 @@ def test_attention_fwd_bwd(B, H, Sq, Sk, causal, masked):
     err = (o.float() - ref).abs().max().item()
     assert err < 3e-2, f"fwd err {err}"
     ref.backward(d_o.float())
-    dq = torch.zeros(B, Sq, H, 64, device="cuda")
+    dq = torch.randn(B, Sq, H, 64, device="cuda")      # kr_attn_bwd zeroes it itself
     dk, dv = torch.empty_like(k), torch.empty_like(v)
     delta = torch.empty(B, H, Sq, device="cuda")
     ops.attn_bwd(q, k, v, o, d_o, lse, delta, dq, dk, dv, key_mask, causal, scale)

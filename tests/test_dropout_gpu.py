@@ -65,7 +65,7 @@ def test_attention_dropout_matches_exported_mask(causal):
     o = torch.empty_like(q)
     lse = torch.empty(B, H, Sq, device="cuda")
     ops.attn_fwd(q, k, v, o, lse, key_mask, causal, 0.125, drop=spec)
-    dq = torch.zeros(B, Sq, H, 64, device="cuda")
+    dq = torch.randn(B, Sq, H, 64, device="cuda")      # kr_attn_bwd zeroes it itself
     dk, dv = torch.empty_like(k), torch.empty_like(v)
     delta = torch.empty(B, H, Sq, device="cuda")
     ops.attn_bwd(q, k, v, o, d_o, lse, delta, dq, dk, dv, key_mask, causal, 0.125, drop=spec)

@@ -25,14 +25,14 @@ DOCS = {
     "kr_mel_stft": "Log-mel features out[B, n_mels, frames_max] = log(melfb(|STFT|^2) + log_eps): reflect pad 512, periodic Hann 1024, hop 256, 513 bins, dense filterbank fb_t[n_mels, 513] (HTK, norm=None); frames beyond 1 + len//256 are zero. Replaces torchaudio.transforms.MelSpectrogram + log of data/dataset.py:162-178,694-697.",
     "kr_spec_augment": "SpecAugment on the cross-attention memory (bf16) or its gradient (fp32): zeroes the per-sample frame / hidden-dim spans in spans[B, n_time+n_feat, 2] = (start, length). training/trainer.py:1578-1604, applied at model/model.py:636-639.",
     "kr_attn_fwd": "tcgen05 flash attention forward, head_dim 64, on token-major [B,S,H,64] bf16 tensors (q_ss/q_bs = seq/batch strides in elements). Causal and per-key padding (key_mask[B,Sk], 1 = masked) are predicates; lse[B,H,Sq] is the log2-domain log-sum-exp kept for the backward. Replaces F.scaled_dot_product_attention with the dense additive mask, model/transformers.py:299-316,393-398.",
-    "kr_attn_bwd": "Flash attention backward: dq (fp32 [B,Sq,H,64], zeroed by the caller, atomically accumulated), dk/dv (bf16). delta[B,H,Sq] is scratch. Autograd of model/transformers.py:393-398.",
+    "kr_attn_bwd": "Flash attention backward: dq (fp32 [B,Sq,H,64], zeroed by the call's own prep kernel, then atomically accumulated), dk/dv (bf16). delta[B,H,Sq] is scratch. Autograd of model/transformers.py:393-398.",
     "kr_stop_head_fwd": "Stop-token logits z[n] = x[n,:].w + b on the (detached) decoder output, model/model.py:562.",
     "kr_stop_head_bwd": "Weight/bias gradient of the stop head (no data gradient: the input is detached, model/model.py:562).",
     "kr_losses_fwd_bwd": "Fused masked losses + gradients w.r.t. the five model outputs: L1 mel, Huber(1) log1p-duration, BCE-with-logits(pos_weight) stop, Huber(delta_var) pitch/energy, clamps 100/100/100/10/10, weighted total; losses[6] = total, mel, dur, stop, pitch, energy. training/losses.py:9-216, criteria training/trainer.py:410-444.",
     "kr_layernorm_fwd": "LayerNorm over the last dim (D in {128,256,512}), fp32 in, bf16 and/or fp32 out, saves mean/rstd. model/transformers.py:478,485,564,572,581,660; model/model.py:122.",
-    "kr_layernorm_bwd": "LayerNorm backward fused with the residual-gradient add (dx = dres + ...), optional bf16 copy of dx, dgamma/dbeta accumulated with atomics.",
+    "kr_layernorm_bwd": "LayerNorm backward fused with the residual-gradient add (dx = dres + ...), optional bf16 copy of dx (with the dropout / stochastic-depth factors of the residual branch it feeds, and its column sums = that branch's output-bias gradient accumulated into dcol_bf16), dgamma/dbeta accumulated with atomics.",
     "kr_rmsnorm_resid_fwd": "FFN output RMSNorm(eps = fp32 finfo.eps) + residual add, model/transformers.py:94,109-111.",
-    "kr_rmsnorm_resid_bwd": "Backward of kr_rmsnorm_resid_fwd w.r.t. y (bf16) and the gain.",
+    "kr_rmsnorm_resid_bwd": "Backward of kr_rmsnorm_resid_fwd w.r.t. y (bf16) and the gain; dcol += column sums of dy (bias gradient of linear2).",
     "kr_qkv_prep_fwd": "Per-head RMSNorm(64) with learned gain on up to three column blocks (q|k|v) + rotate-half RoPE on the blocks selected by rope_mask; position = row % S. model/transformers.py:145-148,260-272; model/positional_encoding.py:196-209.",
     "kr_qkv_prep_bwd": "Backward of kr_qkv_prep_fwd: incoming gradients may be fp32 (grad_f32_mask) or bf16; writes d(raw projection) bf16 and accumulates the gain gradients.",
     "kr_optim_ctrl_size": "sizeof the device-resident optimizer control block (64 bytes; layout in kokoro_ruslan_b200/optim.py CTRL_FIELDS).",
