@@ -22,8 +22,11 @@ constexpr int WARPS = 8;
 // ---------------------------------------------------------------------------------------------
 // length regulator
 // ---------------------------------------------------------------------------------------------
-__global__ void lr_index_kernel(const long long* __restrict__ dur, int* __restrict__ idx,
-                                int* __restrict__ lengths, int P, int Tp) {
+// pad_mask == nullptr: LengthRegulator semantics (durations clamped at 0, utils/lengths.py:38-41).
+// pad_mask != nullptr: the `length_regulate` fallback (utils/lengths.py:108-153): padded tokens are skipped and
+// every remaining duration is clamped to >= 1.
+__global__ void lr_index_kernel(const long long* __restrict__ dur, const unsigned char* __restrict__ pad_mask,
+                                int* __restrict__ idx, int* __restrict__ lengths, int P, int Tp) {
   kr::pdl_entry();
   extern __shared__ int cs[];  // P ints (double-buffered scan: 2*P)
   const int b = blockIdx.x;
@@ -31,7 +34,8 @@ __global__ void lr_index_kernel(const long long* __restrict__ dur, int* __restri
   int* t = cs + P;
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
     const long long d = dur[(long long)b * P + i];
-    a[i] = d > 0 ? (int)d : 0;
+    if (pad_mask != nullptr) a[i] = pad_mask[(long long)b * P + i] ? 0 : (d > 1 ? (int)d : 1);
+    else a[i] = d > 0 ? (int)d : 0;
   }
   __syncthreads();
   for (int off = 1; off < P; off <<= 1) {
@@ -52,6 +56,51 @@ __global__ void lr_index_kernel(const long long* __restrict__ dur, int* __restri
       r = lo;
     }
     idx[(long long)b * Tp + f] = r;
+  }
+}
+
+// out[b, f, :] = x[b, idx[b, f], :] (0 where idx < 0); mask[b, f] = idx < 0   (fp32, exact copy)
+__global__ void expand_rows_kernel(const float* __restrict__ x, const int* __restrict__ idx, float* __restrict__ out,
+                                   unsigned char* __restrict__ mask, int B, int P, int Tp, int D) {
+  kr::pdl_entry();
+  const int lane = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < (long long)B * Tp;
+       r += (long long)gridDim.x * WARPS) {
+    const int b = (int)(r / Tp);
+    const int j = idx[r];
+    if (lane == 0 && mask != nullptr) mask[r] = j < 0 ? 1 : 0;
+    const float4* src = j >= 0 ? reinterpret_cast<const float4*>(x + ((long long)b * P + j) * D) : nullptr;
+    float4* dst = reinterpret_cast<float4*>(out + r * D);
+    for (int c = lane; c < D / 4; c += 32) dst[c] = src != nullptr ? src[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// dx[b, j, :] = sum over the frames f with idx[b, f] == j of dout[b, f, :]: frames of a token are one contiguous
+// run, found by binary search in the (sorted) index row -> deterministic segment sums, no atomics.
+__global__ void expand_rows_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ idx,
+                                       const int* __restrict__ lengths, float* __restrict__ dx, int B, int P, int Tp,
+                                       int D) {
+  kr::pdl_entry();
+  const int lane = threadIdx.x & 31;
+  for (long long t = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); t < (long long)B * P;
+       t += (long long)gridDim.x * WARPS) {
+    const int b = (int)(t / P), j = (int)(t % P);
+    const int* row = idx + (long long)b * Tp;
+    const int L = min(lengths[b], Tp);
+    int lo = 0, hi = L;                     // first f with row[f] >= j
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (row[mid] >= j) hi = mid; else lo = mid + 1; }
+    const int f0 = lo;
+    hi = L;                                 // first f with row[f] > j
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (row[mid] > j) hi = mid; else lo = mid + 1; }
+    const int f1 = lo;
+    for (int c = lane; c < D / 4; c += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int f = f0; f < f1; ++f) {
+        const float4 v = *reinterpret_cast<const float4*>(dout + ((long long)b * Tp + f) * D + 4 * c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(dx + t * D + 4 * c) = acc;
+    }
   }
 }
 
@@ -389,7 +438,39 @@ inline int warp_blocks(long long rows, int cap_mult = 8) {
 extern "C" int kr_lr_index(const long long* dur, int* idx, int* lengths, int B, int P, int Tp, void* stream) {
   if (B <= 0) return KR_OK;
   if (P > 4096) { kr_set_error("kr_lr_index: P > 4096 unsupported"); return KR_ERR_UNSUPPORTED; }
-  kr::launch(lr_index_kernel, B, 256, 2 * P * sizeof(int), (cudaStream_t)stream, dur, idx, lengths, P, Tp);
+  kr::launch(lr_index_kernel, B, 256, 2 * P * sizeof(int), (cudaStream_t)stream, dur, (const unsigned char*)nullptr, idx,
+             lengths, P, Tp);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+extern "C" int kr_lr_index_masked(const long long* dur, const unsigned char* pad_mask, int* idx, int* lengths, int B,
+                                  int P, int Tp, void* stream) {
+  if (B <= 0) return KR_OK;
+  if (P > 4096 || pad_mask == nullptr) { kr_set_error("kr_lr_index_masked: P <= 4096 and a padding mask are required"); return KR_ERR_ARG; }
+  kr::launch(lr_index_kernel, B, 256, 2 * P * sizeof(int), (cudaStream_t)stream, dur, pad_mask, idx, lengths, P, Tp);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+extern "C" int kr_expand_rows_fwd(const float* x, const int* idx, float* out, unsigned char* frame_mask, int B, int P,
+                                  int Tp, int D, void* stream) {
+  if (B <= 0 || Tp <= 0) return KR_OK;
+  if (D % 4) { kr_set_error("kr_expand_rows: D % 4 == 0 required"); return KR_ERR_ARG; }
+  long long nb = ((long long)B * Tp + WARPS - 1) / WARPS;
+  if (nb > kNumSMs * 16) nb = kNumSMs * 16;
+  kr::launch(expand_rows_kernel, (int)nb, WARPS * 32, 0, (cudaStream_t)stream, x, idx, out, frame_mask, B, P, Tp, D);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+extern "C" int kr_expand_rows_bwd(const float* dout, const int* idx, const int* lengths, float* dx, int B, int P, int Tp,
+                                  int D, void* stream) {
+  if (B <= 0 || P <= 0) return KR_OK;
+  if (D % 4) { kr_set_error("kr_expand_rows: D % 4 == 0 required"); return KR_ERR_ARG; }
+  long long nb = ((long long)B * P + WARPS - 1) / WARPS;
+  if (nb > kNumSMs * 16) nb = kNumSMs * 16;
+  kr::launch(expand_rows_bwd_kernel, (int)nb, WARPS * 32, 0, (cudaStream_t)stream, dout, idx, lengths, dx, B, P, Tp, D);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -392,6 +392,26 @@ def lr_index(dur, idx, lengths):
                             _stream()), "kr_lr_index")
 
 
+def lr_index_masked(dur, pad_mask, idx, lengths):
+    """`length_regulate` fallback indices (reference utils/lengths.py:108-153)."""
+    B, P = dur.shape
+    assert pad_mask.dtype == torch.uint8 and pad_mask.shape == dur.shape
+    check(lib().kr_lr_index_masked(_ptr(dur), _ptr(pad_mask), _ptr(idx), _ptr(lengths), c_int(B), c_int(P),
+                                   c_int(idx.shape[1]), _stream()), "kr_lr_index_masked")
+
+
+def expand_rows_fwd(x, idx, out, frame_mask):
+    B, P, D = x.shape
+    check(lib().kr_expand_rows_fwd(_ptr(x), _ptr(idx), _ptr(out), _ptr(frame_mask), c_int(B), c_int(P),
+                                   c_int(idx.shape[1]), c_int(D), _stream()), "kr_expand_rows_fwd")
+
+
+def expand_rows_bwd(dout, idx, lengths, dx):
+    B, P, D = dx.shape
+    check(lib().kr_expand_rows_bwd(_ptr(dout), _ptr(idx), _ptr(lengths), _ptr(dx), c_int(B), c_int(P),
+                                   c_int(idx.shape[1]), c_int(D), _stream()), "kr_expand_rows_bwd")
+
+
 def range_flag(x, flag):
     check(lib().kr_range_flag(_ptr(x), c_ll(x.numel()), _ptr(flag), _stream()), "kr_range_flag")
 

@@ -399,6 +399,34 @@ class TrainStep:
             self.launches_last_step += self._opt_launches + (1 if self.world > 1 else 0)
         return losses
 
+    @torch.no_grad()
+    def eval_losses(self, batch: Dict[str, torch.Tensor], use_ema: bool = True) -> torch.Tensor:
+        """Validation forward (reference trainer.py:1771-1985, validate_epoch): the model in eval() mode — dropout and
+        stochastic depth off, SpecAugment off — evaluated with the EMA weights (`use_ema`, trainer.py:1790-1806), returns
+        the un-scaled losses[6] of the batch.  Gradients, optimizer state and the RNG step are left untouched.  Eager
+        (validation runs once per epoch); the bf16 operand copy of the EMA weights is a scratch buffer."""
+        eng, st = self.engine, self.engine.store
+        batch = self._cap(batch)
+        dev = {k: batch[k].to(self.device, non_blocking=True) for k in BATCH_KEYS}
+        dur = batch["phoneme_durations"]
+        Tp = max(3, int(dur.clamp(min=0).sum(dim=1).max()))
+        saved = (st.params, st.shadow, eng.training, eng.spec_spans)
+        try:
+            if use_ema and st.ema is not None:
+                if getattr(self, "_ema_shadow", None) is None:
+                    self._ema_shadow = torch.empty_like(st.shadow)
+                from . import ops
+                ops.cast_bf16(st.ema, self._ema_shadow)
+                st.params, st.shadow = st.ema, self._ema_shadow
+            eng.training, eng.spec_spans = False, None
+            outs, _ = eng.forward(dev["phoneme_indices"], dev["mel_specs"], dev["phoneme_durations"], dev["pitches"],
+                                  dev["energies"], dev["stress_indices"], expanded_len=Tp)
+            losses, _ = eng.losses(outs, dev["mel_specs"], dev["phoneme_durations"], dev["stop_token_targets"],
+                                   dev["pitches"], dev["energies"], dev["mel_lengths"], dev["phoneme_lengths"])
+            return losses.clone()
+        finally:
+            st.params, st.shadow, eng.training, eng.spec_spans = saved
+
     def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         """Full optimizer step on one micro-batch (gradient_accumulation_steps = 1)."""
         return self.micro_step(batch, True, True, 1)

@@ -127,3 +127,39 @@ def test_gradient_accumulation_window_matches_cpu_oracle(graphs):
         num += float((d_got - d_ref).pow(2).sum())
         den += float(d_ref.pow(2).sum())
     assert (num / den) ** 0.5 < 0.15, (num / den) ** 0.5
+
+
+def test_validation_forward_uses_ema_weights_and_no_dropout():
+    """eval_losses = the reference's validate_epoch forward: EMA weights, eval mode (trainer.py:1771-1824)."""
+    from oracle import acoustic as oa
+    from kokoro_ruslan_b200.engine import DropoutConfig
+    from kokoro_ruslan_b200.optim import OptimConfig
+    from kokoro_ruslan_b200.train_step import ScheduleConfig, TrainStep
+    ocfg, cfg = _tiny()
+    sd = oa.seeded_state_dict(ocfg, seed=0)
+    batch = oa.synthetic_batch(B=3, P=24, T=150, seed=11, ragged=True)
+    ts = TrainStep(cfg, OptimConfig(learning_rate=1e-3, ema_decay=0.5), ScheduleConfig(total_steps=100, use_warmup=False),
+                   device="cuda", use_graphs=True, dropout=DropoutConfig.reference_training())
+    ts.load_state_dict(sd)
+    for _ in range(3):
+        ts.train_step(batch)
+    rng_step = int(ts.engine.drop_state[1])
+    params_before = ts.store.params.clone()
+    got = [ts.eval_losses(batch, use_ema=e).cpu() for e in (True, False, True)]
+    assert torch.equal(got[0], got[2])                                  # deterministic: no dropout in eval
+    assert not torch.allclose(got[0], got[1], rtol=1e-4)                # EMA weights differ from the live weights
+    assert int(ts.engine.drop_state[1]) == rng_step and torch.equal(ts.store.params, params_before)
+    for use_ema, g in zip((True, False), got[:2]):
+        buf = ts.store.ema if use_ema else ts.store.params
+        wsd = {k: v.float().cpu() for k, v in ts.store.state_dict(buf).items()}
+        for k in oa.BUFFER_KEYS:
+            wsd[k] = sd[k]
+        outs = oa.forward_training(wsd, ocfg, batch["phoneme_indices"], batch["mel_specs"], batch["phoneme_durations"],
+                                   batch["pitches"], batch["energies"], batch["stress_indices"])
+        want = oa.training_losses(ocfg, outs, batch["mel_specs"], batch["phoneme_durations"],
+                                  batch["stop_token_targets"], batch["pitches"], batch["energies"],
+                                  batch["mel_lengths"], batch["phoneme_lengths"])
+        want = torch.tensor([float(x) for x in want])
+        assert torch.allclose(g, want, rtol=1.5e-2, atol=1e-4), (use_ema, g, want)
+    ts.train_step(batch)                                                # training continues normally afterwards
+    assert int(ts.engine.drop_state[1]) == rng_step + 1

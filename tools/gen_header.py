@@ -52,6 +52,9 @@ DOCS = {
     "kr_eq_mask_i64": "Byte mask idx == value: the reference text padding mask `phoneme_indices == 0`, model/model.py:586-587.",
     "kr_nonfinite_flag": "Sets `bit` in *flag if x holds a NaN/Inf — the finite-output guard of training/trainer.py:3233-3256 without host syncs.",
     "kr_lr_index": "LengthRegulator index tensor: idx[b,f] = min{j : cumsum(max(0,d))[b,j] > f} for f < L[b], else -1; lengths[b] = L[b]. Bit-exact restatement of utils/lengths.py:16-96 (repeat_interleave + scatter on the CPU in the reference).",
+    "kr_lr_index_masked": "Index tensor of the `length_regulate` fallback (use_variance_predictor=False path, utils/lengths.py:108-153): padded tokens (pad_mask = 1) are skipped, every other duration is clamped to >= 1; lengths[b] = expanded length.",
+    "kr_expand_rows_fwd": "Duration-expand gather out[b,f,:] = x[b, idx[b,f], :] (zeros and frame_mask = 1 where idx < 0), exact fp32 copy: torch.repeat_interleave + left-packed scatter of utils/lengths.py:139-147.",
+    "kr_expand_rows_bwd": "Backward of the gather: deterministic segment sums dx[b,j,:] = sum of dout over the frames of token j (the fallback path keeps autograd, unlike the detached LengthRegulator).",
     "kr_range_flag": "flag |= any(x > 1 or x < 0): the data-dependent normalisation test of model/variance_predictor.py:244,268.",
     "kr_expand_adapt": "Duration-expand gather + pitch/energy bucketize(255 bins) + embedding add + frame masks; writes the predictor input (padded layout) and the decoder memory aligned to the mel length. model/variance_predictor.py:345-437, model/model.py:607-628.",
     "kr_adapt_bwd": "Memory gradient -> pitch/energy embedding rows (the only path through the detached expansion, utils/lengths.py:30).",
