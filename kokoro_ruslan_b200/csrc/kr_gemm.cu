@@ -142,7 +142,10 @@ __device__ __noinline__ void epi_chunk_scalar(const GemmParams& p, const float* 
 
 // BK = 64: 128-byte swizzled K blocks (everything).  BK = 32: 64-byte swizzled K blocks, K-major operands only —
 // the 32-channel HiFi-GAN stage, whose K blocks would otherwise be half zero padding.
-template <int BLOCK_N, bool A_MN, bool B_MN, int BK = BLOCK_K>
+// DROP = the dropout epilogue is compiled in (K-major operands only): a template parameter, not a runtime branch,
+// because the epilogue's instruction footprint matters (an earlier 240 KB kernel thrashed the instruction cache, and
+// the runtime-branch version of the dropout code cost the HiFi-GAN convs 8 % although they never take it).
+template <int BLOCK_N, bool A_MN, bool B_MN, int BK = BLOCK_K, bool DROP = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
@@ -352,10 +355,10 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool use_bias = p.bias != nullptr && first_split;
       const bool use_resid = p.resid != nullptr && first_split;
       // dropout epilogue (attention out-projection): per-row stochastic-depth factors of this lane's 8 rows
-      const bool use_drop = p.drop.state != nullptr;
+      constexpr bool use_drop = DROP;
       DropCtx dc{};
       float rowf[8];
-      if (use_drop) {
+      if (DROP) {
         dc = drop_ctx(p.drop);
 #pragma unroll
         for (int i = 0; i < 8; ++i) rowf[i] = drop_row_scale(p.drop, min(mw0 + (lane >> 3) + 4 * i, p.M - 1));
@@ -505,11 +508,11 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int BK = BLOCK_K>
+template <int BLOCK_N, bool A_MN, bool B_MN, int BK = BLOCK_K, bool DROP = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta_slab, const CUtensorMap& tb, GemmParams p, bool want_resident,
                 int want_slab_rows, cudaStream_t st) {
   using L = SmemLayout<BLOCK_N, BK>;
-  auto kern = kr_gemm_kernel<BLOCK_N, A_MN, B_MN, BK>;
+  auto kern = kr_gemm_kernel<BLOCK_N, A_MN, B_MN, BK, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL + 1024);
@@ -544,6 +547,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta_slab, const CUtenso
 template <int BLOCK_N>
 int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& ta_slab, const CUtensorMap& tb,
                    const GemmParams& p, bool res, int slab_rows, cudaStream_t st) {
+  if (!a_mn && !b_mn && p.drop.state != nullptr)
+    return launch_gemm<BLOCK_N, false, false, BLOCK_K, true>(ta, ta_slab, tb, p, res, slab_rows, st);
   if (!a_mn && !b_mn) return launch_gemm<BLOCK_N, false, false>(ta, ta_slab, tb, p, res, slab_rows, st);
   if (!a_mn && b_mn) return launch_gemm<BLOCK_N, false, true>(ta, ta_slab, tb, p, res, 0, st);
   if (a_mn && !b_mn) return launch_gemm<BLOCK_N, true, false>(ta, ta_slab, tb, p, res, 0, st);
@@ -699,8 +704,9 @@ extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
   p.alpha = a->alpha; p.beta = a->beta;
   p.b_shared = b_shared ? 1 : 0;
   p.drop = kr_drop_to_device(a->drop);
-  if (p.drop.state != nullptr && (batch != 1 || splits != 1 || (N & 3) || (a->ldc & 3) || (a->ldr & 3))) {
-    kr_set_error("kr_gemm_ex: the dropout epilogue needs batch == 1, no split-K and N / leading dimensions % 4 == 0");
+  if (p.drop.state != nullptr && (batch != 1 || splits != 1 || (N & 3) || (a->ldc & 3) || (a->ldr & 3) ||
+                                  a->a_mn_major || a->b_mn_major || conv)) {
+    kr_set_error("kr_gemm_ex: the dropout epilogue needs a plain K-major GEMM, batch == 1, no split-K and N / leading dimensions % 4 == 0");
     return KR_ERR_ARG;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
