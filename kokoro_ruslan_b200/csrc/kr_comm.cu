@@ -163,17 +163,23 @@ __global__ void __launch_bounds__(AR_THREADS) chunk_sqnorm_kernel(const float* _
   if (threadIdx.x == 0) sq_chunk[c] = s;
 }
 
-// sq[t] = sum of the chunk sums of tensor t, in chunk order (deterministic, identical on every replica);
+// sq[t] = sum of the chunk sums of tensor t in a fixed order (deterministic, identical on every replica);
 // a non-finite sum raises the control block's non-finite flag (word `nonfinite_word`).
 __global__ void chunk_to_tensor_kernel(const float* __restrict__ sq_chunk, const int* __restrict__ first_chunk,
                                        float* __restrict__ sq, int n_tensors, int* ctrl_nonfinite) {
   kr::pdl_entry();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per tensor: lane l sums chunks l, l+32, ... in order, then a fixed shuffle tree -> the same bits on
+  // every replica and every run
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (t >= n_tensors) return;
   float s = 0.f;
-  for (int c = first_chunk[t]; c < first_chunk[t + 1]; ++c) s += sq_chunk[c];
-  sq[t] = s;
-  if (!isfinite(s)) atomicExch(ctrl_nonfinite, 1);
+  for (int c = first_chunk[t] + lane; c < first_chunk[t + 1]; c += 32) s += sq_chunk[c];
+  s = warp_sum(s);
+  if (lane == 0) {
+    sq[t] = s;
+    if (!isfinite(s)) atomicExch(ctrl_nonfinite, 1);
+  }
 }
 
 }  // namespace
@@ -210,7 +216,7 @@ extern "C" int kr_chunk_to_tensor_sq(const float* sq_chunk, const int* first_chu
                                      void* ctrl, void* stream) {
   if (n_tensors <= 0) return KR_OK;
   int* nonfinite = reinterpret_cast<int*>(ctrl) + 10;      // Ctrl::nonfinite (kr_optim.cu)
-  kr::launch(chunk_to_tensor_kernel, (n_tensors + 127) / 128, 128, 0, (cudaStream_t)stream, sq_chunk, first_chunk, sq,
+  kr::launch(chunk_to_tensor_kernel, (n_tensors + 7) / 8, 256, 0, (cudaStream_t)stream, sq_chunk, first_chunk, sq,
              n_tensors, nonfinite);
   KR_CHECK_LAUNCH();
   return KR_OK;
