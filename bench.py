@@ -379,12 +379,12 @@ def run_ours(args):
 
     # ---- measured DRAM traffic of the dominant kernel (ncu capture of this command, profiles/) -------------
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_step_traffic_v3.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01_step_traffic_v4.json")) as f:
             tr = json.load(f)["kr_gemm_kernel"]
         if roof is not None and "error" not in roof:
             roof["traffic"] = tr["traffic_per_launch"]
             roof["traffic_note"] = ("mean dram__bytes_read+write per kr_gemm_kernel launch, ncu --clock-control none on "
-                                    "tools/one_step.py (profiles/r01_step_traffic_v3.txt); algorithmic bytes per launch = "
+                                    "tools/one_step.py (profiles/r01_step_traffic_v4.txt); algorithmic bytes per launch = "
                                     "%.1f MB" % (sum(r["bytes"] for r in rows if r["op"].startswith("gemm")) / max(1, g_n) / 1e6))
     except Exception:
         pass
