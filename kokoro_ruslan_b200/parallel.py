@@ -41,6 +41,20 @@ def all_reduce_gradients(flat_grads: torch.Tensor, group=None) -> torch.Tensor:
     return flat_grads
 
 
+def symmetric_memory_usable(group, device) -> bool:
+    """True on every rank iff every rank can allocate and rendezvous a symmetric-memory buffer (collective call)."""
+    ok = 1
+    try:
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty(1024, dtype=torch.float32, device=device)
+        symm.rendezvous(t, group)
+    except Exception:        # noqa: BLE001 — any failure means "not usable here"
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(flag.item()))
+
+
 class SymmetricGradReducer:
     """The step's collective as ONE hand-written kernel over NVLink / NVSwitch peer memory
     (csrc/kr_comm.cu): all-reduce of the flat gradient buffer fused with the optimizer's per-chunk

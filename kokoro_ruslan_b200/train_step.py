@@ -178,9 +178,16 @@ class TrainStep:
         if self.world > 1:
             self.comm = os.environ.get("KR_COMM", "fused")
             if self.comm == "fused":
-                from .parallel import SymmetricGradReducer
-                self.reducer = SymmetricGradReducer(self.engine.store, self.opt, process_group)
-                self.split_layer = None           # nothing to overlap: the kernel needs the whole buffer
+                from .parallel import SymmetricGradReducer, symmetric_memory_usable
+                # every rank must take the same branch: agree on availability first (a box without peer access /
+                # symmetric-memory support falls back to the NCCL all-reduce — still a GPU collective, never a CPU path)
+                if symmetric_memory_usable(process_group, self.device):
+                    self.reducer = SymmetricGradReducer(self.engine.store, self.opt, process_group)
+                    self.split_layer = None       # nothing to overlap: the kernel needs the whole buffer
+                else:
+                    import sys
+                    print("kokoro_ruslan_b200: symmetric memory unavailable, using the NCCL all-reduce", file=sys.stderr)
+                    self.comm = "nccl"
         self.max_seq_cap = max_seq_cap
         # every cached batch shape pins its static input buffers and (once captured) a graph with ~4 GB of
         # activations at the bench shape: dynamic batching produces many shapes, so the cache is LRU-bounded
