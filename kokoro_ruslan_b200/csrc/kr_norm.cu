@@ -429,8 +429,20 @@ int norm_minb() {
   if (v < 0) { const char* e = getenv("KR_NORM_MINB"); v = (e != nullptr && e[0] == '3') ? 3 : 2; }
   return v;
 }
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e != nullptr && e[0] >= '0' && e[0] <= '9') ? atoi(e) : dflt;
+}
 int row_blocks(int N) { return (N + WARPS - 1) / WARPS; }
-int persistent_blocks(int N) { return min(row_blocks(N), kNumSMs * 4); }
+// blocks per SM of the persistent backward kernels (their column-gradient epilogue costs D atomics per block)
+int persistent_blocks(int N) {
+  static int per_sm = env_int("KR_NORM_BLOCKS_PER_SM", 2);   // tools/norm_sweep.sh: 2 beats 1 and 4 (ln_bwd 9.1 vs 10.7 us)
+  return min(row_blocks(N), kNumSMs * per_sm);
+}
+int prep_blocks_per_sm(bool bwd) {
+  static int f = env_int("KR_PREP_FWD_BLOCKS_PER_SM", 8), b = env_int("KR_PREP_BWD_BLOCKS_PER_SM", 2);   // 18.1 us vs 22.3 us at 6
+  return bwd ? b : f;
+}
 
 }  // namespace
 
@@ -515,7 +527,7 @@ extern "C" int kr_qkv_prep_fwd(const void* in0, const void* in1, const void* in2
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long total = ((long long)N * H + 7) / 8;
   const long long nb_ = (total + WARPS - 1) / WARPS;
-  const int per_part = kNumSMs * 8 / n_parts;
+  const int per_part = kNumSMs * prep_blocks_per_sm(false) / n_parts;
   const int blocks = (int)(nb_ < per_part ? nb_ : per_part);
   kr::launch(qkv_prep_fwd_kernel, dim3(blocks, n_parts), WARPS * 32, 0, st, p);
   KR_CHECK_LAUNCH();
@@ -547,7 +559,7 @@ extern "C" int kr_qkv_prep_bwd(const void* in0, const void* in1, const void* in2
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long total = ((long long)N * H + 7) / 8;
   const long long nb_ = (total + WARPS - 1) / WARPS;
-  const int per_part = kNumSMs * 6 / n_parts;
+  const int per_part = kNumSMs * prep_blocks_per_sm(true) / n_parts;
   const int blocks = (int)(nb_ < per_part ? nb_ : per_part);
   if (norm_minb() == 3) kr::launch(qkv_prep_bwd_kernel<3>, dim3(blocks, n_parts), WARPS * 32, 0, st, p);
   else                  kr::launch(qkv_prep_bwd_kernel<2>, dim3(blocks, n_parts), WARPS * 32, 0, st, p);
