@@ -787,13 +787,33 @@ class AcousticEngine:
         return spans
 
     def set_spec_augment(self, spans: Optional[torch.Tensor], n_time: int = 1, n_feat: int = 2) -> None:
-        """spans: host or device int32 [B, n_time + n_feat, 2], or None to disable."""
+        """spans: host or device int32 [B, n_time + n_feat, 2], or None to disable.  The device copy lives in ONE
+        buffer per span-table shape that is never re-allocated: captured CUDA graphs (which are keyed by batch shape
+        and by whether SpecAugment is on, see TrainStep.stage) keep reading valid memory when batch sizes alternate."""
         if spans is None:
             self.spec_spans = None
             return
-        if self.spec_spans is None or self.spec_spans.shape != spans.shape:
-            self.spec_spans = torch.empty(spans.shape, dtype=torch.int32, device=self.device)
-        self.spec_spans.copy_(spans, non_blocking=True)
+        if not hasattr(self, "_spec_bufs"):
+            self._spec_bufs: Dict[Tuple[int, ...], torch.Tensor] = {}
+        key = tuple(spans.shape)
+        buf = self._spec_bufs.get(key)
+        if buf is None:
+            buf = torch.empty(spans.shape, dtype=torch.int32, device=self.device)
+            self._spec_bufs[key] = buf
+        if not spans.is_cuda:
+            # pinned staging ring: the async copy of step n must not see the host write of step n + 1
+            if not hasattr(self, "_spec_ring"):
+                self._spec_ring, self._spec_i = {}, 0
+            ring = self._spec_ring.get(key)
+            if ring is None:
+                ring = torch.empty((16,) + key, dtype=torch.int32).pin_memory()
+                self._spec_ring[key] = ring
+            slot = ring[self._spec_i % 16]
+            self._spec_i += 1
+            slot.copy_(spans.to(torch.int32))
+            spans = slot
+        buf.copy_(spans, non_blocking=True)
+        self.spec_spans = buf
         self.spec_n_time, self.spec_n_feat = n_time, n_feat
 
     def zero_grad(self):

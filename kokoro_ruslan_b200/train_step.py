@@ -16,7 +16,7 @@ scheduler) around the CUDA engine:
 There are no host synchronisations inside a step: the expanded length T' = max_b sum(d) and the
 long-sequence stabiliser are computed from the HOST copy of the batch before the H2D copy, the
 finite guards live in the device-side step control (non-finite gradients skip the step).
-Graphs are cached per (B, P, T, T') shape; unseen shapes run eagerly once (warm-up) and are then
+Graphs are cached per (B, P, T, T', SpecAugment on/off) key; unseen shapes run eagerly once (warm-up) and are then
 captured.
 """
 from __future__ import annotations
@@ -193,7 +193,7 @@ class TrainStep:
         # activations at the bench shape: dynamic batching produces many shapes, so the cache is LRU-bounded
         self.max_cached_shapes = max_cached_shapes
         self._tick = 0
-        self._staged: Dict[Tuple[int, int, int, int], _Staged] = {}
+        self._staged: Dict[Tuple[int, int, int, int, bool], _Staged] = {}
         self._opt_graph: Optional[torch.cuda.CUDAGraph] = None
         self._opt_warm = 0
         self._opt_launches = 0
@@ -236,7 +236,7 @@ class TrainStep:
             out["phoneme_lengths"] = batch["phoneme_lengths"].clamp(max=cap)
         return out
 
-    def stage(self, batch: Dict[str, torch.Tensor], divisor: int = 1) -> Tuple[_Staged, Tuple[int, int, int, int]]:
+    def stage(self, batch: Dict[str, torch.Tensor], divisor: int = 1) -> Tuple[_Staged, Tuple[int, int, int, int, bool]]:
         """Host-side prologue: shape key, stabiliser scalars, async H2D into the static buffers.
         divisor = the accumulation divisor of this micro-batch (trainer.py:2284-2294)."""
         batch = self._cap(batch)
@@ -254,7 +254,8 @@ class TrainStep:
         else:   # device-resident batch (bench `value` leg): caller guarantees sum(d) == T
             Tp, max_d = T, 0
         Tp = max(Tp, 3)
-        key = (B, P, T, Tp)
+        # SpecAugment adds kernels to the step: graphs with and without it are different graphs
+        key = (B, P, T, Tp, self.engine.spec_spans is not None)
         st = self._staged.get(key)
         self._tick += 1
         if st is None:

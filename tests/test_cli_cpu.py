@@ -1,0 +1,140 @@
+"""kokoro-train CLI surface and epoch loop, without a GPU: the parser is compared option by option with a fixture
+dumped from the live reference parser (tests/golden/make_golden_cli.py); the loop runs on a stub step object."""
+import argparse
+import json
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _rows(parser):
+    rows = []
+    for a in parser._actions:
+        if isinstance(a, argparse._HelpAction):
+            continue
+        rows.append({"options": sorted(a.option_strings), "dest": a.dest, "default": a.default,
+                     "type": getattr(a.type, "__name__", None), "action": type(a).__name__})
+    return rows
+
+
+def test_parser_has_every_reference_flag_with_the_same_default():
+    from kokoro_ruslan_b200.cli import build_parser
+    want = json.load(open(os.path.join(HERE, "golden", "cli_flags.json")))
+    mine = {tuple(r["options"]): r for r in _rows(build_parser())}
+    for r in want:
+        got = mine.get(tuple(r["options"]))
+        assert got is not None, f"missing reference flag {r['options']}"
+        assert (got["dest"], got["default"], got["type"], got["action"]) == (r["dest"], r["default"], r["type"], r["action"]), (got, r)
+    extra = {k for k in mine if list(k) not in [r["options"] for r in want]}
+    assert extra == {("--synthetic",), ("--seed",)}, extra
+
+
+def test_config_mapping_follows_the_reference_rules():
+    from kokoro_ruslan_b200.cli import build_parser, create_config_from_args
+    cfg = create_config_from_args(build_parser().parse_args([]))
+    assert (cfg.num_epochs, cfg.learning_rate, cfg.max_frames_per_batch, cfg.validation_split) == (30, 5e-5, 30000, 0.1)
+    assert cfg.gradient_accumulation_steps == 2 and cfg.use_dynamic_batching
+    cfg = create_config_from_args(build_parser().parse_args(
+        ["-c", "corp", "-o", "out", "-b", "1", "-e", "1", "-lr", "1e-4", "--no-validation", "--no-dynamic-batching",
+         "--max-frames", "8000", "--no-mfa"]))
+    assert (cfg.data_dir, cfg.output_dir, cfg.batch_size, cfg.num_epochs, cfg.learning_rate) == ("corp", "out", 1, 1, 1e-4)
+    assert cfg.validation_split == 0.0 and not cfg.use_dynamic_batching and cfg.max_frames_per_batch == 8000
+
+
+def test_accumulation_windows_use_the_exact_tail_divisor():
+    from kokoro_ruslan_b200.cli import accumulation_windows
+    assert accumulation_windows(5, 2) == [[0, 1], [2, 3], [4]]
+    assert accumulation_windows(4, 2) == [[0, 1], [2, 3]]
+    assert accumulation_windows(3, 1) == [[0], [1], [2]]
+    assert accumulation_windows(0, 2) == []
+
+
+class _StubEngine:
+    D = 512
+
+    def __init__(self):
+        self.spec_calls = []
+
+    def set_spec_augment(self, spans, n_time=1, n_feat=2):
+        self.spec_calls.append(None if spans is None else tuple(spans.shape))
+
+
+class _StubStep:
+    """TrainStep surface used by cli.train()."""
+
+    def __init__(self, val_curve):
+        self.engine = _StubEngine()
+        self.calls, self.evals, self.val_curve = [], 0, list(val_curve)
+        self.epoch_marker = 0
+        self.sched = type("S", (), {"current_optimizer_step": 0, "state_dict": lambda s: {"k": 1}})()
+        self.store = type("St", (), {"ema": None})()
+
+    def micro_step(self, batch, first=True, last=True, divisor=1):
+        self.calls.append((tuple(batch["mel_specs"].shape), first, last, divisor))
+        if last:
+            self.sched.current_optimizer_step += 1
+        return torch.tensor([2.0, 1.0, 0.5, 0.25, 0.1, 0.1])
+
+    def eval_losses(self, batch, use_ema=True):
+        v = self.val_curve[min(self.epoch_marker, len(self.val_curve) - 1)]
+        self.evals += 1
+        return torch.tensor([v, v, 0.0, 0.0, 0.0, 0.0])
+
+    def state_dict(self):
+        return {"w": torch.zeros(2)}
+
+
+def test_epoch_loop_windows_spec_augment_validation_and_early_stopping(tmp_path):
+    from kokoro_ruslan_b200 import cli
+    ds = cli.SyntheticDataset(24, seed=1, min_frames=60, max_frames=120)
+    train_ds, val_ds = cli.split_dataset(ds, 0.25, seed=3)
+    assert len(train_ds) == 18 and len(val_ds) == 6
+    cfg = cli.RunConfig(output_dir=str(tmp_path), num_epochs=10, max_frames_per_batch=400, min_batch_size=1,
+                        max_batch_size=4, early_stopping_patience=2, save_every=2)
+    step = _StubStep([1.0, 0.9, 0.95, 0.96, 0.97])
+    orig = step.eval_losses
+
+    logs = []
+
+    def log(s):
+        logs.append(s)
+        step.epoch_marker += 1
+    out = cli.train(cfg, train_ds, val_ds, step, log=log)
+    # val improves in epochs 1-2, then stalls: stop after 2 + patience epochs
+    assert len(out["history"]) == 4 and out["best_val_epoch"] == 1 and abs(out["best_val_loss"] - 0.9) < 1e-6
+    # every window starts with first=True, ends with last=True and carries its own length as divisor
+    i = 0
+    per_epoch = [h["batches"] for h in out["history"]]
+    for nb in per_epoch:
+        for win in cli.accumulation_windows(nb, 2):
+            for k, _ in enumerate(win):
+                shape, first, last, div = step.calls[i]
+                assert (first, last, div) == (k == 0, k == len(win) - 1, len(win))
+                assert shape[0] * shape[1] <= 400 or shape[0] == 1
+                i += 1
+    assert i == len(step.calls)
+    # SpecAugment off in epoch 0, on afterwards (trainer.py:2042-2055)
+    n0 = per_epoch[0]
+    assert all(c is None for c in step.engine.spec_calls[:n0]) and all(c is not None for c in step.engine.spec_calls[n0:])
+    # checkpoints: improvements (epochs 1, 2) + save_every (2, 4), reference file names and keys
+    names = sorted(os.path.basename(p) for p in set(out["checkpoints"]))
+    assert names == ["checkpoint_epoch_1.pth", "checkpoint_epoch_2.pth", "checkpoint_epoch_4.pth"], names
+    ck = torch.load(os.path.join(str(tmp_path), "checkpoint_epoch_2.pth"), weights_only=False)
+    for key in ("epoch", "model_state_dict", "ema_model_state_dict", "current_optimizer_step", "optimizer_steps_completed",
+                "scheduler_state_dict", "loss", "train_loss", "val_loss", "best_val_loss", "best_val_epoch", "config"):
+        assert key in ck, key
+    assert orig is not None
+
+
+def test_main_refuses_to_run_without_cuda():
+    from kokoro_ruslan_b200 import cli
+    if torch.cuda.is_available():
+        return
+    try:
+        cli.main(["--synthetic", "4", "-e", "1"])
+    except RuntimeError as exc:
+        assert "no CPU" in str(exc)
+    else:
+        raise AssertionError("expected a RuntimeError on a CPU-only host")
