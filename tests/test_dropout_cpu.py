@@ -50,3 +50,32 @@ def test_torch_dropout_callback_keeps_expectation_and_drops_paths():
     assert (per_sample == 0).any() and (per_sample > 0).any()
     y0 = drop("dec.0.self.out", t)                # layer 0: rate 0
     assert (y0.flatten(1).abs().sum(1) > 0).all()
+
+
+def test_oracle_dropout_sites_reproduce_the_live_reference_under_the_same_torch_rng():
+    """tests/golden/acoustic_dropout.npz = the LIVE reference in train() mode with every dropout and stochastic depth
+    0.5 on, after torch.manual_seed(seed).  The oracle with the TorchDropout callback consumes the same RNG stream
+    (same sites, order, shapes, semantics) and must land on the same outputs: this pins the PLACEMENT of the dropout
+    sites that the CUDA path is then checked against (tests/test_dropout_gpu.py, exported masks)."""
+    import os
+    from oracle import acoustic as oa
+    fix = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "acoustic_dropout.npz"))
+    if str(fix["torch_version"]) != torch.__version__:
+        import pytest
+        pytest.skip("fixture was generated with another torch RNG implementation")
+    cfg = oa.AcousticConfig(hidden_dim=128, n_heads=2, n_encoder_layers=2, n_decoder_layers=2, ff_dim=256,
+                            variance_filter=64, max_len=1200)
+    batch = oa.synthetic_batch(n_mels=cfg.mel_dim, vocab=cfg.vocab_size, B=3, P=24, T=150, seed=11, ragged=True)
+    sd = oa.seeded_state_dict(cfg, seed=0)
+    pe, pd, pi, pv, ps = (float(x) for x in fix["probs"])
+    drop = oa.TorchDropout(pe, pd, pi, pv, ps, cfg.n_encoder_layers, cfg.n_decoder_layers)
+    torch.manual_seed(int(fix["seed"]))
+    outs = oa.forward_training(sd, cfg, batch["phoneme_indices"], batch["mel_specs"], batch["phoneme_durations"],
+                               batch["pitches"], batch["energies"], batch["stress_indices"], drop=drop)
+    for k, o in zip(("mel", "log_dur", "stop", "pitch", "energy"), outs):
+        want = torch.from_numpy(fix[f"out_{k}"])
+        assert float((o - want).abs().max()) < 1e-4 * max(1.0, float(want.abs().max())), k
+    # and the dropouts really fired: the deterministic forward is far away
+    det = oa.forward_training(sd, cfg, batch["phoneme_indices"], batch["mel_specs"], batch["phoneme_durations"],
+                              batch["pitches"], batch["energies"], batch["stress_indices"])
+    assert float((det[0] - torch.from_numpy(fix["out_mel"])).abs().max()) > 0.1
