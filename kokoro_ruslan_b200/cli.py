@@ -207,8 +207,50 @@ def make_sampler(ds, cfg: RunConfig, shuffle: bool = True):
     return LengthBasedBatchSampler(ds, cfg.batch_size, drop_last=False, shuffle=shuffle)
 
 
+def find_latest_checkpoint(output_dir: str) -> Optional[str]:
+    """`--resume auto`: the checkpoint_epoch_{N}.pth with the largest N (reference checkpoint_manager semantics)."""
+    import re
+    best, best_n = None, -1
+    if os.path.isdir(output_dir):
+        for name in os.listdir(output_dir):
+            m = re.fullmatch(r"checkpoint_epoch_(\d+)\.pth", name)
+            if m and int(m.group(1)) > best_n:
+                best, best_n = os.path.join(output_dir, name), int(m.group(1))
+    return best
+
+
+def resume(cfg: RunConfig, step, log: Callable[[str], None] = print) -> int:
+    """Loads weights (+ EMA, scheduler counters) from cfg.resume_checkpoint ("auto" = latest in the output directory);
+    returns the epoch index to continue with.  Adam moments are not part of this path's checkpoints: they restart."""
+    path = cfg.resume_checkpoint
+    if not path:
+        return 0
+    if path == "auto":
+        path = find_latest_checkpoint(cfg.output_dir)
+        if path is None:
+            log(f"--resume auto: no checkpoint in {cfg.output_dir}, starting from scratch")
+            return 0
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    step.load_state_dict(ck["model_state_dict"])
+    ema = ck.get("ema_model_state_dict")
+    st = step.store
+    if ema is not None and getattr(st, "ema", None) is not None:
+        live = st.params.clone()
+        step.load_state_dict(ema)                 # route the EMA tensors through the same layout conversion ...
+        st.ema.copy_(st.params)
+        st.params.copy_(live)                     # ... then restore the live weights and their bf16 shadow
+        st.refresh_shadow()
+    if "scheduler_state_dict" in ck and hasattr(step.sched, "load_state_dict"):
+        try:
+            step.sched.load_state_dict(ck["scheduler_state_dict"])
+        except (KeyError, TypeError):
+            pass                                   # a reference-trainer checkpoint: its OneCycleLR state does not apply
+    log(f"resumed from {path} (epoch {int(ck.get('epoch', -1)) + 1})")
+    return int(ck.get("epoch", -1)) + 1
+
+
 def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
-          log: Callable[[str], None] = print) -> Dict:
+          log: Callable[[str], None] = print, start_epoch: int = 0) -> Dict:
     """Runs the epochs on an already constructed step object (TrainStep API: micro_step, eval_losses, engine,
     state_dict, store).  Returns a summary dict (per-epoch losses, best epoch, checkpoints written)."""
     from .data import DistributedBatchSampler, collate_fn
@@ -216,7 +258,7 @@ def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
     hist: List[Dict] = []
     best, best_epoch, since_best, saved = float("inf"), -1, 0, []
     os.makedirs(cfg.output_dir, exist_ok=True)
-    for epoch in range(cfg.num_epochs):
+    for epoch in range(start_epoch, cfg.num_epochs):
         random.seed(cfg.seed + epoch)                 # every rank builds the identical epoch batch list
         sampler = make_sampler(train_ds, cfg)
         batches = list(iter(sampler))
@@ -310,10 +352,9 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
                                            decoder_input=cfg.decoder_input_dropout, variance=cfg.variance_dropout,
                                            stochastic_depth=cfg.stochastic_depth_rate, seed=cfg.seed + rank))
     step.store.init_default(seed=cfg.seed)
-    if cfg.resume_checkpoint and cfg.resume_checkpoint != "auto":
-        ck = torch.load(cfg.resume_checkpoint, map_location="cpu", weights_only=False)
-        step.load_state_dict(ck["model_state_dict"])
-    out = train(cfg, train_ds, val_ds, step, rank, world, log=(print if rank == 0 else (lambda s: None)))
+    start_epoch = resume(cfg, step, log=(print if rank == 0 else (lambda s: None)))
+    out = train(cfg, train_ds, val_ds, step, rank, world, log=(print if rank == 0 else (lambda s: None)),
+                start_epoch=start_epoch)
     if rank == 0:
         print(f"done: {len(out['history'])} epochs, best val_loss {out['best_val_loss']:.4f}, "
               f"{len(out['checkpoints'])} checkpoints in {cfg.output_dir}")

@@ -138,3 +138,37 @@ def test_main_refuses_to_run_without_cuda():
         assert "no CPU" in str(exc)
     else:
         raise AssertionError("expected a RuntimeError on a CPU-only host")
+
+
+def test_resume_auto_picks_the_latest_checkpoint_and_continues(tmp_path):
+    from kokoro_ruslan_b200 import cli
+    for n in (1, 3, 12):
+        torch.save({"epoch": n - 1, "model_state_dict": {"w": torch.full((2,), float(n))}, "ema_model_state_dict": None,
+                    "scheduler_state_dict": {"k": n}}, os.path.join(str(tmp_path), f"checkpoint_epoch_{n}.pth"))
+    assert cli.find_latest_checkpoint(str(tmp_path)).endswith("checkpoint_epoch_12.pth")
+    assert cli.find_latest_checkpoint(str(tmp_path / "missing")) is None
+    step = _StubStep([1.0])
+    loaded = {}
+    step.load_state_dict = lambda sd: loaded.update(sd)
+    cfg = cli.RunConfig(output_dir=str(tmp_path), resume_checkpoint="auto", num_epochs=14)
+    start = cli.resume(cfg, step, log=lambda s: None)
+    assert start == 12 and float(loaded["w"][0]) == 12.0
+    ds = cli.SyntheticDataset(6, seed=1, min_frames=60, max_frames=90)
+    cfg.min_batch_size, cfg.max_frames_per_batch, cfg.save_every = 1, 400, 0
+    out = cli.train(cfg, ds, None, step, log=lambda s: None, start_epoch=start)
+    assert [h["epoch"] for h in out["history"]] == [12, 13]
+
+
+def test_data_parallel_ranks_split_every_epoch_evenly():
+    from kokoro_ruslan_b200 import cli
+    ds = cli.SyntheticDataset(40, seed=2, min_frames=60, max_frames=200)
+    cfg = cli.RunConfig(output_dir="/tmp/_kr_cli_dp", num_epochs=2, max_frames_per_batch=600, min_batch_size=1,
+                        max_batch_size=6, save_every=0, gradient_accumulation_steps=2)
+    seen = []
+    for rank in (0, 1):
+        step = _StubStep([1.0])
+        out = cli.train(cfg, ds, None, step, rank=rank, world=2, log=lambda s: None)
+        seen.append((out, step.calls))
+    assert [h["batches"] for h in seen[0][0]["history"]] == [h["batches"] for h in seen[1][0]["history"]]
+    assert len(seen[0][1]) == len(seen[1][1]) > 0            # same number of micro-steps on both ranks (no hang)
+    assert [c[1:] for c in seen[0][1]] == [c[1:] for c in seen[1][1]]      # same window structure -> same collectives
