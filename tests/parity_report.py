@@ -1,5 +1,5 @@
 """Prints the per-output / per-gradient error table of the CUDA engine vs the fp32 CPU oracle
-(diagnostic; run on the GPU box).  usage: python tools/parity_report.py [case ...]"""
+(diagnostic; run on the GPU box).  usage: python tests/parity_report.py [case ...]  (lives under tests/: it imports the oracle)"""
 import os
 import sys
 
@@ -7,7 +7,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # this directory
 
 from oracle import acoustic as oa  # noqa: E402
 from test_engine_gpu import _cases, _engine_for  # noqa: E402

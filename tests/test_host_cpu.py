@@ -174,3 +174,23 @@ def test_adaptive_stabilisation_values():
     assert abs(s - 0.7) < 1e-6 and abs(c - 0.5 / (2000 / 1400) ** 0.5) < 1e-9
     s, c = adaptive_stabilisation(800, 1200, 1.5)
     assert s == 0.25 and abs(c - 0.5 / 8 ** 0.5) < 1e-9
+
+
+def test_only_tests_smoke_and_bench_import_the_oracle():
+    """The oracle is test infrastructure: nothing in the product package or the developer tools may import it
+    (tests/, __graft_entry__.smoke() and bench.py's CPU legs are the only users)."""
+    import ast
+    import glob
+    root = os.path.dirname(HERE)
+    offenders = []
+    for path in glob.glob(os.path.join(root, "kokoro_ruslan_b200", "*.py")) + glob.glob(os.path.join(root, "tools", "*.py")):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            if any(m == "oracle" or m.startswith("oracle.") for m in mods):
+                offenders.append(os.path.relpath(path, root))
+    assert not offenders, offenders

@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 from kokoro_ruslan_b200.optim import OptimConfig  # noqa: E402
 from kokoro_ruslan_b200.params import ModelConfig  # noqa: E402
 from kokoro_ruslan_b200.train_step import ScheduleConfig, TrainStep  # noqa: E402
-from oracle import acoustic as oa  # noqa: E402  (synthetic batches / seeded weights only)
+from bench import synthetic_batch  # noqa: E402
 
 
 def main():
@@ -26,19 +26,15 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    ocfg = oa.AcousticConfig(hidden_dim=128, n_heads=2, n_encoder_layers=2, n_decoder_layers=4, ff_dim=256,
-                             variance_filter=64, max_len=1200)
-    cfg = ModelConfig(vocab_size=ocfg.vocab_size, mel_dim=ocfg.mel_dim, hidden_dim=128, n_encoder_layers=2, n_heads=2,
-                      encoder_ff_dim=256, n_decoder_layers=4, decoder_ff_dim=256, max_decoder_seq_len=1200,
-                      variance_filter_size=64, n_variance_bins=ocfg.n_bins)
-    sd = oa.seeded_state_dict(ocfg, seed=0)
-    batches = [oa.synthetic_batch(B=3, P=24, T=150, seed=100 + r, ragged=True) for r in range(world)]
+    cfg = ModelConfig(vocab_size=59, mel_dim=80, hidden_dim=128, n_encoder_layers=2, n_heads=2, encoder_ff_dim=256,
+                      n_decoder_layers=4, decoder_ff_dim=256, max_decoder_seq_len=1200, variance_filter_size=64)
+    batches = [synthetic_batch(3, 24, 150, 80, 59, seed=100 + r) for r in range(world)]
     sched = ScheduleConfig(total_steps=1000, use_warmup=False, pct_start=0.5)
     ok = True
     for graphs in (False, True):
         ts = TrainStep(cfg, OptimConfig(learning_rate=1e-3), sched, device=dev, use_graphs=graphs,
                        process_group=dist.group.WORLD)
-        ts.load_state_dict(sd)
+        ts.store.init_default(seed=0)          # identical weights on every rank
         mine = [ts.train_step(batches[rank]).cpu() for _ in range(4)]
         torch.cuda.synchronize()
         w_dp = ts.store.params.clone()
@@ -52,7 +48,7 @@ def main():
                 ok &= same
                 print(f"graphs={graphs}: rank {r} weights identical to rank 0: {same}")
             ref = TrainStep(cfg, OptimConfig(learning_rate=1e-3), sched, device=dev, use_graphs=False)
-            ref.load_state_dict(sd)
+            ref.store.init_default(seed=0)
             for k in range(4):
                 want = ref.train_window(batches)
                 for r in range(world):
@@ -62,7 +58,7 @@ def main():
                     if not close:
                         print("loss mismatch", k, r, got.tolist(), want[r].cpu().tolist())
             base = TrainStep(cfg, device=dev, use_graphs=False)
-            base.load_state_dict(sd)
+            base.store.init_default(seed=0)
             p0 = base.store.params
             err = float(((w_dp - p0) - (ref.store.params - p0)).norm() / (ref.store.params - p0).norm())
             print(f"graphs={graphs}: relative L2 error of the accumulated update vs the single-process window: {err:.3e}")
