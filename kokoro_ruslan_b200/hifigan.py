@@ -368,3 +368,41 @@ def load_hifigan_model(model_path, config_path=None, device: str = "cuda") -> Hi
     sd = torch.load(model_path, map_location="cpu", weights_only=True)
     gen.load_state_dict(sd["generator"] if "generator" in sd else sd)
     return gen
+
+
+class VocoderManager:
+    """HiFi-GAN side of the reference's ``VocoderManager`` (inference/vocoder_manager.py:22-206): same constructor
+    arguments, ``mel_to_audio`` with the reference's layout rules and its 1-D / 2-D CPU result.  Griffin-Lim (the
+    reference's CPU fallback when no checkpoint is available) is deliberately NOT provided: this path has no CPU
+    fallback, and model downloads need a network.  ``vocoder`` may be injected (tests, pre-loaded generators)."""
+
+    def __init__(self, vocoder_type: str = "hifigan", vocoder_path: Optional[str] = None, device: str = "cuda",
+                 config_path: Optional[str] = None, vocoder=None):
+        self.vocoder_type = vocoder_type.lower()
+        self.device = device
+        if self.vocoder_type != "hifigan":
+            raise ValueError(f"Unsupported vocoder type on the B200 path: {vocoder_type} (HiFi-GAN only, no Griffin-Lim fallback)")
+        if vocoder is not None:
+            self.vocoder = vocoder
+        elif vocoder_path is not None:
+            self.vocoder = load_hifigan_model(vocoder_path, config_path, device=device)
+        else:
+            raise RuntimeError("VocoderManager needs a local HiFi-GAN checkpoint (vocoder_path): downloads are not supported")
+
+    def mel_to_audio(self, mel_spec: torch.Tensor) -> torch.Tensor:
+        """vocoder_manager.py:154-206: (n_mels, T) -> add a batch dim; a 3-D input whose first dim is not 1 is taken as
+        (batch, T, n_mels) and transposed (a batch of ONE is passed through unchanged and left to the generator's own
+        layout detection, hifigan_vocoder.py:112-117 — the reference's behaviour); the result loses its batch and
+        channel dims when they are 1 and is returned on the CPU."""
+        with torch.no_grad():
+            mel_spec = mel_spec.to(self.device)
+            if mel_spec.dim() == 2:
+                mel_spec = mel_spec.unsqueeze(0)
+            elif mel_spec.dim() == 3 and mel_spec.shape[0] != 1:
+                mel_spec = mel_spec.transpose(1, 2)
+            audio = self.vocoder(mel_spec)
+            if audio.dim() == 3:
+                audio = audio.squeeze(0)
+            if audio.dim() == 2:
+                audio = audio.squeeze(0)
+        return audio.cpu()

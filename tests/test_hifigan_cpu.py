@@ -37,3 +37,29 @@ def test_state_dict_layout():
     assert len(keys) == 78 * 3                     # 78 weight-normed convs: bias, g, v
     n = sum(int(np.prod(s)) for k, s in keys if not k.endswith("original0"))
     assert n == 13926017                           # v + biases (g adds one scalar per out/in channel)
+
+
+def test_vocoder_manager_layout_rules_match_the_reference():
+    """mel_to_audio's layout handling (vocoder_manager.py:176-204) on a stub generator: which tensor reaches the
+    vocoder and which shape comes back."""
+    import torch
+    from kokoro_ruslan_b200.hifigan import VocoderManager
+    seen = []
+
+    def stub(x):
+        seen.append(tuple(x.shape))
+        B = x.shape[0]
+        T = x.shape[2] if x.shape[1] == 80 else x.shape[1]
+        return torch.zeros(B, 1, T * 256)
+    vm = VocoderManager("hifigan", device="cpu", vocoder=stub)
+    assert tuple(vm.mel_to_audio(torch.zeros(80, 50)).shape) == (12800,) and seen[-1] == (1, 80, 50)
+    assert tuple(vm.mel_to_audio(torch.zeros(3, 50, 80)).shape) == (3, 1, 12800) and seen[-1] == (3, 80, 50)
+    assert tuple(vm.mel_to_audio(torch.zeros(1, 80, 50)).shape) == (12800,) and seen[-1] == (1, 80, 50)
+    assert tuple(vm.mel_to_audio(torch.zeros(1, 50, 80)).shape) == (12800,) and seen[-1] == (1, 50, 80)   # batch of one: untouched
+    for bad in ("griffin_lim", "wavernn"):
+        try:
+            VocoderManager(bad, device="cpu", vocoder=stub)
+        except ValueError:
+            pass
+        else:
+            raise AssertionError("expected ValueError")
