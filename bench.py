@@ -222,7 +222,7 @@ def hifigan_leg(peaks, steps: int = 10, B: int = 16, T: int = 800):
     alg_bytes = 2.03e6 * B * T                                # ... and 2.03 MB (bf16) of activation traffic
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_hifigan_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01_hifigan_traffic_v4.json")) as f:
             tr = json.load(f)["kr_gemm_kernel"]
         traffic = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / 2.0    # the capture holds two forwards
     except Exception:
