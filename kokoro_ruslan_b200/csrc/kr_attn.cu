@@ -17,6 +17,7 @@
 //           which is reduced into the fp32 dQ buffer with vector atomics.
 #include "kr_common.cuh"
 #include "kokoro_b200.h"
+#include <stdlib.h>
 
 namespace {
 using namespace kr;
@@ -94,7 +95,13 @@ __device__ __forceinline__ uint32_t allowed_bits(uint32_t pad_bits, bool causal,
 // ---------------------------------------------------------------------------------------------
 constexpr int FWD_SMEM = 7 * TILE_BYTES + 256 + 1024;
 
-template <bool CAUSAL, bool DROP>
+// FAST = opt-in instruction-count variant of the softmax / rescale code (env KR_ATTN_FAST=1; written at the end of
+// round 1 without GPU time left to validate it, so it is NOT the default): the forward's 128 softmax threads are
+// issue-bound (ncu: ~26 M warp instructions, issue slots 28 % busy with 2 warps per scheduler, tensor pipe 7 %), so
+// it removes instructions — the 1/sqrt(d) scale is folded into the exp2 argument with a packed FFMA2 (no pre-scaling
+// pass over S), the row sum adds the fp32 probabilities with FADD2 (no unpack of the bf16-rounded values), and
+// the O rescale-accumulate is a packed FFMA2.  The default instantiations are textually unchanged.
+template <bool CAUSAL, bool DROP, bool FAST = false>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -192,6 +199,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
     for (int c = 0; c < 4; ++c) mw[c] = mask_words[st * 4 + c];
 
+    float alpha;
+    if constexpr (!FAST) {
     // S row (128 keys) is read from TMEM ONCE into registers (TMEM read bandwidth, 64 B/clk/SM, is the
     // scarce resource of this loop); masking folded in as -inf
     float sv[128];
@@ -215,7 +224,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < 128; ++i) mx = fmaxf(mx, sv[i]);
     const float m_new = fmaxf(m_run, mx);
     const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-    const float alpha = fast_exp2(m_run - m_use);
+    alpha = fast_exp2(m_run - m_use);
     // P (bf16) goes back into TENSOR MEMORY, over the S columns this thread has already consumed: the P V MMA
     // then reads its A operand from TMEM, which removes a 32 KB smem write + 32 KB smem read per tile from the
     // loop (shared-memory operand bandwidth is what bounds these d = 64 MMAs).  Packed layout: lane = query row,
@@ -244,6 +253,57 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_st_wait();
     l_run = l_run * alpha + rowsum;
     m_run = m_new;
+    } else {
+      // RAW logits in registers (masked = -inf); scale folded into the exp2 argument
+      float sv[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_S + t_lane + c * 32, r);
+        tmem_ld_wait();
+        const uint32_t ok = allowed_bits(mw[c], CAUSAL, j * TK + c * 32, qi);
+        if (__all_sync(0xffffffffu, ok == 0xffffffffu)) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[c * 32 + i] = __uint_as_float(r[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[c * 32 + i] = ((ok >> i) & 1u) ? __uint_as_float(r[i]) : -INFINITY;
+        }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; ++i) mx = fmaxf(mx, sv[i]);
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);       // scale > 0: max commutes with it
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      alpha = fast_exp2(m_run - m_use);
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_use, -m_use);
+      float2 rs2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int hcol = 0; hcol < 2; ++hcol) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          const float2 a0 = __ffma2_rn(make_float2(sv[hcol * 64 + i], sv[hcol * 64 + i + 1]), sc2, nm2);
+          const float2 a1 = __ffma2_rn(make_float2(sv[hcol * 64 + i + 2], sv[hcol * 64 + i + 3]), sc2, nm2);
+          const float2 e0 = make_float2(fast_exp2(a0.x), fast_exp2(a0.y));   // exp2(-inf) = 0 for masked keys
+          const float2 e1 = make_float2(fast_exp2(a1.x), fast_exp2(a1.y));
+          rs2 = __fadd2_rn(rs2, e0);
+          rs2 = __fadd2_rn(rs2, e1);
+          uint32_t u0 = pack_bf16(e0.x, e0.y), u1 = pack_bf16(e1.x, e1.y);
+          if (DROP) {
+            const uint32_t m = drop_quad_bytes(drow + j * (TK / 4) + hcol * 16 + (i >> 2), dkey, p.thr4);
+            u0 &= keep_lo_pair(m);
+            u1 &= keep_hi_pair(m);
+          }
+          pk[i >> 1] = u0;
+          pk[(i >> 1) + 1] = u1;
+        }
+        tmem_st_32x32(tmem_S + t_lane + hcol * 32, pk);
+      }
+      tmem_st_wait();
+      l_run = l_run * alpha + (rs2.x + rs2.y);
+      m_run = m_new;
+    }
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
@@ -264,8 +324,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t r[32];
       tmem_ld_32x32(tmem_O + t_lane + c * 32, r);
       tmem_ld_wait();
+      if constexpr (!FAST) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(r[i]);
+      } else {
+        const float2 al2 = make_float2(alpha, alpha);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 o2 = __ffma2_rn(make_float2(o_acc[c * 32 + i], o_acc[c * 32 + i + 1]), al2,
+                                       make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+          o_acc[c * 32 + i] = o2.x;
+          o_acc[c * 32 + i + 1] = o2.y;
+        }
+      }
     }
     tc_fence_before();
   }
@@ -652,7 +723,23 @@ extern "C" int kr_attn_fwd(const void* q, long long q_ss, long long q_bs, const 
   dim3 grid((Sq + TQ - 1) / TQ, H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool dr = p.drop.state != nullptr;
-  if (causal && dr)  kr::launch(attn_fwd_kernel<true, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
+  static int fast = -1;
+  if (fast < 0) {
+    const char* e = getenv("KR_ATTN_FAST");
+    fast = (e != nullptr && e[0] == '1') ? 1 : 0;
+    if (fast) {
+      cudaFuncSetAttribute(attn_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+      cudaFuncSetAttribute(attn_fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+      cudaFuncSetAttribute(attn_fwd_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+      cudaFuncSetAttribute(attn_fwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    }
+  }
+  if (fast) {     // opt-in, see the kernel's header comment
+    if (causal && dr)  kr::launch(attn_fwd_kernel<true, true, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
+    else if (causal)   kr::launch(attn_fwd_kernel<true, false, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
+    else if (dr)       kr::launch(attn_fwd_kernel<false, true, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
+    else               kr::launch(attn_fwd_kernel<false, false, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
+  } else if (causal && dr)  kr::launch(attn_fwd_kernel<true, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
   else if (causal)   kr::launch(attn_fwd_kernel<true, false>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
   else if (dr)       kr::launch(attn_fwd_kernel<false, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
   else               kr::launch(attn_fwd_kernel<false, false>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
