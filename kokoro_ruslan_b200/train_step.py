@@ -132,6 +132,26 @@ def adaptive_stabilisation(T: int, max_dur: int, base_clip: float, frame_thr: fl
     return max(0.25, 1.0 / r), min(base_clip, max(0.05, 0.5 / math.sqrt(r)))
 
 
+def validate_batch(batch) -> None:
+    """Error conventions of the reference's `_transfer_batch_to_device` (trainer.py:1262-1297): a missing key is a
+    KeyError, a None field a ValueError, a non-tensor field a TypeError.  This path needs all nine tensors (the
+    variance predictors and the stress embedding are always on, trainer.py:356-382), so the three fields the
+    reference treats as optional are required here as well."""
+    missing = [k for k in BATCH_KEYS if k not in batch]
+    if missing:
+        raise KeyError(f"Batch is missing required keys: {missing}")
+    for k in BATCH_KEYS:
+        v = batch[k]
+        if v is None:
+            raise ValueError(f"Batch field '{k}' is None")
+        if not torch.is_tensor(v):
+            raise TypeError(f"Batch field '{k}' must be a tensor, got {type(v).__name__}")
+    B = batch["mel_specs"].shape[0]
+    for k in BATCH_KEYS:
+        if batch[k].shape[0] != B:
+            raise ValueError(f"Batch field '{k}' has batch size {batch[k].shape[0]}, expected {B}")
+
+
 @dataclass
 class _Staged:
     """Static device buffers + graph for one batch shape."""
@@ -239,10 +259,8 @@ class TrainStep:
     def stage(self, batch: Dict[str, torch.Tensor], divisor: int = 1) -> Tuple[_Staged, Tuple[int, int, int, int, bool]]:
         """Host-side prologue: shape key, stabiliser scalars, async H2D into the static buffers.
         divisor = the accumulation divisor of this micro-batch (trainer.py:2284-2294)."""
+        validate_batch(batch)
         batch = self._cap(batch)
-        for k in BATCH_KEYS:
-            if k not in batch:
-                raise KeyError(f"batch is missing required key '{k}' (reference trainer.py:1262-1297)")
         dur = batch["phoneme_durations"]
         B, P = dur.shape
         T = batch["mel_specs"].shape[1]

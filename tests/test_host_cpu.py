@@ -194,3 +194,23 @@ def test_only_tests_smoke_and_bench_import_the_oracle():
             if any(m == "oracle" or m.startswith("oracle.") for m in mods):
                 offenders.append(os.path.relpath(path, root))
     assert not offenders, offenders
+
+
+def test_batch_validation_error_conventions():
+    """KeyError / ValueError / TypeError as the reference's _transfer_batch_to_device raises them (trainer.py:1262-1297)."""
+    import pytest
+    import torch
+    from kokoro_ruslan_b200.train_step import BATCH_KEYS, validate_batch
+    from oracle import acoustic as oa
+    batch = oa.synthetic_batch(B=2, P=8, T=20, seed=1)
+    validate_batch(batch)
+    for k in BATCH_KEYS:
+        bad = {kk: v for kk, v in batch.items() if kk != k}
+        with pytest.raises(KeyError):
+            validate_batch(bad)
+    with pytest.raises(ValueError):
+        validate_batch({**batch, "pitches": None})
+    with pytest.raises(TypeError):
+        validate_batch({**batch, "mel_lengths": [20, 20]})
+    with pytest.raises(ValueError):
+        validate_batch({**batch, "energies": torch.zeros(3, 20)})
