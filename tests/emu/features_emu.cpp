@@ -1,0 +1,63 @@
+// TEST INFRASTRUCTURE — host emulation of the feature-extraction kernels (kokoro_ruslan_b200/csrc/kr_features.cu).
+// Compiles the kernels' own bodies (kr_features_core.cuh) with -DKR_HOST_EMU, i.e. as one "thread" per block, and
+// loops over the grid exactly as the launch wrappers do.  Built and called by tests/test_features_emu_cpu.py only.
+#define KR_HOST_EMU 1
+#include "kr_features_core.cuh"
+#include <vector>
+
+extern "C" int emu_pitch_num_frames(long long n) { return krf::pitch_num_frames(n); }
+
+extern "C" int emu_pitch_frames(const float* wav, const long long* lengths, float* cand, float* acmax, float* energy,
+                                int B, long long n_max, int frames_max, int sample_rate, float fmin, float fmax) {
+  int lag_min, lag_max;
+  if (!krf::pitch_lag_range(sample_rate, fmin, fmax, &lag_min, &lag_max)) return -4;
+  std::vector<krf_float2> z(krf::NFFT), tw(krf::TW);
+  std::vector<float> cm(krf::MAX_LAGS), red(32);
+  for (int b = 0; b < B; ++b) {
+    const long long n = lengths ? lengths[b] : n_max;
+    for (int f = 0; f < frames_max; ++f) {
+      if (f >= krf::pitch_num_frames(n)) continue;
+      const long long o = (long long)b * frames_max + f;
+      krf::pitch_frame_body(wav + (long long)b * n_max, n, f, lag_min, lag_max, (float)sample_rate, z.data(), tw.data(),
+                            cm.data(), red.data(), cand + o, acmax + o, energy + o);
+    }
+  }
+  return 0;
+}
+
+extern "C" int emu_pitch_track(const float* cand, const float* acmax, const float* energy, const long long* lengths,
+                               float* work, float* out, int B, long long n_max, int frames_max, float fmin, float fmax) {
+  float sel[4];
+  for (int b = 0; b < B; ++b) {
+    const long long n = lengths ? lengths[b] : n_max;
+    int T = krf::pitch_num_frames(n);
+    T = T < frames_max ? T : frames_max;
+    const long long o = (long long)b * frames_max;
+    krf::pitch_track_body(cand + o, acmax + o, energy + o, T, frames_max, fmin, fmax, work + o, sel, out + o);
+  }
+  return 0;
+}
+
+extern "C" int emu_energy_frames(const float* mel, float* e, int B, int T, int n_mels, int time_major, int exp_input,
+                                 int log_domain) {
+  for (int b = 0; b < B; ++b)
+    for (int t = 0; t < T; ++t) {
+      float acc = 0.f;
+      for (int m = 0; m < n_mels; ++m) {
+        const float v = time_major ? mel[((long long)b * T + t) * n_mels + m] : mel[((long long)b * n_mels + m) * T + t];
+        acc += exp_input ? krf_exp(v) : v;
+      }
+      e[(long long)b * T + t] = krf::energy_finish(acc / (float)n_mels, log_domain);
+    }
+  return 0;
+}
+
+extern "C" int emu_energy_norm(const float* e, const long long* frames, float* out, int B, int T_max) {
+  float sel[4], red[32];
+  for (int b = 0; b < B; ++b) {
+    long long T = frames ? frames[b] : T_max;
+    T = T < 0 ? 0 : (T < T_max ? T : T_max);
+    krf::energy_norm_body(e + (long long)b * T_max, (int)T, T_max, sel, red, out + (long long)b * T_max);
+  }
+  return 0;
+}

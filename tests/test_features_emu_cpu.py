@@ -1,0 +1,107 @@
+"""Host emulation of the pitch / energy feature kernels (kokoro_ruslan_b200/csrc/kr_features_core.cuh compiled by g++
+with -DKR_HOST_EMU, one "thread" per block; tests/emu/features_emu.cpp loops over the grid like the launch wrappers)
+against the LIVE-reference fixtures of tests/golden/features.npz and the numpy oracle.  This checks the kernels' own
+source — index arithmetic, in-place FFT pair, CMND, every thresholded decision, rank-counting quantiles — on the CPU;
+the -m gpu test (tests/test_zz_features_gpu.py) checks the same entry points on the device."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    so = tmp_path_factory.mktemp("emu") / "features_emu.so"
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-I", os.path.join(ROOT, "kokoro_ruslan_b200", "csrc"),
+                    os.path.join(HERE, "emu", "features_emu.cpp"), "-o", str(so)], check=True)
+    return ctypes.CDLL(str(so))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def emu_pitch(lib, wav, lengths=None, sr=22050, fmin=50.0, fmax=800.0):
+    wav = np.ascontiguousarray(np.atleast_2d(wav), dtype=np.float32)
+    B, N = wav.shape
+    lens = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int64)
+    T = max(lib.emu_pitch_num_frames(ctypes.c_longlong(int(n))) for n in ([N] if lens is None else lens))
+    bufs = [np.full((B, T), np.nan, np.float32) for _ in range(3)]
+    work, out = np.zeros((B, T), np.float32), np.full((B, T), np.nan, np.float32)
+    f = ctypes.c_float
+    assert lib.emu_pitch_frames(_p(wav), _p(lens), *map(_p, bufs), B, ctypes.c_longlong(N), T, sr, f(fmin), f(fmax)) == 0
+    assert lib.emu_pitch_track(*map(_p, bufs), _p(lens), _p(work), _p(out), B, ctypes.c_longlong(N), T, f(fmin), f(fmax)) == 0
+    return out
+
+
+def emu_energy(lib, mel, time_major=True, exp_input=False, log_domain=True, frames=None):
+    mel = np.ascontiguousarray(mel, dtype=np.float32)
+    B, T, M = mel.shape if time_major else (mel.shape[0], mel.shape[2], mel.shape[1])
+    e, out = np.zeros((B, T), np.float32), np.full((B, T), np.nan, np.float32)
+    fr = None if frames is None else np.ascontiguousarray(frames, dtype=np.int64)
+    assert lib.emu_energy_frames(_p(mel), _p(e), B, T, M, int(time_major), int(exp_input), int(log_domain)) == 0
+    assert lib.emu_energy_norm(_p(e), _p(fr), _p(out), B, T) == 0
+    return out
+
+
+def test_pitch_kernels_match_live_reference(emu):
+    f = np.load(os.path.join(HERE, "golden", "features.npz"))
+    got = emu_pitch(emu, f["wav"])
+    assert got.shape == f["pitch"].shape
+    d = np.abs(got - f["pitch"])
+    assert (d < 1e-4).mean() >= 0.99 and d.max() < 0.05, ((d < 1e-4).mean(), d.max())
+    assert ((got > 0) == (f["pitch"] > 0)).mean() >= 0.99
+    short = emu_pitch(emu, f["wav"][0, :1500])[0]                      # shorter than one analysis window
+    assert short.shape == f["pitch_short"].shape and np.abs(short - f["pitch_short"]).max() < 1e-4
+
+
+def test_pitch_ragged_batch_equals_per_item(emu):
+    """Per-utterance lengths: every row equals the utterance processed alone, padding frames are zero."""
+    from oracle import features as of
+    f = np.load(os.path.join(HERE, "golden", "features.npz"))
+    lens = np.array([35280, 20000, 9001, 1500])
+    wav = f["wav"].copy()
+    for b, n in enumerate(lens):
+        wav[b, n:] = 7.0                                               # garbage beyond the length must never be read
+    got = emu_pitch(emu, wav, lens)
+    for b, n in enumerate(lens):
+        single = emu_pitch(emu, f["wav"][b, :n])[0]
+        T = single.shape[0]
+        assert np.array_equal(got[b, :T], single)
+        assert np.all(got[b, T:] == 0.0)
+        want = of.extract_pitch(f["wav"][b, :n])
+        d = np.abs(single - want)
+        assert (d < 1e-4).mean() >= 0.98 and d.max() < 0.05, (b, (d < 1e-4).mean(), d.max())
+
+
+def test_energy_kernels_match_live_reference(emu):
+    f = np.load(os.path.join(HERE, "golden", "features.npz"))
+    mel = f["mel"]
+    assert np.abs(emu_energy(emu, mel, log_domain=True) - f["e_log"]).max() < 1e-5
+    assert np.abs(emu_energy(emu, np.exp(mel), log_domain=False) - f["e_lin"]).max() < 1e-5
+    # what the product pipeline does: log-mel in (the mel-STFT kernel's output layout), linear-power semantics out
+    cm = np.ascontiguousarray(mel.transpose(0, 2, 1))
+    assert np.abs(emu_energy(emu, cm, time_major=False, exp_input=True, log_domain=False) - f["e_lin"]).max() < 1e-5
+    assert np.abs(emu_energy(emu, mel[:, :2], log_domain=True) - f["e_short"]).max() < 1e-6    # < 3 frames: min / max
+    # ragged: normalisation statistics over the valid frames only, zeros beyond
+    from oracle import features as of
+    got = emu_energy(emu, mel, log_domain=True, frames=[140, 77, 2])
+    for b, t in enumerate([140, 77, 2]):
+        assert np.abs(got[b, :t] - of.extract_energy_from_mel(mel[b, :t], True)).max() < 1e-5
+        assert np.all(got[b, t:] == 0.0)
+
+
+def test_rank_counting_quantiles_with_ties(emu):
+    """Order statistics by rank counting must behave like a sort when values repeat (silences give many equal frames)."""
+    from oracle import features as of
+    rng = np.random.default_rng(0)
+    e = rng.integers(0, 5, size=(6, 1, 57)).astype(np.float32)        # heavy ties
+    mel = np.repeat(e.transpose(0, 2, 1), 4, axis=2)                   # (6, 57, 4): the frame mean is e itself
+    got = emu_energy(emu, mel, log_domain=True)
+    want = np.stack([of.extract_energy_from_mel(mel[b], True) for b in range(6)])
+    assert np.abs(got - want).max() < 1e-6
