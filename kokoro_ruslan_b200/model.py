@@ -12,8 +12,9 @@ parameter's ``.grad`` is a view of.  Nothing here computes on the CPU or through
 
 Dropout and stochastic depth follow the constructor arguments in ``train()`` mode (fused into the
 kernels, counter-based RNG) and are off in ``eval()``.  Reference behaviours that are deliberately
-NOT reproduced on this path are listed in DESIGN.md: inference (``mel_specs=None``) is the "next"
-row N2 and raises NotImplementedError.
+NOT reproduced on this path are listed in DESIGN.md.  Autoregressive inference is
+available as ``forward_inference`` (device KV-cache decode, ``inference.py``); ``forward(mel_specs=None)``
+keeps raising NotImplementedError until that path has had its first hardware validation run.
 """
 from __future__ import annotations
 
@@ -189,3 +190,21 @@ class KokoroModel:
         return outs
 
     __call__ = forward
+
+    def forward_inference(self, phoneme_indices: torch.Tensor, max_len: int = 4000, stop_threshold: float = 0.5,
+                          text_padding_mask: Optional[torch.Tensor] = None, min_len_ratio: float = 0.7,
+                          min_len_floor: int = 12, max_len_ratio: float = 3.0, max_len_cap: int = 1600,
+                          post_expected_stop_threshold: float = 0.2,
+                          stress_indices: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Reference signature (model/model.py:675-687).  Returns the generated mel (B, n_frames, mel_dim) clamped to
+        [-11.5, 2].  Like the reference it does not change train / eval mode; the decode itself always runs without
+        dropout (the reference's generator is only ever used under ``eval()``)."""
+        if text_padding_mask is not None:
+            raise NotImplementedError("explicit text padding mask (the reference derives it as indices == 0, model.py:704)")
+        from .inference import InferenceEngine
+        if getattr(self, "_inference", None) is None:
+            self._inference = InferenceEngine(self.engine)
+        return self._inference.generate(phoneme_indices, stress_indices, max_len=max_len, stop_threshold=stop_threshold,
+                                        post_expected_stop_threshold=post_expected_stop_threshold,
+                                        min_len_ratio=min_len_ratio, min_len_floor=min_len_floor,
+                                        max_len_ratio=max_len_ratio, max_len_cap=max_len_cap)

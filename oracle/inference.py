@@ -112,8 +112,10 @@ def generation_bounds(expected: int, max_len: int = 4000, min_len_ratio: float =
 @torch.no_grad()
 def forward_inference(sd: Dict[str, Tensor], cfg: oa.AcousticConfig, phoneme_indices: Tensor,
                       stress_indices: Optional[Tensor] = None, max_len: int = 4000, stop_threshold: float = 0.5,
-                      post_expected_stop_threshold: float = 0.2, return_stop_probs: bool = False):
-    """(B, n_frames, n_mels) generated mel, clamped to [-11.5, 2] (model.py:675-779 + generator.py:24-127)."""
+                      post_expected_stop_threshold: float = 0.2, return_stop_probs: bool = False,
+                      return_raw: bool = False):
+    """(B, n_frames, n_mels) generated mel, clamped to [-11.5, 2] (model.py:675-779 + generator.py:24-127).
+    return_raw adds the un-clamped frames (what the loop feeds back) as a third result."""
     mem, mem_pad, _ = encode_and_expand(sd, cfg, phoneme_indices, stress_indices)
     B = mem.shape[0]
     expected = mem.shape[1]
@@ -149,5 +151,8 @@ def forward_inference(sd: Dict[str, Tensor], cfg: oa.AcousticConfig, phoneme_ind
             if len(out) >= 30 and float(torch.cat(out[-30:], dim=1).mean()) < -9.5:
                 break
         frame = mel_t
-    mel = torch.cat(out, dim=1).clamp(min=-11.5, max=2.0)
+    raw = torch.cat(out, dim=1)
+    mel = raw.clamp(min=-11.5, max=2.0)
+    if return_raw:
+        return mel, probs, raw
     return (mel, probs) if return_stop_probs else mel

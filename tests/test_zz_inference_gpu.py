@@ -1,0 +1,106 @@
+"""Autoregressive inference on the device: InferenceEngine / DecodeLoop with CudaDecodeBackend
+(kr_dec_feed / kr_dec_attn / kr_dec_finish + the training-path kernels on a 128-row padded batch, one CUDA graph per
+step) against the oracle's forward_inference, which is pinned to the live reference.
+
+STATUS: written after round 1's GPU budget was spent.  The decode kernels' bodies and the DecodeLoop orchestration are
+verified on the CPU through the host emulation (tests/test_decode_emu_cpu.py), the library cross-compiles for sm_100a
+without spills, but nothing here has run on a B200 yet — hence the non-strict xfail marker (XPASS = first hardware run
+green) and the file name that sorts last."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(reason="first hardware run of a path validated by host emulation only", strict=False)]
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _setup():
+    from kokoro_ruslan_b200.engine import AcousticEngine
+    from kokoro_ruslan_b200.inference import InferenceEngine
+    from kokoro_ruslan_b200.params import ModelConfig
+    from oracle import acoustic as oa
+    f = np.load(os.path.join(HERE, "golden", "inference.npz"))
+    ocfg = oa.AcousticConfig(hidden_dim=128, n_heads=2, n_encoder_layers=2, n_decoder_layers=2, ff_dim=256,
+                             variance_filter=64, max_len=1200)
+    sd = oa.seeded_state_dict(ocfg, seed=int(f["seed"]))
+    sd["duration_adaptor.variance_adaptor.duration_predictor.linear.bias"] = torch.tensor([float(f["dur_bias"])])
+    sd["stop_token_predictor.bias"] = torch.tensor([float(f["stop_bias"])])
+    cfg = ModelConfig(vocab_size=ocfg.vocab_size, mel_dim=ocfg.mel_dim, hidden_dim=ocfg.hidden_dim,
+                      n_encoder_layers=ocfg.n_encoder_layers, n_heads=ocfg.n_heads, encoder_ff_dim=ocfg.ff_dim,
+                      n_decoder_layers=ocfg.n_decoder_layers, decoder_ff_dim=ocfg.ff_dim,
+                      max_decoder_seq_len=ocfg.max_len, variance_filter_size=ocfg.variance_filter,
+                      n_variance_bins=ocfg.n_bins)
+    eng = AcousticEngine(cfg, device="cuda:0", with_ema=False)
+    eng.store.load_state_dict(sd)
+    return f, ocfg, sd, InferenceEngine(eng)
+
+
+def _oracle_durations(sd, ocfg, idx, stress):
+    from oracle import inference as oi
+    _, _, log_dur = oi.encode_and_expand(sd, ocfg, idx, stress)
+    return torch.clamp(torch.round(torch.expm1(log_dur)), min=0).long()
+
+
+def test_encode_and_expand_matches_oracle():
+    from oracle import inference as oi
+    f, ocfg, sd, inf = _setup()
+    idx, stress = torch.from_numpy(f["idx"]), torch.from_numpy(f["stress"])
+    want_mem, want_pad, want_ld = oi.encode_and_expand(sd, ocfg, idx, stress)
+    dur = _oracle_durations(sd, ocfg, idx, stress)
+    mem, fmask, log_dur, Tp = inf.encode_and_expand(idx.cuda(), stress.cuda(), durations=dur)
+    assert Tp == want_mem.shape[1]
+    assert torch.equal(fmask.cpu().bool(), want_pad)
+    assert float((log_dur.cpu() - want_ld).abs().max()) < 2e-2 * max(1.0, float(want_ld.abs().max()))
+    got = mem.float().cpu().view(1, Tp, -1)
+    # bucketised embeddings: a predicted value within bf16 noise of a bin edge may select the neighbouring row
+    close = ((got - want_mem).abs().amax(dim=-1) < 2e-2 * float(want_mem.abs().max())).float().mean()
+    assert float(close) >= 0.9, float(close)
+    # predicted durations on their own: within one frame per token of the oracle's
+    _, _, _, Tp_free = inf.encode_and_expand(idx.cuda(), stress.cuda())
+    assert abs(Tp_free - Tp) <= idx.shape[1]
+
+
+def test_teacher_forced_decode_matches_oracle():
+    from oracle import inference as oi
+    f, ocfg, sd, inf = _setup()
+    idx, stress = torch.from_numpy(f["idx"]), torch.from_numpy(f["stress"])
+    want, want_p, raw = oi.forward_inference(sd, ocfg, idx, stress, return_raw=True)
+    n = want.shape[1]
+    forced = torch.zeros(1, 1600, ocfg.mel_dim)
+    forced[:, 1:n] = raw[:, :n - 1]
+    got, probs = inf.generate(idx.cuda(), stress.cuda(), forced=forced.cuda(), return_stop_probs=True,
+                              durations=_oracle_durations(sd, ocfg, idx, stress))
+    assert abs(got.shape[1] - n) <= 1, (got.shape, want.shape)
+    m = min(got.shape[1], n)
+    err = float((got[:, :m].cpu() - want[:, :m]).abs().max()) / float(want.abs().max())
+    assert err < 2e-2, err
+    assert float((probs[:m].cpu() - torch.tensor(want_p)[:m]).abs().max()) < 3e-2
+
+
+def test_free_running_batch_generation():
+    from oracle import inference as oi
+    f, ocfg, sd, inf = _setup()
+    idx = torch.from_numpy(f["idx2"])
+    want = oi.forward_inference(sd, ocfg, idx, None, stop_threshold=0.45)
+    got = inf.generate(idx.cuda(), None, stop_threshold=0.45, durations=_oracle_durations(sd, ocfg, idx, None)).cpu()
+    assert got.shape[0] == 2 and abs(got.shape[1] - want.shape[1]) <= 3, (got.shape, want.shape)
+    assert bool(torch.isfinite(got).all()) and float(got.max()) <= 2.0 and float(got.min()) >= -11.5
+    assert float((got[:, :3] - want[:, :3]).abs().max()) / float(want.abs().max()) < 4e-2
+
+
+def test_model_forward_inference_surface_and_graph_equals_eager(monkeypatch):
+    """KokoroModel.forward_inference (reference signature) end to end at the full model width, and the CUDA-graph replay
+    against the same loop launched eagerly (KR_DECODE_GRAPH=0): identical frames."""
+    from kokoro_ruslan_b200.model import KokoroModel
+    m = KokoroModel(vocab_size=59)
+    m.eval()
+    g = torch.Generator().manual_seed(3)
+    idx = torch.randint(1, 59, (1, 16), generator=g).cuda()
+    a = m.forward_inference(idx, max_len_cap=96)
+    assert a.dim() == 3 and a.shape[0] == 1 and a.shape[2] == 80 and 12 <= a.shape[1] <= 96
+    monkeypatch.setenv("KR_DECODE_GRAPH", "0")
+    b = m.forward_inference(idx, max_len_cap=96)
+    assert a.shape == b.shape and torch.equal(a, b)

@@ -27,6 +27,10 @@ DOCS = {
     "kr_pitch_track": "Per-utterance part of extract_pitch, variance_predictor.py:566-615: voicing threshold clip(0.8 * quantile_25(ac peak), .15, .35), energy gate 0.05 * median, fmin / fmax gate, linear interpolation of unvoiced gaps <= 5 frames, median-5 with reflect padding, normalisation to [0, 1] (0 = unvoiced). Quantiles are exact order statistics by rank counting (no sort). Frames beyond 1 + max(len, 2048) // 256 are zero.",
     "kr_energy_frames": "Per-frame energy of EnergyExtractor.extract_energy_from_mel, variance_predictor.py:659-668: mean over the mel bins (log-domain input) or log1p(max(mean, 0)) (linear power, what data/dataset.py:813 passes); mel is (B, T, n_mels) [time_major = 1] or (B, n_mels, T) [0, the layout kr_mel_stft writes]; exp_input = 1 exponentiates the input first so that kr_mel_stft's log-mel can feed the linear-power branch.",
     "kr_energy_norm": "5 / 95-percentile normalisation of the per-frame energies to [0, 1] per utterance (min / max below 3 frames), variance_predictor.py:675-687; zeros beyond frames[b].",
+    "kr_dec_state_size": "sizeof the device-resident generation state (krd::DecState in csrc/kr_decode_core.cuh: t, done, n_frames, lo, hi, expected, stop_thr, post_thr, ring[30]; 256 bytes; mirrored by kokoro_ruslan_b200/inference.py STATE_FIELDS).",
+    "kr_dec_feed": "Decoder input of frame t of the autoregressive loop: mel_projection_in on the previous output frame + bias + PE row t (model/model.py:519-531 in eval mode, model/generator.py:52-57); t is read from the device state.",
+    "kr_dec_attn": "One decode-step attention per (utterance, head) with the KV cache of model/transformers.py:237-277: per-head RMSNorm of the new query (rotated as position 0 — the reference's q_offset = 0), and for self-attention RMSNorm + RoPE(position t) of the new key and RMSNorm of the new value appended to the bf16 caches, then softmax(q K^T * scale) V over the cached rows; cross-attention reads the pre-normalised memory keys / values with the key-padding mask.",
+    "kr_dec_finish": "End of a decode step: decoder.norm + mel_projection_out + stop head (model/model.py:547-563) and the generator's stop rules on the device (model/generator.py:58-103: min / max length, stop probability mean over the batch against the pre / post-expected-length thresholds, 30-frame silence rule); stores the clamped frame, the un-clamped feedback frame and the stop probability, advances t.",
     "kr_spec_augment": "SpecAugment on the cross-attention memory (bf16) or its gradient (fp32): zeroes the per-sample frame / hidden-dim spans in spans[B, n_time+n_feat, 2] = (start, length). training/trainer.py:1578-1604, applied at model/model.py:636-639.",
     "kr_attn_fwd": "tcgen05 flash attention forward, head_dim 64, on token-major [B,S,H,64] bf16 tensors (q_ss/q_bs = seq/batch strides in elements). Causal and per-key padding (key_mask[B,Sk], 1 = masked) are predicates; lse[B,H,Sq] is the log2-domain log-sum-exp kept for the backward. Replaces F.scaled_dot_product_attention with the dense additive mask, model/transformers.py:299-316,393-398.",
     "kr_attn_bwd": "Flash attention backward: dq (fp32 [B,Sq,H,64], zeroed by the call's own prep kernel, then atomically accumulated), dk/dv (bf16). delta[B,H,Sq] is scratch. Autograd of model/transformers.py:393-398.",
