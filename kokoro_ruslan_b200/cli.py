@@ -100,6 +100,9 @@ class RunConfig:
     resume_checkpoint: Optional[str] = None
     verbose: bool = False
     seed: int = 42
+    # spectral convergence / F0 RMSE of the validation epoch as device reductions (reference trainer.py:1868-1916 always
+    # computes them, with per-utterance host syncs); off by default until kr_val_metrics has had its first hardware run
+    val_metrics: bool = False
 
 
 def create_config_from_args(args) -> RunConfig:
@@ -283,10 +286,14 @@ def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
             rec.update(train_loss=mean[0], train_mel=mean[1], train_dur=mean[2], train_stop=mean[3])
         if val_ds is not None and len(val_ds) and (epoch + 1) % max(1, cfg.validation_interval) == 0:
             vs = make_sampler(val_ds, cfg, shuffle=False)
-            vl = [step.eval_losses(collate_fn([val_ds[i] for i in b])) for b in iter(vs)]
+            acc = step.new_val_metrics() if cfg.val_metrics and hasattr(step, "new_val_metrics") else None
+            extra = {} if acc is None else {"metrics": acc}
+            vl = [step.eval_losses(collate_fn([val_ds[i] for i in b]), **extra) for b in iter(vs)]
             if vl:
                 vm = torch.stack(vl).mean(dim=0).cpu().tolist()
                 rec.update(val_loss=vm[0], val_mel_loss=vm[1], val_dur_loss=vm[2], val_stop_loss=vm[3])
+                if acc is not None:
+                    rec.update({k: v for k, v in step.read_val_metrics(acc).items() if v is not None})
                 if vm[0] < best - cfg.early_stopping_min_delta:
                     best, best_epoch, since_best = vm[0], epoch, 0
                     if rank == 0:

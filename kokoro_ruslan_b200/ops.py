@@ -520,6 +520,25 @@ def spec_augment(x, spans, n_time: int, n_feat: int):
                                 c_int(D), c_int(n_time), c_int(n_feat), _stream()), "kr_spec_augment")
 
 
+def val_metrics_acc_floats() -> int:
+    return int(lib().kr_val_metrics_acc_floats())
+
+
+def val_metrics(mel_pred, mel_tgt, pitch_pred, pitch_tgt, mel_lengths, acc):
+    """Folds one validation batch into acc (see kr_val_metrics)."""
+    B, T, C = mel_tgt.shape
+    mel_pred, mel_tgt = mel_pred.contiguous(), mel_tgt.contiguous()
+    Tp = 0
+    if pitch_pred is not None:
+        pitch_pred = pitch_pred.contiguous()
+        Tp = pitch_pred.shape[1]
+    if pitch_tgt is not None:
+        pitch_tgt = pitch_tgt.contiguous()
+    assert mel_lengths.dtype == torch.int64 and acc.dtype == torch.float32
+    check(lib().kr_val_metrics(_ptr(mel_pred), _ptr(mel_tgt), _ptr(pitch_pred), _ptr(pitch_tgt), _ptr(mel_lengths.contiguous()),
+                               _ptr(acc), c_int(B), c_int(T), c_int(Tp), c_int(C), _stream()), "kr_val_metrics")
+
+
 def zero_(t: torch.Tensor) -> torch.Tensor:
     """In-place zero fill of a contiguous tensor through cudaMemsetAsync (no fill kernel)."""
     assert t.is_contiguous()

@@ -426,10 +426,25 @@ class TrainStep:
         return losses
 
     @torch.no_grad()
-    def eval_losses(self, batch: Dict[str, torch.Tensor], use_ema: bool = True) -> torch.Tensor:
+    def new_val_metrics(self) -> torch.Tensor:
+        """Zeroed device accumulator for eval_losses(..., metrics=acc): one per validation epoch."""
+        from . import ops
+        return ops.zero_(torch.empty(ops.val_metrics_acc_floats(), dtype=torch.float32, device=self.device))
+
+    @staticmethod
+    def read_val_metrics(acc: torch.Tensor) -> Dict[str, Optional[float]]:
+        """The epoch's ONE device read (trainer.py:1933-1934: None when no batch contributed)."""
+        a = acc[:4].cpu().tolist()
+        return {"val_spectral_convergence": a[0] / a[1] if a[1] > 0 else None,
+                "val_f0_rmse": a[2] / a[3] if a[3] > 0 else None}
+
+    @torch.no_grad()
+    def eval_losses(self, batch: Dict[str, torch.Tensor], use_ema: bool = True,
+                    metrics: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Validation forward (reference trainer.py:1771-1985, validate_epoch): the model in eval() mode — dropout and
         stochastic depth off, SpecAugment off — evaluated with the EMA weights (`use_ema`, trainer.py:1790-1806), returns
-        the un-scaled losses[6] of the batch.  Gradients, optimizer state and the RNG step are left untouched.  Eager
+        the un-scaled losses[6] of the batch; with `metrics` (new_val_metrics()) the batch's spectral convergence and F0 RMSE
+        are folded into that device accumulator.  Gradients, optimizer state and the RNG step are left untouched.  Eager
         (validation runs once per epoch); the bf16 operand copy of the EMA weights is a scratch buffer."""
         eng, st = self.engine, self.engine.store
         batch = self._cap(batch)
@@ -449,6 +464,9 @@ class TrainStep:
                                   dev["energies"], dev["stress_indices"], expanded_len=Tp)
             losses, _ = eng.losses(outs, dev["mel_specs"], dev["phoneme_durations"], dev["stop_token_targets"],
                                    dev["pitches"], dev["energies"], dev["mel_lengths"], dev["phoneme_lengths"])
+            if metrics is not None:     # spectral convergence / F0 RMSE accumulated on the device (trainer.py:1868-1916)
+                from . import ops
+                ops.val_metrics(outs[0], dev["mel_specs"], outs[3], dev["pitches"], dev["mel_lengths"], metrics)
             return losses.clone()
         finally:
             st.params, st.shadow, eng.training, eng.spec_spans = saved

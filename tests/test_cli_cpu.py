@@ -172,3 +172,42 @@ def test_data_parallel_ranks_split_every_epoch_evenly():
     assert [h["batches"] for h in seen[0][0]["history"]] == [h["batches"] for h in seen[1][0]["history"]]
     assert len(seen[0][1]) == len(seen[1][1]) > 0            # same number of micro-steps on both ranks (no hang)
     assert [c[1:] for c in seen[0][1]] == [c[1:] for c in seen[1][1]]      # same window structure -> same collectives
+
+
+def test_validation_metrics_are_one_accumulator_per_epoch(tmp_path):
+    """cfg.val_metrics: the loop hands ONE accumulator per validation epoch to every eval_losses call and reads it once
+    (reference trainer.py:1868-1916 syncs four times per utterance instead)."""
+    from kokoro_ruslan_b200 import cli
+
+    class Step(_StubStep):
+        def __init__(self):
+            super().__init__([1.0, 0.9])
+            self.accs, self.reads = [], 0
+
+        def new_val_metrics(self):
+            self.accs.append(torch.zeros(8))
+            return self.accs[-1]
+
+        def eval_losses(self, batch, use_ema=True, metrics=None):
+            assert metrics is self.accs[-1]
+            metrics[:4] += torch.tensor([0.5, 1.0, 0.25, 1.0])
+            return super().eval_losses(batch, use_ema)
+
+        def read_val_metrics(self, acc):
+            self.reads += 1
+            return {"val_spectral_convergence": float(acc[0] / acc[1]), "val_f0_rmse": float(acc[2] / acc[3])}
+
+    ds = cli.SyntheticDataset(16, seed=2, min_frames=60, max_frames=120)
+    train_ds, val_ds = cli.split_dataset(ds, 0.25, seed=3)
+    cfg = cli.RunConfig(output_dir=str(tmp_path), num_epochs=2, max_frames_per_batch=400, min_batch_size=1,
+                        max_batch_size=4, save_every=0, val_metrics=True)
+    step = Step()
+    out = cli.train(cfg, train_ds, val_ds, step, log=lambda s: None)
+    assert len(step.accs) == 2 and step.reads == 2
+    for h in out["history"]:
+        assert h["val_spectral_convergence"] == 0.5 and h["val_f0_rmse"] == 0.25
+    # default: the stub without the metrics surface / cfg.val_metrics False keeps the plain call
+    step2 = _StubStep([1.0])
+    cfg.val_metrics = False
+    cli.train(cfg, train_ds, val_ds, step2, log=lambda s: None)
+    assert step2.evals > 0
