@@ -1,0 +1,177 @@
+"""Checkpoint pieces of the training path in the reference's on-disk format
+(src/kokoro/training/trainer.py:1994-2031, ``save_checkpoint_with_scaler``; resume rules
+training/checkpoint_manager.py:360-525).
+
+* ``optimizer_state_dict`` / ``load_optimizer_state_dict`` — the fused optimizer's flat Adam moment buffers presented
+  as (and restored from) a ``torch.optim.AdamW.state_dict()``: ten param groups in the reference's order
+  (``_setup_optimizer``, trainer.py:446-689; SURVEY A13'), parameters numbered consecutively group by group in
+  ``named_parameters()`` order, per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq`` in the reference's tensor shapes
+  (conv weights permuted back from the tap-major layout the kernels use).  A checkpoint whose group layout differs is
+  not an error: like the reference (checkpoint_manager.py:478-507) the moments then restart from zero.
+* ``AsyncCheckpointWriter`` — device → pinned-host snapshot on a side stream, ``torch.save`` on a worker thread: the
+  training stream waits for the D2H copies of the ~0.8 GB state (weights, EMA, two moment buffers; tens of milliseconds
+  over PCIe 5), not for serialisation or the file system.
+
+Pure tensor plumbing: no kernels, works on whatever device the ParamStore lives on.
+"""
+from __future__ import annotations
+
+import os
+import threading
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from .optim import CTRL_FIELDS, group_hparams, group_of
+
+GROUP_NAMES = ["encoder", "encoder_ffn_decay", "decoder_other_no_decay", "decoder_other_decay", "decoder_attn_decay",
+               "decoder_attn_no_decay", "decoder_ffn_decay", "decoder_ffn_no_decay", "variance_embed", "stop_head"]
+_STEP = CTRL_FIELDS.index("step")
+
+
+def group_layout(names: List[str]) -> List[List[str]]:
+    """Parameter names per AdamW group, each in named_parameters() order (how the reference fills its groups)."""
+    groups: List[List[str]] = [[] for _ in GROUP_NAMES]
+    for n in names:
+        groups[group_of(n)].append(n)
+    return groups
+
+
+def optimizer_state_dict(opt, lrs: Optional[List[float]] = None, step: Optional[int] = None) -> Dict:
+    """``torch.optim.AdamW.state_dict()``-shaped snapshot (CPU tensors) of a FusedAdamW."""
+    st, cfg = opt.store, opt.cfg
+    if step is None:
+        step = int(opt.ctrl.cpu()[_STEP])
+    if lrs is None:
+        lrs = [float(x) for x in opt.g_lr.cpu().tolist()]
+    hp = group_hparams(cfg)
+    state: Dict[int, Dict[str, torch.Tensor]] = {}
+    param_groups = []
+    idx = 0
+    for g, names in enumerate(group_layout(st.order)):
+        ids = []
+        for n in names:
+            if step > 0:                              # torch creates a parameter's state at its first step
+                state[idx] = {"step": torch.tensor(float(step)),
+                              "exp_avg": st.ref_view(st.exp_avg, n).detach().cpu().contiguous().clone(),
+                              "exp_avg_sq": st.ref_view(st.exp_avg_sq, n).detach().cpu().contiguous().clone()}
+            ids.append(idx)
+            idx += 1
+        param_groups.append({"lr": float(lrs[g]), "betas": tuple(cfg.adam_betas), "eps": cfg.adam_eps,
+                             "weight_decay": float(hp[g][1]), "amsgrad": False, "maximize": False, "foreach": None,
+                             "capturable": False, "differentiable": False, "fused": True,
+                             "decoupled_weight_decay": True, "name": GROUP_NAMES[g],
+                             "initial_lr": cfg.learning_rate * hp[g][0], "params": ids})
+    return {"state": state, "param_groups": param_groups}
+
+
+def load_optimizer_state_dict(opt, sd: Optional[Dict], log: Callable[[str], None] = lambda s: None) -> bool:
+    """Restores the Adam moments and the step counter.  Returns False (moments zeroed, counter kept at the caller's
+    value) when the checkpoint's group layout does not match — the reference's behaviour for a changed group count."""
+    st = opt.store
+    layout = group_layout(st.order)
+
+    def restart(why: str) -> bool:
+        log(f"optimizer state not loaded ({why}): Adam moments restart from zero")
+        st.exp_avg.zero_()
+        st.exp_avg_sq.zero_()
+        return False
+
+    if not sd or "param_groups" not in sd or "state" not in sd:
+        return restart("no optimizer_state_dict")
+    pgs = sd["param_groups"]
+    if len(pgs) != len(layout) or any(len(pg["params"]) != len(names) for pg, names in zip(pgs, layout)):
+        return restart(f"{len(pgs)} param groups of sizes {[len(pg['params']) for pg in pgs]} in the checkpoint, "
+                       f"{[len(n) for n in layout]} here")
+    state = sd["state"]
+    step = 0
+    with torch.no_grad():
+        for pg, names in zip(pgs, layout):
+            for pid, n in zip(pg["params"], names):
+                s = state.get(pid, state.get(str(pid)))
+                if s is None:                                      # a parameter that never received a gradient
+                    st.ref_view(st.exp_avg, n).zero_()
+                    st.ref_view(st.exp_avg_sq, n).zero_()
+                    continue
+                want = tuple(st.ref_view(st.exp_avg, n).shape)
+                if tuple(s["exp_avg"].shape) != want:
+                    return restart(f"shape of {n}: {tuple(s['exp_avg'].shape)} vs {want}")
+                st.ref_view(st.exp_avg, n).copy_(s["exp_avg"].to(st.device, torch.float32))
+                st.ref_view(st.exp_avg_sq, n).copy_(s["exp_avg_sq"].to(st.device, torch.float32))
+                step = max(step, int(float(s["step"])))
+        ctrl = opt.ctrl.cpu()
+        ctrl[_STEP] = step
+        opt.ctrl.copy_(ctrl)
+    return True
+
+
+class AsyncCheckpointWriter:
+    """``writer.save(path, tensors_and_scalars)``: snapshots every tensor of the (nested) dict into host memory — pinned
+    and through a side stream when it lives on a CUDA device — and hands the file write to a worker thread.
+    ``wait()`` blocks until every pending file is on disk (call it before reading a checkpoint back, and at exit)."""
+
+    def __init__(self):
+        self._threads: List[threading.Thread] = []
+        self._errors: List[BaseException] = []
+        self._stream = None
+
+    def _snapshot(self, obj):
+        if isinstance(obj, torch.Tensor):
+            if obj.is_cuda:
+                host = torch.empty(obj.shape, dtype=obj.dtype, pin_memory=True)
+                host.copy_(obj.detach(), non_blocking=True)
+                return host
+            return obj.detach().clone()
+        if isinstance(obj, dict):
+            return {k: self._snapshot(v) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(self._snapshot(v) for v in obj)
+        return obj
+
+    def save(self, path: str, payload: Dict) -> None:
+        event = None
+        if torch.cuda.is_available() and any(t.is_cuda for t in _tensors(payload)):
+            if self._stream is None:
+                self._stream = torch.cuda.Stream()
+            self._stream.wait_stream(torch.cuda.current_stream())      # the snapshot sees the state as of this call
+            with torch.cuda.stream(self._stream):
+                snap = self._snapshot(payload)
+                event = torch.cuda.Event()
+                event.record(self._stream)
+            # the training stream must not overwrite the buffers before the copies have read them
+            torch.cuda.current_stream().wait_stream(self._stream)
+        else:
+            snap = self._snapshot(payload)
+
+        def work():
+            try:
+                if event is not None:
+                    event.synchronize()
+                tmp = path + ".tmp"
+                torch.save(snap, tmp)
+                os.replace(tmp, path)                                   # readers never see a half-written file
+            except BaseException as exc:                               # surfaced by wait()
+                self._errors.append(exc)
+
+        t = threading.Thread(target=work, name="kokoro-ckpt-writer", daemon=False)
+        t.start()
+        self._threads.append(t)
+
+    def wait(self) -> None:
+        for t in self._threads:
+            t.join()
+        self._threads = []
+        if self._errors:
+            err, self._errors = self._errors[0], []
+            raise RuntimeError(f"asynchronous checkpoint write failed: {err}") from err
+
+
+def _tensors(obj):
+    if isinstance(obj, torch.Tensor):
+        yield obj
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            yield from _tensors(v)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            yield from _tensors(v)

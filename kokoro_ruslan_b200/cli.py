@@ -224,7 +224,9 @@ def find_latest_checkpoint(output_dir: str) -> Optional[str]:
 
 def resume(cfg: RunConfig, step, log: Callable[[str], None] = print) -> int:
     """Loads weights (+ EMA, scheduler counters) from cfg.resume_checkpoint ("auto" = latest in the output directory);
-    returns the epoch index to continue with.  Adam moments are not part of this path's checkpoints: they restart."""
+    returns the epoch index to continue with.  Adam moments are restored from `optimizer_state_dict` when its ten-group
+    layout matches (ours, or a reference checkpoint written with the un-collapsed groups); otherwise they restart from
+    zero, which is also what the reference does for a changed group count (checkpoint_manager.py:478-507)."""
     path = cfg.resume_checkpoint
     if not path:
         return 0
@@ -248,6 +250,9 @@ def resume(cfg: RunConfig, step, log: Callable[[str], None] = print) -> int:
             step.sched.load_state_dict(ck["scheduler_state_dict"])
         except (KeyError, TypeError):
             pass                                   # a reference-trainer checkpoint: its OneCycleLR state does not apply
+    if hasattr(step, "opt"):
+        from .checkpoint import load_optimizer_state_dict
+        load_optimizer_state_dict(step.opt, ck.get("optimizer_state_dict"), log)
     log(f"resumed from {path} (epoch {int(ck.get('epoch', -1)) + 1})")
     return int(ck.get("epoch", -1)) + 1
 
@@ -325,6 +330,9 @@ def save_checkpoint(cfg: RunConfig, step, epoch: int, rec: Dict, best: float, be
             "val_mel_loss": rec.get("val_mel_loss"), "val_dur_loss": rec.get("val_dur_loss"),
             "val_stop_loss": rec.get("val_stop_loss"), "best_val_loss": best, "best_val_epoch": best_epoch,
             "config": dict(cfg.__dict__)}
+    if hasattr(step, "opt"):                          # Adam moments + step in torch.optim.AdamW.state_dict() form
+        from .checkpoint import optimizer_state_dict
+        ckpt["optimizer_state_dict"] = optimizer_state_dict(step.opt)
     torch.save(ckpt, path)
     return path
 

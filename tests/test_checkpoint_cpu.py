@@ -1,0 +1,143 @@
+"""Optimizer-state checkpoints in torch.optim.AdamW's own format and the asynchronous writer —
+pure tensor plumbing, exercised on a CPU ParamStore against torch.optim.AdamW itself."""
+import os
+
+import pytest
+import torch
+
+
+def _tiny():
+    from kokoro_ruslan_b200.optim import FusedAdamW, OptimConfig
+    from kokoro_ruslan_b200.params import ModelConfig, ParamStore
+    cfg = ModelConfig(vocab_size=59, mel_dim=80, hidden_dim=128, n_encoder_layers=2, n_heads=2, encoder_ff_dim=256,
+                      n_decoder_layers=2, decoder_ff_dim=256, max_decoder_seq_len=400, variance_filter_size=64,
+                      n_variance_bins=256)
+    store = ParamStore(cfg, torch.device("cpu"), with_ema=True)
+    g = torch.Generator().manual_seed(0)
+    store.params.copy_(torch.randn(store.total, generator=g) * 0.05)
+    return store, FusedAdamW(store, OptimConfig())
+
+
+def _torch_adamw(store, opt):
+    """torch.optim.AdamW over reference-shaped copies of the parameters, grouped like the reference trainer."""
+    from kokoro_ruslan_b200.checkpoint import group_layout
+    from kokoro_ruslan_b200.optim import group_hparams
+    hp = group_hparams(opt.cfg)
+    params = {n: torch.nn.Parameter(store.ref_view(store.params, n).clone().contiguous()) for n in store.order}
+    groups = [{"params": [params[n] for n in names], "lr": opt.cfg.learning_rate * hp[g][0], "weight_decay": hp[g][1]}
+              for g, names in enumerate(group_layout(store.order))]
+    return torch.optim.AdamW(groups, betas=opt.cfg.adam_betas, eps=opt.cfg.adam_eps), params
+
+
+def test_layout_is_the_references_ten_groups():
+    from kokoro_ruslan_b200.checkpoint import GROUP_NAMES, group_layout
+    from kokoro_ruslan_b200.params import ModelConfig, param_specs
+    names = [n for n, _ in param_specs(ModelConfig(vocab_size=59))]
+    layout = group_layout(names)
+    assert len(GROUP_NAMES) == 10 and [len(g) for g in layout] == [94, 12, 52, 20, 48, 48, 12, 18, 2, 2]   # SURVEY A13'
+    flat = [n for g in layout for n in g]
+    assert sorted(flat) == sorted(names) and len(set(flat)) == 308
+
+
+def test_state_dict_loads_into_torch_adamw_and_back():
+    from kokoro_ruslan_b200.checkpoint import group_layout, load_optimizer_state_dict, optimizer_state_dict
+    store, opt = _tiny()
+    # (1) torch -> ours: two real AdamW steps, then restore the moments into the flat buffers
+    topt, params = _torch_adamw(store, opt)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(2):
+        for p in params.values():
+            p.grad = torch.randn(p.shape, generator=g)
+        topt.step()
+    tsd = topt.state_dict()
+    assert load_optimizer_state_dict(opt, tsd) is True
+    flat_names = [n for grp in group_layout(store.order) for n in grp]
+    for i, n in enumerate(flat_names):
+        assert torch.equal(store.ref_view(store.exp_avg, n), tsd["state"][i]["exp_avg"]), n
+        assert torch.equal(store.ref_view(store.exp_avg_sq, n), tsd["state"][i]["exp_avg_sq"]), n
+    from kokoro_ruslan_b200.optim import CTRL_FIELDS
+    assert int(opt.ctrl[CTRL_FIELDS.index("step")]) == 2
+    conv = [n for n in store.order if n.endswith("conv_layers.0.weight")][0]
+    assert store.ref_view(store.exp_avg, conv).shape[-1] == 3            # reference conv shape [C_out, C_in, 3]
+    # (2) ours -> torch: torch.optim.AdamW validates and accepts the snapshot, tensors identical
+    sd = optimizer_state_dict(opt)
+    assert [len(pg["params"]) for pg in sd["param_groups"]] == [len(grp) for grp in group_layout(store.order)]
+    assert [pg["params"][0] for pg in sd["param_groups"]][0] == 0 and sd["param_groups"][-1]["params"][-1] == len(flat_names) - 1
+    topt2, params2 = _torch_adamw(store, opt)
+    topt2.load_state_dict(sd)
+    st2 = topt2.state_dict()["state"]
+    for i in range(len(flat_names)):
+        assert torch.equal(st2[i]["exp_avg"], tsd["state"][i]["exp_avg"]) and float(st2[i]["step"]) == 2.0
+    # (3) a fresh optimizer (no step yet) has no per-parameter state, like torch
+    store3, opt3 = _tiny()
+    assert optimizer_state_dict(opt3)["state"] == {}
+
+
+def test_mismatching_layout_restarts_the_moments():
+    from kokoro_ruslan_b200.checkpoint import load_optimizer_state_dict, optimizer_state_dict
+    store, opt = _tiny()
+    store.exp_avg.fill_(1.0)
+    store.exp_avg_sq.fill_(2.0)
+    sd = optimizer_state_dict(opt, step=5)
+    collapsed = {"state": sd["state"], "param_groups": [dict(sd["param_groups"][0],
+                                                             params=[i for pg in sd["param_groups"] for i in pg["params"]])]}
+    msgs = []
+    assert load_optimizer_state_dict(opt, collapsed, msgs.append) is False      # the torch.compile single-group collapse
+    assert float(store.exp_avg.abs().sum()) == 0.0 and float(store.exp_avg_sq.abs().sum()) == 0.0
+    assert msgs and "restart" in msgs[0]
+    assert load_optimizer_state_dict(opt, None) is False
+
+
+def test_cli_checkpoint_round_trip_with_moments(tmp_path):
+    from kokoro_ruslan_b200 import cli
+    store, opt = _tiny()
+    g = torch.Generator().manual_seed(2)
+    store.exp_avg.copy_(torch.randn(store.total, generator=g))
+    store.exp_avg_sq.copy_(torch.rand(store.total, generator=g))
+    want_m, want_v = store.exp_avg.clone(), store.exp_avg_sq.clone()
+    from kokoro_ruslan_b200.optim import CTRL_FIELDS
+    opt.ctrl[CTRL_FIELDS.index("step")] = 11
+
+    class Step:
+        def __init__(self, store, opt):
+            self.store, self.opt = store, opt
+            self.sched = type("S", (), {"current_optimizer_step": 11, "state_dict": lambda s: {"current_optimizer_step": 11,
+                                                                                                "sched_step": 11},
+                                        "load_state_dict": lambda s, sd: None})()
+
+        def state_dict(self):
+            return self.store.state_dict()
+
+        def load_state_dict(self, sd):
+            for n in self.store.order:
+                self.store.ref_view(self.store.params, n).copy_(sd[n])
+
+    cfg = cli.RunConfig(output_dir=str(tmp_path))
+    path = cli.save_checkpoint(cfg, Step(store, opt), 3, {"train_loss": 1.0}, 0.5, 2)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck["optimizer_state_dict"]) == {"state", "param_groups"} and len(ck["optimizer_state_dict"]["param_groups"]) == 10
+    store2, opt2 = _tiny()
+    store2.ema = None
+    cfg.resume_checkpoint = path
+    assert cli.resume(cfg, Step(store2, opt2), log=lambda s: None) == 4
+    # padding between 64-element aligned tensors is not part of any tensor: compare tensor by tensor
+    for n in store.order:
+        assert torch.equal(store2.ref_view(store2.exp_avg, n), store.ref_view(want_m, n))
+        assert torch.equal(store2.ref_view(store2.exp_avg_sq, n), store.ref_view(want_v, n))
+    assert int(opt2.ctrl[CTRL_FIELDS.index("step")]) == 11
+
+
+def test_async_writer_snapshots_and_surfaces_errors(tmp_path):
+    from kokoro_ruslan_b200.checkpoint import AsyncCheckpointWriter
+    w = AsyncCheckpointWriter()
+    t = torch.arange(10.0)
+    path = os.path.join(str(tmp_path), "a.pth")
+    w.save(path, {"x": t, "nested": {"y": [t * 2, 3]}, "epoch": 4})
+    t.add_(100.0)                                    # mutate after save(): the snapshot must not see it
+    w.wait()
+    back = torch.load(path, weights_only=False)
+    assert torch.equal(back["x"], torch.arange(10.0)) and torch.equal(back["nested"]["y"][0], torch.arange(10.0) * 2)
+    assert back["epoch"] == 4 and not os.path.exists(path + ".tmp")
+    w.save(os.path.join(str(tmp_path), "no_such_dir", "b.pth"), {"x": t})
+    with pytest.raises(RuntimeError):
+        w.wait()
