@@ -1,0 +1,73 @@
+"""Micro-benchmark of the feature-extraction kernels at the bench shape (8 utterances x 800 frames),
+CUDA-graph replays, with the HBM roofline each one is bounded by.  Prints one JSON line per kernel.
+
+Algorithmic bytes: kr_mel_stft 1 KB of unique waveform + 320 B per frame; kr_pitch_frames 1 KB of
+unique waveform (hop 256 x 4 B; the 2048-sample windows overlap 8x in L2) + 12 B per frame; kr_energy_frames 320 B + 4 B."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from kokoro_ruslan_b200.features import EnergyExtractor, FeaturePipeline, LogMelSpectrogram, PitchExtractor  # noqa: E402
+
+
+def bench(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def peak_gbs():
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        for k in ("hbm_copy_gbs", "hbm_gbs", "hbm_copy_GBps"):
+            if k in d:
+                return float(d[k]), "MEASURED_PEAKS.json"
+    except (OSError, ValueError):
+        pass
+    return 6548.8, "round-1 measured copy bandwidth (fallback)"
+
+
+def main():
+    B, frames = 8, 800
+    n = 256 * (frames - 1) + 100
+    wav = torch.randn(B, n, device="cuda") * 0.1
+    peak, src = peak_gbs()
+    mel_tr = LogMelSpectrogram()
+    mel = mel_tr(wav)
+    rows = [
+        ("kr_mel_stft", lambda: mel_tr(wav), B * frames * (1024 + 320)),
+        ("kr_pitch_frames+track", lambda: PitchExtractor.extract_pitch(wav), B * frames * (1024 + 12 + 16)),
+        ("kr_energy_frames+norm", lambda: EnergyExtractor.extract_energy_from_mel(mel, False, channel_major=True,
+                                                                                  exp_input=True), B * frames * (320 + 12)),
+    ]
+    for name, fn, nbytes in rows:
+        t = bench(fn)
+        print(json.dumps({"kernel": name, "us": round(t * 1e6, 2), "frames_per_s": round(B * frames / t),
+                          "roofline": {"bound": "hbm", "achieved": round(nbytes / t / 1e9, 2), "peak": peak, "unit": "GB/s",
+                                       "frac": round(nbytes / t / 1e9 / peak, 4), "peak_source": src}}))
+    pipe = FeaturePipeline()
+    lens = torch.full((B,), n, dtype=torch.int64, device="cuda")      # device-resident: no H2D inside graph capture
+    t = bench(lambda: pipe(wav, lens), iters=5)
+    print(json.dumps({"kernel": "FeaturePipeline (mel + pitch + energy)", "us": round(t * 1e6, 2),
+                      "frames_per_s": round(B * frames / t)}))
+
+
+if __name__ == "__main__":
+    main()
