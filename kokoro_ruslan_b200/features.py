@@ -197,3 +197,55 @@ class FeaturePipeline:
         energy = EnergyExtractor.extract_energy_from_mel(mel, log_domain=False, frames=mel_lengths, channel_major=True,
                                                          exp_input=True)             # :813-815
         return {"mel_spec": mel, "pitch": pitch, "energy": energy, "mel_lengths": mel_lengths}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Speed perturbation (data/dataset.py:674-684): torchaudio.functional.resample with torchaudio's defaults, batched
+# ----------------------------------------------------------------------------------------------------------------
+def resample(waveform: torch.Tensor, orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99,
+             lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``torchaudio.functional.resample(waveform, orig_freq, new_freq)`` (Hann-windowed sinc) for (N,) or (B, N) CUDA
+    tensors.  ``lengths`` (new, optional): per-row sample counts of a padded batch; rows are zero beyond
+    ``ceil(new * len / orig)``.  No filter bank is materialised (csrc/kr_resample_core.cuh)."""
+    _need_cuda(waveform, "resample")
+    if int(orig_freq) != orig_freq or int(new_freq) != new_freq:
+        raise Exception("Frequencies must be of integer type to ensure quality resampling computation.")
+    if lowpass_filter_width <= 0:
+        raise ValueError("Low pass filter width should be positive.")
+    squeeze = waveform.dim() == 1
+    x = (waveform.unsqueeze(0) if squeeze else waveform).to(torch.float32).contiguous()
+    if int(orig_freq) == int(new_freq):
+        return waveform
+    B, n_max = x.shape
+    L = lib()
+    L.kr_resample_length.restype = ctypes.c_longlong
+    m_max = int(L.kr_resample_length(ctypes.c_longlong(n_max), ctypes.c_int(int(orig_freq)), ctypes.c_int(int(new_freq))))
+    if lengths is not None:
+        lengths = lengths.to(x.device, torch.int64).contiguous()
+    y = torch.empty(B, m_max, dtype=torch.float32, device=x.device)
+    check(L.kr_resample(_ptr(x), _ptr(lengths), _ptr(y), ctypes.c_int(B), ctypes.c_longlong(n_max), ctypes.c_longlong(m_max),
+                        ctypes.c_int(int(orig_freq)), ctypes.c_int(int(new_freq)), ctypes.c_int(int(lowpass_filter_width)),
+                        ctypes.c_float(rolloff), _stream()), "kr_resample")
+    return y[0] if squeeze else y
+
+
+def speed_perturb(waveform: torch.Tensor, factor: float, sample_rate: int = 22050,
+                  lengths: Optional[torch.Tensor] = None):
+    """The dataset's speed perturbation, data/dataset.py:677-684: resample to ``int(sample_rate * factor)`` and re-normalise
+    to unit peak.  Returns (waveform, lengths) — lengths are the resampled sample counts (None in, None out)."""
+    if factor == 1.0:
+        return waveform, lengths
+    new_sr = int(sample_rate * factor)
+    y = resample(waveform, sample_rate, new_sr, lengths=lengths)
+    y2 = y.unsqueeze(0) if y.dim() == 1 else y
+    B, m_max = y2.shape
+    new_len = None
+    if lengths is not None:
+        g = math.gcd(sample_rate, new_sr)
+        o, n = sample_rate // g, new_sr // g
+        new_len = (lengths.to(y.device, torch.int64) * n + o - 1) // o
+    peak = torch.empty(B, dtype=torch.float32, device=y.device)
+    check(lib().kr_wave_peak(_ptr(y2), _ptr(new_len), _ptr(peak), ctypes.c_int(B), ctypes.c_longlong(m_max), _stream()),
+          "kr_wave_peak")
+    out = y2 / (peak[:, None] + 1e-9)
+    return (out[0] if y.dim() == 1 else out), new_len

@@ -91,3 +91,19 @@ def test_feature_pipeline_full_size():
         e = of.extract_energy_from_mel(np.exp(mel.T.astype(np.float64)).astype(np.float32), False)
         assert float(np.abs(out["energy"][b, :T].cpu().numpy() - e).max()) < 1e-3
         assert float(out["pitch"][b, T:].abs().sum()) == 0.0 and float(out["energy"][b, T:].abs().sum()) == 0.0
+
+
+def test_resample_matches_torchaudio_fixture():
+    from kokoro_ruslan_b200.features import resample, speed_perturb
+    f = np.load(os.path.join(HERE, "golden", "resample.npz"))
+    x = torch.from_numpy(f["x"]).cuda()
+    for factor in f["factors"]:
+        new = int(22050 * float(factor))
+        want, js, exact = f[f"y_{new}"], f[f"js_{new}"], f[f"exact_{new}"]
+        got = resample(x, 22050, new).cpu().numpy()
+        assert got.shape == want.shape
+        assert np.abs(got[:, js] - exact).max() < 5e-7, factor             # exact application of torchaudio's filter bank
+        assert np.abs(got - want).max() < max(2e-6, 2.5 * np.abs(want[:, js] - exact).max()), factor
+    y, lens = speed_perturb(x, 0.93, lengths=torch.tensor([12000, 7001]))
+    assert lens.tolist() == [11160, 6512] and float(y.abs().amax(dim=1).min()) == pytest.approx(1.0, abs=1e-6)
+    assert float(y[1, 6512:].abs().sum()) == 0.0
