@@ -234,26 +234,23 @@ class CudaDecodeBackend:
 
 
 class _GraphedStep:
+    """Frame 0 runs eagerly (it warms up lazy kernel attributes and the TMA-descriptor cache, which must not happen
+    under capture); the identical launch sequence is then captured once and replayed for every later frame.  Capture
+    only records: the device state is not advanced by it."""
+
     def __init__(self, fn, device):
         self.fn, self.device, self.graph = fn, device, None
 
     def __call__(self):
-        if self.graph is None:
-            # first call: run eagerly (this IS frame 0) on a side stream as graph capture requires a warmed-up path,
-            # then capture the identical launch sequence for the remaining frames
-            s = torch.cuda.Stream(device=self.device)
-            s.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(s):
-                self.fn()
-            torch.cuda.current_stream(self.device).wait_stream(s)
-            torch.cuda.synchronize(self.device)
-            g = torch.cuda.CUDAGraph()
-            # capture must not execute: the launches are only recorded, device state is untouched
-            with torch.cuda.graph(g):
-                self.fn()
-            self.graph = g
+        if self.graph is not None:
+            self.graph.replay()
             return
-        self.graph.replay()
+        self.fn()
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.fn()
+        self.graph = g
 
 
 class InferenceEngine:
