@@ -347,3 +347,24 @@ class InferenceEngine:
                           fmask.contiguous())
         mel, probs = loop.run(lo, hi, Tp, stop_threshold, post_expected_stop_threshold, forced=forced)
         return (mel, probs) if return_stop_probs else mel
+
+
+class Synthesizer:
+    """Phoneme indices -> waveform on the device: the acoustic half of ``KokoroTTS.text_to_speech``
+    (reference src/kokoro/inference/inference.py:489-560: ``model.forward_inference`` then
+    ``VocoderManager.mel_to_audio``) without the text front-end (phonemisation is host string processing and out of this
+    path's scope).  ``vocoder`` is a ``kokoro_ruslan_b200.hifigan.HiFiGANGenerator`` (or anything callable on a
+    (B, frames, n_mels) CUDA mel)."""
+
+    def __init__(self, model, vocoder):
+        self.model, self.vocoder = model, vocoder
+
+    @torch.no_grad()
+    def __call__(self, phoneme_indices: torch.Tensor, stress_indices: Optional[torch.Tensor] = None,
+                 **generate_kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Returns (audio (B, samples), mel (B, frames, n_mels)); samples = frames * hop (256)."""
+        mel = self.model.forward_inference(phoneme_indices, stress_indices=stress_indices, **generate_kwargs)
+        audio = self.vocoder(mel.contiguous())               # (B, T, 80) is auto-detected like the reference's forward
+        if audio.dim() == 3:
+            audio = audio.squeeze(1)
+        return audio, mel

@@ -104,3 +104,17 @@ def test_model_forward_inference_surface_and_graph_equals_eager(monkeypatch):
     monkeypatch.setenv("KR_DECODE_GRAPH", "0")
     b = m.forward_inference(idx, max_len_cap=96)
     assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_synthesizer_mel_to_waveform():
+    """forward_inference -> HiFi-GAN on the device: 256 samples per generated frame, finite audio in [-1, 1]."""
+    from kokoro_ruslan_b200.hifigan import HiFiGANConfig, HiFiGANGenerator
+    from kokoro_ruslan_b200.inference import Synthesizer
+    from kokoro_ruslan_b200.model import KokoroModel
+    m = KokoroModel(vocab_size=59)
+    m.eval()
+    voc = HiFiGANGenerator(HiFiGANConfig.get_default_config())
+    idx = torch.randint(1, 59, (1, 12), generator=torch.Generator().manual_seed(5)).cuda()
+    audio, mel = Synthesizer(m, voc)(idx, max_len_cap=64)
+    assert audio.shape == (1, mel.shape[1] * 256) and bool(torch.isfinite(audio).all())
+    assert float(audio.abs().max()) <= 1.0
