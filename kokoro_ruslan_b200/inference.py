@@ -321,8 +321,7 @@ class InferenceEngine:
             energy = eng._vp_fwd(va + "energy_predictor.", xg_frm, gf, fmask, {}, "energy")
             # pass 2: predicted values, clamped to [0, 1] (:410, :431), select the embeddings
             _, mem, fmask = expand(pitch.clamp(0.0, 1.0).contiguous(), energy.clamp(0.0, 1.0).contiguous())
-            eng._join_all()
-            return mem, fmask, log_dur, Tp
+            return mem, fmask, log_dur, Tp       # nothing above forks onto the engine's side streams
         finally:
             eng.training = was_training
 

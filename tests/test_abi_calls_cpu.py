@@ -1,0 +1,213 @@
+"""ctypes call sites vs the C prototypes of include/kokoro_b200.h, without a GPU: the Python wrappers of the newest entry
+points (feature extraction, resampler, decode step, validation metrics) are driven with CPU tensors against a RECORDING
+stand-in for libkokoro_b200.so, and every recorded call is checked against the header — argument count, and per
+argument the ctypes class the C type needs (a bare Python int for a `long long` parameter would be passed as a 32-bit
+int).  Catches wrong order / arity / width before the first hardware run; says nothing about the kernels themselves."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def prototypes():
+    header = open(os.path.join(ROOT, "include", "kokoro_b200.h")).read()
+    protos = {}
+    for m in re.finditer(r"^(?:const\s+)?(?:long long|\w+)\*?\s+(kr_\w+)\s*\(([^;]*?)\);", header, re.M | re.S):
+        name, args = m.group(1), re.sub(r"\s+", " ", m.group(2).strip())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        protos[name] = params
+    return protos
+
+
+def expected_ctype(param: str):
+    if "*" in param:
+        return "pointer"
+    t = param.rsplit(" ", 1)[0].replace("const ", "").strip()
+    return {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float}[t]
+
+
+class RecordingLib:
+    def __init__(self, returns=None):
+        self.calls, self.returns = [], returns or {}
+
+    def __getattr__(self, name):
+        if not name.startswith("kr_"):
+            raise AttributeError(name)
+
+        class Fn:
+            restype = ctypes.c_int
+
+            def __call__(fn, *args):
+                self.calls.append((name, args))
+                return self.returns.get(name, 0)
+        f = Fn()
+        object.__setattr__(self, name, f)
+        return f
+
+
+def check_calls(calls):
+    protos = prototypes()
+    assert calls
+    for name, args in calls:
+        assert name in protos, f"{name} is not declared in include/kokoro_b200.h"
+        params = protos[name]
+        assert len(args) == len(params), f"{name}: {len(args)} arguments passed, prototype has {len(params)}: {params}"
+        for i, (a, p) in enumerate(zip(args, params)):
+            want = expected_ctype(p)
+            if want == "pointer":
+                ok = a is None or isinstance(a, ctypes.c_void_p) or type(a).__name__ == "CArgObject"
+            else:
+                ok = isinstance(a, want)
+            assert ok, f"{name}: argument {i} ({p!r}) got {type(a).__name__}"
+
+
+@pytest.fixture()
+def rec(monkeypatch):
+    from kokoro_ruslan_b200 import _lib, features, ops
+    lib = RecordingLib({"kr_dec_state_size": 256, "kr_val_metrics_acc_floats": 128, "kr_resample_length": 1000,
+                        "kr_optim_ctrl_size": 64})
+    ptr = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())      # noqa: E731
+    for mod in (ops, features):
+        monkeypatch.setattr(mod, "lib", lambda: lib)
+        monkeypatch.setattr(mod, "_ptr", ptr)
+        monkeypatch.setattr(mod, "_stream", lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(_lib, "lib", lambda: lib)
+    monkeypatch.setattr(features, "_need_cuda", lambda t, what: None)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    return lib
+
+
+def test_feature_wrappers_match_the_header(rec):
+    from kokoro_ruslan_b200 import features
+    wav = torch.zeros(2, 6000)
+    lens = torch.tensor([6000, 4000])
+    features.PitchExtractor.extract_pitch(wav, lengths=lens)
+    features.PitchExtractor.extract_pitch(wav[0])
+    mel = torch.zeros(2, 30, 80)
+    features.EnergyExtractor.extract_energy_from_mel(mel, log_domain=True, frames=torch.tensor([30, 12]))
+    features.EnergyExtractor.extract_energy_from_mel(mel.transpose(1, 2).contiguous(), False, channel_major=True, exp_input=True)
+    features.resample(wav[:, :1000], 22050, 20506, lengths=torch.tensor([1000, 500]))
+    features.speed_perturb(wav[:, :1000], 0.93, lengths=torch.tensor([1000, 500]))
+    tr = features.LogMelSpectrogram(device="cpu")
+    tr(wav, lens)
+    pipe = features.FeaturePipeline(device="cpu")
+    out = pipe(wav, lens)
+    assert out["mel_spec"].shape == (2, 80, 24) and out["pitch"].shape == (2, 24) and out["energy"].shape == (2, 24)
+    assert out["mel_lengths"].tolist() == [24, 16]
+    names = {n for n, _ in rec.calls}
+    assert {"kr_pitch_frames", "kr_pitch_track", "kr_energy_frames", "kr_energy_norm", "kr_resample", "kr_resample_length",
+            "kr_wave_peak", "kr_mel_stft"} <= names
+    check_calls(rec.calls)
+
+
+def test_decode_backend_and_metrics_match_the_header(rec):
+    from kokoro_ruslan_b200 import inference, ops
+    D, H, B, Tp, cap = 128, 2, 2, 9, 64
+
+    class Store:
+        device = torch.device("cpu")
+        pe = torch.zeros(100, D)
+        rope_cos = torch.zeros(100, 32)
+        rope_sin = torch.zeros(100, 32)
+        shadow = torch.zeros(1)
+
+        def p(self, name):
+            return torch.zeros(3 * D * D)
+
+        def w(self, name):
+            return torch.zeros(D, D, dtype=torch.bfloat16)
+
+        def span(self, buf, first, rows, cols):
+            return torch.zeros(rows, cols, dtype=torch.bfloat16)
+
+    eng = type("Eng", (), {"store": Store(), "device": torch.device("cpu"), "D": D})()
+    be = inference.CudaDecodeBackend(eng)
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt)             # noqa: E731
+    bf = torch.bfloat16
+    state = z(64, dt=torch.int32)
+    be.dec_feed(state, z(B, 80), None, z(D, 80), z(D), be.pe, z(128, D), B, D, 80)
+    be.dec_feed(state, z(B, 80), z(B, cap, 80), z(D, 80), z(D), be.pe, z(128, D), B, D, 80)
+    qkv = z(128, 3 * D, dt=bf)
+    be.dec_attn(state, qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], z(64), z(64), z(64), z(B, cap, D, dt=bf),
+                z(B, cap, D, dt=bf), -1, None, z(128, D, dt=bf), B, H)
+    kv = z(B * Tp, 2 * D, dt=bf).view(B, Tp, 2 * D)
+    be.dec_attn(state, z(128, D, dt=bf), None, None, z(64), None, None, kv[:, :, :D], kv[:, :, D:], Tp,
+                z(B, Tp, dt=torch.uint8), z(128, D, dt=bf), B, H)
+    be.dec_finish(state, z(128, D), z(D), z(D), z(80, D), z(80), z(1, D), z(1), z(B, cap, 80), z(B, 80), z(cap), B, D, 80, cap)
+    acc = z(ops.val_metrics_acc_floats())
+    ops.val_metrics(z(B, 20, 80), z(B, 20, 80), z(B, 20), z(B, 20), torch.tensor([20, 7]), acc)
+    ops.val_metrics(z(B, 20, 80), z(B, 20, 80), None, None, torch.tensor([20, 7]), acc)
+    check_calls(rec.calls)
+    # the self-attention call passes the cache strides (row, utterance), the cross call the memory's
+    attn = [a for n, a in rec.calls if n == "kr_dec_attn"]
+    assert attn[0][13].value == D and attn[0][14].value == cap * D and attn[0][15].value == -1
+    assert attn[1][13].value == 2 * D and attn[1][14].value == Tp * 2 * D and attn[1][15].value == Tp
+
+
+def test_header_parser_sees_every_entry_point():
+    protos = prototypes()
+    assert len(protos) >= 69 and "kr_gemm_bf16" in protos and "kr_launch_count" in protos
+    assert protos["kr_dec_state_size"] == [] and len(protos["kr_pitch_frames"]) == 13
+
+
+def test_inference_engine_dry_run_on_the_recording_lib(rec, monkeypatch):
+    """InferenceEngine.generate end to end on CPU tensors with the recording library: no numerics, but every Python line of
+    the device path runs — engine calls in eval mode, geometry tables, buffer shapes / strides asserted by the wrappers,
+    cross K/V, DecodeLoop wiring, polling — and every C call it makes is checked against the header."""
+    from kokoro_ruslan_b200 import engine as engine_mod
+    from kokoro_ruslan_b200 import inference, ops, params
+    from kokoro_ruslan_b200.params import ModelConfig
+    monkeypatch.setenv("KR_DECODE_GRAPH", "0")
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    for mod in (engine_mod, params):
+        if hasattr(mod, "lib"):
+            monkeypatch.setattr(mod, "lib", lambda: rec)
+    frames = {"n": 0}
+
+    class Finish:
+        restype = ctypes.c_int
+
+        def __call__(self, *args):
+            rec.calls.append(("kr_dec_finish", args))
+            st = (ctypes.c_int * 8).from_address(args[0].value)      # the stand-in "device" advances the state
+            if st[1]:
+                return 0                                             # done: the real kernel returns early too
+            st[0] += 1
+            frames["n"] = st[0]
+            if st[0] >= st[3] + 2:                                   # two frames past the minimum length
+                st[1], st[2] = 1, st[0]
+            return 0
+    object.__setattr__(rec, "kr_dec_finish", Finish())
+    cfg = ModelConfig(vocab_size=59, mel_dim=80, hidden_dim=128, n_encoder_layers=2, n_heads=2, encoder_ff_dim=256,
+                      n_decoder_layers=2, decoder_ff_dim=256, max_decoder_seq_len=400, variance_filter_size=64,
+                      n_variance_bins=256)
+    eng = engine_mod.AcousticEngine(cfg, device="cpu", with_ema=False, multi_stream=False)
+    inf = inference.InferenceEngine(eng)
+    idx = torch.randint(1, 59, (2, 11))
+    dur = torch.randint(1, 4, (2, 11))
+    dur[1, 8:] = 0
+    mel, probs = inf.generate(idx, torch.randint(0, 3, (2, 11)), durations=dur, return_stop_probs=True)
+    Tp = int(dur.sum(dim=1).max())
+    lo, hi = inference.generation_bounds(Tp, 400)
+    assert mel.shape == (2, lo + 2, 80) and probs.shape == (lo + 2,)
+    assert frames["n"] == lo + 2                                      # polling stopped calling once `done` was set ...
+    n_finish = sum(1 for n, _ in rec.calls if n == "kr_dec_finish")
+    assert n_finish == -(-(lo + 2) // 32) * 32                       # ... at the next multiple of the poll interval
+    names = [n for n, _ in rec.calls]
+    per_step = 2 + 2 * cfg.n_decoder_layers                          # feed + finish + 2 attentions per layer
+    assert names.count("kr_dec_attn") == 2 * cfg.n_decoder_layers * n_finish
+    assert names.count("kr_dec_feed") == n_finish and per_step == 6
+    # eval mode: no dropout specs reached the kernels, the engine's training flag is restored
+    assert eng.training is True
+    check_calls([c for c in rec.calls if c[0] in ("kr_dec_feed", "kr_dec_attn", "kr_dec_finish", "kr_lr_index",
+                                                   "kr_expand_adapt", "kr_embed_fwd", "kr_layernorm_fwd", "kr_glu_fwd",
+                                                   "kr_rmsnorm_resid_fwd", "kr_eq_mask_i64", "kr_scatter_rows",
+                                                   "kr_vp_head_fwd", "kr_gn_fwd", "kr_memset_zero", "kr_gemm_bf16",
+                                                   "kr_qkv_prep_fwd", "kr_attn_fwd")])
+    # predicted-duration path (no override): zeros from the stand-in -> Tp is padded to the 3-frame minimum
+    mem, fmask, log_dur, Tp0 = inf.encode_and_expand(idx, None)
+    assert Tp0 == 3 and mem.shape == (2 * 3, 128) and fmask.shape == (2, 3) and log_dur.shape == (2, 11)
