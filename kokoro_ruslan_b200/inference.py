@@ -138,13 +138,17 @@ class DecodeLoop:
             self._graph = be.capture(self.step)
         done = 0
         n_frames = 0
-        while not done:
+        for _ in range(hi // poll + 2):               # the device stops at t = hi at the latest: a bounded host loop
             for _ in range(poll):
                 self._graph()
             st = be.to_host(self.state)
             done, n_frames = int(st[ST_DONE]), int(st[ST_NFRAMES])
             if int(st[ST_T]) > hi:
                 raise RuntimeError("decode ran past its bound (corrupt device state)")
+            if done:
+                break
+        if not done:
+            raise RuntimeError(f"decode did not finish within {hi} frames (device state: t={int(st[ST_T])})")
         return self.mel_out[:, :n_frames].clone(), self.probs[:n_frames].clone()
 
 

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
               pytest.mark.xfail(reason="first hardware run of kernels validated by host emulation only", strict=False)]
 HERE = os.path.dirname(os.path.abspath(__file__))
 

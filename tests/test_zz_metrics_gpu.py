@@ -4,7 +4,7 @@ tests/test_metrics_emu_cpu.py) — non-strict xfail, sorts last."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
               pytest.mark.xfail(reason="first hardware run of a kernel validated by host emulation only", strict=False)]
 
 
