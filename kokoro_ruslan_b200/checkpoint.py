@@ -105,6 +105,51 @@ def load_optimizer_state_dict(opt, sd: Optional[Dict], log: Callable[[str], None
     return True
 
 
+def build_model_metadata(model_cfg, run_cfg=None) -> Dict:
+    """``model_metadata`` of the reference's checkpoints (training/checkpoint_manager.py:178-241, schema 2): the
+    architecture record its resume path demands (`checkpoint_manager.py:360-420`) and the inference controls.  Built from
+    the ModelConfig the engine was constructed with (the authoritative record here — the reference re-derives the FFN
+    widths from module attributes for the same reason) and the run's dropout settings."""
+    g = lambda name, default: getattr(run_cfg, name, default) if run_cfg is not None else default      # noqa: E731
+    return {
+        "schema_version": 2,
+        "architecture": {
+            "mel_dim": int(model_cfg.mel_dim), "hidden_dim": int(model_cfg.hidden_dim),
+            "n_encoder_layers": int(model_cfg.n_encoder_layers), "n_decoder_layers": int(model_cfg.n_decoder_layers),
+            "n_heads": int(model_cfg.n_heads), "encoder_ff_dim": int(model_cfg.encoder_ff_dim),
+            "decoder_ff_dim": int(model_cfg.decoder_ff_dim), "encoder_dropout": float(g("encoder_dropout", 0.15)),
+            "max_decoder_seq_len": int(model_cfg.max_decoder_seq_len), "use_variance_predictor": True,
+            "variance_filter_size": int(model_cfg.variance_filter_size),
+            "variance_kernel_size": int(model_cfg.variance_kernel_size),
+            "variance_dropout": float(g("variance_dropout", 0.1)), "n_variance_bins": int(model_cfg.n_variance_bins),
+            "pitch_min": 0.0, "pitch_max": 1.0, "energy_min": 0.0, "energy_max": 1.0,
+            "use_stochastic_depth": float(g("stochastic_depth_rate", 0.1)) > 0.0,
+            "stochastic_depth_rate": float(g("stochastic_depth_rate", 0.1)), "qk_norm": bool(model_cfg.qk_norm),
+            "ffn_output_norm": bool(model_cfg.ffn_output_norm), "vocab_size": int(model_cfg.vocab_size),
+        },
+        "inference_controls": {"max_len": 1200, "stop_threshold": 0.45, "min_len_ratio": 0.7, "min_len_floor": 12},
+    }
+
+
+def check_model_metadata(meta: Optional[Dict], model_cfg) -> List[str]:
+    """Differences between a checkpoint's architecture record and this engine (empty = compatible).  The reference
+    refuses to resume on a mismatch (checkpoint_manager.py:380-420); a checkpoint without the record is let through —
+    the strict state-dict load that follows is the real gate."""
+    if not meta or "architecture" not in meta:
+        return []
+    arch, bad = meta["architecture"], []
+    for key in ("mel_dim", "hidden_dim", "n_encoder_layers", "n_decoder_layers", "n_heads", "encoder_ff_dim",
+                "decoder_ff_dim", "variance_filter_size", "variance_kernel_size", "n_variance_bins", "vocab_size"):
+        if key in arch and int(arch[key]) != int(getattr(model_cfg, key)):
+            bad.append(f"{key}: checkpoint {arch[key]} vs model {getattr(model_cfg, key)}")
+    for key, want in (("pitch_min", 0.0), ("pitch_max", 1.0), ("energy_min", 0.0), ("energy_max", 1.0)):
+        if key in arch and float(arch[key]) != want:
+            bad.append(f"{key}: checkpoint {arch[key]} vs {want} (targets are normalised to [0, 1])")
+    if arch.get("use_variance_predictor") is False:
+        bad.append("use_variance_predictor: False in the checkpoint")
+    return bad
+
+
 class AsyncCheckpointWriter:
     """``writer.save(path, tensors_and_scalars)``: snapshots every tensor of the (nested) dict into host memory — pinned
     and through a side stream when it lives on a CUDA device — and hands the file write to a worker thread.

@@ -236,6 +236,12 @@ def resume(cfg: RunConfig, step, log: Callable[[str], None] = print) -> int:
             log(f"--resume auto: no checkpoint in {cfg.output_dir}, starting from scratch")
             return 0
     ck = torch.load(path, map_location="cpu", weights_only=False)
+    model_cfg = getattr(getattr(step, "engine", None), "cfg", None)
+    if model_cfg is not None and hasattr(model_cfg, "hidden_dim"):
+        from .checkpoint import check_model_metadata
+        bad = check_model_metadata(ck.get("model_metadata"), model_cfg)
+        if bad:
+            raise RuntimeError(f"checkpoint {path} was written for a different architecture: " + "; ".join(bad))
     step.load_state_dict(ck["model_state_dict"])
     ema = ck.get("ema_model_state_dict")
     st = step.store
@@ -333,6 +339,10 @@ def save_checkpoint(cfg: RunConfig, step, epoch: int, rec: Dict, best: float, be
     if hasattr(step, "opt"):                          # Adam moments + step in torch.optim.AdamW.state_dict() form
         from .checkpoint import optimizer_state_dict
         ckpt["optimizer_state_dict"] = optimizer_state_dict(step.opt)
+    model_cfg = getattr(getattr(step, "engine", None), "cfg", None)
+    if model_cfg is not None and hasattr(model_cfg, "hidden_dim"):
+        from .checkpoint import build_model_metadata
+        ckpt["model_metadata"] = build_model_metadata(model_cfg, cfg)
     torch.save(ckpt, path)
     return path
 

@@ -141,3 +141,52 @@ def test_async_writer_snapshots_and_surfaces_errors(tmp_path):
     w.save(os.path.join(str(tmp_path), "no_such_dir", "b.pth"), {"x": t})
     with pytest.raises(RuntimeError):
         w.wait()
+
+
+def test_model_metadata_matches_the_reference_schema_and_gates_resume(tmp_path):
+    from kokoro_ruslan_b200 import cli
+    from kokoro_ruslan_b200.checkpoint import build_model_metadata, check_model_metadata
+    from kokoro_ruslan_b200.params import ModelConfig
+    mc = ModelConfig(vocab_size=59)
+    meta = build_model_metadata(mc, cli.RunConfig())
+    # key set of build_model_metadata, reference training/checkpoint_manager.py:178-241
+    assert meta["schema_version"] == 2
+    assert set(meta["architecture"]) == {
+        "mel_dim", "hidden_dim", "n_encoder_layers", "n_decoder_layers", "n_heads", "encoder_ff_dim", "decoder_ff_dim",
+        "encoder_dropout", "max_decoder_seq_len", "use_variance_predictor", "variance_filter_size", "variance_kernel_size",
+        "variance_dropout", "n_variance_bins", "pitch_min", "pitch_max", "energy_min", "energy_max", "use_stochastic_depth",
+        "stochastic_depth_rate", "qk_norm", "ffn_output_norm", "vocab_size"}
+    assert set(meta["inference_controls"]) == {"max_len", "stop_threshold", "min_len_ratio", "min_len_floor"}
+    assert meta["architecture"]["encoder_ff_dim"] == 1536 and meta["architecture"]["encoder_dropout"] == 0.15
+    assert check_model_metadata(meta, mc) == [] and check_model_metadata(None, mc) == []
+    other = ModelConfig(vocab_size=59, hidden_dim=256, n_heads=4)
+    bad = check_model_metadata(meta, other)
+    assert len(bad) == 2 and bad[0].startswith("hidden_dim")
+    meta["architecture"]["pitch_max"] = 800.0
+    assert any("pitch_max" in b for b in check_model_metadata(meta, mc))
+
+    # through cli.save_checkpoint / cli.resume
+    store, opt = _tiny()
+    store.ema = None                                  # (the EMA restore path refreshes the bf16 shadow: a device op)
+
+    class Step:
+        def __init__(self, cfg):
+            self.store, self.opt = store, opt
+            self.engine = type("E", (), {"cfg": cfg})()
+            self.sched = type("S", (), {"current_optimizer_step": 0, "state_dict": lambda s: {}})()
+
+        def state_dict(self):
+            return self.store.state_dict()
+
+        def load_state_dict(self, sd):
+            pass
+
+    tiny = ModelConfig(vocab_size=59, hidden_dim=128, n_encoder_layers=2, n_heads=2, encoder_ff_dim=256, n_decoder_layers=2,
+                       decoder_ff_dim=256, max_decoder_seq_len=400, variance_filter_size=64)
+    cfg = cli.RunConfig(output_dir=str(tmp_path))
+    path = cli.save_checkpoint(cfg, Step(tiny), 0, {}, 1.0, 0)
+    assert torch.load(path, weights_only=False)["model_metadata"]["architecture"]["hidden_dim"] == 128
+    cfg.resume_checkpoint = path
+    assert cli.resume(cfg, Step(tiny), log=lambda s: None) == 1
+    with pytest.raises(RuntimeError, match="different architecture"):
+        cli.resume(cfg, Step(mc), log=lambda s: None)
