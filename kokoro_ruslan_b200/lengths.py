@@ -92,3 +92,21 @@ def length_regulate(encoder_outputs: torch.Tensor, durations: torch.Tensor,
         raise RuntimeError("kokoro_ruslan_b200.lengths needs CUDA tensors (no CPU fallback)")
     out, mask = _LengthRegulateFn.apply(encoder_outputs, durations, text_padding_mask)
     return out, mask.bool()
+
+
+def average_by_duration(values: torch.Tensor, durations: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Reference ``average_by_duration`` (lengths.py:156-208): frame-level (B, T) values -> token-level (B, P) means through
+    the durations.  Bit-identical to the reference's scatter formulation, quirks included (frames no token covers are
+    averaged into token 0; tokens starting past the last frame pile their labels onto frame T - 1) — see
+    csrc/kr_lengths_core.cuh."""
+    if not values.is_cuda:
+        raise RuntimeError("kokoro_ruslan_b200.lengths needs CUDA tensors (no CPU fallback)")
+    B, P = durations.shape
+    T = values.shape[1]
+    v = values.float().contiguous()
+    dur = durations.long().contiguous()
+    m = None if mask is None else mask.to(torch.uint8).contiguous()
+    label = torch.empty(B, T, dtype=torch.int32, device=v.device)
+    out = torch.empty(B, P, dtype=torch.float32, device=v.device)
+    ops.average_by_duration(v, dur, m, label, out)
+    return out.to(values.dtype)

@@ -520,6 +520,13 @@ def spec_augment(x, spans, n_time: int, n_feat: int):
                                 c_int(D), c_int(n_time), c_int(n_feat), _stream()), "kr_spec_augment")
 
 
+def average_by_duration(values, dur, mask, label, out):
+    B, P = dur.shape
+    T = values.shape[1]
+    check(lib().kr_average_by_duration(_ptr(values), _ptr(dur), _ptr(mask), _ptr(label), _ptr(out), c_int(B), c_int(P),
+                                       c_int(T), _stream()), "kr_average_by_duration")
+
+
 def val_metrics_acc_floats() -> int:
     return int(lib().kr_val_metrics_acc_floats())
 

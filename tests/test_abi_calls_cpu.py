@@ -141,6 +141,7 @@ def test_decode_backend_and_metrics_match_the_header(rec):
     acc = z(ops.val_metrics_acc_floats())
     ops.val_metrics(z(B, 20, 80), z(B, 20, 80), z(B, 20), z(B, 20), torch.tensor([20, 7]), acc)
     ops.val_metrics(z(B, 20, 80), z(B, 20, 80), None, None, torch.tensor([20, 7]), acc)
+    ops.average_by_duration(z(B, 20), torch.ones(B, 5, dtype=torch.int64), None, z(B, 20, dt=torch.int32), z(B, 5))
     check_calls(rec.calls)
     # the self-attention call passes the cache strides (row, utterance), the cross call the memory's
     attn = [a for n, a in rec.calls if n == "kr_dec_attn"]

@@ -1,0 +1,59 @@
+"""Host emulation of kr_average_by_duration (csrc/kr_lengths_core.cuh compiled by g++ -DKR_HOST_EMU) against fixtures
+from the LIVE reference function (tests/golden/make_golden_average.py) and the reference's own unit-test values
+(tests/unit/test_utils_lengths.py:77-91): bit-identical, quirks included."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    so = tmp_path_factory.mktemp("emu") / "lengths_emu.so"
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-I", os.path.join(ROOT, "kokoro_ruslan_b200", "csrc"),
+                    os.path.join(HERE, "emu", "lengths_emu.cpp"), "-o", str(so)], check=True)
+    return ctypes.CDLL(str(so))
+
+
+def run(lib, values, dur, mask=None):
+    values, dur = values.float().contiguous(), dur.long().contiguous()
+    B, T = values.shape
+    P = dur.shape[1]
+    label, out = torch.zeros(B, T, dtype=torch.int32), torch.full((B, P), float("nan"))
+    m = None if mask is None else mask.to(torch.uint8).contiguous()
+    p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())        # noqa: E731
+    assert lib.emu_average_by_duration(p(values), p(dur), p(m), p(label), p(out), B, P, T) == 0
+    return out
+
+
+def test_reference_unit_test_values(emu):
+    values = torch.tensor([[1.0, 2.0, 3.0, 4.0], [10.0, 20.0, 30.0, 40.0]])
+    durations = torch.tensor([[1, 3], [0, 4]])
+    avg = run(emu, values, durations)
+    assert torch.allclose(avg[0], torch.tensor([1.0, 3.0])) and torch.allclose(avg[1], torch.tensor([0.0, 25.0]))
+    avg2 = run(emu, values, durations, torch.tensor([[False, True], [False, False]]))
+    assert torch.allclose(avg2[0], torch.tensor([1.0, 0.0]))
+
+
+def test_bit_identical_to_live_reference_fixtures(emu):
+    f = np.load(os.path.join(HERE, "golden", "average_by_duration.npz"))
+    for k in range(4):
+        v, d, m = (torch.from_numpy(f[f"{n}{k}"]) for n in "vdm")
+        assert torch.equal(run(emu, v, d), torch.from_numpy(f[f"a{k}"])), k
+        assert torch.equal(run(emu, v, d, m), torch.from_numpy(f[f"am{k}"])), k
+
+
+def test_reference_quirks_are_reproduced(emu):
+    """Values checked against the live reference function when this test was written."""
+    # frames 3..5 are covered by no token: their label is 0, so token 0 averages them too -> (1+2+4+5+6)/5, not 1.5
+    got = run(emu, torch.tensor([[1.0, 2, 3, 4, 5, 6]]), torch.tensor([[2, 1]]))
+    assert torch.allclose(got, torch.tensor([[3.6, 3.0]]))
+    # durations past the last frame: tokens 1 and 2 pile their labels (1 + 2 = 3 >= P) onto frame T-1, which drops out
+    got = run(emu, torch.tensor([[1.0, 2, 3, 4]]), torch.tensor([[3, 2, 5]]))
+    assert torch.allclose(got, torch.tensor([[2.0, 0.0, 0.0]]))

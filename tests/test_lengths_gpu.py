@@ -56,3 +56,4 @@ def test_long_utterances_bit_exact_indices():
     lens = torch.empty(1, dtype=torch.int32, device="cuda")
     ops.lr_index_masked(dur.cuda(), pad.to(torch.uint8).cuda(), idx, lens)
     assert torch.equal(idx.cpu().long(), want) and int(lens[0]) == int(L[0]) and int(L[0]) > 1500
+
