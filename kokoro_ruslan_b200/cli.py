@@ -100,6 +100,8 @@ class RunConfig:
     resume_checkpoint: Optional[str] = None
     verbose: bool = False
     seed: int = 42
+    ema_decay: Optional[float] = None         # None: computed from the steps per epoch (config.py:85-86)
+    ema_half_life_epochs: float = 1.0
     # spectral convergence / F0 RMSE of the validation epoch as device reductions (reference trainer.py:1868-1916 always
     # computes them, with per-utterance host syncs); off by default until kr_val_metrics has had its first hardware run
     val_metrics: bool = False
@@ -370,7 +372,10 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     random.seed(cfg.seed)
     steps_per_epoch = max(1, len(list(iter(make_sampler(train_ds, cfg)))) // max(1, world))
     opt_steps = max(1, (steps_per_epoch + cfg.gradient_accumulation_steps - 1) // cfg.gradient_accumulation_steps)
-    step = TrainStep(ModelConfig(vocab_size=ds.vocab_size), OptimConfig(learning_rate=cfg.learning_rate),
+    # EMA half-life = ema_half_life_epochs (1.0) epochs of optimizer steps, the reference's default (trainer.py:808-822)
+    from .optim import recommended_ema_decay
+    ema_decay = cfg.ema_decay if cfg.ema_decay is not None else recommended_ema_decay(opt_steps, 1, cfg.ema_half_life_epochs)
+    step = TrainStep(ModelConfig(vocab_size=ds.vocab_size), OptimConfig(learning_rate=cfg.learning_rate, ema_decay=ema_decay),
                      ScheduleConfig(total_steps=cfg.num_epochs * opt_steps), device=f"cuda:{local}",
                      process_group=torch.distributed.group.WORLD if world > 1 else None,
                      dropout=DropoutConfig(encoder=cfg.encoder_dropout, decoder=cfg.decoder_dropout,

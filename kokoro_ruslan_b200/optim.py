@@ -53,6 +53,18 @@ class OptimConfig:
     ema_decay: float = 0.999
 
 
+def recommended_ema_decay(n_train: int, batch_size: int, k: float) -> float:
+    """EMA decay whose half-life is k epochs (reference utils/ema.py:6-27): exp(-ln 2 / (n_train / batch_size * k)),
+    clipped to [0.9, 0.9999]; 0.9999 for degenerate inputs.  The reference trainer calls it with the optimizer steps per
+    epoch as n_train and batch_size = 1 (training/trainer.py:808-822) when config.ema_decay is None — the default."""
+    if n_train <= 0 or batch_size <= 0:
+        return 0.9999
+    half_life_steps = (n_train / batch_size) * k
+    if half_life_steps <= 0:
+        return 0.9999
+    return max(0.9, min(math.exp(-math.log(2) / half_life_steps), 0.9999))
+
+
 GROUP_NAMES = ["encoder", "encoder_ffn_decay", "decoder_other_no_decay", "decoder_other_decay",
                "decoder_attn_decay", "decoder_attn_no_decay", "decoder_ffn_decay", "decoder_ffn_no_decay",
                "variance_embed", "stop_head"]

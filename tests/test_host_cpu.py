@@ -214,3 +214,15 @@ def test_batch_validation_error_conventions():
         validate_batch({**batch, "mel_lengths": [20, 20]})
     with pytest.raises(ValueError):
         validate_batch({**batch, "energies": torch.zeros(3, 20)})
+
+
+def test_recommended_ema_decay_matches_reference_formula():
+    """utils/ema.py:6-27 as the trainer calls it (trainer.py:808-822: n_train = optimizer steps per epoch, batch_size 1)."""
+    import math
+    from kokoro_ruslan_b200.optim import recommended_ema_decay
+    assert recommended_ema_decay(0, 1, 1.0) == 0.9999 and recommended_ema_decay(10, 0, 1.0) == 0.9999
+    assert recommended_ema_decay(100, 1, 0.0) == 0.9999
+    assert recommended_ema_decay(1000, 1, 1.0) == pytest.approx(math.exp(-math.log(2) / 1000))
+    assert recommended_ema_decay(3, 1, 1.0) == 0.9                       # clipped below
+    assert recommended_ema_decay(10 ** 6, 1, 1.0) == 0.9999              # clipped above
+    assert recommended_ema_decay(5000, 10, 2.0) == pytest.approx(math.exp(-math.log(2) / 1000))
