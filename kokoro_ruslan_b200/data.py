@@ -12,7 +12,6 @@ epoch).  B200-first difference: collated tensors are allocated in PINNED host me
 """
 from __future__ import annotations
 
-import math
 import random
 from typing import Dict, Iterator, List, Optional, Sequence
 

@@ -12,7 +12,6 @@ in the CUDA library (tcgen05 GEMM / flash attention + HBM kernels).  Dropout and
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 

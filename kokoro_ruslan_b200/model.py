@@ -22,7 +22,7 @@ from typing import Callable, Dict, Iterator, List, Optional, Tuple
 
 import torch
 
-from .engine import AcousticEngine, DropoutConfig, LossConfig
+from .engine import AcousticEngine, DropoutConfig
 from .params import ModelConfig
 
 

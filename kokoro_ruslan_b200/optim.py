@@ -8,9 +8,8 @@ src/kokoro/training/trainer.py:446-689) for an UN-compiled model, i.e. the inten
 """
 from __future__ import annotations
 
-import ctypes
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import torch

@@ -16,7 +16,7 @@ Two layout rules differ from the reference and are hidden at the state-dict boun
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import torch
