@@ -4,6 +4,7 @@ import argparse
 import json
 import os
 
+import pytest
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -211,3 +212,48 @@ def test_validation_metrics_are_one_accumulator_per_epoch(tmp_path):
     cfg.val_metrics = False
     cli.train(cfg, train_ds, val_ds, step2, log=lambda s: None)
     assert step2.evals > 0
+
+
+def test_main_wires_configs_into_the_step(tmp_path, monkeypatch, capsys):
+    """cli.main() end to end on a stand-in TrainStep (no device): the optimizer gets the half-life EMA decay computed
+    from the epoch's optimizer steps (reference trainer.py:808-822), the schedule its total step count, the dropout
+    configuration the reference's training values; checkpoints of the run carry optimizer state and model metadata."""
+    import math
+    from kokoro_ruslan_b200 import cli, parallel, train_step
+    from kokoro_ruslan_b200.optim import FusedAdamW
+    from kokoro_ruslan_b200.params import ModelConfig, ParamStore
+    made = {}
+
+    class FakeStep(_StubStep):
+        def __init__(self, model_cfg, optim_cfg, sched_cfg, device=None, process_group=None, dropout=None):
+            super().__init__([1.0, 0.9, 0.8])
+            made.update(model_cfg=model_cfg, optim_cfg=optim_cfg, sched_cfg=sched_cfg, device=device, dropout=dropout)
+            tiny = ModelConfig(vocab_size=model_cfg.vocab_size, hidden_dim=128, n_encoder_layers=1, n_heads=2,
+                               encoder_ff_dim=256, n_decoder_layers=1, decoder_ff_dim=256, max_decoder_seq_len=400,
+                               variance_filter_size=64)
+            self.store = ParamStore(tiny, torch.device("cpu"), with_ema=False)
+            self.store.init_default = lambda seed=0: None
+            self.opt = FusedAdamW(self.store, optim_cfg)
+            self.engine.cfg = tiny
+
+        def state_dict(self):
+            return self.store.state_dict()
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(parallel, "init_distributed", lambda: (0, 0, 1))
+    monkeypatch.setattr(train_step, "TrainStep", FakeStep)
+    rc = cli.main(["--synthetic", "12", "-e", "2", "-o", str(tmp_path), "--max-frames", "2400", "--min-batch-size", "1",
+                   "--max-batch-size", "4", "--save-every", "1", "--val-split", "0.25", "--seed", "5"])
+    assert rc == 0 and "done: 2 epochs" in capsys.readouterr().out
+    total = made["sched_cfg"].total_steps
+    assert total % 2 == 0 and total >= 2
+    opt_steps = total // 2
+    assert made["optim_cfg"].ema_decay == pytest.approx(max(0.9, min(math.exp(-math.log(2) / opt_steps), 0.9999)))
+    assert made["optim_cfg"].learning_rate == 5.0e-5 and made["device"] == "cuda:0"
+    d = made["dropout"]
+    assert (d.encoder, d.decoder, d.decoder_input, d.variance, d.stochastic_depth) == (0.15, 0.20, 0.15, 0.1, 0.1)
+    ck = torch.load(os.path.join(str(tmp_path), "checkpoint_epoch_2.pth"), weights_only=False)
+    assert ck["model_metadata"]["architecture"]["hidden_dim"] == 128
+    assert len(ck["optimizer_state_dict"]["param_groups"]) == 10 and ck["config"]["ema_half_life_epochs"] == 1.0
