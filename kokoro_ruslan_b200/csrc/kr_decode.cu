@@ -62,7 +62,39 @@ dec_finish_kernel(krd::DecState* st, const float* __restrict__ y, const float* _
                        next_frame, probs);
 }
 
+constexpr int GEMV_THREADS = 256, GEMV_MAX_K = 1536;
+
+__global__ void __launch_bounds__(GEMV_THREADS)
+dec_gemv_kernel(const krd::DecState* __restrict__ st, const bf16* __restrict__ x, long long ld_x,
+                const bf16* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ resid, long long ld_r,
+                void* __restrict__ out, long long ld_o, int out_f32, int B, int N, int K) {
+  kr::pdl_entry();
+  __shared__ __align__(16) bf16 xs[krd::GEMV_MAX_B * GEMV_MAX_K];       // 24 KB
+  if (st != nullptr && st->done) return;
+  const int warps = GEMV_THREADS / 32;
+  krd::dec_gemv_body(x, ld_x, w, bias, resid, ld_r, out, ld_o, out_f32, B, N, K, blockIdx.x * warps, gridDim.x * warps, xs);
+}
+
 }  // namespace
+
+// out[b, n] (bf16 or fp32, row stride ld_o) = x[b, :K] (bf16, row stride ld_x) . w[n, :K] (bf16, dense [N, K])
+// + bias[n] + resid[b, n] (fp32, row stride ld_r); B <= 8, K % 8 == 0, K <= 1536.  `state` (optional): skipped once done.
+extern "C" int kr_dec_gemv(const void* state, const void* x, long long ld_x, const void* w, const float* bias,
+                           const float* resid, long long ld_r, void* out, long long ld_o, int out_f32, int B, int N, int K,
+                           void* stream) {
+  if (B <= 0 || N <= 0) return KR_OK;
+  if (B > krd::GEMV_MAX_B || K <= 0 || K % 8 != 0 || K > GEMV_MAX_K) {
+    kr_set_error("kr_dec_gemv: needs B <= 8, K % 8 == 0, K <= 1536");
+    return KR_ERR_UNSUPPORTED;
+  }
+  const int warps = GEMV_THREADS / 32;
+  int blocks = (N + warps - 1) / warps;
+  if (blocks > 2 * kr::kNumSMs) blocks = 2 * kr::kNumSMs;
+  kr::launch(dec_gemv_kernel, dim3(blocks), GEMV_THREADS, 0, (cudaStream_t)stream, (const krd::DecState*)state,
+             (const bf16*)x, ld_x, (const bf16*)w, bias, resid, ld_r, out, ld_o, out_f32, B, N, K);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
 
 extern "C" int kr_dec_state_size(void) { return (int)sizeof(krd::DecState); }
 

@@ -42,6 +42,7 @@ KRD_DEV krd_bf16 krd_f2b(float f) {                    // round to nearest even,
 KRD_DEV float krd_warp_sum(float v) { return v; }
 KRD_DEV float krd_block_sum(float v, float*) { return v; }
 KRD_DEV float krd_rsqrt(float x) { return 1.f / sqrtf(x); }
+KRD_DEV void krd_load8(const krd_bf16* p, float* v) { for (int i = 0; i < 8; ++i) v[i] = krd_b2f(p[i]); }
 #else
 #define KRD_DEV __device__ __forceinline__
 #define KRD_TID ((int)threadIdx.x)
@@ -57,6 +58,15 @@ KRD_DEV krd_bf16 krd_f2b(float f) { return __float2bfloat16_rn(f); }
 KRD_DEV float krd_warp_sum(float v) { return kr::warp_sum(v); }
 KRD_DEV float krd_block_sum(float v, float* red) { return kr::block_sum(v, red); }
 KRD_DEV float krd_rsqrt(float x) { return rsqrtf(x); }
+KRD_DEV void krd_load8(const krd_bf16* p, float* v) {          // one 16-byte load of 8 bf16 (p is 16-byte aligned)
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
 #endif
 
 namespace krd {
@@ -236,6 +246,47 @@ KRD_DEV void dec_finish_body(DecState* st, const float* y, const float* ln_g, co
     if (t + 1 >= st->hi || t + 1 >= t_cap) stop = 1;
     st->t = t + 1;
     if (stop) { st->n_frames = t + 1; st->done = 1; }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Skinny projection of a decode step: out[b, n] = sum_k x[b, k] * W[n, k] (+ bias[n]) (+ resid[b, n]) for B <= 8 rows.
+// The weight matrix is streamed ONCE by the whole grid (a warp owns output feature n and reads its K bf16 weights with
+// 16-byte loads), the B activation rows sit in shared memory as bf16; fp32 accumulation.  This is the weight-bandwidth
+// shape of a decode step — the padded 128-row tensor-core GEMM it replaces touches the same bytes from 2 - 12 CTAs only.
+// xs: shared memory, B * K bf16 (filled here).  K % 8 == 0.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int GEMV_MAX_B = 8;
+
+KRD_DEV void dec_gemv_body(const krd_bf16* x, long long ld_x, const krd_bf16* w, const float* bias, const float* resid,
+                           long long ld_r, void* out, long long ld_o, int out_f32, int B, int N, int K, int n_first,
+                           int n_step, krd_bf16* xs) {
+  for (int i = KRD_TID; i < B * K; i += KRD_NT) xs[i] = x[(long long)(i / K) * ld_x + (i % K)];
+  KRD_SYNC();
+  const int lane = KRD_LANE, chunks = K / 8;
+  for (int n = n_first + KRD_WARP; n < N; n += n_step) {
+    float acc[GEMV_MAX_B];
+    for (int b = 0; b < GEMV_MAX_B; ++b) acc[b] = 0.f;
+    const krd_bf16* wrow = w + (long long)n * K;
+    for (int c = lane; c < chunks; c += KRD_NLANES) {
+      float wv[8], xv[8];
+      krd_load8(wrow + c * 8, wv);
+      for (int b = 0; b < B; ++b) {
+        krd_load8(xs + b * K + c * 8, xv);
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += wv[i] * xv[i];
+        acc[b] += s;
+      }
+    }
+    for (int b = 0; b < B; ++b) {
+      const float v = krd_warp_sum(acc[b]);
+      if (lane == 0) {
+        float o = v + (bias != nullptr ? bias[n] : 0.f) + (resid != nullptr ? resid[(long long)b * ld_r + n] : 0.f);
+        if (out_f32) reinterpret_cast<float*>(out)[(long long)b * ld_o + n] = o;
+        else reinterpret_cast<krd_bf16*>(out)[(long long)b * ld_o + n] = krd_f2b(o);
+      }
+    }
   }
 }
 

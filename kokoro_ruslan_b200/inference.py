@@ -82,6 +82,8 @@ class DecodeLoop:
         self.vc = [z((B, t_cap, D), torch.bfloat16) for _ in range(n_layers)]
         self.forced: Optional[torch.Tensor] = None
         self._graph = None
+        if hasattr(be, "state_for_gemv"):
+            be.state_for_gemv = self.state
 
     # one decode step: every launch reads t / done from self.state, no host-side per-step values
     def step(self) -> None:
@@ -95,25 +97,25 @@ class DecodeLoop:
             sa, ca, ffp = pre + "self_attn.", pre + "cross_attn.", pre + "ff."
             # self-attention sub-layer (transformers.py:564-569)
             be.layernorm(cur, P(pre + "norm1.weight"), P(pre + "norm1.bias"), self.h, self.stat)
-            be.gemm(self.h, be.weight_span(sa + "w_q.weight", 3 * D), self.qkv)
+            be.gemm(self.h, be.weight_span(sa + "w_q.weight", 3 * D), self.qkv, rows=B)
             be.dec_attn(self.state, self.qkv[:, :D], self.qkv[:, D:2 * D], self.qkv[:, 2 * D:], P(sa + "q_norm.weight"),
                         P(sa + "k_norm.weight"), P(sa + "v_norm.weight"), self.kc[i], self.vc[i], -1, None, self.o, B,
                         self.H)
-            be.gemm(self.o, W(sa + "w_o.weight"), nxt, bias=P(sa + "w_o.bias"), resid=cur)
+            be.gemm(self.o, W(sa + "w_o.weight"), nxt, bias=P(sa + "w_o.bias"), resid=cur, rows=B)
             cur, nxt = nxt, cur
             # cross-attention sub-layer (:572-578)
             be.layernorm(cur, P(pre + "norm2.weight"), P(pre + "norm2.bias"), self.h, self.stat)
-            be.gemm(self.h, W(ca + "w_q.weight"), self.q)
+            be.gemm(self.h, W(ca + "w_q.weight"), self.q, rows=B)
             kv = self.cross_kv[i].view(B, self.Tp, 2 * D)
             be.dec_attn(self.state, self.q, None, None, P(ca + "q_norm.weight"), None, None, kv[:, :, :D], kv[:, :, D:],
                         self.Tp, self.mem_pad, self.o, B, self.H)
-            be.gemm(self.o, W(ca + "w_o.weight"), nxt, bias=P(ca + "w_o.bias"), resid=cur)
+            be.gemm(self.o, W(ca + "w_o.weight"), nxt, bias=P(ca + "w_o.bias"), resid=cur, rows=B)
             cur, nxt = nxt, cur
             # GLU feed-forward sub-layer (:581, :105-111)
             be.layernorm(cur, P(pre + "norm3.weight"), P(pre + "norm3.bias"), self.h, self.stat)
-            be.gemm(self.h, W(ffp + "linear1.weight"), self.hff, bias=P(ffp + "linear1.bias"))
+            be.gemm(self.h, W(ffp + "linear1.weight"), self.hff, bias=P(ffp + "linear1.bias"), rows=B)
             be.glu(self.hff, self.u)
-            be.gemm(self.u, W(ffp + "linear2.weight"), self.yff, bias=P(ffp + "linear2.bias"))
+            be.gemm(self.u, W(ffp + "linear2.weight"), self.yff, bias=P(ffp + "linear2.bias"), rows=B)
             be.rmsnorm_resid(self.yff, P(ffp + "output_norm.weight"), cur, nxt)
             cur, nxt = nxt, cur
         be.dec_finish(self.state, cur, P("decoder.norm.weight"), P("decoder.norm.bias"), P("mel_projection_out.weight"),
@@ -165,6 +167,9 @@ class CudaDecodeBackend:
         n = int(lib().kr_dec_state_size())
         if n != STATE_WORDS * 4:
             raise RuntimeError(f"DecState is {n} bytes in libkokoro_b200.so, {STATE_WORDS * 4} expected")
+        import os
+        self.use_gemv = os.environ.get("KR_DECODE_GEMV", "0") == "1"
+        self.state_for_gemv = None        # DecodeLoop's state tensor once a loop is bound (lets the kernel skip after `done`)
 
     def zeros(self, shape, dtype):
         return self.ops.zero_(torch.empty(*shape, dtype=dtype, device=self.device))
@@ -190,7 +195,20 @@ class CudaDecodeBackend:
     def layernorm(self, x, g, b, out_bf16, stat):
         self.ops.layernorm_fwd(x, g, b, out_bf16, None, stat[0], stat[1])
 
-    def gemm(self, a, w, out, bias=None, resid=None):
+    def gemm(self, a, w, out, bias=None, resid=None, rows=None):
+        """Projection of the step.  Default: the validated tcgen05 GEMM on the 128-row padded buffers.  KR_DECODE_GEMV=1
+        (and at most 8 utterances): kr_dec_gemv on the `rows` live rows — every SM streams a slice of the weights once
+        instead of 2 - 12 CTAs; opt-in until it has been measured against the default."""
+        if self.use_gemv and rows is not None and rows <= 8 and w.shape[1] % 8 == 0 and w.shape[1] <= 1536:
+            o, c = self.ops, ctypes
+            assert a.stride(1) == 1 and w.is_contiguous() and out.stride(1) == 1
+            self._check(self._lib().kr_dec_gemv(o._ptr(self.state_for_gemv), o._ptr(a), c.c_longlong(a.stride(0)), o._ptr(w),
+                                                o._ptr(bias), o._ptr(resid),
+                                                c.c_longlong(0 if resid is None else resid.stride(0)), o._ptr(out),
+                                                c.c_longlong(out.stride(0)), c.c_int(int(out.dtype == torch.float32)),
+                                                c.c_int(rows), c.c_int(w.shape[0]), c.c_int(w.shape[1]), o._stream()),
+                        "kr_dec_gemv")
+            return
         self.ops.gemm(a, w, out, bias=bias, resid=resid)
 
     def glu(self, h, u):

@@ -138,6 +138,12 @@ def test_decode_backend_and_metrics_match_the_header(rec):
     be.dec_attn(state, z(128, D, dt=bf), None, None, z(64), None, None, kv[:, :, :D], kv[:, :, D:], Tp,
                 z(B, Tp, dt=torch.uint8), z(128, D, dt=bf), B, H)
     be.dec_finish(state, z(128, D), z(D), z(D), z(80, D), z(80), z(1, D), z(1), z(B, cap, 80), z(B, 80), z(cap), B, D, 80, cap)
+    be.use_gemv, be.state_for_gemv = True, state
+    be.gemm(z(128, D, dt=bf), z(3 * D, D, dt=bf), z(128, 3 * D, dt=bf), rows=B)
+    be.gemm(z(128, D, dt=bf), z(D, D, dt=bf), z(128, D), bias=z(D), resid=z(128, D), rows=B)
+    gemv = [a for n, a in rec.calls if n == "kr_dec_gemv"]
+    assert len(gemv) == 2 and gemv[0][9].value == 0 and gemv[1][9].value == 1 and gemv[1][10].value == B
+    be.use_gemv = False
     acc = z(ops.val_metrics_acc_floats())
     ops.val_metrics(z(B, 20, 80), z(B, 20, 80), z(B, 20), z(B, 20), torch.tensor([20, 7]), acc)
     ops.val_metrics(z(B, 20, 80), z(B, 20, 80), None, None, torch.tensor([20, 7]), acc)

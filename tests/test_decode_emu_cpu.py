@@ -73,7 +73,7 @@ class EmuBackend:
     def layernorm(self, x, g, b, out_bf16, stat):
         out_bf16.copy_(F.layer_norm(x, (x.shape[-1],), g, b, 1e-5).to(BF16))
 
-    def gemm(self, a, w, out, bias=None, resid=None):
+    def gemm(self, a, w, out, bias=None, resid=None, rows=None):
         y = a.float() @ w.float().t()
         if bias is not None:
             y = y + bias
@@ -113,6 +113,18 @@ class EmuBackend:
         return fn
 
 
+class EmuGemvBackend(EmuBackend):
+    """Projections through the emulated kr_dec_gemv (the KR_DECODE_GEMV=1 variant of CudaDecodeBackend)."""
+
+    def gemm(self, a, w, out, bias=None, resid=None, rows=None):
+        self.launches += 1
+        ll = ctypes.c_longlong
+        assert rows is not None and rows <= 8 and w.is_contiguous()
+        assert self.lib.emu_dec_gemv(None, _p(a), ll(a.stride(0)), _p(w), _p(bias), _p(resid),
+                                     ll(0 if resid is None else resid.stride(0)), _p(out), ll(out.stride(0)),
+                                     int(out.dtype == torch.float32), rows, w.shape[0], w.shape[1]) == 0
+
+
 def _setup():
     from oracle import acoustic as oa
     f = np.load(os.path.join(HERE, "golden", "inference.npz"))
@@ -142,12 +154,12 @@ def _memory(sd, cfg, idx, stress):
     return cross, mem_pad.to(torch.uint8).contiguous(), Tp
 
 
-def _loop(emu, sd, cfg, idx, stress):
+def _loop(emu, sd, cfg, idx, stress, backend=None):
     from kokoro_ruslan_b200.inference import DecodeLoop, generation_bounds
     cross, mem_pad, Tp = _memory(sd, cfg, idx, stress)
     lo, hi = generation_bounds(Tp)
     t_cap = ((hi + 63) // 64) * 64
-    be = EmuBackend(emu, sd, cfg.max_len)
+    be = (backend or EmuBackend)(emu, sd, cfg.max_len)
     loop = DecodeLoop(be, cfg.n_decoder_layers, cfg.hidden_dim, cfg.n_heads, cfg.ff_dim, cfg.mel_dim, idx.shape[0], Tp,
                       t_cap, cross, mem_pad)
     return loop, be, lo, hi, Tp
@@ -239,3 +251,23 @@ def test_stop_rules_on_the_device_state(emu):
     st, mel, nxt, _ = run(12, 60, -12.0, -5.0, 40)               # silence: mean of 30 frames < -9.5 once 30 exist
     assert int(st[inf.ST_NFRAMES]) == 30
     assert float(mel[:, :30].min()) == -11.5 and float(nxt.min()) == -12.0      # output clamped, feedback not
+
+
+def test_gemv_projection_variant_matches_the_gemm_path(emu):
+    """kr_dec_gemv (emulated) in place of the projections: same frames as the torch bf16-GEMM stand-in of the default path
+    (both accumulate in fp32 over bf16 operands; only the summation order differs), teacher-forced, batch of two."""
+    from oracle import inference as oi
+    f, cfg, sd = _setup()
+    idx = torch.from_numpy(f["idx2"])
+    want, want_p, raw = oi.forward_inference(sd, cfg, idx, None, stop_threshold=0.45, return_raw=True)
+    n = want.shape[1]
+    outs = []
+    for backend in (EmuBackend, EmuGemvBackend):
+        loop, be, lo, hi, Tp = _loop(emu, sd, cfg, idx, None, backend)
+        forced = torch.zeros(2, hi, cfg.mel_dim)
+        forced[:, 1:n] = raw[:, :n - 1]
+        got, _ = loop.run(lo, hi, Tp, stop_threshold=0.45, forced=forced)
+        assert got.shape == want.shape
+        outs.append(got)
+    assert float((outs[1] - want).abs().max()) / float(want.abs().max()) < 1e-2
+    assert float((outs[1] - outs[0]).abs().max()) / float(want.abs().max()) < 2e-3

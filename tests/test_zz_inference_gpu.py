@@ -118,3 +118,25 @@ def test_synthesizer_mel_to_waveform():
     audio, mel = Synthesizer(m, voc)(idx, min_len_floor=48, max_len_cap=64)      # 49..64 frames
     assert audio.shape == (1, mel.shape[1] * 256) and bool(torch.isfinite(audio).all())
     assert float(audio.abs().max()) <= 1.0
+
+
+def test_gemv_projection_variant_equals_default_path(monkeypatch):
+    """KR_DECODE_GEMV=1 (kr_dec_gemv instead of the padded tcgen05 GEMMs): same teacher-forced frames as the default."""
+    from oracle import inference as oi
+    f, ocfg, sd, inf = _setup()
+    idx = torch.from_numpy(f["idx2"])
+    want, _, raw = oi.forward_inference(sd, ocfg, idx, None, stop_threshold=0.45, return_raw=True)
+    n = want.shape[1]
+    forced = torch.zeros(2, 1600, ocfg.mel_dim)
+    forced[:, 1:n] = raw[:, :n - 1]
+    dur = _oracle_durations(sd, ocfg, idx, None)
+    a = inf.generate(idx.cuda(), None, stop_threshold=0.45, forced=forced.cuda(), durations=dur).cpu()
+    monkeypatch.setenv("KR_DECODE_GEMV", "1")
+    from kokoro_ruslan_b200.inference import InferenceEngine
+    inf2 = InferenceEngine(inf.eng)
+    assert inf2.be.use_gemv
+    b = inf2.generate(idx.cuda(), None, stop_threshold=0.45, forced=forced.cuda(), durations=dur).cpu()
+    assert a.shape == b.shape
+    assert float((a - b).abs().max()) / float(want.abs().max()) < 5e-3
+    m = min(a.shape[1], n)
+    assert float((b[:, :m] - want[:, :m]).abs().max()) / float(want.abs().max()) < 2e-2

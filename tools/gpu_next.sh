@@ -12,6 +12,7 @@ timeout 200 compute-sanitizer --tool racecheck python -m pytest tests/test_zz_in
   > gpurun_out/racecheck_decode.log 2>&1; tail -3 gpurun_out/racecheck_decode.log
 timeout 120 python tools/features_bench.py > gpurun_out/features_bench.log 2>&1; cat gpurun_out/features_bench.log
 timeout 200 python tools/decode_bench.py 1 64 400 > gpurun_out/decode_bench.log 2>&1; cat gpurun_out/decode_bench.log
+KR_DECODE_GEMV=1 timeout 200 python tools/decode_bench.py 1 64 400 > gpurun_out/decode_bench_gemv.log 2>&1; cat gpurun_out/decode_bench_gemv.log
 KR_ATTN_FAST=1 python -m pytest tests -m gpu -q -x --deselect tests/test_zz_features_gpu.py --deselect tests/test_zz_inference_gpu.py \
   --deselect tests/test_zz_metrics_gpu.py --deselect tests/test_zz_lengths_gpu.py > gpurun_out/pytest_attn_fast.log 2>&1; tail -3 gpurun_out/pytest_attn_fast.log
 # ncu evidence for the feature kernels (mel-STFT = SURVEY 8 row A16 has no capture yet; pitch / energy / resample = N1):
