@@ -65,33 +65,42 @@ dec_finish_kernel(krd::DecState* st, const float* __restrict__ y, const float* _
 constexpr int GEMV_THREADS = 256, GEMV_MAX_K = 1536;
 
 __global__ void __launch_bounds__(GEMV_THREADS)
-dec_gemv_kernel(const krd::DecState* __restrict__ st, const bf16* __restrict__ x, long long ld_x,
+dec_gemv_kernel(const krd::DecState* __restrict__ st, const bf16* __restrict__ x, const float* __restrict__ x_f32,
+                long long ld_x, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                 const bf16* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ resid, long long ld_r,
-                void* __restrict__ out, long long ld_o, int out_f32, int B, int N, int K) {
+                void* __restrict__ out, long long ld_o, int out_f32, int glu, int B, int N, int K) {
   kr::pdl_entry();
   __shared__ __align__(16) bf16 xs[krd::GEMV_MAX_B * GEMV_MAX_K];       // 24 KB
   if (st != nullptr && st->done) return;
   const int warps = GEMV_THREADS / 32;
-  krd::dec_gemv_body(x, ld_x, w, bias, resid, ld_r, out, ld_o, out_f32, B, N, K, blockIdx.x * warps, gridDim.x * warps, xs);
+  krd::dec_gemv_body(x, x_f32, ld_x, ln_g, ln_b, w, bias, resid, ld_r, out, ld_o, out_f32, glu, B, N, K,
+                     blockIdx.x * warps, gridDim.x * warps, xs);
 }
 
 }  // namespace
 
-// out[b, n] (bf16 or fp32, row stride ld_o) = x[b, :K] (bf16, row stride ld_x) . w[n, :K] (bf16, dense [N, K])
-// + bias[n] + resid[b, n] (fp32, row stride ld_r); B <= 8, K % 8 == 0, K <= 1536.  `state` (optional): skipped once done.
-extern "C" int kr_dec_gemv(const void* state, const void* x, long long ld_x, const void* w, const float* bias,
-                           const float* resid, long long ld_r, void* out, long long ld_o, int out_f32, int B, int N, int K,
-                           void* stream) {
+// out[b, n] (bf16 or fp32, row stride ld_o) = x[b, :K] . w[n, :K] (bf16, dense) + bias[n] + resid[b, n] (fp32, row stride
+// ld_r); B <= 8, K % 8 == 0, K <= 1536.  The activation rows are x (bf16, row stride ld_x) or, when x_f32 is given,
+// LayerNorm(x_f32[b]; ln_g, ln_b) computed in the kernel's prologue.  glu != 0: w is [2 * N, K], bias [2 * N], and
+// out[b, n] = gelu_erf(gate_n) * lin_n (bf16, no residual).  `state` (optional): skipped once done.
+extern "C" int kr_dec_gemv(const void* state, const void* x, const float* x_f32, long long ld_x, const float* ln_g,
+                           const float* ln_b, const void* w, const float* bias, const float* resid, long long ld_r,
+                           void* out, long long ld_o, int out_f32, int glu, int B, int N, int K, void* stream) {
   if (B <= 0 || N <= 0) return KR_OK;
   if (B > krd::GEMV_MAX_B || K <= 0 || K % 8 != 0 || K > GEMV_MAX_K) {
     kr_set_error("kr_dec_gemv: needs B <= 8, K % 8 == 0, K <= 1536");
     return KR_ERR_UNSUPPORTED;
   }
+  if ((x == nullptr) == (x_f32 == nullptr) || (x_f32 != nullptr && (ln_g == nullptr || ln_b == nullptr)) ||
+      (glu && (resid != nullptr || out_f32))) {
+    kr_set_error("kr_dec_gemv: inconsistent operand combination");
+    return KR_ERR_ARG;
+  }
   const int warps = GEMV_THREADS / 32;
   int blocks = (N + warps - 1) / warps;
   if (blocks > 2 * kr::kNumSMs) blocks = 2 * kr::kNumSMs;
   kr::launch(dec_gemv_kernel, dim3(blocks), GEMV_THREADS, 0, (cudaStream_t)stream, (const krd::DecState*)state,
-             (const bf16*)x, ld_x, (const bf16*)w, bias, resid, ld_r, out, ld_o, out_f32, B, N, K);
+             (const bf16*)x, x_f32, ld_x, ln_g, ln_b, (const bf16*)w, bias, resid, ld_r, out, ld_o, out_f32, glu, B, N, K);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -259,30 +259,62 @@ KRD_DEV void dec_finish_body(DecState* st, const float* y, const float* ln_g, co
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int GEMV_MAX_B = 8;
 
-KRD_DEV void dec_gemv_body(const krd_bf16* x, long long ld_x, const krd_bf16* w, const float* bias, const float* resid,
-                           long long ld_r, void* out, long long ld_o, int out_f32, int B, int N, int K, int n_first,
-                           int n_step, krd_bf16* xs) {
-  for (int i = KRD_TID; i < B * K; i += KRD_NT) xs[i] = x[(long long)(i / K) * ld_x + (i % K)];
+KRD_DEV float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+// Fusions (each removes one launch per use from the 13-kernel decoder layer):
+//   x_f32 != nullptr  LayerNorm prologue: the activation rows are LN(x_f32[b]; ln_g, ln_b, eps 1e-5) rounded to bf16
+//                     (what kr_layernorm_fwd would have written), computed redundantly by every block — B <= 8 rows;
+//   glu != 0          GLU epilogue (model/transformers.py:105-108): W is linear1 [2 * N, K], a warp computes the gate
+//                     feature n and the linear feature n + N together and writes gelu_erf(gate + b) * (lin + b) as bf16.
+KRD_DEV void dec_gemv_body(const krd_bf16* x, const float* x_f32, long long ld_x, const float* ln_g, const float* ln_b,
+                           const krd_bf16* w, const float* bias, const float* resid, long long ld_r, void* out,
+                           long long ld_o, int out_f32, int glu, int B, int N, int K, int n_first, int n_step,
+                           krd_bf16* xs) {
+  const int lane = KRD_LANE;
+  if (x_f32 != nullptr) {
+    for (int b = KRD_WARP; b < B; b += KRD_NWARPS) {              // one warp per row
+      const float* row = x_f32 + (long long)b * ld_x;
+      float s = 0.f;
+      for (int k = lane; k < K; k += KRD_NLANES) s += row[k];
+      const float mean = krd_warp_sum(s) / (float)K;
+      float v = 0.f;
+      for (int k = lane; k < K; k += KRD_NLANES) { const float c = row[k] - mean; v += c * c; }
+      const float rstd = krd_rsqrt(krd_warp_sum(v) / (float)K + 1e-5f);
+      for (int k = lane; k < K; k += KRD_NLANES) xs[b * K + k] = krd_f2b((row[k] - mean) * rstd * ln_g[k] + ln_b[k]);
+    }
+  } else {
+    for (int i = KRD_TID; i < B * K; i += KRD_NT) xs[i] = x[(long long)(i / K) * ld_x + (i % K)];
+  }
   KRD_SYNC();
-  const int lane = KRD_LANE, chunks = K / 8;
+  const int chunks = K / 8;
   for (int n = n_first + KRD_WARP; n < N; n += n_step) {
-    float acc[GEMV_MAX_B];
-    for (int b = 0; b < GEMV_MAX_B; ++b) acc[b] = 0.f;
+    float acc[GEMV_MAX_B], acc2[GEMV_MAX_B];
+    for (int b = 0; b < GEMV_MAX_B; ++b) acc[b] = acc2[b] = 0.f;
     const krd_bf16* wrow = w + (long long)n * K;
+    const krd_bf16* wrow2 = w + (long long)(n + N) * K;           // the "lin" half of linear1 (GLU only)
     for (int c = lane; c < chunks; c += KRD_NLANES) {
-      float wv[8], xv[8];
+      float wv[8], wv2[8], xv[8];
       krd_load8(wrow + c * 8, wv);
+      if (glu) krd_load8(wrow2 + c * 8, wv2);
       for (int b = 0; b < B; ++b) {
         krd_load8(xs + b * K + c * 8, xv);
-        float s = 0.f;
+        float s = 0.f, s2 = 0.f;
         for (int i = 0; i < 8; ++i) s += wv[i] * xv[i];
+        if (glu) for (int i = 0; i < 8; ++i) s2 += wv2[i] * xv[i];
         acc[b] += s;
+        acc2[b] += s2;
       }
     }
     for (int b = 0; b < B; ++b) {
       const float v = krd_warp_sum(acc[b]);
+      const float v2 = glu ? krd_warp_sum(acc2[b]) : 0.f;
       if (lane == 0) {
-        float o = v + (bias != nullptr ? bias[n] : 0.f) + (resid != nullptr ? resid[(long long)b * ld_r + n] : 0.f);
+        float o;
+        if (glu) {
+          o = gelu_erf(v + (bias != nullptr ? bias[n] : 0.f)) * (v2 + (bias != nullptr ? bias[n + N] : 0.f));
+        } else {
+          o = v + (bias != nullptr ? bias[n] : 0.f) + (resid != nullptr ? resid[(long long)b * ld_r + n] : 0.f);
+        }
         if (out_f32) reinterpret_cast<float*>(out)[(long long)b * ld_o + n] = o;
         else reinterpret_cast<krd_bf16*>(out)[(long long)b * ld_o + n] = krd_f2b(o);
       }

@@ -89,6 +89,7 @@ class DecodeLoop:
     def step(self) -> None:
         be, D, B = self.be, self.D, self.B
         P, W = be.param, be.weight
+        fused = bool(getattr(be, "use_gemv", False)) and B <= 8     # LN / GLU folded into the skinny projections
         cur, nxt = self.x
         be.dec_feed(self.state, self.prev, self.forced, P("mel_projection_in.weight"), P("mel_projection_in.bias"),
                     be.pe, cur, B, D, self.n_mels)
@@ -96,25 +97,37 @@ class DecodeLoop:
             pre = f"decoder.layers.{i}."
             sa, ca, ffp = pre + "self_attn.", pre + "cross_attn.", pre + "ff."
             # self-attention sub-layer (transformers.py:564-569)
-            be.layernorm(cur, P(pre + "norm1.weight"), P(pre + "norm1.bias"), self.h, self.stat)
-            be.gemm(self.h, be.weight_span(sa + "w_q.weight", 3 * D), self.qkv, rows=B)
+            if fused:
+                be.ln_gemv(cur, P(pre + "norm1.weight"), P(pre + "norm1.bias"), be.weight_span(sa + "w_q.weight", 3 * D),
+                           None, self.qkv, B, glu=False)
+            else:
+                be.layernorm(cur, P(pre + "norm1.weight"), P(pre + "norm1.bias"), self.h, self.stat)
+                be.gemm(self.h, be.weight_span(sa + "w_q.weight", 3 * D), self.qkv, rows=B)
             be.dec_attn(self.state, self.qkv[:, :D], self.qkv[:, D:2 * D], self.qkv[:, 2 * D:], P(sa + "q_norm.weight"),
                         P(sa + "k_norm.weight"), P(sa + "v_norm.weight"), self.kc[i], self.vc[i], -1, None, self.o, B,
                         self.H)
             be.gemm(self.o, W(sa + "w_o.weight"), nxt, bias=P(sa + "w_o.bias"), resid=cur, rows=B)
             cur, nxt = nxt, cur
             # cross-attention sub-layer (:572-578)
-            be.layernorm(cur, P(pre + "norm2.weight"), P(pre + "norm2.bias"), self.h, self.stat)
-            be.gemm(self.h, W(ca + "w_q.weight"), self.q, rows=B)
+            if fused:
+                be.ln_gemv(cur, P(pre + "norm2.weight"), P(pre + "norm2.bias"), W(ca + "w_q.weight"), None, self.q, B,
+                           glu=False)
+            else:
+                be.layernorm(cur, P(pre + "norm2.weight"), P(pre + "norm2.bias"), self.h, self.stat)
+                be.gemm(self.h, W(ca + "w_q.weight"), self.q, rows=B)
             kv = self.cross_kv[i].view(B, self.Tp, 2 * D)
             be.dec_attn(self.state, self.q, None, None, P(ca + "q_norm.weight"), None, None, kv[:, :, :D], kv[:, :, D:],
                         self.Tp, self.mem_pad, self.o, B, self.H)
             be.gemm(self.o, W(ca + "w_o.weight"), nxt, bias=P(ca + "w_o.bias"), resid=cur, rows=B)
             cur, nxt = nxt, cur
             # GLU feed-forward sub-layer (:581, :105-111)
-            be.layernorm(cur, P(pre + "norm3.weight"), P(pre + "norm3.bias"), self.h, self.stat)
-            be.gemm(self.h, W(ffp + "linear1.weight"), self.hff, bias=P(ffp + "linear1.bias"), rows=B)
-            be.glu(self.hff, self.u)
+            if fused:           # LayerNorm + linear1 + GLU in one launch
+                be.ln_gemv(cur, P(pre + "norm3.weight"), P(pre + "norm3.bias"), W(ffp + "linear1.weight"),
+                           P(ffp + "linear1.bias"), self.u, B, glu=True)
+            else:
+                be.layernorm(cur, P(pre + "norm3.weight"), P(pre + "norm3.bias"), self.h, self.stat)
+                be.gemm(self.h, W(ffp + "linear1.weight"), self.hff, bias=P(ffp + "linear1.bias"), rows=B)
+                be.glu(self.hff, self.u)
             be.gemm(self.u, W(ffp + "linear2.weight"), self.yff, bias=P(ffp + "linear2.bias"), rows=B)
             be.rmsnorm_resid(self.yff, P(ffp + "output_norm.weight"), cur, nxt)
             cur, nxt = nxt, cur
@@ -195,21 +208,30 @@ class CudaDecodeBackend:
     def layernorm(self, x, g, b, out_bf16, stat):
         self.ops.layernorm_fwd(x, g, b, out_bf16, None, stat[0], stat[1])
 
+    def _gemv(self, x_bf16, x_f32, ln_g, ln_b, w, bias, resid, out, rows, glu):
+        o, c = self.ops, ctypes
+        x = x_bf16 if x_bf16 is not None else x_f32
+        n_out = w.shape[0] // 2 if glu else w.shape[0]
+        assert x.stride(1) == 1 and w.is_contiguous() and out.stride(1) == 1 and out.shape[1] == n_out
+        self._check(self._lib().kr_dec_gemv(o._ptr(self.state_for_gemv), o._ptr(x_bf16), o._ptr(x_f32),
+                                            c.c_longlong(x.stride(0)), o._ptr(ln_g), o._ptr(ln_b), o._ptr(w), o._ptr(bias),
+                                            o._ptr(resid), c.c_longlong(0 if resid is None else resid.stride(0)),
+                                            o._ptr(out), c.c_longlong(out.stride(0)),
+                                            c.c_int(int(out.dtype == torch.float32)), c.c_int(int(glu)), c.c_int(rows),
+                                            c.c_int(n_out), c.c_int(w.shape[1]), o._stream()), "kr_dec_gemv")
+
     def gemm(self, a, w, out, bias=None, resid=None, rows=None):
         """Projection of the step.  Default: the validated tcgen05 GEMM on the 128-row padded buffers.  KR_DECODE_GEMV=1
         (and at most 8 utterances): kr_dec_gemv on the `rows` live rows — every SM streams a slice of the weights once
         instead of 2 - 12 CTAs; opt-in until it has been measured against the default."""
         if self.use_gemv and rows is not None and rows <= 8 and w.shape[1] % 8 == 0 and w.shape[1] <= 1536:
-            o, c = self.ops, ctypes
-            assert a.stride(1) == 1 and w.is_contiguous() and out.stride(1) == 1
-            self._check(self._lib().kr_dec_gemv(o._ptr(self.state_for_gemv), o._ptr(a), c.c_longlong(a.stride(0)), o._ptr(w),
-                                                o._ptr(bias), o._ptr(resid),
-                                                c.c_longlong(0 if resid is None else resid.stride(0)), o._ptr(out),
-                                                c.c_longlong(out.stride(0)), c.c_int(int(out.dtype == torch.float32)),
-                                                c.c_int(rows), c.c_int(w.shape[0]), c.c_int(w.shape[1]), o._stream()),
-                        "kr_dec_gemv")
+            self._gemv(a, None, None, None, w, bias, resid, out, rows, False)
             return
         self.ops.gemm(a, w, out, bias=bias, resid=resid)
+
+    def ln_gemv(self, x_f32, ln_g, ln_b, w, bias, out, rows, glu):
+        """LayerNorm(x) . W^T (+ bias) in one launch; glu: W = linear1, out = gelu(gate) * lin (KR_DECODE_GEMV=1 only)."""
+        self._gemv(None, x_f32, ln_g, ln_b, w, bias, None, out, rows, glu)
 
     def glu(self, h, u):
         self.ops.glu_fwd(h, u)

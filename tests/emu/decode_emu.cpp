@@ -52,12 +52,14 @@ extern "C" int emu_dec_finish(void* state, const float* y, const float* ln_g, co
   return 0;
 }
 
-extern "C" int emu_dec_gemv(const void* state, const uint16_t* x, long long ld_x, const uint16_t* w, const float* bias,
-                            const float* resid, long long ld_r, void* out, long long ld_o, int out_f32, int B, int N, int K) {
+extern "C" int emu_dec_gemv(const void* state, const uint16_t* x, const float* x_f32, long long ld_x, const float* ln_g,
+                            const float* ln_b, const uint16_t* w, const float* bias, const float* resid, long long ld_r,
+                            void* out, long long ld_o, int out_f32, int glu, int B, int N, int K) {
   if (B > krd::GEMV_MAX_B || K % 8 != 0) return -4;
+  if ((x == nullptr) == (x_f32 == nullptr) || (glu && (resid != nullptr || out_f32))) return -1;
   if (state && ((const krd::DecState*)state)->done) return 0;
   std::vector<uint16_t> xs((size_t)B * K);
   // the launch wrapper runs `blocks` blocks of 8 warps; one emulated block with n_step = 1 covers every feature once
-  krd::dec_gemv_body(x, ld_x, w, bias, resid, ld_r, out, ld_o, out_f32, B, N, K, 0, 1, xs.data());
+  krd::dec_gemv_body(x, x_f32, ld_x, ln_g, ln_b, w, bias, resid, ld_r, out, ld_o, out_f32, glu, B, N, K, 0, 1, xs.data());
   return 0;
 }

@@ -141,8 +141,10 @@ def test_decode_backend_and_metrics_match_the_header(rec):
     be.use_gemv, be.state_for_gemv = True, state
     be.gemm(z(128, D, dt=bf), z(3 * D, D, dt=bf), z(128, 3 * D, dt=bf), rows=B)
     be.gemm(z(128, D, dt=bf), z(D, D, dt=bf), z(128, D), bias=z(D), resid=z(128, D), rows=B)
+    be.ln_gemv(z(128, D), z(D), z(D), z(4 * D, D, dt=bf), z(4 * D), z(128, 2 * D, dt=bf), B, glu=True)
     gemv = [a for n, a in rec.calls if n == "kr_dec_gemv"]
-    assert len(gemv) == 2 and gemv[0][9].value == 0 and gemv[1][9].value == 1 and gemv[1][10].value == B
+    assert len(gemv) == 3 and [g[12].value for g in gemv] == [0, 1, 0] and [g[13].value for g in gemv] == [0, 0, 1]
+    assert [g[14].value for g in gemv] == [B, B, B] and [g[15].value for g in gemv] == [3 * D, D, 2 * D]
     be.use_gemv = False
     acc = z(ops.val_metrics_acc_floats())
     ops.val_metrics(z(B, 20, 80), z(B, 20, 80), z(B, 20), z(B, 20), torch.tensor([20, 7]), acc)

@@ -114,15 +114,31 @@ class EmuBackend:
 
 
 class EmuGemvBackend(EmuBackend):
-    """Projections through the emulated kr_dec_gemv (the KR_DECODE_GEMV=1 variant of CudaDecodeBackend)."""
+    """Projections through the emulated kr_dec_gemv (the KR_DECODE_GEMV=1 variant of CudaDecodeBackend), with its
+    LayerNorm prologue and GLU epilogue."""
+    use_gemv = True
 
-    def gemm(self, a, w, out, bias=None, resid=None, rows=None):
+    def _gemv(self, x_bf16, x_f32, ln_g, ln_b, w, bias, resid, out, rows, glu):
         self.launches += 1
         ll = ctypes.c_longlong
-        assert rows is not None and rows <= 8 and w.is_contiguous()
-        assert self.lib.emu_dec_gemv(None, _p(a), ll(a.stride(0)), _p(w), _p(bias), _p(resid),
-                                     ll(0 if resid is None else resid.stride(0)), _p(out), ll(out.stride(0)),
-                                     int(out.dtype == torch.float32), rows, w.shape[0], w.shape[1]) == 0
+        x = x_bf16 if x_bf16 is not None else x_f32
+        n_out = w.shape[0] // 2 if glu else w.shape[0]
+        assert rows <= 8 and w.is_contiguous() and out.shape[1] == n_out
+        assert self.lib.emu_dec_gemv(None, _p(x_bf16), _p(x_f32), ll(x.stride(0)), _p(ln_g), _p(ln_b), _p(w), _p(bias),
+                                     _p(resid), ll(0 if resid is None else resid.stride(0)), _p(out), ll(out.stride(0)),
+                                     int(out.dtype == torch.float32), int(glu), rows, n_out, w.shape[1]) == 0
+
+    def gemm(self, a, w, out, bias=None, resid=None, rows=None):
+        self._gemv(a, None, None, None, w, bias, resid, out, rows, False)
+
+    def ln_gemv(self, x_f32, ln_g, ln_b, w, bias, out, rows, glu):
+        self._gemv(None, x_f32, ln_g, ln_b, w, bias, None, out, rows, glu)
+
+    def layernorm(self, *a):
+        raise AssertionError("the fused variant must not launch a separate LayerNorm")
+
+    def glu(self, *a):
+        raise AssertionError("the fused variant must not launch a separate GLU")
 
 
 def _setup():
@@ -270,4 +286,8 @@ def test_gemv_projection_variant_matches_the_gemm_path(emu):
         assert got.shape == want.shape
         outs.append(got)
     assert float((outs[1] - want).abs().max()) / float(want.abs().max()) < 1e-2
-    assert float((outs[1] - outs[0]).abs().max()) / float(want.abs().max()) < 2e-3
+    # vs the un-fused stand-in: the GLU input is no longer rounded to bf16 in between, so the two differ by about one
+    # bf16 rounding of the FFN hidden state (0.7e-2 of max here); both sit within 1e-2 of the fp32 oracle
+    assert float((outs[1] - outs[0]).abs().max()) / float(want.abs().max()) < 1e-2
+    print("fused / un-fused error vs oracle:", float((outs[1] - want).abs().max()), float((outs[0] - want).abs().max()))
+    assert be.launches == (2 + 8 * cfg.n_decoder_layers) * (-(-n // 32) * 32)      # 8 decode-kernel launches per layer
