@@ -163,7 +163,8 @@ def test_header_parser_sees_every_entry_point():
     assert protos["kr_dec_state_size"] == [] and len(protos["kr_pitch_frames"]) == 13
 
 
-def test_inference_engine_dry_run_on_the_recording_lib(rec, monkeypatch):
+@pytest.mark.parametrize("gemv", [False, True])
+def test_inference_engine_dry_run_on_the_recording_lib(rec, monkeypatch, gemv):
     """InferenceEngine.generate end to end on CPU tensors with the recording library: no numerics, but every Python line of
     the device path runs — engine calls in eval mode, geometry tables, buffer shapes / strides asserted by the wrappers,
     cross K/V, DecodeLoop wiring, polling — and every C call it makes is checked against the header."""
@@ -171,6 +172,7 @@ def test_inference_engine_dry_run_on_the_recording_lib(rec, monkeypatch):
     from kokoro_ruslan_b200 import inference, ops, params
     from kokoro_ruslan_b200.params import ModelConfig
     monkeypatch.setenv("KR_DECODE_GRAPH", "0")
+    monkeypatch.setenv("KR_DECODE_GEMV", "1" if gemv else "0")
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     for mod in (engine_mod, params):
         if hasattr(mod, "lib"):
@@ -210,9 +212,12 @@ def test_inference_engine_dry_run_on_the_recording_lib(rec, monkeypatch):
     per_step = 2 + 2 * cfg.n_decoder_layers                          # feed + finish + 2 attentions per layer
     assert names.count("kr_dec_attn") == 2 * cfg.n_decoder_layers * n_finish
     assert names.count("kr_dec_feed") == n_finish and per_step == 6
+    # KR_DECODE_GEMV=1: six skinny projections per layer and no separate LayerNorm / GLU launches inside the loop
+    assert names.count("kr_dec_gemv") == (6 * cfg.n_decoder_layers * n_finish if gemv else 0)
+    assert (names.count("kr_glu_fwd") == cfg.n_encoder_layers) == gemv          # only the encoder FFNs are left
     # eval mode: no dropout specs reached the kernels, the engine's training flag is restored
     assert eng.training is True
-    check_calls([c for c in rec.calls if c[0] in ("kr_dec_feed", "kr_dec_attn", "kr_dec_finish", "kr_lr_index",
+    check_calls([c for c in rec.calls if c[0] in ("kr_dec_feed", "kr_dec_attn", "kr_dec_finish", "kr_dec_gemv", "kr_lr_index",
                                                    "kr_expand_adapt", "kr_embed_fwd", "kr_layernorm_fwd", "kr_glu_fwd",
                                                    "kr_rmsnorm_resid_fwd", "kr_eq_mask_i64", "kr_scatter_rows",
                                                    "kr_vp_head_fwd", "kr_gn_fwd", "kr_memset_zero", "kr_gemm_bf16",
