@@ -75,6 +75,7 @@ def rec(monkeypatch):
         monkeypatch.setattr(mod, "lib", lambda: lib)
         monkeypatch.setattr(mod, "_ptr", ptr)
         monkeypatch.setattr(mod, "_stream", lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(ops, "_p", lambda t: None if t is None else t.data_ptr())     # struct-field pointers (kr_gemm_ex)
     monkeypatch.setattr(_lib, "lib", lambda: lib)
     monkeypatch.setattr(features, "_need_cuda", lambda t, what: None)
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
@@ -225,3 +226,71 @@ def test_inference_engine_dry_run_on_the_recording_lib(rec, monkeypatch, gemv):
     # predicted-duration path (no override): zeros from the stand-in -> Tp is padded to the 3-frame minimum
     mem, fmask, log_dur, Tp0 = inf.encode_and_expand(idx, None)
     assert Tp0 == 3 and mem.shape == (2 * 3, 128) and fmask.shape == (2, 3) and log_dur.shape == (2, 11)
+
+
+def test_eval_losses_with_metrics_dry_run(rec, monkeypatch):
+    """TrainStep.eval_losses(metrics=acc) on the recording library: the EMA-weights eval forward, the loss call and the
+    metrics fold run through every Python line of the device path; the C calls are checked against the header."""
+    monkeypatch.setenv("KR_STREAMS", "0")
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: None)
+    from kokoro_ruslan_b200 import engine as engine_mod
+    from kokoro_ruslan_b200 import optim, params
+    from kokoro_ruslan_b200 import train_step as ts_mod
+    from kokoro_ruslan_b200.params import ModelConfig
+    from oracle import acoustic as oa
+    ptr = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())      # noqa: E731
+    for mod in (engine_mod, params, optim, ts_mod):
+        for name, val in (("lib", lambda: rec), ("_ptr", ptr), ("_stream", lambda: ctypes.c_void_p(0))):
+            if hasattr(mod, name):
+                monkeypatch.setattr(mod, name, val)
+    cfg = ModelConfig(vocab_size=59, hidden_dim=128, n_encoder_layers=2, n_heads=2, encoder_ff_dim=256, n_decoder_layers=2,
+                      decoder_ff_dim=256, max_decoder_seq_len=1200, variance_filter_size=64)
+    ts = ts_mod.TrainStep(cfg, sched_cfg=ts_mod.ScheduleConfig(total_steps=10), device="cpu", use_graphs=False)
+    batch = oa.synthetic_batch(B=3, P=24, T=150, seed=11, ragged=True)
+    acc = ts.new_val_metrics()
+    assert acc.shape == (128,) and acc.dtype == torch.float32
+    before = (ts.engine.store.params.data_ptr(), ts.engine.training)
+    losses = ts.eval_losses(batch, use_ema=True, metrics=acc)
+    assert losses.shape == (6,)
+    assert (ts.engine.store.params.data_ptr(), ts.engine.training) == before      # EMA swap and eval mode undone
+    assert set(ts.read_val_metrics(acc)) == {"val_spectral_convergence", "val_f0_rmse"}
+    names = [n for n, _ in rec.calls]
+    assert names.count("kr_val_metrics") == 1 and names.count("kr_losses_fwd_bwd") == 1
+    vm = [a for n, a in rec.calls if n == "kr_val_metrics"][0]
+    assert (vm[6].value, vm[7].value, vm[9].value) == (3, 150, 80)                # B, T, n_mels
+    check_calls([c for c in rec.calls if c[0] in ("kr_val_metrics", "kr_losses_fwd_bwd", "kr_cast_bf16", "kr_expand_adapt")])
+
+
+@pytest.mark.parametrize("with_dropout", [False, True])
+def test_full_training_step_dry_run_conforms_to_the_header(rec, monkeypatch, with_dropout):
+    """One whole optimizer step (forward, losses, backward, norms, step control, AdamW / EMA, projection) on the recording
+    library: a regression net over every ctypes call site of the training path — ~40 entry points, a few hundred calls —
+    against the header prototypes."""
+    monkeypatch.setenv("KR_STREAMS", "0")
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: None)
+    from kokoro_ruslan_b200 import engine as engine_mod
+    from kokoro_ruslan_b200 import optim, params
+    from kokoro_ruslan_b200 import train_step as ts_mod
+    from kokoro_ruslan_b200.engine import DropoutConfig
+    from kokoro_ruslan_b200.params import ModelConfig
+    from oracle import acoustic as oa
+    ptr = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())      # noqa: E731
+    for mod in (engine_mod, params, optim, ts_mod):
+        for name, val in (("lib", lambda: rec), ("_ptr", ptr), ("_stream", lambda: ctypes.c_void_p(0))):
+            if hasattr(mod, name):
+                monkeypatch.setattr(mod, name, val)
+    cfg = ModelConfig(vocab_size=59, hidden_dim=128, n_encoder_layers=2, n_heads=2, encoder_ff_dim=256, n_decoder_layers=2,
+                      decoder_ff_dim=256, max_decoder_seq_len=1200, variance_filter_size=64)
+    ts = ts_mod.TrainStep(cfg, sched_cfg=ts_mod.ScheduleConfig(total_steps=10), device="cpu", use_graphs=False,
+                          dropout=DropoutConfig.reference_training() if with_dropout else None)
+    rec.calls.clear()
+    losses = ts.train_step(oa.synthetic_batch(B=3, P=24, T=150, seed=11, ragged=True))
+    assert losses.shape == (6,)
+    names = {n for n, _ in rec.calls}
+    assert {"kr_gemm_bf16", "kr_attn_fwd", "kr_attn_bwd", "kr_losses_fwd_bwd", "kr_adamw_step", "kr_step_control",
+            "kr_expand_adapt", "kr_lr_index", "kr_layernorm_bwd", "kr_qkv_prep_bwd"} <= names
+    assert ("kr_drop_begin" in names) == with_dropout
+    assert len(rec.calls) > 200 and len(names) >= 35
+    check_calls(rec.calls)
