@@ -294,3 +294,48 @@ def test_full_training_step_dry_run_conforms_to_the_header(rec, monkeypatch, wit
     assert ("kr_drop_begin" in names) == with_dropout
     assert len(rec.calls) > 200 and len(names) >= 35
     check_calls(rec.calls)
+
+
+def test_model_forward_inference_and_synthesizer_dry_run(rec, monkeypatch):
+    """KokoroModel.forward_inference (reference signature) -> HiFi-GAN through Synthesizer on the recording library: the
+    Python of the whole text-free TTS path, ~2000 C calls checked against the header (incl. kr_gemm_ex's argument struct)."""
+    monkeypatch.setenv("KR_STREAMS", "0")
+    monkeypatch.setenv("KR_DECODE_GRAPH", "0")
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: None)
+    from kokoro_ruslan_b200 import engine as engine_mod
+    from kokoro_ruslan_b200 import hifigan, inference, model, optim, params
+    ptr = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())      # noqa: E731
+    for mod in (engine_mod, params, optim, hifigan, model, inference):
+        for name, val in (("lib", lambda: rec), ("_ptr", ptr), ("_stream", lambda: ctypes.c_void_p(0))):
+            if hasattr(mod, name):
+                monkeypatch.setattr(mod, name, val)
+
+    class Finish:
+        restype = ctypes.c_int
+
+        def __call__(self, *args):
+            rec.calls.append(("kr_dec_finish", args))
+            st = (ctypes.c_int * 8).from_address(args[0].value)
+            if not st[1]:
+                st[0] += 1
+                if st[0] >= st[3] + 2:
+                    st[1], st[2] = 1, st[0]
+            return 0
+    object.__setattr__(rec, "kr_dec_finish", Finish())
+    with pytest.raises(NotImplementedError):
+        model.KokoroModel(vocab_size=59, device="cpu")              # the reference's qk_norm=False default is not on this path
+    m = model.KokoroModel(vocab_size=59, qk_norm=True, hidden_dim=128, n_encoder_layers=1, n_heads=2, encoder_ff_dim=256,
+                          n_decoder_layers=1, decoder_ff_dim=256, max_decoder_seq_len=400, variance_filter_size=64,
+                          device="cpu")
+    m.eval()
+    idx = torch.randint(1, 59, (1, 12))
+    with pytest.raises(NotImplementedError):
+        m(idx)                                                       # forward(mel_specs=None) still refuses (DESIGN.md)
+    mel = m.forward_inference(idx, min_len_floor=48, max_len_cap=64, stress_indices=torch.zeros(1, 12, dtype=torch.int64))
+    assert mel.shape == (1, 50, 80)
+    voc = hifigan.HiFiGANGenerator(hifigan.HiFiGANConfig.get_default_config(), device="cpu", use_graphs=False)
+    audio, mel = inference.Synthesizer(m, voc)(idx, min_len_floor=48, max_len_cap=64)
+    assert audio.shape == (1, 50 * 256) and mel.shape == (1, 50, 80)
+    assert len(rec.calls) > 1000
+    check_calls(rec.calls)

@@ -95,7 +95,7 @@ def test_model_forward_inference_surface_and_graph_equals_eager(monkeypatch):
     """KokoroModel.forward_inference (reference signature) end to end at the full model width, and the CUDA-graph replay
     against the same loop launched eagerly (KR_DECODE_GRAPH=0): identical frames."""
     from kokoro_ruslan_b200.model import KokoroModel
-    m = KokoroModel(vocab_size=59)
+    m = KokoroModel(vocab_size=59, encoder_ff_dim=1536, decoder_ff_dim=1536, qk_norm=True)
     m.eval()
     g = torch.Generator().manual_seed(3)
     idx = torch.randint(1, 59, (1, 16), generator=g).cuda()
@@ -111,7 +111,7 @@ def test_synthesizer_mel_to_waveform():
     from kokoro_ruslan_b200.hifigan import HiFiGANConfig, HiFiGANGenerator
     from kokoro_ruslan_b200.inference import Synthesizer
     from kokoro_ruslan_b200.model import KokoroModel
-    m = KokoroModel(vocab_size=59)
+    m = KokoroModel(vocab_size=59, encoder_ff_dim=1536, decoder_ff_dim=1536, qk_norm=True)
     m.eval()
     voc = HiFiGANGenerator(HiFiGANConfig.get_default_config())
     idx = torch.randint(1, 59, (1, 12), generator=torch.Generator().manual_seed(5)).cuda()

@@ -20,7 +20,7 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     P = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     frames = int(sys.argv[3]) if len(sys.argv) > 3 else 400
-    m = KokoroModel(vocab_size=59)
+    m = KokoroModel(vocab_size=59, encoder_ff_dim=1536, decoder_ff_dim=1536, qk_norm=True)
     m.eval()
     g = torch.Generator().manual_seed(0)
     idx = torch.randint(1, 59, (B, P), generator=g).cuda()
