@@ -32,7 +32,7 @@ class Finish:
         st = (ctypes.c_int * 8).from_address(args[0].value)
         if st[1]: return 0
         st[0] += 1
-        if st[0] >= st[3] + 2: st[1], st[2] = 1, st[0]
+        if st[0] >= st[3] + 2 or st[0] >= st[4]: st[1], st[2] = 1, st[0]      # two frames past lo, or the hard bound hi
         return 0
 object.__setattr__(lib, "kr_dec_finish", Finish())
 ptr = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())
