@@ -105,6 +105,7 @@ class RunConfig:
     # spectral convergence / F0 RMSE of the validation epoch as device reductions (reference trainer.py:1868-1916 always
     # computes them, with per-utterance host syncs); off by default until kr_val_metrics has had its first hardware run
     val_metrics: bool = False
+    async_checkpoints: bool = False           # torch.save on a writer thread (checkpoint.AsyncCheckpointWriter)
 
 
 def create_config_from_args(args) -> RunConfig:
@@ -274,6 +275,10 @@ def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
     hist: List[Dict] = []
     best, best_epoch, since_best, saved = float("inf"), -1, 0, []
     os.makedirs(cfg.output_dir, exist_ok=True)
+    writer = None
+    if cfg.async_checkpoints and rank == 0:
+        from .checkpoint import AsyncCheckpointWriter
+        writer = AsyncCheckpointWriter()
     for epoch in range(start_epoch, cfg.num_epochs):
         random.seed(cfg.seed + epoch)                 # every rank builds the identical epoch batch list
         sampler = make_sampler(train_ds, cfg)
@@ -310,21 +315,23 @@ def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
                 if vm[0] < best - cfg.early_stopping_min_delta:
                     best, best_epoch, since_best = vm[0], epoch, 0
                     if rank == 0:
-                        saved.append(save_checkpoint(cfg, step, epoch, rec, best, best_epoch))
+                        saved.append(save_checkpoint(cfg, step, epoch, rec, best, best_epoch, writer))
                 else:
                     since_best += 1
         hist.append(rec)
         log(f"epoch {epoch + 1}/{cfg.num_epochs}: " + ", ".join(f"{k}={v:.4f}" for k, v in rec.items()
                                                                   if isinstance(v, float)))
         if rank == 0 and cfg.save_every > 0 and (epoch + 1) % cfg.save_every == 0:
-            saved.append(save_checkpoint(cfg, step, epoch, rec, best, best_epoch))
+            saved.append(save_checkpoint(cfg, step, epoch, rec, best, best_epoch, writer))
         if val_ds is not None and cfg.early_stopping_patience > 0 and since_best >= cfg.early_stopping_patience:
             log(f"early stopping after epoch {epoch + 1} (best val_loss {best:.4f} at epoch {best_epoch + 1})")
             break
+    if writer is not None:
+        writer.wait()                                 # every file is on disk (or the failure is raised) before returning
     return {"history": hist, "best_val_loss": best, "best_val_epoch": best_epoch, "checkpoints": saved}
 
 
-def save_checkpoint(cfg: RunConfig, step, epoch: int, rec: Dict, best: float, best_epoch: int) -> str:
+def save_checkpoint(cfg: RunConfig, step, epoch: int, rec: Dict, best: float, best_epoch: int, writer=None) -> str:
     """checkpoint_epoch_{N}.pth with the reference's key names (trainer.py:1994-2031) for what this path owns."""
     path = os.path.join(cfg.output_dir, f"checkpoint_epoch_{epoch + 1}.pth")
     st = step.store
@@ -345,7 +352,10 @@ def save_checkpoint(cfg: RunConfig, step, epoch: int, rec: Dict, best: float, be
     if model_cfg is not None and hasattr(model_cfg, "hidden_dim"):
         from .checkpoint import build_model_metadata
         ckpt["model_metadata"] = build_model_metadata(model_cfg, cfg)
-    torch.save(ckpt, path)
+    if writer is not None:
+        writer.save(path, ckpt)                       # serialisation + file system on the writer thread
+    else:
+        torch.save(ckpt, path)
     return path
 
 

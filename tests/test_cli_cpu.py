@@ -257,3 +257,17 @@ def test_main_wires_configs_into_the_step(tmp_path, monkeypatch, capsys):
     ck = torch.load(os.path.join(str(tmp_path), "checkpoint_epoch_2.pth"), weights_only=False)
     assert ck["model_metadata"]["architecture"]["hidden_dim"] == 128
     assert len(ck["optimizer_state_dict"]["param_groups"]) == 10 and ck["config"]["ema_half_life_epochs"] == 1.0
+
+
+def test_async_checkpoints_are_complete_when_train_returns(tmp_path):
+    from kokoro_ruslan_b200 import cli
+    ds = cli.SyntheticDataset(12, seed=1, min_frames=60, max_frames=120)
+    train_ds, val_ds = cli.split_dataset(ds, 0.25, seed=3)
+    cfg = cli.RunConfig(output_dir=str(tmp_path), num_epochs=3, max_frames_per_batch=400, min_batch_size=1,
+                        max_batch_size=4, save_every=1, async_checkpoints=True)
+    out = cli.train(cfg, train_ds, val_ds, _StubStep([1.0, 0.9, 0.8]), log=lambda s: None)
+    names = sorted(os.path.basename(p) for p in set(out["checkpoints"]))
+    assert names == ["checkpoint_epoch_1.pth", "checkpoint_epoch_2.pth", "checkpoint_epoch_3.pth"]
+    for n in names:
+        ck = torch.load(os.path.join(str(tmp_path), n), weights_only=False)
+        assert "model_state_dict" in ck and not os.path.exists(os.path.join(str(tmp_path), n + ".tmp"))
