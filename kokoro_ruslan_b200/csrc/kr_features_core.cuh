@@ -101,8 +101,8 @@ namespace krf {
 constexpr int WIN = 2048;          // max(2048, hop * 8) with hop 256, variance_predictor.py:492
 constexpr int HOP = 256;
 constexpr int NFFT = 2 * WIN;      // zero-padded autocorrelation length, :517
-constexpr int LOG2_NFFT = 12;
-constexpr int TW = NFFT / 4;       // twiddle table: exp(-2 pi i j / 2048), j < 1024
+constexpr int LOG4_NFFT = 6;
+constexpr int TW = NFFT / 4 + 1;   // quarter-wave twiddle table: exp(-2 pi i j / 4096), j <= 1024
 constexpr int MAX_LAGS = 512;      // lag_max - lag_min + 1 (415 for 50..800 Hz at 22.05 kHz)
 
 // Number of analysis frames of an utterance of n samples: the signal is zero-padded to WIN, reflect-padded by
@@ -125,7 +125,127 @@ KRF_HD bool pitch_lag_range(int sample_rate, float fmin, float fmax, int* lag_mi
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Per-frame analysis.  One block per (frame f, utterance b).  Shared memory: z[NFFT] complex, tw[TW] complex,
+// In-place radix-4 FFT pair in shared memory, N = 4^m points, block-cooperative (N / 4 butterflies per stage spread over
+// the block, one barrier per stage).  fft4_forward is decimation-in-frequency: natural order in, base-4 digit-reversed
+// order out.  fft4_inverse is its exact mirror (decimation-in-time, conjugate twiddles, stages in reverse order):
+// digit-reversed in, natural order out, unnormalised.  A pointwise operation between the two (the power spectrum of the
+// autocorrelation) therefore needs no permutation at all; digit_reverse4() maps a natural bin index to its position for
+// consumers that do (the mel filterbank).  Twiddles come from a QUARTER-wave table qw[j] = exp(-2 pi i j / N),
+// j <= N / 4, rotated by multiples of -i for the other quadrants (exponents reach 3 N / 4).
+// Half the shared-memory passes and barriers of a radix-2 transform of the same size.
+// ------------------------------------------------------------------------------------------------------------------
+KRF_DEV void fft4_fill_twiddles(krf_float2* qw, int N) {
+  for (int j = KRF_TID; j <= N / 4; j += KRF_NT) {
+    float s, c;
+    krf_sincospi(-2.f * (float)j / (float)N, &s, &c);
+    qw[j] = krf_make2(c, s);
+  }
+}
+
+KRF_DEV krf_float2 fft4_twiddle(const krf_float2* qw, int e, int N) {      // exp(-2 pi i e / N), 0 <= e < N
+  const int quarter = N / 4, quad = e / quarter;
+  const krf_float2 t = qw[e - quad * quarter];
+  if (quad == 0) return t;
+  if (quad == 1) return krf_make2(t.y, -t.x);                              // * (-i)
+  if (quad == 2) return krf_make2(-t.x, -t.y);
+  return krf_make2(-t.y, t.x);                                             // * (+i)
+}
+
+KRF_DEV krf_float2 cmul(krf_float2 a, krf_float2 b) { return krf_make2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+KRF_DEV krf_float2 cmul_conj(krf_float2 a, krf_float2 b) {                 // a * conj(b)
+  return krf_make2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+KRF_DEV void fft4_forward(krf_float2* z, const krf_float2* qw, int N, int log4n) {
+  for (int st = log4n - 1; st >= 0; --st) {
+    const int lq = 2 * st, q = 1 << lq;                                    // quarter size of this stage's blocks
+    const int tw_step = N >> (lq + 2);                                     // N / (4 q)
+    for (int i = KRF_TID; i < N / 4; i += KRF_NT) {
+      const int k = i & (q - 1);
+      const int base = ((i >> lq) << (lq + 2)) + k;
+      const krf_float2 a0 = z[base], a1 = z[base + q], a2 = z[base + 2 * q], a3 = z[base + 3 * q];
+      const krf_float2 t0 = krf_make2(a0.x + a2.x, a0.y + a2.y), t1 = krf_make2(a0.x - a2.x, a0.y - a2.y);
+      const krf_float2 t2 = krf_make2(a1.x + a3.x, a1.y + a3.y);
+      const krf_float2 t3 = krf_make2(a1.y - a3.y, -(a1.x - a3.x));        // -i (a1 - a3)
+      const int e = k * tw_step;
+      z[base] = krf_make2(t0.x + t2.x, t0.y + t2.y);
+      z[base + q] = cmul(krf_make2(t1.x + t3.x, t1.y + t3.y), fft4_twiddle(qw, e, N));
+      z[base + 2 * q] = cmul(krf_make2(t0.x - t2.x, t0.y - t2.y), fft4_twiddle(qw, 2 * e, N));
+      z[base + 3 * q] = cmul(krf_make2(t1.x - t3.x, t1.y - t3.y), fft4_twiddle(qw, 3 * e, N));
+    }
+    KRF_SYNC();
+  }
+}
+
+KRF_DEV void fft4_inverse(krf_float2* z, const krf_float2* qw, int N, int log4n) {
+  for (int st = 0; st < log4n; ++st) {
+    const int lq = 2 * st, q = 1 << lq;
+    const int tw_step = N >> (lq + 2);
+    for (int i = KRF_TID; i < N / 4; i += KRF_NT) {
+      const int k = i & (q - 1);
+      const int base = ((i >> lq) << (lq + 2)) + k;
+      const int e = k * tw_step;
+      const krf_float2 b0 = z[base];
+      const krf_float2 b1 = cmul_conj(z[base + q], fft4_twiddle(qw, e, N));
+      const krf_float2 b2 = cmul_conj(z[base + 2 * q], fft4_twiddle(qw, 2 * e, N));
+      const krf_float2 b3 = cmul_conj(z[base + 3 * q], fft4_twiddle(qw, 3 * e, N));
+      const krf_float2 t0 = krf_make2(b0.x + b2.x, b0.y + b2.y), t1 = krf_make2(b0.x - b2.x, b0.y - b2.y);
+      const krf_float2 t2 = krf_make2(b1.x + b3.x, b1.y + b3.y);
+      const krf_float2 t3 = krf_make2(-(b1.y - b3.y), b1.x - b3.x);        // +i (b1 - b3)
+      z[base] = krf_make2(t0.x + t2.x, t0.y + t2.y);
+      z[base + q] = krf_make2(t1.x + t3.x, t1.y + t3.y);
+      z[base + 2 * q] = krf_make2(t0.x - t2.x, t0.y - t2.y);
+      z[base + 3 * q] = krf_make2(t1.x - t3.x, t1.y - t3.y);
+    }
+    KRF_SYNC();
+  }
+}
+
+// position of natural bin k in the output of fft4_forward: reverse the log4n base-4 digits of k
+KRF_DEV int digit_reverse4(int k, int log4n) {
+  int r = 0;
+  for (int d = 0; d < log4n; ++d) { r = (r << 2) | (k & 3); k >>= 2; }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Log-mel frame on the radix-4 transform (opt-in variant of kr_mel_stft, KR_MELSTFT_R4=1; the radix-2 Stockham kernel in
+// kr_melstft.cu is the hardware-validated default): reflect pad 512, periodic Hann 1024, 1024-point FFT (5 radix-4 stages
+// instead of 10 radix-2 ones), |X|^2 of the 513 one-sided bins read through the digit reversal, HTK filterbank (one warp
+// per filter), log.  Reference data/dataset.py:162-178, 694-697.  Shared memory: z[1024], qw[257], pw[513].
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int MEL_NFFT = 1024, MEL_LOG4 = 5, MEL_BINS = MEL_NFFT / 2 + 1;
+
+KRF_DEV void mel_frame_body(const float* x, long long n, int f, float gain, const float* fb_t, int n_mels,
+                            long long out_stride, float log_eps, krf_float2* z, krf_float2* qw, float* pw, float* orow) {
+  const int tid = KRF_TID, nt = KRF_NT;
+  fft4_fill_twiddles(qw, MEL_NFFT);
+  for (int i = tid; i < MEL_NFFT; i += nt) {
+    long long j = (long long)f * HOP + i - MEL_NFFT / 2;
+    if (j < 0) j = -j;
+    if (j >= n) j = 2 * (n - 1) - j;
+    j = j < 0 ? 0 : j;
+    const float w = 0.5f - 0.5f * krf_cospi(2.f * (float)i / (float)MEL_NFFT);
+    z[i] = krf_make2(krf_ldg(x + j) * gain * w, 0.f);
+  }
+  KRF_SYNC();
+  fft4_forward(z, qw, MEL_NFFT, MEL_LOG4);
+  for (int k = tid; k < MEL_BINS; k += nt) {
+    const krf_float2 u = z[digit_reverse4(k, MEL_LOG4)];
+    pw[k] = u.x * u.x + u.y * u.y;
+  }
+  KRF_SYNC();
+  for (int m = KRF_WARP; m < n_mels; m += KRF_NWARPS) {
+    const float* frow = fb_t + (long long)m * MEL_BINS;
+    float acc = 0.f;
+    for (int i = KRF_LANE; i < MEL_BINS; i += KRF_NLANES) acc = fmaf(pw[i], krf_ldg(frow + i), acc);
+    acc = krf_warp_sum(acc);
+    if (KRF_LANE == 0) orow[(long long)m * out_stride] = logf(acc + log_eps);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Per-frame analysis.  One block per (frame f, utterance b).  Shared memory: z[NFFT] complex, tw[TW] complex (quarter wave),
 // cm[MAX_LAGS] floats, red[32] floats.  Outputs (one float each per frame): the frequency candidate
 // before any voicing decision, the autocorrelation peak in the lag range, the mean energy of the windowed frame.
 // ------------------------------------------------------------------------------------------------------------------
@@ -134,12 +254,8 @@ KRF_DEV void pitch_frame_body(const float* x, long long n, int f, int lag_min, i
                               float* cand_out, float* acmax_out, float* energy_out) {
   const int tid = KRF_TID, nt = KRF_NT;
   const long long L = n < WIN ? WIN : n;
-  // phase 0: twiddles exp(-2 pi i j / 2048)
-  for (int j = tid; j < TW; j += nt) {
-    float s, c;
-    krf_sincospi(-2.f * (float)j / (float)(NFFT / 2), &s, &c);
-    tw[j] = krf_make2(c, s);
-  }
+  // phase 0: quarter-wave twiddle table
+  fft4_fill_twiddles(tw, NFFT);
   // phase 1: pre-emphasis (:499-503, applied AFTER the zero padding to WIN), reflect padding (:505-506),
   // periodic Hann (:512); upper half of the FFT buffer is the zero padding of the autocorrelation
   float e_part = 0.f;
@@ -161,57 +277,16 @@ KRF_DEV void pitch_frame_body(const float* x, long long n, int f, int lag_min, i
   }
   const float e_sum = krf_block_sum(e_part, red);      // (contains the barriers that publish z and tw)
   KRF_SYNC();
-  // phase 2: forward radix-2 decimation-in-frequency FFT, in place, natural order in, bit-reversed order out
-  for (int lh = LOG2_NFFT - 1; lh >= 0; --lh) {
-    const int h = 1 << lh;
-    for (int i = tid; i < NFFT / 2; i += nt) {
-      const int k = i & (h - 1);
-      const int a = ((i >> lh) << (lh + 1)) + k, b = a + h;
-      const int e = k << (LOG2_NFFT - 1 - lh);           // exponent of exp(-2 pi i / 4096)
-      krf_float2 w;
-      if (e & 1) {                                       // only in the first stage (h = 2048)
-        float s, c;
-        krf_sincospi(-2.f * (float)e / (float)NFFT, &s, &c);
-        w = krf_make2(c, s);
-      } else {
-        w = tw[e >> 1];
-      }
-      const krf_float2 u = z[a], v = z[b];
-      const float dx = u.x - v.x, dy = u.y - v.y;
-      z[a] = krf_make2(u.x + v.x, u.y + v.y);
-      z[b] = krf_make2(dx * w.x - dy * w.y, dx * w.y + dy * w.x);
-    }
-    KRF_SYNC();
-  }
-  // phase 3: power spectrum (pointwise, so the bit-reversed order does not matter)
+  // phase 2: forward radix-4 FFT (digit-reversed order out)
+  fft4_forward(z, tw, NFFT, LOG4_NFFT);
+  // phase 3: power spectrum (pointwise, so the digit-reversed order does not matter)
   for (int i = tid; i < NFFT; i += nt) {
     const krf_float2 u = z[i];
     z[i] = krf_make2(u.x * u.x + u.y * u.y, 0.f);
   }
   KRF_SYNC();
-  // phase 4: inverse radix-2 decimation-in-time FFT, bit-reversed order in, natural order out (unnormalised)
-  for (int lh = 0; lh < LOG2_NFFT; ++lh) {
-    const int h = 1 << lh;
-    for (int i = tid; i < NFFT / 2; i += nt) {
-      const int k = i & (h - 1);
-      const int a = ((i >> lh) << (lh + 1)) + k, b = a + h;
-      const int e = k << (LOG2_NFFT - 1 - lh);
-      krf_float2 w;
-      if (e & 1) {
-        float s, c;
-        krf_sincospi(2.f * (float)e / (float)NFFT, &s, &c);
-        w = krf_make2(c, s);
-      } else {
-        w = tw[e >> 1];
-        w.y = -w.y;                                      // conjugate twiddle
-      }
-      const krf_float2 u = z[a], v = z[b];
-      const float tx = v.x * w.x - v.y * w.y, ty = v.x * w.y + v.y * w.x;
-      z[a] = krf_make2(u.x + tx, u.y + ty);
-      z[b] = krf_make2(u.x - tx, u.y - ty);
-    }
-    KRF_SYNC();
-  }
+  // phase 4: inverse radix-4 FFT (digit-reversed in, natural order out, unnormalised)
+  fft4_inverse(z, tw, NFFT, LOG4_NFFT);
   // phase 5: cumulative mean normalised difference over the lag range (:522-529).  diff(tau) = 2 acf(0) - 2 acf(tau);
   // cmnd(tau) = diff(tau) / (cumsum(diff)[tau] / tau + 1e-8).  The running sum over tau < lag_min is one short serial
   // loop (torch accumulates a float cumsum in double on the CPU; so does this).

@@ -7,7 +7,9 @@
 // memory (fp32, exact-table twiddles) -> |X|^2 for the 513 one-sided bins -> HTK triangular
 // filterbank (dense [n_mels, 513] weights, each warp reduces its filters with shuffles) -> log.
 #include "kr_common.cuh"
+#include "kr_features_core.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace {
 using namespace kr;
@@ -100,6 +102,32 @@ mel_stft_kernel(const float* __restrict__ wav, const long long* __restrict__ len
   }
 }
 
+// Opt-in radix-4 variant (KR_MELSTFT_R4=1): body in kr_features_core.cuh (mel_frame_body), also compiled as a host
+// emulation by the CPU tests.  Written after the last GPU run of round 1: not yet executed on hardware, hence not the default.
+__global__ void __launch_bounds__(THREADS)
+mel_stft_r4_kernel(const float* __restrict__ wav, const long long* __restrict__ lengths, const float* __restrict__ peak,
+                   const float* __restrict__ fb_t, float* __restrict__ out, long long n_max, int frames_max, int n_mels,
+                   float log_eps) {
+  kr::pdl_entry();
+  __shared__ float2 z[krf::MEL_NFFT];
+  __shared__ float2 qw[krf::MEL_NFFT / 4 + 1];
+  __shared__ float pw[krf::MEL_BINS + 3];
+  const int f = blockIdx.x, b = blockIdx.y;
+  const long long n = lengths != nullptr ? lengths[b] : n_max;
+  float* orow = out + ((long long)b * n_mels) * frames_max + f;
+  if (f >= 1 + (int)(n / HOP)) {
+    for (int m = threadIdx.x; m < n_mels; m += THREADS) orow[(long long)m * frames_max] = 0.f;
+    return;
+  }
+  const float gain = peak != nullptr ? 1.f / (peak[b] + 1e-9f) : 1.f;
+  krf::mel_frame_body(wav + (long long)b * n_max, n, f, gain, fb_t, n_mels, frames_max, log_eps, z, qw, pw, orow);
+}
+
+bool use_r4() {                       // read per call (one launch per batch, not a hot loop) so tests can A/B in-process
+  const char* e = getenv("KR_MELSTFT_R4");
+  return e != nullptr && e[0] == '1';
+}
+
 }  // namespace
 
 extern "C" int kr_wave_peak(const float* wav, const long long* lengths, float* peak, int B, long long n_max, void* stream) {
@@ -119,8 +147,12 @@ extern "C" int kr_mel_stft(const float* wav, const long long* lengths, const flo
   if (n_fft != NFFT || hop != HOP) { kr_set_error("kr_mel_stft: built for n_fft 1024 / hop 256"); return KR_ERR_UNSUPPORTED; }
   if (B <= 0 || frames_max <= 0) return KR_OK;
   if (n_max < NFFT / 2 + 1) { kr_set_error("kr_mel_stft: waveform shorter than the reflect padding"); return KR_ERR_ARG; }
-  kr::launch(mel_stft_kernel, dim3(frames_max, B), THREADS, 0, (cudaStream_t)stream, wav, lengths, peak, fb_t, out, n_max,
-                                                                              frames_max, n_mels, log_eps);
+  if (use_r4())
+    kr::launch(mel_stft_r4_kernel, dim3(frames_max, B), THREADS, 0, (cudaStream_t)stream, wav, lengths, peak, fb_t, out,
+               n_max, frames_max, n_mels, log_eps);
+  else
+    kr::launch(mel_stft_kernel, dim3(frames_max, B), THREADS, 0, (cudaStream_t)stream, wav, lengths, peak, fb_t, out, n_max,
+               frames_max, n_mels, log_eps);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -105,3 +105,38 @@ def test_rank_counting_quantiles_with_ties(emu):
     got = emu_energy(emu, mel, log_domain=True)
     want = np.stack([of.extract_energy_from_mel(mel[b], True) for b in range(6)])
     assert np.abs(got - want).max() < 1e-6
+
+
+def test_radix4_mel_stft_variant_matches_torchaudio_golden(emu):
+    """KR_MELSTFT_R4=1 kernel body (radix-4 FFT + digit reversal) against torchaudio's own output and the float64 oracle,
+    at the gates of the device test of the default kernel (tests/test_melstft_gpu.py): 1e-3 absolute on the log-mel."""
+    import torch
+    from kokoro_ruslan_b200.features import mel_filterbank_htk
+    from oracle import melstft as om
+    fix = np.load(os.path.join(HERE, "golden", "melstft.npz"))
+    fb_t = np.ascontiguousarray(mel_filterbank_htk(513, 0.0, 8000.0, 80, 22050).t().numpy())
+    for case in ("a", "b", "c"):
+        wav = np.ascontiguousarray(fix[f"wav_{case}"], dtype=np.float32).reshape(1, -1)
+        want = fix[f"mel_{case}"]
+        n = wav.shape[1]
+        frames = 1 + n // 256
+        peak = np.array([np.abs(wav).max()], np.float32)
+        out = np.full((1, 80, frames), np.nan, np.float32)
+        assert emu.emu_mel_stft_r4(_p(wav), None, _p(peak), _p(fb_t), _p(out), 1, ctypes.c_longlong(n), frames, 80,
+                                   ctypes.c_float(1e-9)) == 0
+        assert out[0].shape == want.shape
+        assert np.abs(out[0] - want).max() < 1e-3, case
+        assert np.abs(out[0] - om.log_mel(wav[0])).max() < 1e-3
+    # ragged: frames beyond 1 + len // 256 are zero, the others equal the single run
+    wav2 = np.zeros((2, 9000), np.float32)
+    wav2[0] = fix["wav_a"][:9000]
+    wav2[1, :5000] = fix["wav_a"][:5000]
+    lens = np.array([9000, 5000], np.int64)
+    out2 = np.full((2, 80, 36), np.nan, np.float32)
+    assert emu.emu_mel_stft_r4(_p(wav2), _p(lens), None, _p(fb_t), _p(out2), 2, ctypes.c_longlong(9000), 36, 80,
+                               ctypes.c_float(1e-9)) == 0
+    single = np.full((1, 80, 20), np.nan, np.float32)
+    w1 = np.ascontiguousarray(wav2[1:2, :5000])
+    assert emu.emu_mel_stft_r4(_p(w1), None, None, _p(fb_t), _p(single), 1, ctypes.c_longlong(5000), 20, 80,
+                               ctypes.c_float(1e-9)) == 0
+    assert np.array_equal(out2[1, :, :20], single[0]) and np.all(out2[1, :, 20:] == 0.0)

@@ -107,3 +107,22 @@ def test_resample_matches_torchaudio_fixture():
     y, lens = speed_perturb(x, 0.93, lengths=torch.tensor([12000, 7001]))
     assert lens.tolist() == [11160, 6511] and float(y.abs().amax(dim=1).min()) == pytest.approx(1.0, abs=1e-6)
     assert float(y[1, 6511:].abs().sum()) == 0.0
+
+
+def test_radix4_mel_stft_variant(monkeypatch):
+    """KR_MELSTFT_R4=1 (radix-4 FFT kernel) against torchaudio's golden output and against the default radix-2 kernel."""
+    from kokoro_ruslan_b200.features import LogMelSpectrogram
+    fix = np.load(os.path.join(HERE, "golden", "melstft.npz"))
+    tr = LogMelSpectrogram()
+    wav = torch.from_numpy(fix["wav_a"]).cuda()
+    base = tr(wav).cpu()
+    monkeypatch.setenv("KR_MELSTFT_R4", "1")
+    got = tr(wav).cpu()
+    assert float((got[0] - torch.from_numpy(fix["mel_a"])).abs().max()) < 1e-3
+    assert float((got - base).abs().max()) < 1e-3 and not torch.equal(got, base)      # a different summation order
+    g = torch.Generator().manual_seed(5)
+    big = torch.randn(8, 256 * 799 + 100, generator=g).cuda()
+    a = tr(big, peak_normalize=False)
+    monkeypatch.setenv("KR_MELSTFT_R4", "0")
+    b = tr(big, peak_normalize=False)
+    assert a.shape == (8, 80, 800) and float((a - b).abs().max()) < 1e-3

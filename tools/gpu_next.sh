@@ -11,6 +11,7 @@ timeout 120 compute-sanitizer --tool racecheck python -m pytest tests/test_zz_fe
 timeout 200 compute-sanitizer --tool racecheck python -m pytest tests/test_zz_inference_gpu.py -m gpu -q -x -k teacher \
   > gpurun_out/racecheck_decode.log 2>&1; tail -3 gpurun_out/racecheck_decode.log
 timeout 120 python tools/features_bench.py > gpurun_out/features_bench.log 2>&1; cat gpurun_out/features_bench.log
+KR_MELSTFT_R4=1 timeout 120 python tools/features_bench.py > gpurun_out/features_bench_r4.log 2>&1; head -1 gpurun_out/features_bench_r4.log
 timeout 200 python tools/decode_bench.py 1 64 400 > gpurun_out/decode_bench.log 2>&1; cat gpurun_out/decode_bench.log
 KR_DECODE_GEMV=1 timeout 200 python tools/decode_bench.py 1 64 400 > gpurun_out/decode_bench_gemv.log 2>&1; cat gpurun_out/decode_bench_gemv.log
 KR_ATTN_FAST=1 python -m pytest tests -m gpu -q -x --deselect tests/test_zz_features_gpu.py --deselect tests/test_zz_inference_gpu.py \
