@@ -79,6 +79,11 @@ def rec(monkeypatch):
     monkeypatch.setattr(_lib, "lib", lambda: lib)
     monkeypatch.setattr(features, "_need_cuda", lambda t, what: None)
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    # nothing is computed in a dry run: hand out zero-filled activations instead of uninitialised memory, so that the few
+    # host decisions taken on device results (predicted durations -> expanded length) are deterministic
+    from kokoro_ruslan_b200 import engine as engine_mod
+    monkeypatch.setattr(engine_mod.AcousticEngine, "_empty",
+                        lambda self, *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype))
     return lib
 
 

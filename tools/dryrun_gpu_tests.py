@@ -44,6 +44,7 @@ ops._p = lambda t: None if t is None else t.data_ptr()
 features._need_cuda = lambda t, w: None
 _lib.lib = lambda: lib
 torch.cuda.is_available = lambda: True
+E.AcousticEngine._empty = lambda self, *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype)   # deterministic dry run
 torch.Tensor.pin_memory = lambda self, *a, **k: self
 torch.cuda.current_stream = lambda *a, **k: None
 torch.Tensor.cuda = lambda self, *a, **k: self
