@@ -92,6 +92,17 @@ energy_norm_kernel(const float* __restrict__ e, const long long* __restrict__ fr
   krf::energy_norm_body(e + o, (int)T, T_max, sel, red, out + o);
 }
 
+__global__ void __launch_bounds__(TRACK_THREADS)
+trim_end_kernel(const float* __restrict__ e, const long long* __restrict__ frames, int* __restrict__ t_end, int T_max) {
+  kr::pdl_entry();
+  __shared__ float sel[4];
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  long long T = frames != nullptr ? frames[b] : T_max;
+  T = T < 0 ? 0 : (T < T_max ? T : T_max);
+  krf::trim_end_body(e + (long long)b * T_max, (int)T, sel, red, t_end + b);
+}
+
 }  // namespace
 
 // cand / acmax / energy: [B, frames_max] fp32 per-frame intermediates (entries of frames beyond an utterance's own
@@ -138,6 +149,15 @@ extern "C" int kr_energy_frames(const float* mel, float* e, int B, int T, int n_
 extern "C" int kr_energy_norm(const float* e, const long long* frames, float* out, int B, int T, void* stream) {
   if (B <= 0 || T <= 0) return KR_OK;
   kr::launch(energy_norm_kernel, dim3(B), TRACK_THREADS, 0, (cudaStream_t)stream, e, frames, out, T);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+// e: [B, T] per-frame mel means (kr_energy_frames with log_domain = 1); t_end[b] = frames to keep of utterance b.
+extern "C" int kr_trim_end(const float* e, const long long* frames, int* t_end, int B, int T, void* stream) {
+  if (B <= 0) return KR_OK;
+  if (T <= 0) { kr_set_error("kr_trim_end: no frames"); return KR_ERR_ARG; }
+  kr::launch(trim_end_kernel, dim3(B), TRACK_THREADS, 0, (cudaStream_t)stream, e, frames, t_end, T);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

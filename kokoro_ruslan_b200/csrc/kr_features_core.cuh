@@ -466,4 +466,34 @@ KRF_DEV void energy_norm_body(const float* e, int T, int T_max, float* sel, floa
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Trailing-silence trim of a generated mel before vocoding (reference inference/inference.py:590-621): from the per-frame
+// means e[0..T) (kr_energy_frames, log-domain branch) the threshold clamp(0.5 * (q10 + q20), -9.8, -9.2), the last frame
+// above it, and t_end = min(T, max(60, last + 24 + 1)); T when no frame is above the threshold.  One block per utterance.
+// ------------------------------------------------------------------------------------------------------------------
+KRF_DEV void trim_end_body(const float* e, int T, float* sel, float* red, int* t_end) {
+  if (T <= 0) { if (KRF_TID == 0) *t_end = 0; return; }
+  int rk[4];
+  float w0, w1;
+  quantile_ranks(0.10f, T, &rk[0], &rk[1], &w0);
+  quantile_ranks(0.20f, T, &rk[2], &rk[3], &w1);
+  select_ranks(e, T, rk, 4, sel);
+  const float q10 = lerp_torch(sel[0], sel[1], w0), q20 = lerp_torch(sel[2], sel[3], w1);
+  const float thr = fmaxf(-9.8f, fminf(-9.2f, 0.5f * (q10 + q20)));
+  float last = -1.f;                                       // frame indices are exact in float (T < 2^24)
+  for (int t = KRF_TID; t < T; t += KRF_NT)
+    if (e[t] > thr) last = fmaxf(last, (float)t);
+  last = krf_block_max(last, red);
+  if (KRF_TID == 0) {
+    int end = T;
+    if (last >= 0.f) {
+      const int proposed = (int)last + 24 + 1 < T ? (int)last + 24 + 1 : T;
+      end = proposed > 60 ? proposed : 60;
+      end = end < T ? end : T;
+    }
+    *t_end = end;
+  }
+}
+
 }  // namespace krf

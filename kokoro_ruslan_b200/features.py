@@ -249,3 +249,21 @@ def speed_perturb(waveform: torch.Tensor, factor: float, sample_rate: int = 2205
           "kr_wave_peak")
     out = y2 / (peak[:, None] + 1e-9)
     return (out[0] if y.dim() == 1 else out), new_len
+
+
+def trailing_trim_end(mel_spec: torch.Tensor, frames: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Frames to keep per utterance after the reference's conservative trailing-silence trim
+    (src/kokoro/inference/inference.py:590-621).  ``mel_spec``: (B, T, n_mels) or (T, n_mels) log-mel, already clamped to
+    [-11.5, 2] like the reference's input.  Returns an int32 tensor (B,) (or a 0-d tensor) on the device."""
+    _need_cuda(mel_spec, "trailing_trim_end")
+    squeeze = mel_spec.dim() == 2
+    mel = (mel_spec.unsqueeze(0) if squeeze else mel_spec).to(torch.float32).contiguous()
+    B, T, M = mel.shape
+    if frames is not None:
+        frames = frames.to(mel.device, torch.int64).contiguous()
+    e = torch.empty(B, T, dtype=torch.float32, device=mel.device)
+    t_end = torch.empty(B, dtype=torch.int32, device=mel.device)
+    check(lib().kr_energy_frames(_ptr(mel), _ptr(e), ctypes.c_int(B), ctypes.c_int(T), ctypes.c_int(M), ctypes.c_int(1),
+                                 ctypes.c_int(0), ctypes.c_int(1), _stream()), "kr_energy_frames")
+    check(lib().kr_trim_end(_ptr(e), _ptr(frames), _ptr(t_end), ctypes.c_int(B), ctypes.c_int(T), _stream()), "kr_trim_end")
+    return t_end[0] if squeeze else t_end

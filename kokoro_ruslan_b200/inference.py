@@ -399,14 +399,19 @@ class Synthesizer:
     path's scope).  ``vocoder`` is a ``kokoro_ruslan_b200.hifigan.HiFiGANGenerator`` (or anything callable on a
     (B, frames, n_mels) CUDA mel)."""
 
-    def __init__(self, model, vocoder):
-        self.model, self.vocoder = model, vocoder
+    def __init__(self, model, vocoder, trim_trailing_silence: bool = True):
+        self.model, self.vocoder, self.trim = model, vocoder, trim_trailing_silence
 
     @torch.no_grad()
     def __call__(self, phoneme_indices: torch.Tensor, stress_indices: Optional[torch.Tensor] = None,
                  **generate_kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Returns (audio (B, samples), mel (B, frames, n_mels)); samples = frames * hop (256)."""
+        """Returns (audio (B, samples), mel (B, frames, n_mels)); samples = frames * hop (256).  With
+        ``trim_trailing_silence`` (single utterance, like the reference) the mel is cut at the reference's conservative
+        trailing-silence point first (inference.py:590-621; one host read of the frame count)."""
         mel = self.model.forward_inference(phoneme_indices, stress_indices=stress_indices, **generate_kwargs)
+        if self.trim and mel.shape[0] == 1 and mel.shape[1] > 0:
+            from .features import trailing_trim_end
+            mel = mel[:, :int(trailing_trim_end(mel)[0])]
         audio = self.vocoder(mel.contiguous())               # (B, T, 80) is auto-detected like the reference's forward
         if audio.dim() == 3:
             audio = audio.squeeze(1)

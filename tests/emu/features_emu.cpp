@@ -82,3 +82,13 @@ extern "C" int emu_mel_stft_r4(const float* wav, const long long* lengths, const
   }
   return 0;
 }
+
+extern "C" int emu_trim_end(const float* e, const long long* frames, int* t_end, int B, int T_max) {
+  float sel[4], red[32];
+  for (int b = 0; b < B; ++b) {
+    long long T = frames ? frames[b] : T_max;
+    T = T < 0 ? 0 : (T < T_max ? T : T_max);
+    krf::trim_end_body(e + (long long)b * T_max, (int)T, sel, red, t_end + b);
+  }
+  return 0;
+}

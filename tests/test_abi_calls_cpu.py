@@ -98,6 +98,7 @@ def test_feature_wrappers_match_the_header(rec):
     features.EnergyExtractor.extract_energy_from_mel(mel.transpose(1, 2).contiguous(), False, channel_major=True, exp_input=True)
     features.resample(wav[:, :1000], 22050, 20506, lengths=torch.tensor([1000, 500]))
     features.speed_perturb(wav[:, :1000], 0.93, lengths=torch.tensor([1000, 500]))
+    assert features.trailing_trim_end(mel).shape == (2,) and features.trailing_trim_end(mel[0]).dim() == 0
     tr = features.LogMelSpectrogram(device="cpu")
     tr(wav, lens)
     pipe = features.FeaturePipeline(device="cpu")
@@ -106,7 +107,7 @@ def test_feature_wrappers_match_the_header(rec):
     assert out["mel_lengths"].tolist() == [24, 16]
     names = {n for n, _ in rec.calls}
     assert {"kr_pitch_frames", "kr_pitch_track", "kr_energy_frames", "kr_energy_norm", "kr_resample", "kr_resample_length",
-            "kr_wave_peak", "kr_mel_stft"} <= names
+            "kr_wave_peak", "kr_mel_stft", "kr_trim_end"} <= names
     check_calls(rec.calls)
 
 

@@ -140,3 +140,36 @@ def test_radix4_mel_stft_variant_matches_torchaudio_golden(emu):
     assert emu.emu_mel_stft_r4(_p(w1), None, None, _p(fb_t), _p(single), 1, ctypes.c_longlong(5000), 20, 80,
                                ctypes.c_float(1e-9)) == 0
     assert np.array_equal(out2[1, :, :20], single[0]) and np.all(out2[1, :, 20:] == 0.0)
+
+
+def _reference_trim_end(mel):
+    """inference/inference.py:593-619, literally (mel: (T, n_mels) torch tensor)."""
+    import torch
+    frame_means = mel.mean(dim=-1)
+    q10 = float(torch.quantile(frame_means, 0.10).item())
+    q20 = float(torch.quantile(frame_means, 0.20).item())
+    thr = max(-9.8, min(-9.2, 0.5 * (q10 + q20)))
+    voiced = (frame_means > thr).nonzero(as_tuple=False).squeeze(-1)
+    if voiced.numel() == 0:
+        return mel.shape[0]
+    proposed_end = min(mel.shape[0], int(voiced[-1]) + 24 + 1)
+    return min(max(60, proposed_end), mel.shape[0])
+
+
+def test_trailing_trim_matches_reference_rule(emu):
+    import torch
+    g = torch.Generator().manual_seed(0)
+    cases = []
+    for T, speech_end in ((300, 180), (300, 299), (90, 20), (40, 10), (500, 0), (200, 100)):
+        mel = torch.full((T, 80), -10.5) + 0.3 * torch.randn(T, 80, generator=g)          # quiet tail level
+        mel[:speech_end] = -5.0 + 2.0 * torch.randn(speech_end, 80, generator=g)          # speech
+        cases.append(mel.clamp(-11.5, 2.0))
+    cases.append(torch.full((120, 80), -11.0))                                            # nothing above the threshold
+    for mel in cases:
+        T = mel.shape[0]
+        m = np.ascontiguousarray(mel.numpy()[None])
+        e, t_end = np.zeros((1, T), np.float32), np.full(1, -1, np.int32)
+        assert emu.emu_energy_frames(_p(m), _p(e), 1, T, 80, 1, 0, 1) == 0
+        assert emu.emu_trim_end(_p(e), None, _p(t_end), 1, T) == 0
+        assert int(t_end[0]) == _reference_trim_end(mel), (T, int(t_end[0]), _reference_trim_end(mel))
+    assert _reference_trim_end(cases[0]) == 180 + 24 and _reference_trim_end(cases[3]) == 40

@@ -126,3 +126,14 @@ def test_radix4_mel_stft_variant(monkeypatch):
     monkeypatch.setenv("KR_MELSTFT_R4", "0")
     b = tr(big, peak_normalize=False)
     assert a.shape == (8, 80, 800) and float((a - b).abs().max()) < 1e-3
+
+
+def test_trailing_trim_matches_reference_rule():
+    from kokoro_ruslan_b200.features import trailing_trim_end
+    from test_features_emu_cpu import _reference_trim_end
+    g = torch.Generator().manual_seed(0)
+    for T, speech_end in ((300, 180), (300, 299), (90, 20), (40, 10), (500, 0)):
+        mel = torch.full((T, 80), -10.5) + 0.3 * torch.randn(T, 80, generator=g)
+        mel[:speech_end] = -5.0 + 2.0 * torch.randn(speech_end, 80, generator=g)
+        mel = mel.clamp(-11.5, 2.0)
+        assert int(trailing_trim_end(mel.cuda())) == _reference_trim_end(mel), T

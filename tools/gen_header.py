@@ -37,6 +37,7 @@ DOCS = {
     "kr_resample": "Hann-windowed sinc resampling with torchaudio.functional.resample's defaults (lowpass_filter_width 6, rolloff 0.99) — the speed perturbation of data/dataset.py:674-684. Every output sample evaluates its own ~14 taps (float64 like torchaudio's filter-bank construction, including its float32 phase offsets, rounded to float32) instead of a [new, 2 * width + orig] filter bank and a strided conv1d; rows are zero beyond ceil(new * len[b] / orig).",
     "kr_average_by_duration": "Frame-level values averaged to token level through the durations, bit-identical to the scatter formulation of utils/lengths.py:156-208 (clamped starts / ends, frames no token covers fall to token 0, masked or zero-duration tokens give 0); sums run in ascending frame order per token.",
     "kr_dec_gemv": "Skinny projection of a decode step (B <= 8 rows): out = x . W^T (+ bias) (+ residual), the weight matrix streamed once by the whole grid, one warp per output feature, fp32 accumulation; optional LayerNorm prologue (the pre-norm of model/transformers.py:564,572,581) and GLU epilogue (gelu_erf(gate) * lin, :105-108) — the weight-bandwidth-shaped replacement of the nn.Linear calls of model/transformers.py:228,258-259,434,105-111 inside the autoregressive loop (model/generator.py:44-103).",
+    "kr_trim_end": "Trailing-silence trim point of a generated mel before vocoding, inference/inference.py:590-621: threshold clamp(0.5 * (q10 + q20) of the frame means, -9.8, -9.2), last frame above it + 24 frames of margin, at least 60 frames, at most T; T when nothing is above the threshold. Input = kr_energy_frames' per-frame means.",
     "kr_spec_augment": "SpecAugment on the cross-attention memory (bf16) or its gradient (fp32): zeroes the per-sample frame / hidden-dim spans in spans[B, n_time+n_feat, 2] = (start, length). training/trainer.py:1578-1604, applied at model/model.py:636-639.",
     "kr_attn_fwd": "tcgen05 flash attention forward, head_dim 64, on token-major [B,S,H,64] bf16 tensors (q_ss/q_bs = seq/batch strides in elements). Causal and per-key padding (key_mask[B,Sk], 1 = masked) are predicates; lse[B,H,Sq] is the log2-domain log-sum-exp kept for the backward. Replaces F.scaled_dot_product_attention with the dense additive mask, model/transformers.py:299-316,393-398.",
     "kr_attn_bwd": "Flash attention backward: dq (fp32 [B,Sq,H,64], zeroed by the call's own prep kernel, then atomically accumulated), dk/dv (bf16). delta[B,H,Sq] is scratch. Autograd of model/transformers.py:393-398.",
