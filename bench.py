@@ -14,6 +14,9 @@ through TrainStep.train_step() with pinned HOST batches (H2D inside the timed re
 read of the losses every step.  `roofline` = the tcgen05 GEMM family (dominant kernel) timed per
 launch with CUDA events in an instrumented eager step right after the timed region;
 `cpu_baseline` = the oracle port of the same step on the host cores (bounded sample).
+`first_hardware_run` (N = 1 only, `--no-extras` skips it) = micro-benchmarks of the kernels added after round 1's
+GPU budget was spent, each in its own subprocess with a hard timeout AFTER every headline measurement is done, so
+that a fault in a never-run kernel cannot touch the numbers above; not part of the headline metric.
 `--impl reference` times the CPU oracle port only (the reference is pure Python/PyTorch and its
 algorithm is restated in oracle/).
 """
@@ -244,6 +247,43 @@ def hifigan_leg(peaks, steps: int = 10, B: int = 16, T: int = 800):
 # ----------------------------------------------------------------------------------------------
 # product arm
 # ----------------------------------------------------------------------------------------------
+def first_hardware_run_leg(budget_s: float = 240.0):
+    """Micro-benchmarks of the kernels written after round 1's GPU budget was spent (feature pipeline N1, decode step N2:
+    tools/features_bench.py, tools/decode_bench.py, default and opt-in variants), each in its OWN subprocess with a hard
+    timeout, after every headline measurement is finished: a fault or a hang in a kernel that has never run on hardware
+    cannot touch the numbers above.  Not part of the headline metric; parity of these kernels is what
+    tests/test_zz_*_gpu.py check (first-run xfail markers)."""
+    import subprocess
+    root = os.path.dirname(os.path.abspath(__file__))
+    runs = [("features", ["tools/features_bench.py"], {}),
+            ("features_mel_radix4", ["tools/features_bench.py"], {"KR_MELSTFT_R4": "1"}),
+            ("decode", ["tools/decode_bench.py", "1", "64", "400"], {}),
+            ("decode_gemv", ["tools/decode_bench.py", "1", "64", "400"], {"KR_DECODE_GEMV": "1"})]
+    out = {"note": "first hardware run of kernels verified by host emulation only (DESIGN.md 3a); timings, not parity"}
+    t_end = time.time() + budget_s
+    for name, cmd, env in runs:
+        left = t_end - time.time()
+        if left < 20.0:
+            out[name] = {"error": "skipped: time budget of the leg used up"}
+            continue
+        try:
+            r = subprocess.run([sys.executable] + cmd, cwd=root, env={**os.environ, **env}, capture_output=True, text=True,
+                               timeout=min(120.0, left))
+            rows = []
+            for ln in r.stdout.splitlines():
+                if ln.startswith("{"):
+                    try:
+                        rows.append(json.loads(ln))
+                    except ValueError:
+                        pass
+            out[name] = rows if (r.returncode == 0 and rows) else {"rc": r.returncode, "error": (r.stderr or r.stdout)[-400:]}
+        except subprocess.TimeoutExpired:
+            out[name] = {"error": "timeout"}
+        except Exception as exc:                                    # never let an extra take the bench line down
+            out[name] = {"error": repr(exc)}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -406,6 +446,14 @@ def run_ours(args):
         except Exception as exc:
             cpu = {"error": repr(exc)}
 
+    # ---- kernels that have not had a hardware run yet: isolated subprocesses, after everything above ------
+    extras = None
+    if world == 1 and not args.no_extras:
+        try:
+            extras = first_hardware_run_leg()
+        except Exception as exc:
+            extras = {"error": repr(exc)}
+
     line = {"metric": METRIC, "value": frames_per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -421,7 +469,7 @@ def run_ours(args):
             "e2e": {"value": frames_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d_bytes + 8 + 40, "d2h_bytes_per_step": 24},
             "gpu_launches": launches_per_step * args.steps * 2, "launches_per_step": launches_per_step,
-            "hifigan": hifi, "clocks": clocks, "losses_first": first_losses, "losses_last": final_losses, "top_ops": top_ops,
+            "hifigan": hifi, "first_hardware_run": extras, "clocks": clocks, "losses_first": first_losses, "losses_last": final_losses, "top_ops": top_ops,
             "lib": str(_lib.LIB_PATH)}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -440,6 +488,8 @@ def main():
                          "off = the deterministic parity configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hifigan", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the isolated micro-benchmarks of the kernels that have not had a hardware run yet")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
