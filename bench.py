@@ -248,20 +248,29 @@ def hifigan_leg(peaks, steps: int = 10, B: int = 16, T: int = 800):
 # product arm
 # ----------------------------------------------------------------------------------------------
 def first_hardware_run_leg(budget_s: float = 240.0):
-    """Micro-benchmarks of the kernels written after round 1's GPU budget was spent (feature pipeline N1, decode step N2:
-    tools/features_bench.py, tools/decode_bench.py, default and opt-in variants), each in its OWN subprocess with a hard
-    timeout, after every headline measurement is finished: a fault or a hang in a kernel that has never run on hardware
-    cannot touch the numbers above.  Not part of the headline metric; parity of these kernels is what
-    tests/test_zz_*_gpu.py check (first-run xfail markers)."""
+    """First hardware run of what was written after round 1's GPU budget was spent: the device tests of the new kernels
+    (tests/test_zz_*_gpu.py with -rxX, so the reason of every xfail is recorded), their micro-benchmarks
+    (tools/features_bench.py, tools/decode_bench.py, default and opt-in variants) and the whole validated suite under the
+    opt-in KR_ATTN_FAST=1 attention forward — each in its OWN subprocess with a hard timeout, after every headline
+    measurement is finished: a fault or a hang in a never-run kernel cannot touch the numbers above.  Not part of the
+    headline metric."""
     import subprocess
     root = os.path.dirname(os.path.abspath(__file__))
-    runs = [("features", ["tools/features_bench.py"], {}),
-            ("features_mel_radix4", ["tools/features_bench.py"], {"KR_MELSTFT_R4": "1"}),
-            ("decode", ["tools/decode_bench.py", "1", "64", "400"], {}),
-            ("decode_gemv", ["tools/decode_bench.py", "1", "64", "400"], {"KR_DECODE_GEMV": "1"})]
-    out = {"note": "first hardware run of kernels verified by host emulation only (DESIGN.md 3a); timings, not parity"}
+    zz = ["tests/test_zz_features_gpu.py", "tests/test_zz_lengths_gpu.py", "tests/test_zz_metrics_gpu.py",
+          "tests/test_zz_inference_gpu.py"]
+    # (name, argv after the interpreter, extra environment, "json" = collect JSON lines | "tail" = keep the last lines)
+    runs = [("device_tests", ["-m", "pytest", *zz, "-m", "gpu", "-q", "-rxX", "--tb=line", "-p", "no:cacheprovider"], {}, "tail"),
+            ("features", ["tools/features_bench.py"], {}, "json"),
+            ("decode", ["tools/decode_bench.py", "1", "64", "400"], {}, "json"),
+            ("decode_gemv", ["tools/decode_bench.py", "1", "64", "400"], {"KR_DECODE_GEMV": "1"}, "json"),
+            ("features_mel_radix4", ["tools/features_bench.py"], {"KR_MELSTFT_R4": "1"}, "json"),
+            # the opt-in attention-forward variant of DESIGN.md section 10.1 over the whole validated suite
+            ("attn_fast_suite", ["-m", "pytest", "tests", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                                 *[a for z in zz for a in ("--deselect", z)]], {"KR_ATTN_FAST": "1"}, "tail")]
+    out = {"note": "first hardware run of kernels verified by host emulation only (DESIGN.md 3a) and of the opt-in "
+                   "variants; isolated subprocesses after the headline measurements; not part of the headline metric"}
     t_end = time.time() + budget_s
-    for name, cmd, env in runs:
+    for name, cmd, env, kind in runs:
         left = t_end - time.time()
         if left < 20.0:
             out[name] = {"error": "skipped: time budget of the leg used up"}
@@ -269,6 +278,9 @@ def first_hardware_run_leg(budget_s: float = 240.0):
         try:
             r = subprocess.run([sys.executable] + cmd, cwd=root, env={**os.environ, **env}, capture_output=True, text=True,
                                timeout=min(120.0, left))
+            if kind == "tail":
+                out[name] = {"rc": r.returncode, "tail": [ln[:300] for ln in r.stdout.splitlines()[-30:]]}
+                continue
             rows = []
             for ln in r.stdout.splitlines():
                 if ln.startswith("{"):
