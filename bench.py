@@ -249,7 +249,7 @@ def hifigan_leg(peaks, steps: int = 10, B: int = 16, T: int = 800):
 # ----------------------------------------------------------------------------------------------
 def first_hardware_run_leg(budget_s: float = 240.0):
     """First hardware run of what was written after round 1's GPU budget was spent: the device tests of the new kernels
-    (tests/test_zz_*_gpu.py with -rxX, so the reason of every xfail is recorded), their micro-benchmarks
+    (tests/test_zz_*_gpu.py with --runxfail, so that every failure is recorded with its exception line), their micro-benchmarks
     (tools/features_bench.py, tools/decode_bench.py, default and opt-in variants) and the whole validated suite under the
     opt-in KR_ATTN_FAST=1 attention forward — each in its OWN subprocess with a hard timeout, after every headline
     measurement is finished: a fault or a hang in a never-run kernel cannot touch the numbers above.  Not part of the
@@ -259,7 +259,9 @@ def first_hardware_run_leg(budget_s: float = 240.0):
     zz = ["tests/test_zz_features_gpu.py", "tests/test_zz_lengths_gpu.py", "tests/test_zz_metrics_gpu.py",
           "tests/test_zz_inference_gpu.py"]
     # (name, argv after the interpreter, extra environment, "json" = collect JSON lines | "tail" = keep the last lines)
-    runs = [("device_tests", ["-m", "pytest", *zz, "-m", "gpu", "-q", "-rxX", "--tb=line", "-p", "no:cacheprovider"], {}, "tail"),
+    runs = [# --runxfail: the first-run xfail markers are ignored here, so a failure is reported with its exception line
+            ("device_tests", ["-m", "pytest", *zz, "-m", "gpu", "-q", "--runxfail", "-rfE", "--tb=line", "-p", "no:cacheprovider"],
+             {}, "tail"),
             ("features", ["tools/features_bench.py"], {}, "json"),
             ("decode", ["tools/decode_bench.py", "1", "64", "400"], {}, "json"),
             ("decode_gemv", ["tools/decode_bench.py", "1", "64", "400"], {"KR_DECODE_GEMV": "1"}, "json"),
