@@ -3,7 +3,7 @@
 # validation metrics N3) get their first hardware run, then their micro-benchmarks.  Outputs land in gpurun_out/.
 #   gpurun --timeout 900 -- 'bash tools/gpu_next.sh'
 mkdir -p gpurun_out
-python -m pytest tests/test_zz_features_gpu.py tests/test_zz_lengths_gpu.py tests/test_zz_metrics_gpu.py tests/test_zz_inference_gpu.py -m gpu -q -rxX \
+python -m pytest tests/test_zz_features_gpu.py tests/test_zz_lengths_gpu.py tests/test_zz_metrics_gpu.py tests/test_zz_inference_gpu.py -m gpu -q --runxfail --tb=short -rfE \
   > gpurun_out/pytest_zz.log 2>&1
 tail -15 gpurun_out/pytest_zz.log
 timeout 120 compute-sanitizer --tool racecheck python -m pytest tests/test_zz_features_gpu.py -m gpu -q -x -k "pitch_matches or energy" \
