@@ -35,7 +35,7 @@ dec_attn_kernel(const krd::DecState* __restrict__ st, const bf16* __restrict__ q
                 const float* __restrict__ gq, const float* __restrict__ gk, const float* __restrict__ gv,
                 const float* __restrict__ cos_t, const float* __restrict__ sin_t, bf16* kc, bf16* vc, long long cache_ld,
                 long long cache_bs, int n_keys, const unsigned char* __restrict__ mask, bf16* __restrict__ o,
-                long long ld_o, float scale) {
+                long long ld_o, float scale, int rotate_q) {
   kr::pdl_entry();
   __shared__ float qs[krd::DK], wm[krd::MAX_WARPS], wl[krd::MAX_WARPS], wacc[krd::MAX_WARPS * krd::DK];
   if (st->done) return;
@@ -48,7 +48,7 @@ dec_attn_kernel(const krd::DecState* __restrict__ st, const bf16* __restrict__ q
                      self ? cos_t + (long long)t * (krd::DK / 2) : nullptr, self ? sin_t + (long long)t * (krd::DK / 2) : nullptr,
                      kc + (long long)b * cache_bs + col, vc + (long long)b * cache_bs + col, cache_ld,
                      self ? t + 1 : n_keys, self ? t : -1, mask != nullptr ? mask + (long long)b * n_keys : nullptr,
-                     scale, 1.1920929e-7f, qs, wm, wl, wacc, o + (long long)b * ld_o + col);
+                     scale, 1.1920929e-7f, rotate_q, qs, wm, wl, wacc, o + (long long)b * ld_o + col);
 }
 
 __global__ void __launch_bounds__(FINISH_THREADS)
@@ -120,12 +120,14 @@ extern "C" int kr_dec_feed(const void* state, const float* prev, const float* fo
 
 // n_keys < 0: self-attention of the new frame — k_raw / v_raw (this step's projections, row stride ld_kv) are normalised,
 // rotated (key) and appended to the caches at row t, scores over rows 0..t.  n_keys >= 0: cross-attention over n_keys
-// pre-normalised memory keys / values with the key-padding mask [B, n_keys] (1 = masked).  Caches: bf16, key j of
+// pre-normalised memory keys / values with the key-padding mask [B, n_keys] (1 = masked).  rotate_q != 0 (self-attention):
+// rotate the new query to position t like training does, instead of the reference decode's position 0.  Caches: bf16, key j of
 // utterance b at kc + b * cache_bs + j * cache_ld (+ head * 64).
 extern "C" int kr_dec_attn(const void* state, const void* q, long long ld_q, const void* k_raw, const void* v_raw,
                            long long ld_kv, const float* gq, const float* gk, const float* gv, const float* cos_t,
                            const float* sin_t, void* kc, void* vc, long long cache_ld, long long cache_bs, int n_keys,
-                           const unsigned char* mask, void* o, long long ld_o, int B, int H, float scale, void* stream) {
+                           const unsigned char* mask, void* o, long long ld_o, int B, int H, float scale, int rotate_q,
+                           void* stream) {
   if (B <= 0 || H <= 0) return KR_OK;
   if (n_keys < 0 && (k_raw == nullptr || v_raw == nullptr || cos_t == nullptr || sin_t == nullptr)) {
     kr_set_error("kr_dec_attn: self-attention needs the new key / value projections and the RoPE tables");
@@ -133,7 +135,7 @@ extern "C" int kr_dec_attn(const void* state, const void* q, long long ld_q, con
   }
   kr::launch(dec_attn_kernel, dim3(H, B), ATTN_THREADS, 0, (cudaStream_t)stream, (const krd::DecState*)state,
              (const bf16*)q, ld_q, (const bf16*)k_raw, (const bf16*)v_raw, ld_kv, gq, gk, gv, cos_t, sin_t, (bf16*)kc,
-             (bf16*)vc, cache_ld, cache_bs, n_keys, mask, (bf16*)o, ld_o, scale);
+             (bf16*)vc, cache_ld, cache_bs, n_keys, mask, (bf16*)o, ld_o, scale, rotate_q);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -111,13 +111,14 @@ KRD_DEV void dec_feed_body(const DecState* st, const float* frame, const float* 
 // outputs.  kc / vc: this (utterance, head)'s cache columns, key j at kc + j * ld.  append_at >= 0 (self-attention):
 // the new key / value are normalised, the key rotated to position append_at (cos_row / sin_row = that row of the RoPE
 // tables) and both stored at row append_at before the scores are taken over n_keys = append_at + 1 rows.
+// rotate_q != 0 (self-attention only): the query is rotated to position append_at as well instead of position 0.
 // mask (cross-attention): 1 = padded memory frame.  Shared memory: qs[64], wm[8], wl[8], wacc[8 * 64].
 // ------------------------------------------------------------------------------------------------------------------
 KRD_DEV void dec_attn_body(const krd_bf16* q_raw, const float* gq, const krd_bf16* k_raw, const float* gk,
                            const krd_bf16* v_raw, const float* gv, const float* cos_row, const float* sin_row,
                            krd_bf16* kc, krd_bf16* vc, long long ld, int n_keys, int append_at,
-                           const unsigned char* mask, float scale, float eps, float* qs, float* wm, float* wl,
-                           float* wacc, krd_bf16* o_out) {
+                           const unsigned char* mask, float scale, float eps, int rotate_q, float* qs, float* wm,
+                           float* wl, float* wacc, krd_bf16* o_out) {
   const int lane = KRD_LANE, warp = KRD_WARP, nw = KRD_NWARPS;
   constexpr int HALF = DK / 2;
   // phase A: the three per-head RMSNorms, each by one warp (the same warp when the block has fewer)
@@ -125,7 +126,17 @@ KRD_DEV void dec_attn_body(const krd_bf16* q_raw, const float* gq, const krd_bf1
     float ss = 0.f;
     for (int d = lane; d < DK; d += KRD_NLANES) { const float v = krd_b2f(q_raw[d]); ss += v * v; }
     const float r = rms_scale(krd_warp_sum(ss), eps);
-    for (int d = lane; d < DK; d += KRD_NLANES) qs[d] = krd_b2f(q_raw[d]) * r * gq[d];     // RoPE at position 0 = identity
+    if (rotate_q && append_at >= 0) {
+      // opt-in FIX of the reference's quirk: rotate the new query to its true position (what training does)
+      for (int d = lane; d < HALF; d += KRD_NLANES) {
+        const float a = krd_b2f(q_raw[d]) * r * gq[d], b = krd_b2f(q_raw[d + HALF]) * r * gq[d + HALF];
+        const float c = cos_row[d], s = sin_row[d];
+        qs[d] = a * c - b * s;
+        qs[d + HALF] = b * c + a * s;
+      }
+    } else {
+      for (int d = lane; d < DK; d += KRD_NLANES) qs[d] = krd_b2f(q_raw[d]) * r * gq[d];   // RoPE at position 0 = identity
+    }
   }
   if (append_at >= 0 && warp == 1 % nw) {
     float ss = 0.f;

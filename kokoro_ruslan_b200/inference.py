@@ -182,6 +182,9 @@ class CudaDecodeBackend:
             raise RuntimeError(f"DecState is {n} bytes in libkokoro_b200.so, {STATE_WORDS * 4} expected")
         import os
         self.use_gemv = os.environ.get("KR_DECODE_GEMV", "0") == "1"
+        # False = the reference's behaviour (new query rotated as position 0, transformers.py:276-277); True rotates it
+        # to its true position like the training forward does (an opt-in fix of that train / inference mismatch)
+        self.rotate_query = os.environ.get("KR_DECODE_ROPE_QUERY", "0") == "1"
         self.state_for_gemv = None        # DecodeLoop's state tensor once a loop is bound (lets the kernel skip after `done`)
 
     def zeros(self, shape, dtype):
@@ -258,7 +261,7 @@ class CudaDecodeBackend:
                                             o._ptr(self.st.rope_cos), o._ptr(self.st.rope_sin), o._ptr(kc), o._ptr(vc),
                                             c.c_longlong(kc.stride(1)), c.c_longlong(kc.stride(0)), c.c_int(n_keys),
                                             o._ptr(mask), o._ptr(out), c.c_longlong(out.stride(0)), c.c_int(B), c.c_int(H),
-                                            c.c_float(0.125), o._stream()), "kr_dec_attn")
+                                            c.c_float(0.125), c.c_int(int(self.rotate_query)), o._stream()), "kr_dec_attn")
 
     def dec_finish(self, state, y, ln_g, ln_b, w_out, b_out, w_stop, b_stop, mel_out, next_frame, probs, B, D, n_mels,
                    t_cap):

@@ -22,7 +22,7 @@ extern "C" int emu_dec_attn(const void* state, const uint16_t* q, long long ld_q
                             const uint16_t* v_raw, long long ld_kv, const float* gq, const float* gk, const float* gv,
                             const float* cos_t, const float* sin_t, uint16_t* kc, uint16_t* vc, long long cache_ld,
                             long long cache_bs, int n_keys, const unsigned char* mask, uint16_t* o, long long ld_o, int B,
-                            int H, float scale) {
+                            int H, float scale, int rotate_q) {
   const krd::DecState* st = (const krd::DecState*)state;
   if (st->done) return 0;
   float qs[krd::DK], wm[krd::MAX_WARPS], wl[krd::MAX_WARPS], wacc[krd::MAX_WARPS * krd::DK];
@@ -36,7 +36,7 @@ extern "C" int emu_dec_attn(const void* state, const uint16_t* q, long long ld_q
                          self ? cos_t + (long long)t * (krd::DK / 2) : nullptr,
                          self ? sin_t + (long long)t * (krd::DK / 2) : nullptr, kc + (long long)b * cache_bs + col,
                          vc + (long long)b * cache_bs + col, cache_ld, self ? t + 1 : n_keys, self ? t : -1,
-                         mask ? mask + (long long)b * n_keys : nullptr, scale, 1.1920929e-7f, qs, wm, wl, wacc,
+                         mask ? mask + (long long)b * n_keys : nullptr, scale, 1.1920929e-7f, rotate_q, qs, wm, wl, wacc,
                          o + (long long)b * ld_o + col);
     }
   return 0;

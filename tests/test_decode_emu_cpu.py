@@ -41,6 +41,7 @@ class EmuBackend:
         self.cos, self.sin = rope_tables(max_len, 64)
         self._w = {}
         self.launches = 0
+        self.rotate_query = False
 
     def zeros(self, shape, dtype):
         return torch.zeros(*shape, dtype=dtype)
@@ -101,7 +102,7 @@ class EmuBackend:
         assert self.lib.emu_dec_attn(_p(state), _p(q), ll(q.stride(0)), _p(k_raw), _p(v_raw),
                                      ll(0 if k_raw is None else k_raw.stride(0)), _p(gq), _p(gk), _p(gv), _p(self.cos),
                                      _p(self.sin), _p(kc), _p(vc), ll(kc.stride(1)), ll(kc.stride(0)), n_keys, _p(mask),
-                                     _p(out), ll(out.stride(0)), B, H, ctypes.c_float(0.125)) == 0
+                                     _p(out), ll(out.stride(0)), B, H, ctypes.c_float(0.125), int(self.rotate_query)) == 0
 
     def dec_finish(self, state, y, ln_g, ln_b, w_out, b_out, w_stop, b_stop, mel_out, next_frame, probs, B, D, n_mels,
                    t_cap):
@@ -291,3 +292,37 @@ def test_gemv_projection_variant_matches_the_gemm_path(emu):
     assert float((outs[1] - outs[0]).abs().max()) / float(want.abs().max()) < 1e-2
     print("fused / un-fused error vs oracle:", float((outs[1] - want).abs().max()), float((outs[0] - want).abs().max()))
     assert be.launches == (2 + 8 * cfg.n_decoder_layers) * (-(-n // 32) * 32)      # 8 decode-kernel launches per layer
+
+
+def test_query_rotation_fix_makes_decode_equal_the_causal_training_forward(emu):
+    """KR_DECODE_ROPE_QUERY=1 (rotate the new query to its true position): the teacher-forced KV-cache decode then equals
+    the TRAINING-style causal pass of the decoder over the same memory — the reference's decode (position 0) does not.
+    Isolates the quirk: same kernels, same cache, one flag."""
+    import torch.nn.functional as F
+    from oracle import acoustic as oa
+    from oracle import inference as oi
+    f, cfg, sd = _setup()
+    idx, stress = torch.from_numpy(f["idx"]), torch.from_numpy(f["stress"])
+    with torch.no_grad():
+        mem, mem_pad, _ = oi.encode_and_expand(sd, cfg, idx, stress)
+        n = 24
+        g = torch.Generator().manual_seed(1)
+        frames = torch.randn(1, n, cfg.mel_dim, generator=g) * 1.5 - 4.0                 # the "previous frames" fed in
+        shifted = F.pad(frames[:, :-1], (0, 0, 1, 0))                                      # teacher forcing: frame t sees t-1
+        y = shifted @ sd["mel_projection_in.weight"].t() + sd["mel_projection_in.bias"] + sd["positional_encoding.pe"][0, :n]
+        for i in range(cfg.n_decoder_layers):
+            y = oa.decoder_block(sd, f"decoder.layers.{i}.", cfg, y, mem, mem_pad)
+        y = oa._ln(sd, "decoder.norm.", y)
+        causal = (y @ sd["mel_projection_out.weight"].t() + sd["mel_projection_out.bias"]).clamp(-11.5, 2.0)
+    outs = {}
+    for rotate in (False, True):
+        loop, be, lo, hi, Tp = _loop(emu, sd, cfg, idx, stress)
+        be.rotate_query = rotate
+        forced = torch.zeros(1, hi, cfg.mel_dim)
+        forced[:, :n] = shifted
+        got, _ = loop.run(n, n + 1, Tp, forced=forced)                                     # exactly n + 1 frames
+        outs[rotate] = got[:, :n]
+    scale = float(causal.abs().max())
+    assert float((outs[True] - causal).abs().max()) / scale < 1e-2                         # fixed decode == training pass
+    assert float((outs[False][:, :1] - causal[:, :1]).abs().max()) / scale < 1e-2          # frame 0: position 0 either way
+    assert float((outs[False][:, 4:] - causal[:, 4:]).abs().max()) / scale > 3e-2          # the reference's mismatch

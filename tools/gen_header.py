@@ -29,7 +29,7 @@ DOCS = {
     "kr_energy_norm": "5 / 95-percentile normalisation of the per-frame energies to [0, 1] per utterance (min / max below 3 frames), variance_predictor.py:675-687; zeros beyond frames[b].",
     "kr_dec_state_size": "sizeof the device-resident generation state (krd::DecState in csrc/kr_decode_core.cuh: t, done, n_frames, lo, hi, expected, stop_thr, post_thr, ring[30]; 256 bytes; mirrored by kokoro_ruslan_b200/inference.py STATE_FIELDS).",
     "kr_dec_feed": "Decoder input of frame t of the autoregressive loop: mel_projection_in on the previous output frame + bias + PE row t (model/model.py:519-531 in eval mode, model/generator.py:52-57); t is read from the device state.",
-    "kr_dec_attn": "One decode-step attention per (utterance, head) with the KV cache of model/transformers.py:237-277: per-head RMSNorm of the new query (rotated as position 0 — the reference's q_offset = 0), and for self-attention RMSNorm + RoPE(position t) of the new key and RMSNorm of the new value appended to the bf16 caches, then softmax(q K^T * scale) V over the cached rows; cross-attention reads the pre-normalised memory keys / values with the key-padding mask.",
+    "kr_dec_attn": "One decode-step attention per (utterance, head) with the KV cache of model/transformers.py:237-277: per-head RMSNorm of the new query (rotated as position 0 — the reference's q_offset = 0), and for self-attention RMSNorm + RoPE(position t) of the new key and RMSNorm of the new value appended to the bf16 caches, then softmax(q K^T * scale) V over the cached rows; cross-attention reads the pre-normalised memory keys / values with the key-padding mask. rotate_q = 1 rotates the query to position t instead (opt-in fix of that train / inference mismatch).",
     "kr_dec_finish": "End of a decode step: decoder.norm + mel_projection_out + stop head (model/model.py:547-563) and the generator's stop rules on the device (model/generator.py:58-103: min / max length, stop probability mean over the batch against the pre / post-expected-length thresholds, 30-frame silence rule); stores the clamped frame, the un-clamped feedback frame and the stop probability, advances t.",
     "kr_val_metrics_acc_floats": "Length (floats) of the validation-metrics accumulator of kr_val_metrics.",
     "kr_val_metrics": "Validation metrics of KokoroTrainer.validate_epoch as device reductions, training/trainer.py:1868-1916: per utterance ||mel - pred||_F / ||mel||_F over its valid frames (spectral convergence) and sqrt(mean((pitch - pred)^2)) (frame-level F0 RMSE); the batch means of the valid utterances are added to epoch accumulators by the last block to finish. Replaces a Python loop with four .item() syncs per utterance.",
