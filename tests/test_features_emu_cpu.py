@@ -173,3 +173,18 @@ def test_trailing_trim_matches_reference_rule(emu):
         assert emu.emu_trim_end(_p(e), None, _p(t_end), 1, T) == 0
         assert int(t_end[0]) == _reference_trim_end(mel), (T, int(t_end[0]), _reference_trim_end(mel))
     assert _reference_trim_end(cases[0]) == 180 + 24 and _reference_trim_end(cases[3]) == 40
+
+
+def test_edge_inputs_match_live_reference(emu):
+    """Silence, DC, one sample, noise, an impulse, tones at both ends of the pitch range; energy on 1-5 frames."""
+    from oracle import features as of
+    f = np.load(os.path.join(HERE, "golden", "features_edge.npz"))
+    for k in ("zeros", "dc", "n1", "noise", "impulse", "tone60", "tone790"):
+        got, want = emu_pitch(emu, f[f"wav_{k}"])[0], f[f"pitch_{k}"]
+        assert got.shape == want.shape and not np.isnan(got).any(), k
+        assert np.abs(got - want).max() < 1e-5, (k, np.abs(got - want).max())
+        assert np.abs(of.extract_pitch(f[f"wav_{k}"]) - want).max() < 1e-5, k           # the oracle on the same inputs
+    assert (f["pitch_tone60"] > 0).all() and (f["pitch_noise"] == 0).all()
+    for T in (1, 2, 3, 5):
+        got = emu_energy(emu, f[f"mel_{T}"][None], log_domain=True)[0]
+        assert np.abs(got - f[f"energy_{T}"]).max() < 1e-6, T
