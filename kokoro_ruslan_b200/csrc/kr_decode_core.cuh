@@ -43,6 +43,7 @@ KRD_DEV float krd_warp_sum(float v) { return v; }
 KRD_DEV float krd_block_sum(float v, float*) { return v; }
 KRD_DEV float krd_rsqrt(float x) { return 1.f / sqrtf(x); }
 KRD_DEV void krd_load8(const krd_bf16* p, float* v) { for (int i = 0; i < 8; ++i) v[i] = krd_b2f(p[i]); }
+template <int N> KRD_DEV void krd_loadn(const krd_bf16* p, float* v) { for (int i = 0; i < N; ++i) v[i] = krd_b2f(p[i]); }
 #else
 #define KRD_DEV __device__ __forceinline__
 #define KRD_TID ((int)threadIdx.x)
@@ -66,6 +67,13 @@ KRD_DEV void krd_load8(const krd_bf16* p, float* v) {          // one 16-byte lo
     v[2 * i] = __uint_as_float(w[i] << 16);
     v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
+}
+// N consecutive bf16; the decode attention uses N = 2: one 4-byte load per lane, 128 contiguous bytes per warp and key
+template <int N> KRD_DEV void krd_loadn(const krd_bf16* p, float* v) {
+  static_assert(N == 2, "a lane owns two consecutive head dimensions");
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+  v[0] = __uint_as_float(u << 16);
+  v[1] = __uint_as_float(u & 0xffff0000u);
 }
 #endif
 
@@ -157,24 +165,26 @@ KRD_DEV void dec_attn_body(const krd_bf16* q_raw, const float* gq, const krd_bf1
   }
   KRD_SYNC();
   // phase B: every warp takes keys warp, warp + nw, ... with an online softmax; a lane owns DK / NLANES output dims
-  constexpr int PER = DK / KRD_NLANES;
-  float m = NEG_INF, l = 0.f, acc[PER];
-  for (int i = 0; i < PER; ++i) acc[i] = 0.f;
+  constexpr int PER = DK / KRD_NLANES;                     // consecutive dims lane * PER .. lane * PER + PER - 1
+  const int d0 = lane * PER;
+  float m = NEG_INF, l = 0.f, acc[PER], qv[PER];
+  for (int i = 0; i < PER; ++i) { acc[i] = 0.f; qv[i] = qs[d0 + i]; }
   for (int j = warp; j < n_keys; j += nw) {
     if (mask != nullptr && mask[j]) continue;
-    const krd_bf16* krow = kc + (long long)j * ld;
-    const krd_bf16* vrow = vc + (long long)j * ld;
+    float kv[PER], vv[PER];
+    krd_loadn<PER>(kc + (long long)j * ld + d0, kv);
+    krd_loadn<PER>(vc + (long long)j * ld + d0, vv);
     float dot = 0.f;
-    for (int i = 0; i < PER; ++i) { const int d = lane + i * KRD_NLANES; dot += qs[d] * krd_b2f(krow[d]); }
+    for (int i = 0; i < PER; ++i) dot += qv[i] * kv[i];
     const float s = krd_warp_sum(dot) * scale;
     const float m_new = fmaxf(m, s);
     const float corr = expf(m - m_new), p = expf(s - m_new);
     l = l * corr + p;
-    for (int i = 0; i < PER; ++i) { const int d = lane + i * KRD_NLANES; acc[i] = acc[i] * corr + p * krd_b2f(vrow[d]); }
+    for (int i = 0; i < PER; ++i) acc[i] = acc[i] * corr + p * vv[i];
     m = m_new;
   }
   if (lane == 0) { wm[warp] = m; wl[warp] = l; }
-  for (int i = 0; i < PER; ++i) wacc[warp * DK + lane + i * KRD_NLANES] = acc[i];
+  for (int i = 0; i < PER; ++i) wacc[warp * DK + d0 + i] = acc[i];
   KRD_SYNC();
   // phase C: merge the warps' partial softmaxes
   for (int d = KRD_TID; d < DK; d += KRD_NT) {
