@@ -24,6 +24,18 @@
 #include <stdint.h>
 #include <string.h>
 #define KRD_DEV static inline
+#ifdef KR_HOST_EMU_SIMT            // one host thread per CUDA thread, real block / warp geometry (tests/emu/emu_simt.h)
+#include "emu_simt.h"
+#define KRD_TID (emu::tid())
+#define KRD_NT (emu::nthreads())
+#define KRD_LANE (emu::tid() & 31)
+#define KRD_NLANES 32
+#define KRD_WARP (emu::tid() >> 5)
+#define KRD_NWARPS (emu::nthreads() >> 5)
+#define KRD_SYNC() emu::syncthreads()
+KRD_DEV float krd_warp_sum(float v) { return emu::warp_sum(v); }
+KRD_DEV float krd_block_sum(float v, float* red) { return emu::block_sum(v, red); }
+#else                              // one sequential "thread" per block
 #define KRD_TID 0
 #define KRD_NT 1
 #define KRD_LANE 0
@@ -31,6 +43,9 @@
 #define KRD_WARP 0
 #define KRD_NWARPS 1
 #define KRD_SYNC() do { } while (0)
+KRD_DEV float krd_warp_sum(float v) { return v; }
+KRD_DEV float krd_block_sum(float v, float*) { return v; }
+#endif
 typedef uint16_t krd_bf16;
 KRD_DEV float krd_b2f(krd_bf16 v) { uint32_t u = (uint32_t)v << 16; float f; memcpy(&f, &u, 4); return f; }
 KRD_DEV krd_bf16 krd_f2b(float f) {                    // round to nearest even, like __float2bfloat16_rn
@@ -39,8 +54,6 @@ KRD_DEV krd_bf16 krd_f2b(float f) {                    // round to nearest even,
   u += 0x7fffu + ((u >> 16) & 1u);
   return (krd_bf16)(u >> 16);
 }
-KRD_DEV float krd_warp_sum(float v) { return v; }
-KRD_DEV float krd_block_sum(float v, float*) { return v; }
 KRD_DEV float krd_rsqrt(float x) { return 1.f / sqrtf(x); }
 KRD_DEV void krd_load8(const krd_bf16* p, float* v) { for (int i = 0; i < 8; ++i) v[i] = krd_b2f(p[i]); }
 template <int N> KRD_DEV void krd_loadn(const krd_bf16* p, float* v) { for (int i = 0; i < N; ++i) v[i] = krd_b2f(p[i]); }

@@ -17,6 +17,24 @@
 #include <stdint.h>
 #define KRF_DEV static inline
 #define KRF_HD static inline
+#ifdef KR_HOST_EMU_SIMT            // one host thread per CUDA thread, real block / warp geometry (tests/emu/emu_simt.h)
+#include "emu_simt.h"
+#define KRF_TID (emu::tid())
+#define KRF_NT (emu::nthreads())
+#define KRF_LANE (emu::tid() & 31)
+#define KRF_NLANES 32
+#define KRF_WARP (emu::tid() >> 5)
+#define KRF_NWARPS (emu::nthreads() >> 5)
+#define KRF_SYNC() emu::syncthreads()
+#define KRF_WARP_SYNC() do { } while (0)
+KRF_DEV float krf_warp_sum(float v) { return emu::warp_sum(v); }
+KRF_DEV float krf_warp_min(float v) { return emu::warp_min(v); }
+KRF_DEV float krf_warp_max(float v) { return emu::warp_max(v); }
+KRF_DEV int krf_warp_min_int(int v) { return emu::warp_min_int(v); }
+KRF_DEV float krf_block_sum(float v, float* red) { return emu::block_sum(v, red); }
+KRF_DEV float krf_block_max(float v, float* red) { return emu::block_max(v, red); }
+KRF_DEV int krf_block_sum_int(int v, int* red) { return emu::block_sum_int(v, red); }
+#else                              // one sequential "thread" per block
 #define KRF_TID 0
 #define KRF_NT 1
 #define KRF_LANE 0
@@ -25,8 +43,6 @@
 #define KRF_NWARPS 1
 #define KRF_SYNC() do { } while (0)
 #define KRF_WARP_SYNC() do { } while (0)
-struct krf_float2 { float x, y; };
-KRF_DEV krf_float2 krf_make2(float x, float y) { krf_float2 r; r.x = x; r.y = y; return r; }
 KRF_DEV float krf_warp_sum(float v) { return v; }
 KRF_DEV float krf_warp_min(float v) { return v; }
 KRF_DEV float krf_warp_max(float v) { return v; }
@@ -34,6 +50,9 @@ KRF_DEV int krf_warp_min_int(int v) { return v; }
 KRF_DEV float krf_block_sum(float v, float*) { return v; }
 KRF_DEV float krf_block_max(float v, float*) { return v; }
 KRF_DEV int krf_block_sum_int(int v, int*) { return v; }
+#endif
+struct krf_float2 { float x, y; };
+KRF_DEV krf_float2 krf_make2(float x, float y) { krf_float2 r; r.x = x; r.y = y; return r; }
 KRF_DEV void krf_sincospi(float x, float* s, float* c) { const double a = M_PI * (double)x; *s = (float)sin(a); *c = (float)cos(a); }
 KRF_DEV float krf_cospi(float x) { return (float)cos(M_PI * (double)x); }
 KRF_DEV float krf_mul(float a, float b) { volatile float r = a * b; return r; }      // no FMA contraction

@@ -12,9 +12,16 @@
 
 #ifdef KR_HOST_EMU
 #define KRL_DEV static inline
+#ifdef KR_HOST_EMU_SIMT            // one host thread per CUDA thread (tests/emu/emu_simt.h)
+#include "emu_simt.h"
+#define KRL_TID (emu::tid())
+#define KRL_NT (emu::nthreads())
+#define KRL_SYNC() emu::syncthreads()
+#else
 #define KRL_TID 0
 #define KRL_NT 1
 #define KRL_SYNC() do { } while (0)
+#endif
 #else
 #define KRL_DEV __device__ __forceinline__
 #define KRL_TID ((int)threadIdx.x)

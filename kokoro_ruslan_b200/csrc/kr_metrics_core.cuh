@@ -11,9 +11,16 @@
 #ifdef KR_HOST_EMU
 #include <math.h>
 #define KRM_DEV static inline
+#ifdef KR_HOST_EMU_SIMT            // one host thread per CUDA thread (tests/emu/emu_simt.h)
+#include "emu_simt.h"
+#define KRM_TID (emu::tid())
+#define KRM_NT (emu::nthreads())
+KRM_DEV float krm_block_sum(float v, float* red) { return emu::block_sum(v, red); }
+#else
 #define KRM_TID 0
 #define KRM_NT 1
 KRM_DEV float krm_block_sum(float v, float*) { return v; }
+#endif
 KRM_DEV unsigned krm_arrive(unsigned* counter) { return (*counter)++; }      // blocks run in order: the last one folds
 #else
 #define KRM_DEV __device__ __forceinline__

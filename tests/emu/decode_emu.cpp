@@ -5,6 +5,22 @@
 #include "kr_decode_core.cuh"
 #include <vector>
 
+// Block execution: one sequential "thread" (default) or, with -DKR_HOST_EMU_SIMT, the real block size on a pool of host
+// threads (tests/emu/emu_simt.h).  EMU_BLOCK(n, stmt) runs `stmt` as one thread block of n threads.
+#ifdef KR_HOST_EMU_SIMT
+#include <map>
+#include <memory>
+static emu::Pool& emu_pool(int n) {
+  static std::map<int, std::unique_ptr<emu::Pool>> pools;
+  auto& p = pools[n];
+  if (!p) p.reset(new emu::Pool(n));
+  return *p;
+}
+#define EMU_BLOCK(n, stmt) emu_pool(n).run([&] { stmt; })
+#else
+#define EMU_BLOCK(n, stmt) do { stmt; } while (0)
+#endif
+
 extern "C" int emu_dec_state_size(void) { return (int)sizeof(krd::DecState); }
 
 extern "C" int emu_dec_feed(const void* state, const float* prev, const float* forced, int forced_T, const float* w_in,
@@ -13,7 +29,7 @@ extern "C" int emu_dec_feed(const void* state, const float* prev, const float* f
   if (st->done) return 0;
   for (int b = 0; b < B; ++b) {
     const float* frame = forced ? forced + ((long long)b * forced_T + st->t) * n_mels : prev + (long long)b * n_mels;
-    krd::dec_feed_body(st, frame, w_in, b_in, pe, D, n_mels, x + (long long)b * D);
+    EMU_BLOCK(256, krd::dec_feed_body(st, frame, w_in, b_in, pe, D, n_mels, x + (long long)b * D));
   }
   return 0;
 }
@@ -31,13 +47,13 @@ extern "C" int emu_dec_attn(const void* state, const uint16_t* q, long long ld_q
   for (int b = 0; b < B; ++b)
     for (int h = 0; h < H; ++h) {
       const int col = h * krd::DK;
-      krd::dec_attn_body(q + (long long)b * ld_q + col, gq, self ? k_raw + (long long)b * ld_kv + col : nullptr, gk,
+      EMU_BLOCK(128, krd::dec_attn_body(q + (long long)b * ld_q + col, gq, self ? k_raw + (long long)b * ld_kv + col : nullptr, gk,
                          self ? v_raw + (long long)b * ld_kv + col : nullptr, gv,
                          self ? cos_t + (long long)t * (krd::DK / 2) : nullptr,
                          self ? sin_t + (long long)t * (krd::DK / 2) : nullptr, kc + (long long)b * cache_bs + col,
                          vc + (long long)b * cache_bs + col, cache_ld, self ? t + 1 : n_keys, self ? t : -1,
                          mask ? mask + (long long)b * n_keys : nullptr, scale, 1.1920929e-7f, rotate_q, qs, wm, wl, wacc,
-                         o + (long long)b * ld_o + col);
+                         o + (long long)b * ld_o + col));
     }
   return 0;
 }
@@ -47,8 +63,8 @@ extern "C" int emu_dec_finish(void* state, const float* y, const float* ln_g, co
                               float* next_frame, float* probs, int B, int D, int n_mels, int t_cap) {
   if (B > krd::MAX_B || n_mels > 128) return -4;
   std::vector<float> stats(2 * krd::MAX_B), vals(krd::MAX_B * 129), red(32);
-  krd::dec_finish_body((krd::DecState*)state, y, ln_g, ln_b, w_out, b_out, w_stop, b_stop, B, D, n_mels, t_cap,
-                       stats.data(), vals.data(), red.data(), mel_out, next_frame, probs);
+  EMU_BLOCK(256, krd::dec_finish_body((krd::DecState*)state, y, ln_g, ln_b, w_out, b_out, w_stop, b_stop, B, D, n_mels, t_cap,
+                                      stats.data(), vals.data(), red.data(), mel_out, next_frame, probs));
   return 0;
 }
 
@@ -59,7 +75,15 @@ extern "C" int emu_dec_gemv(const void* state, const uint16_t* x, const float* x
   if ((x == nullptr) == (x_f32 == nullptr) || (glu && (resid != nullptr || out_f32))) return -1;
   if (state && ((const krd::DecState*)state)->done) return 0;
   std::vector<uint16_t> xs((size_t)B * K);
+#ifdef KR_HOST_EMU_SIMT
+  // like the launch wrapper: blocks of 8 warps, block i starts at feature 8 i, stride = blocks * 8
+  const int blocks = (N + 7) / 8 < 4 ? (N + 7) / 8 : 4;
+  for (int blk = 0; blk < blocks; ++blk)
+    EMU_BLOCK(256, krd::dec_gemv_body(x, x_f32, ld_x, ln_g, ln_b, w, bias, resid, ld_r, out, ld_o, out_f32, glu, B, N, K,
+                                      blk * 8, blocks * 8, xs.data()));
+#else
   // the launch wrapper runs `blocks` blocks of 8 warps; one emulated block with n_step = 1 covers every feature once
   krd::dec_gemv_body(x, x_f32, ld_x, ln_g, ln_b, w, bias, resid, ld_r, out, ld_o, out_f32, glu, B, N, K, 0, 1, xs.data());
+#endif
   return 0;
 }

@@ -5,6 +5,22 @@
 #include "kr_features_core.cuh"
 #include <vector>
 
+// Block execution: one sequential "thread" (default) or, with -DKR_HOST_EMU_SIMT, the real block size on a pool of host
+// threads (tests/emu/emu_simt.h).  EMU_BLOCK(n, stmt) runs `stmt` as one thread block of n threads.
+#ifdef KR_HOST_EMU_SIMT
+#include <map>
+#include <memory>
+static emu::Pool& emu_pool(int n) {
+  static std::map<int, std::unique_ptr<emu::Pool>> pools;
+  auto& p = pools[n];
+  if (!p) p.reset(new emu::Pool(n));
+  return *p;
+}
+#define EMU_BLOCK(n, stmt) emu_pool(n).run([&] { stmt; })
+#else
+#define EMU_BLOCK(n, stmt) do { stmt; } while (0)
+#endif
+
 extern "C" int emu_pitch_num_frames(long long n) { return krf::pitch_num_frames(n); }
 
 extern "C" int emu_pitch_frames(const float* wav, const long long* lengths, float* cand, float* acmax, float* energy,
@@ -18,8 +34,8 @@ extern "C" int emu_pitch_frames(const float* wav, const long long* lengths, floa
     for (int f = 0; f < frames_max; ++f) {
       if (f >= krf::pitch_num_frames(n)) continue;
       const long long o = (long long)b * frames_max + f;
-      krf::pitch_frame_body(wav + (long long)b * n_max, n, f, lag_min, lag_max, (float)sample_rate, z.data(), tw.data(),
-                            cm.data(), red.data(), cand + o, acmax + o, energy + o);
+      EMU_BLOCK(512, krf::pitch_frame_body(wav + (long long)b * n_max, n, f, lag_min, lag_max, (float)sample_rate, z.data(),
+                                           tw.data(), cm.data(), red.data(), cand + o, acmax + o, energy + o));
     }
   }
   return 0;
@@ -33,7 +49,7 @@ extern "C" int emu_pitch_track(const float* cand, const float* acmax, const floa
     int T = krf::pitch_num_frames(n);
     T = T < frames_max ? T : frames_max;
     const long long o = (long long)b * frames_max;
-    krf::pitch_track_body(cand + o, acmax + o, energy + o, T, frames_max, fmin, fmax, work + o, sel, out + o);
+    EMU_BLOCK(256, krf::pitch_track_body(cand + o, acmax + o, energy + o, T, frames_max, fmin, fmax, work + o, sel, out + o));
   }
   return 0;
 }
@@ -57,7 +73,7 @@ extern "C" int emu_energy_norm(const float* e, const long long* frames, float* o
   for (int b = 0; b < B; ++b) {
     long long T = frames ? frames[b] : T_max;
     T = T < 0 ? 0 : (T < T_max ? T : T_max);
-    krf::energy_norm_body(e + (long long)b * T_max, (int)T, T_max, sel, red, out + (long long)b * T_max);
+    EMU_BLOCK(256, krf::energy_norm_body(e + (long long)b * T_max, (int)T, T_max, sel, red, out + (long long)b * T_max));
   }
   return 0;
 }
@@ -76,8 +92,8 @@ extern "C" int emu_mel_stft_r4(const float* wav, const long long* lengths, const
         for (int m = 0; m < n_mels; ++m) orow[(long long)m * frames_max] = 0.f;
         continue;
       }
-      krf::mel_frame_body(wav + (long long)b * n_max, n, f, gain, fb_t, n_mels, frames_max, log_eps, z.data(), qw.data(),
-                          pw.data(), orow);
+      EMU_BLOCK(256, krf::mel_frame_body(wav + (long long)b * n_max, n, f, gain, fb_t, n_mels, frames_max, log_eps, z.data(),
+                                         qw.data(), pw.data(), orow));
     }
   }
   return 0;
@@ -88,7 +104,7 @@ extern "C" int emu_trim_end(const float* e, const long long* frames, int* t_end,
   for (int b = 0; b < B; ++b) {
     long long T = frames ? frames[b] : T_max;
     T = T < 0 ? 0 : (T < T_max ? T : T_max);
-    krf::trim_end_body(e + (long long)b * T_max, (int)T, sel, red, t_end + b);
+    EMU_BLOCK(256, krf::trim_end_body(e + (long long)b * T_max, (int)T, sel, red, t_end + b));
   }
   return 0;
 }

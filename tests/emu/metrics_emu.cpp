@@ -3,6 +3,22 @@
 #define KR_HOST_EMU 1
 #include "kr_metrics_core.cuh"
 
+// Block execution: one sequential "thread" (default) or, with -DKR_HOST_EMU_SIMT, the real block size on a pool of host
+// threads (tests/emu/emu_simt.h).  EMU_BLOCK(n, stmt) runs `stmt` as one thread block of n threads.
+#ifdef KR_HOST_EMU_SIMT
+#include <map>
+#include <memory>
+static emu::Pool& emu_pool(int n) {
+  static std::map<int, std::unique_ptr<emu::Pool>> pools;
+  auto& p = pools[n];
+  if (!p) p.reset(new emu::Pool(n));
+  return *p;
+}
+#define EMU_BLOCK(n, stmt) emu_pool(n).run([&] { stmt; })
+#else
+#define EMU_BLOCK(n, stmt) do { stmt; } while (0)
+#endif
+
 extern "C" int emu_val_metrics_acc_floats(void) { return krm::ACC_FLOATS; }
 
 extern "C" int emu_val_metrics(const float* mel_pred, const float* mel_tgt, const float* pitch_pred, const float* pitch_tgt,
@@ -11,9 +27,9 @@ extern "C" int emu_val_metrics(const float* mel_pred, const float* mel_tgt, cons
   float red[32];
   for (int b = 0; b < B; ++b) {
     const long long o = (long long)b * T * C;
-    krm::utterance_metrics(mel_pred + o, mel_tgt + o, pitch_pred ? pitch_pred + (long long)b * Tp : nullptr,
-                           pitch_tgt ? pitch_tgt + (long long)b * T : nullptr, mel_lengths[b], T, Tp, C, red,
-                           acc + krm::ACC_HEAD + 2 * b);
+    EMU_BLOCK(512, krm::utterance_metrics(mel_pred + o, mel_tgt + o, pitch_pred ? pitch_pred + (long long)b * Tp : nullptr,
+                                          pitch_tgt ? pitch_tgt + (long long)b * T : nullptr, mel_lengths[b], T, Tp, C, red,
+                                          acc + krm::ACC_HEAD + 2 * b));
     const unsigned ticket = krm_arrive(reinterpret_cast<unsigned*>(acc + 4));
     if (ticket == (unsigned)(B - 1)) {
       krm::fold_batch(acc, B);

@@ -12,12 +12,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    so = tmp_path_factory.mktemp("emu") / "metrics_emu.so"
-    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-I", os.path.join(ROOT, "kokoro_ruslan_b200", "csrc"),
-                    os.path.join(HERE, "emu", "metrics_emu.cpp"), "-o", str(so)], check=True)
-    return ctypes.CDLL(str(so))
+@pytest.fixture(scope="module", params=["seq", "simt"])
+def emu(request, tmp_path_factory):
+    """The kernels' bodies as a host library: "seq" = one sequential thread per block; "simt" = one host thread per CUDA
+    thread with the real block / warp geometry, barriers and warp reductions (tests/emu/emu_simt.h)."""
+    simt = request.param == "simt"
+    so = tmp_path_factory.mktemp("emu") / ("metrics_emu_%s.so" % request.param)
+    flags = ["-DKR_HOST_EMU_SIMT", "-pthread", "-I", os.path.join(HERE, "emu")] if simt else []
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", *flags, "-x", "c++", "-I",
+                    os.path.join(ROOT, "kokoro_ruslan_b200", "csrc"), os.path.join(HERE, "emu", "metrics_emu.cpp"), "-o", str(so)],
+                   check=True)
+    lib = ctypes.CDLL(str(so))
+    lib.simt = simt
+    return lib
 
 
 def reference_loop(batches):
