@@ -34,6 +34,8 @@
 #define KRD_NWARPS (emu::nthreads() >> 5)
 #define KRD_SYNC() emu::syncthreads()
 KRD_DEV float krd_warp_sum(float v) { return emu::warp_sum(v); }
+KRD_DEV float krd_warp_max(float v) { return emu::warp_max(v); }
+KRD_DEV void krd_warp_sum_vec64(float* v) { emu::warp_sum_vec(v, 64); }
 KRD_DEV float krd_block_sum(float v, float* red) { return emu::block_sum(v, red); }
 #else                              // one sequential "thread" per block
 #define KRD_TID 0
@@ -44,6 +46,8 @@ KRD_DEV float krd_block_sum(float v, float* red) { return emu::block_sum(v, red)
 #define KRD_NWARPS 1
 #define KRD_SYNC() do { } while (0)
 KRD_DEV float krd_warp_sum(float v) { return v; }
+KRD_DEV float krd_warp_max(float v) { return v; }
+KRD_DEV void krd_warp_sum_vec64(float*) { }
 KRD_DEV float krd_block_sum(float v, float*) { return v; }
 #endif
 typedef uint16_t krd_bf16;
@@ -70,6 +74,11 @@ typedef __nv_bfloat16 krd_bf16;
 KRD_DEV float krd_b2f(krd_bf16 v) { return __bfloat162float(v); }
 KRD_DEV krd_bf16 krd_f2b(float f) { return __float2bfloat16_rn(f); }
 KRD_DEV float krd_warp_sum(float v) { return kr::warp_sum(v); }
+KRD_DEV float krd_warp_max(float v) { return kr::warp_max(v); }
+KRD_DEV void krd_warp_sum_vec64(float* v) {                     // 64 butterfly reductions; every lane gets every sum
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = kr::warp_sum(v[i]);
+}
 KRD_DEV float krd_block_sum(float v, float* red) { return kr::block_sum(v, red); }
 KRD_DEV float krd_rsqrt(float x) { return rsqrtf(x); }
 KRD_DEV void krd_load8(const krd_bf16* p, float* v) {          // one 16-byte load of 8 bf16 (p is 16-byte aligned)
@@ -177,27 +186,63 @@ KRD_DEV void dec_attn_body(const krd_bf16* q_raw, const float* gq, const krd_bf1
     for (int d = lane; d < DK; d += KRD_NLANES) vc[(long long)append_at * ld + d] = krd_f2b(krd_b2f(v_raw[d]) * r * gv[d]);
   }
   KRD_SYNC();
-  // phase B: every warp takes keys warp, warp + nw, ... with an online softmax; a lane owns DK / NLANES output dims
-  constexpr int PER = DK / KRD_NLANES;                     // consecutive dims lane * PER .. lane * PER + PER - 1
-  const int d0 = lane * PER;
-  float m = NEG_INF, l = 0.f, acc[PER], qv[PER];
-  for (int i = 0; i < PER; ++i) { acc[i] = 0.f; qv[i] = qs[d0 + i]; }
-  for (int j = warp; j < n_keys; j += nw) {
+  // phase B: ONE KEY PER LANE.  Lane l of warp w takes keys w * 32 + l, + 32 * nw, ...: it reads its key / value rows
+  // with 16-byte loads (8 per row), the query from shared memory (broadcast), and keeps a private online softmax
+  // (m, l, acc[64]) — no cross-lane traffic and no dependent shuffle chain inside the loop, which is what bounds a
+  // one-key-per-warp formulation at long contexts.  The 32 partial softmaxes of a warp are merged once at the end.
+  float m = NEG_INF, l = 0.f, acc[DK];
+#ifndef KR_HOST_EMU
+#pragma unroll
+#endif
+  for (int d = 0; d < DK; ++d) acc[d] = 0.f;
+  for (int j = warp * KRD_NLANES + lane; j < n_keys; j += nw * KRD_NLANES) {
     if (mask != nullptr && mask[j]) continue;
-    float kv[PER], vv[PER];
-    krd_loadn<PER>(kc + (long long)j * ld + d0, kv);
-    krd_loadn<PER>(vc + (long long)j * ld + d0, vv);
+    const krd_bf16* krow = kc + (long long)j * ld;
+    const krd_bf16* vrow = vc + (long long)j * ld;
     float dot = 0.f;
-    for (int i = 0; i < PER; ++i) dot += qv[i] * kv[i];
-    const float s = krd_warp_sum(dot) * scale;
+#ifndef KR_HOST_EMU
+#pragma unroll
+#endif
+    for (int c = 0; c < DK / 8; ++c) {
+      float kv[8];
+      krd_load8(krow + c * 8, kv);
+#ifndef KR_HOST_EMU
+#pragma unroll
+#endif
+      for (int i = 0; i < 8; ++i) dot += qs[c * 8 + i] * kv[i];
+    }
+    const float s = dot * scale;
     const float m_new = fmaxf(m, s);
     const float corr = expf(m - m_new), p = expf(s - m_new);
     l = l * corr + p;
-    for (int i = 0; i < PER; ++i) acc[i] = acc[i] * corr + p * vv[i];
+#ifndef KR_HOST_EMU
+#pragma unroll
+#endif
+    for (int c = 0; c < DK / 8; ++c) {
+      float vv[8];
+      krd_load8(vrow + c * 8, vv);
+#ifndef KR_HOST_EMU
+#pragma unroll
+#endif
+      for (int i = 0; i < 8; ++i) acc[c * 8 + i] = acc[c * 8 + i] * corr + p * vv[i];
+    }
     m = m_new;
   }
-  if (lane == 0) { wm[warp] = m; wl[warp] = l; }
-  for (int i = 0; i < PER; ++i) wacc[warp * DK + d0 + i] = acc[i];
+  // merge the lanes of this warp (all 32 lanes take part: the loop above has no early exit, only skipped iterations)
+  const float m_w = krd_warp_max(m);
+  const float f = l > 0.f ? expf(m - m_w) : 0.f;
+  const float l_w = krd_warp_sum(l * f);
+#ifndef KR_HOST_EMU
+#pragma unroll
+#endif
+  for (int d = 0; d < DK; ++d) acc[d] *= f;
+  krd_warp_sum_vec64(acc);
+#ifndef KR_HOST_EMU
+#pragma unroll
+#endif
+  for (int d = 0; d < DK; ++d)
+    if ((d % KRD_NLANES) == lane) wacc[warp * DK + d] = acc[d];
+  if (lane == 0) { wm[warp] = m_w; wl[warp] = l_w; }
   KRD_SYNC();
   // phase C: merge the warps' partial softmaxes
   for (int d = KRD_TID; d < DK; d += KRD_NT) {

@@ -24,8 +24,10 @@ struct Block {
   std::vector<pthread_barrier_t> warp_bar;
   std::vector<float> wf;       // [warps][32]
   std::vector<int> wi;
+  std::vector<float> wv;       // [warps][32][kVec]: vector reductions
 };
 
+constexpr int kVec = 64;
 inline thread_local int t_tid = 0;
 inline thread_local Block* t_blk = nullptr;
 
@@ -49,6 +51,21 @@ inline float warp_max(float v) { return warp_reduce(v, t_blk->wf, [](float a, fl
 inline float warp_min(float v) { return warp_reduce(v, t_blk->wf, [](float a, float b) { return a < b ? a : b; }); }
 inline int warp_min_int(int v) { return warp_reduce(v, t_blk->wi, [](int a, int b) { return a < b ? a : b; }); }
 inline int warp_sum_int(int v) { return warp_reduce(v, t_blk->wi, [](int a, int b) { return a + b; }); }
+
+// element-wise sum of n <= kVec values per lane across the warp (one exchange instead of n)
+inline void warp_sum_vec(float* v, int n) {
+  Block* b = t_blk;
+  const int w = t_tid >> 5, l = t_tid & 31;
+  float* buf = b->wv.data() + (size_t)w * 32 * kVec;
+  for (int i = 0; i < n; ++i) buf[l * kVec + i] = v[i];
+  pthread_barrier_wait(&b->warp_bar[w]);
+  for (int i = 0; i < n; ++i) {
+    float s = 0.f;
+    for (int k = 0; k < 32; ++k) s += buf[k * kVec + i];
+    v[i] = s;
+  }
+  pthread_barrier_wait(&b->warp_bar[w]);
+}
 
 // the device's kr::block_sum pattern (kr_common.cuh): warp reduce, one value per warp through shared memory, reduce again
 template <class T, class WR>
@@ -79,6 +96,7 @@ class Pool {
     }
     blk_.wf.assign(nw * 32, 0.f);
     blk_.wi.assign(nw * 32, 0);
+    blk_.wv.assign((size_t)nw * 32 * kVec, 0.f);
     pthread_barrier_init(&gate_, nullptr, nthreads + 1);
     for (int t = 0; t < nthreads; ++t) threads_.emplace_back([this, t] { loop(t); });
   }

@@ -42,9 +42,9 @@ def test_a_removed_barrier_is_reported(tmp_path):
             shutil.copy(os.path.join(CSRC, f), broken / f)
     p = broken / "kr_decode_core.cuh"
     s = p.read_text()
-    needle = "  KRD_SYNC();\n  // phase B: every warp takes keys"
+    needle = "  KRD_SYNC();\n  // phase B: ONE KEY PER LANE"
     assert needle in s
-    p.write_text(s.replace(needle, "  // phase B: every warp takes keys", 1))
+    p.write_text(s.replace(needle, "  // phase B: ONE KEY PER LANE", 1))
     exe = tmp_path / "tsan_broken"
     _build(str(broken), exe)
     r = subprocess.run([str(exe)], capture_output=True, text=True, env=ENV, timeout=300)
