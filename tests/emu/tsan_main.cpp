@@ -40,6 +40,8 @@ int main() {
   for (auto& v : mel) v = -6.f + 3.f * frand();
   emu_energy_frames(mel.data(), e.data(), 1, 40, 80, 1, 0, 1);
   emu_energy_norm(e.data(), nullptr, eo.data(), 1, 40);
+  long long two = 2;
+  emu_energy_norm(e.data(), &two, eo.data(), 1, 40);          // the min / max branch for fewer than 3 frames
   int t_end = -1;
   emu_trim_end(e.data(), nullptr, &t_end, 1, 40);
   std::vector<float> fb(80 * 513, 0.001f), lm(80 * 3);
@@ -82,6 +84,8 @@ int main() {
   std::vector<int> label(2 * 30);
   std::vector<float> avg(2 * 6);
   emu_average_by_duration(pp.data(), dur, nullptr, label.data(), avg.data(), 2, 6, 30);
+  unsigned char tok_mask[2 * 6] = {0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
+  emu_average_by_duration(pp.data(), dur, tok_mask, label.data(), avg.data(), 2, 6, 30);
   printf("simt emulation done: t=%d frames=%d t_end=%d acc=%.3f pitch0=%.3f\n", st.t, T, t_end, acc[1], pitch[1]);
   return 0;
 }
