@@ -179,7 +179,13 @@ class KokoroModel:
                 text_padding_mask: Optional[torch.Tensor] = None, mel_padding_mask: Optional[torch.Tensor] = None,
                 stress_indices: Optional[torch.Tensor] = None):
         if mel_specs is None:
-            raise NotImplementedError("autoregressive inference is not on the B200 hot path yet (SURVEY.md 8(f) N2)")
+            import os
+            if os.environ.get("KR_FORWARD_INFERENCE", "0") == "1":      # the reference's dispatch, model.py:813-818
+                return self.forward_inference(phoneme_indices, max_len=self.max_decoder_seq_len,
+                                              text_padding_mask=text_padding_mask, stress_indices=stress_indices)
+            raise NotImplementedError("forward(mel_specs=None): the device decode path (forward_inference, SURVEY.md 8(f) "
+                                      "N2) has not had its first hardware validation run; call forward_inference() "
+                                      "directly or set KR_FORWARD_INFERENCE=1")
         if phoneme_durations is None or stop_token_targets is None:
             raise ValueError("phoneme_durations and stop_token_targets must be provided for training mode.")
         if text_padding_mask is not None or mel_padding_mask is not None:

@@ -340,6 +340,9 @@ def test_model_forward_inference_and_synthesizer_dry_run(rec, monkeypatch):
         m(idx)                                                       # forward(mel_specs=None) still refuses
     mel = m.forward_inference(idx, min_len_floor=48, max_len_cap=64, stress_indices=torch.zeros(1, 12, dtype=torch.int64))
     assert mel.shape == (1, 50, 80)
+    monkeypatch.setenv("KR_FORWARD_INFERENCE", "1")                  # opt-in: the reference's forward() dispatch
+    assert m(idx).shape == (1, 14, 80)                               # lo = 12 -> the stand-in stops two frames later
+    monkeypatch.setenv("KR_FORWARD_INFERENCE", "0")
     voc = hifigan.HiFiGANGenerator(hifigan.HiFiGANConfig.get_default_config(), device="cpu", use_graphs=False)
     audio, mel = inference.Synthesizer(m, voc)(idx, min_len_floor=48, max_len_cap=64)
     assert audio.shape == (1, 50 * 256) and mel.shape == (1, 50, 80)
