@@ -307,6 +307,7 @@ class InferenceEngine:
     def __init__(self, engine):
         self.eng = engine
         self.be = CudaDecodeBackend(engine)
+        self.last_predictions: dict = {}
 
     @torch.no_grad()
     def encode_and_expand(self, phoneme_indices: torch.Tensor, stress_indices: Optional[torch.Tensor],
@@ -352,14 +353,15 @@ class InferenceEngine:
             gf = eng._geom(B, Tp)
             flags = eng._zeros(2, dtype=torch.int32)
 
+            p_bin, e_bin = eng._empty(B, Tp, dtype=torch.int32), eng._empty(B, Tp, dtype=torch.int32)
+
             def expand(pitch, energy):
                 xg = eng._zeros(gf.R + 2, D, dtype=torch.bfloat16)
                 mem = eng._empty(B * Tp, D, dtype=torch.bfloat16)
                 fm_t, fm_p = eng._empty(B, Tp, dtype=torch.uint8), eng._empty(B, Tp, dtype=torch.uint8)
                 ops.expand_adapt(enc, lr_idx, lengths, pitch, energy, flags, st.pitch_bins, st.energy_bins,
                                  st.p(va + "pitch_embedding.weight"), st.p(va + "energy_embedding.weight"), gf.row_of_tok,
-                                 xg[1:], mem, eng._empty(B, Tp, dtype=torch.int32), eng._empty(B, Tp, dtype=torch.int32),
-                                 fm_t, fm_p, B, P, D, Tp, Tp)
+                                 xg[1:], mem, p_bin, e_bin, fm_t, fm_p, B, P, D, Tp, Tp)
                 return xg, mem, fm_p
 
             zero = eng._zeros(B, Tp)
@@ -368,6 +370,9 @@ class InferenceEngine:
             energy = eng._vp_fwd(va + "energy_predictor.", xg_frm, gf, fmask, {}, "energy")
             # pass 2: predicted values, clamped to [0, 1] (:410, :431), select the embeddings
             _, mem, fmask = expand(pitch.clamp(0.0, 1.0).contiguous(), energy.clamp(0.0, 1.0).contiguous())
+            # the adaptor's inference outputs besides the memory (variance_predictor.py:433-437) stay readable
+            self.last_predictions = {"pitch": pitch, "energy": energy, "pitch_bins": p_bin, "energy_bins": e_bin,
+                                     "encoder": enc}
             return mem, fmask, log_dur, Tp       # nothing above forks onto the engine's side streams
         finally:
             eng.training = was_training

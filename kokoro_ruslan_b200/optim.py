@@ -125,9 +125,12 @@ def preclip_of(name: str, cfg: OptimConfig) -> float:
 
 
 def wnmax_of(name: str, cfg: OptimConfig) -> float:
-    """decoder.layers.{i}.ff.linear{1,2}.weight are projected to ||W|| <= limit (trainer.py:852-912)."""
-    if name.startswith("decoder.layers.") and (name.endswith(".ff.linear1.weight") or name.endswith(".ff.linear2.weight")):
-        return cfg.dec_ffn_max_weight_norm
+    """decoder.layers.{i}.ff.linear{1,2}.weight AND transformer_encoder_layers.{i}.ff.linear{1,2}.weight (12 + 12 matrices
+    at the default depth) are projected to ||W|| <= dec_ffn_max_weight_norm after every successful step
+    (trainer.py:845-881 registers both lists, :900-912 clamps both with the same ceiling)."""
+    if (name.startswith("decoder.layers.") or name.startswith("transformer_encoder_layers.")) and \
+            (name.endswith(".ff.linear1.weight") or name.endswith(".ff.linear2.weight")):
+        return max(0.0, cfg.dec_ffn_max_weight_norm)
     return 0.0
 
 

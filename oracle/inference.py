@@ -44,8 +44,9 @@ def _heads(t: Tensor, H: int) -> Tensor:
 
 
 def encode_and_expand(sd: Dict[str, Tensor], cfg: oa.AcousticConfig, phoneme_indices: Tensor,
-                      stress_indices: Optional[Tensor]) -> Tuple[Tensor, Tensor, Tensor]:
-    """Inference branch of _encode_and_expand (model.py:450-508): (memory (B,T',D), frame_mask, log_dur)."""
+                      stress_indices: Optional[Tensor], details: Optional[dict] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """Inference branch of _encode_and_expand (model.py:450-508): (memory (B,T',D), frame_mask, log_dur).
+    `details` (a dict) receives the intermediate predictions and selected bins (for staged parity checks)."""
     B, P = phoneme_indices.shape
     D = cfg.hidden_dim
     pe = sd["positional_encoding.pe"][0]
@@ -70,6 +71,8 @@ def encode_and_expand(sd: Dict[str, Tensor], cfg: oa.AcousticConfig, phoneme_ind
     energy = oa.variance_predictor(sd, va + "energy_predictor.", cfg, mem, fmask)
     p_idx = torch.bucketize(pitch.clamp(0.0, 1.0), sd[va + "pitch_bins"])     # :410, :431
     e_idx = torch.bucketize(energy.clamp(0.0, 1.0), sd[va + "energy_bins"])
+    if details is not None:
+        details.update(pitch=pitch, energy=energy, pitch_idx=p_idx, energy_idx=e_idx, encoder=enc)
     mem = mem + sd[va + "pitch_embedding.weight"][p_idx] + sd[va + "energy_embedding.weight"][e_idx]
     return mem.masked_fill(fmask.unsqueeze(-1), 0.0), fmask, log_dur
 

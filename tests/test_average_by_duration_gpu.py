@@ -1,14 +1,12 @@
 """kr_average_by_duration on the device against fixtures from the live reference function (utils/lengths.py:156-208).
-STATUS: first hardware run pending (kernel body verified bit-identical by host emulation, tests/test_lengths_emu_cpu.py)
-— non-strict xfail, sorts last so that a device fault cannot disturb the validated suite."""
+(The kernel body is also verified bit-identical by host emulation, tests/test_lengths_emu_cpu.py.)"""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(reason="first hardware run of a kernel validated by host emulation only", strict=False)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 def test_average_by_duration_bit_identical_to_reference_fixtures():

@@ -4,7 +4,7 @@ device-state protocol, polling) with a test backend made of
   * plain torch restatements of the shared training-path kernels (LayerNorm, bf16 GEMM with fp32 accumulation, GLU,
     RMSNorm + residual) in the same mixed precision,
 against the oracle's forward_inference, which is pinned to the live reference (tests/test_inference_cpu.py).
-The device path (CudaDecodeBackend) is checked by tests/test_zz_inference_gpu.py."""
+The device path (CudaDecodeBackend) is checked by tests/test_inference_gpu.py."""
 import ctypes
 import os
 import subprocess

@@ -2,7 +2,7 @@
 with -DKR_HOST_EMU, one "thread" per block; tests/emu/features_emu.cpp loops over the grid like the launch wrappers)
 against the LIVE-reference fixtures of tests/golden/features.npz and the numpy oracle.  This checks the kernels' own
 source — index arithmetic, in-place FFT pair, CMND, every thresholded decision, rank-counting quantiles — on the CPU;
-the -m gpu test (tests/test_zz_features_gpu.py) checks the same entry points on the device."""
+the -m gpu test (tests/test_features_gpu.py) checks the same entry points on the device."""
 import ctypes
 import os
 import subprocess

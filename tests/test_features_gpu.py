@@ -1,18 +1,15 @@
 """Pitch / energy feature kernels on the device against the LIVE-reference fixtures and the numpy
 oracle, through the C ABI (kr_pitch_frames / kr_pitch_track / kr_energy_frames / kr_energy_norm).
 
-STATUS: these kernels were written after round 1's GPU budget was spent.  Their source is verified on the CPU by the
-host emulation (tests/test_features_emu_cpu.py: identical to the live reference on every fixture frame) and they
-cross-compile for sm_100a without spills, but they have not run on a B200 yet — hence the non-strict xfail marker
-(an XPASS in the report means "first hardware run green") and the file name that sorts last."""
+The same kernel source is also verified on the CPU by the host emulation (tests/test_features_emu_cpu.py: identical to
+the live reference on every fixture frame); first hardware run: round 2, all green."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(reason="first hardware run of kernels validated by host emulation only", strict=False)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 

@@ -167,6 +167,50 @@ def test_oracle_and_product_agree_on_groups_and_preclip():
         assert preclip_of(name, OptimConfig()) == spike_clip(name), name
 
 
+def _trainer_fixture():
+    import numpy as np
+    return np.load(os.path.join(HERE, "golden", "trainer_step.npz"))
+
+
+def test_group_table_preclip_and_projection_sets_match_the_live_trainer():
+    """A13' / A12 / A14 against tests/golden/trainer_step.npz, generated by the LIVE KokoroTrainer's _setup_optimizer,
+    _preclip_projection_spikes and _setup_weight_norm_constraints (tests/golden/make_golden_trainer_step.py)."""
+    from kokoro_ruslan_b200.optim import OptimConfig, group_hparams, group_of, preclip_of, wnmax_of
+    from oracle.train_step import GROUPS, param_group, spike_clip, wn_projected
+    fx = _trainer_fixture()
+    names = [str(n) for n in fx["plain/names"]]
+    lr = 1e-3                                              # the fixture's base learning rate
+    hp = group_hparams(OptimConfig(learning_rate=lr))
+    assert int(fx["plain/n_groups"]) == 10
+    for i, n in enumerate(names):
+        m, wd = hp[group_of(n)]
+        assert abs(lr * m - float(fx["plain/group_lr"][i])) < 1e-12 and wd == float(fx["plain/group_wd"][i]), n
+        assert group_of(n) == int(fx["plain/group_index"][i]) == param_group(n), n     # live groups are in our order
+        assert (wnmax_of(n, OptimConfig()) > 0) == bool(fx["plain/wn_projected"][i]) == wn_projected(n), n
+    assert sum(bool(x) for x in fx["plain/wn_projected"]) == 8     # (2 encoder + 2 decoder layers) x linear1, linear2
+    # pre-clip membership: in the hot first step of "plain" every tensor with a ceiling exceeds it
+    for i, n in enumerate(names):
+        has = preclip_of(n, OptimConfig()) > 0
+        assert has == (spike_clip(n) > 0)
+        if fx["plain/preclipped"][0][i]:
+            assert has, n
+    hot = {n for i, n in enumerate(names) if fx["explosion/preclipped"][6][i]}
+    assert hot == {n for n in names if preclip_of(n, OptimConfig()) > 0}
+
+
+def test_oracle_optimizer_step_matches_the_live_trainer():
+    """oracle.train_step.CpuTrainStep.optimizer_step vs the live trainer: detector outputs exactly, weights and EMA
+    weights to 1e-6 (measured 0: it is the same torch arithmetic in the same order)."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden_trainer_step as mk
+    fx = _trainer_fixture()
+    for case in mk.CASES:
+        fix = {k.split("/", 1)[1]: fx[k] for k in fx.files if k.startswith(case + "/")}
+        assert mk.check_oracle(case, fix) < 1e-6, case
+    assert fx["explosion/exploding"].tolist() == [0, 0, 0, 1, 0, 0, 1] and fx["explosion/skipped"].tolist() == [0, 0, 0, 0, 1, 0, 0]
+
+
 def test_adaptive_stabilisation_values():
     from kokoro_ruslan_b200.train_step import adaptive_stabilisation
     assert adaptive_stabilisation(800, 20, 1.5) == (1.0, 1.5)

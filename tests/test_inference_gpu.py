@@ -2,18 +2,21 @@
 (kr_dec_feed / kr_dec_attn / kr_dec_finish + the training-path kernels on a 128-row padded batch, one CUDA graph per
 step) against the oracle's forward_inference, which is pinned to the live reference.
 
-STATUS: written after round 1's GPU budget was spent.  The decode kernels' bodies and the DecodeLoop orchestration are
-verified on the CPU through the host emulation (tests/test_decode_emu_cpu.py), the library cross-compiles for sm_100a
-without spills, but nothing here has run on a B200 yet — hence the non-strict xfail marker (XPASS = first hardware run
-green) and the file name that sorts last."""
+Conditioning of the comparison: at inference the pitch / energy embeddings are selected by bucketising PREDICTED values
+into 256 bins of width 1/255, which is below the bf16 noise of the predictors (the reference's own autocast run has the
+same property), so a neighbouring bin is routinely selected.  With i.i.d. random embedding tables a neighbouring row is
+an unrelated vector and the comparison would measure nothing but that (first hardware run of round 2: 47 % of the
+memory rows "differ"; the fp32 oracle with 3e-3 relative noise on its own predictions gives 52 %).  The fixtures
+therefore use embedding tables that vary smoothly with the bin index — as trained tables do — and the test checks the
+three stages separately: predicted values within tolerance, selected bins within the bins that tolerance spans, memory
+rows within tolerance."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(reason="first hardware run of a path validated by host emulation only", strict=False)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -28,6 +31,7 @@ def _setup():
     sd = oa.seeded_state_dict(ocfg, seed=int(f["seed"]))
     sd["duration_adaptor.variance_adaptor.duration_predictor.linear.bias"] = torch.tensor([float(f["dur_bias"])])
     sd["stop_token_predictor.bias"] = torch.tensor([float(f["stop_bias"])])
+    _smooth_variance_embeddings(sd)
     cfg = ModelConfig(vocab_size=ocfg.vocab_size, mel_dim=ocfg.mel_dim, hidden_dim=ocfg.hidden_dim,
                       n_encoder_layers=ocfg.n_encoder_layers, n_heads=ocfg.n_heads, encoder_ff_dim=ocfg.ff_dim,
                       n_decoder_layers=ocfg.n_decoder_layers, decoder_ff_dim=ocfg.ff_dim,
@@ -36,6 +40,20 @@ def _setup():
     eng = AcousticEngine(cfg, device="cuda:0", with_ema=False)
     eng.store.load_state_dict(sd)
     return f, ocfg, sd, InferenceEngine(eng)
+
+
+def _smooth_variance_embeddings(sd, sigma_bins: float = 24.0):
+    """Low-pass the pitch / energy embedding tables along the bin axis (same RMS): neighbouring bins -> neighbouring
+    vectors, see the module docstring."""
+    va = "duration_adaptor.variance_adaptor."
+    for k in (va + "pitch_embedding.weight", va + "energy_embedding.weight"):
+        w = sd[k]
+        n = w.shape[0]
+        i = torch.arange(n, dtype=torch.float32)
+        kern = torch.exp(-0.5 * ((i[:, None] - i[None, :]) / sigma_bins) ** 2)
+        kern = kern / kern.sum(dim=1, keepdim=True)
+        sm = kern @ w
+        sd[k] = (sm * (w.pow(2).mean().sqrt() / sm.pow(2).mean().sqrt())).contiguous()
 
 
 def _oracle_durations(sd, ocfg, idx, stress):
@@ -48,16 +66,32 @@ def test_encode_and_expand_matches_oracle():
     from oracle import inference as oi
     f, ocfg, sd, inf = _setup()
     idx, stress = torch.from_numpy(f["idx"]), torch.from_numpy(f["stress"])
-    want_mem, want_pad, want_ld = oi.encode_and_expand(sd, ocfg, idx, stress)
+    det = {}
+    want_mem, want_pad, want_ld = oi.encode_and_expand(sd, ocfg, idx, stress, details=det)
     dur = _oracle_durations(sd, ocfg, idx, stress)
     mem, fmask, log_dur, Tp = inf.encode_and_expand(idx.cuda(), stress.cuda(), durations=dur)
     assert Tp == want_mem.shape[1]
     assert torch.equal(fmask.cpu().bool(), want_pad)
     assert float((log_dur.cpu() - want_ld).abs().max()) < 2e-2 * max(1.0, float(want_ld.abs().max()))
-    got = mem.float().cpu().view(1, Tp, -1)
-    # bucketised embeddings: a predicted value within bf16 noise of a bin edge may select the neighbouring row
-    close = ((got - want_mem).abs().amax(dim=-1) < 2e-2 * float(want_mem.abs().max())).float().mean()
-    assert float(close) >= 0.9, float(close)
+    live = ~want_pad
+    got = inf.last_predictions
+    enc_err = float((got["encoder"].float().cpu().view_as(det["encoder"]) - det["encoder"]).abs().max()) \
+        / float(det["encoder"].abs().max())
+    assert enc_err < 1e-2, enc_err
+    for name in ("pitch", "energy"):
+        w, g = det[name], got[name].float().cpu().view_as(det[name])
+        tol = 2e-2 * max(1.0, float(w[live].abs().max()))
+        err = float((g - w)[live].abs().max())
+        assert err < tol, (name, err, tol)
+        # selected bins: within the number of 1/255-wide bins the prediction tolerance spans (values clamp to [0, 1])
+        wb, gb = det[name + "_idx"], got[name + "_bins"].cpu().long().view_as(det[name + "_idx"])
+        dbin = int((gb - wb)[live].abs().max())
+        assert dbin <= int(err * 255) + 1, (name, dbin, err)
+        print(f"{name}: max err {err:.2e}, max bin distance {dbin}")
+    got_mem = mem.float().cpu().view(1, Tp, -1)
+    err = float((got_mem - want_mem).abs().max()) / float(want_mem.abs().max())
+    print(f"encoder {enc_err:.2e}, expanded memory {err:.2e}")
+    assert err < 2e-2, err
     # predicted durations on their own: within one frame per token of the oracle's
     _, _, _, Tp_free = inf.encode_and_expand(idx.cuda(), stress.cuda())
     assert abs(Tp_free - Tp) <= idx.shape[1]

@@ -1,11 +1,9 @@
 """kr_val_metrics on the device against the literal reference loop, and through
-TrainStep.eval_losses(metrics=...).  STATUS: first hardware run pending (kernel body verified by host emulation,
-tests/test_metrics_emu_cpu.py) — non-strict xfail, sorts last."""
+TrainStep.eval_losses(metrics=...).  (The kernel body is also verified by host emulation, tests/test_metrics_emu_cpu.py.)"""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(reason="first hardware run of a kernel validated by host emulation only", strict=False)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 def test_kernel_matches_reference_loop():

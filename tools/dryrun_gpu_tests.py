@@ -5,7 +5,7 @@ flushes out before any GPU minute is spent are Python-level errors on the device
 arguments, a ctypes arity mismatch, a shape assert in a wrapper.  (It found the `KokoroModel(vocab_size=59)` constructor
 bug of the first inference tests.)
 
-    python tools/dryrun_gpu_tests.py [test_module ...]        # default: the tests/test_zz_*_gpu.py modules
+    python tools/dryrun_gpu_tests.py [test_module ...]        # default: the the four late-round-1 modules
 
 Limits: parametrised tests are reported as TypeError (call them by hand), and tests that use torch's OWN CUDA features
 (torch.cuda.synchronize, torch's fused AdamW as a checker) cannot be dry-run.
@@ -67,7 +67,7 @@ _orig_device = torch.device
 import pytest
 class MP:
     def setenv(self, k, v): os.environ[k] = v
-MODULES = sys.argv[1:] or ["test_zz_features_gpu", "test_zz_metrics_gpu", "test_zz_lengths_gpu", "test_zz_inference_gpu"]
+MODULES = sys.argv[1:] or ["test_features_gpu", "test_metrics_gpu", "test_average_by_duration_gpu", "test_inference_gpu"]
 bad = 0
 for modname in MODULES:
     mod = importlib.import_module(modname)

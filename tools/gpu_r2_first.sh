@@ -1,23 +1,15 @@
 #!/bin/bash
-# First GPU call of the next round: the kernels written after round 1's GPU budget was spent (features N1, decode N2,
-# validation metrics N3) get their first hardware run, then their micro-benchmarks.  Outputs land in gpurun_out/.
-#   gpurun --timeout 900 -- 'bash tools/gpu_next.sh'
+# Round 2, first GPU call: real assertions for the N1/N2/N3 device tests, micro-benchmarks, KR_ATTN_FAST suite, feature ncu.
 mkdir -p gpurun_out
-python -m pytest tests/test_zz_features_gpu.py tests/test_zz_lengths_gpu.py tests/test_zz_metrics_gpu.py tests/test_zz_inference_gpu.py -m gpu -q --runxfail --tb=short -rfE \
+python -m pytest tests/test_zz_features_gpu.py tests/test_zz_lengths_gpu.py tests/test_zz_metrics_gpu.py tests/test_zz_inference_gpu.py -m gpu -q --runxfail --tb=long -rfE \
   > gpurun_out/pytest_zz.log 2>&1
 tail -15 gpurun_out/pytest_zz.log
-timeout 120 compute-sanitizer --tool racecheck python -m pytest tests/test_zz_features_gpu.py -m gpu -q -x -k "pitch_matches or energy" \
-  > gpurun_out/racecheck_features.log 2>&1; tail -3 gpurun_out/racecheck_features.log
-timeout 200 compute-sanitizer --tool racecheck python -m pytest tests/test_zz_inference_gpu.py -m gpu -q -x -k teacher \
-  > gpurun_out/racecheck_decode.log 2>&1; tail -3 gpurun_out/racecheck_decode.log
 timeout 120 python tools/features_bench.py > gpurun_out/features_bench.log 2>&1; cat gpurun_out/features_bench.log
 KR_MELSTFT_R4=1 timeout 120 python tools/features_bench.py > gpurun_out/features_bench_r4.log 2>&1; head -1 gpurun_out/features_bench_r4.log
 timeout 200 python tools/decode_bench.py 1 64 400 > gpurun_out/decode_bench.log 2>&1; cat gpurun_out/decode_bench.log
 KR_DECODE_GEMV=1 timeout 200 python tools/decode_bench.py 1 64 400 > gpurun_out/decode_bench_gemv.log 2>&1; cat gpurun_out/decode_bench_gemv.log
 KR_ATTN_FAST=1 python -m pytest tests -m gpu -q -x --deselect tests/test_zz_features_gpu.py --deselect tests/test_zz_inference_gpu.py \
   --deselect tests/test_zz_metrics_gpu.py --deselect tests/test_zz_lengths_gpu.py > gpurun_out/pytest_attn_fast.log 2>&1; tail -3 gpurun_out/pytest_attn_fast.log
-# ncu evidence for the feature kernels (mel-STFT = SURVEY 8 row A16 has no capture yet; pitch / energy / resample = N1):
-# launch list with per-launch time + DRAM bytes, then one full capture each of the two FFT kernels
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
 timeout 300 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/features_launches.csv \
   python -c "
