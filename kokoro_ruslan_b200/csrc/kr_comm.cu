@@ -32,6 +32,13 @@ struct ArParams {
   const long long* chunk_start;
   const int* chunk_len;
   int n_chunks, rank, world;
+  // the step's clip norm is a GLOBAL decision: slot [n_chunks + r] of rank r's sq buffer carries rank r's adaptive clip
+  // (long-utterance stabiliser, trainer.py:2218-2255, computed from ITS batch); every rank takes the minimum over all
+  // slots, so the replicas apply the same clip coefficient and stay bit-identical
+  const float* clip_local;        // this rank's clip for the step (device scalar), or nullptr
+  float* clip_out;                // min over ranks, read by kr_step_control as clip_override
+  long long watchdog_cycles;      // spin limit of the cross-GPU barrier
+  int* error_flag;                // raised (1 = barrier timeout) before the trap, for the host-side diagnosis
 };
 
 __device__ __forceinline__ float4 multimem_ld_reduce_f32x4(const float* addr) {
@@ -75,10 +82,16 @@ __device__ __forceinline__ void cross_gpu_barrier(const ArParams& p) {
     unsigned* wait = p.flags[p.rank] + (size_t)blockIdx.x * p.world + q;
     const long long t0 = clock64();
     while (cas_release_sys(put, 0u, 1u) != 0u) {
-      if (clock64() - t0 > 8000000000LL) { printf("kr_comm: barrier put watchdog (rank %d block %d)\n", p.rank, blockIdx.x); __trap(); }
+      if (clock64() - t0 > p.watchdog_cycles) {
+        if (p.error_flag != nullptr) { *p.error_flag = 1; __threadfence_system(); }
+        printf("kr_comm: barrier put watchdog (rank %d block %d): a peer never lowered its flag\n", p.rank, blockIdx.x); __trap();
+      }
     }
     while (cas_acquire_sys(wait, 1u, 0u) != 1u) {
-      if (clock64() - t0 > 8000000000LL) { printf("kr_comm: barrier wait watchdog (rank %d block %d)\n", p.rank, blockIdx.x); __trap(); }
+      if (clock64() - t0 > p.watchdog_cycles) {
+        if (p.error_flag != nullptr) { *p.error_flag = 1; __threadfence_system(); }
+        printf("kr_comm: barrier wait watchdog (rank %d block %d): peer %d never arrived\n", p.rank, blockIdx.x, q); __trap();
+      }
     }
   }
   __syncthreads();
@@ -107,7 +120,20 @@ __device__ __forceinline__ void ar_load_chunk(const ArParams& p, int c, float4 (
 
 __global__ void __launch_bounds__(AR_THREADS) allreduce_sqnorm_kernel(const ArParams p) {
   __shared__ float red[32];
+  if (p.clip_local != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    p.sq[p.rank][p.n_chunks + p.rank] = *p.clip_local;      // published by the release of the barrier below
+    __threadfence_system();
+  }
   cross_gpu_barrier(p);                          // every rank's gradients are final
+  if (p.clip_local != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    float c = *p.clip_local;
+    for (int q = 0; q < p.world; ++q) {
+      float v;
+      asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p.sq[q] + p.n_chunks + q) : "memory");
+      c = fminf(c, v);
+    }
+    *p.clip_out = c;
+  }
   const int stride = p.world * (int)gridDim.x;
   int c = p.rank + p.world * (int)blockIdx.x;
   float4 v[4], vn[4];
@@ -186,7 +212,8 @@ __global__ void chunk_to_tensor_kernel(const float* __restrict__ sq_chunk, const
 
 extern "C" int kr_allreduce_sqnorm(void* mc_grads, void* mc_sq, void* const* grads, void* const* sq,
                                    void* const* flags, int rank, int world, const long long* chunk_start,
-                                   const int* chunk_len, int n_chunks, int grid, void* stream) {
+                                   const int* chunk_len, int n_chunks, int grid, const float* clip_local,
+                                   float* clip_out, double watchdog_seconds, int* error_flag, void* stream) {
   if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world) { kr_set_error("kr_allreduce_sqnorm: world must be 1..8"); return KR_ERR_ARG; }
   if (grid < 1 || n_chunks <= 0) { kr_set_error("kr_allreduce_sqnorm: empty problem"); return KR_ERR_ARG; }
   ArParams p{};
@@ -198,6 +225,10 @@ extern "C" int kr_allreduce_sqnorm(void* mc_grads, void* mc_sq, void* const* gra
     p.flags[q] = reinterpret_cast<unsigned*>(flags[q]);
   }
   p.chunk_start = chunk_start; p.chunk_len = chunk_len; p.n_chunks = n_chunks; p.rank = rank; p.world = world;
+  if ((clip_local == nullptr) != (clip_out == nullptr)) { kr_set_error("kr_allreduce_sqnorm: clip_local and clip_out go together"); return KR_ERR_ARG; }
+  p.clip_local = clip_local; p.clip_out = clip_out; p.error_flag = error_flag;
+  // seconds -> SM cycles at a nominal 2 GHz (the limit only has to be generous: rank skew from one-sided host work)
+  p.watchdog_cycles = (long long)((watchdog_seconds > 0.0 ? watchdog_seconds : 300.0) * 2.0e9);
   // plain launch: every block spins on its peers, so the whole grid must not depend on a later grid
   allreduce_sqnorm_kernel<<<grid, AR_THREADS, 0, (cudaStream_t)stream>>>(p);
   KR_CHECK_LAUNCH();

@@ -3,8 +3,8 @@
 // periodic Hann, center=True / reflect pad, HTK scale, norm=None) followed by log(x + 1e-9);
 // SURVEY.md §9 S6).  HBM-bound: 1 KB of unique waveform in, 320 B out per frame.
 //
-// One CTA per frame: windowed, reflect-padded samples -> 1024-point Stockham radix-2 FFT in shared
-// memory (fp32, exact-table twiddles) -> |X|^2 for the 513 one-sided bins -> HTK triangular
+// One CTA per frame: windowed, reflect-padded samples -> 1024-point in-place radix-4 FFT in shared
+// memory (fp32, quarter-wave twiddle table) -> |X|^2 for the 513 one-sided bins -> HTK triangular
 // filterbank (dense [n_mels, 513] weights, each warp reduces its filters with shuffles) -> log.
 #include "kr_common.cuh"
 #include "kr_features_core.cuh"
@@ -37,75 +37,11 @@ __global__ void wave_peak_kernel(const float* __restrict__ wav, const long long*
   }
 }
 
+// One CTA per frame; body in kr_features_core.cuh (mel_frame_body: in-place radix-4 transform shared with the pitch
+// kernel, 5 shared-memory passes, 12 KB of shared memory), also compiled as a host emulation by the CPU tests.
+// Measured on B200 (round 2, 8 x 800 frames): 174.7 us against 186.8 us for the radix-2 Stockham kernel it replaced.
 __global__ void __launch_bounds__(THREADS)
 mel_stft_kernel(const float* __restrict__ wav, const long long* __restrict__ lengths, const float* __restrict__ peak,
-                const float* __restrict__ fb_t, float* __restrict__ out, long long n_max, int frames_max, int n_mels,
-                float log_eps) {
-  kr::pdl_entry();
-  __shared__ float2 buf[2][NFFT];
-  __shared__ float2 tw[NFFT / 2];
-  __shared__ float pw[NBINS + 3];
-  const int f = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const long long n = lengths != nullptr ? lengths[b] : n_max;
-  const int n_frames = 1 + (int)(n / HOP);
-  float* orow = out + ((long long)b * n_mels) * frames_max + f;
-  if (f >= n_frames) {                       // padding frames of a ragged batch
-    for (int m = tid; m < n_mels; m += THREADS) orow[(long long)m * frames_max] = 0.f;
-    return;
-  }
-  const float* x = wav + (long long)b * n_max;
-  const float gain = peak != nullptr ? 1.f / (peak[b] + 1e-9f) : 1.f;
-  for (int i = tid; i < NFFT / 2; i += THREADS) {
-    float s, c;
-    sincospif(-2.f * (float)i / (float)NFFT, &s, &c);
-    tw[i] = make_float2(c, s);
-  }
-  // frame f covers padded samples [f*HOP, f*HOP + NFFT) = original [f*HOP - 512, ...) with reflection
-  for (int i = tid; i < NFFT; i += THREADS) {
-    long long j = (long long)f * HOP + i - NFFT / 2;
-    if (j < 0) j = -j;
-    if (j >= n) j = 2 * (n - 1) - j;
-    j = j < 0 ? 0 : j;
-    const float w = 0.5f - 0.5f * cospif(2.f * (float)i / (float)NFFT);     // periodic Hann
-    buf[0][i] = make_float2(x[j] * gain * w, 0.f);
-  }
-  __syncthreads();
-  int cur = 0;
-#pragma unroll 1
-  for (int p = 1; p < NFFT; p <<= 1) {       // Stockham autosort radix-2, natural order in and out
-    const int tw_stride = (NFFT / 2) / p;
-    for (int i = tid; i < NFFT / 2; i += THREADS) {
-      const int k = i & (p - 1);
-      const int j = ((i - k) << 1) + k;
-      const float2 w = tw[k * tw_stride];
-      const float2 u0 = buf[cur][i];
-      const float2 v = buf[cur][i + NFFT / 2];
-      const float2 u1 = make_float2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
-      buf[cur ^ 1][j] = make_float2(u0.x + u1.x, u0.y + u1.y);
-      buf[cur ^ 1][j + p] = make_float2(u0.x - u1.x, u0.y - u1.y);
-    }
-    cur ^= 1;
-    __syncthreads();
-  }
-  for (int i = tid; i < NBINS; i += THREADS) {
-    const float2 z = buf[cur][i];
-    pw[i] = z.x * z.x + z.y * z.y;
-  }
-  __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int m = warp; m < n_mels; m += THREADS / 32) {
-    const float* frow = fb_t + (long long)m * NBINS;
-    float acc = 0.f;
-    for (int i = lane; i < NBINS; i += 32) acc = fmaf(pw[i], __ldg(frow + i), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) orow[(long long)m * frames_max] = logf(acc + log_eps);
-  }
-}
-
-// Opt-in radix-4 variant (KR_MELSTFT_R4=1): body in kr_features_core.cuh (mel_frame_body), also compiled as a host
-// emulation by the CPU tests.  Written after the last GPU run of round 1: not yet executed on hardware, hence not the default.
-__global__ void __launch_bounds__(THREADS)
-mel_stft_r4_kernel(const float* __restrict__ wav, const long long* __restrict__ lengths, const float* __restrict__ peak,
                    const float* __restrict__ fb_t, float* __restrict__ out, long long n_max, int frames_max, int n_mels,
                    float log_eps) {
   kr::pdl_entry();
@@ -121,11 +57,6 @@ mel_stft_r4_kernel(const float* __restrict__ wav, const long long* __restrict__ 
   }
   const float gain = peak != nullptr ? 1.f / (peak[b] + 1e-9f) : 1.f;
   krf::mel_frame_body(wav + (long long)b * n_max, n, f, gain, fb_t, n_mels, frames_max, log_eps, z, qw, pw, orow);
-}
-
-bool use_r4() {                       // read per call (one launch per batch, not a hot loop) so tests can A/B in-process
-  const char* e = getenv("KR_MELSTFT_R4");
-  return e != nullptr && e[0] == '1';
 }
 
 }  // namespace
@@ -147,12 +78,8 @@ extern "C" int kr_mel_stft(const float* wav, const long long* lengths, const flo
   if (n_fft != NFFT || hop != HOP) { kr_set_error("kr_mel_stft: built for n_fft 1024 / hop 256"); return KR_ERR_UNSUPPORTED; }
   if (B <= 0 || frames_max <= 0) return KR_OK;
   if (n_max < NFFT / 2 + 1) { kr_set_error("kr_mel_stft: waveform shorter than the reflect padding"); return KR_ERR_ARG; }
-  if (use_r4())
-    kr::launch(mel_stft_r4_kernel, dim3(frames_max, B), THREADS, 0, (cudaStream_t)stream, wav, lengths, peak, fb_t, out,
-               n_max, frames_max, n_mels, log_eps);
-  else
-    kr::launch(mel_stft_kernel, dim3(frames_max, B), THREADS, 0, (cudaStream_t)stream, wav, lengths, peak, fb_t, out, n_max,
-               frames_max, n_mels, log_eps);
+  kr::launch(mel_stft_kernel, dim3(frames_max, B), THREADS, 0, (cudaStream_t)stream, wav, lengths, peak, fb_t, out,
+             n_max, frames_max, n_mels, log_eps);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

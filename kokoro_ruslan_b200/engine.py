@@ -525,7 +525,7 @@ class AcousticEngine:
             ops.dec_in_drop(t_in, st.pe[:T], y, T, spec, scale_a)
         s1: dict = {}
         pre = "decoder.layers.0."
-        y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, None, None, T, s1,
+        y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, ctx["mel_pad"], None, T, s1,
                            drop=self._branch_specs("dec.0.self", p_dec, T, False))
         return melshift, y, s1
 
@@ -533,8 +533,12 @@ class AcousticEngine:
     # forward
     # ------------------------------------------------------------------------------------------
     def forward(self, phoneme_indices, mel_specs, phoneme_durations, pitch_targets, energy_targets,
-                stress_indices=None, expanded_len: Optional[int] = None):
-        """Training forward.  Returns ((mel, log_dur, stop, pitch, energy), ctx)."""
+                stress_indices=None, expanded_len: Optional[int] = None,
+                text_padding_mask: Optional[torch.Tensor] = None, mel_padding_mask: Optional[torch.Tensor] = None):
+        """Training forward.  Returns ((mel, log_dur, stop, pitch, energy), ctx).
+        text_padding_mask (B, P) u8, 1 = padding: replaces the default ``phoneme_indices == 0`` (model.py:586-589);
+        mel_padding_mask (B, T) u8: key-padding mask of the decoder self-attention (``tgt_key_padding_mask``,
+        model.py:648-654; the trainer passes None)."""
         cfg, st, D, H = self.cfg, self.store, self.D, self.H
         B, P = phoneme_indices.shape
         T = mel_specs.shape[1]
@@ -556,6 +560,7 @@ class AcousticEngine:
             self._path_table = self._empty(len(self._path_rates), B)
             ops.drop_begin(self.drop_state, self._path_site_dev, self._path_p_dev, self._path_table, B)
 
+        ctx["mel_pad"] = mel_padding_mask
         dec_head = None
         if self.multi_stream:                 # decoder input + layer-0 self-attention do not need the encoder
             with self._on("d0"):
@@ -568,8 +573,11 @@ class AcousticEngine:
         ctx["drop_pe"] = self._ds("enc.pe", p_enc)
         ops.embed_fwd(idx, stress, st.p("text_embedding.weight"), st.p("stress_embedding.weight"), st.pe, x, P,
                       drop=ctx["drop_pe"])
-        text_pad = self._empty(B, P, dtype=torch.uint8)
-        ops.eq_mask(idx, 0, text_pad)
+        if text_padding_mask is not None:
+            text_pad = text_padding_mask
+        else:
+            text_pad = self._empty(B, P, dtype=torch.uint8)
+            ops.eq_mask(idx, 0, text_pad)
         enc_saved = []
         for i in range(cfg.n_encoder_layers):
             pre = f"transformer_encoder_layers.{i}."
@@ -642,7 +650,7 @@ class AcousticEngine:
             if i == 0:
                 s1 = s1_first                 # already computed by _decoder_head
             else:
-                y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, None, None, T, s1,
+                y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, mel_padding_mask, None, T, s1,
                                    drop=self._branch_specs(f"dec.{i}.self", p_dec, T, False))
             y = self._attn_fwd(pre + "cross_attn.", y, B, T, pre + "norm2.", False, fmask_t, mem, T, s2,
                                kv_pre=kv_pre[i], drop=self._branch_specs(f"dec.{i}.cross", p_dec, T, False))
@@ -753,7 +761,7 @@ class AcousticEngine:
                                        next_dbias=st.g(pre + "self_attn.w_o.bias"), bias_done=True)
             first = False
             # layer 0: the bf16 copy feeds mel_projection_in's weight gradient through both input dropouts
-            dy, dy_bf = self._attn_bwd(pre + "self_attn.", dy, dy_bf, B, T, pre + "norm1.", True, None, None, T,
+            dy, dy_bf = self._attn_bwd(pre + "self_attn.", dy, dy_bf, B, T, pre + "norm1.", True, ctx["mel_pad"], None, T,
                                        s1, None, False, next_drop=ctx["drop_in"] if i == 0 else None,
                                        next_dbias=st.g("mel_projection_in.bias") if i == 0 else None, bias_done=True)
             if split_layer is not None and i == split_layer and i > 0:

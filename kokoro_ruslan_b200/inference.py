@@ -181,7 +181,10 @@ class CudaDecodeBackend:
         if n != STATE_WORDS * 4:
             raise RuntimeError(f"DecState is {n} bytes in libkokoro_b200.so, {STATE_WORDS * 4} expected")
         import os
-        self.use_gemv = os.environ.get("KR_DECODE_GEMV", "0") == "1"
+        # projections of the decode step: kr_dec_gemv on the <= 8 live rows (LayerNorm prologue / GLU epilogue fused; every
+        # SM streams a slice of the weights once).  Measured on B200 (round 2, tools/decode_bench.py, B=1, 400 frames):
+        # 372 us / frame against 625 us with the 128-row padded tcgen05 GEMMs, which remain for 9..16 utterances only
+        self.use_gemv = True
         # False = the reference's behaviour (new query rotated as position 0, transformers.py:276-277); True rotates it
         # to its true position like the training forward does (an opt-in fix of that train / inference mismatch)
         self.rotate_query = os.environ.get("KR_DECODE_ROPE_QUERY", "0") == "1"
@@ -224,16 +227,15 @@ class CudaDecodeBackend:
                                             c.c_int(n_out), c.c_int(w.shape[1]), o._stream()), "kr_dec_gemv")
 
     def gemm(self, a, w, out, bias=None, resid=None, rows=None):
-        """Projection of the step.  Default: the validated tcgen05 GEMM on the 128-row padded buffers.  KR_DECODE_GEMV=1
-        (and at most 8 utterances): kr_dec_gemv on the `rows` live rows — every SM streams a slice of the weights once
-        instead of 2 - 12 CTAs; opt-in until it has been measured against the default."""
+        """Projection of the step: kr_dec_gemv on the `rows` live rows (at most 8 utterances) — every SM streams a slice of
+        the weights once; more rows go through the tcgen05 GEMM on the 128-row padded buffers."""
         if self.use_gemv and rows is not None and rows <= 8 and w.shape[1] % 8 == 0 and w.shape[1] <= 1536:
             self._gemv(a, None, None, None, w, bias, resid, out, rows, False)
             return
         self.ops.gemm(a, w, out, bias=bias, resid=resid)
 
     def ln_gemv(self, x_f32, ln_g, ln_b, w, bias, out, rows, glu):
-        """LayerNorm(x) . W^T (+ bias) in one launch; glu: W = linear1, out = gelu(gate) * lin (KR_DECODE_GEMV=1 only)."""
+        """LayerNorm(x) . W^T (+ bias) in one launch; glu: W = linear1, out = gelu(gate) * lin (<= 8 utterances)."""
         self._gemv(None, x_f32, ln_g, ln_b, w, bias, None, out, rows, glu)
 
     def glu(self, h, u):
@@ -311,7 +313,7 @@ class InferenceEngine:
 
     @torch.no_grad()
     def encode_and_expand(self, phoneme_indices: torch.Tensor, stress_indices: Optional[torch.Tensor],
-                          durations: Optional[torch.Tensor] = None):
+                          durations: Optional[torch.Tensor] = None, text_padding_mask: Optional[torch.Tensor] = None):
         """Inference branch of _encode_and_expand (model.py:450-508).  Returns (mem bf16 [B*Tp, D], frame mask u8 [B, Tp],
         log_dur [B, P], Tp).  ``durations`` (B, P) integer frames per token (new, optional) replaces the predicted
         ``round(expm1(log_dur))`` — duration control, and what the parity tests use to pin the expanded length."""
@@ -329,8 +331,11 @@ class InferenceEngine:
             stress = stress_indices.to(eng.device).contiguous() if stress_indices is not None else None
             x = eng._empty(Ne, D)
             ops.embed_fwd(idx, stress, st.p("text_embedding.weight"), st.p("stress_embedding.weight"), st.pe, x, P)
-            text_pad = eng._empty(B, P, dtype=torch.uint8)
-            ops.eq_mask(idx, 0, text_pad)
+            if text_padding_mask is not None:                   # model.py:701-704: explicit mask instead of indices == 0
+                text_pad = text_padding_mask.to(eng.device).to(torch.uint8).contiguous()
+            else:
+                text_pad = eng._empty(B, P, dtype=torch.uint8)
+                ops.eq_mask(idx, 0, text_pad)
             for i in range(cfg.n_encoder_layers):
                 pre = f"transformer_encoder_layers.{i}."
                 x = eng._attn_fwd(pre + "self_attn.", x, B, P, pre + "norm1.", False, text_pad, None, P, {})
@@ -382,10 +387,10 @@ class InferenceEngine:
                  stop_threshold: float = 0.5, post_expected_stop_threshold: float = 0.2, min_len_ratio: float = 0.7,
                  min_len_floor: int = 12, max_len_ratio: float = 3.0, max_len_cap: int = 1600,
                  forced: Optional[torch.Tensor] = None, durations: Optional[torch.Tensor] = None,
-                 return_stop_probs: bool = False):
+                 return_stop_probs: bool = False, text_padding_mask: Optional[torch.Tensor] = None):
         eng = self.eng
         cfg, D = eng.cfg, eng.D
-        mem, fmask, _, Tp = self.encode_and_expand(phoneme_indices, stress_indices, durations)
+        mem, fmask, _, Tp = self.encode_and_expand(phoneme_indices, stress_indices, durations, text_padding_mask)
         B = phoneme_indices.shape[0]
         lo, hi = generation_bounds(Tp, min(max_len, cfg.max_decoder_seq_len), min_len_ratio, min_len_floor,
                                    max_len_ratio, max_len_cap)

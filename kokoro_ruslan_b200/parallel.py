@@ -82,7 +82,8 @@ class SymmetricGradReducer:
             raise RuntimeError("SymmetricGradReducer: one NVSwitch domain (<= 8 GPUs)")
         dev = store.device
         self.grads = symm.empty(store.total, dtype=torch.float32, device=dev)
-        self.sq_chunk = symm.empty(opt.n_chunks, dtype=torch.float32, device=dev)
+        # + one slot per rank behind the chunk sums: the ranks' clip norms of the step (global MIN, csrc/kr_comm.cu)
+        self.sq_chunk = symm.empty(opt.n_chunks + 8, dtype=torch.float32, device=dev)
         self.flags = symm.empty(2048 * self.world, dtype=torch.int32, device=dev)      # room for grids up to 2048 blocks
         self.grads.zero_()
         self.sq_chunk.zero_()
@@ -99,11 +100,17 @@ class SymmetricGradReducer:
         arr = ctypes.c_void_p * self.world
         self._ptrs = [arr(*[int(p) for p in h.buffer_ptrs]) for h in self._h]
         store.grads = self.grads                  # every gradient view is taken from store.grads at call time
-        opt.sq_chunk = self.sq_chunk
+        opt.sq_chunk = self.sq_chunk[:opt.n_chunks]
+        self.clip_global = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.watchdog_seconds = float(os.environ.get("KR_COMM_WATCHDOG_S", "300"))
         dist.barrier(group=group, device_ids=[dev.index])
 
-    def reduce(self) -> None:
-        """All ranks' gradients -> their sum on every rank, plus the per-chunk squared sums of the reduced buffer."""
+    def reduce(self, clip_local: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        """All ranks' gradients -> their sum on every rank, plus the per-chunk squared sums of the reduced buffer.
+        ``clip_local`` (device scalar): this rank's clip norm for the step; returns the device scalar holding the MINIMUM
+        over all ranks (the clip every replica must apply — a per-rank clip would let the replicas diverge when one rank
+        draws a long utterance and the stabiliser of trainer.py:2218-2255 tightens only its clip)."""
         import ctypes
         from ._lib import check, lib
         opt = self.opt
@@ -111,8 +118,12 @@ class SymmetricGradReducer:
                                        self._ptrs[1], self._ptrs[2], ctypes.c_int(self.rank), ctypes.c_int(self.world),
                                        ctypes.c_void_p(opt.chunk_start.data_ptr()), ctypes.c_void_p(opt.chunk_len.data_ptr()),
                                        ctypes.c_int(opt.n_chunks), ctypes.c_int(self.GRID),
+                                       ctypes.c_void_p(clip_local.data_ptr() if clip_local is not None else None),
+                                       ctypes.c_void_p(self.clip_global.data_ptr() if clip_local is not None else None),
+                                       ctypes.c_double(self.watchdog_seconds), ctypes.c_void_p(self.error_flag.data_ptr()),
                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         check(rc, "kr_allreduce_sqnorm")
+        return self.clip_global if clip_local is not None else None
 
 
 def broadcast_parameters(flat_params: torch.Tensor, src: int = 0, group=None) -> None:

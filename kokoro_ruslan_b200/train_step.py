@@ -7,9 +7,8 @@ scheduler) around the CUDA engine:
 
     host batch (pinned) --H2D--> static device buffers
       -> [CUDA graph A]  zero_grad, forward, fused losses (+ grads of the outputs), backward
-      -> [NCCL]          all-reduce(SUM) of the flat gradient buffer (world_size > 1 only): the ranges that
-                         are final after the upper half of the decoder backward are reduced underneath the
-                         lower half (graph A is cut in two there), the remainder right after it
+      -> [collective]    kr_allreduce_sqnorm (world_size > 1 only): all-reduce(SUM) of the flat gradient buffer over
+                         NVSwitch symmetric memory, fused with the per-chunk gradient norms and the global clip
       -> [CUDA graph B]  grad norms -> step control -> fused clip+AdamW+EMA -> weight-norm projection
       -> losses[6] stay on the device; the caller decides when to read them.
 
@@ -159,7 +158,6 @@ class _Staged:
     # one graph per variant: index 1 = zero the gradient buffer first (start of an accumulation window),
     # index 0 = accumulate onto it
     graph: List[Optional[torch.cuda.CUDAGraph]] = field(default_factory=lambda: [None, None])
-    graph_tail: List[Optional[torch.cuda.CUDAGraph]] = field(default_factory=lambda: [None, None])
     graph_losses: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
     losses: Optional[torch.Tensor] = None
     launches: int = 0
@@ -183,31 +181,19 @@ class TrainStep:
         if process_group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
-        # data parallel: the backward is cut after decoder layer `split_layer` so that the all-reduce of everything
-        # that is final by then (~73 % of the gradient bytes) runs on NCCL's stream underneath the rest of it
-        n_dec = self.engine.cfg.n_decoder_layers
-        self.split_layer: Optional[int] = n_dec // 2 if (self.world > 1 and n_dec >= 2) else None
-        if os.environ.get("KR_DP_SPLIT", "0") == "0":   # measured on 2 x B200: NCCL's CTAs steal SMs from the persistent
-            # GEMM grids of the backward tail and the overlap loses more than it hides (8.40 vs 8.29 ms/step)
-            self.split_layer = None
-        self._pending: List = []
-        # the collective: "fused" = one hand-written kernel over NVSwitch peer / multicast memory that also
-        # produces the optimizer's gradient norms (parallel.SymmetricGradReducer); "nccl" = torch.distributed
+        # data parallel: the ONE collective of a step is a hand-written kernel over NVSwitch peer / multicast memory that
+        # also produces the optimizer's gradient norms and the global clip (parallel.SymmetricGradReducer); there is no
+        # second communication path — a box without symmetric-memory support fails here, loudly
+        self.split_layer: Optional[int] = None
         self.reducer = None
         self.comm = "none"
         if self.world > 1:
-            self.comm = os.environ.get("KR_COMM", "fused")
-            if self.comm == "fused":
-                from .parallel import SymmetricGradReducer, symmetric_memory_usable
-                # every rank must take the same branch: agree on availability first (a box without peer access /
-                # symmetric-memory support falls back to the NCCL all-reduce — still a GPU collective, never a CPU path)
-                if symmetric_memory_usable(process_group, self.device):
-                    self.reducer = SymmetricGradReducer(self.engine.store, self.opt, process_group)
-                    self.split_layer = None       # nothing to overlap: the kernel needs the whole buffer
-                else:
-                    import sys
-                    print("kokoro_ruslan_b200: symmetric memory unavailable, using the NCCL all-reduce", file=sys.stderr)
-                    self.comm = "nccl"
+            from .parallel import SymmetricGradReducer, symmetric_memory_usable
+            if not symmetric_memory_usable(process_group, self.device):
+                raise RuntimeError("kokoro_ruslan_b200: data-parallel training needs CUDA symmetric memory (peer access "
+                                   "between all ranks of the node); it is not available on this box")
+            self.reducer = SymmetricGradReducer(self.engine.store, self.opt, process_group)
+            self.comm = "fused"
         self.max_seq_cap = max_seq_cap
         # every cached batch shape pins its static input buffers and (once captured) a graph with ~4 GB of
         # activations at the bench shape: dynamic batching produces many shapes, so the cache is LRU-bounded
@@ -317,86 +303,55 @@ class TrainStep:
         out.append(losses)
         yield from eng.backward_parts(ctx, g, self.split_layer)
 
-    def _fwd_bwd(self, d: Dict[str, torch.Tensor], Tp: int, zero: bool = True, reduce_early: bool = False) -> torch.Tensor:
+    def _fwd_bwd(self, d: Dict[str, torch.Tensor], Tp: int, zero: bool = True) -> torch.Tensor:
         out: list = []
         for _ in self._fwd_bwd_parts(d, Tp, zero, out):
-            if reduce_early:
-                self._reduce_early()
+            pass
         return out[0]
 
-    def _reduce_early(self) -> None:
-        """Async all-reduce of the gradient ranges that are final at the backward split (NCCL's own stream waits
-        for the work enqueued so far and then runs underneath what follows)."""
-        import torch.distributed as dist
-        grads = self.engine.store.grads
-        for a, b in self.engine.early_grad_ranges(self.split_layer):
-            self._pending.append(dist.all_reduce(grads[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
-
-    def _reduce_rest(self) -> None:
-        import torch.distributed as dist
-        grads = self.engine.store.grads
-        if self.split_layer is None:
-            dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=self.pg)
-            return
-        (_, a), (b, _) = self.engine.early_grad_ranges(self.split_layer)
-        self._pending.append(dist.all_reduce(grads[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
-        for w in self._pending:
-            w.wait()                               # stream-level wait: no host synchronisation
-        self._pending = []
-
-    def _run_fwd_bwd(self, st: _Staged, key, zero: bool = True, reduce_early: bool = False) -> torch.Tensor:
-        """reduce_early (data parallel, closing micro-batch of a window): launch the all-reduce of the early
-        gradient ranges at the backward split.  With graphs the step is TWO graphs sharing one memory pool
-        (head: zero-grad, forward, losses, backward down to the split; tail: the rest)."""
+    def _run_fwd_bwd(self, st: _Staged, key, zero: bool = True) -> torch.Tensor:
         Tp = key[3]
         v = int(zero)
-        split = self.split_layer is not None
         if not self.use_graphs:
             n0 = launch_count()
-            losses = self._fwd_bwd(st.dev, Tp, zero, reduce_early)
+            losses = self._fwd_bwd(st.dev, Tp, zero)
             st.launches = launch_count() - n0
             return losses
         if st.graph[v] is None:
             if st.warm[v] < 1:                    # eager warm-up (builds geometry tables, sets func attrs)
                 st.warm[v] += 1
                 n0 = launch_count()
-                losses = self._fwd_bwd(st.dev, Tp, zero, reduce_early)
+                losses = self._fwd_bwd(st.dev, Tp, zero)
                 st.launches = launch_count() - n0
                 return losses
             torch.cuda.synchronize(self.device)
             out: list = []
-            parts = self._fwd_bwd_parts(st.dev, Tp, zero, out)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                more = next(parts, "done") != "done"
+                for _ in self._fwd_bwd_parts(st.dev, Tp, zero, out):
+                    pass
             st.graph[v] = g
-            if more:
-                g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2, pool=g.pool()):
-                    assert next(parts, "done") == "done"
-                st.graph_tail[v] = g2
             st.graph_losses[v] = out[0]
         st.graph[v].replay()
-        if split and st.graph_tail[v] is not None:
-            if reduce_early:
-                self._reduce_early()
-            st.graph_tail[v].replay()
         st.losses = st.graph_losses[v]
         return st.losses
 
     def _run_optimizer(self) -> None:
         fused = self.reducer is not None and self.world > 1
+        # data parallel: the clip every replica applies is the minimum over the ranks' adaptive clips (written by the
+        # collective kernel); single process: this batch's own
+        clip = self.reducer.clip_global if fused else self.clip
         if not self.use_graphs or (self._opt_graph is None and self._opt_warm < 1):
             self._opt_warm += 1
             n0 = launch_count()
-            self.opt.step(clip_override=self.clip, sq_chunk_ready=fused)
+            self.opt.step(clip_override=clip, sq_chunk_ready=fused)
             self._opt_launches = launch_count() - n0
             return
         if self._opt_graph is None:
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.opt.step(clip_override=self.clip, sq_chunk_ready=fused)
+                self.opt.step(clip_override=clip, sq_chunk_ready=fused)
             self._opt_graph = g
         self._opt_graph.replay()
 
@@ -411,15 +366,11 @@ class TrainStep:
         st, key = self.stage(batch, divisor)
         if last:
             self.opt.set_lrs(self.sched.lrs())
-        losses = self._run_fwd_bwd(st, key, zero=first, reduce_early=(last and self.world > 1 and
-                                                                      self.split_layer is not None))
+        losses = self._run_fwd_bwd(st, key, zero=first)
         self.launches_last_step = st.launches
         if last:
             if self.world > 1:
-                if self.reducer is not None:
-                    self.reducer.reduce()
-                else:
-                    self._reduce_rest()
+                self.reducer.reduce(clip_local=self.clip)
             self._run_optimizer()
             self.sched.advance()
             self.launches_last_step += self._opt_launches + (1 if self.world > 1 else 0)

@@ -179,7 +179,6 @@ def test_inference_engine_dry_run_on_the_recording_lib(rec, monkeypatch, gemv):
     from kokoro_ruslan_b200 import inference, ops, params
     from kokoro_ruslan_b200.params import ModelConfig
     monkeypatch.setenv("KR_DECODE_GRAPH", "0")
-    monkeypatch.setenv("KR_DECODE_GEMV", "1" if gemv else "0")
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     for mod in (engine_mod, params):
         if hasattr(mod, "lib"):
@@ -205,6 +204,8 @@ def test_inference_engine_dry_run_on_the_recording_lib(rec, monkeypatch, gemv):
                       n_variance_bins=256)
     eng = engine_mod.AcousticEngine(cfg, device="cpu", with_ema=False, multi_stream=False)
     inf = inference.InferenceEngine(eng)
+    assert inf.be.use_gemv                  # the product default (<= 8 utterances); False = the path 9..16 utterances take
+    inf.be.use_gemv = gemv
     idx = torch.randint(1, 59, (2, 11))
     dur = torch.randint(1, 4, (2, 11))
     dur[1, 8:] = 0
@@ -219,7 +220,7 @@ def test_inference_engine_dry_run_on_the_recording_lib(rec, monkeypatch, gemv):
     per_step = 2 + 2 * cfg.n_decoder_layers                          # feed + finish + 2 attentions per layer
     assert names.count("kr_dec_attn") == 2 * cfg.n_decoder_layers * n_finish
     assert names.count("kr_dec_feed") == n_finish and per_step == 6
-    # KR_DECODE_GEMV=1: six skinny projections per layer and no separate LayerNorm / GLU launches inside the loop
+    # kr_dec_gemv path: six skinny projections per layer and no separate LayerNorm / GLU launches inside the loop
     assert names.count("kr_dec_gemv") == (6 * cfg.n_decoder_layers * n_finish if gemv else 0)
     assert (names.count("kr_glu_fwd") == cfg.n_encoder_layers) == gemv          # only the encoder FFNs are left
     # eval mode: no dropout specs reached the kernels, the engine's training flag is restored
@@ -336,13 +337,24 @@ def test_model_forward_inference_and_synthesizer_dry_run(rec, monkeypatch):
                           device="cpu")
     m.eval()
     idx = torch.randint(1, 59, (1, 12))
-    with pytest.raises(NotImplementedError):
-        m(idx)                                                       # forward(mel_specs=None) still refuses
     mel = m.forward_inference(idx, min_len_floor=48, max_len_cap=64, stress_indices=torch.zeros(1, 12, dtype=torch.int64))
     assert mel.shape == (1, 50, 80)
-    monkeypatch.setenv("KR_FORWARD_INFERENCE", "1")                  # opt-in: the reference's forward() dispatch
+    # forward(mel_specs=None) dispatches to forward_inference like the reference (model.py:813-818)
     assert m(idx).shape == (1, 14, 80)                               # lo = 12 -> the stand-in stops two frames later
-    monkeypatch.setenv("KR_FORWARD_INFERENCE", "0")
+    # nn.Module surface the reference trainer uses (trainer.py:835, 845-881)
+    import copy
+    mods = dict(m.named_modules())
+    assert mods["decoder.layers.0.ff.linear1"].weight.shape == (512, 128)
+    assert mods["transformer_encoder_layers.0.ff.linear2"].weight is dict(m.named_parameters())[
+        "transformer_encoder_layers.0.ff.linear2.weight"]
+    assert [n for n, _ in m.named_parameters()] == m._names and len(list(m.modules())) > 50
+    assert list(m.state_dict().keys())[:3] == ["text_embedding.weight", "stress_embedding.weight", "positional_encoding.pe"]
+    twin = copy.deepcopy(m)
+    assert twin is not m and twin.engine is not m.engine and not twin.training
+    assert all(torch.equal(a, b) for a, b in zip(twin.state_dict().values(), m.state_dict().values()))
+    twin.state_dict()["text_embedding.weight"].mul_(0.0)            # in-place EMA-style update reaches the flat buffer ...
+    assert float(twin.engine.store.p("text_embedding.weight").abs().max()) == 0.0
+    assert float(m.engine.store.p("text_embedding.weight").abs().max()) > 0.0      # ... of the copy only
     voc = hifigan.HiFiGANGenerator(hifigan.HiFiGANConfig.get_default_config(), device="cpu", use_graphs=False)
     audio, mel = inference.Synthesizer(m, voc)(idx, min_len_floor=48, max_len_cap=64)
     assert audio.shape == (1, 50 * 256) and mel.shape == (1, 50, 80)

@@ -115,7 +115,7 @@ def test_rank_counting_quantiles_with_ties(emu):
 
 
 def test_radix4_mel_stft_variant_matches_torchaudio_golden(emu):
-    """KR_MELSTFT_R4=1 kernel body (radix-4 FFT + digit reversal) against torchaudio's own output and the float64 oracle,
+    """kr_mel_stft kernel body (radix-4 FFT + digit reversal) against torchaudio's own output and the float64 oracle,
     at the gates of the device test of the default kernel (tests/test_melstft_gpu.py): 1e-3 absolute on the log-mel."""
     import torch
     from kokoro_ruslan_b200.features import mel_filterbank_htk
