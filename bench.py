@@ -12,13 +12,19 @@ forward -> fused losses -> backward -> (all-reduce) -> clip + AdamW + EMA (one o
 Prints ONE JSON line (rank 0).  `value` = device-resident whole-job throughput; `e2e` = the same
 through TrainStep.train_step() with pinned HOST batches (H2D inside the timed region) and a D2H
 read of the losses every step.  `roofline` = the tcgen05 GEMM family (dominant kernel) timed per
-launch with CUDA events in an instrumented eager step right after the timed region;
-`cpu_baseline` = the oracle port of the same step on the host cores (bounded sample).
-`first_hardware_run` (N = 1 only, `--no-extras` skips it) = micro-benchmarks of the kernels added after round 1's
-GPU budget was spent, each in its own subprocess with a hard timeout AFTER every headline measurement is done, so
-that a fault in a never-run kernel cannot touch the numbers above; not part of the headline metric.
-`--impl reference` times the CPU oracle port only (the reference is pure Python/PyTorch and its
-algorithm is restated in oracle/).
+launch with CUDA events right after the timed region — and, inside the same object so that the driver keeps
+them, `top_ops` (per-op table of the step), `hifigan` (second half of BASELINE.json's metric: HiFi-GAN samples/s
+with its own e2e and roofline fractions), `features` and `decode` (micro-benchmarks of the feature-extraction and
+autoregressive-decode kernels, isolated subprocesses with hard timeouts after every headline measurement).
+`cpu_baseline` = the reference's own CPU path (below) on a bounded sample, plus `gpu_eager_ms`: the unmodified
+reference model trained with plain PyTorch (bf16 autocast, fused AdamW) on the SAME GPU.
+
+`--impl reference` runs the UNMODIFIED reference from baseline/_ref on the host cores through its own code: the
+reference `KokoroTrainer.train_epoch` (forward, reference losses, backward, pre-clip, explosion detector, clip, AdamW,
+EMA, projection) around the reference `KokoroModel`, fp32, reference dropout defaults, at the SAME fixed batch
+(B = 8, P = 128, T = 800).  A CPU step takes many seconds, so when K + W steps do not fit the arm's time budget the
+number of timed steps is cut (never the batch) and the line says so (`steps` = timed steps, `requested_steps` = K).
+Falls back to the oracle port (`kind: "port"`) only when baseline/_ref is absent.
 """
 from __future__ import annotations
 
@@ -126,15 +132,10 @@ DROPOUT_DESC = {"reference": "reference training defaults: encoder 0.15, decoder
                 "off": "0.0 (deterministic parity configuration)"}
 
 
-def cpu_oracle_run(steps: int, warmup: int, budget_s: float, dropout: str = "reference"):
-    """Times the oracle port of the training step (fwd + losses + bwd + pre-clip + clip + AdamW +
-    EMA, fp32; dropout / stochastic depth at the reference's training defaults unless dropout == "off")
-    on the host cores.  Returns (frames/s, ms/step, cores, sample text)."""
+def _host_threads():
+    """All the host cores the box has: torchrun exports OMP_NUM_THREADS=1, which would make the CPU arm
+    single-threaded under N > 1 launches."""
     import torch
-    from oracle import acoustic as oa
-    from oracle.train_step import CpuTrainStep
-    # all the host cores the box has: torchrun exports OMP_NUM_THREADS=1, which would make the CPU arm
-    # single-threaded under N > 1 launches
     try:
         import psutil
         want = psutil.cpu_count(logical=False) or os.cpu_count() or 1
@@ -146,46 +147,108 @@ def cpu_oracle_run(steps: int, warmup: int, budget_s: float, dropout: str = "ref
         pass
     if torch.get_num_threads() < want:
         torch.set_num_threads(want)
-    cores = torch.get_num_threads()
+    return torch.get_num_threads()
+
+
+REF_TRAINER_OVERRIDES = dict(  # the bench point: default model (training/config.py), one optimizer step per batch
+    gradient_accumulation_steps=1, num_epochs=1, use_fused_adamw=False, enable_profiling=False, profile_epoch_start=999,
+    use_torch_compile=False, use_spec_augment=False)
+
+
+def cpu_reference_run(steps: int, warmup: int, budget_s: float, dropout: str = "reference"):
+    """The reference's own CPU implementation of the step: the unmodified KokoroTrainer.train_epoch from baseline/_ref
+    around the reference KokoroModel (oracle/ref_trainer.py builds the trainer object without a dataset on disk), fp32,
+    fixed B = 8 batch.  Steps are cut to the time budget, never the batch.
+    Returns (frames/s, ms/step, cores, sample text, timed steps, kind)."""
+    import torch
+    from oracle import ref_trainer as rt
+    if not rt.reference_available():
+        v, ms, cores, sample, n = cpu_oracle_run(steps, warmup, budget_s, dropout)
+        return v, ms, cores, sample, n, "port"
+    cores = _host_threads()
+    over = dict(REF_TRAINER_OVERRIDES)
+    if dropout == "off":
+        over.update(encoder_dropout=0.0, decoder_dropout=0.0, decoder_input_dropout=0.0, variance_dropout=0.0,
+                    use_stochastic_depth=False)
+    torch.manual_seed(0)
+    tr = rt.build_trainer(None, torch.device("cpu"), 59, over)
+    batch = synthetic_batch(B_PER_GPU, P_LEN, T_LEN, N_MELS, 59, seed=1)
+    t0 = time.perf_counter()
+    rt.run_epoch(tr, [batch])                                   # first step: allocator / thread-pool warm-up
+    t_first = time.perf_counter() - t0
+    n_warm = 1
+    left = budget_s - t_first
+    n_timed = max(1, min(steps, int(left / t_first) - max(0, min(warmup, 2) - 1)))
+    extra_warm = max(0, min(warmup - 1, int(left / t_first) - n_timed))
+    if extra_warm:
+        rt.run_epoch(tr, [batch] * extra_warm)
+        n_warm += extra_warm
+    done0 = tr.optimizer_steps_completed
+    t0 = time.perf_counter()
+    rt.run_epoch(tr, [batch] * n_timed)
+    dt = time.perf_counter() - t0
+    assert tr.optimizer_steps_completed - done0 == n_timed, "the reference trainer skipped a batch"
+    sample = (f"{n_timed} optimizer steps of the UNMODIFIED reference KokoroTrainer.train_epoch (baseline/_ref: forward, "
+              f"losses, backward, pre-clip, explosion detector, clip, AdamW, EMA, projection; fp32, gradient checkpointing "
+              f"as the reference configures it, dropout {'0' if dropout == 'off' else 'at the reference training defaults'}) on "
+              f"B={B_PER_GPU} utterances x P={P_LEN} x T={T_LEN} after {n_warm} warm-up step(s), torch {torch.__version__} CPU, "
+              f"{cores} threads")
+    return n_timed * B_PER_GPU * T_LEN / dt, dt / n_timed * 1e3, cores, sample, n_timed, "reference"
+
+
+def cpu_oracle_run(steps: int, warmup: int, budget_s: float, dropout: str = "reference"):
+    """Fallback when baseline/_ref is absent: the oracle port of the training step (oracle/train_step.py, pinned to the live
+    trainer by tests/golden/trainer_step.npz), fixed B = 8, steps cut to the budget."""
+    import torch
+    from oracle import acoustic as oa
+    from oracle.train_step import CpuTrainStep
+    cores = _host_threads()
     cfg = oa.AcousticConfig()
     drop = None
     if dropout != "off":      # training/config.py:108-121,195
         drop = oa.TorchDropout(p_enc=0.15, p_dec=0.20, p_in=0.15, p_var=0.1, sd_rate=0.1,
                                n_enc=cfg.n_encoder_layers, n_dec=cfg.n_decoder_layers)
     step = CpuTrainStep(cfg, oa.seeded_state_dict(cfg, seed=0), drop=drop)
-    B = B_PER_GPU
-    batch = oa.synthetic_batch(B=B, P=P_LEN, T=T_LEN, seed=1)
+    batch = oa.synthetic_batch(B=B_PER_GPU, P=P_LEN, T=T_LEN, seed=1)
     t0 = time.perf_counter()
     step.train_step(batch)
     t_first = time.perf_counter() - t0
-    done_warm = 1
-    if (steps + max(0, warmup - 1)) * t_first > budget_s and B > 1:
-        B = max(1, int(B * budget_s / ((steps + max(0, warmup - 1)) * t_first)))
-        batch = {k: (v[:B].clone() if hasattr(v, "shape") else v) for k, v in batch.items()}
-    while done_warm < warmup:
-        step.train_step(batch)
-        done_warm += 1
+    n_timed = max(1, min(steps, int((budget_s - t_first) / t_first)))
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(n_timed):
         step.train_step(batch)
     dt = time.perf_counter() - t0
-    frames = steps * B * T_LEN
-    sample = (f"{steps} full optimizer steps (fwd+losses+bwd+pre-clip+clip+AdamW+EMA, fp32, dropout "
+    sample = (f"{n_timed} full optimizer steps of the oracle PORT (fwd+losses+bwd+pre-clip+clip+AdamW+EMA, fp32, dropout "
               f"{'0' if drop is None else 'at the reference training defaults'}) of "
-              f"B={B} utterances x P={P_LEN} x T={T_LEN}, torch {torch.__version__} CPU, {cores} threads")
-    return frames / dt, dt / steps * 1e3, cores, sample
+              f"B={B_PER_GPU} utterances x P={P_LEN} x T={T_LEN}, torch {torch.__version__} CPU, {cores} threads")
+    return n_timed * B_PER_GPU * T_LEN / dt, dt / n_timed * 1e3, cores, sample, n_timed
+
+
+def bench_config(world: int, dropout: str, comm=None):
+    """The `config` object shared by both arms (same workload, same keys)."""
+    return {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "params": 49432276,
+            "precision": "bf16 tcgen05 GEMM/attention operands, fp32 accumulate/residual/optimizer",
+            "dropout": DROPOUT_DESC[dropout], "grad_accum": 1, "parallelism": f"dp{world}", "comm": comm,
+            "l2": "no flush: a step streams >1 GB of weights/optimizer state/activations (> 126 MB L2)",
+            "cuda_graphs": True}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, cores, sample = cpu_oracle_run(args.steps, args.warmup, budget_s=150.0, dropout=args.dropout)
+    value, ms, cores, sample, n_timed, kind = cpu_reference_run(args.steps, args.warmup, budget_s=240.0, dropout=args.dropout)
+    cfg = bench_config(1, args.dropout)
+    cfg.update(precision="fp32 (the reference's CPU path)", cuda_graphs=False, parallelism="cpu",
+               l2="n/a (host cores)")
+    if n_timed != args.steps:
+        cfg["reference_arm_note"] = (f"same fixed batch (B=8, P=128, T=800); {n_timed} of the requested {args.steps} steps "
+                                     f"timed to fit the arm's 240 s budget (a CPU step takes ~{ms / 1e3:.0f} s)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "dropout": DROPOUT_DESC[args.dropout]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "steps": n_timed, "requested_steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -225,7 +288,8 @@ def hifigan_leg(peaks, steps: int = 10, B: int = 16, T: int = 800):
     alg_bytes = 2.03e6 * B * T                                # ... and 2.03 MB (bf16) of activation traffic
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_hifigan_traffic_v4.json")) as f:
+        import glob
+        with open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_hifigan_traffic*.json")))[-1]) as f:
             tr = json.load(f)["kr_gemm_kernel"]
         traffic = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / 2.0    # the capture holds two forwards
     except Exception:
@@ -247,55 +311,45 @@ def hifigan_leg(peaks, steps: int = 10, B: int = 16, T: int = 800):
 # ----------------------------------------------------------------------------------------------
 # product arm
 # ----------------------------------------------------------------------------------------------
-def first_hardware_run_leg(budget_s: float = 240.0):
-    """First hardware run of what was written after round 1's GPU budget was spent: the device tests of the new kernels
-    (tests/test_zz_*_gpu.py with --runxfail, so that every failure is recorded with its exception line), their micro-benchmarks
-    (tools/features_bench.py, tools/decode_bench.py, default and opt-in variants) and the whole validated suite under the
-    opt-in KR_ATTN_FAST=1 attention forward — each in its OWN subprocess with a hard timeout, after every headline
-    measurement is finished: a fault or a hang in a never-run kernel cannot touch the numbers above.  Not part of the
-    headline metric."""
+def _json_subprocess(cmd, env=None, timeout=120.0):
+    """Runs `python cmd...` in its own process with a hard timeout; returns the JSON lines it printed (or an error dict):
+    an auxiliary measurement can never take the bench line down."""
     import subprocess
     root = os.path.dirname(os.path.abspath(__file__))
-    zz = ["tests/test_zz_features_gpu.py", "tests/test_zz_lengths_gpu.py", "tests/test_zz_metrics_gpu.py",
-          "tests/test_zz_inference_gpu.py"]
-    # (name, argv after the interpreter, extra environment, "json" = collect JSON lines | "tail" = keep the last lines)
-    runs = [# --runxfail: the first-run xfail markers are ignored here, so a failure is reported with its exception line
-            ("device_tests", ["-m", "pytest", *zz, "-m", "gpu", "-q", "--runxfail", "-rfE", "--tb=line", "-p", "no:cacheprovider"],
-             {}, "tail"),
-            ("features", ["tools/features_bench.py"], {}, "json"),
-            ("decode", ["tools/decode_bench.py", "1", "64", "400"], {}, "json"),
-            ("decode_gemv", ["tools/decode_bench.py", "1", "64", "400"], {"KR_DECODE_GEMV": "1"}, "json"),
-            ("features_mel_radix4", ["tools/features_bench.py"], {"KR_MELSTFT_R4": "1"}, "json"),
-            # the opt-in attention-forward variant of DESIGN.md section 10.1 over the whole validated suite
-            ("attn_fast_suite", ["-m", "pytest", "tests", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
-                                 *[a for z in zz for a in ("--deselect", z)]], {"KR_ATTN_FAST": "1"}, "tail")]
-    out = {"note": "first hardware run of kernels verified by host emulation only (DESIGN.md 3a) and of the opt-in "
-                   "variants; isolated subprocesses after the headline measurements; not part of the headline metric"}
-    t_end = time.time() + budget_s
-    for name, cmd, env, kind in runs:
-        left = t_end - time.time()
-        if left < 20.0:
-            out[name] = {"error": "skipped: time budget of the leg used up"}
-            continue
-        try:
-            r = subprocess.run([sys.executable] + cmd, cwd=root, env={**os.environ, **env}, capture_output=True, text=True,
-                               timeout=min(120.0, left))
-            if kind == "tail":
-                out[name] = {"rc": r.returncode, "tail": [ln[:300] for ln in r.stdout.splitlines()[-30:]]}
-                continue
-            rows = []
-            for ln in r.stdout.splitlines():
-                if ln.startswith("{"):
-                    try:
-                        rows.append(json.loads(ln))
-                    except ValueError:
-                        pass
-            out[name] = rows if (r.returncode == 0 and rows) else {"rc": r.returncode, "error": (r.stderr or r.stdout)[-400:]}
-        except subprocess.TimeoutExpired:
-            out[name] = {"error": "timeout"}
-        except Exception as exc:                                    # never let an extra take the bench line down
-            out[name] = {"error": repr(exc)}
-    return out
+    try:
+        r = subprocess.run([sys.executable] + cmd, cwd=root, env={**os.environ, **(env or {})}, capture_output=True,
+                           text=True, timeout=timeout)
+        rows = []
+        for ln in r.stdout.splitlines():
+            if ln.startswith("{"):
+                try:
+                    rows.append(json.loads(ln))
+                except ValueError:
+                    pass
+        return rows if (r.returncode == 0 and rows) else {"rc": r.returncode, "error": (r.stderr or r.stdout)[-400:]}
+    except subprocess.TimeoutExpired:
+        return {"error": "timeout"}
+    except Exception as exc:
+        return {"error": repr(exc)}
+
+
+def kernel_legs():
+    """Micro-benchmarks of the kernels beside the training step: feature extraction at the bench
+    shape with the HBM fraction of each kernel, autoregressive decode frames/s — isolated subprocesses after every
+    headline measurement.  They land inside `roofline` so that the driver's record keeps them."""
+    return {"features": _json_subprocess(["tools/features_bench.py"]),
+            "decode": _json_subprocess(["tools/decode_bench.py", "1", "64", "400"], timeout=200.0)}
+
+
+def reference_gpu_eager_ms():
+    """The unmodified reference model (baseline/_ref) trained with plain PyTorch — bf16 autocast, fused AdamW, its own loss
+    function — on the SAME GPU at the bench shape: the like-for-like bar of SURVEY.md 8(d).  ms per step, or an error."""
+    rows = _json_subprocess(["tools/ref_gpu_step.py"], timeout=240.0)
+    if isinstance(rows, list):
+        for r in rows:
+            if r.get("autocast") == "bf16":
+                return r
+    return rows
 
 
 def run_ours(args):
@@ -433,12 +487,14 @@ def run_ours(args):
 
     # ---- measured DRAM traffic of the dominant kernel (ncu capture of this command, profiles/) -------------
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_step_traffic_v4.json")) as f:
+        import glob
+        tfile = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_step_traffic*.json")))[-1]
+        with open(tfile) as f:
             tr = json.load(f)["kr_gemm_kernel"]
         if roof is not None and "error" not in roof:
             roof["traffic"] = tr["traffic_per_launch"]
             roof["traffic_note"] = ("mean dram__bytes_read+write per kr_gemm_kernel launch, ncu --clock-control none on "
-                                    "tools/one_step.py (profiles/r01_step_traffic_v4.txt); algorithmic bytes per launch = "
+                                    "tools/one_step.py (profiles/" + os.path.basename(tfile) + "); algorithmic bytes per launch = "
                                     "%.1f MB" % (sum(r["bytes"] for r in rows if r["op"].startswith("gemm")) / max(1, g_n) / 1e6))
     except Exception:
         pass
@@ -451,40 +507,45 @@ def run_ours(args):
         except Exception as exc:
             hifi = {"error": repr(exc)}
 
-    # ---- CPU baseline (oracle port, bounded sample) ---------------------------------------------------
+    # ---- CPU baseline: the reference's own trainer step on the host cores (bounded sample) + the reference on this GPU
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            v, _, cores, sample = cpu_oracle_run(steps=2, warmup=1, budget_s=40.0, dropout=args.dropout)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            v, ms_cpu, cores, sample, _, kind = cpu_reference_run(steps=2, warmup=1, budget_s=45.0, dropout=args.dropout)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "ms_per_step": ms_cpu}
+            eager = reference_gpu_eager_ms()
+            if isinstance(eager, dict) and "ms_per_step" in eager:
+                cpu["gpu_eager_ms"] = eager["ms_per_step"]
+                cpu["gpu_eager_note"] = eager.get("what")
+            else:
+                cpu["gpu_eager_ms"] = None
+                cpu["gpu_eager_error"] = eager
         except Exception as exc:
             cpu = {"error": repr(exc)}
 
-    # ---- kernels that have not had a hardware run yet: isolated subprocesses, after everything above ------
-    extras = None
-    if world == 1 and not args.no_extras:
-        try:
-            extras = first_hardware_run_leg()
-        except Exception as exc:
-            extras = {"error": repr(exc)}
+    # ---- the kernels beside the step (features, decode): isolated subprocesses, after everything above ------
+    if roof is not None:
+        roof["top_ops"] = top_ops
+        roof["hifigan"] = hifi
+        if world == 1 and not args.no_extras:
+            try:
+                roof.update(kernel_legs())
+            except Exception as exc:
+                roof["kernel_legs_error"] = repr(exc)
 
+    comm = None
+    if world > 1:
+        comm = "fused all-reduce + grad-norm + global-clip kernel over symmetric memory (%s)" % (
+            "NVSwitch multicast" if ts.reducer.multicast else "peer loads/stores")
     line = {"metric": METRIC, "value": frames_per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "params": 49432276,
-                       "precision": "bf16 tcgen05 GEMM/attention operands, fp32 accumulate/residual/optimizer",
-                       "dropout": DROPOUT_DESC[args.dropout], "grad_accum": 1, "parallelism": f"dp{world}",
-                       "comm": (None if world == 1 else ("fused all-reduce + grad-norm kernel over symmetric memory (%s)" %
-                                                         ("NVSwitch multicast" if ts.reducer.multicast else "peer loads/stores")
-                                                         if ts.reducer is not None else "NCCL all-reduce")),
-                       "l2": "no flush: a step streams >1 GB of weights/optimizer state/activations (> 126 MB L2)",
-                       "cuda_graphs": True},
+            "config": bench_config(world, args.dropout, comm),
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": frames_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d_bytes + 8 + 40, "d2h_bytes_per_step": 24},
             "gpu_launches": launches_per_step * args.steps * 2, "launches_per_step": launches_per_step,
-            "hifigan": hifi, "first_hardware_run": extras, "clocks": clocks, "losses_first": first_losses, "losses_last": final_losses, "top_ops": top_ops,
-            "lib": str(_lib.LIB_PATH)}
+            "clocks": clocks, "losses_first": first_losses, "losses_last": final_losses, "lib": str(_lib.LIB_PATH)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(device_ids=[local])
@@ -503,7 +564,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hifigan", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
-                    help="skip the isolated micro-benchmarks of the kernels that have not had a hardware run yet")
+                    help="skip the isolated micro-benchmarks of the feature / decode kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -123,12 +123,13 @@ class WarmupOneCycle:
 def adaptive_stabilisation(T: int, max_dur: int, base_clip: float, frame_thr: float = 1400.0,
                            dur_thr: float = 150.0) -> Tuple[float, float]:
     """(loss scale, clip norm) for long utterances, reference trainer.py:2218-2255: with
-    r = max(T/1400, max(d)/150) > 1 the loss is scaled by max(0.25, 1/r) and the clip becomes
-    max(0.05, 0.5/sqrt(r)) (never above the configured clip)."""
+    r = max(T/1400, max(d)/150) > 1 the loss is scaled by max(0.25, 1/r) and the clip BECOMES
+    max(0.05, 0.5/sqrt(r)) — assigned, not min-ed with the configured clip (:2246-2247; the soft stage of :2233-2236 has
+    the same thresholds and is always overwritten by it)."""
     r = max(T / frame_thr, max_dur / dur_thr)
     if r <= 1.0:
         return 1.0, base_clip
-    return max(0.25, 1.0 / r), min(base_clip, max(0.05, 0.5 / math.sqrt(r)))
+    return max(0.25, 1.0 / r), max(0.05, 0.5 / math.sqrt(r))
 
 
 def validate_batch(batch) -> None:

@@ -39,7 +39,8 @@ def main():
     n = mel.shape[1]
     dec_params = sum(p.numel() for name, p in m.named_parameters() if name.startswith("decoder."))
     print(json.dumps({"workload": f"AR decode B={B} P={P} memory={6 * P} frames", "frames": n,
-                      "gemv": os.environ.get("KR_DECODE_GEMV", "0") == "1", "s": round(dt, 4),
+                      "projections": "kr_dec_gemv" if inf.be.use_gemv and B <= 8 else "tcgen05 GEMM, 128 padded rows",
+                      "s": round(dt, 4),
                       "frames_per_s": round(B * n / dt), "us_per_step": round(dt / n * 1e6, 1),
                       "x_realtime": round(n * 256 / 22050 / dt, 1),
                       "weights_mb_per_step": round(dec_params * 2 / 1e6, 1)}))

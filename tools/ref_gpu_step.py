@@ -70,6 +70,11 @@ for autocast in (True, False):
         loss = step(autocast)
     sync()
     ms = (time.perf_counter() - t0) / n * 1e3
+    import json
+    print(json.dumps({"autocast": "bf16" if autocast else "fp32", "ms_per_step": round(ms, 2),
+                      "mel_frames_per_s": round(B_PER_GPU * T_LEN / ms * 1e3),
+                      "what": "unmodified reference KokoroModel + calculate_training_losses + clip + fused AdamW, plain PyTorch "
+                              "eager on this GPU, B=8 P=128 T=800 (no EMA / pre-clip / explosion checks of the trainer)"}))
     print(f"reference PyTorch eager on this GPU, {'bf16 autocast' if autocast else 'fp32'}: {ms:.1f} ms/step = "
           f"{B_PER_GPU * T_LEN / ms * 1e3:,.0f} mel-frames/s (loss {loss:.3f}; fwd+loss+bwd+clip+fused AdamW, no EMA / pre-clip / "
           f"explosion checks of the trainer)")
