@@ -7,10 +7,10 @@
 // outputs are consumed in place.  The T x T mask is never materialised: causality and the per-key
 // padding byte-mask are predicates on the S tile.
 //
-// forward : one CTA per (128-query tile, head, batch).  S = Q K^T lands in TMEM (128 lanes x 128
-//           cols), each of the 128 threads owns one query row: online softmax in registers, P is
-//           written to swizzled smem as the bf16 A operand of O_tile = P V (V is the MN-major B
-//           operand straight from its natural [kv, d] tile), O accumulates in registers.
+// forward : one CTA per (pair of 128-query tiles, head, batch), warp-specialised (TMA warp, MMA warp, two softmax
+//           warpgroups ping-ponging): S = Q K^T lands in TMEM, each softmax thread owns one query row, P goes back
+//           into TMEM as the bf16 A operand of O += P V (V is the MN-major B operand straight from its natural
+//           [kv, d] tile), O accumulates in TMEM with lazy rescaling.
 // backward: one CTA per (128-key tile, head, batch) looping over query tiles: S and dP = dO V^T in
 //           TMEM, P / dS rebuilt per row, then dV += P^T dO, dK += dS^T Q (P, dS as MN-major A
 //           operands, dO / Q as MN-major B operands — no transposed copies) and dQ_tile = dS K,
@@ -91,274 +91,287 @@ __device__ __forceinline__ uint32_t allowed_bits(uint32_t pad_bits, bool causal,
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward
+// forward — warp-specialised, two query tiles ping-ponging on one SM
+//
+// One CTA per (PAIR of adjacent 128-query tiles, head, batch), 320 threads:
+//   warps 0-3 = softmax warpgroup 0 (query tile 2i),  warps 4-7 = softmax warpgroup 1 (query tile 2i+1):
+//               one thread per query row (= TMEM lane), the whole 128-key S row in registers
+//   warp 8    = MMA issuer (one elected lane issues every tcgen05.mma / commit)
+//   warp 9    = TMA producer (Q tiles once, K / V tiles through a 3-stage ring shared by both warpgroups)
+// Tensor memory (all 512 columns): S_w (128 fp32 columns), P_w (64 columns of packed bf16 pairs) and O_w (64 columns)
+// per warpgroup.  O stays in TMEM for the whole key loop — the P V MMA accumulates into it — and is rescaled in
+// place only when a row's running maximum moves by more than 2^8 (lazy rescale: the softmax is computed against a
+// possibly stale maximum, P <= 256 is harmless in bf16 / fp32; S is not overwritten by P, so the rare rescale simply
+// redoes the pass), so the per-tile O read-back + 64 FMAs per row of the previous kernel are gone, and the S row is
+// streamed through registers 32 keys at a time (no 128-register row, no spills).  While warpgroup 0 runs its softmax
+// on the CUDA cores (MUFU-bound: 128 x 128 exp2 per tile), the tensor pipe runs warpgroup 1's P V and next
+// Q K^T, and vice versa; the issue order per key tile j is  [P_0 ready] PV_0(j), S_0(j+1), [P_1 ready] PV_1(j), S_1(j+1).
+// In-order MMA execution makes "S_w(j+1) complete" imply "PV_w(j) complete", so one barrier per warpgroup covers
+// both the next softmax and the lazy rescale of O.  The 1/sqrt(d) scale is folded into the exp2 argument
+// (packed FFMA2), row sums add the fp32 probabilities (FADD2).  Masks (causal, key padding) are predicates on the
+// S registers; the key-padding bits of ALL key tiles are ballotted into shared memory once, in the prologue.
 // ---------------------------------------------------------------------------------------------
-constexpr int FWD_SMEM = 7 * TILE_BYTES + 256 + 1024;
+constexpr int FWD_STAGES = 3;
+constexpr int FWD_THREADS = 320;
+constexpr int FWD_MAX_KTILES = 64;                                   // key-padding bit table: Sk <= 8192
+constexpr int FWD_SMEM = (2 + 2 * FWD_STAGES) * TILE_BYTES + 256 + FWD_MAX_KTILES * 16 + 1024;
+constexpr float FWD_RESCALE_LOG2 = 8.f;                              // rescale O when the row max grows by > 2^8
 
-// FAST = opt-in instruction-count variant of the softmax / rescale code (env KR_ATTN_FAST=1; written at the end of
-// round 1: the attention unit tests pass with it and it is 2-13 us faster per launch, but the full parity suite was
-// not re-run with it, so it is NOT the default yet): the forward's 128 softmax threads are
-// issue-bound (ncu: ~26 M warp instructions, issue slots 28 % busy with 2 warps per scheduler, tensor pipe 7 %), so
-// it removes instructions — the 1/sqrt(d) scale is folded into the exp2 argument with a packed FFMA2 (no pre-scaling
-// pass over S), the row sum adds the fp32 probabilities with FADD2 (no unpack of the bf16-rounded values), and
-// the O rescale-accumulate is a packed FFMA2.  The default instantiations are textually unchanged.
-template <bool CAUSAL, bool DROP, bool FAST = false>
-__global__ void __launch_bounds__(128, 2)
+template <bool CAUSAL, bool DROP>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + TILE_BYTES;       // 2 stages
-  uint8_t* sV = smem + 3 * TILE_BYTES;   // 2 stages
-  uint8_t* sP = smem + 5 * TILE_BYTES;   // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * TILE_BYTES);
-  uint64_t* q_bar = bars;
-  uint64_t* k_bar = bars + 1;
-  uint64_t* v_bar = bars + 3;
-  uint64_t* s_bar = bars + 5;
-  uint64_t* o_bar = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-  uint32_t* mask_words = tmem_slot + 2;  // [2][4]
+  uint8_t* sQ = smem;                                   // [2] query tiles
+  uint8_t* sK = smem + 2 * TILE_BYTES;                  // [FWD_STAGES]
+  uint8_t* sV = sK + FWD_STAGES * TILE_BYTES;           // [FWD_STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FWD_STAGES * TILE_BYTES);
+  uint64_t* q_bar = bars;                               // Q tiles landed (tx)
+  uint64_t* k_full = bars + 1;                          // [FWD_STAGES] (tx)
+  uint64_t* v_full = k_full + FWD_STAGES;               // [FWD_STAGES] (tx)
+  uint64_t* kv_empty = v_full + FWD_STAGES;             // [FWD_STAGES] commit: every MMA reading the stage is done
+  uint64_t* s_full = kv_empty + FWD_STAGES;             // [2] commit: S_w(j) (and with it PV_w(j-1)) complete
+  uint64_t* p_ready = s_full + 2;                       // [2] 128 arrivals: P_w(j) (and a rescaled O_w) are in TMEM
+  uint64_t* o_final = p_ready + 2;                      // [2] commit: the last PV_w is complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
+  uint32_t* mask_words = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [n_ktiles][4]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // causal: the last query tile attends to the most keys -> schedule the heavy tiles first
-  const int qt = CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
-  const int q0 = qt * TQ, h = blockIdx.y, b = blockIdx.z;
-  int n_tiles = (p.Sk + TK - 1) / TK;
-  if (CAUSAL) n_tiles = min(n_tiles, qt + 1);
+  const int n_qtiles = (p.Sq + TQ - 1) / TQ;
+  // causal: the last pair attends to the most keys -> schedule the heavy pairs first
+  const int pair = CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_ktiles = (p.Sk + TK - 1) / TK;
+  int n_w[2];
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    const int qt = 2 * pair + w;
+    n_w[w] = qt < n_qtiles ? (CAUSAL ? min(n_ktiles, qt + 1) : n_ktiles) : 0;
+  }
+  const int n_max = max(n_w[0], n_w[1]);
 
   pdl_launch_dependents();
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    mbar_init(q_bar, 1);
+    for (int i = 0; i < FWD_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(&s_full[w], 1); mbar_init(&p_ready[w], 128); mbar_init(&o_final[w], 1); }
     fence_barrier_init();
   }
-  if (warp == 0) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  pdl_wait();
+  // key-padding bits of every key tile (bit e of word [t][c] set = key 128 t + 32 c + e is padding / out of range)
+  for (int wi = warp; wi < n_max * 4; wi += FWD_THREADS / 32) {
+    const int key = wi * 32 + lane;
+    bool masked = key >= p.Sk;
+    if (!masked && p.key_mask != nullptr) masked = p.key_mask[(long long)b * p.Sk + key] != 0;
+    const unsigned bits = __ballot_sync(0xffffffffu, masked);
+    if (lane == 0) mask_words[wi] = bits;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
-  const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
-
-  if (tid == 0) {
-    mbar_arrive_expect_tx(q_bar, TILE_BYTES);
-    tma_load_4d(sQ, &tmQ, q_bar, 0, h, q0, b);
-    mbar_arrive_expect_tx(&k_bar[0], TILE_BYTES);
-    tma_load_4d(sK, &tmK, &k_bar[0], 0, h, 0, b);
-    mbar_arrive_expect_tx(&v_bar[0], TILE_BYTES);
-    tma_load_4d(sV, &tmV, &v_bar[0], 0, h, 0, b);
-  }
-
-  float o_acc[HD];
-#pragma unroll
-  for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-  const int qi = q0 + tid;
-  uint2 dkey = make_uint2(0u, 0u);
-  uint32_t drow = 0;
-  if (DROP) {
-    dkey = drop_key(p.drop.state, p.drop.site_a);
-    drow = (uint32_t)(((long long)b * p.H + h) * p.Sq + min(qi, p.Sq - 1)) * p.sk_pad_quarter;
-  }
   constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
   constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
 
-  for (int j = 0; j < n_tiles; ++j) {
-    const int st = j & 1;
-    {
-      const int key = j * TK + tid;
-      bool masked = key >= p.Sk;
-      if (!masked && p.key_mask != nullptr) masked = p.key_mask[(long long)b * p.Sk + key] != 0;
-      const unsigned w = __ballot_sync(0xffffffffu, masked);
-      if (lane == 0) mask_words[st * 4 + warp] = w;
-    }
-    if (tid == 0) {
-      if (j + 1 < n_tiles) {
-        const int ns = st ^ 1;
-        mbar_arrive_expect_tx(&k_bar[ns], TILE_BYTES);
-        tma_load_4d(sK + ns * TILE_BYTES, &tmK, &k_bar[ns], 0, h, (j + 1) * TK, b);
-        mbar_arrive_expect_tx(&v_bar[ns], TILE_BYTES);
-        tma_load_4d(sV + ns * TILE_BYTES, &tmV, &v_bar[ns], 0, h, (j + 1) * TK, b);
+  if (warp == 9) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_bar, TILE_BYTES * (n_w[1] > 0 ? 2 : 1));
+      tma_load_4d(sQ, &tmQ, q_bar, 0, h, (2 * pair) * TQ, b);
+      if (n_w[1] > 0) tma_load_4d(sQ + TILE_BYTES, &tmQ, q_bar, 0, h, (2 * pair + 1) * TQ, b);
+      for (int j = 0; j < n_max; ++j) {
+        const int st = j % FWD_STAGES;
+        if (j >= FWD_STAGES) mbar_wait(&kv_empty[st], ((j / FWD_STAGES) - 1) & 1);
+        mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+        tma_load_4d(sK + st * TILE_BYTES, &tmK, &k_full[st], 0, h, j * TK, b);
+        mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+        tma_load_4d(sV + st * TILE_BYTES, &tmV, &v_full[st], 0, h, j * TK, b);
       }
-      if (j == 0) mbar_wait(q_bar, 0);
-      mbar_wait(&k_bar[st], (j >> 1) & 1);
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      mbar_wait(q_bar, 0);
+      mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + st * TILE_BYTES);
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
-        umma_bf16_ss(tmem_S, desc_k64(aQ, k), desc_k64(aK, k), idesc_s, k > 0 ? 1u : 0u);
-      umma_commit(s_bar);
-    }
-    __syncthreads();
-    mbar_wait(s_bar, j & 1);
-    tc_fence_after();
-    uint32_t mw[4];
+      for (int w = 0; w < 2; ++w) {
+        if (n_w[w] > 0) {
+          const uint32_t aQ = smem_u32(sQ + w * TILE_BYTES), aK = smem_u32(sK);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) mw[c] = mask_words[st * 4 + c];
-
-    float alpha;
-    if constexpr (!FAST) {
-    // S row (128 keys) is read from TMEM ONCE into registers (TMEM read bandwidth, 64 B/clk/SM, is the
-    // scarce resource of this loop); masking folded in as -inf
-    float sv[128];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_S + t_lane + c * 32, r);
-      tmem_ld_wait();
-      const uint32_t ok = allowed_bits(mw[c], CAUSAL, j * TK + c * 32, qi);
-      if (__all_sync(0xffffffffu, ok == 0xffffffffu)) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sv[c * 32 + i] = __uint_as_float(r[i]) * p.scale_log2;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          sv[c * 32 + i] = ((ok >> i) & 1u) ? __uint_as_float(r[i]) * p.scale_log2 : -INFINITY;
-      }
-    }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 128; ++i) mx = fmaxf(mx, sv[i]);
-    const float m_new = fmaxf(m_run, mx);
-    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-    alpha = fast_exp2(m_run - m_use);
-    // P (bf16) goes back into TENSOR MEMORY, over the S columns this thread has already consumed: the P V MMA
-    // then reads its A operand from TMEM, which removes a 32 KB smem write + 32 KB smem read per tile from the
-    // loop (shared-memory operand bandwidth is what bounds these d = 64 MMAs).  Packed layout: lane = query row,
-    // 32-bit column c holds keys (2c, 2c+1).
-    float rowsum = 0.f;
-#pragma unroll
-    for (int hcol = 0; hcol < 2; ++hcol) {
-      uint32_t pk[32];
-#pragma unroll
-      for (int i = 0; i < 64; i += 4) {
-        // exp2(-inf) = 0 handles the masked entries; the row sum uses the bf16-rounded values the MMA sees
-        uint32_t u0 = pack_bf16(fast_exp2(sv[hcol * 64 + i] - m_use), fast_exp2(sv[hcol * 64 + i + 1] - m_use));
-        uint32_t u1 = pack_bf16(fast_exp2(sv[hcol * 64 + i + 2] - m_use), fast_exp2(sv[hcol * 64 + i + 3] - m_use));
-        const float2 ra = unpack_bf16(u0), rb = unpack_bf16(u1);
-        rowsum += (ra.x + ra.y) + (rb.x + rb.y);   // the softmax denominator is that of the un-dropped probabilities
-        if (DROP) {
-          const uint32_t m = drop_quad_bytes(drow + j * (TK / 4) + hcol * 16 + (i >> 2), dkey, p.thr4);
-          u0 &= keep_lo_pair(m);
-          u1 &= keep_hi_pair(m);
-        }
-        pk[i >> 1] = u0;
-        pk[(i >> 1) + 1] = u1;
-      }
-      tmem_st_32x32(tmem_S + t_lane + hcol * 32, pk);
-    }
-    tmem_st_wait();
-    l_run = l_run * alpha + rowsum;
-    m_run = m_new;
-    } else {
-      // RAW logits in registers (masked = -inf); scale folded into the exp2 argument
-      float sv[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_S + t_lane + c * 32, r);
-        tmem_ld_wait();
-        const uint32_t ok = allowed_bits(mw[c], CAUSAL, j * TK + c * 32, qi);
-        if (__all_sync(0xffffffffu, ok == 0xffffffffu)) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sv[c * 32 + i] = __uint_as_float(r[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sv[c * 32 + i] = ((ok >> i) & 1u) ? __uint_as_float(r[i]) : -INFINITY;
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16_ss(tmem_base + w * 128, desc_k64(aQ, k), desc_k64(aK, k), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[w]);
         }
       }
-      float mx = -INFINITY;
+      for (int j = 0; j < n_max; ++j) {
+        const int st = j % FWD_STAGES;
 #pragma unroll
-      for (int i = 0; i < 128; ++i) mx = fmaxf(mx, sv[i]);
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);       // scale > 0: max commutes with it
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      alpha = fast_exp2(m_run - m_use);
+        for (int w = 0; w < 2; ++w) {
+          if (j >= n_w[w]) continue;
+          mbar_wait(&p_ready[w], j & 1);
+          mbar_wait(&v_full[st], (j / FWD_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t tS = tmem_base + w * 128, tP = tmem_base + 256 + w * 64, tO = tmem_base + 384 + w * 64;
+          const uint32_t aV = smem_u32(sV + st * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < TK / 16; ++k)       // 16 keys = 8 packed TMEM columns per MMA
+            umma_bf16_ts(tO, tP + k * 8, desc_mn64(aV, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          if (j + 1 < n_w[w]) {
+            const int ns = (j + 1) % FWD_STAGES;
+            mbar_wait(&k_full[ns], ((j + 1) / FWD_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t aQ = smem_u32(sQ + w * TILE_BYTES), aK = smem_u32(sK + ns * TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k)
+              umma_bf16_ss(tS, desc_k64(aQ, k), desc_k64(aK, k), idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&s_full[w]);
+          } else {
+            umma_commit(&o_final[w]);
+          }
+        }
+        umma_commit(&kv_empty[st]);               // S_*(j) and PV_*(j) were all issued before this point
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int w = warp >> 2;                       // warpgroup = query tile of the pair
+    const int row = tid & 127;                     // query row inside the tile = TMEM lane
+    const int q0 = (2 * pair + w) * TQ, qi = q0 + row;
+    const uint32_t t_lane = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + w * 128 + t_lane, tP = tmem_base + 256 + w * 64 + t_lane,
+                   tO = tmem_base + 384 + w * 64 + t_lane;
+    // a warp whose 32 rows all lie beyond Sq only keeps the barriers moving
+    const bool warp_live = q0 + (warp & 3) * 32 < p.Sq;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint2 dkey = make_uint2(0u, 0u);
+    uint32_t drow = 0;
+    if (DROP) {
+      dkey = drop_key(p.drop.state, p.drop.site_a);
+      drow = (uint32_t)(((long long)b * p.H + h) * p.Sq + min(qi, p.Sq - 1)) * p.sk_pad_quarter;
+    }
+    const int nt = n_w[w];
+    // One pass over the S row in 32-key chunks (the next chunk's TMEM load is in flight while the current one is
+    // processed): masks, running tile maximum of the RAW logits, P = exp2(s * scale - m_use) -> packed bf16 (+ dropout)
+    // -> TMEM, fp32 row sum.  WRITE = false only finds the maximum (first key tile).
+    auto row_pass = [&](int j, float m_use, bool write, float& tile_max, float& tile_sum) {
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_use, -m_use);
       float2 rs2 = make_float2(0.f, 0.f);
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+      uint32_t buf[2][32];
+      tmem_ld_32x32(tS, buf[0]);
 #pragma unroll
-      for (int hcol = 0; hcol < 2; ++hcol) {
-        uint32_t pk[32];
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < 4) tmem_ld_32x32(tS + (c + 1) * 32, buf[(c + 1) & 1]);
+        uint32_t (&r)[32] = buf[c & 1];
+        const uint32_t ok = allowed_bits(mask_words[j * 4 + c], CAUSAL, j * TK + c * 32, qi);
+        if (!__all_sync(0xffffffffu, ok == 0xffffffffu)) {
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          const float2 a0 = __ffma2_rn(make_float2(sv[hcol * 64 + i], sv[hcol * 64 + i + 1]), sc2, nm2);
-          const float2 a1 = __ffma2_rn(make_float2(sv[hcol * 64 + i + 2], sv[hcol * 64 + i + 3]), sc2, nm2);
-          const float2 e0 = make_float2(fast_exp2(a0.x), fast_exp2(a0.y));   // exp2(-inf) = 0 for masked keys
-          const float2 e1 = make_float2(fast_exp2(a1.x), fast_exp2(a1.y));
-          rs2 = __fadd2_rn(rs2, e0);
-          rs2 = __fadd2_rn(rs2, e1);
-          uint32_t u0 = pack_bf16(e0.x, e0.y), u1 = pack_bf16(e1.x, e1.y);
-          if (DROP) {
-            const uint32_t m = drop_quad_bytes(drow + j * (TK / 4) + hcol * 16 + (i >> 2), dkey, p.thr4);
-            u0 &= keep_lo_pair(m);
-            u1 &= keep_hi_pair(m);
-          }
-          pk[i >> 1] = u0;
-          pk[(i >> 1) + 1] = u1;
+          for (int i = 0; i < 32; ++i) r[i] = ((ok >> i) & 1u) ? r[i] : 0xff800000u;      // -inf
         }
-        tmem_st_32x32(tmem_S + t_lane + hcol * 32, pk);
-      }
-      tmem_st_wait();
-      l_run = l_run * alpha + (rs2.x + rs2.y);
-      m_run = m_new;
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(&v_bar[st], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t aV = smem_u32(sV + st * TILE_BYTES);
-#pragma unroll
-      for (int k = 0; k < TK / 16; ++k)       // 16 keys = 8 packed TMEM columns per MMA
-        umma_bf16_ts(tmem_O, tmem_S + k * 8, desc_mn64(aV, k), idesc_o, k > 0 ? 1u : 0u);
-      umma_commit(o_bar);
-    }
-    __syncwarp();
-    mbar_wait(o_bar, j & 1);
-    tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_O + t_lane + c * 32, r);
-      tmem_ld_wait();
-      if constexpr (!FAST) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(r[i]);
-      } else {
-        const float2 al2 = make_float2(alpha, alpha);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float2 o2 = __ffma2_rn(make_float2(o_acc[c * 32 + i], o_acc[c * 32 + i + 1]), al2,
-                                       make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
-          o_acc[c * 32 + i] = o2.x;
-          o_acc[c * 32 + i + 1] = o2.y;
+          mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+        }
+        if (write) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float2 a0 = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, nm2);
+            const float2 a1 = __ffma2_rn(make_float2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), sc2, nm2);
+            const float2 e0 = make_float2(fast_exp2(a0.x), fast_exp2(a0.y));   // exp2(-inf) = 0 for masked keys
+            const float2 e1 = make_float2(fast_exp2(a1.x), fast_exp2(a1.y));
+            rs2 = __fadd2_rn(rs2, e0);               // the softmax denominator is that of the un-dropped probabilities
+            rs2 = __fadd2_rn(rs2, e1);
+            uint32_t u0 = pack_bf16(e0.x, e0.y), u1 = pack_bf16(e1.x, e1.y);
+            if (DROP) {
+              const uint32_t m = drop_quad_bytes(drow + j * (TK / 4) + c * 8 + (i >> 2), dkey, p.thr4);
+              u0 &= keep_lo_pair(m);
+              u1 &= keep_hi_pair(m);
+            }
+            pk[i >> 1] = u0;
+            pk[(i >> 1) + 1] = u1;
+          }
+          tmem_st_32x16(tP + c * 16, pk);            // packed: 32-bit column k holds keys (2k, 2k+1)
         }
       }
-    }
-    tc_fence_before();
-  }
-
-  if (qi < p.Sq) {
-    float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    if (DROP) inv *= p.drop.scale;
-    bf16* orow = p.O + (long long)b * p.o_bs + (long long)qi * p.o_ss + h * HD;
+      tile_max = fmaxf(mx0, mx1) * p.scale_log2;     // scale > 0: max commutes with it
+      tile_sum = rs2.x + rs2.y;
+    };
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&s_full[w], j & 1);
+      tc_fence_after();
+      if (warp_live) {
+        float mx, rs;
+        if (j == 0) {                                // first key tile: find the maximum first
+          row_pass(0, 0.f, false, mx, rs);
+          m_run = mx;
+        }
+        row_pass(j, (m_run == -INFINITY) ? 0.f : m_run, true, mx, rs);
+        // Lazy rescale: the pass above used the running (possibly stale) maximum; only when some row of the warp
+        // outgrew it by more than 2^8 are O and l rescaled and the pass redone (warp-uniform branch: the TMEM accesses
+        // are warp-collective).  S is still intact: P lives in its own TMEM columns.
+        if (__any_sync(0xffffffffu, mx > m_run + FWD_RESCALE_LOG2)) {
+          const float m_new = fmaxf(m_run, mx);
+          const float alpha = fast_exp2(m_run - ((m_new == -INFINITY) ? 0.f : m_new));   // m_run = -inf -> 0
+          if (j > 0) {                               // PV(j-1) is complete (s_full ordering): O can be touched
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      uint4 q;
-      q.x = pack_bf16(o_acc[8 * i] * inv, o_acc[8 * i + 1] * inv);
-      q.y = pack_bf16(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv);
-      q.z = pack_bf16(o_acc[8 * i + 4] * inv, o_acc[8 * i + 5] * inv);
-      q.w = pack_bf16(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv);
-      *reinterpret_cast<uint4*>(orow + 8 * i) = q;
+            for (int c = 0; c < 2; ++c) {
+              uint32_t r[32];
+              tmem_ld_32x32(tO + c * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st_32x32(tO + c * 32, r);
+            }
+          }
+          l_run *= alpha;
+          m_run = m_new;
+          row_pass(j, (m_run == -INFINITY) ? 0.f : m_run, true, mx, rs);
+        }
+        l_run += rs;
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&p_ready[w]);
     }
-    p.lse[((long long)b * p.H + h) * p.Sq + qi] = l_run > 0.f ? m_run + log2f(l_run) : 0.f;
+    if (nt > 0) {
+      mbar_wait(&o_final[w], 0);
+      tc_fence_after();
+      if (warp_live) {
+        float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        if (DROP) inv *= p.drop.scale;
+        bf16* orow = p.O + (long long)b * p.o_bs + (long long)qi * p.o_ss + h * HD;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tO + c * 32, r);
+          tmem_ld_wait();
+          if (qi < p.Sq) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 q;
+              q.x = pack_bf16(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
+              q.y = pack_bf16(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
+              q.z = pack_bf16(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
+              q.w = pack_bf16(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + c * 32 + 8 * i) = q;
+            }
+          }
+        }
+        if (qi < p.Sq) p.lse[((long long)b * p.H + h) * p.Sq + qi] = l_run > 0.f ? m_run + log2f(l_run) : 0.f;
+      }
+    }
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -713,6 +726,7 @@ extern "C" int kr_attn_fwd(const void* q, long long q_ss, long long q_bs, const 
   p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.key_mask = key_mask; p.O = reinterpret_cast<bf16*>(o); p.o_ss = o_ss; p.o_bs = o_bs; p.lse = lse;
   if ((rc = set_drop(p, drop, "kr_attn_fwd")) != KR_OK) return rc;
+  if ((Sk + TK - 1) / TK > FWD_MAX_KTILES) { kr_set_error("kr_attn_fwd: Sk > 8192 keys is not supported"); return KR_ERR_UNSUPPORTED; }
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
@@ -721,29 +735,14 @@ extern "C" int kr_attn_fwd(const void* q, long long q_ss, long long q_bs, const 
     cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
     attr = true;
   }
-  dim3 grid((Sq + TQ - 1) / TQ, H, B);
+  const int n_qtiles = (Sq + TQ - 1) / TQ;
+  dim3 grid((n_qtiles + 1) / 2, H, B);          // one CTA per PAIR of query tiles
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool dr = p.drop.state != nullptr;
-  static int fast = -1;
-  if (fast < 0) {
-    const char* e = getenv("KR_ATTN_FAST");
-    fast = (e != nullptr && e[0] == '1') ? 1 : 0;
-    if (fast) {
-      cudaFuncSetAttribute(attn_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
-      cudaFuncSetAttribute(attn_fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
-      cudaFuncSetAttribute(attn_fwd_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
-      cudaFuncSetAttribute(attn_fwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
-    }
-  }
-  if (fast) {     // opt-in, see the kernel's header comment
-    if (causal && dr)  kr::launch(attn_fwd_kernel<true, true, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
-    else if (causal)   kr::launch(attn_fwd_kernel<true, false, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
-    else if (dr)       kr::launch(attn_fwd_kernel<false, true, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
-    else               kr::launch(attn_fwd_kernel<false, false, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
-  } else if (causal && dr)  kr::launch(attn_fwd_kernel<true, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
-  else if (causal)   kr::launch(attn_fwd_kernel<true, false>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
-  else if (dr)       kr::launch(attn_fwd_kernel<false, true>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
-  else               kr::launch(attn_fwd_kernel<false, false>, grid, 128, FWD_SMEM, st, tq, tk, tv, p);
+  if (causal && dr)  kr::launch(attn_fwd_kernel<true, true>, grid, FWD_THREADS, FWD_SMEM, st, tq, tk, tv, p);
+  else if (causal)   kr::launch(attn_fwd_kernel<true, false>, grid, FWD_THREADS, FWD_SMEM, st, tq, tk, tv, p);
+  else if (dr)       kr::launch(attn_fwd_kernel<false, true>, grid, FWD_THREADS, FWD_SMEM, st, tq, tk, tv, p);
+  else               kr::launch(attn_fwd_kernel<false, false>, grid, FWD_THREADS, FWD_SMEM, st, tq, tk, tv, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

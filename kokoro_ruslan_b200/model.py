@@ -217,6 +217,20 @@ class KokoroModel(torch.nn.Module):
         memo[id(self)] = twin
         return twin
 
+    @property
+    def variance_adaptor(self):
+        """model.py:222-231: the wrapped VarianceAdaptor (here: its name-space node with the parameters and bins)."""
+        return self.duration_adaptor.variance_adaptor
+
+    def get_model_info(self) -> dict:
+        """model.py:820-845."""
+        total = sum(p.numel() for p in self._params)
+        return {"vocab_size": self.vocab_size, "mel_dim": self.mel_dim, "hidden_dim": self.hidden_dim,
+                "n_encoder_layers": len(self.transformer_encoder_layers), "n_decoder_layers": self.decoder.num_layers,
+                "total_parameters": total, "trainable_parameters": total, "model_size_mb": total * 4 / (1024 * 1024),
+                "gradient_checkpointing": {"enabled": False, "segments": self.checkpoint_segments,
+                                           "memory_savings_estimated": "n/a (activations are kept: 180 GB HBM)"}}
+
     # ---- augmentation hook -------------------------------------------------------------------------
     def set_memory_augment(self, fn: Optional[Callable]) -> None:
         """Reference hook (model.py:212-220): ``fn`` maps the (B, T, D) cross-attention memory to its augmented version,

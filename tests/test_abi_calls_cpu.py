@@ -343,6 +343,9 @@ def test_model_forward_inference_and_synthesizer_dry_run(rec, monkeypatch):
     assert m(idx).shape == (1, 14, 80)                               # lo = 12 -> the stand-in stops two frames later
     # nn.Module surface the reference trainer uses (trainer.py:835, 845-881)
     import copy
+    info = m.get_model_info()
+    assert info["n_decoder_layers"] == 1 and info["total_parameters"] == sum(p.numel() for p in m.parameters())
+    assert m.variance_adaptor.pitch_bins.shape == (255,)
     mods = dict(m.named_modules())
     assert mods["decoder.layers.0.ff.linear1"].weight.shape == (512, 128)
     assert mods["transformer_encoder_layers.0.ff.linear2"].weight is dict(m.named_parameters())[

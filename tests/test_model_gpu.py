@@ -93,7 +93,17 @@ def test_surface_matches_reference_module():
     with pytest.raises(ValueError):
         m(x, torch.zeros(1, 20, 80).cuda())                   # mel without durations / stop targets
     assert m.training == was                                  # forward never flips train/eval
-    with pytest.raises(NotImplementedError):
-        m(x)
+    mel = m.eval()(x)                                         # mel_specs=None -> forward_inference (model.py:813-818)
+    assert mel.dim() == 3 and mel.shape[0] == 1 and mel.shape[2] == 80 and mel.shape[1] >= 12
+    m.train(was)
     with pytest.raises(RuntimeError):
         m.to("cpu")
+    # nn.Module surface the reference trainer relies on (trainer.py:835, 845-881)
+    import copy
+    mods = dict(m.named_modules())
+    assert all(f"decoder.layers.{i}.ff.linear{k}" in mods and f"transformer_encoder_layers.{i}.ff.linear{k}" in mods
+               for i in range(6) for k in (1, 2))
+    assert mods["decoder.layers.3.ff.linear1"].weight.shape == (3072, 512)
+    twin = copy.deepcopy(m)
+    assert twin.engine is not m.engine and all(torch.equal(a, b) for a, b in zip(twin.state_dict().values(),
+                                                                                 m.state_dict().values()))
