@@ -108,9 +108,44 @@ class RunConfig:
     async_checkpoints: bool = False           # torch.save on a writer thread (checkpoint.AsyncCheckpointWriter)
 
 
+class TrainingConfig(RunConfig):
+    """What checkpoints pickle as their ``config`` entry.  The reference stores a pickled
+    ``kokoro.training.config.TrainingConfig`` INSTANCE there (trainer.py:1994-2031, registered as a safe global at
+    trainer.py:47) and its resume path reads attributes off it, so the class advertises that import path: a checkpoint
+    written here unpickles, in a reference environment, into the reference's own dataclass (pickle restores the attribute
+    dict onto it — same field names), and in an environment with the ``kokoro`` shim of this repository (shim/kokoro) into
+    this class."""
+
+
+TrainingConfig.__module__ = "kokoro.training.config"
+TrainingConfig.__qualname__ = "TrainingConfig"
+
+
+def _picklable_config(cfg: RunConfig):
+    """cfg as an instance of whatever ``kokoro.training.config.TrainingConfig`` is importable here — the shim's class
+    (= TrainingConfig above) or the reference's own dataclass when the reference package is installed.  The in-tree shim
+    directory is put on sys.path if nothing named ``kokoro`` is installed; a plain dict only if even that fails."""
+    import importlib
+    try:
+        mod = importlib.import_module("kokoro.training.config")
+    except ImportError:
+        shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shim")
+        if not os.path.isdir(os.path.join(shim, "kokoro")):
+            return dict(cfg.__dict__)
+        sys.path.append(shim)
+        try:
+            mod = importlib.import_module("kokoro.training.config")
+        except ImportError:
+            return dict(cfg.__dict__)
+    out = mod.TrainingConfig()
+    for k, v in cfg.__dict__.items():
+        setattr(out, k, v)
+    return out
+
+
 def create_config_from_args(args) -> RunConfig:
     """cli/cli.py:225-290."""
-    cfg = RunConfig(data_dir=args.corpus, output_dir=args.output, batch_size=args.batch_size, save_every=args.save_every,
+    cfg = TrainingConfig(data_dir=args.corpus, output_dir=args.output, batch_size=args.batch_size, save_every=args.save_every,
                     use_dynamic_batching=args.dynamic_batching,
                     max_frames_per_batch=args.max_frames if args.max_frames is not None else 30000,
                     min_batch_size=args.min_batch_size, max_batch_size=args.max_batch_size,
@@ -262,6 +297,9 @@ def resume(cfg: RunConfig, step, log: Callable[[str], None] = print) -> int:
     if hasattr(step, "opt"):
         from .checkpoint import load_optimizer_state_dict
         load_optimizer_state_dict(step.opt, ck.get("optimizer_state_dict"), log)
+        det = ck.get("grad_explosion_state")
+        if det and hasattr(step.opt, "write_detector_state"):
+            step.opt.write_detector_state(float(det["ema_norm"]), int(det["ema_steps"]))
     log(f"resumed from {path} (epoch {int(ck.get('epoch', -1)) + 1})")
     return int(ck.get("epoch", -1)) + 1
 
@@ -279,6 +317,9 @@ def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
     if cfg.async_checkpoints and rank == 0:
         from .checkpoint import AsyncCheckpointWriter
         writer = AsyncCheckpointWriter()
+    micro_batches_seen, skipped_seen = 0, 0
+    if hasattr(step, "opt") and hasattr(step.opt, "read_ctrl"):
+        skipped_seen = int(step.opt.read_ctrl()["skipped_total"])
     for epoch in range(start_epoch, cfg.num_epochs):
         random.seed(cfg.seed + epoch)                 # every rank builds the identical epoch batch list
         sampler = make_sampler(train_ds, cfg)
@@ -298,7 +339,16 @@ def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
                     step.engine.set_spec_augment(None)
                 dev_losses.append(step.micro_step(batch, first=(k == 0), last=(k == len(win) - 1),
                                                   divisor=len(win)).clone())
-        rec: Dict = {"epoch": epoch, "batches": len(batches)}
+        micro_batches_seen += len(batches)
+        rec: Dict = {"epoch": epoch, "batches": len(batches), "global_step": micro_batches_seen}
+        # steps the device-side non-finite guard skipped did not update the weights: the reference does not advance its
+        # LR schedule on such a step (trainer.py:2479-2482); the host schedule is rolled back here, once per epoch
+        if hasattr(step, "opt") and hasattr(step.opt, "read_ctrl") and hasattr(step.sched, "rewind"):
+            skipped = int(step.opt.read_ctrl()["skipped_total"])
+            if skipped > skipped_seen:
+                step.sched.rewind(skipped - skipped_seen)
+                log(f"epoch {epoch + 1}: {skipped - skipped_seen} optimizer step(s) skipped (non-finite gradients)")
+                skipped_seen = skipped
         if dev_losses:
             mean = torch.stack(dev_losses).mean(dim=0).cpu().tolist()          # one device read per epoch
             rec.update(train_loss=mean[0], train_mel=mean[1], train_dur=mean[2], train_stop=mean[3])
@@ -323,12 +373,46 @@ def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
                                                                   if isinstance(v, float)))
         if rank == 0 and cfg.save_every > 0 and (epoch + 1) % cfg.save_every == 0:
             saved.append(save_checkpoint(cfg, step, epoch, rec, best, best_epoch, writer))
+        if world > 1:
+            # rank 0 alone may just have written a checkpoint (hundreds of MB through torch.save): the others must not
+            # enter the next epoch's collective kernel and spin on it for the duration of one-sided host work
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.barrier(device_ids=[torch.cuda.current_device()] if torch.cuda.is_available() else None)
         if val_ds is not None and cfg.early_stopping_patience > 0 and since_best >= cfg.early_stopping_patience:
             log(f"early stopping after epoch {epoch + 1} (best val_loss {best:.4f} at epoch {best_epoch + 1})")
             break
     if writer is not None:
         writer.wait()                                 # every file is on disk (or the failure is raised) before returning
     return {"history": hist, "best_val_loss": best, "best_val_epoch": best_epoch, "checkpoints": saved}
+
+
+def _steps_completed(step) -> int:
+    opt = getattr(step, "opt", None)
+    if opt is not None and hasattr(opt, "read_ctrl"):
+        return int(opt.read_ctrl()["step"])
+    return int(step.sched.current_optimizer_step)
+
+
+def _scheduler_config(step) -> Dict:
+    """The hyper-parameters the schedule was built from (the reference stores OneCycleLR's constructor arguments under
+    this key and re-anchors on resume, checkpoint_manager.py:757-793)."""
+    sc = getattr(step.sched, "cfg", None)
+    out = dict(getattr(sc, "__dict__", {}) or {})
+    for k in ("base_lr", "max_lr", "warmup_steps", "onecycle_steps", "div_factor"):
+        if hasattr(step.sched, k):
+            out[k] = getattr(step.sched, k)
+    return out
+
+
+def _detector_state(step) -> Optional[Dict]:
+    """Gradient-explosion detector state (norm EMA + the number of norms it has seen, trainer.py:914-925), so that a
+    resumed run does not spend min_ema_steps steps without the EMA threshold."""
+    opt = getattr(step, "opt", None)
+    if opt is None or not hasattr(opt, "read_ctrl"):
+        return None
+    c = opt.read_ctrl()
+    return {"ema_norm": c["ema_norm"], "ema_steps": c["ema_steps"], "skipped_total": c["skipped_total"]}
 
 
 def save_checkpoint(cfg: RunConfig, step, epoch: int, rec: Dict, best: float, best_epoch: int, writer=None) -> str:
@@ -338,13 +422,19 @@ def save_checkpoint(cfg: RunConfig, step, epoch: int, rec: Dict, best: float, be
     ckpt = {"epoch": epoch, "model_state_dict": {k: v.detach().cpu() for k, v in step.state_dict().items()},
             "ema_model_state_dict": ({k: v.detach().cpu() for k, v in st.state_dict(st.ema).items()}
                                      if getattr(st, "ema", None) is not None else None),
+            # counters: scheduler calls made / optimizer steps that really updated the weights (device-side counter: a
+            # non-finite step is skipped on the device without a host sync) / micro-batches seen (trainer.py:1994-2031)
             "current_optimizer_step": step.sched.current_optimizer_step,
-            "optimizer_steps_completed": step.sched.current_optimizer_step,
+            "optimizer_steps_completed": _steps_completed(step),
+            "global_step": rec.get("global_step", step.sched.current_optimizer_step * max(1, cfg.gradient_accumulation_steps)),
+            "ema_updates": _steps_completed(step),
             "scheduler_state_dict": step.sched.state_dict(),
+            "scheduler_config": _scheduler_config(step),
+            "grad_explosion_state": _detector_state(step),
             "loss": rec.get("train_loss"), "train_loss": rec.get("train_loss"), "val_loss": rec.get("val_loss"),
             "val_mel_loss": rec.get("val_mel_loss"), "val_dur_loss": rec.get("val_dur_loss"),
             "val_stop_loss": rec.get("val_stop_loss"), "best_val_loss": best, "best_val_epoch": best_epoch,
-            "config": dict(cfg.__dict__)}
+            "config": _picklable_config(cfg)}
     if hasattr(step, "opt"):                          # Adam moments + step in torch.optim.AdamW.state_dict() form
         from .checkpoint import optimizer_state_dict
         ckpt["optimizer_state_dict"] = optimizer_state_dict(step.opt)

@@ -28,12 +28,10 @@ void kr_prefer_max_smem(const void* kernel) {
 }
 }  // namespace kr
 
-int kr_pdl_enabled() {
-  static int v = -1;
-  // measured: no gain inside CUDA graphs on B200 -> opt-in
-  if (v < 0) { const char* e = getenv("KR_PDL"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
-  return v;
-}
+// Programmatic dependent launch is always on: every kernel of the library starts with griddepcontrol.launch_dependents /
+// griddepcontrol.wait (kr_common.cuh), so the launch latency and prologue of kernel N+1 overlap the tail of kernel N.
+// Measured on B200 inside the step's CUDA graphs (round 2, bench shape): 6.67 ms vs 6.75 ms per step without it.
+int kr_pdl_enabled() { return 1; }
 
 extern "C" const char* kr_last_error(void) { return g_err; }
 // Kernels launched by this library since it was loaded (every launch site counts itself).

@@ -29,7 +29,7 @@
 
 void kr_set_error(const char* msg);
 void kr_count_launch();
-int kr_pdl_enabled();   // programmatic dependent launch: opt-in with env KR_PDL=1
+int kr_pdl_enabled();   // programmatic dependent launch (always on, see kr_api.cu)
 
 typedef __nv_bfloat16 bf16;
 

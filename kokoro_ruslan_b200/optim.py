@@ -232,6 +232,13 @@ class FusedAdamW:
                                   _ptr(self.t_wnmax), _ptr(self.wsq), _ptr(self.ctrl), _stream()), "kr_wn_project")
         s.refresh_conv_dgrad()
 
+    def write_detector_state(self, ema_norm: float, ema_steps: int) -> None:
+        """Restores the explosion detector's norm EMA (checkpoint resume)."""
+        raw = self.ctrl.cpu()
+        raw.view(torch.float32)[CTRL_FIELDS.index("ema_norm")] = float(ema_norm)
+        raw[CTRL_FIELDS.index("ema_steps")] = int(ema_steps)
+        self.ctrl.copy_(raw)
+
     def read_ctrl(self) -> Dict[str, float]:
         """Host copy of the device control block (synchronises; logging only)."""
         raw = self.ctrl.cpu()

@@ -112,6 +112,14 @@ class WarmupOneCycle:
             self.sched_step += 1
         self.current_optimizer_step += 1
 
+    def rewind(self, n: int) -> None:
+        """Un-does the last n advance() calls (optimizer steps the device-side guard skipped: the reference does not step
+        its scheduler on a skipped step, runtime_policies.py:81-85)."""
+        k = max(0, self.current_optimizer_step - max(0, int(n)))
+        self.current_optimizer_step, self.sched_step = 0, 0
+        for _ in range(k):
+            self.advance()
+
     def state_dict(self):
         return {"current_optimizer_step": self.current_optimizer_step, "sched_step": self.sched_step}
 

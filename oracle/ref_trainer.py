@@ -28,8 +28,15 @@ def reference_available() -> bool:
 
 
 def _import_reference():
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
+    # the repository's own `kokoro` shim (shim/kokoro: the B200 implementation behind the reference's import paths) may
+    # already be imported in this process; the harness wants the REFERENCE package
+    mod = sys.modules.get("kokoro")
+    if mod is not None and not os.path.abspath(getattr(mod, "__file__", "") or "").startswith(REF):
+        for k in [k for k in sys.modules if k == "kokoro" or k.startswith("kokoro.")]:
+            del sys.modules[k]
+    if REF in sys.path:
+        sys.path.remove(REF)
+    sys.path.insert(0, REF)
     import kokoro.training.trainer as rt
     from kokoro.training.config import TrainingConfig
     return rt, TrainingConfig

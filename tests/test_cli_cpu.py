@@ -256,7 +256,11 @@ def test_main_wires_configs_into_the_step(tmp_path, monkeypatch, capsys):
     assert (d.encoder, d.decoder, d.decoder_input, d.variance, d.stochastic_depth) == (0.15, 0.20, 0.15, 0.1, 0.1)
     ck = torch.load(os.path.join(str(tmp_path), "checkpoint_epoch_2.pth"), weights_only=False)
     assert ck["model_metadata"]["architecture"]["hidden_dim"] == 128
-    assert len(ck["optimizer_state_dict"]["param_groups"]) == 10 and ck["config"]["ema_half_life_epochs"] == 1.0
+    # `config` is a pickled kokoro.training.config.TrainingConfig instance like the reference's (trainer.py:1994-2031)
+    assert type(ck["config"]).__module__ == "kokoro.training.config" and type(ck["config"]).__name__ == "TrainingConfig"
+    for key in ("global_step", "ema_updates", "scheduler_config", "grad_explosion_state", "optimizer_steps_completed"):
+        assert key in ck, key
+    assert len(ck["optimizer_state_dict"]["param_groups"]) == 10 and ck["config"].ema_half_life_epochs == 1.0
 
 
 def test_async_checkpoints_are_complete_when_train_returns(tmp_path):
@@ -271,3 +275,48 @@ def test_async_checkpoints_are_complete_when_train_returns(tmp_path):
     for n in names:
         ck = torch.load(os.path.join(str(tmp_path), n), weights_only=False)
         assert "model_state_dict" in ck and not os.path.exists(os.path.join(str(tmp_path), n + ".tmp"))
+
+
+def test_kokoro_shim_import_paths_and_console_script():
+    """the reference's import paths and console script exist (shim/kokoro + pyproject.toml), resolve to the
+    B200 implementation, and the checkpoint `config` pickles as kokoro.training.config.TrainingConfig.  Run in a fresh
+    interpreter: this process may hold the REFERENCE's kokoro package (oracle harness)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, pickle; sys.path[:0] = [%r, %r]\n"
+        "import kokoro.cli.training as t, kokoro.cli.cli as c, kokoro.training.config as cfg\n"
+        "import kokoro.data.dataset as d, kokoro.utils.lengths as l\n"
+        "from kokoro_ruslan_b200 import cli, data, lengths\n"
+        "assert t.main is cli.main and c.build_parser is cli.build_parser\n"
+        "assert cfg.TrainingConfig is cli.TrainingConfig and d.collate_fn is data.collate_fn\n"
+        "assert d.DynamicFrameBatchSampler is data.DynamicFrameBatchSampler and l.length_regulate is lengths.length_regulate\n"
+        "conf = cli.create_config_from_args(cli.build_parser().parse_args(['--epochs', '3']))\n"
+        "back = pickle.loads(pickle.dumps(cli._picklable_config(conf)))\n"
+        "assert type(back) is cfg.TrainingConfig and back.num_epochs == 3\n"
+        "print('ok')\n" % (root, os.path.join(root, "shim")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]
+    py = open(os.path.join(root, "pyproject.toml")).read()
+    assert 'kokoro-train = "kokoro.cli.training:main"' in py
+    # the model / vocoder modules import the CUDA-side packages lazily enough to be importable without a device
+    code2 = ("import sys; sys.path[:0] = [%r, %r]\n"
+             "import kokoro.model.model as m, kokoro.inference.hifigan_vocoder as h\n"
+             "from kokoro_ruslan_b200.model import KokoroModel\n"
+             "assert m.KokoroModel is KokoroModel and hasattr(h, 'HiFiGANGenerator') and hasattr(h, 'load_hifigan_model')\n"
+             "print('ok')\n" % (root, os.path.join(root, "shim")))
+    r = subprocess.run([sys.executable, "-c", code2], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]
+
+
+def test_schedule_rewind_undoes_skipped_steps():
+    from kokoro_ruslan_b200.train_step import ScheduleConfig, WarmupOneCycle
+    a = WarmupOneCycle(1e-3, [1.0, 0.5], ScheduleConfig(total_steps=50, warmup_steps=5))
+    b = WarmupOneCycle(1e-3, [1.0, 0.5], ScheduleConfig(total_steps=50, warmup_steps=5))
+    for _ in range(12):
+        a.advance()
+    for _ in range(9):
+        b.advance()
+    a.rewind(3)
+    assert a.state_dict() == b.state_dict() and a.lrs() == b.lrs()

@@ -42,8 +42,8 @@ def _live_reference_outputs(ocfg, sd, batch):
     """(fp32 outputs, bf16-autocast outputs) of the unmodified reference KokoroModel on the GPU, or None."""
     if not os.path.isdir(os.path.join(REF, "kokoro")):
         return None
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
+    from oracle.ref_trainer import _import_reference
+    _import_reference()                                  # puts baseline/_ref first (and evicts the repo's own kokoro shim)
     import logging
     logging.getLogger("kokoro").setLevel(logging.ERROR)
     from kokoro.model.model import KokoroModel
