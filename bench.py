@@ -535,8 +535,10 @@ def run_ours(args):
 
     comm = None
     if world > 1:
-        comm = "fused all-reduce + grad-norm + global-clip kernel over symmetric memory (%s)" % (
-            "NVSwitch multicast" if ts.reducer.multicast else "peer loads/stores")
+        comm = "fused all-reduce + grad-norm + global-clip kernel over symmetric memory (%s; %s)" % (
+            "NVSwitch multicast" if ts.reducer.multicast else "peer loads/stores",
+            ("early gradient ranges reduced underneath the backward after decoder layers %s" % ts.split_layer)
+            if ts.split_layer is not None else "one launch after the backward")
     line = {"metric": METRIC, "value": frames_per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",

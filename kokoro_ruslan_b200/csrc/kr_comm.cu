@@ -32,6 +32,10 @@ struct ArParams {
   const long long* chunk_start;
   const int* chunk_len;
   int n_chunks, rank, world;
+  // the chunks this launch reduces: two half-open chunk-index ranges (the step reduces the gradient ranges that are final
+  // half-way through the backward pass from a side stream underneath the rest of it, and the remainder afterwards);
+  // virtual index v = position in the concatenation of the two ranges, owned by rank v % world
+  int r0_begin, r0_len, r1_begin, r1_len;
   // the step's clip norm is a GLOBAL decision: slot [n_chunks + r] of rank r's sq buffer carries rank r's adaptive clip
   // (long-utterance stabiliser, trainer.py:2218-2255, computed from ITS batch); every rank takes the minimum over all
   // slots, so the replicas apply the same clip coefficient and stay bit-identical
@@ -135,13 +139,16 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_sqnorm_kernel(const ArPa
     *p.clip_out = c;
   }
   const int stride = p.world * (int)gridDim.x;
-  int c = p.rank + p.world * (int)blockIdx.x;
+  const int n_virtual = p.r0_len + p.r1_len;
+  auto chunk_of = [&](int vi) { return vi < p.r0_len ? p.r0_begin + vi : p.r1_begin + (vi - p.r0_len); };
+  int vi = p.rank + p.world * (int)blockIdx.x;
   float4 v[4], vn[4];
-  if (c < p.n_chunks) ar_load_chunk(p, c, vn);
-  for (; c < p.n_chunks; c += stride) {
+  if (vi < n_virtual) ar_load_chunk(p, chunk_of(vi), vn);
+  for (; vi < n_virtual; vi += stride) {
+    const int c = chunk_of(vi);
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = vn[k];
-    if (c + stride < p.n_chunks) ar_load_chunk(p, c + stride, vn);   // next chunk's loads fly under this chunk's stores
+    if (vi + stride < n_virtual) ar_load_chunk(p, chunk_of(vi + stride), vn);   // next chunk's loads fly under this chunk's stores
     const long long off = p.chunk_start[c];
     const int n4 = (p.chunk_len[c] + 3) >> 2;
     float s = 0.f;
@@ -212,8 +219,9 @@ __global__ void chunk_to_tensor_kernel(const float* __restrict__ sq_chunk, const
 
 extern "C" int kr_allreduce_sqnorm(void* mc_grads, void* mc_sq, void* const* grads, void* const* sq,
                                    void* const* flags, int rank, int world, const long long* chunk_start,
-                                   const int* chunk_len, int n_chunks, int grid, const float* clip_local,
-                                   float* clip_out, double watchdog_seconds, int* error_flag, void* stream) {
+                                   const int* chunk_len, int n_chunks, const int* chunk_ranges, int grid,
+                                   const float* clip_local, float* clip_out, double watchdog_seconds, int* error_flag,
+                                   void* stream) {
   if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world) { kr_set_error("kr_allreduce_sqnorm: world must be 1..8"); return KR_ERR_ARG; }
   if (grid < 1 || n_chunks <= 0) { kr_set_error("kr_allreduce_sqnorm: empty problem"); return KR_ERR_ARG; }
   ArParams p{};
@@ -225,6 +233,16 @@ extern "C" int kr_allreduce_sqnorm(void* mc_grads, void* mc_sq, void* const* gra
     p.flags[q] = reinterpret_cast<unsigned*>(flags[q]);
   }
   p.chunk_start = chunk_start; p.chunk_len = chunk_len; p.n_chunks = n_chunks; p.rank = rank; p.world = world;
+  // chunk_ranges (HOST array {begin0, end0, begin1, end1}, may be NULL = all chunks)
+  p.r0_begin = 0; p.r0_len = n_chunks; p.r1_begin = 0; p.r1_len = 0;
+  if (chunk_ranges != nullptr) {
+    p.r0_begin = chunk_ranges[0]; p.r0_len = chunk_ranges[1] - chunk_ranges[0];
+    p.r1_begin = chunk_ranges[2]; p.r1_len = chunk_ranges[3] - chunk_ranges[2];
+    if (p.r0_begin < 0 || p.r0_len < 0 || p.r1_begin < 0 || p.r1_len < 0 || p.r0_begin + p.r0_len > n_chunks ||
+        p.r1_begin + p.r1_len > n_chunks || p.r0_len + p.r1_len == 0) {
+      kr_set_error("kr_allreduce_sqnorm: bad chunk ranges"); return KR_ERR_ARG;
+    }
+  }
   if ((clip_local == nullptr) != (clip_out == nullptr)) { kr_set_error("kr_allreduce_sqnorm: clip_local and clip_out go together"); return KR_ERR_ARG; }
   p.clip_local = clip_local; p.clip_out = clip_out; p.error_flag = error_flag;
   // seconds -> SM cycles at a nominal 2 GHz (the limit only has to be generous: rank skew from one-sided host work)

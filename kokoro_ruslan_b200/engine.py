@@ -124,7 +124,10 @@ class AcousticEngine:
         if os.environ.get("KR_STREAMS", "1") == "0":
             multi_stream = False
         self.multi_stream = multi_stream
-        self._side = {k: torch.cuda.Stream(device=self.device) for k in ("w0", "w1", "vp", "enc", "kv", "d0")} if multi_stream else {}
+        self._side = {k: torch.cuda.Stream(device=self.device) for k in ("w0", "w1", "vp", "enc", "kv", "d0", "comm")} if multi_stream else {}
+        # data parallel: callable(split_layer) that all-reduces early_grad_ranges(split_layer); backward_parts() runs it on
+        # the "comm" side stream once those ranges are final, underneath the rest of the backward (TrainStep installs it)
+        self.early_reduce_hook = None
         self._w_rr = 0
         self._forked: List[torch.cuda.Stream] = []
         # every tensor of a step stays referenced until the next step starts: memory is never
@@ -707,10 +710,12 @@ class AcousticEngine:
         b = st.entries[f"decoder.layers.{split_layer}.self_attn.w_q.weight"].offset
         return [(0, a), (b, st.total)]
 
-    def backward_parts(self, ctx: dict, g: dict, split_layer: Optional[int]):
-        """Backward as a generator that yields ONCE (when split_layer is not None), after the encoder, the
-        predictors, the heads and decoder layers n-1 .. split_layer are done and every side stream has been
-        joined: the data-parallel step all-reduces early_grad_ranges() underneath the rest of the backward."""
+    def backward_parts(self, ctx: dict, g: dict, split_layer):
+        """Backward pass.  split_layer (an int or a list of decoder layer indices, None = off): after the backward of each
+        listed decoder layer, `early_reduce_hook(layer)` runs on the "comm" side stream, which first waits for everything
+        enqueued so far on every stream — the data-parallel step all-reduces the gradient ranges that are final at that
+        point (early_grad_ranges) underneath the rest of the backward.  Without a hook the generator joins all streams
+        and yields there instead."""
         cfg, st, D = self.cfg, self.store, self.D
         B, P, T, Tp = ctx["B"], ctx["P"], ctx["T"], ctx["Tp"]
         Ne, Nd = B * P, B * T
@@ -764,9 +769,24 @@ class AcousticEngine:
             dy, dy_bf = self._attn_bwd(pre + "self_attn.", dy, dy_bf, B, T, pre + "norm1.", True, ctx["mel_pad"], None, T,
                                        s1, None, False, next_drop=ctx["drop_in"] if i == 0 else None,
                                        next_dbias=st.g("mel_projection_in.bias") if i == 0 else None, bias_done=True)
-            if split_layer is not None and i == split_layer and i > 0:
-                self._join_all()
-                yield
+            if split_layer is not None and i > 0 and (i == split_layer or (isinstance(split_layer, (list, tuple))
+                                                                           and i in split_layer)):
+                if self.early_reduce_hook is not None and self.multi_stream:
+                    # everything in early_grad_ranges(split_layer) has been ENQUEUED by now (encoder / predictor backward
+                    # on their streams, weight gradients of layers >= split_layer on w0 / w1 / kv): the comm stream waits
+                    # for exactly that work, the main chain goes on with the lower decoder layers without waiting
+                    comm = self._side["comm"]
+                    cur = torch.cuda.current_stream(self.device)
+                    comm.wait_stream(cur)
+                    for name in ("enc", "vp", "w0", "w1", "kv"):
+                        comm.wait_stream(self._side[name])
+                    if comm not in self._forked:
+                        self._forked.append(comm)
+                    with torch.cuda.stream(comm):
+                        self.early_reduce_hook(i)
+                else:
+                    self._join_all()
+                    yield
         self._wgrad(dy_bf, ctx["melshift"], st.g("mel_projection_in.weight"), None)   # bias: layer 0's layernorm_bwd
         self._join_all()
         # memory gradient (accumulated on the "kv" stream) reaches only the pitch / energy embedding rows

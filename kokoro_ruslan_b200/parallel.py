@@ -106,8 +106,11 @@ class SymmetricGradReducer:
         self.watchdog_seconds = float(os.environ.get("KR_COMM_WATCHDOG_S", "300"))
         dist.barrier(group=group, device_ids=[dev.index])
 
-    def reduce(self, clip_local: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    def reduce(self, clip_local: Optional[torch.Tensor] = None, chunk_ranges: Optional[Tuple[int, int, int, int]] = None,
+               grid: Optional[int] = None) -> Optional[torch.Tensor]:
         """All ranks' gradients -> their sum on every rank, plus the per-chunk squared sums of the reduced buffer.
+        ``chunk_ranges`` = (begin0, end0, begin1, end1): only these two chunk-index ranges (the step reduces what is final
+        half-way through the backward pass underneath the rest of it); None = everything.
         ``clip_local`` (device scalar): this rank's clip norm for the step; returns the device scalar holding the MINIMUM
         over all ranks (the clip every replica must apply — a per-rank clip would let the replicas diverge when one rank
         draws a long utterance and the stabiliser of trainer.py:2218-2255 tightens only its clip)."""
@@ -117,7 +120,9 @@ class SymmetricGradReducer:
         rc = lib().kr_allreduce_sqnorm(ctypes.c_void_p(self._mc[0]), ctypes.c_void_p(self._mc[1]), self._ptrs[0],
                                        self._ptrs[1], self._ptrs[2], ctypes.c_int(self.rank), ctypes.c_int(self.world),
                                        ctypes.c_void_p(opt.chunk_start.data_ptr()), ctypes.c_void_p(opt.chunk_len.data_ptr()),
-                                       ctypes.c_int(opt.n_chunks), ctypes.c_int(self.GRID),
+                                       ctypes.c_int(opt.n_chunks),
+                                       (ctypes.c_int * 4)(*chunk_ranges) if chunk_ranges is not None else None,
+                                       ctypes.c_int(grid or self.GRID),
                                        ctypes.c_void_p(clip_local.data_ptr() if clip_local is not None else None),
                                        ctypes.c_void_p(self.clip_global.data_ptr() if clip_local is not None else None),
                                        ctypes.c_double(self.watchdog_seconds), ctypes.c_void_p(self.error_flag.data_ptr()),

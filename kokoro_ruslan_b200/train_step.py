@@ -166,11 +166,12 @@ class _Staged:
     dev: Dict[str, torch.Tensor]
     # one graph per variant: index 1 = zero the gradient buffer first (start of an accumulation window),
     # index 0 = accumulate onto it
-    graph: List[Optional[torch.cuda.CUDAGraph]] = field(default_factory=lambda: [None, None])
-    graph_losses: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
+    # (index bit 1 = the closing micro-batch of a data-parallel window: the early all-reduce is part of the graph)
+    graph: List[Optional[torch.cuda.CUDAGraph]] = field(default_factory=lambda: [None] * 4)
+    graph_losses: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None] * 4)
     losses: Optional[torch.Tensor] = None
     launches: int = 0
-    warm: List[int] = field(default_factory=lambda: [0, 0])
+    warm: List[int] = field(default_factory=lambda: [0] * 4)
     last_used: int = 0
 
 
@@ -203,6 +204,32 @@ class TrainStep:
                                    "between all ranks of the node); it is not available on this box")
             self.reducer = SymmetricGradReducer(self.engine.store, self.opt, process_group)
             self.comm = "fused"
+            # overlap: the gradient ranges that are final once the backward has passed decoder layer `split_layer`
+            # (embeddings + encoder + predictors at the front of the flat buffer, the upper decoder layers + heads at its
+            # tail: ~72 % of the bytes) are reduced from the engine's "comm" side stream underneath the lower decoder
+            # layers, by a small grid that shares the SMs with the backward kernels; the rest follows graph A
+            n_dec = self.engine.cfg.n_decoder_layers
+            # measured (round 2, bench shape): 8 GPUs / multicast 6.79 -> 6.55 ms per step with a 32-block early launch
+            # (16 and 64 blocks: 6.60); 2 GPUs / peer loads 6.74 -> 7.03 ms (the latency-bound peer path needs ~4 blocks per
+            # SM and then takes the SMs away from the backward), so the overlap is used on the multicast path only
+            if n_dec >= 2 and self.engine.multi_stream and self.reducer.multicast:
+                # two early launches: after decoder layer n/2 (embeddings + encoder + predictors + upper decoder layers +
+                # heads, ~72 % of the bytes) and after layer 1 (the layers in between); layer 0, mel_projection_in and the
+                # pitch / energy embedding rows (~10 %) follow graph A together with the global clip
+                splits = sorted({n_dec // 2, 1}, reverse=True) if n_dec >= 4 else [n_dec // 2]
+                starts = self.opt.chunk_start.cpu().tolist()
+                ent = self.engine.store.entries
+                ca = starts.index(ent["duration_adaptor.variance_adaptor.pitch_embedding.weight"].offset)
+                hi = self.opt.n_chunks
+                self._early_ranges = {}
+                for k, layer in enumerate(splits):
+                    cb = starts.index(ent[f"decoder.layers.{layer}.self_attn.w_q.weight"].offset)
+                    self._early_ranges[layer] = (0, ca, cb, hi) if k == 0 else (cb, hi, 0, 0)
+                    hi = cb
+                self._late_ranges = (ca, hi, 0, 0)
+                self.split_layer = splits
+                self._early_on = False
+                self.engine.early_reduce_hook = self._early_reduce
         self.max_seq_cap = max_seq_cap
         # every cached batch shape pins its static input buffers and (once captured) a graph with ~4 GB of
         # activations at the bench shape: dynamic batching produces many shapes, so the cache is LRU-bounded
@@ -310,7 +337,14 @@ class TrainStep:
                                d["pitches"], d["energies"], d["mel_lengths"], d["phoneme_lengths"],
                                loss_scale=self.loss_scale)
         out.append(losses)
-        yield from eng.backward_parts(ctx, g, self.split_layer)
+        yield from eng.backward_parts(ctx, g, self.split_layer if getattr(self, "_early_on", False) else None)
+
+    EARLY_GRID = 32      # blocks of the overlapped all-reduce: small enough to share the SMs with the backward kernels
+
+    def _early_reduce(self, split_layer: int) -> None:
+        """engine.early_reduce_hook: runs on the comm side stream (inside graph A when graphs are on)."""
+        if self._early_on:
+            self.reducer.reduce(chunk_ranges=self._early_ranges[split_layer], grid=self.EARLY_GRID)
 
     def _fwd_bwd(self, d: Dict[str, torch.Tensor], Tp: int, zero: bool = True) -> torch.Tensor:
         out: list = []
@@ -318,9 +352,10 @@ class TrainStep:
             pass
         return out[0]
 
-    def _run_fwd_bwd(self, st: _Staged, key, zero: bool = True) -> torch.Tensor:
+    def _run_fwd_bwd(self, st: _Staged, key, zero: bool = True, early: bool = False) -> torch.Tensor:
         Tp = key[3]
-        v = int(zero)
+        self._early_on = bool(early) and self.split_layer is not None
+        v = int(zero) + 2 * int(self._early_on)
         if not self.use_graphs:
             n0 = launch_count()
             losses = self._fwd_bwd(st.dev, Tp, zero)
@@ -375,11 +410,13 @@ class TrainStep:
         st, key = self.stage(batch, divisor)
         if last:
             self.opt.set_lrs(self.sched.lrs())
-        losses = self._run_fwd_bwd(st, key, zero=first)
+        losses = self._run_fwd_bwd(st, key, zero=first, early=(last and self.world > 1))
         self.launches_last_step = st.launches
         if last:
             if self.world > 1:
-                self.reducer.reduce(clip_local=self.clip)
+                # what the overlapped launch did not cover (everything, without the overlap) + the global clip
+                self.reducer.reduce(clip_local=self.clip,
+                                    chunk_ranges=self._late_ranges if self.split_layer is not None else None)
             self._run_optimizer()
             self.sched.advance()
             self.launches_last_step += self._opt_launches + (1 if self.world > 1 else 0)

@@ -50,6 +50,9 @@ def main():
         ts = TrainStep(cfg, OptimConfig(learning_rate=1e-3), sched, device=dev, use_graphs=graphs,
                        process_group=dist.group.WORLD)
         ts.store.init_default(seed=0)          # identical weights on every rank
+        if rank == 0:
+            print(f"graphs={graphs}: multicast={ts.reducer.multicast}, overlapped early launches after decoder layers "
+                  f"{ts.split_layer}")
         mine = [ts.train_step(batches[rank]).cpu() for _ in range(4)]
         torch.cuda.synchronize()
         w_dp = ts.store.params.clone()

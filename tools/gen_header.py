@@ -80,7 +80,7 @@ DOCS = {
     "kr_drop_begin": "Once per training forward: state[1] += 1 (new dropout step) and table[s, b] = stochastic-depth factor of residual branch s for sample b (0 with probability path_p[s], else 1/(1-p)): drop_path of model/transformers.py:16-40 with the per-layer rates of model/model.py:99-107.",
     "kr_dec_in_drop": "Decoder input y = drop_b(drop_a(t) + PE[row % T]) for t = mel_projection_in(shifted mel): F.dropout(p = decoder_input_dropout) then PositionalEncoding's own dropout, model/model.py:525-531, model/positional_encoding.py:72-74. scale_a = 1/keep_a; drop->scale = 1/(keep_a*keep_b).",
     "kr_drop_export_mask": "Test aid: out[r*cols + c] = keep(element r*ld + c) of one dropout site as bytes, so a CPU oracle can apply exactly the masks the fused kernels regenerate.",
-    "kr_allreduce_sqnorm": "Data-parallel gradient all-reduce FUSED with the optimizer's squared-norm pass, over symmetric memory (NVSwitch multicast multimem.ld_reduce / multimem.st when mc_grads != NULL, else peer loads / stores): chunk c is reduced by rank c % world, broadcast, and its squared sum written to sq[.][c] on every rank. grads / sq / flags are HOST arrays of `world` device pointers (each rank's buffers as mapped into this process); flags = zero-initialised unsigned [grid * world] per rank. New functionality (the reference is single-process); replaces the per-parameter norm loop of training/trainer.py:2355-2362 on the reduced buffer.",
+    "kr_allreduce_sqnorm": "Data-parallel gradient all-reduce FUSED with the optimizer's squared-norm pass, over symmetric memory (NVSwitch multicast multimem.ld_reduce / multimem.st when mc_grads != NULL, else peer loads / stores): chunk c is reduced by rank c % world, broadcast, and its squared sum written to sq[.][c] on every rank. grads / sq / flags are HOST arrays of `world` device pointers (each rank's buffers as mapped into this process); flags = zero-initialised unsigned [grid * world] per rank. chunk_ranges = HOST {begin0, end0, begin1, end1} chunk-index ranges to reduce (NULL = all): the step reduces the ranges that are final half-way through the backward from a side stream underneath the rest of it. clip_local / clip_out (device scalars, both or neither): this rank's clip norm for the step in, the minimum over all ranks out (slot n_chunks + rank of the sq buffers carries it, so they hold n_chunks + world floats). New functionality (the reference is single-process); replaces the per-parameter norm loop of training/trainer.py:2355-2362 on the reduced buffer.",
     "kr_chunk_sqnorm": "Per-chunk squared sums of the flat gradient buffer (single-GPU first optimizer phase; deterministic, no atomics).",
     "kr_chunk_to_tensor_sq": "sq[t] = sum over the chunks of tensor t in chunk order (first_chunk[n_tensors + 1]); raises the control block's non-finite flag (training/trainer.py:1308-1313).",
     "kr_conv_dgrad_shadow": "bf16 tap-reversed transpose of a tap-major conv weight: the B operand of the conv data-gradient GEMM.",
