@@ -481,7 +481,7 @@ def run_ours(args):
                        "timed one by one with an event pair each in an eager pass (adds ~3 us to every ~15 us launch); "
                        "share_of_step from the eager pass" % replay_n}
         top_ops = [{"op": r["op"], "n": r["launches"], "ms": round(r["ms"], 4), "share": round(r["share"], 4),
-                    "tflops": round(r["tflops"], 1), "gbs": round(r["gbs"], 1)} for r in rows[:14]]
+                    "tflops": round(r["tflops"], 1), "gbs": round(r["gbs"], 1)} for r in rows[:48]]
     except Exception as exc:  # the bench line must still be printed
         roof = {"bound": "tensor", "error": repr(exc)}
 

@@ -36,7 +36,7 @@ int kr_pdl_enabled() { return 1; }
 extern "C" const char* kr_last_error(void) { return g_err; }
 // Kernels launched by this library since it was loaded (every launch site counts itself).
 extern "C" long long kr_launch_count(void) { return (long long)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
-extern "C" int kr_abi_version(void) { return 2; }
+extern "C" int kr_abi_version(void) { return 3; }
 
 // Device sanity probe: returns the compute capability major*10+minor of the current device, or <0.
 extern "C" int kr_device_cc(void) {

@@ -117,7 +117,7 @@ def test_c_abi_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, missing
     lib.kr_abi_version.restype = ctypes.c_int
-    assert lib.kr_abi_version() == 2
+    assert lib.kr_abi_version() == 3
 
 
 def test_ops_refuse_cpu_tensors():

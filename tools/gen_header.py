@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 DOCS = {
     "kr_last_error": "Thread-local message of the last failing call (every entry point returns 0 or a negative KR_ERR_* code; the Python side maps non-zero to RuntimeError, which the reference trainer's per-batch handler expects: training/trainer.py:2679-2686).",
-    "kr_abi_version": "ABI version of this header (2: dropout specs).",
+    "kr_abi_version": "ABI version of this header (3: kr_allreduce_sqnorm chunk ranges / global clip / watchdog).",
     "kr_launch_count": "Number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches evidence).",
     "kr_memset_zero": "Asynchronous zero fill (memset node under graph capture) — replaces the torch fill kernels for gradient / scratch buffers.",
     "kr_device_cc": "Compute capability (major*10+minor) of the current device; 100 on B200.",
