@@ -182,7 +182,9 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     mbar_init(bres_bar, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], EPI_WARPS);   // one arrive per epilogue warp
+      // one arrive per epilogue warp that works on the buffer: all 8, or — narrow outputs, see the epilogue — the 4 of
+      // the warp set that owns it
+      mbar_init(&tmem_empty_bar[s], p.N <= 32 ? EPI_WARPS / 2 : EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -342,8 +344,14 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int ccol = (lane & 7) * 4;     // ... columns [ccol, ccol + 4) of the chunk
     const bool vec_ok = ((p.N & 3) == 0) && ((p.ldc & 3) == 0) && ((p.ldr & 3) == 0) && ((p.ldr2 & 3) == 0) &&
                         ((p.ldc2 & 3) == 0);
+    // Narrow outputs (N <= 32: the 32-channel HiFi-GAN stage): a tile has ONE 32-column chunk, which would leave the
+    // second warp of every lane group idle while the first runs a latency chain (TMEM load, smem transpose, global
+    // stores) per tile.  The two warp sets then alternate TILES instead of column chunks: set h owns accumulator
+    // buffer h (= tiles with lt % 2 == h), so two tiles' epilogues are in flight per CTA.
+    const bool tile_alt = p.N <= 32;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      if (tile_alt && (lt & 1) != half) continue;
       const TileCoord tc = decode_tile(p, tile);
       const int mw0 = tc.m_blk * BLOCK_M + lg * 32;   // first row of this warp's 32-row slab
       const int n0 = tc.n_blk * BLOCK_N;
@@ -364,7 +372,7 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int i = 0; i < 8; ++i) rowf[i] = drop_row_scale(p.drop, min(mw0 + (lane >> 3) + 4 * i, p.M - 1));
       }
 #pragma unroll 1
-      for (int c = half; c < BLOCK_N / 32; c += 2) {
+      for (int c = tile_alt ? 0 : half; c < BLOCK_N / 32; c += 2) {
         const int nb = n0 + c * 32;
         if (nb >= p.N) break;                          // warp-uniform
         // The epilogue is ISSUE-bound for the short-K GEMMs / convs of this model (it was ~870 warp instructions
