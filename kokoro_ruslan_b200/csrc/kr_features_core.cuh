@@ -228,15 +228,18 @@ KRF_DEV int digit_reverse4(int k, int log4n) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Log-mel frame on the radix-4 transform (opt-in variant of kr_mel_stft, KR_MELSTFT_R4=1; the radix-2 Stockham kernel in
-// kr_melstft.cu is the hardware-validated default): reflect pad 512, periodic Hann 1024, 1024-point FFT (5 radix-4 stages
+// Log-mel frame on the radix-4 transform (kr_mel_stft): reflect pad 512, periodic Hann 1024, 1024-point FFT (5 radix-4 stages
 // instead of 10 radix-2 ones), |X|^2 of the 513 one-sided bins read through the digit reversal, HTK filterbank (one warp
 // per filter), log.  Reference data/dataset.py:162-178, 694-697.  Shared memory: z[1024], qw[257], pw[513].
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int MEL_NFFT = 1024, MEL_LOG4 = 5, MEL_BINS = MEL_NFFT / 2 + 1;
 
-KRF_DEV void mel_frame_body(const float* x, long long n, int f, float gain, const float* fb_t, int n_mels,
-                            long long out_stride, float log_eps, krf_float2* z, krf_float2* qw, float* pw, float* orow) {
+// fb_ranges (optional, [n_mels][2] = first non-zero bin, one past the last): the HTK filters are triangles, i.e. ~13 of
+// the 513 weights of a row are non-zero on average; the dense dot products were 40 % of the frame's work.  A lane keeps
+// the bins it has in the dense loop (bin % 32 == lane), so skipping exact zeros leaves every partial sum bit-identical.
+KRF_DEV void mel_frame_body(const float* x, long long n, int f, float gain, const float* fb_t, const int* fb_ranges,
+                            int n_mels, long long out_stride, float log_eps, krf_float2* z, krf_float2* qw, float* pw,
+                            float* orow) {
   const int tid = KRF_TID, nt = KRF_NT;
   fft4_fill_twiddles(qw, MEL_NFFT);
   for (int i = tid; i < MEL_NFFT; i += nt) {
@@ -257,7 +260,10 @@ KRF_DEV void mel_frame_body(const float* x, long long n, int f, float gain, cons
   for (int m = KRF_WARP; m < n_mels; m += KRF_NWARPS) {
     const float* frow = fb_t + (long long)m * MEL_BINS;
     float acc = 0.f;
-    for (int i = KRF_LANE; i < MEL_BINS; i += KRF_NLANES) acc = fmaf(pw[i], krf_ldg(frow + i), acc);
+    int lo = 0, hi = MEL_BINS;
+    if (fb_ranges != nullptr) { lo = fb_ranges[2 * m]; hi = fb_ranges[2 * m + 1]; }
+    for (int i = (lo / KRF_NLANES) * KRF_NLANES + KRF_LANE; i < hi; i += KRF_NLANES)
+      if (i >= lo) acc = fmaf(pw[i], krf_ldg(frow + i), acc);
     acc = krf_warp_sum(acc);
     if (KRF_LANE == 0) orow[(long long)m * out_stride] = logf(acc + log_eps);
   }

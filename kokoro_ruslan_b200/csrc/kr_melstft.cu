@@ -42,8 +42,8 @@ __global__ void wave_peak_kernel(const float* __restrict__ wav, const long long*
 // Measured on B200 (round 2, 8 x 800 frames): 174.7 us against 186.8 us for the radix-2 Stockham kernel it replaced.
 __global__ void __launch_bounds__(THREADS)
 mel_stft_kernel(const float* __restrict__ wav, const long long* __restrict__ lengths, const float* __restrict__ peak,
-                   const float* __restrict__ fb_t, float* __restrict__ out, long long n_max, int frames_max, int n_mels,
-                   float log_eps) {
+                const float* __restrict__ fb_t, const int* __restrict__ fb_ranges, float* __restrict__ out, long long n_max,
+                int frames_max, int n_mels, float log_eps) {
   kr::pdl_entry();
   __shared__ float2 z[krf::MEL_NFFT];
   __shared__ float2 qw[krf::MEL_NFFT / 4 + 1];
@@ -56,7 +56,7 @@ mel_stft_kernel(const float* __restrict__ wav, const long long* __restrict__ len
     return;
   }
   const float gain = peak != nullptr ? 1.f / (peak[b] + 1e-9f) : 1.f;
-  krf::mel_frame_body(wav + (long long)b * n_max, n, f, gain, fb_t, n_mels, frames_max, log_eps, z, qw, pw, orow);
+  krf::mel_frame_body(wav + (long long)b * n_max, n, f, gain, fb_t, fb_ranges, n_mels, frames_max, log_eps, z, qw, pw, orow);
 }
 
 }  // namespace
@@ -72,14 +72,14 @@ extern "C" int kr_wave_peak(const float* wav, const long long* lengths, float* p
   return KR_OK;
 }
 
-extern "C" int kr_mel_stft(const float* wav, const long long* lengths, const float* peak, const float* fb_t, float* out,
-                           int B, long long n_max, int frames_max, int n_mels, int n_fft, int hop, float log_eps,
-                           void* stream) {
+extern "C" int kr_mel_stft(const float* wav, const long long* lengths, const float* peak, const float* fb_t,
+                           const int* fb_ranges, float* out, int B, long long n_max, int frames_max, int n_mels, int n_fft,
+                           int hop, float log_eps, void* stream) {
   if (n_fft != NFFT || hop != HOP) { kr_set_error("kr_mel_stft: built for n_fft 1024 / hop 256"); return KR_ERR_UNSUPPORTED; }
   if (B <= 0 || frames_max <= 0) return KR_OK;
   if (n_max < NFFT / 2 + 1) { kr_set_error("kr_mel_stft: waveform shorter than the reflect padding"); return KR_ERR_ARG; }
-  kr::launch(mel_stft_kernel, dim3(frames_max, B), THREADS, 0, (cudaStream_t)stream, wav, lengths, peak, fb_t, out,
-             n_max, frames_max, n_mels, log_eps);
+  kr::launch(mel_stft_kernel, dim3(frames_max, B), THREADS, 0, (cudaStream_t)stream, wav, lengths, peak, fb_t, fb_ranges,
+             out, n_max, frames_max, n_mels, log_eps);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

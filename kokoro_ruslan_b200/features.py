@@ -47,6 +47,11 @@ class LogMelSpectrogram:
         self.device = torch.device(device)
         fb = mel_filterbank_htk(n_fft // 2 + 1, f_min, f_max, n_mels, sample_rate)
         self.fb_t = fb.t().contiguous().to(self.device)            # [n_mels, 513]
+        # the filters are triangles: [first non-zero bin, one past the last) per mel row — the kernel skips the exact zeros
+        nz = fb.t() != 0
+        first = torch.where(nz.any(dim=1), nz.float().argmax(dim=1), torch.zeros(n_mels, dtype=torch.long))
+        last = torch.where(nz.any(dim=1), nz.shape[1] - nz.flip(1).float().argmax(dim=1), torch.zeros(n_mels, dtype=torch.long))
+        self.fb_ranges = torch.stack([first, last], dim=1).to(torch.int32).contiguous().to(self.device)
 
     def __call__(self, wav: torch.Tensor, lengths: Optional[torch.Tensor] = None,
                  peak_normalize: bool = True) -> torch.Tensor:
@@ -69,7 +74,7 @@ class LogMelSpectrogram:
             peak = torch.empty(B, dtype=torch.float32, device=self.device)
             check(lib().kr_wave_peak(_ptr(wav), _ptr(lengths), _ptr(peak), ctypes.c_int(B), ctypes.c_longlong(n_max),
                                      _stream()), "kr_wave_peak")
-        check(lib().kr_mel_stft(_ptr(wav), _ptr(lengths), _ptr(peak), _ptr(self.fb_t), _ptr(out), ctypes.c_int(B),
+        check(lib().kr_mel_stft(_ptr(wav), _ptr(lengths), _ptr(peak), _ptr(self.fb_t), _ptr(self.fb_ranges), _ptr(out), ctypes.c_int(B),
                                 ctypes.c_longlong(n_max), ctypes.c_int(frames), ctypes.c_int(self.n_mels),
                                 ctypes.c_int(self.n_fft), ctypes.c_int(self.hop), ctypes.c_float(self.log_eps),
                                 _stream()), "kr_mel_stft")

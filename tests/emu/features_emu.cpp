@@ -79,8 +79,9 @@ extern "C" int emu_energy_norm(const float* e, const long long* frames, float* o
 }
 
 // kr_mel_stft, KR_MELSTFT_R4=1 variant (mel_stft_r4_kernel in kr_melstft.cu)
-extern "C" int emu_mel_stft_r4(const float* wav, const long long* lengths, const float* peak, const float* fb_t, float* out,
-                               int B, long long n_max, int frames_max, int n_mels, float log_eps) {
+extern "C" int emu_mel_stft_r4(const float* wav, const long long* lengths, const float* peak, const float* fb_t,
+                               const int* fb_ranges, float* out, int B, long long n_max, int frames_max, int n_mels,
+                               float log_eps) {
   std::vector<krf_float2> z(krf::MEL_NFFT), qw(krf::MEL_NFFT / 4 + 1);
   std::vector<float> pw(krf::MEL_BINS + 3);
   for (int b = 0; b < B; ++b) {
@@ -92,7 +93,7 @@ extern "C" int emu_mel_stft_r4(const float* wav, const long long* lengths, const
         for (int m = 0; m < n_mels; ++m) orow[(long long)m * frames_max] = 0.f;
         continue;
       }
-      EMU_BLOCK(256, krf::mel_frame_body(wav + (long long)b * n_max, n, f, gain, fb_t, n_mels, frames_max, log_eps, z.data(),
+      EMU_BLOCK(256, krf::mel_frame_body(wav + (long long)b * n_max, n, f, gain, fb_t, fb_ranges, n_mels, frames_max, log_eps, z.data(),
                                          qw.data(), pw.data(), orow));
     }
   }

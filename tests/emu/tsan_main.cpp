@@ -45,7 +45,7 @@ int main() {
   int t_end = -1;
   emu_trim_end(e.data(), nullptr, &t_end, 1, 40);
   std::vector<float> fb(80 * 513, 0.001f), lm(80 * 3);
-  emu_mel_stft_r4(wav.data(), nullptr, nullptr, fb.data(), lm.data(), 1, n, 3, 80, 1e-9f);
+  emu_mel_stft_r4(wav.data(), nullptr, nullptr, fb.data(), nullptr, lm.data(), 1, n, 3, 80, 1e-9f);
   // ---- decode: two self-attention steps with cache append, a masked cross-attention, fused GEMVs, finish
   const int D = 128, H = 2, B = 2, cap = 8, Tp = 5, M = 80;
   krd::DecState st = {};

@@ -122,6 +122,10 @@ def test_radix4_mel_stft_variant_matches_torchaudio_golden(emu):
     from oracle import melstft as om
     fix = np.load(os.path.join(HERE, "golden", "melstft.npz"))
     fb_t = np.ascontiguousarray(mel_filterbank_htk(513, 0.0, 8000.0, 80, 22050).t().numpy())
+    # [first non-zero bin, one past the last) per filter, as features.LogMelSpectrogram builds it
+    nz = fb_t != 0
+    rng = np.ascontiguousarray(np.stack([nz.argmax(axis=1), 513 - nz[:, ::-1].argmax(axis=1)], axis=1).astype(np.int32))
+    assert int((rng[:, 1] - rng[:, 0]).max()) < 64 and bool(nz.any(axis=1).all())
     for case in ("a", "b", "c"):
         wav = np.ascontiguousarray(fix[f"wav_{case}"], dtype=np.float32).reshape(1, -1)
         want = fix[f"mel_{case}"]
@@ -129,8 +133,12 @@ def test_radix4_mel_stft_variant_matches_torchaudio_golden(emu):
         frames = 1 + n // 256
         peak = np.array([np.abs(wav).max()], np.float32)
         out = np.full((1, 80, frames), np.nan, np.float32)
-        assert emu.emu_mel_stft_r4(_p(wav), None, _p(peak), _p(fb_t), _p(out), 1, ctypes.c_longlong(n), frames, 80,
+        assert emu.emu_mel_stft_r4(_p(wav), None, _p(peak), _p(fb_t), _p(rng), _p(out), 1, ctypes.c_longlong(n), frames, 80,
                                    ctypes.c_float(1e-9)) == 0
+        dense = np.full((1, 80, frames), np.nan, np.float32)        # skipping exact zeros changes no bit
+        assert emu.emu_mel_stft_r4(_p(wav), None, _p(peak), _p(fb_t), None, _p(dense), 1, ctypes.c_longlong(n), frames, 80,
+                                   ctypes.c_float(1e-9)) == 0
+        assert np.array_equal(out, dense)
         assert out[0].shape == want.shape
         assert np.abs(out[0] - want).max() < 1e-3, case
         assert np.abs(out[0] - om.log_mel(wav[0])).max() < 1e-3
@@ -140,11 +148,11 @@ def test_radix4_mel_stft_variant_matches_torchaudio_golden(emu):
     wav2[1, :5000] = fix["wav_a"][:5000]
     lens = np.array([9000, 5000], np.int64)
     out2 = np.full((2, 80, 36), np.nan, np.float32)
-    assert emu.emu_mel_stft_r4(_p(wav2), _p(lens), None, _p(fb_t), _p(out2), 2, ctypes.c_longlong(9000), 36, 80,
+    assert emu.emu_mel_stft_r4(_p(wav2), _p(lens), None, _p(fb_t), _p(rng), _p(out2), 2, ctypes.c_longlong(9000), 36, 80,
                                ctypes.c_float(1e-9)) == 0
     single = np.full((1, 80, 20), np.nan, np.float32)
     w1 = np.ascontiguousarray(wav2[1:2, :5000])
-    assert emu.emu_mel_stft_r4(_p(w1), None, None, _p(fb_t), _p(single), 1, ctypes.c_longlong(5000), 20, 80,
+    assert emu.emu_mel_stft_r4(_p(w1), None, None, _p(fb_t), _p(rng), _p(single), 1, ctypes.c_longlong(5000), 20, 80,
                                ctypes.c_float(1e-9)) == 0
     assert np.array_equal(out2[1, :, :20], single[0]) and np.all(out2[1, :, 20:] == 0.0)
 

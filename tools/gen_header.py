@@ -22,7 +22,7 @@ DOCS = {
     "kr_hifi_pack_mel": "Mel (B,80,T) [time_major=0] or (B,T,80) [1] fp32 -> channels-last bf16 [B, T+2*halo, c_phys] (interior rows; halos and padded channels stay zero): the input-layout handling of inference/hifigan_vocoder.py:112-117 fused with the bf16 cast.",
     "kr_hifi_post_tanh": "conv_post (C -> 1, k=7, pad 3) + tanh on the channels-last activation, inference/hifigan_vocoder.py:131-132.",
     "kr_wave_peak": "peak[b] = max |wav[b, :len[b]]| — the peak normalisation x / (max|x| + 1e-9) of data/dataset.py:672 is applied inside kr_mel_stft.",
-    "kr_mel_stft": "Log-mel features out[B, n_mels, frames_max] = log(melfb(|STFT|^2) + log_eps): reflect pad 512, periodic Hann 1024, hop 256, 513 bins, dense filterbank fb_t[n_mels, 513] (HTK, norm=None); frames beyond 1 + len//256 are zero. Replaces torchaudio.transforms.MelSpectrogram + log of data/dataset.py:162-178,694-697.",
+    "kr_mel_stft": "Log-mel features out[B, n_mels, frames_max] = log(melfb(|STFT|^2) + log_eps): reflect pad 512, periodic Hann 1024, hop 256, 513 bins, dense filterbank fb_t[n_mels, 513] (HTK, norm=None) with optional fb_ranges[n_mels][2] = [first non-zero bin, one past the last) so that the exact zeros of the triangular filters are skipped (bit-identical to the dense product); frames beyond 1 + len//256 are zero. Replaces torchaudio.transforms.MelSpectrogram + log of data/dataset.py:162-178,694-697.",
     "kr_pitch_frames": "Per-frame YIN / CMND analysis of PitchExtractor.extract_pitch, model/variance_predictor.py:492-563: zero pad to 2048, pre-emphasis 0.97, reflect pad 1024, periodic Hann 2048, 4096-point FFT autocorrelation, cumulative-mean-normalised difference over the lags sample_rate/fmax .. sample_rate/fmin, first dip below 0.15 else the minimum, parabolic interpolation. One CTA per (frame, utterance); writes the frequency candidate, the autocorrelation peak and the mean frame energy to [B, frames_max] fp32 rows.",
     "kr_pitch_track": "Per-utterance part of extract_pitch, variance_predictor.py:566-615: voicing threshold clip(0.8 * quantile_25(ac peak), .15, .35), energy gate 0.05 * median, fmin / fmax gate, linear interpolation of unvoiced gaps <= 5 frames, median-5 with reflect padding, normalisation to [0, 1] (0 = unvoiced). Quantiles are exact order statistics by rank counting (no sort). Frames beyond 1 + max(len, 2048) // 256 are zero.",
     "kr_energy_frames": "Per-frame energy of EnergyExtractor.extract_energy_from_mel, variance_predictor.py:659-668: mean over the mel bins (log-domain input) or log1p(max(mean, 0)) (linear power, what data/dataset.py:813 passes); mel is (B, T, n_mels) [time_major = 1] or (B, n_mels, T) [0, the layout kr_mel_stft writes]; exp_input = 1 exponentiates the input first so that kr_mel_stft's log-mel can feed the linear-power branch.",
