@@ -270,3 +270,28 @@ def test_recommended_ema_decay_matches_reference_formula():
     assert recommended_ema_decay(3, 1, 1.0) == 0.9                       # clipped below
     assert recommended_ema_decay(10 ** 6, 1, 1.0) == 0.9999              # clipped above
     assert recommended_ema_decay(5000, 10, 2.0) == pytest.approx(math.exp(-math.log(2) / 1000))
+
+
+def test_oracle_explicit_padding_masks_match_reference_golden():
+    """Explicit text_padding_mask / mel_padding_mask (model/model.py:586-589, 648-654): oracle vs the live-reference
+    fixture tests/golden/acoustic_masks.npz (make_golden_masks.py)."""
+    import sys
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from oracle import acoustic as oa
+    ocfg = oa.AcousticConfig(hidden_dim=128, n_heads=2, n_encoder_layers=2, n_decoder_layers=2, ff_dim=256,
+                             variance_filter=64, max_len=1200)
+    batch = oa.synthetic_batch(B=3, P=24, T=150, seed=11, ragged=True)
+    sd = oa.seeded_state_dict(ocfg, seed=0)
+    text = batch["phoneme_indices"] == 0
+    for b in range(3):
+        text[b, int(batch["phoneme_lengths"][b]) - 1] = True
+    mel = torch.arange(150).unsqueeze(0) >= batch["mel_lengths"].unsqueeze(1)
+    with torch.no_grad():
+        outs = oa.forward_training(sd, ocfg, batch["phoneme_indices"], batch["mel_specs"], batch["phoneme_durations"],
+                                   batch["pitches"], batch["energies"], batch["stress_indices"], text_padding_mask=text,
+                                   mel_padding_mask=mel)
+    fix = np.load(os.path.join(HERE, "golden", "acoustic_masks.npz"))
+    for k, o in zip(("mel", "log_dur", "stop", "pitch", "energy"), outs):
+        assert np.abs(o.numpy() - fix[f"out_{k}"]).max() < 1e-4, k

@@ -107,3 +107,49 @@ def test_surface_matches_reference_module():
     twin = copy.deepcopy(m)
     assert twin.engine is not m.engine and all(torch.equal(a, b) for a, b in zip(twin.state_dict().values(),
                                                                                  m.state_dict().values()))
+
+
+def test_explicit_padding_masks_match_oracle_and_reference_golden():
+    """forward(..., text_padding_mask=, mel_padding_mask=) (model/model.py:586-589, 648-654): the text mask replaces
+    indices == 0 everywhere it is used, the mel mask is the key-padding mask of the decoder self-attention (on top of the
+    causal predicate).  Against the oracle and the live-reference fixture; gradients flow."""
+    import os
+    import numpy as np
+    from oracle import acoustic as oa
+    from kokoro_ruslan_b200.model import KokoroModel
+    ocfg = oa.AcousticConfig(hidden_dim=128, n_heads=2, n_encoder_layers=2, n_decoder_layers=2, ff_dim=256,
+                             variance_filter=64, max_len=1200)
+    batch = oa.synthetic_batch(B=3, P=24, T=150, seed=11, ragged=True)
+    sd = oa.seeded_state_dict(ocfg, seed=0)
+    text = batch["phoneme_indices"] == 0
+    for b in range(3):
+        text[b, int(batch["phoneme_lengths"][b]) - 1] = True
+    mel_mask = torch.arange(150).unsqueeze(0) >= batch["mel_lengths"].unsqueeze(1)
+    m = KokoroModel(vocab_size=ocfg.vocab_size, hidden_dim=128, n_encoder_layers=2, n_heads=2, encoder_ff_dim=256,
+                    n_decoder_layers=2, decoder_ff_dim=256, max_decoder_seq_len=1200, variance_filter_size=64,
+                    encoder_dropout=0.0, decoder_dropout=0.0, decoder_input_dropout=0.0, variance_dropout=0.0,
+                    use_stochastic_depth=False, qk_norm=True, device="cuda")
+    m.load_state_dict(sd)
+    dev = {k: v.cuda() for k, v in batch.items()}
+    outs = m(dev["phoneme_indices"], dev["mel_specs"], dev["phoneme_durations"], dev["stop_token_targets"],
+             pitch_targets=dev["pitches"], energy_targets=dev["energies"], text_padding_mask=text.cuda(),
+             mel_padding_mask=mel_mask.cuda(), stress_indices=dev["stress_indices"])
+    plain = m(dev["phoneme_indices"], dev["mel_specs"], dev["phoneme_durations"], dev["stop_token_targets"],
+              pitch_targets=dev["pitches"], energy_targets=dev["energies"], stress_indices=dev["stress_indices"])
+    with torch.no_grad():
+        want = oa.forward_training(sd, ocfg, batch["phoneme_indices"], batch["mel_specs"], batch["phoneme_durations"],
+                                   batch["pitches"], batch["energies"], batch["stress_indices"], text_padding_mask=text,
+                                   mel_padding_mask=mel_mask)
+    fix = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "acoustic_masks.npz"))
+    live = ~mel_mask
+    for k, got, w in zip(("mel", "log_dur", "stop", "pitch", "energy"), outs, want):
+        g = got.detach().float().cpu()
+        f = torch.from_numpy(fix[f"out_{k}"])
+        if k in ("mel", "stop"):           # frame-level outputs: the real frames (padded ones never reach a loss)
+            g, w, f = g[live], w[live], f[live]
+        tol = 2e-2 * float(w.abs().max())
+        assert float((g - w).abs().max()) < tol and float((g - f).abs().max()) < tol, k
+    assert float((plain[0] - outs[0]).abs().max()) > 1e-2          # the masks really changed the forward
+    (outs[0].float().pow(2).mean() + outs[1].float().pow(2).mean()).backward()
+    gw = dict(m.named_parameters())["decoder.layers.0.self_attn.w_q.weight"].grad
+    assert gw is not None and bool(torch.isfinite(gw).all()) and float(gw.abs().max()) > 0
