@@ -9,6 +9,7 @@ restated against this repository's host helpers and oracle — written fresh, ci
                                                         q_offset = 0 RoPE quirk, which the oracle reproduces and exposes)
 """
 import math
+import os
 
 import pytest
 import torch
@@ -127,3 +128,28 @@ def test_kv_cached_self_attention_equals_causal_pass_up_to_the_q_offset_quirk():
     assert torch.allclose(fixed, full, atol=1e-5)
     assert torch.allclose(quirk[:, :1], full[:, :1], atol=1e-5)               # position 0: no difference yet
     assert not torch.allclose(quirk[:, 1:], full[:, 1:], atol=1e-3)           # later frames: the train / inference mismatch
+
+
+def test_reference_fallback_model_path_cannot_train():
+    """SURVEY.md row A8': with use_variance_predictor=False the reference's own training forward raises — model/model.py:489-499
+    passes `pitch_target_is_frame_level=` to SimpleDurationAdaptor.forward, which does not accept it
+    (model/duration_adaptor.py:66-73).  There is no training behaviour to match on that path, which is why the B200
+    KokoroModel refuses the flag and only the OPERATORS of that path (length_regulate, average_by_duration) are provided.
+    Checked against the installed reference (baseline/_ref); skipped where it is absent."""
+    import logging
+    import sys
+    import pytest
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from oracle import ref_trainer
+    if not ref_trainer.reference_available():
+        pytest.skip("baseline/_ref is not installed")
+    ref_trainer._import_reference()
+    logging.getLogger("kokoro").setLevel(logging.CRITICAL)
+    from kokoro.model.model import KokoroModel
+    m = KokoroModel(vocab_size=59, hidden_dim=128, n_heads=2, n_encoder_layers=1, n_decoder_layers=1, encoder_ff_dim=128,
+                    decoder_ff_dim=128, use_variance_predictor=False, qk_norm=True)
+    m.train()
+    with pytest.raises(TypeError, match="pitch_target_is_frame_level"):
+        m(torch.randint(1, 59, (1, 6)), torch.randn(1, 12, 80), torch.full((1, 6), 2), torch.zeros(1, 12))
