@@ -202,6 +202,32 @@ class HiFiGANGenerator:
         out[:co, :, :ci] = w.permute(0, 2, 1)
         return out.reshape(rows, k * cin_phys).to(BF16).contiguous()
 
+    @staticmethod
+    def _tap_major_time_folded(w: torch.Tensor) -> torch.Tensor:
+        """Dilation-1 conv [C, C, k] on a [L, C] activation as a conv on its TIME-FOLDED view [L/2, 2C] (two consecutive
+        time steps side by side in the channel dimension — the same memory): output row r holds y(2r) | y(2r+1), folded tap
+        f reads x(2(r+f)) | x(2(r+f)+1), so block (row half a, column half c) of tap f is the original tap at time offset
+        o = 2f + c - a.  k taps become 2*ceil(h/2) + 1 (h = (k-1)/2) of twice the width: the MMA work grows (half of each
+        block-sparse weight is zero) but the narrow stage is bound by per-TILE latency, and the tile count halves.
+        Returns bf16 [2C, taps * 2C] (tap-major K)."""
+        co, ci, k = w.shape
+        hh = (k - 1) // 2
+        hf = (hh + 1) // 2
+        out = torch.zeros(2 * co, 2 * hf + 1, 2 * ci, dtype=F32, device=w.device)
+        for fi, f in enumerate(range(-hf, hf + 1)):
+            for a in (0, 1):
+                for c in (0, 1):
+                    o = 2 * f + c - a
+                    if abs(o) <= hh:
+                        out[a * co:(a + 1) * co, fi, c * ci:(c + 1) * ci] = w[:, :, o + hh]
+        return out.reshape(2 * co, (2 * hf + 1) * 2 * ci).to(BF16).contiguous()
+
+    def _time_folded(self, stage: int) -> bool:
+        """Stages whose dilation-1 convs run on the time-folded view (see _tap_major_time_folded): the 32-channel stage
+        (measured on B200, 16 x 800 frames: 18.59 -> 17.67 ms; folding the 64-channel stage as well gives 17.67 ms for its
+        k = 3 convs and 17.9 - 18.0 ms with k = 7 / 11, whose folded weights no longer fit next to the activation ring)."""
+        return self.h.upsample_initial_channel // 2 ** (stage + 1) == 32
+
     def _fold(self) -> None:
         h, W = self.h, {}
         c0 = h.upsample_initial_channel
@@ -228,6 +254,10 @@ class HiFiGANGenerator:
                     for d in range(len(h.resblock_dilation_sizes[j])):
                         W[f"{p}.{grp}.{d}.w"] = self._tap_major(self._eff(f"{p}.{grp}.{d}"), cout_p)
                         W[f"{p}.{grp}.{d}.b"] = self._sd[f"{p}.{grp}.{d}.bias"].contiguous()
+                        dil = 1 if grp == "convs2" else h.resblock_dilation_sizes[j][d]
+                        if self._time_folded(i) and dil == 1 and cout_p == cout:
+                            W[f"{p}.{grp}.{d}.w2"] = self._tap_major_time_folded(self._eff(f"{p}.{grp}.{d}"))
+                            W[f"{p}.{grp}.{d}.b2"] = torch.cat([W[f"{p}.{grp}.{d}.b"]] * 2).contiguous()
         wpost = self._eff("conv_post")                        # [1, ch, 7]
         W["post.w"] = wpost[0].t().contiguous()               # [7, ch] fp32
         W["post.b"] = self._sd["conv_post.bias"].contiguous()
@@ -286,27 +316,51 @@ class HiFiGANGenerator:
             for j, (k, dils) in enumerate(zip(h.resblock_kernel_sizes, h.resblock_dilation_sizes)):
                 p = f"resblocks.{i * self.num_kernels + j}"
                 y_raw, y_act = b[f"h_raw{i}"], b[f"h_act{i}"]
+                # time-folded views (dilation-1 convs of the narrow stage, see _tap_major_time_folded): [B, rows/2, 2C] over
+                # the same memory; f2 = the padded activation buffer, i2 = its inner L rows, x2 = an un-padded [B, L, C] tensor
+                hf = ((k - 1) // 2 + 1) // 2
+                f2 = lambda t: t.view(B, (L + 2 * HALO) // 2, 2 * cp)                       # noqa: E731
+                i2 = lambda t: f2(t)[:, HALO // 2:HALO // 2 + L // 2]                       # noqa: E731
+                x2 = lambda t: t.view(B, L // 2, 2 * cout)                                  # noqa: E731
                 for d, dil in enumerate(dils):
-                    ops.conv1d_cl(y_act, W[f"{p}.convs1.{d}.w"], rows=L, row0=HALO - dil * (k - 1) // 2, taps=k,
-                                  dil=dil, bias=W[f"{p}.convs1.{d}.b"], out_act=inner(b[f"t_act{i}"], L)[:, :, :cout],
-                                  act_slope=0.1)
+                    if f"{p}.convs1.{d}.w2" in W:
+                        ops.conv1d_cl(f2(y_act), W[f"{p}.convs1.{d}.w2"], rows=L // 2, row0=HALO // 2 - hf, taps=2 * hf + 1,
+                                      dil=1, bias=W[f"{p}.convs1.{d}.b2"], out_act=i2(b[f"t_act{i}"]), act_slope=0.1)
+                    else:
+                        ops.conv1d_cl(y_act, W[f"{p}.convs1.{d}.w"], rows=L, row0=HALO - dil * (k - 1) // 2, taps=k,
+                                      dil=dil, bias=W[f"{p}.convs1.{d}.b"], out_act=inner(b[f"t_act{i}"], L)[:, :, :cout],
+                                      act_slope=0.1)
                     final = d == len(dils) - 1
+                    folded = f"{p}.convs2.{d}.w2" in W
                     if not final:
                         n_raw, n_act = (b[f"ya_raw{i}"], b[f"ya_act{i}"]) if d % 2 == 0 else (b[f"yb_raw{i}"], b[f"yb_act{i}"])
-                        ops.conv1d_cl(b[f"t_act{i}"], W[f"{p}.convs2.{d}.w"], rows=L, row0=HALO - (k - 1) // 2,
-                                      taps=k, dil=1, bias=W[f"{p}.convs2.{d}.b"], resid=inner(y_raw, L)[:, :, :cout],
-                                      out=inner(n_raw, L)[:, :, :cout], out_act=inner(n_act, L)[:, :, :cout],
-                                      act_slope=0.1)
+                        if folded:
+                            ops.conv1d_cl(f2(b[f"t_act{i}"]), W[f"{p}.convs2.{d}.w2"], rows=L // 2, row0=HALO // 2 - hf,
+                                          taps=2 * hf + 1, dil=1, bias=W[f"{p}.convs2.{d}.b2"], resid=i2(y_raw),
+                                          out=i2(n_raw), out_act=i2(n_act), act_slope=0.1)
+                        else:
+                            ops.conv1d_cl(b[f"t_act{i}"], W[f"{p}.convs2.{d}.w"], rows=L, row0=HALO - (k - 1) // 2,
+                                          taps=k, dil=1, bias=W[f"{p}.convs2.{d}.b"], resid=inner(y_raw, L)[:, :, :cout],
+                                          out=inner(n_raw, L)[:, :, :cout], out_act=inner(n_act, L)[:, :, :cout],
+                                          act_slope=0.1)
                         y_raw, y_act = n_raw, n_act
                     else:
                         # xs (+)= (y + conv)/num_kernels; the last resblock also emits lrelu(xs) for the next stage
                         last_rb = j == self.num_kernels - 1
-                        ops.conv1d_cl(b[f"t_act{i}"], W[f"{p}.convs2.{d}.w"], rows=L, row0=HALO - (k - 1) // 2,
-                                      taps=k, dil=1, bias=W[f"{p}.convs2.{d}.b"], resid=inner(y_raw, L)[:, :, :cout],
-                                      resid2=xs if j > 0 else None, beta=1.0 / self.num_kernels,
-                                      out=None if last_rb else xs,
-                                      out_act=inner(b[f"x_act{i}"], L)[:, :, :cout] if last_rb else None,
-                                      act_slope=0.01 if last_stage else 0.1)
+                        if folded:
+                            ops.conv1d_cl(f2(b[f"t_act{i}"]), W[f"{p}.convs2.{d}.w2"], rows=L // 2, row0=HALO // 2 - hf,
+                                          taps=2 * hf + 1, dil=1, bias=W[f"{p}.convs2.{d}.b2"], resid=i2(y_raw),
+                                          resid2=x2(xs) if j > 0 else None, beta=1.0 / self.num_kernels,
+                                          out=None if last_rb else x2(xs),
+                                          out_act=i2(b[f"x_act{i}"]) if last_rb else None,
+                                          act_slope=0.01 if last_stage else 0.1)
+                        else:
+                            ops.conv1d_cl(b[f"t_act{i}"], W[f"{p}.convs2.{d}.w"], rows=L, row0=HALO - (k - 1) // 2,
+                                          taps=k, dil=1, bias=W[f"{p}.convs2.{d}.b"], resid=inner(y_raw, L)[:, :, :cout],
+                                          resid2=xs if j > 0 else None, beta=1.0 / self.num_kernels,
+                                          out=None if last_rb else xs,
+                                          out_act=inner(b[f"x_act{i}"], L)[:, :, :cout] if last_rb else None,
+                                          act_slope=0.01 if last_stage else 0.1)
             x_act = b[f"x_act{i}"]
         ch = c0 // 2 ** self.num_upsamples
         check(lib().kr_hifi_post_tanh(ops._ptr(x_act), ops._ptr(W["post.w"]), ops._ptr(W["post.b"]),
