@@ -323,17 +323,45 @@ class HiFiGANGenerator:
                 i2 = lambda t: f2(t)[:, HALO // 2:HALO // 2 + L // 2]                       # noqa: E731
                 x2 = lambda t: t.view(B, L // 2, 2 * cout)                                  # noqa: E731
                 for d, dil in enumerate(dils):
-                    if f"{p}.convs1.{d}.w2" in W:
+                    final = d == len(dils) - 1
+                    last_rb = j == self.num_kernels - 1
+                    n_raw, n_act = (b[f"ya_raw{i}"], b[f"ya_act{i}"]) if d % 2 == 0 else (b[f"yb_raw{i}"], b[f"yb_act{i}"])
+                    # destination of this step: the next step's (raw, act) pair, or — last step of the ResBlock — the MRF
+                    # accumulator xs (+)= (x + conv) / num_kernels, whose last writer emits lrelu(xs) for the next stage
+                    fold1, fold2 = f"{p}.convs1.{d}.w2" in W, f"{p}.convs2.{d}.w2" in W
+                    fz_ok = fold1 and fold2
+                    if lib().kr_hifi_resblock_resident(ctypes.c_int(64 if fz_ok else cp), ctypes.c_int(2 * hf + 1 if fz_ok else k),
+                                                       ctypes.c_int(2 * hf + 1 if fz_ok else k)) and (fz_ok or cp in (64, 128)):
+                        # ONE kernel for c1 -> lrelu -> c2 -> + x (csrc/kr_hifi_resblock.cu); on the narrow stage through
+                        # the time-folded views (dilation-1 steps only)
+                        fz = fold1 and fold2
+                        v_in = f2(y_act) if fz else y_act
+                        iv = i2 if fz else (lambda t: inner(t, L)[:, :, :cout])
+                        xv = x2 if fz else (lambda t: t)
+                        w1, b1 = (W[f"{p}.convs1.{d}.w2"], W[f"{p}.convs1.{d}.b2"]) if fz else (W[f"{p}.convs1.{d}.w"], W[f"{p}.convs1.{d}.b"])
+                        w2, b2 = (W[f"{p}.convs2.{d}.w2"], W[f"{p}.convs2.{d}.b2"]) if fz else (W[f"{p}.convs2.{d}.w"], W[f"{p}.convs2.{d}.b"])
+                        kk = 2 * hf + 1 if fz else k
+                        kw = dict(resid=iv(y_raw))
+                        if not final:
+                            kw.update(out=iv(n_raw), out_act=iv(n_act), act_slope=0.1)
+                        else:
+                            kw.update(resid2=xv(xs) if j > 0 else None, beta=1.0 / self.num_kernels,
+                                      out=None if last_rb else xv(xs), out_act=iv(b[f"x_act{i}"]) if last_rb else None,
+                                      act_slope=0.01 if last_stage else 0.1)
+                        ops.hifi_resblock(v_in, L // 2 if fz else L, HALO // 2 if fz else HALO, w1, kk, 1 if fz else dil, b1,
+                                          w2, kk, b2, **kw)
+                        if not final:
+                            y_raw, y_act = n_raw, n_act
+                        continue
+                    if fold1:
                         ops.conv1d_cl(f2(y_act), W[f"{p}.convs1.{d}.w2"], rows=L // 2, row0=HALO // 2 - hf, taps=2 * hf + 1,
                                       dil=1, bias=W[f"{p}.convs1.{d}.b2"], out_act=i2(b[f"t_act{i}"]), act_slope=0.1)
                     else:
                         ops.conv1d_cl(y_act, W[f"{p}.convs1.{d}.w"], rows=L, row0=HALO - dil * (k - 1) // 2, taps=k,
                                       dil=dil, bias=W[f"{p}.convs1.{d}.b"], out_act=inner(b[f"t_act{i}"], L)[:, :, :cout],
                                       act_slope=0.1)
-                    final = d == len(dils) - 1
-                    folded = f"{p}.convs2.{d}.w2" in W
+                    folded = fold2
                     if not final:
-                        n_raw, n_act = (b[f"ya_raw{i}"], b[f"ya_act{i}"]) if d % 2 == 0 else (b[f"yb_raw{i}"], b[f"yb_act{i}"])
                         if folded:
                             ops.conv1d_cl(f2(b[f"t_act{i}"]), W[f"{p}.convs2.{d}.w2"], rows=L // 2, row0=HALO // 2 - hf,
                                           taps=2 * hf + 1, dil=1, bias=W[f"{p}.convs2.{d}.b2"], resid=i2(y_raw),
@@ -345,8 +373,6 @@ class HiFiGANGenerator:
                                           act_slope=0.1)
                         y_raw, y_act = n_raw, n_act
                     else:
-                        # xs (+)= (y + conv)/num_kernels; the last resblock also emits lrelu(xs) for the next stage
-                        last_rb = j == self.num_kernels - 1
                         if folded:
                             ops.conv1d_cl(f2(b[f"t_act{i}"]), W[f"{p}.convs2.{d}.w2"], rows=L // 2, row0=HALO // 2 - hf,
                                           taps=2 * hf + 1, dil=1, bias=W[f"{p}.convs2.{d}.b2"], resid=i2(y_raw),
