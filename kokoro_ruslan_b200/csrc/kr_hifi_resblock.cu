@@ -13,8 +13,9 @@
 // kernel refuses shapes whose weights do not fit; the caller keeps the two-launch path for those):
 //
 //   tile = 128 - 2*h2 output rows (h2 = (k2-1)/2): conv1 produces exactly the 128 rows of t that conv2 needs for them
-//   warp 0    TMA producer: weights once; per tile the x_act slab (128 + 2*h1*d1 rows, fetched ONCE — the taps are
-//             row-shifted views of it) into a double-buffered slot
+//   warp 0    TMA producer: weights once; per tile the x_act slab (128 + conv1's span rows, fetched ONCE — the taps are
+//             row-shifted views of it) into a double-buffered slot.  conv1's taps are (tau - h1) * d1 or an explicit
+//             offset list (the time-folded dilated convs of the narrow stage, whose folded taps are not equidistant)
 //   warp 1    tcgen05.mma issuer: GEMM1 -> acc1 (TMEM), GEMM2 (A = the t tile in smem, taps = row shifts) -> acc2 (TMEM)
 //   warps 2-9 two independent TILE SLOTS of four epilogue warps each (even / odd tiles; own acc1, acc2, t tile, barriers):
 //             epilogue 1: acc1 -> +b1 -> lrelu -> zero outside [0, L) (conv2's zero padding applies to t) -> bf16 ->
@@ -38,7 +39,8 @@ constexpr int RB_SMEM_MAX = 227 * 1024 - 1024;
 
 struct RbParams {
   int B, C, L, halo;                     // C = physical channels (64 / 128); activations [B, L + 2*halo, C]
-  int k1, d1, k2;                        // conv1: k1 taps, dilation d1; conv2: k2 taps, dilation 1
+  int k1, k2, lead1;                     // conv1: k1 taps at slab rows off1[]; conv2: k2 taps, dilation 1; lead1 = -min tap offset
+  short off1[32];                        // conv1 tap -> row offset into the slab (>= 0)
   int slab_rows, rows_out, tiles_per_item, total_tiles;
   const float* b1; const float* b2;
   const float* resid; long long r_ld, r_bs;         // fp32, pointing at time 0 of item 0
@@ -73,7 +75,7 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   uint8_t* wres = tt + 2 * T_BYTES;             // [n1 + n2][C rows][128 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h1 = (p.k1 - 1) / 2, h2 = (p.k2 - 1) / 2;
+  const int h2 = (p.k2 - 1) / 2;
   const int n1 = p.k1 * CB, n2 = p.k2 * CB;                   // weight K blocks of the two GEMMs
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -113,8 +115,8 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const int sb = lt & 1;
         mbar_wait(&slab_empty[sb], ((lt >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&slab_full[sb], (uint32_t)(CB * p.slab_rows * 128));
-        // t row j <-> time m0 - h2 + j; its conv1 taps read times m0 - h2 + j + (tau - h1) * d1
-        const int row0 = p.halo + m0 - h2 - h1 * p.d1;
+        // t row j <-> time m0 - h2 + j; conv1 tap tau reads time m0 - h2 + j + off1[tau] - lead1
+        const int row0 = p.halo + m0 - h2 - p.lead1;
 #pragma unroll
         for (int cb = 0; cb < CB; ++cb)
           tma_load_3d(slab + sb * SLAB_BYTES + cb * (RB_MAX_SLAB * 128), &tm_x, &slab_full[sb], cb * 64, row0, bz);
@@ -155,7 +157,7 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const uint32_t acc1 = tmem_base + s * C;
         for (int kb = 0; kb < n1; ++kb) {
           const int tap = kb / CB, cb = kb - tap * CB;
-          const uint32_t a = smem_u32(slab + s * SLAB_BYTES + cb * (RB_MAX_SLAB * 128) + tap * p.d1 * 128);
+          const uint32_t a = smem_u32(slab + s * SLAB_BYTES + cb * (RB_MAX_SLAB * 128) + p.off1[tap] * 128);
           const uint32_t b = smem_u32(wres + kb * W_STAGE);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -327,17 +329,25 @@ bool rb_fits(int C, int k1, int k2) {
 }  // namespace
 
 extern "C" int kr_hifi_resblock(const void* x_act, int B, long long L, int halo, int C, const void* w1, int k1, int d1,
-                                const float* b1, const void* w2, int k2, const float* b2, const float* resid,
+                                const int* taps1, const float* b1, const void* w2, int k2, const float* b2, const float* resid,
                                 long long r_ld, long long r_bs, const float* resid2, long long r2_ld, long long r2_bs,
                                 float beta, float* out, long long o_ld, long long o_bs, void* out_act, long long a_ld,
                                 long long a_bs, float slope, void* stream) {
   if (B <= 0 || L <= 0) return KR_OK;
   if (C != 64 && C != 128) { kr_set_error("kr_hifi_resblock: C must be 64 or 128 physical channels"); return KR_ERR_UNSUPPORTED; }
-  if (k1 < 1 || k2 < 1 || !(k1 & 1) || !(k2 & 1) || d1 < 1) { kr_set_error("kr_hifi_resblock: odd kernel sizes, dilation >= 1"); return KR_ERR_ARG; }
+  if (k1 < 1 || k2 < 1 || !(k2 & 1) || (taps1 == nullptr && (!(k1 & 1) || d1 < 1))) { kr_set_error("kr_hifi_resblock: odd kernel sizes, dilation >= 1"); return KR_ERR_ARG; }
+  if (taps1 != nullptr ? (k1 < 1 || k1 > 32) : (k1 > 32)) { kr_set_error("kr_hifi_resblock: at most 32 conv1 taps"); return KR_ERR_ARG; }
   const int h1 = (k1 - 1) / 2, h2 = (k2 - 1) / 2;
-  const int slab_rows = (128 + 2 * h1 * d1 + 7) / 8 * 8;
-  if (h2 > 8 || slab_rows > RB_MAX_SLAB || halo < h2 + h1 * d1) {
-    kr_set_error("kr_hifi_resblock: receptive field too large (k2 <= 17, 128 + (k1-1)*d1 <= 184 rows, halo >= h2 + h1*d1)");
+  // conv1 tap offsets (rows relative to the output row): the explicit ascending list, or (tau - h1) * d1
+  int offs[32];
+  for (int t = 0; t < k1; ++t) {
+    offs[t] = taps1 != nullptr ? taps1[t] : (t - h1) * d1;
+    if (t > 0 && offs[t] <= offs[t - 1]) { kr_set_error("kr_hifi_resblock: taps1 must be strictly ascending"); return KR_ERR_ARG; }
+  }
+  const int lead = -offs[0] > 0 ? -offs[0] : 0, trail = offs[k1 - 1] > 0 ? offs[k1 - 1] : 0;
+  const int slab_rows = (128 + lead + trail + 7) / 8 * 8;
+  if (h2 > 8 || slab_rows > RB_MAX_SLAB || halo < h2 + (lead > trail ? lead : trail)) {
+    kr_set_error("kr_hifi_resblock: receptive field too large (k2 <= 17, 128 + conv1 span <= 184 rows, halo >= h2 + conv1 reach)");
     return KR_ERR_UNSUPPORTED;
   }
   if (!rb_fits(C, k1, k2)) {
@@ -349,7 +359,8 @@ extern "C" int kr_hifi_resblock(const void* x_act, int B, long long L, int halo,
     kr_set_error("kr_hifi_resblock: leading dimensions / batch strides must be multiples of 4 elements"); return KR_ERR_ARG;
   }
   RbParams p{};
-  p.B = B; p.C = C; p.L = (int)L; p.halo = halo; p.k1 = k1; p.d1 = d1; p.k2 = k2;
+  p.B = B; p.C = C; p.L = (int)L; p.halo = halo; p.k1 = k1; p.k2 = k2; p.lead1 = lead;
+  for (int t = 0; t < k1; ++t) p.off1[t] = (short)(offs[t] + lead);
   p.slab_rows = slab_rows; p.rows_out = 128 - 2 * h2;
   p.tiles_per_item = (int)((L + p.rows_out - 1) / p.rows_out);
   p.total_tiles = p.tiles_per_item * B;

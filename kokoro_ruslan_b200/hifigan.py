@@ -203,24 +203,34 @@ class HiFiGANGenerator:
         return out.reshape(rows, k * cin_phys).to(BF16).contiguous()
 
     @staticmethod
-    def _tap_major_time_folded(w: torch.Tensor) -> torch.Tensor:
-        """Dilation-1 conv [C, C, k] on a [L, C] activation as a conv on its TIME-FOLDED view [L/2, 2C] (two consecutive
-        time steps side by side in the channel dimension — the same memory): output row r holds y(2r) | y(2r+1), folded tap
-        f reads x(2(r+f)) | x(2(r+f)+1), so block (row half a, column half c) of tap f is the original tap at time offset
-        o = 2f + c - a.  k taps become 2*ceil(h/2) + 1 (h = (k-1)/2) of twice the width: the MMA work grows (half of each
-        block-sparse weight is zero) but the narrow stage is bound by per-TILE latency, and the tile count halves.
-        Returns bf16 [2C, taps * 2C] (tap-major K)."""
+    def _folded_taps(k: int, dil: int = 1):
+        """Folded tap offsets f (ascending) with a non-zero block: some o = 2f + c - a (a, c in {0, 1}) is a tap offset
+        j * dil, |j| <= (k-1)/2, of the original conv."""
+        hh = (k - 1) // 2
+        reach = (hh * dil + 1) // 2
+        orig = {j * dil for j in range(-hh, hh + 1)}
+        return [f for f in range(-reach, reach + 1) if any((2 * f + c - a) in orig for a in (0, 1) for c in (0, 1))]
+
+    @classmethod
+    def _tap_major_time_folded(cls, w: torch.Tensor, dil: int = 1) -> torch.Tensor:
+        """Conv [C, C, k] (dilation dil, odd) on a [L, C] activation as a conv on its TIME-FOLDED view [L/2, 2C] (two
+        consecutive time steps side by side in the channel dimension — the same memory): output row r holds y(2r) | y(2r+1),
+        folded tap f reads x(2(r+f)) | x(2(r+f)+1), so block (row half a, column half c) of tap f is the original tap at time
+        offset o = 2f + c - a.  With dil = 1, k taps become 2*ceil(h/2) + 1 (h = (k-1)/2) contiguous taps of twice the
+        width; a dilated conv becomes the NON-equidistant taps of _folded_taps (only the fused ResBlock kernel takes those).
+        The MMA work grows (half or more of each block-sparse weight is zero) but the narrow stage is bound by per-TILE
+        latency, and the tile count halves.  Returns bf16 [2C, taps * 2C] (tap-major K)."""
         co, ci, k = w.shape
         hh = (k - 1) // 2
-        hf = (hh + 1) // 2
-        out = torch.zeros(2 * co, 2 * hf + 1, 2 * ci, dtype=F32, device=w.device)
-        for fi, f in enumerate(range(-hf, hf + 1)):
+        taps = cls._folded_taps(k, dil)
+        out = torch.zeros(2 * co, len(taps), 2 * ci, dtype=F32, device=w.device)
+        for fi, f in enumerate(taps):
             for a in (0, 1):
                 for c in (0, 1):
                     o = 2 * f + c - a
-                    if abs(o) <= hh:
-                        out[a * co:(a + 1) * co, fi, c * ci:(c + 1) * ci] = w[:, :, o + hh]
-        return out.reshape(2 * co, (2 * hf + 1) * 2 * ci).to(BF16).contiguous()
+                    if o % dil == 0 and abs(o // dil) <= hh:
+                        out[a * co:(a + 1) * co, fi, c * ci:(c + 1) * ci] = w[:, :, o // dil + hh]
+        return out.reshape(2 * co, len(taps) * 2 * ci).to(BF16).contiguous()
 
     def _time_folded(self, stage: int) -> bool:
         """Stages whose dilation-1 convs run on the time-folded view (see _tap_major_time_folded): the 32-channel stage
@@ -258,6 +268,16 @@ class HiFiGANGenerator:
                         if self._time_folded(i) and dil == 1 and cout_p == cout:
                             W[f"{p}.{grp}.{d}.w2"] = self._tap_major_time_folded(self._eff(f"{p}.{grp}.{d}"))
                             W[f"{p}.{grp}.{d}.b2"] = torch.cat([W[f"{p}.{grp}.{d}.b"]] * 2).contiguous()
+                        elif self._time_folded(i) and cout_p == cout:
+                            # dilated conv1 of the narrow stage: folded taps are not equidistant — only for the fused
+                            # ResBlock kernel, and only when both convs' folded weights stay resident in shared memory
+                            kj = h.resblock_kernel_sizes[j]
+                            taps = self._folded_taps(kj, dil)
+                            if lib().kr_hifi_resblock_resident(ctypes.c_int(2 * cout), ctypes.c_int(len(taps)),
+                                                               ctypes.c_int(len(self._folded_taps(kj)))):
+                                W[f"{p}.{grp}.{d}.w2d"] = self._tap_major_time_folded(self._eff(f"{p}.{grp}.{d}"), dil)
+                                W[f"{p}.{grp}.{d}.b2"] = torch.cat([W[f"{p}.{grp}.{d}.b"]] * 2).contiguous()
+                                W[f"{p}.{grp}.{d}.taps"] = taps
         wpost = self._eff("conv_post")                        # [1, ch, 7]
         W["post.w"] = wpost[0].t().contiguous()               # [7, ch] fp32
         W["post.b"] = self._sd["conv_post.bias"].contiguous()
@@ -329,16 +349,20 @@ class HiFiGANGenerator:
                     # destination of this step: the next step's (raw, act) pair, or — last step of the ResBlock — the MRF
                     # accumulator xs (+)= (x + conv) / num_kernels, whose last writer emits lrelu(xs) for the next stage
                     fold1, fold2 = f"{p}.convs1.{d}.w2" in W, f"{p}.convs2.{d}.w2" in W
-                    fz_ok = fold1 and fold2
-                    if lib().kr_hifi_resblock_resident(ctypes.c_int(64 if fz_ok else cp), ctypes.c_int(2 * hf + 1 if fz_ok else k),
+                    fold1d = f"{p}.convs1.{d}.w2d" in W                 # dilated conv1, folded with an explicit tap list
+                    fz_ok = (fold1 or fold1d) and fold2
+                    taps1 = W[f"{p}.convs1.{d}.taps"] if fold1d else None
+                    if lib().kr_hifi_resblock_resident(ctypes.c_int(64 if fz_ok else cp),
+                                                       ctypes.c_int(len(taps1) if fold1d else (2 * hf + 1 if fz_ok else k)),
                                                        ctypes.c_int(2 * hf + 1 if fz_ok else k)) and (fz_ok or cp in (64, 128)):
                         # ONE kernel for c1 -> lrelu -> c2 -> + x (csrc/kr_hifi_resblock.cu); on the narrow stage through
                         # the time-folded views (dilation-1 steps only)
-                        fz = fold1 and fold2
+                        fz = fz_ok
                         v_in = f2(y_act) if fz else y_act
                         iv = i2 if fz else (lambda t: inner(t, L)[:, :, :cout])
                         xv = x2 if fz else (lambda t: t)
-                        w1, b1 = (W[f"{p}.convs1.{d}.w2"], W[f"{p}.convs1.{d}.b2"]) if fz else (W[f"{p}.convs1.{d}.w"], W[f"{p}.convs1.{d}.b"])
+                        w1, b1 = (W[f"{p}.convs1.{d}.w2d" if fold1d else f"{p}.convs1.{d}.w2"], W[f"{p}.convs1.{d}.b2"]) if fz \
+                            else (W[f"{p}.convs1.{d}.w"], W[f"{p}.convs1.{d}.b"])
                         w2, b2 = (W[f"{p}.convs2.{d}.w2"], W[f"{p}.convs2.{d}.b2"]) if fz else (W[f"{p}.convs2.{d}.w"], W[f"{p}.convs2.{d}.b"])
                         kk = 2 * hf + 1 if fz else k
                         kw = dict(resid=iv(y_raw))
@@ -348,8 +372,8 @@ class HiFiGANGenerator:
                             kw.update(resid2=xv(xs) if j > 0 else None, beta=1.0 / self.num_kernels,
                                       out=None if last_rb else xv(xs), out_act=iv(b[f"x_act{i}"]) if last_rb else None,
                                       act_slope=0.01 if last_stage else 0.1)
-                        ops.hifi_resblock(v_in, L // 2 if fz else L, HALO // 2 if fz else HALO, w1, kk, 1 if fz else dil, b1,
-                                          w2, kk, b2, **kw)
+                        ops.hifi_resblock(v_in, L // 2 if fz else L, HALO // 2 if fz else HALO, w1, len(taps1) if fold1d else kk,
+                                          1 if fz else dil, b1, w2, kk, b2, taps1=taps1, **kw)
                         if not final:
                             y_raw, y_act = n_raw, n_act
                         continue

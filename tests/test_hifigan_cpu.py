@@ -63,3 +63,30 @@ def test_vocoder_manager_layout_rules_match_the_reference():
             pass
         else:
             raise AssertionError("expected ValueError")
+
+
+def test_time_folded_weights_equal_the_dilated_conv():
+    """Host logic of the narrow stage (kokoro_ruslan_b200/hifigan.py): a (k, dilation) conv on [L, C] equals the block-sparse
+    folded conv with the taps of _folded_taps on the time-folded view [L/2, 2C] — the operand layout the fused ResBlock
+    kernel consumes (dilation 1: contiguous taps; dilated: an explicit tap list)."""
+    import torch.nn.functional as F
+    from kokoro_ruslan_b200.hifigan import HiFiGANGenerator as G
+    torch.manual_seed(0)
+    C, L = 8, 64
+    for k in (3, 7, 11):
+        for dil in (1, 3, 5):
+            w = torch.randn(C, C, k).to(torch.bfloat16).float()
+            x = torch.randn(1, C, L)
+            want = F.conv1d(x, w, padding=dil * (k - 1) // 2, dilation=dil)[0]
+            taps = G._folded_taps(k, dil)
+            assert taps == sorted(taps) and taps[0] == -taps[-1]
+            if dil == 1:
+                hf = ((k - 1) // 2 + 1) // 2
+                assert taps == list(range(-hf, hf + 1))
+            wf = G._tap_major_time_folded(w, dil).float().view(2 * C, len(taps), 2 * C)
+            xf = x[0].t().contiguous().view(L // 2, 2 * C)
+            out = torch.zeros(L // 2, 2 * C)
+            for fi, f in enumerate(taps):
+                lo, hi = max(0, -f), min(L // 2, L // 2 - f)
+                out[lo:hi] += xf[lo + f:hi + f] @ wf[:, fi, :].t()
+            assert float((out.view(L, C).t() - want).abs().max()) < 1e-4, (k, dil)

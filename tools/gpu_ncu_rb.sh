@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:hifi_resblock_kernel -s 20 -c 1 -o gpurun_out/r02_rb -f python tools/hifigan_one.py > gpurun_out/ncu_r02_rb.log 2>&1; tail -1 gpurun_out/ncu_r02_rb.log
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:hifi_resblock_kernel -s 3 -c 1 -o gpurun_out/r02_rb -f python tools/hifigan_one.py > gpurun_out/ncu_r02_rb.log 2>&1; tail -1 gpurun_out/ncu_r02_rb.log
 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"hifi_resblock|kr_gemm" --csv --log-file gpurun_out/rb_launches.csv python tools/hifigan_one.py > /dev/null 2>&1
 python - <<'PY'
 import csv,re
