@@ -45,6 +45,10 @@ struct GemmParams {
   int m_tiles, n_tiles, total_tiles;
   int conv_taps, conv_dil, conv_row0, conv_cin_blocks;
   int conv_slab, slab_rows;   // slab mode: one [slab_rows x 64ch] load per (tile, chunk); taps = row offsets into it
+  // slab-stream mode (conv whose weights do NOT fit in smem): the activation slab of a tile is still fetched once per
+  // 64-channel block, the weight K blocks stream through the ring, and every weight block feeds `msub` 128-row sub-tiles
+  // (msub accumulators in TMEM) — the L2 -> SM traffic per MMA is what bounds these convs
+  int slab_stream, msub, slab_bufs, slab_buf_bytes, slab_box_rows, tmem_cols;
   void* C; long long ldc, c_batch_stride; int c_mode;
   bf16* C2; long long ldc2, c2_batch_stride; float act_slope;
   const float* bias;
@@ -164,7 +168,9 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
   uint64_t* bres_bar = tmem_empty_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  uint64_t* slab_full_bar = bres_bar + 1;             // [4] slab-stream mode
+  uint64_t* slab_empty_bar = slab_full_bar + 4;       // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slab_empty_bar + 4);
   uint8_t* b_res = smem + RING_OFFSET0;
   uint8_t* ring = b_res + p.b_res_bytes;
 
@@ -180,6 +186,7 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(bres_bar, 1);
+    for (int s = 0; s < 4; ++s) { mbar_init(&slab_full_bar[s], 1); mbar_init(&slab_empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       // one arrive per epilogue warp that works on the buffer: all 8, or — narrow outputs, see the epilogue — the 4 of
@@ -189,7 +196,7 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, L::TMEM_COLS);
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -214,6 +221,40 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       }
+      if (p.slab_stream) {
+        // units u = (local tile, 64-channel block); the slab of unit u + 1 is requested BEFORE the weight blocks of unit u
+        // (its buffer was released by unit u + 1 - slab_bufs, two units behind the MMA front when slab_bufs == 3)
+        const int cinb = p.conv_cin_blocks;
+        const int n_local = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int n_units = n_local * cinb;
+        uint8_t* ring_b = ring + p.slab_bufs * p.slab_buf_bytes;
+        auto slab_issue = [&](int u) {
+          if (u >= n_units) return;
+          const int lt = u / cinb, cb = u - lt * cinb;
+          const TileCoord tc = decode_tile(p, blockIdx.x + lt * gridDim.x);
+          const int sbuf = u % p.slab_bufs;
+          mbar_wait(&slab_empty_bar[sbuf], (((uint32_t)(u / p.slab_bufs)) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&slab_full_bar[sbuf], (uint32_t)p.slab_buf_bytes);
+          const int row = p.conv_row0 + tc.m_blk * BLOCK_M * p.msub;
+          for (int r = 0; r < p.slab_rows; r += p.slab_box_rows)
+            tma_load_3d(ring + sbuf * p.slab_buf_bytes + r * ROWB, &tmap_a, &slab_full_bar[sbuf], cb * BK, row + r, tc.bz);
+        };
+        slab_issue(0);
+        for (int u = 0; u < n_units; ++u) {
+          slab_issue(u + 1);
+          const int lt = u / cinb, cb = u - lt * cinb;
+          const TileCoord tc = decode_tile(p, blockIdx.x + lt * gridDim.x);
+          for (int tap = 0; tap < p.conv_taps; ++tap) {
+            const int s = ring_s;
+            const uint32_t ph = ring_ph;
+            if (++ring_s == STAGES) { ring_s = 0; ring_ph ^= 1u; }
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)L::B_BYTES);
+            tma_load_3d(ring_b + s * L::B_BYTES, &tmap_b, &full_bar[s], (tap * cinb + cb) * BK, tc.n_blk * BLOCK_N,
+                        p.b_shared ? 0 : tc.bz);
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BLOCK_N;
@@ -283,7 +324,37 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t use = (uint32_t)(lt >> 1);
         mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
+        const uint32_t tmem_d = tmem_base + buf * p.msub * BLOCK_N;
+        if (p.slab_stream) {
+          const uint8_t* ring_b = ring + p.slab_bufs * p.slab_buf_bytes;
+          for (int cb = 0; cb < p.conv_cin_blocks; ++cb) {
+            const int u = lt * p.conv_cin_blocks + cb;
+            const int sbuf = u % p.slab_bufs;
+            mbar_wait(&slab_full_bar[sbuf], ((uint32_t)(u / p.slab_bufs)) & 1u);
+            tc_fence_after();
+            const uint32_t slab = smem_u32(ring + sbuf * p.slab_buf_bytes);
+            for (int tap = 0; tap < p.conv_taps; ++tap) {
+              const int s = ring_s;
+              const uint32_t ph = ring_ph;
+              if (++ring_s == STAGES) { ring_s = 0; ring_ph ^= 1u; }
+              mbar_wait(&full_bar[s], ph);
+              tc_fence_after();
+              const uint32_t sb = smem_u32(ring_b + s * L::B_BYTES);
+              const uint32_t acc = (cb > 0 || tap > 0) ? 1u : 0u;
+              for (int sub = 0; sub < p.msub; ++sub) {
+                const uint32_t sa = slab + (tap * p.conv_dil + sub * BLOCK_M) * ROWB;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                  umma_bf16_ss(tmem_d + sub * BLOCK_N, make_smem_desc_sw(sa + k * 32, 16, SBO, LAYOUT),
+                               make_smem_desc_sw(sb + k * b_kstep, b_lbo, SBO, LAYOUT), idesc, (acc | (k > 0)) ? 1u : 0u);
+              }
+              umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&slab_empty_bar[sbuf]);
+          }
+          umma_commit(&tmem_full_bar[buf]);
+          continue;
+        }
         if (p.conv_slab) {
           const int s = ring_s;
           const uint32_t ph = ring_ph;
@@ -353,12 +424,12 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       if (tile_alt && (lt & 1) != half) continue;
       const TileCoord tc = decode_tile(p, tile);
-      const int mw0 = tc.m_blk * BLOCK_M + lg * 32;   // first row of this warp's 32-row slab
+      for (int sub = 0; sub < p.msub; ++sub) {        // 128-row sub-tiles of the tile (1 except in slab-stream mode)
+      const int mw0 = (tc.m_blk * p.msub + sub) * BLOCK_M + lg * 32;   // first row of this warp's 32-row slab
       const int n0 = tc.n_blk * BLOCK_N;
       const int buf = lt & 1;
       const uint32_t use = (uint32_t)(lt >> 1);
-      mbar_wait(&tmem_full_bar[buf], use & 1);
-      tc_fence_after();
+      if (sub == 0) { mbar_wait(&tmem_full_bar[buf], use & 1); tc_fence_after(); }
       const bool first_split = (tc.split == 0);
       const bool use_bias = p.bias != nullptr && first_split;
       const bool use_resid = p.resid != nullptr && first_split;
@@ -420,7 +491,7 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // (2) accumulator chunk: TMEM -> registers (row layout) -> smem (16-byte slots XOR-swizzled by row:
         //     conflict-free both ways)
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + buf * BLOCK_N + (static_cast<uint32_t>(lg * 32) << 16) + c * 32, r);
+        tmem_ld_32x32(tmem_base + (buf * p.msub + sub) * BLOCK_N + (static_cast<uint32_t>(lg * 32) << 16) + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -503,16 +574,17 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         __syncwarp();  // staging buffer is reused by the next chunk; also reconverges for tcgen05.ld
       }
+      }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[lt & 1]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, L::TMEM_COLS);
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -526,6 +598,19 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta_slab, const CUtenso
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL + 1024);
     if (e != cudaSuccess) { kr_set_error(cudaGetErrorString(e)); return KR_ERR_CUDA; }
     attr_set = true;
+  }
+  {
+    int cols = L::TMEM_COLS;
+    while (cols < 2 * p.msub * BLOCK_N) cols *= 2;
+    p.tmem_cols = cols;                                    // <= 512: kr_gemm_ex only picks msub = 2 for BLOCK_N <= 128
+  }
+  if (p.slab_stream) {   // geometry chosen by kr_gemm_ex: slab buffers first, then p.stages weight stages
+    p.b_resident = 0; p.b_res_bytes = 0; p.conv_slab = 0; p.stage_bytes = L::B_BYTES;
+    const int smem_ss = RING_OFFSET0 + p.slab_bufs * p.slab_buf_bytes + p.stages * L::B_BYTES + 1024;
+    const int grid_ss = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    kr::launch(kern, grid_ss, GEMM_THREADS, smem_ss, st, ta_slab, tb, p);
+    KR_CHECK_LAUNCH();
+    return KR_OK;
   }
   // ring geometry: keep the weight operand resident when it fits next to >= 4 A-only stages
   const int avail = SMEM_TOTAL - RING_OFFSET0;
@@ -699,6 +784,7 @@ extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
   if (rc != KR_OK) return rc;
 
   GemmParams p{};
+  p.msub = 1;
   p.M = M; p.N = N; p.K = K; p.batch = batch; p.splits = splits; p.kb_per_split = kb_per_split;
   p.total_kb = total_kb; p.m_tiles = m_tiles; p.n_tiles = (N + block_n - 1) / block_n;
   p.total_tiles = p.m_tiles * p.n_tiles * batch * splits;
@@ -723,7 +809,39 @@ extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
   // slab tensor map: same tensor, box = all rows a tile touches (128 + (taps-1)*dil, rounded up to 8)
   CUtensorMap ta_slab = ta;
   int slab_rows = 0;
-  if (conv && res && a->conv_taps > 1 && !a->no_slab) {
+  // weights that cannot stay resident (launch_gemm's rule): slab-stream mode — activation slab per (tile, 64-channel
+  // block), streamed weight blocks, two 128-row sub-tiles per weight block when two double-buffered accumulator pairs fit
+  // in TMEM.  Measured on B200 (HiFi-GAN C = 128 / 256 stages): the per-tap path moves A + B tiles = 32 KB from L2 per 4
+  // MMAs, ~3x the ~42 B/clk/SM the L2 delivers chip-wide, and ran at 0.55 - 0.9 PFLOP/s.
+  {
+    const int avail = SMEM_TOTAL - RING_OFFSET0;
+    const long long b_bytes = (long long)block_n * bk * 2, a_bytes = (long long)BLOCK_M * bk * 2;
+    const bool resident_fits = res && (long long)total_kb * b_bytes + 4 * a_bytes <= avail;
+    if (conv && a->conv_taps > 1 && !a->no_slab && !resident_fits && bk == BLOCK_K && !a->b_mn_major && splits == 1 &&
+        (batch == 1 || b_shared)) {
+      // two sub-tiles per weight block only while the halved tile count still fills the machine
+      const long long tiles2 = (long long)((m_tiles + 1) / 2) * p.n_tiles * batch;
+      for (int msub = (block_n <= 128 && tiles2 >= kNumSMs) ? 2 : 1; msub >= 1 && !p.slab_stream; --msub) {
+        const int rows = (BLOCK_M * msub + (a->conv_taps - 1) * a->conv_dil + 15) / 16 * 16;
+        if (rows > 512) continue;
+        const int bytes = rows * BLOCK_K * 2;
+        for (int bufs = 3; bufs >= 2 && !p.slab_stream; --bufs) {
+          long long stages = (avail - (long long)bufs * bytes) / b_bytes;
+          if (stages < 3) continue;
+          p.slab_stream = 1; p.msub = msub; p.slab_bufs = bufs; p.slab_buf_bytes = bytes; p.slab_rows = rows;
+          p.slab_box_rows = rows > 256 ? rows / 2 : rows;
+          p.stages = (int)(stages > MAX_STAGES ? MAX_STAGES : stages);
+        }
+      }
+      if (p.slab_stream) {
+        p.m_tiles = (M + BLOCK_M * p.msub - 1) / (BLOCK_M * p.msub);
+        p.total_tiles = p.m_tiles * p.n_tiles * batch * splits;
+        rc = kr_make_tmap_bf16_3d(&ta_slab, a->A, a->conv_cin, a->a_rows, batch, a->lda, bstride_a, bk, p.slab_box_rows);
+        if (rc != KR_OK) return rc;
+      }
+    }
+  }
+  if (!p.slab_stream && conv && res && a->conv_taps > 1 && !a->no_slab) {
     slab_rows = (BLOCK_M + (a->conv_taps - 1) * a->conv_dil + 7) / 8 * 8;
     if (slab_rows <= 256) {
       rc = kr_make_tmap_bf16_3d(&ta_slab, a->A, a->conv_cin, a->a_rows, batch, a->lda, bstride_a, bk, slab_rows, bk == 32);

@@ -144,3 +144,44 @@ def test_conv1d_slab_mode_matches_tap_refetch(cin, cout, k, dil):
     assert (outs[0] - ref).abs().max().item() / scale < 5e-3
     assert (outs[1] - ref).abs().max().item() / scale < 5e-3, "slab mode differs from torch"
     assert torch.equal(outs[0], outs[1]), "slab mode is not bit-identical to the tap re-fetch path"
+
+
+@pytest.mark.parametrize("cin,cout,k,dil,Bn,L", [(128, 128, 7, 3, 3, 256 * 60 + 37), (128, 128, 11, 5, 3, 256 * 60 + 200),
+                                                  (256, 256, 3, 1, 2, 128 * 90 + 5), (256, 256, 11, 5, 2, 128 * 80),
+                                                  (64, 64, 11, 1, 4, 256 * 50 + 129), (64, 64, 11, 5, 1, 700),
+                                                  (512, 256, 7, 1, 1, 1000)])
+def test_conv1d_slab_stream_mode(cin, cout, k, dil, Bn, L):
+    """Convs whose weights do NOT fit in shared memory (the 128 / 256-channel HiFi-GAN stages, k = 11 of the 64-channel
+    one): activation slab per (tile, 64-channel block), streamed weight blocks, two 128-row sub-tiles per block where TMEM
+    allows.  Against torch and against the tap re-fetch path (same products, different fp32 summation order), including
+    the fused residual / MRF / activation epilogue on ragged row counts."""
+    from kokoro_ruslan_b200 import ops
+    halo = 32
+    pad = dil * (k - 1) // 2
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(Bn, cin, L, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(cout, generator=g)
+    resid = torch.randn(Bn, L, cout, generator=g)
+    resid2 = torch.randn(Bn, L, cout, generator=g)
+    conv = torch.nn.functional.conv1d(x.float(), w.float(), bias, padding=pad, dilation=dil).permute(0, 2, 1)
+    want = (conv + resid) * (1.0 / 3.0) + resid2
+    xcl = torch.zeros(Bn, L + 2 * halo, cin, dtype=torch.bfloat16, device="cuda")
+    xcl[:, halo:halo + L] = x.permute(0, 2, 1).cuda()
+    wt = w.permute(0, 2, 1).reshape(cout, k * cin).contiguous().cuda()
+    outs, acts = [], []
+    for no_slab in (True, False):
+        out = torch.zeros(Bn, L, cout, dtype=torch.float32, device="cuda")
+        act = torch.zeros(Bn, L + 2 * halo, cout, dtype=torch.bfloat16, device="cuda")
+        ops.conv1d_cl(xcl, wt, rows=L, row0=halo - pad, taps=k, dil=dil, bias=bias.cuda(), out=out,
+                      out_act=act[:, halo:halo + L], act_slope=0.1, resid=resid.cuda(), resid2=resid2.cuda(), beta=1.0 / 3.0,
+                      no_slab=no_slab)
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+        acts.append(act.float().cpu())
+    scale = want.abs().max().item()
+    assert (outs[1] - want).abs().max().item() / scale < 5e-3
+    assert (outs[1] - outs[0]).abs().max().item() / scale < 1e-5
+    assert float(acts[1][:, :halo].abs().max()) == 0.0 and float(acts[1][:, halo + L:].abs().max()) == 0.0
+    lre = torch.nn.functional.leaky_relu(outs[1], 0.1)
+    assert (acts[1][:, halo:halo + L] - lre).abs().max().item() / scale < 1e-2
