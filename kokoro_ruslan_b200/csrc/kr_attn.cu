@@ -448,7 +448,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 14 * TILE_BYTES);
   uint64_t* kv_bar = bars;
   uint64_t* qdo_bar = bars + 1;   // [2]
-  uint64_t* sdp_bar = bars + 3;   // [2] one per 64-key half of the S / dP tiles
+  uint64_t* s_bar = bars + 3;     // S(it) complete: the exp2 half of the softmax starts while dP is still in the tensor pipe
+  uint64_t* dp_bar = bars + 4;    // dP(it) complete
   uint64_t* out_bar = bars + 5;
   uint64_t* soft_bar = bars + 6;  // [2] one per half (128 threads each)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
@@ -464,7 +465,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     mbar_init(kv_bar, 1); mbar_init(&qdo_bar[0], 1); mbar_init(&qdo_bar[1], 1);
-    mbar_init(&sdp_bar[0], 1); mbar_init(&sdp_bar[1], 1); mbar_init(out_bar, 1);
+    mbar_init(s_bar, 1); mbar_init(dp_bar, 1); mbar_init(out_bar, 1);
     mbar_init(&soft_bar[0], 128); mbar_init(&soft_bar[1], 128);
     fence_barrier_init();
   }
@@ -507,11 +508,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16_ss(tmem_S, desc_k64(aQ, k), desc_k64(aK, k), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_bar);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16_ss(tmem_dP, desc_k64(adO, k), desc_k64(aV, k), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&sdp_bar[0]);
-        umma_commit(&sdp_bar[1]);
+        umma_commit(dp_bar);
       };
       mbar_wait(kv_bar, 0);
       mbar_wait(&qdo_bar[0], 0);
@@ -560,83 +561,124 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (DROP) dkey = drop_key(p.drop.state, p.drop.site_a);
     const float dp_scale = DROP ? p.scale * p.drop.scale : p.scale;   // dP_eff = mask * dP / keep
 
-    auto dq_flush = [&](int it_done) {       // dQ tile of iteration it_done: this thread owns 32 columns of one row
-      const int qi = (i_begin + it_done) * TQ + row;
+    // dQ tile of iteration it_done -> fp32 dQ buffer (vector atomics).  The thread's 32 columns of its TMEM row are
+    // transposed through a swizzled 4 KB staging tile so that every warp instruction adds 4 rows x 128 CONTIGUOUS bytes
+    // (a row-per-thread RED touched 32 separate lines per instruction: 2048 LSU wavefronts per iteration and SM, measured
+    // 12 of 97 us at 8 x 8 x 800 x 800).  The staging tile is the warp's own 32-row x 64-key block of the P tile of that
+    // iteration, which MMA2(it_done) has finished reading and which this warp rewrites next in soft(it_done + 2).
+    auto dq_flush = [&](int it_done) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_dQ + t_lane + ch * 32, r);
       tmem_ld_wait();
-      if (qi < p.Sq && p.dQ != nullptr) {
-        float* dq = p.dQ + (long long)b * p.dq_bs + (long long)qi * p.dq_ss + h * HD + ch * 32;
+      if (p.dQ != nullptr) {
+        float* stg = reinterpret_cast<float*>(sP + (it_done & 1) * 2 * TILE_BYTES + ch * TILE_BYTES + lg * 4096);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          atomicAdd(reinterpret_cast<float4*>(dq + 4 * e),
-                    make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]),
-                                __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3])));
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+              make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        __syncwarp();
+        const int crow = lane >> 3, xs = lane & 7;
+        const int q_first = (i_begin + it_done) * TQ + lg * 32 + crow;       // this lane's rows: q_first + 4 * i
+        float* dq = p.dQ + (long long)b * p.dq_bs + (long long)q_first * p.dq_ss + h * HD + ch * 32 + 4 * xs;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + crow) * 32 + ((xs ^ (((i & 1) << 2) | crow)) << 2));
+          if (q_first + 4 * i < p.Sq) atomicAdd(reinterpret_cast<float4*>(dq + (long long)(4 * i) * p.dq_ss), v);
+        }
       }
       __syncwarp();
     };
 
+    // lse / delta of the NEXT query tile are requested one iteration ahead (their L2 latency was 10 % of the samples)
+    float lse_nx = 0.f, delta_nx = 0.f;
+    if (i_begin * TQ + row < p.Sq) {
+      lse_nx = p.lse[bh * p.Sq + i_begin * TQ + row];
+      delta_nx = p.delta[bh * p.Sq + i_begin * TQ + row];
+    }
     for (int it = 0; it < n_it; ++it) {
       const int q0 = (i_begin + it) * TQ;
       const int qi = q0 + row;
       const bool row_ok = qi < p.Sq;
-      const float lse_i = row_ok ? p.lse[bh * p.Sq + qi] : 0.f;
-      const float delta_i = row_ok ? p.delta[bh * p.Sq + qi] : 0.f;
+      const float lse_i = lse_nx, delta_i = delta_nx;
+      if (it + 1 < n_it && qi + TQ < p.Sq) {
+        lse_nx = p.lse[bh * p.Sq + qi + TQ];
+        delta_nx = p.delta[bh * p.Sq + qi + TQ];
+      } else {
+        lse_nx = 0.f; delta_nx = 0.f;
+      }
       uint8_t* tP = sP + (it & 1) * 2 * TILE_BYTES;
       uint8_t* tdS = sdS + (it & 1) * 2 * TILE_BYTES;
-      mbar_wait(&sdp_bar[ch], it & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = 2 * ch + cc;            // 32-column chunk of the 128-key tile
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32(tmem_S + t_lane + c * 32, rs);
-        tmem_ld_32x32(tmem_dP + t_lane + c * 32, rp);
-        tmem_ld_wait();
-        uint32_t ok = allowed_bits(cc == 0 ? mw0 : mw1, CAUSAL, kv0 + c * 32, qi);
-        if (!row_ok) ok = 0u;
-        const float nds = -delta_i * p.scale;
-        uint32_t pkP[16], pkS[16];
-        if (DROP) {
-          const uint32_t prow = (uint32_t)(bh * p.Sq + min(qi, p.Sq - 1)) * p.sk_pad_quarter + ((kv0 + c * 32) >> 2);
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nlse2 = make_float2(-lse_i, -lse_i);
+      const float nds = -delta_i * p.scale;
+      const float2 dps2 = make_float2(dp_scale, dp_scale), nds2 = make_float2(nds, nds);
+      // The softmax half of the backward is ISSUE- and latency-bound (2 warps per sub-partition, ~950 instructions per
+      // thread and iteration before this version; 16 compute warps were measured slower — 96 vs 86 us — because the
+      // per-warp overhead doubles): packed fp32x2 FMAs, masks applied as bit operations (-inf on the S bits of disallowed
+      // keys; dropout keep bytes expanded by PRMT and ANDed), a warp-uniform branch for the common nothing-masked tile.
+      // Both 32-key chunks of the thread are in flight together: the dropout hashes run BEFORE the wait for S (while
+      // MMA1 executes), the two S loads share one tcgen05.wait, and the second dP load flies under the first dS chunk.
+      uint32_t rs0[32], rs1[32], dm0[8], dm1[8];
+      uint32_t ok0 = allowed_bits(mw0, CAUSAL, kv0 + (2 * ch) * 32, qi);
+      uint32_t ok1 = allowed_bits(mw1, CAUSAL, kv0 + (2 * ch + 1) * 32, qi);
+      if (!row_ok) { ok0 = 0u; ok1 = 0u; }
+      if (DROP) {
+        const uint32_t prow = (uint32_t)(bh * p.Sq + min(qi, p.Sq - 1)) * p.sk_pad_quarter + ((kv0 + 2 * ch * 32) >> 2);
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const uint32_t m = drop_quad_bytes(prow + (e >> 2), dkey, p.thr4);
-            float pv[4], gv[4];
+        for (int e = 0; e < 8; ++e) { dm0[e] = drop_quad_bytes(prow + e, dkey, p.thr4); dm1[e] = drop_quad_bytes(prow + 8 + e, dkey, p.thr4); }
+      }
+      const bool all_ok = __all_sync(0xffffffffu, (ok0 & ok1) == 0xffffffffu);
+      // P = exp2(S * scale - lse): fp32 kept in rs for dS, bf16 (dropout-masked: dV += (mask P)^T dO, 1/keep at the store) -> smem
+      auto p_chunk = [&](uint32_t (&rs)[32], const uint32_t (&dm)[8], uint32_t ok, int c) {
+        uint32_t pk[16];
+        if (!all_ok) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float pe = fast_exp2(fmaf(__uint_as_float(rs[e + t]), p.scale_log2, -lse_i));
-              pv[t] = ((ok >> (e + t)) & 1u) ? pe : 0.f;
-              gv[t] = ((m >> (8 * t)) & 1u) ? __uint_as_float(rp[e + t]) : 0.f;
-            }
-            pkP[e >> 1] = pack_bf16(pv[0], pv[1]) & keep_lo_pair(m);          // dV += (mask P)^T dO  (1/keep at the store)
-            pkP[(e >> 1) + 1] = pack_bf16(pv[2], pv[3]) & keep_hi_pair(m);
-            pkS[e >> 1] = pack_bf16(pv[0] * fmaf(gv[0], dp_scale, nds), pv[1] * fmaf(gv[1], dp_scale, nds));
-            pkS[(e >> 1) + 1] = pack_bf16(pv[2] * fmaf(gv[2], dp_scale, nds), pv[3] * fmaf(gv[3], dp_scale, nds));
-          }
-        } else if (__all_sync(0xffffffffu, ok == 0xffffffffu)) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse_i));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse_i));
-            pkP[e >> 1] = pack_bf16(p0, p1);
-            pkS[e >> 1] = pack_bf16(p0 * fmaf(__uint_as_float(rp[e]), p.scale, nds),
-                                    p1 * fmaf(__uint_as_float(rp[e + 1]), p.scale, nds));
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float p0 = fast_exp2(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse_i));
-            float p1 = fast_exp2(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse_i));
-            p0 = ((ok >> e) & 1u) ? p0 : 0.f;
-            p1 = ((ok >> (e + 1)) & 1u) ? p1 : 0.f;
-            pkP[e >> 1] = pack_bf16(p0, p1);
-            pkS[e >> 1] = pack_bf16(p0 * fmaf(__uint_as_float(rp[e]), p.scale, nds),
-                                    p1 * fmaf(__uint_as_float(rp[e + 1]), p.scale, nds));
-          }
+          for (int e = 0; e < 32; ++e) rs[e] = ((ok >> e) & 1u) ? rs[e] : 0xff800000u;   // -inf: exp2 -> 0
         }
-        store_chunk_sw128(tP, row, c, pkP);
-        store_chunk_sw128(tdS, row, c, pkS);
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float2 a = __ffma2_rn(make_float2(__uint_as_float(rs[e]), __uint_as_float(rs[e + 1])), sc2, nlse2);
+          const float p0 = fast_exp2(a.x), p1 = fast_exp2(a.y);
+          rs[e] = __float_as_uint(p0); rs[e + 1] = __float_as_uint(p1);
+          pk[e >> 1] = pack_bf16(p0, p1);
+        }
+        if (DROP) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { pk[2 * e] &= keep_lo_pair(dm[e]); pk[2 * e + 1] &= keep_hi_pair(dm[e]); }
+        }
+        store_chunk_sw128(tP, row, c, pk);
+      };
+      // dS = P * (mask * dP / keep - delta) * scale -> smem
+      auto ds_chunk = [&](uint32_t (&rp)[32], const uint32_t (&rs)[32], const uint32_t (&dm)[8], int c) {
+        uint32_t pk[16];
+        if (DROP) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) rp[e] &= __byte_perm(dm[e >> 2], 0u, 0x1111u * (e & 3));
+        }
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float2 t = __ffma2_rn(make_float2(__uint_as_float(rp[e]), __uint_as_float(rp[e + 1])), dps2, nds2);
+          const float2 d = __fmul2_rn(make_float2(__uint_as_float(rs[e]), __uint_as_float(rs[e + 1])), t);
+          pk[e >> 1] = pack_bf16(d.x, d.y);
+        }
+        store_chunk_sw128(tdS, row, c, pk);
+      };
+      mbar_wait(s_bar, it & 1);
+      tc_fence_after();
+      tmem_ld_32x32(tmem_S + t_lane + (2 * ch) * 32, rs0);
+      tmem_ld_32x32(tmem_S + t_lane + (2 * ch + 1) * 32, rs1);
+      tmem_ld_wait();
+      p_chunk(rs0, dm0, ok0, 2 * ch);
+      p_chunk(rs1, dm1, ok1, 2 * ch + 1);
+      {
+        uint32_t rp0[32], rp1[32];
+        mbar_wait(dp_bar, it & 1);
+        tc_fence_after();
+        tmem_ld_32x32(tmem_dP + t_lane + (2 * ch) * 32, rp0);
+        tmem_ld_wait();
+        tmem_ld_32x32(tmem_dP + t_lane + (2 * ch + 1) * 32, rp1);
+        ds_chunk(rp0, rs0, dm0, 2 * ch);
+        tmem_ld_wait();
+        ds_chunk(rp1, rs1, dm1, 2 * ch + 1);
       }
       if (it > 0) {
         mbar_wait(out_bar, (it - 1) & 1);     // MMA2(it-1) done: its dQ tile is complete

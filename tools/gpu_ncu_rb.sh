@@ -1,6 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:hifi_resblock_kernel -s 3 -c 1 -o gpurun_out/r02_rb -f python tools/hifigan_one.py > gpurun_out/ncu_r02_rb.log 2>&1; tail -1 gpurun_out/ncu_r02_rb.log
 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"hifi_resblock|kr_gemm" --csv --log-file gpurun_out/rb_launches.csv python tools/hifigan_one.py > /dev/null 2>&1
 python - <<'PY'
 import csv,re
@@ -14,7 +13,7 @@ for r in rows:
     if n=="gpu__time_duration.sum": v = v/1000.0 if u.startswith("n") else v
     else: v*={"byte":1,"Kbyte":1e3,"Mbyte":1e6,"Gbyte":1e9}.get(u,1)
     per[k][n]=v; per[k]["kernel"]=r["Kernel Name"]
-ids=order[len(order)//2:]
+ids=order[-68:]
 for i,k in enumerate(ids):
     x=per[k]; t=x["gpu__time_duration.sum"]; rd=x.get("dram__bytes_read.sum",0); wr=x.get("dram__bytes_write.sum",0)
     nm="RB" if "resblock" in x["kernel"] else re.sub(r".*kr_gemm_kernel<([^>]*)>.*",r"\1",x["kernel"])
