@@ -174,8 +174,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
   constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+  // A partial last key tile is computed only on its 32-key chunks that hold real keys: S MMA with N = 32 * nck, the
+  // softmax over nck chunks, P V over 32 * nck keys (at Sk = 800 the seventh tile has 32 keys: 3/4 of its work is skipped).
+  auto nck_of = [&](int j) { return min(4, (p.Sk - j * TK + 31) >> 5); };
 
   if (warp == 9) {
     // ------------------------------------------------------------------ TMA producer
@@ -202,6 +204,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int w = 0; w < 2; ++w) {
         if (n_w[w] > 0) {
           const uint32_t aQ = smem_u32(sQ + w * TILE_BYTES), aK = smem_u32(sK);
+          const uint32_t idesc_s = make_idesc_bf16(128, 32 * nck_of(0), 0, 0);
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k)
             umma_bf16_ss(tmem_base + w * 128, desc_k64(aQ, k), desc_k64(aK, k), idesc_s, k > 0 ? 1u : 0u);
@@ -218,14 +221,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc_fence_after();
           const uint32_t tS = tmem_base + w * 128, tP = tmem_base + 256 + w * 64, tO = tmem_base + 384 + w * 64;
           const uint32_t aV = smem_u32(sV + st * TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < TK / 16; ++k)       // 16 keys = 8 packed TMEM columns per MMA
+          const int ksteps = 2 * nck_of(j);
+          for (int k = 0; k < ksteps; ++k)        // 16 keys = 8 packed TMEM columns per MMA
             umma_bf16_ts(tO, tP + k * 8, desc_mn64(aV, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
           if (j + 1 < n_w[w]) {
             const int ns = (j + 1) % FWD_STAGES;
             mbar_wait(&k_full[ns], ((j + 1) / FWD_STAGES) & 1);
             tc_fence_after();
             const uint32_t aQ = smem_u32(sQ + w * TILE_BYTES), aK = smem_u32(sK + ns * TILE_BYTES);
+            const uint32_t idesc_s = make_idesc_bf16(128, 32 * nck_of(j + 1), 0, 0);
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k)
               umma_bf16_ss(tS, desc_k64(aQ, k), desc_k64(aK, k), idesc_s, k > 0 ? 1u : 0u);
@@ -263,11 +267,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float2 rs2 = make_float2(0.f, 0.f);
       float mx0 = -INFINITY, mx1 = -INFINITY;
       uint32_t buf[2][32];
+      const int nck = nck_of(j);
       tmem_ld_32x32(tS, buf[0]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         tmem_ld_wait();
-        if (c + 1 < 4) tmem_ld_32x32(tS + (c + 1) * 32, buf[(c + 1) & 1]);
+        if (c + 1 < 4) tmem_ld_32x32(tS + (c + 1) * 32, buf[(c + 1) & 1]);   // (stale columns beyond nck are loaded, not used)
+        if (c < nck) {                              // CTA-uniform: chunks beyond the last real key are skipped
         uint32_t (&r)[32] = buf[c & 1];
         const uint32_t ok = allowed_bits(mask_words[j * 4 + c], CAUSAL, j * TK + c * 32, qi);
         if (!__all_sync(0xffffffffu, ok == 0xffffffffu)) {
@@ -299,6 +305,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             pk[(i >> 1) + 1] = u1;
           }
           tmem_st_32x16(tP + c * 16, pk);            // packed: 32-bit column k holds keys (2k, 2k+1)
+        }
         }
       }
       tile_max = fmaxf(mx0, mx1) * p.scale_log2;     // scale > 0: max commutes with it
@@ -456,10 +463,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t* mask_words = tmem_slot + 2;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kv0 = blockIdx.x * TK, h = blockIdx.y, b = blockIdx.z;
+  // 1-D grid, key tile outermost: the CTAs of key tile 0 (the longest under a causal mask) are scheduled first and those
+  // of the last, usually partial, key tile last — they fill the tail of the final wave (448 CTAs on 148 SMs at 8 x 8 x 800)
+  const int per_tile = p.H * p.B;
+  const int ktile = (int)blockIdx.x / per_tile, hb = (int)blockIdx.x - ktile * per_tile;
+  const int kv0 = ktile * TK, h = hb % p.H, b = hb / p.H;
   const int n_q_tiles = (p.Sq + TQ - 1) / TQ;
-  const int i_begin = CAUSAL ? (int)blockIdx.x : 0;
+  const int i_begin = CAUSAL ? ktile : 0;
   const int n_it = n_q_tiles - i_begin;
+  // partial key tile: only the 32-key chunks that hold real keys are computed — S / dP MMAs with N = 32 * nck, the
+  // softmax on nck chunks, the dQ contraction over 32 * nck keys.  The other columns of the P / dS tiles are never
+  // written; they only reach rows of dV / dK beyond Sk, which are not stored.
+  const int nck = (min(TK, p.Sk - kv0) + 31) >> 5;
   pdl_launch_dependents();
 
   if (tid == 0) {
@@ -484,7 +499,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dV = tmem_base + 256,
                  tmem_dK = tmem_base + 320, tmem_dQ = tmem_base + 384;
-  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);    // S, dP
+  const uint32_t idesc_s = make_idesc_bf16(128, 32 * nck, 0, 0);   // S, dP
   constexpr uint32_t idesc_tt = make_idesc_bf16(128, 64, 1, 1);    // dV, dK
   constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);    // dQ
 
@@ -538,7 +553,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int k = 0; k < TQ / 16; ++k)   // dK[kv,d] += dS^T Q
             umma_bf16_ss(tmem_dK, desc_mn128(adS, k), desc_mn64(aQ, k), idesc_tt, (it > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < TK / 16; ++k)   // dQ[q,d] = dS K, contraction over the 128 keys
+          for (int k = 0; k < 2 * nck; ++k)   // dQ[q,d] = dS K, contraction over the (computed) keys
             umma_bf16_ss(tmem_dQ, desc_k128(adS, k), desc_mn64(aK, k), idesc_dq, k > 0 ? 1u : 0u);
           umma_commit(out_bar);
         }
@@ -621,7 +636,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t ok0 = allowed_bits(mw0, CAUSAL, kv0 + (2 * ch) * 32, qi);
       uint32_t ok1 = allowed_bits(mw1, CAUSAL, kv0 + (2 * ch + 1) * 32, qi);
       if (!row_ok) { ok0 = 0u; ok1 = 0u; }
-      if (DROP) {
+      if (DROP && 2 * ch < nck) {
         const uint32_t prow = (uint32_t)(bh * p.Sq + min(qi, p.Sq - 1)) * p.sk_pad_quarter + ((kv0 + 2 * ch * 32) >> 2);
 #pragma unroll
         for (int e = 0; e < 8; ++e) { dm0[e] = drop_quad_bytes(prow + e, dkey, p.thr4); dm1[e] = drop_quad_bytes(prow + 8 + e, dkey, p.thr4); }
@@ -662,23 +677,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         store_chunk_sw128(tdS, row, c, pk);
       };
+      const bool do0 = 2 * ch < nck, do1 = 2 * ch + 1 < nck;      // CTA-uniform: chunks beyond the last real key are skipped
       mbar_wait(s_bar, it & 1);
       tc_fence_after();
-      tmem_ld_32x32(tmem_S + t_lane + (2 * ch) * 32, rs0);
-      tmem_ld_32x32(tmem_S + t_lane + (2 * ch + 1) * 32, rs1);
-      tmem_ld_wait();
-      p_chunk(rs0, dm0, ok0, 2 * ch);
-      p_chunk(rs1, dm1, ok1, 2 * ch + 1);
-      {
+      if (do0) {
+        tmem_ld_32x32(tmem_S + t_lane + (2 * ch) * 32, rs0);
+        if (do1) tmem_ld_32x32(tmem_S + t_lane + (2 * ch + 1) * 32, rs1);
+        tmem_ld_wait();
+        p_chunk(rs0, dm0, ok0, 2 * ch);
+        if (do1) p_chunk(rs1, dm1, ok1, 2 * ch + 1);
+      }
+      mbar_wait(dp_bar, it & 1);
+      tc_fence_after();
+      if (do0) {
         uint32_t rp0[32], rp1[32];
-        mbar_wait(dp_bar, it & 1);
-        tc_fence_after();
         tmem_ld_32x32(tmem_dP + t_lane + (2 * ch) * 32, rp0);
         tmem_ld_wait();
-        tmem_ld_32x32(tmem_dP + t_lane + (2 * ch + 1) * 32, rp1);
+        if (do1) tmem_ld_32x32(tmem_dP + t_lane + (2 * ch + 1) * 32, rp1);
         ds_chunk(rp0, rs0, dm0, 2 * ch);
         tmem_ld_wait();
-        ds_chunk(rp1, rs1, dm1, 2 * ch + 1);
+        if (do1) ds_chunk(rp1, rs1, dm1, 2 * ch + 1);
       }
       if (it > 0) {
         mbar_wait(out_bar, (it - 1) & 1);     // MMA2(it-1) done: its dQ tile is complete
@@ -827,7 +845,7 @@ extern "C" int kr_attn_bwd(const void* q, long long q_ss, long long q_bs, const 
     cudaFuncSetAttribute(attn_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
     attr = true;
   }
-  dim3 grid((Sk + TK - 1) / TK, H, B);
+  dim3 grid(((Sk + TK - 1) / TK) * H * B, 1, 1);
   const bool dr = p.drop.state != nullptr;
   if (causal && dr)  kr::launch(attn_bwd_kernel<true, true>, grid, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, p);
   else if (causal)   kr::launch(attn_bwd_kernel<true, false>, grid, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, p);
