@@ -290,8 +290,9 @@ def hifigan_leg(peaks, steps: int = 10, B: int = 16, T: int = 800):
     try:
         import glob
         with open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_hifigan_traffic*.json")))[-1]) as f:
-            tr = json.load(f)["kr_gemm_kernel"]
-        traffic = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / 2.0    # the capture holds two forwards
+            tr = json.load(f)
+        convs = [tr[k] for k in ("kr_gemm_kernel", "hifi_resblock_kernel") if k in tr]
+        traffic = sum(c["dram_read_bytes"] + c["dram_write_bytes"] for c in convs) / float(tr.get("_forwards_in_capture", 2))
     except Exception:
         pass
     return {"metric": "hifigan_audio_samples_per_sec", "value": samples / (ms * 1e-3), "unit": "samples/s",
@@ -299,12 +300,13 @@ def hifigan_leg(peaks, steps: int = 10, B: int = 16, T: int = 800):
                                            "dtype": "bf16 tcgen05 implicit-GEMM convs, fp32 residual stream"},
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_batch": ms_e2e,
                     "h2d_bytes_per_step": mel_host.numel() * 4, "d2h_bytes_per_step": samples * 4},
-            "roofline": {"bound": "hbm", "kernel": "kr_gemm_kernel conv mode (77 launches per forward)",
+            "roofline": {"bound": "hbm", "kernel": "kr_gemm_kernel conv mode + hifi_resblock_kernel (%d launches per forward)" % gen.launches_last_forward,
                          "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": alg_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
                          "tensor_frac": flops / (ms * 1e-3) / 1e12 / peaks["tf_sustained"],
                          "note": "algorithmic bytes = 2.03 MB/frame (bf16, each conv reads its input and writes its output "
-                                 "once); traffic = ncu dram bytes of the conv kernels per forward"},
+                                 "once; the fp32 residual stream this implementation keeps for accuracy is NOT in it); traffic = ncu dram bytes "
+                                 "of the conv kernels per forward (profiles/r02_hifigan_traffic.json)"},
             "gpu_launches": gen.launches_last_forward * steps * 2}
 
 
