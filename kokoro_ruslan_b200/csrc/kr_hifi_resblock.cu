@@ -9,22 +9,27 @@
 // With two kr_gemm_ex launches the intermediate t costs a bf16 write and a bf16 read of the whole activation per step —
 // 26 % of the step's DRAM traffic on the HBM-bound 64-channel stage, and a second kernel's worth of per-tile latency on
 // the narrow one.  Here both implicit GEMMs run back to back on the tensor cores, with the weights of BOTH convs resident
-// in shared memory (streaming a [C x 64] weight block per 4 MMAs would need the SM's whole 64 B / cycle L2 port: the
-// kernel refuses shapes whose weights do not fit; the caller keeps the two-launch path for those):
+// in shared memory (streaming a weight block per few MMAs would need the SM's whole 64 B / cycle L2 port: the kernel
+// refuses shapes whose weights do not fit; the caller keeps the two-launch path for those).
 //
-//   tile = 128 - 2*h2 output rows (h2 = (k2-1)/2): conv1 produces exactly the 128 rows of t that conv2 needs for them
-//   warp 0    TMA producer: weights once; per tile the x_act slab (128 + conv1's span rows, fetched ONCE — the taps are
-//             row-shifted views of it) into a double-buffered slot.  conv1's taps are (tau - h1) * d1 or an explicit
-//             offset list (the time-folded dilated convs of the narrow stage, whose folded taps are not equidistant)
-//   warp 1    tcgen05.mma issuer: GEMM1 -> acc1 (TMEM), GEMM2 (A = the t tile in smem, taps = row shifts) -> acc2 (TMEM)
+// Both convs are given as lists of K-HALF BLOCKS: block i = a [64 output channels x 32 input channels] bf16 weight block
+// applied to the activation row at offset off[i] (relative to the output row) and input-channel half kh[i] (0 / 1).  A
+// plain 64-channel tap is two such blocks; the TIME-FOLDED convs of the 32-channel stage (hifigan.py: [L, 32] viewed as
+// [L/2, 64]) are block-sparse — their zero halves are simply not listed, which halves the MMA work and the shared memory
+// of the folded weights (all nine steps of that stage then fit, including k = 11 with dilation 3 / 5).
+//
+//   tile = 128 - 2*h2 output rows (h2 = conv2's reach): conv1 produces exactly the 128 rows of t that conv2 needs for them
+//   warp 0    TMA producer: weights once (64-byte-swizzled 4 KB blocks); per tile the x_act slab (128 + conv1's span rows,
+//             fetched ONCE — the taps are row-shifted views of it) into a double-buffered slot
+//   warp 1    tcgen05.mma issuer: GEMM1 -> acc1 (TMEM), GEMM2 (A = the t tile in smem, taps = row shifts) -> acc2 (TMEM);
+//             two K = 16 MMAs per half block (A descriptor: 128B-swizzled row + 64 * kh bytes, B descriptor: the block)
 //   warps 2-9 two independent TILE SLOTS of four epilogue warps each (even / odd tiles; own acc1, acc2, t tile, barriers):
 //             epilogue 1: acc1 -> +b1 -> lrelu -> zero outside [0, L) (conv2's zero padding applies to t) -> bf16 ->
 //             128B-swizzled smem tile;  epilogue 2: residual operands requested BEFORE the wait for GEMM2, then
-//             acc2 -> fused bias / residual / MRF / activation -> global (a thread owns a row: 128 contiguous bytes)
+//             acc2 -> fused bias / residual / MRF / activation -> global, in a coalesced layout through a staged transpose
 // Issue order  G1(0), G1(1), G2(0), G1(2), G2(1), ...: while one slot converts its t tile or writes its outputs, the tensor
 // pipe works for the other slot.
-// Channels-last activations [B, L + 2*halo, C] with zero halos (halo >= h2 + h1*d1), C = 64 or 128 physical channels
-// (the 32-channel stage arrives time-folded as C = 64, see hifigan.py); weights tap-major [C, k*C] bf16.
+// Channels-last activations [B, L + 2*halo, 64] with zero halos (halo >= h2 + conv1's reach); weights [64, n * 32] bf16.
 #include "kr_common.cuh"
 #include "kokoro_b200.h"
 
@@ -37,10 +42,16 @@ constexpr int RB_TROWS = 144;            // t tile: 128 rows + 16 zero rows read
 constexpr int RB_MAX_SLAB = 184;         // 128 + 2 * 25 = 178 rows, rounded up to the 8-row swizzle atom
 constexpr int RB_SMEM_MAX = 227 * 1024 - 1024;
 
+constexpr int RB_C = 64;                 // physical channels of the activations
+constexpr int RB_MAX_BLOCKS = 48;        // half blocks per conv
+constexpr int RB_HB_BYTES = RB_C * 64;   // one [64 x 32] bf16 half block
+
 struct RbParams {
-  int B, C, L, halo;                     // C = physical channels (64 / 128); activations [B, L + 2*halo, C]
-  int k1, k2, lead1;                     // conv1: k1 taps at slab rows off1[]; conv2: k2 taps, dilation 1; lead1 = -min tap offset
-  short off1[32];                        // conv1 tap -> row offset into the slab (>= 0)
+  int B, L, halo;                        // activations [B, L + 2*halo, 64]
+  int n1, n2, lead1, h2;                 // half blocks of conv1 / conv2; lead1 = -min conv1 offset; h2 = conv2's reach
+  short off1[RB_MAX_BLOCKS];             // conv1 block -> row offset into the slab (>= 0)
+  short off2[RB_MAX_BLOCKS];             // conv2 block -> row offset into the t tile (0 .. 2*h2)
+  unsigned char kh1[RB_MAX_BLOCKS], kh2[RB_MAX_BLOCKS];   // input-channel half of the block
   int slab_rows, rows_out, tiles_per_item, total_tiles;
   const float* b1; const float* b2;
   const float* resid; long long r_ld, r_bs;         // fp32, pointing at time 0 of item 0
@@ -50,12 +61,11 @@ struct RbParams {
   bf16* out_act; long long a_ld, a_bs;
 };
 
-template <int C>
 __global__ void __launch_bounds__(RB_THREADS, 1)
 hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
                      const __grid_constant__ CUtensorMap tm_w2, const RbParams p) {
-  constexpr int CB = C / 64;                                  // 64-channel K blocks per tap
-  constexpr int W_STAGE = C * 128;                            // one weight K block: [C rows x 64 k] bf16
+  constexpr int C = RB_C;
+  constexpr int CB = 1;
   constexpr int SLAB_BYTES = CB * RB_MAX_SLAB * 128;
   constexpr int T_BYTES = CB * RB_TROWS * 128;
   extern __shared__ uint8_t smem_raw[];
@@ -72,11 +82,11 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 2);
   uint8_t* slab = smem + 1024;                  // [2][CB][RB_MAX_SLAB rows][128 B]
   uint8_t* tt = slab + 2 * SLAB_BYTES;          // [2 slots][CB][RB_TROWS rows][128 B]
-  uint8_t* wres = tt + 2 * T_BYTES;             // [n1 + n2][C rows][128 B]
+  uint8_t* wres = tt + 2 * T_BYTES;             // [n1 + n2] half blocks: [64 rows][64 B], 64B-swizzled
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h2 = (p.k2 - 1) / 2;
-  const int n1 = p.k1 * CB, n2 = p.k2 * CB;                   // weight K blocks of the two GEMMs
+  const int h2 = p.h2;
+  const int n1 = p.n1, n2 = p.n2;                             // half blocks of the two GEMMs
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_w1); tma_prefetch_desc(&tm_w2);
@@ -104,10 +114,10 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(wres_bar, (uint32_t)((n1 + n2) * W_STAGE));
-      for (int kb = 0; kb < n1 + n2; ++kb) {
-        if (kb < n1) tma_load_3d(wres + kb * W_STAGE, &tm_w1, wres_bar, kb * 64, 0, 0);
-        else         tma_load_3d(wres + kb * W_STAGE, &tm_w2, wres_bar, (kb - n1) * 64, 0, 0);
+      mbar_arrive_expect_tx(wres_bar, (uint32_t)((n1 + n2) * RB_HB_BYTES));
+      for (int hb = 0; hb < n1 + n2; ++hb) {
+        if (hb < n1) tma_load_3d(wres + hb * RB_HB_BYTES, &tm_w1, wres_bar, hb * 32, 0, 0);
+        else         tma_load_3d(wres + hb * RB_HB_BYTES, &tm_w2, wres_bar, (hb - n1) * 32, 0, 0);
       }
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
@@ -115,7 +125,7 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const int sb = lt & 1;
         mbar_wait(&slab_empty[sb], ((lt >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&slab_full[sb], (uint32_t)(CB * p.slab_rows * 128));
-        // t row j <-> time m0 - h2 + j; conv1 tap tau reads time m0 - h2 + j + off1[tau] - lead1
+        // t row j <-> time m0 - h2 + j; conv1 block i reads time m0 - h2 + j + off1[i] - lead1
         const int row0 = p.halo + m0 - h2 - p.lead1;
 #pragma unroll
         for (int cb = 0; cb < CB; ++cb)
@@ -128,7 +138,7 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       constexpr uint32_t idesc = make_idesc_bf16(128, C, 0, 0);
       mbar_wait(wres_bar, 0);
       tc_fence_after();
-      // GEMM2 of local tile `g`: acc2[slot] = sum over (tap, channel block) of t[slot][rows shifted by tap] . W2 block
+      // GEMM2 of local tile `g`: acc2[slot] = sum over the half blocks of t[slot][rows shifted by off2, half kh2] . W2 block
       auto gemm2 = [&](int g) {
         const int s = g & 1;
         const uint32_t ph = (uint32_t)(g >> 1) & 1u;
@@ -136,33 +146,31 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         mbar_wait(&acc2_empty[s], ph ^ 1u);         // ... and finished reading acc2 of the slot's previous tile
         tc_fence_after();
         const uint32_t acc2 = tmem_base + 2 * C + s * C;
-        for (int kb = 0; kb < n2; ++kb) {
-          const int tap = kb / CB, cb = kb - tap * CB;
-          const uint32_t a = smem_u32(tt + (s * CB + cb) * (RB_TROWS * 128) + tap * 128);
-          const uint32_t b = smem_u32(wres + (n1 + kb) * W_STAGE);
+        for (int i = 0; i < n2; ++i) {
+          const uint32_t a = smem_u32(tt + s * T_BYTES + p.off2[i] * 128 + p.kh2[i] * 64);
+          const uint32_t b = smem_u32(wres + (n1 + i) * RB_HB_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(acc2, make_smem_desc_sw128(a + k * 32, 16, 1024), make_smem_desc_sw128(b + k * 32, 16, 1024),
-                         idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 2; ++k)
+            umma_bf16_ss(acc2, make_smem_desc_sw128(a + k * 32, 16, 1024), make_smem_desc_sw(b + k * 32, 16, 512, 4u),
+                         idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&acc2_full[s]);
       };
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
         const int s = lt & 1;
-        // ---- GEMM1: acc1[slot] = sum over (tap, channel block) of slab[rows shifted by tap*d1] . W1 block ----
+        // ---- GEMM1: acc1[slot] = sum over the half blocks of slab[rows shifted by off1, channel half kh1] . W1 block ----
         // (acc1[slot] is free: GEMM2 of the slot's previous tile was issued, i.e. its t tile — read from acc1 — was complete)
         mbar_wait(&slab_full[s], (lt >> 1) & 1);
         tc_fence_after();
         const uint32_t acc1 = tmem_base + s * C;
-        for (int kb = 0; kb < n1; ++kb) {
-          const int tap = kb / CB, cb = kb - tap * CB;
-          const uint32_t a = smem_u32(slab + s * SLAB_BYTES + cb * (RB_MAX_SLAB * 128) + p.off1[tap] * 128);
-          const uint32_t b = smem_u32(wres + kb * W_STAGE);
+        for (int i = 0; i < n1; ++i) {
+          const uint32_t a = smem_u32(slab + s * SLAB_BYTES + p.off1[i] * 128 + p.kh1[i] * 64);
+          const uint32_t b = smem_u32(wres + i * RB_HB_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(acc1, make_smem_desc_sw128(a + k * 32, 16, 1024), make_smem_desc_sw128(b + k * 32, 16, 1024),
-                         idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 2; ++k)
+            umma_bf16_ss(acc1, make_smem_desc_sw128(a + k * 32, 16, 1024), make_smem_desc_sw(b + k * 32, 16, 512, 4u),
+                         idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&slab_empty[s]);
         umma_commit(&acc1_full[s]);
@@ -303,55 +311,53 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 4 * C); }
 }
 
-template <int C>
-constexpr int rb_fixed_smem() { return 1024 + 2 * (C / 64) * RB_MAX_SLAB * 128 + 2 * (C / 64) * RB_TROWS * 128; }
+constexpr int rb_fixed_smem() { return 1024 + 2 * RB_MAX_SLAB * 128 + 2 * RB_TROWS * 128; }
 
-template <int C>
 int launch_rb(const CUtensorMap& tx, const CUtensorMap& t1, const CUtensorMap& t2, const RbParams& p, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(hifi_resblock_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM_MAX + 1024);
+    cudaError_t e = cudaFuncSetAttribute(hifi_resblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM_MAX + 1024);
     if (e != cudaSuccess) { kr_set_error(cudaGetErrorString(e)); return KR_ERR_CUDA; }
     attr = true;
   }
-  const int smem = rb_fixed_smem<C>() + (p.k1 + p.k2) * (C / 64) * C * 128 + 1024;
+  const int smem = rb_fixed_smem() + (p.n1 + p.n2) * RB_HB_BYTES + 1024;
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  kr::launch(hifi_resblock_kernel<C>, grid, RB_THREADS, smem, st, tx, t1, t2, p);
+  kr::launch(hifi_resblock_kernel, grid, RB_THREADS, smem, st, tx, t1, t2, p);
   return KR_OK;
 }
 
-bool rb_fits(int C, int k1, int k2) {
-  if (C != 64 && C != 128) return false;
-  const int fixed = C == 64 ? rb_fixed_smem<64>() : rb_fixed_smem<128>();
-  return fixed + (k1 + k2) * (C / 64) * C * 128 <= RB_SMEM_MAX;
+bool rb_fits(int n1, int n2) {
+  return n1 >= 1 && n2 >= 1 && n1 <= RB_MAX_BLOCKS && n2 <= RB_MAX_BLOCKS &&
+         rb_fixed_smem() + (n1 + n2) * RB_HB_BYTES <= RB_SMEM_MAX;
 }
 
 }  // namespace
 
-extern "C" int kr_hifi_resblock(const void* x_act, int B, long long L, int halo, int C, const void* w1, int k1, int d1,
-                                const int* taps1, const float* b1, const void* w2, int k2, const float* b2, const float* resid,
-                                long long r_ld, long long r_bs, const float* resid2, long long r2_ld, long long r2_bs,
-                                float beta, float* out, long long o_ld, long long o_bs, void* out_act, long long a_ld,
-                                long long a_bs, float slope, void* stream) {
+extern "C" int kr_hifi_resblock(const void* x_act, int B, long long L, int halo, const void* w1, int n1, const int* off1,
+                                const int* kh1, const float* b1, const void* w2, int n2, const int* off2, const int* kh2,
+                                const float* b2, const float* resid, long long r_ld, long long r_bs, const float* resid2,
+                                long long r2_ld, long long r2_bs, float beta, float* out, long long o_ld, long long o_bs,
+                                void* out_act, long long a_ld, long long a_bs, float slope, void* stream) {
   if (B <= 0 || L <= 0) return KR_OK;
-  if (C != 64 && C != 128) { kr_set_error("kr_hifi_resblock: C must be 64 or 128 physical channels"); return KR_ERR_UNSUPPORTED; }
-  if (k1 < 1 || k2 < 1 || !(k2 & 1) || (taps1 == nullptr && (!(k1 & 1) || d1 < 1))) { kr_set_error("kr_hifi_resblock: odd kernel sizes, dilation >= 1"); return KR_ERR_ARG; }
-  if (taps1 != nullptr ? (k1 < 1 || k1 > 32) : (k1 > 32)) { kr_set_error("kr_hifi_resblock: at most 32 conv1 taps"); return KR_ERR_ARG; }
-  const int h1 = (k1 - 1) / 2, h2 = (k2 - 1) / 2;
-  // conv1 tap offsets (rows relative to the output row): the explicit ascending list, or (tau - h1) * d1
-  int offs[32];
-  for (int t = 0; t < k1; ++t) {
-    offs[t] = taps1 != nullptr ? taps1[t] : (t - h1) * d1;
-    if (t > 0 && offs[t] <= offs[t - 1]) { kr_set_error("kr_hifi_resblock: taps1 must be strictly ascending"); return KR_ERR_ARG; }
-  }
-  const int lead = -offs[0] > 0 ? -offs[0] : 0, trail = offs[k1 - 1] > 0 ? offs[k1 - 1] : 0;
-  const int slab_rows = (128 + lead + trail + 7) / 8 * 8;
-  if (h2 > 8 || slab_rows > RB_MAX_SLAB || halo < h2 + (lead > trail ? lead : trail)) {
-    kr_set_error("kr_hifi_resblock: receptive field too large (k2 <= 17, 128 + conv1 span <= 184 rows, halo >= h2 + conv1 reach)");
+  if (off1 == nullptr || kh1 == nullptr || off2 == nullptr || kh2 == nullptr) { kr_set_error("kr_hifi_resblock: null block lists"); return KR_ERR_ARG; }
+  if (!rb_fits(n1, n2)) {
+    kr_set_error("kr_hifi_resblock: 1 .. 48 half blocks per conv, and the weights of both convs must fit in shared memory (see kr_hifi_resblock_resident)");
     return KR_ERR_UNSUPPORTED;
   }
-  if (!rb_fits(C, k1, k2)) {
-    kr_set_error("kr_hifi_resblock: the weights of both convs do not fit in shared memory (see kr_hifi_resblock_resident)");
+  int lo1 = 0, hi1 = 0, h2 = 0;
+  for (int i = 0; i < n1; ++i) {
+    if (kh1[i] < 0 || kh1[i] > 1) { kr_set_error("kr_hifi_resblock: channel half must be 0 or 1"); return KR_ERR_ARG; }
+    lo1 = off1[i] < lo1 ? off1[i] : lo1; hi1 = off1[i] > hi1 ? off1[i] : hi1;
+  }
+  for (int i = 0; i < n2; ++i) {
+    if (kh2[i] < 0 || kh2[i] > 1) { kr_set_error("kr_hifi_resblock: channel half must be 0 or 1"); return KR_ERR_ARG; }
+    const int r = off2[i] < 0 ? -off2[i] : off2[i];
+    h2 = r > h2 ? r : h2;
+  }
+  const int lead = -lo1, reach = lead > hi1 ? lead : hi1;
+  const int slab_rows = (128 + lead + hi1 + 7) / 8 * 8;
+  if (h2 > 8 || slab_rows > RB_MAX_SLAB || halo < h2 + reach) {
+    kr_set_error("kr_hifi_resblock: receptive field too large (conv2 reach <= 8, 128 + conv1 span <= 184 rows, halo >= conv2 reach + conv1 reach)");
     return KR_ERR_UNSUPPORTED;
   }
   if (resid == nullptr || (out == nullptr && out_act == nullptr)) { kr_set_error("kr_hifi_resblock: needs resid and an output"); return KR_ERR_ARG; }
@@ -359,8 +365,9 @@ extern "C" int kr_hifi_resblock(const void* x_act, int B, long long L, int halo,
     kr_set_error("kr_hifi_resblock: leading dimensions / batch strides must be multiples of 4 elements"); return KR_ERR_ARG;
   }
   RbParams p{};
-  p.B = B; p.C = C; p.L = (int)L; p.halo = halo; p.k1 = k1; p.k2 = k2; p.lead1 = lead;
-  for (int t = 0; t < k1; ++t) p.off1[t] = (short)(offs[t] + lead);
+  p.B = B; p.L = (int)L; p.halo = halo; p.n1 = n1; p.n2 = n2; p.lead1 = lead; p.h2 = h2;
+  for (int i = 0; i < n1; ++i) { p.off1[i] = (short)(off1[i] + lead); p.kh1[i] = (unsigned char)kh1[i]; }
+  for (int i = 0; i < n2; ++i) { p.off2[i] = (short)(off2[i] + h2); p.kh2[i] = (unsigned char)kh2[i]; }
   p.slab_rows = slab_rows; p.rows_out = 128 - 2 * h2;
   p.tiles_per_item = (int)((L + p.rows_out - 1) / p.rows_out);
   p.total_tiles = p.tiles_per_item * B;
@@ -370,18 +377,18 @@ extern "C" int kr_hifi_resblock(const void* x_act, int B, long long L, int halo,
   const long long rows_phys = L + 2LL * halo;
   CUtensorMap tx, t1, t2;
   int rc;
-  // activation: (C, rows_phys, B), box (64 channels, slab_rows, 1); rows beyond the tensor are zero-filled by TMA
-  if ((rc = kr_make_tmap_bf16_3d(&tx, x_act, C, rows_phys, B, C, rows_phys * C, 64, slab_rows)) != KR_OK) return rc;
-  // weights: (K = k*C, C rows, 1), box (64 k, C rows)
-  if ((rc = kr_make_tmap_bf16_3d(&t1, w1, (unsigned long long)k1 * C, C, 1, (unsigned long long)k1 * C, (unsigned long long)k1 * C * C, 64, C)) != KR_OK) return rc;
-  if ((rc = kr_make_tmap_bf16_3d(&t2, w2, (unsigned long long)k2 * C, C, 1, (unsigned long long)k2 * C, (unsigned long long)k2 * C * C, 64, C)) != KR_OK) return rc;
+  // activation: (64, rows_phys, B), box (64 channels, slab_rows, 1); rows beyond the tensor are zero-filled by TMA
+  if ((rc = kr_make_tmap_bf16_3d(&tx, x_act, RB_C, rows_phys, B, RB_C, rows_phys * RB_C, 64, slab_rows)) != KR_OK) return rc;
+  // weights: (K = n * 32, 64 rows, 1), box (32 k, 64 rows), 64-byte swizzle
+  if ((rc = kr_make_tmap_bf16_3d(&t1, w1, (unsigned long long)n1 * 32, RB_C, 1, (unsigned long long)n1 * 32, (unsigned long long)n1 * 32 * RB_C, 32, RB_C, 1)) != KR_OK) return rc;
+  if ((rc = kr_make_tmap_bf16_3d(&t2, w2, (unsigned long long)n2 * 32, RB_C, 1, (unsigned long long)n2 * 32, (unsigned long long)n2 * 32 * RB_C, 32, RB_C, 1)) != KR_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  rc = C == 64 ? launch_rb<64>(tx, t1, t2, p, st) : launch_rb<128>(tx, t1, t2, p, st);
+  rc = launch_rb(tx, t1, t2, p, st);
   if (rc != KR_OK) return rc;
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
 
-// 1 if the weights of both convs of a (C, k1, k2) ResBlock step fit in shared memory next to the activation slab (the fused
-// kernel then beats two kr_gemm_ex launches; otherwise it is bound by weight streaming and the caller should not use it).
-extern "C" int kr_hifi_resblock_resident(int C, int k1, int k2) { return rb_fits(C, k1, k2) ? 1 : 0; }
+// 1 if the weights of both convs of a ResBlock step (n1 / n2 half blocks) fit in shared memory next to the activation
+// slabs (the fused kernel then beats two kr_gemm_ex launches; otherwise the caller keeps the two-launch path).
+extern "C" int kr_hifi_resblock_resident(int n1, int n2) { return rb_fits(n1, n2) ? 1 : 0; }

@@ -232,6 +232,42 @@ class HiFiGANGenerator:
                         out[a * co:(a + 1) * co, fi, c * ci:(c + 1) * ci] = w[:, :, o // dil + hh]
         return out.reshape(2 * co, len(taps) * 2 * ci).to(BF16).contiguous()
 
+    @classmethod
+    def _half_blocks(cls, w: torch.Tensor, dil: int, folded: bool):
+        """Operand of the fused ResBlock kernel (csrc/kr_hifi_resblock.cu): the conv as a list of K-HALF BLOCKS, block i =
+        [64 output channels x 32 input channels] applied to the activation row at offset off[i] and input-channel half
+        kh[i].  A plain 64-channel conv [64, 64, k]: two blocks per tap at offset (tau - h) * dil.  folded = True: a
+        32-channel conv [32, 32, k] on the TIME-FOLDED view [L/2, 64] (see _tap_major_time_folded): block (f, c) holds, for
+        output half a (rows a*32 .. a*32+31), the original tap at time offset o = 2f + c - a where that is a tap of the conv,
+        zeros otherwise — blocks that are entirely zero are not listed (half of them for dilation 1, ~3/4 when dilated).
+        Returns (bf16 [64, n * 32], offsets, halves)."""
+        co, ci, k = w.shape
+        hh = (k - 1) // 2
+        blocks, offs, khs = [], [], []
+        if not folded:
+            assert co == 64 and ci == 64
+            for tau in range(k):
+                for c in (0, 1):
+                    blocks.append(w[:, c * 32:(c + 1) * 32, tau])
+                    offs.append((tau - hh) * dil)
+                    khs.append(c)
+        else:
+            assert co == 32 and ci == 32
+            for f in cls._folded_taps(k, dil):
+                for c in (0, 1):
+                    blk = torch.zeros(64, 32, dtype=w.dtype, device=w.device)
+                    used = False
+                    for a in (0, 1):
+                        o = 2 * f + c - a
+                        if o % dil == 0 and abs(o // dil) <= hh:
+                            blk[a * 32:(a + 1) * 32] = w[:, :, o // dil + hh]
+                            used = True
+                    if used:
+                        blocks.append(blk)
+                        offs.append(f)
+                        khs.append(c)
+        return torch.cat(blocks, dim=1).to(BF16).contiguous(), offs, khs
+
     def _time_folded(self, stage: int) -> bool:
         """Stages whose dilation-1 convs run on the time-folded view (see _tap_major_time_folded): the 32-channel stage
         (measured on B200, 16 x 800 frames: 18.59 -> 17.67 ms; folding the 64-channel stage as well gives 17.67 ms for its
@@ -268,16 +304,17 @@ class HiFiGANGenerator:
                         if self._time_folded(i) and dil == 1 and cout_p == cout:
                             W[f"{p}.{grp}.{d}.w2"] = self._tap_major_time_folded(self._eff(f"{p}.{grp}.{d}"))
                             W[f"{p}.{grp}.{d}.b2"] = torch.cat([W[f"{p}.{grp}.{d}.b"]] * 2).contiguous()
-                        elif self._time_folded(i) and cout_p == cout:
-                            # dilated conv1 of the narrow stage: folded taps are not equidistant — only for the fused
-                            # ResBlock kernel, and only when both convs' folded weights stay resident in shared memory
-                            kj = h.resblock_kernel_sizes[j]
-                            taps = self._folded_taps(kj, dil)
-                            if lib().kr_hifi_resblock_resident(ctypes.c_int(2 * cout), ctypes.c_int(len(taps)),
-                                                               ctypes.c_int(len(self._folded_taps(kj)))):
-                                W[f"{p}.{grp}.{d}.w2d"] = self._tap_major_time_folded(self._eff(f"{p}.{grp}.{d}"), dil)
-                                W[f"{p}.{grp}.{d}.b2"] = torch.cat([W[f"{p}.{grp}.{d}.b"]] * 2).contiguous()
-                                W[f"{p}.{grp}.{d}.taps"] = taps
+                # fused ResBlock step (csrc/kr_hifi_resblock.cu): 64 physical channels — the 64-channel stage as it is, the
+                # 32-channel stage time-folded — whenever the half-block weights of both convs stay resident in shared memory
+                folded = self._time_folded(i) and cout_p == cout
+                if cout_p == 64 and cout == 64 or folded:
+                    for d, dil in enumerate(h.resblock_dilation_sizes[j]):
+                        w1, o1, k1 = self._half_blocks(self._eff(f"{p}.convs1.{d}"), dil, folded)
+                        w2, o2, k2 = self._half_blocks(self._eff(f"{p}.convs2.{d}"), 1, folded)
+                        if lib().kr_hifi_resblock_resident(ctypes.c_int(len(o1)), ctypes.c_int(len(o2))):
+                            rep_b = (lambda t: torch.cat([t] * 2).contiguous()) if folded else (lambda t: t)
+                            W[f"{p}.rb.{d}"] = dict(w1=w1, off1=o1, kh1=k1, b1=rep_b(W[f"{p}.convs1.{d}.b"]), w2=w2, off2=o2, kh2=k2,
+                                                    b2=rep_b(W[f"{p}.convs2.{d}.b"]), folded=folded)
         wpost = self._eff("conv_post")                        # [1, ch, 7]
         W["post.w"] = wpost[0].t().contiguous()               # [7, ch] fp32
         W["post.b"] = self._sd["conv_post.bias"].contiguous()
@@ -349,22 +386,13 @@ class HiFiGANGenerator:
                     # destination of this step: the next step's (raw, act) pair, or — last step of the ResBlock — the MRF
                     # accumulator xs (+)= (x + conv) / num_kernels, whose last writer emits lrelu(xs) for the next stage
                     fold1, fold2 = f"{p}.convs1.{d}.w2" in W, f"{p}.convs2.{d}.w2" in W
-                    fold1d = f"{p}.convs1.{d}.w2d" in W                 # dilated conv1, folded with an explicit tap list
-                    fz_ok = (fold1 or fold1d) and fold2
-                    taps1 = W[f"{p}.convs1.{d}.taps"] if fold1d else None
-                    if lib().kr_hifi_resblock_resident(ctypes.c_int(64 if fz_ok else cp),
-                                                       ctypes.c_int(len(taps1) if fold1d else (2 * hf + 1 if fz_ok else k)),
-                                                       ctypes.c_int(2 * hf + 1 if fz_ok else k)) and (fz_ok or cp in (64, 128)):
-                        # ONE kernel for c1 -> lrelu -> c2 -> + x (csrc/kr_hifi_resblock.cu); on the narrow stage through
-                        # the time-folded views (dilation-1 steps only)
-                        fz = fz_ok
+                    rb = W.get(f"{p}.rb.{d}")
+                    if rb is not None:
+                        # ONE kernel for c1 -> lrelu -> c2 -> + x; on the narrow stage through the time-folded views
+                        fz = rb["folded"]
                         v_in = f2(y_act) if fz else y_act
                         iv = i2 if fz else (lambda t: inner(t, L)[:, :, :cout])
                         xv = x2 if fz else (lambda t: t)
-                        w1, b1 = (W[f"{p}.convs1.{d}.w2d" if fold1d else f"{p}.convs1.{d}.w2"], W[f"{p}.convs1.{d}.b2"]) if fz \
-                            else (W[f"{p}.convs1.{d}.w"], W[f"{p}.convs1.{d}.b"])
-                        w2, b2 = (W[f"{p}.convs2.{d}.w2"], W[f"{p}.convs2.{d}.b2"]) if fz else (W[f"{p}.convs2.{d}.w"], W[f"{p}.convs2.{d}.b"])
-                        kk = 2 * hf + 1 if fz else k
                         kw = dict(resid=iv(y_raw))
                         if not final:
                             kw.update(out=iv(n_raw), out_act=iv(n_act), act_slope=0.1)
@@ -372,8 +400,8 @@ class HiFiGANGenerator:
                             kw.update(resid2=xv(xs) if j > 0 else None, beta=1.0 / self.num_kernels,
                                       out=None if last_rb else xv(xs), out_act=iv(b[f"x_act{i}"]) if last_rb else None,
                                       act_slope=0.01 if last_stage else 0.1)
-                        ops.hifi_resblock(v_in, L // 2 if fz else L, HALO // 2 if fz else HALO, w1, len(taps1) if fold1d else kk,
-                                          1 if fz else dil, b1, w2, kk, b2, taps1=taps1, **kw)
+                        ops.hifi_resblock(v_in, L // 2 if fz else L, HALO // 2 if fz else HALO, rb["w1"], rb["off1"], rb["kh1"],
+                                          rb["b1"], rb["w2"], rb["off2"], rb["kh2"], rb["b2"], **kw)
                         if not final:
                             y_raw, y_act = n_raw, n_act
                         continue

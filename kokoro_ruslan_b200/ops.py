@@ -221,23 +221,22 @@ def conv1d_cl(x: torch.Tensor, w: torch.Tensor, *, rows: int, row0: int, taps: i
     check(lib().kr_gemm_ex(ctypes.byref(a), _stream()), "kr_gemm_ex")
 
 
-def hifi_resblock(x_act: torch.Tensor, L: int, halo: int, w1: torch.Tensor, k1: int, d1: int, b1: torch.Tensor,
-                  w2: torch.Tensor, k2: int, b2: torch.Tensor, resid: torch.Tensor, *, resid2: Optional[torch.Tensor] = None,
+def hifi_resblock(x_act: torch.Tensor, L: int, halo: int, w1: torch.Tensor, off1, kh1, b1: torch.Tensor,
+                  w2: torch.Tensor, off2, kh2, b2: torch.Tensor, resid: torch.Tensor, *, resid2: Optional[torch.Tensor] = None,
                   beta: float = 1.0, out: Optional[torch.Tensor] = None, out_act: Optional[torch.Tensor] = None,
-                  act_slope: float = 0.1, taps1=None) -> None:
+                  act_slope: float = 0.1) -> None:
     """One fused HiFi-GAN ResBlock step (csrc/kr_hifi_resblock.cu): v = conv2(lrelu(conv1(x_act) + b1)) + b2 + resid;
     v = v * beta + resid2; out = v; out_act = lrelu(v, act_slope).  x_act: the padded channels-last activation
-    [B, L + 2*halo, C] bf16 (C = 64 / 128, zero halos); w1 / w2: [C, k*C] bf16 tap-major; resid / resid2 / out / out_act:
-    [B, L, C]-shaped views (any row / batch strides, unit inner stride) that start at time 0.  taps1: explicit ascending row
-    offsets of conv1's k1 taps (host ints) instead of the equidistant (tau - (k1-1)/2) * d1."""
+    [B, L + 2*halo, 64] bf16 (zero halos); both convs as K-half-block lists (hifigan.HiFiGANGenerator._half_blocks):
+    w [64, n*32] bf16, row offsets off[n] and input-channel halves kh[n] (host ints); resid / resid2 / out / out_act:
+    [B, L, 64]-shaped views (any row / batch strides, unit inner stride) that start at time 0."""
     assert x_act.dtype == torch.bfloat16 and x_act.dim() == 3 and x_act.is_contiguous()
-    taps_arr = None
-    if taps1 is not None:
-        assert len(taps1) == k1
-        taps_arr = (c_int * k1)(*[int(t) for t in taps1])
     B, rows_phys, C = x_act.shape
-    assert rows_phys == L + 2 * halo and w1.shape == (C, k1 * C) and w2.shape == (C, k2 * C)
+    n1, n2 = len(off1), len(off2)
+    assert C == 64 and rows_phys == L + 2 * halo and w1.shape == (C, n1 * 32) and w2.shape == (C, n2 * 32)
+    assert len(kh1) == n1 and len(kh2) == n2
     assert w1.is_contiguous() and w2.is_contiguous() and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+    arr = lambda v: (c_int * len(v))(*[int(t) for t in v])     # noqa: E731
 
     def view(t, dtype):
         if t is None:
@@ -248,10 +247,10 @@ def hifi_resblock(x_act: torch.Tensor, L: int, halo: int, w1: torch.Tensor, k1: 
     r2, r2_ld, r2_bs = view(resid2, torch.float32)
     o, o_ld, o_bs = view(out, torch.float32)
     a, a_ld, a_bs = view(out_act, torch.bfloat16)
-    check(lib().kr_hifi_resblock(_ptr(x_act), c_int(B), c_ll(L), c_int(halo), c_int(C), _ptr(w1), c_int(k1), c_int(d1), taps_arr, _ptr(b1),
-                                 _ptr(w2), c_int(k2), _ptr(b2), _ptr(r), c_ll(r_ld), c_ll(r_bs), _ptr(r2), c_ll(r2_ld), c_ll(r2_bs),
-                                 c_float(beta), _ptr(o), c_ll(o_ld), c_ll(o_bs), _ptr(a), c_ll(a_ld), c_ll(a_bs),
-                                 c_float(act_slope), _stream()), "kr_hifi_resblock")
+    check(lib().kr_hifi_resblock(_ptr(x_act), c_int(B), c_ll(L), c_int(halo), _ptr(w1), c_int(n1), arr(off1), arr(kh1), _ptr(b1),
+                                 _ptr(w2), c_int(n2), arr(off2), arr(kh2), _ptr(b2), _ptr(r), c_ll(r_ld), c_ll(r_bs), _ptr(r2),
+                                 c_ll(r2_ld), c_ll(r2_bs), c_float(beta), _ptr(o), c_ll(o_ld), c_ll(o_bs), _ptr(a), c_ll(a_ld),
+                                 c_ll(a_bs), c_float(act_slope), _stream()), "kr_hifi_resblock")
 
 
 def _heads_strides(t: torch.Tensor):

@@ -90,3 +90,38 @@ def test_time_folded_weights_equal_the_dilated_conv():
                 lo, hi = max(0, -f), min(L // 2, L // 2 - f)
                 out[lo:hi] += xf[lo + f:hi + f] @ wf[:, fi, :].t()
             assert float((out.view(L, C).t() - want).abs().max()) < 1e-4, (k, dil)
+
+
+def test_half_block_lists_equal_the_conv():
+    """Operand layout of the fused ResBlock kernel (HiFiGANGenerator._half_blocks): summing, over the listed K-half blocks,
+    W_i [64 x 32] @ x[row + off_i, 32 kh_i : 32 kh_i + 32] reproduces the conv — plain 64-channel convs and the block-sparse
+    time-folded 32-channel ones (zero halves not listed)."""
+    import torch.nn.functional as F
+    from kokoro_ruslan_b200.hifigan import HiFiGANGenerator as G
+    torch.manual_seed(1)
+    L = 96
+    for folded, C in ((False, 64), (True, 32)):
+        for k in (3, 7, 11):
+            for dil in (1, 3, 5):
+                w = torch.randn(C, C, k).to(torch.bfloat16).float()
+                x = torch.randn(1, C, L)
+                want = F.conv1d(x, w, padding=dil * (k - 1) // 2, dilation=dil)[0].t()          # [L, C]
+                wb, offs, khs = G._half_blocks(w, dil, folded)
+                n = len(offs)
+                assert wb.shape == (64, n * 32) and len(khs) == n and set(khs) <= {0, 1}
+                rows = L // 2 if folded else L
+                xv = x[0].t().contiguous().view(rows, 64)
+                out = torch.zeros(rows, 64)
+                for i in range(n):
+                    blk = wb[:, i * 32:(i + 1) * 32].float()
+                    lo, hi = max(0, -offs[i]), min(rows, rows - offs[i])
+                    out[lo:hi] += xv[lo + offs[i]:hi + offs[i], khs[i] * 32:(khs[i] + 1) * 32] @ blk.t()
+                assert float((out.view(L, C) - want).abs().max()) < 1e-4, (folded, k, dil)
+                if folded:      # the block-sparse form lists at most 2 blocks per original tap
+                    assert n <= 2 * k
+    # all nine steps of the folded 32-channel stage fit next to the kernel's 83 KB of slabs (35 blocks of 4 KB)
+    for k in (3, 7, 11):
+        for dil in (1, 3, 5):
+            n1 = len(G._half_blocks(torch.zeros(32, 32, k), dil, True)[1])
+            n2 = len(G._half_blocks(torch.zeros(32, 32, k), 1, True)[1])
+            assert n1 + n2 <= 35, (k, dil, n1, n2)

@@ -102,3 +102,53 @@ def test_slab_path_parity_mid_size():
     got = gen(mel.cuda()).float().cpu()
     want = oh.generator_forward(sd, cfg, mel)
     assert _rel(got, want) < TOL
+
+
+@pytest.mark.parametrize("folded,k,dil,L,final", [(False, 3, 1, 1000, False), (False, 7, 5, 4096 + 77, True),
+                                                   (True, 3, 3, 2 * 1234, False), (True, 11, 5, 2 * 3000, True),
+                                                   (True, 11, 1, 2 * 515, False), (True, 7, 3, 2 * 64, True)])
+def test_fused_resblock_step_against_torch(folded, k, dil, L, final):
+    """kr_hifi_resblock alone (through ops.hifi_resblock) against torch fp32 on the same bf16-rounded operands: plain
+    64-channel steps and time-folded 32-channel ones (block-sparse half-block lists, including the k = 11 dilated steps),
+    ragged lengths, the intermediate (out + out_act) and the final (MRF accumulation, out_act only) epilogue forms."""
+    import torch.nn.functional as F
+    from kokoro_ruslan_b200 import ops
+    from kokoro_ruslan_b200.hifigan import HALO, HiFiGANGenerator as G
+    C = 32 if folded else 64
+    B = 2
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, C, L, generator=g)                                          # residual stream (fp32)
+    w1 = (torch.randn(C, C, k, generator=g) / (C * k) ** 0.5).to(torch.bfloat16).float()
+    w2 = (torch.randn(C, C, k, generator=g) / (C * k) ** 0.5).to(torch.bfloat16).float()
+    b1, b2 = torch.randn(C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    xs = torch.randn(B, C, L, generator=g)
+    act = F.leaky_relu(x, 0.1).to(torch.bfloat16)
+    t = F.leaky_relu(F.conv1d(act.float(), w1, b1, padding=dil * (k - 1) // 2, dilation=dil), 0.1).to(torch.bfloat16).float()
+    v = F.conv1d(t, w2, b2, padding=(k - 1) // 2) + x
+    if final:
+        v = v / 3.0 + xs
+    want = v.permute(0, 2, 1)                                                      # [B, L, C]
+    x_act = torch.zeros(B, L + 2 * HALO, C, dtype=torch.bfloat16, device="cuda")
+    x_act[:, HALO:HALO + L] = act.permute(0, 2, 1).cuda()
+    resid = x.permute(0, 2, 1).contiguous().cuda()
+    r2 = xs.permute(0, 2, 1).contiguous().cuda()
+    out = torch.zeros(B, L, C, device="cuda")
+    out_act = torch.zeros(B, L + 2 * HALO, C, dtype=torch.bfloat16, device="cuda")
+    wb1, o1, h1 = G._half_blocks(w1.cuda(), dil, folded)
+    wb2, o2, h2 = G._half_blocks(w2.cuda(), 1, folded)
+    rep = (lambda t_: torch.cat([t_] * 2)) if folded else (lambda t_: t_)
+    fl = 2 if folded else 1
+    f3 = lambda t_: t_.view(B, t_.shape[1] // fl, 64)                              # noqa: E731  (time-folded view)
+    kw = dict(resid=f3(resid), out_act=f3(out_act)[:, HALO // fl:(HALO + L) // fl], act_slope=0.1)
+    if final:
+        kw.update(resid2=f3(r2), beta=1.0 / 3.0)
+    else:
+        kw.update(out=f3(out))
+    ops.hifi_resblock(f3(x_act), L // fl, HALO // fl, wb1, o1, h1, rep(b1).cuda(), wb2, o2, h2, rep(b2).cuda(), **kw)
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    got_act = out_act[:, HALO:HALO + L].float().cpu()
+    assert float((got_act - F.leaky_relu(want, 0.1)).abs().max()) / scale < 1e-2
+    assert float(out_act[:, :HALO].abs().max()) == 0.0 and float(out_act[:, HALO + L:].abs().max()) == 0.0     # halos untouched
+    if not final:
+        assert float((out.cpu() - want).abs().max()) / scale < 3e-3
