@@ -28,7 +28,8 @@
 //             128B-swizzled smem tile;  epilogue 2: residual operands requested BEFORE the wait for GEMM2, then
 //             acc2 -> fused bias / residual / MRF / activation -> global, in a coalesced layout through a staged transpose
 // Issue order  G1(0), G1(1), G2(0), G1(2), G2(1), ...: while one slot converts its t tile or writes its outputs, the tensor
-// pipe works for the other slot.
+// pipe works for the other slot.  Weights that only fit next to ONE slot (k = 11 on 64 channels: 176 KB) run in one-slot mode,
+// G1(0), G2(0), G1(1), G2(1), ...: epilogue 2 of a tile still runs under GEMM1 of the next.
 // Channels-last activations [B, L + 2*halo, 64] with zero halos (halo >= h2 + conv1's reach); weights [64, n * 32] bf16.
 #include "kr_common.cuh"
 #include "kokoro_b200.h"
@@ -49,6 +50,7 @@ constexpr int RB_HB_BYTES = RB_C * 64;   // one [64 x 32] bf16 half block
 struct RbParams {
   int B, L, halo;                        // activations [B, L + 2*halo, 64]
   int n1, n2, lead1, h2;                 // half blocks of conv1 / conv2; lead1 = -min conv1 offset; h2 = conv2's reach
+  int slots;                             // 2: two tile slots ping-pong; 1: one slot (its slab / t tile make room for more weights)
   short off1[RB_MAX_BLOCKS];             // conv1 block -> row offset into the slab (>= 0)
   short off2[RB_MAX_BLOCKS];             // conv2 block -> row offset into the t tile (0 .. 2*h2)
   unsigned char kh1[RB_MAX_BLOCKS], kh2[RB_MAX_BLOCKS];   // input-channel half of the block
@@ -81,8 +83,9 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   uint64_t* acc2_empty = acc2_full + 2;         // [2] 4 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 2);
   uint8_t* slab = smem + 1024;                  // [2][CB][RB_MAX_SLAB rows][128 B]
-  uint8_t* tt = slab + 2 * SLAB_BYTES;          // [2 slots][CB][RB_TROWS rows][128 B]
-  uint8_t* wres = tt + 2 * T_BYTES;             // [n1 + n2] half blocks: [64 rows][64 B], 64B-swizzled
+  const int sh = p.slots - 1;                   // local tile lt -> slot lt & sh, use count lt >> sh
+  uint8_t* tt = slab + p.slots * SLAB_BYTES;    // [slots][RB_TROWS rows][128 B]
+  uint8_t* wres = tt + p.slots * T_BYTES;       // [n1 + n2] half blocks: [64 rows][64 B], 64B-swizzled
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h2 = p.h2;
@@ -100,7 +103,7 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 4 * C); tmem_relinquish(); }
   // the 16 spare rows of both t tiles stay zero for the whole kernel
-  for (int i = threadIdx.x; i < 2 * CB * 16 * 8; i += RB_THREADS) {
+  for (int i = threadIdx.x; i < p.slots * CB * 16 * 8; i += RB_THREADS) {
     const int blk = i / (16 * 8), r = (i / 8) % 16, q = i % 8;        // blk = slot * CB + cb
     *reinterpret_cast<uint4*>(tt + blk * (RB_TROWS * 128) + (128 + r) * 128 + q * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
@@ -122,8 +125,8 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
         const int bz = tile / p.tiles_per_item, m0 = (tile % p.tiles_per_item) * p.rows_out;
-        const int sb = lt & 1;
-        mbar_wait(&slab_empty[sb], ((lt >> 1) & 1) ^ 1);
+        const int sb = lt & sh;
+        mbar_wait(&slab_empty[sb], ((lt >> sh) & 1) ^ 1);
         mbar_arrive_expect_tx(&slab_full[sb], (uint32_t)(CB * p.slab_rows * 128));
         // t row j <-> time m0 - h2 + j; conv1 block i reads time m0 - h2 + j + off1[i] - lead1
         const int row0 = p.halo + m0 - h2 - p.lead1;
@@ -140,8 +143,8 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       tc_fence_after();
       // GEMM2 of local tile `g`: acc2[slot] = sum over the half blocks of t[slot][rows shifted by off2, half kh2] . W2 block
       auto gemm2 = [&](int g) {
-        const int s = g & 1;
-        const uint32_t ph = (uint32_t)(g >> 1) & 1u;
+        const int s = g & sh;
+        const uint32_t ph = (uint32_t)(g >> sh) & 1u;
         mbar_wait(&t_full[s], ph);                  // the slot's epilogue warps wrote the t tile (generic proxy, fenced)
         mbar_wait(&acc2_empty[s], ph ^ 1u);         // ... and finished reading acc2 of the slot's previous tile
         tc_fence_after();
@@ -158,10 +161,12 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       };
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-        const int s = lt & 1;
+        const int s = lt & sh;
+        // one slot: acc1 is that of the PREVIOUS tile, whose t tile must be complete before it is overwritten -> G2 first
+        if (sh == 0 && lt > 0) gemm2(lt - 1);
         // ---- GEMM1: acc1[slot] = sum over the half blocks of slab[rows shifted by off1, channel half kh1] . W1 block ----
         // (acc1[slot] is free: GEMM2 of the slot's previous tile was issued, i.e. its t tile — read from acc1 — was complete)
-        mbar_wait(&slab_full[s], (lt >> 1) & 1);
+        mbar_wait(&slab_full[s], (lt >> sh) & 1);
         tc_fence_after();
         const uint32_t acc1 = tmem_base + s * C;
         for (int i = 0; i < n1; ++i) {
@@ -174,7 +179,7 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         }
         umma_commit(&slab_empty[s]);
         umma_commit(&acc1_full[s]);
-        if (lt > 0) gemm2(lt - 1);
+        if (sh != 0 && lt > 0) gemm2(lt - 1);
       }
       if (lt > 0) gemm2(lt - 1);
     }
@@ -187,8 +192,8 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     uint8_t* tts = tt + slot * T_BYTES;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-      if ((lt & 1) != slot) continue;
-      const uint32_t ph = (uint32_t)(lt >> 1) & 1u;
+      if (slot > sh || (lt & sh) != slot) continue;             // (one-slot mode: warps 6-9 only keep the block barriers)
+      const uint32_t ph = (uint32_t)(lt >> sh) & 1u;
       const int bz = tile / p.tiles_per_item, m0 = (tile % p.tiles_per_item) * p.rows_out;
       // ---- epilogue 1: t row j (time m0 - h2 + j) ----
       mbar_wait(&acc1_full[slot], ph);
@@ -311,7 +316,7 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 4 * C); }
 }
 
-constexpr int rb_fixed_smem() { return 1024 + 2 * RB_MAX_SLAB * 128 + 2 * RB_TROWS * 128; }
+constexpr int rb_fixed_smem(int slots) { return 1024 + slots * (RB_MAX_SLAB * 128 + RB_TROWS * 128); }
 
 int launch_rb(const CUtensorMap& tx, const CUtensorMap& t1, const CUtensorMap& t2, const RbParams& p, cudaStream_t st) {
   static bool attr = false;
@@ -320,15 +325,19 @@ int launch_rb(const CUtensorMap& tx, const CUtensorMap& t1, const CUtensorMap& t
     if (e != cudaSuccess) { kr_set_error(cudaGetErrorString(e)); return KR_ERR_CUDA; }
     attr = true;
   }
-  const int smem = rb_fixed_smem() + (p.n1 + p.n2) * RB_HB_BYTES + 1024;
+  const int smem = rb_fixed_smem(p.slots) + (p.n1 + p.n2) * RB_HB_BYTES + 1024;
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
   kr::launch(hifi_resblock_kernel, grid, RB_THREADS, smem, st, tx, t1, t2, p);
   return KR_OK;
 }
 
-bool rb_fits(int n1, int n2) {
-  return n1 >= 1 && n2 >= 1 && n1 <= RB_MAX_BLOCKS && n2 <= RB_MAX_BLOCKS &&
-         rb_fixed_smem() + (n1 + n2) * RB_HB_BYTES <= RB_SMEM_MAX;
+// tile slots the kernel can run with for (n1, n2) half blocks: 2 (ping-pong), 1 (k = 11 of the 64-channel stage: 44 blocks),
+// 0 = the weights do not fit
+int rb_slots(int n1, int n2) {
+  if (n1 < 1 || n2 < 1 || n1 > RB_MAX_BLOCKS || n2 > RB_MAX_BLOCKS) return 0;
+  for (int slots = 2; slots >= 1; --slots)
+    if (rb_fixed_smem(slots) + (n1 + n2) * RB_HB_BYTES <= RB_SMEM_MAX) return slots;
+  return 0;
 }
 
 }  // namespace
@@ -340,7 +349,7 @@ extern "C" int kr_hifi_resblock(const void* x_act, int B, long long L, int halo,
                                 void* out_act, long long a_ld, long long a_bs, float slope, void* stream) {
   if (B <= 0 || L <= 0) return KR_OK;
   if (off1 == nullptr || kh1 == nullptr || off2 == nullptr || kh2 == nullptr) { kr_set_error("kr_hifi_resblock: null block lists"); return KR_ERR_ARG; }
-  if (!rb_fits(n1, n2)) {
+  if (rb_slots(n1, n2) == 0) {
     kr_set_error("kr_hifi_resblock: 1 .. 48 half blocks per conv, and the weights of both convs must fit in shared memory (see kr_hifi_resblock_resident)");
     return KR_ERR_UNSUPPORTED;
   }
@@ -365,7 +374,7 @@ extern "C" int kr_hifi_resblock(const void* x_act, int B, long long L, int halo,
     kr_set_error("kr_hifi_resblock: leading dimensions / batch strides must be multiples of 4 elements"); return KR_ERR_ARG;
   }
   RbParams p{};
-  p.B = B; p.L = (int)L; p.halo = halo; p.n1 = n1; p.n2 = n2; p.lead1 = lead; p.h2 = h2;
+  p.B = B; p.L = (int)L; p.halo = halo; p.n1 = n1; p.n2 = n2; p.lead1 = lead; p.h2 = h2; p.slots = rb_slots(n1, n2);
   for (int i = 0; i < n1; ++i) { p.off1[i] = (short)(off1[i] + lead); p.kh1[i] = (unsigned char)kh1[i]; }
   for (int i = 0; i < n2; ++i) { p.off2[i] = (short)(off2[i] + h2); p.kh2[i] = (unsigned char)kh2[i]; }
   p.slab_rows = slab_rows; p.rows_out = 128 - 2 * h2;
@@ -389,6 +398,7 @@ extern "C" int kr_hifi_resblock(const void* x_act, int B, long long L, int halo,
   return KR_OK;
 }
 
-// 1 if the weights of both convs of a ResBlock step (n1 / n2 half blocks) fit in shared memory next to the activation
-// slabs (the fused kernel then beats two kr_gemm_ex launches; otherwise the caller keeps the two-launch path).
-extern "C" int kr_hifi_resblock_resident(int n1, int n2) { return rb_fits(n1, n2) ? 1 : 0; }
+// Non-zero if the weights of both convs of a ResBlock step (n1 / n2 half blocks) fit in shared memory next to the
+// activation slabs: the number of tile slots the kernel will run with (2 = ping-pong, 1); 0 = the caller keeps the
+// two-launch path.
+extern "C" int kr_hifi_resblock_resident(int n1, int n2) { return rb_slots(n1, n2); }

@@ -105,11 +105,12 @@ def test_slab_path_parity_mid_size():
 
 
 @pytest.mark.parametrize("folded,k,dil,L,final", [(False, 3, 1, 1000, False), (False, 7, 5, 4096 + 77, True),
+                                                   (False, 11, 5, 128 * 40 + 3, False), (False, 11, 1, 777, True),
                                                    (True, 3, 3, 2 * 1234, False), (True, 11, 5, 2 * 3000, True),
                                                    (True, 11, 1, 2 * 515, False), (True, 7, 3, 2 * 64, True)])
 def test_fused_resblock_step_against_torch(folded, k, dil, L, final):
     """kr_hifi_resblock alone (through ops.hifi_resblock) against torch fp32 on the same bf16-rounded operands: plain
-    64-channel steps and time-folded 32-channel ones (block-sparse half-block lists, including the k = 11 dilated steps),
+    64-channel steps (k = 11: 44 blocks, one-slot mode) and time-folded 32-channel ones (block-sparse half-block lists),
     ragged lengths, the intermediate (out + out_act) and the final (MRF accumulation, out_act only) epilogue forms."""
     import torch.nn.functional as F
     from kokoro_ruslan_b200 import ops

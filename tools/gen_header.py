@@ -21,7 +21,7 @@ DOCS = {
     "kr_gemm_ex": "Persistent tcgen05 GEMM / implicit-GEMM conv1d with the full fused epilogue (see kr_gemm_args). kr_gemm_bf16 is the plain-argument subset. The conv mode replaces nn.Conv1d / nn.ConvTranspose1d (polyphase) of inference/hifigan_vocoder.py:31-133.",
     "kr_hifi_pack_mel": "Mel (B,80,T) [time_major=0] or (B,T,80) [1] fp32 -> channels-last bf16 [B, T+2*halo, c_phys] (interior rows; halos and padded channels stay zero): the input-layout handling of inference/hifigan_vocoder.py:112-117 fused with the bf16 cast.",
     "kr_hifi_resblock": "One HiFi-GAN ResBlock step in one kernel (inference/hifigan_vocoder.py:31-83: xt = c1(lrelu(x)); xt = c2(lrelu(xt)); x = xt + x): t = lrelu(conv1(x_act) + b1, 0.1) stays in shared memory (bf16); v = conv2(t) + b2 + resid; v = v * beta + resid2 (MRF accumulation, optional); out = v (fp32, optional); out_act = bf16(lrelu(v, slope)) (optional). x_act = padded channels-last bf16 activation [B, L + 2*halo, 64] with zero halos (the 32-channel stage arrives time-folded). Both convs are lists of K-half blocks (host arrays): block i = bf16 weights w[:, 32 i .. 32 i + 31] ([64 output channels x 32 input channels], w is [64, n*32]) applied to the activation row at offset off[i] relative to the output row and to input-channel half kh[i] (0 / 1); a plain tap is two blocks, the zero halves of the block-sparse time-folded convs are not listed. resid / resid2 / out / out_act start at time 0 of item 0 with row (ld) and batch strides in elements.",
-    "kr_hifi_resblock_resident": "1 if kr_hifi_resblock can keep the weights of both convs (n1 / n2 K-half blocks of 4 KB) resident in shared memory next to its activation slabs — the only regime it supports; 0 = use two kr_gemm_ex launches.",
+    "kr_hifi_resblock_resident": "Non-zero if kr_hifi_resblock can keep the weights of both convs (n1 / n2 K-half blocks of 4 KB) resident in shared memory next to its activation slabs — the only regime it supports: the number of tile slots it will run with (2 = two tiles ping-pong, 1); 0 = use two kr_gemm_ex launches.",
     "kr_hifi_post_tanh": "conv_post (C -> 1, k=7, pad 3) + tanh on the channels-last activation, inference/hifigan_vocoder.py:131-132.",
     "kr_wave_peak": "peak[b] = max |wav[b, :len[b]]| — the peak normalisation x / (max|x| + 1e-9) of data/dataset.py:672 is applied inside kr_mel_stft.",
     "kr_mel_stft": "Log-mel features out[B, n_mels, frames_max] = log(melfb(|STFT|^2) + log_eps): reflect pad 512, periodic Hann 1024, hop 256, 513 bins, dense filterbank fb_t[n_mels, 513] (HTK, norm=None) with optional fb_ranges[n_mels][2] = [first non-zero bin, one past the last) so that the exact zeros of the triangular filters are skipped (bit-identical to the dense product); frames beyond 1 + len//256 are zero. Replaces torchaudio.transforms.MelSpectrogram + log of data/dataset.py:162-178,694-697.",
