@@ -49,6 +49,12 @@ struct GemmParams {
   // 64-channel block, the weight K blocks stream through the ring, and every weight block feeds `msub` 128-row sub-tiles
   // (msub accumulators in TMEM) — the L2 -> SM traffic per MMA is what bounds these convs
   int slab_stream, msub, slab_bufs, slab_buf_bytes, slab_box_rows, tmem_cols;
+  // slab-stream with swapped operands (BLOCK_N = 128, msub = 2): D^T[128 output channels x 256 rows] = W_blk . slab^T — ONE
+  // N = 256 MMA per K step instead of two N = 128 ones.  A 1-CTA N = 128 MMA re-reads 8 KB of operands per 64 clocks, the
+  // whole shared-memory bandwidth (measured cap 0.85 PFLOP/s, also at 8192^3 with BLOCK_N = 128); N = 256 reads 12 KB per
+  // 128 clocks.  The accumulator then holds channels on the TMEM lanes and rows in the columns; the epilogue's staging
+  // tile transposes it back, everything after the staging tile is unchanged.
+  int swap;
   void* C; long long ldc, c_batch_stride; int c_mode;
   bf16* C2; long long ldc2, c2_batch_stride; float act_slope;
   const float* bias;
@@ -341,6 +347,14 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tc_fence_after();
               const uint32_t sb = smem_u32(ring_b + s * L::B_BYTES);
               const uint32_t acc = (cb > 0 || tap > 0) ? 1u : 0u;
+              if (p.swap) {
+                constexpr uint32_t idesc_t = make_idesc_bf16(128, 256, 0, 0);
+                const uint32_t sx = slab + tap * p.conv_dil * ROWB;      // 256 consecutive slab rows = the N operand
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                  umma_bf16_ss(tmem_d, make_smem_desc_sw(sb + k * 32, 16, SBO, LAYOUT), make_smem_desc_sw(sx + k * 32, 16, SBO, LAYOUT),
+                               idesc_t, (acc | (k > 0)) ? 1u : 0u);
+              } else
               for (int sub = 0; sub < p.msub; ++sub) {
                 const uint32_t sa = slab + (tap * p.conv_dil + sub * BLOCK_M) * ROWB;
 #pragma unroll
@@ -425,7 +439,7 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (tile_alt && (lt & 1) != half) continue;
       const TileCoord tc = decode_tile(p, tile);
       for (int sub = 0; sub < p.msub; ++sub) {        // 128-row sub-tiles of the tile (1 except in slab-stream mode)
-      const int mw0 = (tc.m_blk * p.msub + sub) * BLOCK_M + lg * 32;   // first row of this warp's 32-row slab
+      const int mw0_t = (tc.m_blk * p.msub + sub) * BLOCK_M + lg * 32;   // first row of this warp's 32-row slab
       const int n0 = tc.n_blk * BLOCK_N;
       const int buf = lt & 1;
       const uint32_t use = (uint32_t)(lt >> 1);
@@ -440,11 +454,13 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (DROP) {
         dc = drop_ctx(p.drop);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rowf[i] = drop_row_scale(p.drop, min(mw0 + (lane >> 3) + 4 * i, p.M - 1));
+        for (int i = 0; i < 8; ++i) rowf[i] = drop_row_scale(p.drop, min(mw0_t + (lane >> 3) + 4 * i, p.M - 1));
       }
 #pragma unroll 1
       for (int c = tile_alt ? 0 : half; c < BLOCK_N / 32; c += 2) {
-        const int nb = n0 + c * 32;
+        // swapped slab-stream tiles: TMEM lanes = output channels n0 + 32 lg .., column chunk (sub, c) = 32 output rows
+        const int nb = p.swap ? n0 + lg * 32 : n0 + c * 32;
+        const int mw0 = p.swap ? tc.m_blk * (2 * BLOCK_M) + (sub * (BLOCK_N / 32) + c) * 32 : mw0_t;
         if (nb >= p.N) break;                          // warp-uniform
         // The epilogue is ISSUE-bound for the short-K GEMMs / convs of this model (it was ~870 warp instructions
         // per 32x32 chunk = 3500 issue cycles per 128x128 tile vs ~2000 MMA cycles), so everything below keeps
@@ -493,19 +509,29 @@ kr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (buf * p.msub + sub) * BLOCK_N + (static_cast<uint32_t>(lg * 32) << 16) + c * 32, r);
         tmem_ld_wait();
+        if (p.swap) {      // register t of lane l = (row t, channel l) of the 32 x 32 block: transposed, conflict-free both ways
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) =
-              make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+          for (int t = 0; t < 32; ++t) stg[t * 32 + lane] = __uint_as_float(r[t]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+                make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        }
         __syncwarp();
         if (vec_ok) {
           // (3) back in the coalesced layout: v[i] = row m_first + 4*i, columns [n, n+4)
           float4 v[8];
           const float* sp = stg + crow * 32;
           const int xs = lane & 7;
+          if (p.swap) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)   // row 4*i + crow: (row & 7) = ((i & 1) << 2) | crow
-            v[i] = *reinterpret_cast<const float4*>(sp + i * 128 + ((xs ^ (((i & 1) << 2) | crow)) << 2));
+            for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(sp + i * 128 + (xs << 2));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)   // row 4*i + crow: (row & 7) = ((i & 1) << 2) | crow
+              v[i] = *reinterpret_cast<const float4*>(sp + i * 128 + ((xs ^ (((i & 1) << 2) | crow)) << 2));
+          }
           if (p.alpha != 1.f) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { v[i].x *= p.alpha; v[i].y *= p.alpha; v[i].z *= p.alpha; v[i].w *= p.alpha; }
@@ -768,6 +794,16 @@ extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
     block_n = a->force_block_n;
 
   const bool b_shared = batch > 1 && a->stride_b == 0;
+  // Convs whose weights cannot stay resident even as a 128-row tile (the 128 / 256-channel HiFi-GAN stages): 128-column
+  // tiles, so that slab-stream mode below runs with swapped operands (N = 256 MMAs, see GemmParams::swap).
+  {
+    const long long tiles2 = (long long)((m_tiles + 1) / 2) * ((N + 127) / 128) * batch;
+    const bool vec = !(N & 3) && !(a->ldc & 3) && !(a->ldr & 3) && !(a->ldr2 & 3) && !(a->ldc2 & 3);
+    if (conv && a->conv_taps > 1 && !a->no_slab && bk == BLOCK_K && !a->b_mn_major && splits == 1 && (batch == 1 || b_shared) &&
+        (N % 128) == 0 && vec && a->force_block_n == 0 && tiles2 >= kNumSMs &&
+        (long long)total_kb * 128 * bk * 2 + 4LL * BLOCK_M * bk * 2 > SMEM_TOTAL - RING_OFFSET0)
+      block_n = 128;
+  }
   const uint64_t bstride_a = batch > 1 ? (uint64_t)a->stride_a
                                        : (uint64_t)a->lda * (a->a_mn_major ? K : (conv ? a->a_rows : M));
   const uint64_t bstride_b = (batch > 1 && !b_shared) ? (uint64_t)a->stride_b
@@ -829,6 +865,8 @@ extern "C" int kr_gemm_ex(const kr_gemm_args* a, void* stream) {
           long long stages = (avail - (long long)bufs * bytes) / b_bytes;
           if (stages < 3) continue;
           p.slab_stream = 1; p.msub = msub; p.slab_bufs = bufs; p.slab_buf_bytes = bytes; p.slab_rows = rows;
+          p.swap = (msub == 2 && block_n == 128 && (N % 128) == 0 && !(N & 3) && !(a->ldc & 3) && !(a->ldr & 3) &&
+                    !(a->ldr2 & 3) && !(a->ldc2 & 3)) ? 1 : 0;
           p.slab_box_rows = rows > 256 ? rows / 2 : rows;
           p.stages = (int)(stages > MAX_STAGES ? MAX_STAGES : stages);
         }
