@@ -19,10 +19,10 @@
 // of the folded weights (all nine steps of that stage then fit, including k = 11 with dilation 3 / 5).
 //
 //   tile = 128 - 2*h2 output rows (h2 = conv2's reach): conv1 produces exactly the 128 rows of t that conv2 needs for them
-//   warp 0    TMA producer: weights once (64-byte-swizzled 4 KB blocks); per tile the x_act slab (128 + conv1's span rows,
+//   warp 0    TMA producer: weights once (two half blocks per 128B-swizzled 8 KB tile); per tile the x_act slab (128 + conv1's span rows,
 //             fetched ONCE — the taps are row-shifted views of it) into a double-buffered slot
 //   warp 1    tcgen05.mma issuer: GEMM1 -> acc1 (TMEM), GEMM2 (A = the t tile in smem, taps = row shifts) -> acc2 (TMEM);
-//             two K = 16 MMAs per half block (A descriptor: 128B-swizzled row + 64 * kh bytes, B descriptor: the block)
+//             two K = 16 MMAs per half block (A descriptor: 128B-swizzled row + 64 * kh bytes, B descriptor: the block's half of its tile)
 //   warps 2-9 two independent TILE SLOTS of four epilogue warps each (even / odd tiles; own acc1, acc2, t tile, barriers):
 //             epilogue 1: acc1 -> +b1 -> lrelu -> zero outside [0, L) (conv2's zero padding applies to t) -> bf16 ->
 //             128B-swizzled smem tile;  epilogue 2: residual operands requested BEFORE the wait for GEMM2, then
@@ -45,15 +45,14 @@ constexpr int RB_SMEM_MAX = 227 * 1024 - 1024;
 
 constexpr int RB_C = 64;                 // physical channels of the activations
 constexpr int RB_MAX_BLOCKS = 48;        // half blocks per conv
-constexpr int RB_HB_BYTES = RB_C * 64;   // one [64 x 32] bf16 half block
+constexpr int RB_PAIR_BYTES = RB_C * 128; // two half blocks side by side: one 128B-swizzled [64 x 64] bf16 tile (8 KB)
 
 struct RbParams {
   int B, L, halo;                        // activations [B, L + 2*halo, 64]
   int n1, n2, lead1, h2;                 // half blocks of conv1 / conv2; lead1 = -min conv1 offset; h2 = conv2's reach
   int slots;                             // 2: two tile slots ping-pong; 1: one slot (its slab / t tile make room for more weights)
-  short off1[RB_MAX_BLOCKS];             // conv1 block -> row offset into the slab (>= 0)
-  short off2[RB_MAX_BLOCKS];             // conv2 block -> row offset into the t tile (0 .. 2*h2)
-  unsigned char kh1[RB_MAX_BLOCKS], kh2[RB_MAX_BLOCKS];   // input-channel half of the block
+  // block -> start of its A operand inside the slab (conv1) / the t tile (conv2), in 64-byte units: 2 * row offset + half
+  unsigned short a1[RB_MAX_BLOCKS], a2[RB_MAX_BLOCKS];
   int slab_rows, rows_out, tiles_per_item, total_tiles;
   const float* b1; const float* b2;
   const float* resid; long long r_ld, r_bs;         // fp32, pointing at time 0 of item 0
@@ -85,11 +84,14 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   uint8_t* slab = smem + 1024;                  // [2][CB][RB_MAX_SLAB rows][128 B]
   const int sh = p.slots - 1;                   // local tile lt -> slot lt & sh, use count lt >> sh
   uint8_t* tt = slab + p.slots * SLAB_BYTES;    // [slots][RB_TROWS rows][128 B]
-  uint8_t* wres = tt + p.slots * T_BYTES;       // [n1 + n2] half blocks: [64 rows][64 B], 64B-swizzled
+  // weights: half blocks 2t, 2t+1 of a conv share the 128B-swizzled tile t ([64 rows][128 B]); conv2's tiles follow conv1's
+  // (a 64-byte-swizzled 4 KB tile per half block was measured 25 % slower on the MMA-bound k = 7 steps)
+  uint8_t* wres = tt + p.slots * T_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h2 = p.h2;
   const int n1 = p.n1, n2 = p.n2;                             // half blocks of the two GEMMs
+  const int t1 = (n1 + 1) >> 1, t2 = (n2 + 1) >> 1;           // ... and their weight tiles
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_w1); tma_prefetch_desc(&tm_w2);
@@ -117,10 +119,10 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(wres_bar, (uint32_t)((n1 + n2) * RB_HB_BYTES));
-      for (int hb = 0; hb < n1 + n2; ++hb) {
-        if (hb < n1) tma_load_3d(wres + hb * RB_HB_BYTES, &tm_w1, wres_bar, hb * 32, 0, 0);
-        else         tma_load_3d(wres + hb * RB_HB_BYTES, &tm_w2, wres_bar, (hb - n1) * 32, 0, 0);
+      mbar_arrive_expect_tx(wres_bar, (uint32_t)((t1 + t2) * RB_PAIR_BYTES));   // (columns beyond n * 32 are zero-filled)
+      for (int t = 0; t < t1 + t2; ++t) {
+        if (t < t1) tma_load_3d(wres + t * RB_PAIR_BYTES, &tm_w1, wres_bar, t * 64, 0, 0);
+        else        tma_load_3d(wres + t * RB_PAIR_BYTES, &tm_w2, wres_bar, (t - t1) * 64, 0, 0);
       }
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
@@ -128,7 +130,7 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const int sb = lt & sh;
         mbar_wait(&slab_empty[sb], ((lt >> sh) & 1) ^ 1);
         mbar_arrive_expect_tx(&slab_full[sb], (uint32_t)(CB * p.slab_rows * 128));
-        // t row j <-> time m0 - h2 + j; conv1 block i reads time m0 - h2 + j + off1[i] - lead1
+        // t row j <-> time m0 - h2 + j; conv1 block i reads time m0 - h2 + j + (its row offset) - lead1
         const int row0 = p.halo + m0 - h2 - p.lead1;
 #pragma unroll
         for (int cb = 0; cb < CB; ++cb)
@@ -149,13 +151,17 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         mbar_wait(&acc2_empty[s], ph ^ 1u);         // ... and finished reading acc2 of the slot's previous tile
         tc_fence_after();
         const uint32_t acc2 = tmem_base + 2 * C + s * C;
+        const uint32_t a_base = smem_u32(tt + s * T_BYTES), b_base = smem_u32(wres + t1 * RB_PAIR_BYTES);
+        // (unrolled: the block table reads of the next blocks are issued ahead — one thread feeds the tensor pipe, and a
+        //  dependent constant load per two 32-clock MMAs made the k = 7 steps issue-bound: 361 vs 285 us)
+        //  and the descriptors are one 64-bit add each: the start-address field counts 16-byte units and cannot carry)
+        const uint64_t da0 = make_smem_desc_sw128(a_base, 16, 1024), db0 = make_smem_desc_sw128(b_base, 16, 1024);
+#pragma unroll 4
         for (int i = 0; i < n2; ++i) {
-          const uint32_t a = smem_u32(tt + s * T_BYTES + p.off2[i] * 128 + p.kh2[i] * 64);
-          const uint32_t b = smem_u32(wres + (n1 + i) * RB_HB_BYTES);
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_bf16_ss(acc2, make_smem_desc_sw128(a + k * 32, 16, 1024), make_smem_desc_sw(b + k * 32, 16, 512, 4u),
-                         idesc, (i > 0 || k > 0) ? 1u : 0u);
+          const uint64_t da = da0 + (uint32_t)p.a2[i] * 4u;
+          const uint64_t db = db0 + (uint32_t)((i >> 1) * (RB_PAIR_BYTES / 16) + (i & 1) * 4);
+          umma_bf16_ss(acc2, da, db, idesc, i > 0 ? 1u : 0u);
+          umma_bf16_ss(acc2, da + 2, db + 2, idesc, 1u);
         }
         umma_commit(&acc2_full[s]);
       };
@@ -169,13 +175,14 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         mbar_wait(&slab_full[s], (lt >> sh) & 1);
         tc_fence_after();
         const uint32_t acc1 = tmem_base + s * C;
+        const uint32_t a_base = smem_u32(slab + s * SLAB_BYTES), b_base = smem_u32(wres);
+        const uint64_t da0 = make_smem_desc_sw128(a_base, 16, 1024), db0 = make_smem_desc_sw128(b_base, 16, 1024);
+#pragma unroll 4
         for (int i = 0; i < n1; ++i) {
-          const uint32_t a = smem_u32(slab + s * SLAB_BYTES + p.off1[i] * 128 + p.kh1[i] * 64);
-          const uint32_t b = smem_u32(wres + i * RB_HB_BYTES);
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_bf16_ss(acc1, make_smem_desc_sw128(a + k * 32, 16, 1024), make_smem_desc_sw(b + k * 32, 16, 512, 4u),
-                         idesc, (i > 0 || k > 0) ? 1u : 0u);
+          const uint64_t da = da0 + (uint32_t)p.a1[i] * 4u;
+          const uint64_t db = db0 + (uint32_t)((i >> 1) * (RB_PAIR_BYTES / 16) + (i & 1) * 4);
+          umma_bf16_ss(acc1, da, db, idesc, i > 0 ? 1u : 0u);
+          umma_bf16_ss(acc1, da + 2, db + 2, idesc, 1u);
         }
         umma_commit(&slab_empty[s]);
         umma_commit(&acc1_full[s]);
@@ -325,7 +332,7 @@ int launch_rb(const CUtensorMap& tx, const CUtensorMap& t1, const CUtensorMap& t
     if (e != cudaSuccess) { kr_set_error(cudaGetErrorString(e)); return KR_ERR_CUDA; }
     attr = true;
   }
-  const int smem = rb_fixed_smem(p.slots) + (p.n1 + p.n2) * RB_HB_BYTES + 1024;
+  const int smem = rb_fixed_smem(p.slots) + ((p.n1 + 1) / 2 + (p.n2 + 1) / 2) * RB_PAIR_BYTES + 1024;
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
   kr::launch(hifi_resblock_kernel, grid, RB_THREADS, smem, st, tx, t1, t2, p);
   return KR_OK;
@@ -336,7 +343,7 @@ int launch_rb(const CUtensorMap& tx, const CUtensorMap& t1, const CUtensorMap& t
 int rb_slots(int n1, int n2) {
   if (n1 < 1 || n2 < 1 || n1 > RB_MAX_BLOCKS || n2 > RB_MAX_BLOCKS) return 0;
   for (int slots = 2; slots >= 1; --slots)
-    if (rb_fixed_smem(slots) + (n1 + n2) * RB_HB_BYTES <= RB_SMEM_MAX) return slots;
+    if (rb_fixed_smem(slots) + ((n1 + 1) / 2 + (n2 + 1) / 2) * RB_PAIR_BYTES <= RB_SMEM_MAX) return slots;
   return 0;
 }
 
@@ -375,8 +382,8 @@ extern "C" int kr_hifi_resblock(const void* x_act, int B, long long L, int halo,
   }
   RbParams p{};
   p.B = B; p.L = (int)L; p.halo = halo; p.n1 = n1; p.n2 = n2; p.lead1 = lead; p.h2 = h2; p.slots = rb_slots(n1, n2);
-  for (int i = 0; i < n1; ++i) { p.off1[i] = (short)(off1[i] + lead); p.kh1[i] = (unsigned char)kh1[i]; }
-  for (int i = 0; i < n2; ++i) { p.off2[i] = (short)(off2[i] + h2); p.kh2[i] = (unsigned char)kh2[i]; }
+  for (int i = 0; i < n1; ++i) p.a1[i] = (unsigned short)(2 * (off1[i] + lead) + kh1[i]);
+  for (int i = 0; i < n2; ++i) p.a2[i] = (unsigned short)(2 * (off2[i] + h2) + kh2[i]);
   p.slab_rows = slab_rows; p.rows_out = 128 - 2 * h2;
   p.tiles_per_item = (int)((L + p.rows_out - 1) / p.rows_out);
   p.total_tiles = p.tiles_per_item * B;
@@ -388,9 +395,9 @@ extern "C" int kr_hifi_resblock(const void* x_act, int B, long long L, int halo,
   int rc;
   // activation: (64, rows_phys, B), box (64 channels, slab_rows, 1); rows beyond the tensor are zero-filled by TMA
   if ((rc = kr_make_tmap_bf16_3d(&tx, x_act, RB_C, rows_phys, B, RB_C, rows_phys * RB_C, 64, slab_rows)) != KR_OK) return rc;
-  // weights: (K = n * 32, 64 rows, 1), box (32 k, 64 rows), 64-byte swizzle
-  if ((rc = kr_make_tmap_bf16_3d(&t1, w1, (unsigned long long)n1 * 32, RB_C, 1, (unsigned long long)n1 * 32, (unsigned long long)n1 * 32 * RB_C, 32, RB_C, 1)) != KR_OK) return rc;
-  if ((rc = kr_make_tmap_bf16_3d(&t2, w2, (unsigned long long)n2 * 32, RB_C, 1, (unsigned long long)n2 * 32, (unsigned long long)n2 * 32 * RB_C, 32, RB_C, 1)) != KR_OK) return rc;
+  // weights: (K = n * 32, 64 rows, 1), box (64 k = two half blocks, 64 rows), 128-byte swizzle
+  if ((rc = kr_make_tmap_bf16_3d(&t1, w1, (unsigned long long)n1 * 32, RB_C, 1, (unsigned long long)n1 * 32, (unsigned long long)n1 * 32 * RB_C, 64, RB_C)) != KR_OK) return rc;
+  if ((rc = kr_make_tmap_bf16_3d(&t2, w2, (unsigned long long)n2 * 32, RB_C, 1, (unsigned long long)n2 * 32, (unsigned long long)n2 * 32 * RB_C, 64, RB_C)) != KR_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   rc = launch_rb(tx, t1, t2, p, st);
   if (rc != KR_OK) return rc;
