@@ -28,8 +28,9 @@
 //             128B-swizzled smem tile;  epilogue 2: residual operands requested BEFORE the wait for GEMM2, then
 //             acc2 -> fused bias / residual / MRF / activation -> global, in a coalesced layout through a staged transpose
 // Issue order  G1(0), G1(1), G2(0), G1(2), G2(1), ...: while one slot converts its t tile or writes its outputs, the tensor
-// pipe works for the other slot.  Weights that only fit next to ONE slot (k = 11 on 64 channels: 176 KB) run in one-slot mode,
-// G1(0), G2(0), G1(1), G2(1), ...: epilogue 2 of a tile still runs under GEMM1 of the next.
+// pipe works for the other slot.  Weights that only fit next to ONE slot (k = 11 on 64 channels: 176 KB) run in one-slot mode:
+// the same issue order with a single slab, t tile and acc2 and four epilogue warps — acc1 stays double-buffered, so GEMM1 of
+// the next tile runs under the epilogues of the current one.
 // Channels-last activations [B, L + 2*halo, 64] with zero halos (halo >= h2 + conv1's reach); weights [64, n * 32] bf16.
 #include "kr_common.cuh"
 #include "kokoro_b200.h"
@@ -168,13 +169,13 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
         const int s = lt & sh;
-        // one slot: acc1 is that of the PREVIOUS tile, whose t tile must be complete before it is overwritten -> G2 first
-        if (sh == 0 && lt > 0) gemm2(lt - 1);
         // ---- GEMM1: acc1[slot] = sum over the half blocks of slab[rows shifted by off1, channel half kh1] . W1 block ----
         // (acc1[slot] is free: GEMM2 of the slot's previous tile was issued, i.e. its t tile — read from acc1 — was complete)
         mbar_wait(&slab_full[s], (lt >> sh) & 1);
         tc_fence_after();
-        const uint32_t acc1 = tmem_base + s * C;
+        // acc1 is double-buffered by tile parity in BOTH modes (in one-slot mode only the slab, the t tile and acc2 are single):
+        // acc1[lt & 1] was last read by epilogue 1 of tile lt - 2, which finished before GEMM2(lt - 2) was issued
+        const uint32_t acc1 = tmem_base + (lt & 1) * C;
         const uint32_t a_base = smem_u32(slab + s * SLAB_BYTES), b_base = smem_u32(wres);
         const uint64_t da0 = make_smem_desc_sw128(a_base, 16, 1024), db0 = make_smem_desc_sw128(b_base, 16, 1024);
 #pragma unroll 4
@@ -185,8 +186,8 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           umma_bf16_ss(acc1, da + 2, db + 2, idesc, 1u);
         }
         umma_commit(&slab_empty[s]);
-        umma_commit(&acc1_full[s]);
-        if (sh != 0 && lt > 0) gemm2(lt - 1);
+        umma_commit(&acc1_full[lt & 1]);
+        if (lt > 0) gemm2(lt - 1);
       }
       if (lt > 0) gemm2(lt - 1);
     }
@@ -195,7 +196,7 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const int lg = warp & 3, slot = (warp - 2) >> 2;
     const int j = lg * 32 + lane;                                       // row of the tile owned by this thread
     const uint32_t t_lane = static_cast<uint32_t>(lg * 32) << 16;
-    const uint32_t acc1 = tmem_base + slot * C + t_lane, acc2 = tmem_base + 2 * C + slot * C + t_lane;
+    const uint32_t acc2 = tmem_base + 2 * C + slot * C + t_lane;
     uint8_t* tts = tt + slot * T_BYTES;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
@@ -203,7 +204,8 @@ hifi_resblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       const uint32_t ph = (uint32_t)(lt >> sh) & 1u;
       const int bz = tile / p.tiles_per_item, m0 = (tile % p.tiles_per_item) * p.rows_out;
       // ---- epilogue 1: t row j (time m0 - h2 + j) ----
-      mbar_wait(&acc1_full[slot], ph);
+      const uint32_t acc1 = tmem_base + (lt & 1) * C + t_lane;
+      mbar_wait(&acc1_full[lt & 1], (uint32_t)(lt >> 1) & 1u);
       tc_fence_after();
       {
         const int time = m0 - h2 + j;
