@@ -221,9 +221,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc_fence_after();
           const uint32_t tS = tmem_base + w * 128, tP = tmem_base + 256 + w * 64, tO = tmem_base + 384 + w * 64;
           const uint32_t aV = smem_u32(sV + st * TILE_BYTES);
-          const int ksteps = 2 * nck_of(j);
-          for (int k = 0; k < ksteps; ++k)        // 16 keys = 8 packed TMEM columns per MMA
-            umma_bf16_ts(tO, tP + k * 8, desc_mn64(aV, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          const int ksteps = 2 * nck_of(j);       // 16 keys = 8 packed TMEM columns per MMA
+          if (ksteps == TK / 16) {                // full tile: unrolled (one thread issues every MMA of the CTA)
+#pragma unroll
+            for (int k = 0; k < TK / 16; ++k)
+              umma_bf16_ts(tO, tP + k * 8, desc_mn64(aV, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          } else {
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16_ts(tO, tP + k * 8, desc_mn64(aV, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          }
           if (j + 1 < n_w[w]) {
             const int ns = (j + 1) % FWD_STAGES;
             mbar_wait(&k_full[ns], ((j + 1) / FWD_STAGES) & 1);
@@ -553,8 +559,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int k = 0; k < TQ / 16; ++k)   // dK[kv,d] += dS^T Q
             umma_bf16_ss(tmem_dK, desc_mn128(adS, k), desc_mn64(aQ, k), idesc_tt, (it > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 2 * nck; ++k)   // dQ[q,d] = dS K, contraction over the (computed) keys
-            umma_bf16_ss(tmem_dQ, desc_k128(adS, k), desc_mn64(aK, k), idesc_dq, k > 0 ? 1u : 0u);
+          if (nck == 4) {                     // dQ[q,d] = dS K, contraction over the (computed) keys
+#pragma unroll
+            for (int k = 0; k < TK / 16; ++k)
+              umma_bf16_ss(tmem_dQ, desc_k128(adS, k), desc_mn64(aK, k), idesc_dq, k > 0 ? 1u : 0u);
+          } else {
+            for (int k = 0; k < 2 * nck; ++k)
+              umma_bf16_ss(tmem_dQ, desc_k128(adS, k), desc_mn64(aK, k), idesc_dq, k > 0 ? 1u : 0u);
+          }
           umma_commit(out_bar);
         }
         if (it + 2 < n_it) {                  // refill this Q/dO buffer once MMA2(it) has drained it
