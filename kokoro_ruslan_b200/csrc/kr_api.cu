@@ -19,10 +19,8 @@ namespace kr {
 void kr_prefer_max_smem(const void* kernel) {
   static std::mutex mu;
   static std::unordered_set<const void*> seen;
-  static int enabled = -1;
   std::lock_guard<std::mutex> lock(mu);
-  if (enabled < 0) { const char* e = getenv("KR_CARVEOUT"); enabled = (e != nullptr && e[0] == '0') ? 0 : 1; }
-  if (!enabled || !seen.insert(kernel).second) return;
+  if (!seen.insert(kernel).second) return;
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaGetLastError();   // best effort
 }

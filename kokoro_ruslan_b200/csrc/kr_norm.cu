@@ -422,27 +422,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) qkv_prep_bwd_kernel(const Pr
   if (threadIdx.x < 64 && pp.dgain != nullptr) atomicAdd(pp.dgain + threadIdx.x, sm[threadIdx.x]);
 }
 
-// occupancy variant of the two register-heavy backward kernels: 3 blocks / SM caps them at 80 registers (they
-// spill ~260 bytes since the dropout specs were added), 2 blocks / SM lets them keep everything in registers
-int norm_minb() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("KR_NORM_MINB"); v = (e != nullptr && e[0] == '3') ? 3 : 2; }
-  return v;
-}
-int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e != nullptr && e[0] >= '0' && e[0] <= '9') ? atoi(e) : dflt;
-}
+// Launch geometry, fixed by sweeps on B200 (round 2, bench shape; the sweep knobs are gone):
+//   * ln_bwd runs at 2 blocks / SM (launch bounds): 3 blocks / SM would cap it at 80 registers and spill ~260 bytes since
+//     the dropout specs were added;
+//   * persistent backward kernels (their column-gradient epilogue costs D atomics per block): 2 blocks per SM beat 1 and 4
+//     (ln_bwd 9.1 vs 10.7 us);
+//   * qkv_prep: 8 blocks per SM forward, 2 backward (18.1 vs 22.3 us at 6).
 int row_blocks(int N) { return (N + WARPS - 1) / WARPS; }
-// blocks per SM of the persistent backward kernels (their column-gradient epilogue costs D atomics per block)
-int persistent_blocks(int N) {
-  static int per_sm = env_int("KR_NORM_BLOCKS_PER_SM", 2);   // tools/norm_sweep.sh: 2 beats 1 and 4 (ln_bwd 9.1 vs 10.7 us)
-  return min(row_blocks(N), kNumSMs * per_sm);
-}
-int prep_blocks_per_sm(bool bwd) {
-  static int f = env_int("KR_PREP_FWD_BLOCKS_PER_SM", 8), b = env_int("KR_PREP_BWD_BLOCKS_PER_SM", 2);   // 18.1 us vs 22.3 us at 6
-  return bwd ? b : f;
-}
+int persistent_blocks(int N) { return min(row_blocks(N), kNumSMs * 2); }
+int prep_blocks_per_sm(bool bwd) { return bwd ? 2 : 8; }
 
 }  // namespace
 
@@ -471,15 +459,9 @@ extern "C" int kr_layernorm_bwd(const float* dy, const float* x, const float* me
                                 float* dcol_bf16, void* stream) {
   if (N <= 0) return KR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (norm_minb() == 3) {
-    DISPATCH_NV(D, (kr::launch(ln_bwd_kernel<NV, 3>, persistent_blocks(N), WARPS * 32, 0, st,
-                       dy, x, mean, rstd, gamma, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dgamma,
-                       dbeta, N, kr_drop_to_device(drop_bf16), dcol_bf16)));
-  } else {
-    DISPATCH_NV(D, (kr::launch(ln_bwd_kernel<NV, 2>, persistent_blocks(N), WARPS * 32, 0, st,
-                       dy, x, mean, rstd, gamma, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dgamma,
-                       dbeta, N, kr_drop_to_device(drop_bf16), dcol_bf16)));
-  }
+  DISPATCH_NV(D, (kr::launch(ln_bwd_kernel<NV, 2>, persistent_blocks(N), WARPS * 32, 0, st,
+                     dy, x, mean, rstd, gamma, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dgamma,
+                     dbeta, N, kr_drop_to_device(drop_bf16), dcol_bf16)));
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
@@ -561,8 +543,7 @@ extern "C" int kr_qkv_prep_bwd(const void* in0, const void* in1, const void* in2
   const long long nb_ = (total + WARPS - 1) / WARPS;
   const int per_part = kNumSMs * prep_blocks_per_sm(true) / n_parts;
   const int blocks = (int)(nb_ < per_part ? nb_ : per_part);
-  if (norm_minb() == 3) kr::launch(qkv_prep_bwd_kernel<3>, dim3(blocks, n_parts), WARPS * 32, 0, st, p);
-  else                  kr::launch(qkv_prep_bwd_kernel<2>, dim3(blocks, n_parts), WARPS * 32, 0, st, p);
+  kr::launch(qkv_prep_bwd_kernel<2>, dim3(blocks, n_parts), WARPS * 32, 0, st, p);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }
