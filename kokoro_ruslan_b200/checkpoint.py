@@ -37,14 +37,16 @@ def group_layout(names: List[str]) -> List[List[str]]:
     return groups
 
 
-def optimizer_state_dict(opt, lrs: Optional[List[float]] = None, step: Optional[int] = None) -> Dict:
-    """``torch.optim.AdamW.state_dict()``-shaped snapshot (CPU tensors) of a FusedAdamW."""
+def optimizer_state_dict(opt, lrs: Optional[List[float]] = None, step: Optional[int] = None, on_device: bool = False) -> Dict:
+    """``torch.optim.AdamW.state_dict()``-shaped snapshot of a FusedAdamW: CPU tensors, or — on_device, for save_sharded,
+    which copies only a rank's share — views of the device moment buffers."""
     st, cfg = opt.store, opt.cfg
     if step is None:
         step = int(opt.ctrl.cpu()[_STEP])
     if lrs is None:
         lrs = [float(x) for x in opt.g_lr.cpu().tolist()]
     hp = group_hparams(cfg)
+    take = (lambda t: t.detach()) if on_device else (lambda t: t.detach().cpu().contiguous().clone())
     state: Dict[int, Dict[str, torch.Tensor]] = {}
     param_groups = []
     idx = 0
@@ -53,8 +55,7 @@ def optimizer_state_dict(opt, lrs: Optional[List[float]] = None, step: Optional[
         for n in names:
             if step > 0:                              # torch creates a parameter's state at its first step
                 state[idx] = {"step": torch.tensor(float(step)),
-                              "exp_avg": st.ref_view(st.exp_avg, n).detach().cpu().contiguous().clone(),
-                              "exp_avg_sq": st.ref_view(st.exp_avg_sq, n).detach().cpu().contiguous().clone()}
+                              "exp_avg": take(st.ref_view(st.exp_avg, n)), "exp_avg_sq": take(st.ref_view(st.exp_avg_sq, n))}
             ids.append(idx)
             idx += 1
         param_groups.append({"lr": float(lrs[g]), "betas": tuple(cfg.adam_betas), "eps": cfg.adam_eps,
@@ -220,3 +221,106 @@ def _tensors(obj):
     elif isinstance(obj, (list, tuple)):
         for v in obj:
             yield from _tensors(v)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Sharded checkpoints.  The data-parallel replicas hold IDENTICAL state (weights, EMA, Adam moments:
+# tests/test_dp_gpu.py), so no gather is needed: rank r copies only ITS share of the tensors off the device and writes
+# `<path>.shard<r>of<N>`; rank 0 also writes `<path>` itself with every non-tensor entry and the table of which shard holds
+# which tensor.  `load_sharded(path)` rebuilds exactly the dict a single-file `torch.save(payload, path)` would have held,
+# so `cli.resume`, the reference's `torch.load(...)["model_state_dict"]` consumers and the EMA export read it unchanged
+# after one merge.  Device-to-host volume and file-system time per rank drop by the world size.
+# ----------------------------------------------------------------------------------------------------------------------
+_SHARD_KEY = "__kokoro_b200_sharded__"
+
+
+def _tensor_paths(obj, prefix=()):
+    if isinstance(obj, torch.Tensor):
+        yield prefix, obj
+    elif isinstance(obj, dict):
+        for k, v in obj.items():
+            yield from _tensor_paths(v, prefix + (k,))
+    elif isinstance(obj, (list, tuple)):
+        for i, v in enumerate(obj):
+            yield from _tensor_paths(v, prefix + (i,))
+
+
+def shard_assignment(payload: Dict, world: int) -> Dict[tuple, int]:
+    """tensor path -> rank: largest tensors first, each to the currently lightest rank (deterministic on every rank)."""
+    items = sorted(_tensor_paths(payload), key=lambda kv: (-kv[1].numel() * kv[1].element_size(), repr(kv[0])))
+    load = [0] * world
+    out = {}
+    for path, t in items:
+        r = min(range(world), key=lambda i: (load[i], i))
+        out[path] = r
+        load[r] += t.numel() * t.element_size()
+    return out
+
+
+def _strip(obj, prefix, table):
+    """payload with every tensor replaced by a (marker, rank) placeholder"""
+    if isinstance(obj, torch.Tensor):
+        return (_SHARD_KEY, table[prefix])
+    if isinstance(obj, dict):
+        return {k: _strip(v, prefix + (k,), table) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_strip(v, prefix + (i,), table) for i, v in enumerate(obj))
+    return obj
+
+
+def shard_path(path: str, rank: int, world: int) -> str:
+    return f"{path}.shard{rank}of{world}"
+
+
+def save_sharded(path: str, payload: Dict, rank: int, world: int, writer: Optional["AsyncCheckpointWriter"] = None) -> List[str]:
+    """Called by EVERY rank with the same (replicated) payload; tensors may live on the device.  Returns the files this rank
+    wrote (or queued on `writer`)."""
+    table = shard_assignment(payload, world)
+    mine = {repr(p): t for p, t in _tensor_paths(payload) if table[p] == rank}
+    files = [(shard_path(path, rank, world), {"rank": rank, "world": world, "tensors": mine})]
+    if rank == 0:
+        files.append((path, {_SHARD_KEY: {"world": world, "version": 1}, "skeleton": _strip(payload, (), table)}))
+    for f, obj in files:
+        if writer is not None:
+            writer.save(f, obj)                                        # snapshots this rank's tensors only
+        else:
+            if "tensors" in obj:
+                obj = dict(obj, tensors={k: v.detach().cpu() for k, v in obj["tensors"].items()})
+            tmp = f + ".tmp"
+            torch.save(obj, tmp)
+            os.replace(tmp, f)
+    return [f for f, _ in files]
+
+
+def is_sharded(obj) -> bool:
+    return isinstance(obj, dict) and _SHARD_KEY in obj
+
+
+def load_sharded(path: str, map_location="cpu") -> Dict:
+    """The merged payload of a sharded checkpoint; a plain single-file checkpoint is returned as it is."""
+    head = torch.load(path, map_location=map_location, weights_only=False)
+    if not is_sharded(head):
+        return head
+    world = int(head[_SHARD_KEY]["world"])
+    shards = []
+    for r in range(world):
+        f = shard_path(path, r, world)
+        if not os.path.exists(f):
+            raise FileNotFoundError(f"sharded checkpoint {path}: shard {r} of {world} is missing ({f})")
+        s = torch.load(f, map_location=map_location, weights_only=False)
+        if s.get("rank") != r or s.get("world") != world:
+            raise RuntimeError(f"{f}: written as shard {s.get('rank')} of {s.get('world')}, expected {r} of {world}")
+        shards.append(s["tensors"])
+
+    def fill(obj, prefix):
+        if isinstance(obj, tuple) and len(obj) == 2 and obj[0] == _SHARD_KEY:
+            try:
+                return shards[obj[1]][repr(prefix)]
+            except KeyError:
+                raise RuntimeError(f"sharded checkpoint {path}: tensor {prefix} is not in shard {obj[1]}") from None
+        if isinstance(obj, dict):
+            return {k: fill(v, prefix + (k,)) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(fill(v, prefix + (i,)) for i, v in enumerate(obj))
+        return obj
+    return fill(head["skeleton"], ())

@@ -106,6 +106,9 @@ class RunConfig:
     # computes them, with per-utterance host syncs); off by default until kr_val_metrics has had its first hardware run
     val_metrics: bool = False
     async_checkpoints: bool = False           # torch.save on a writer thread (checkpoint.AsyncCheckpointWriter)
+    # data-parallel runs: every rank writes 1 / world of the tensors (checkpoint.save_sharded; the replicas are identical, so
+    # nothing is gathered); `resume` and checkpoint.load_sharded read both forms.  Off = the reference's single file.
+    sharded_checkpoints: bool = False
 
 
 class TrainingConfig(RunConfig):
@@ -183,7 +186,7 @@ class SyntheticDataset:
                 "phoneme_durations": dur, "stop_token_targets": build_stop_token_targets(T),
                 "pitch": torch.rand(T, generator=g), "energy": torch.rand(T, generator=g),
                 "mel_length": T, "phoneme_length": P, "text": f"synthetic {i}", "audio_file": f"synthetic_{i}.wav"})
-            self.samples.append({"audio_length": T * 256})
+            self.samples.append({"audio_length": T})       # mel frames, as the reference indexes its corpus (dataset.py:311-338)
         self.vocab_size = vocab_size
 
     def __len__(self) -> int:
@@ -197,6 +200,7 @@ class _Subset:
     def __init__(self, ds, indices: Sequence[int]):
         self.ds, self.indices = ds, list(indices)
         self.samples = [ds.samples[i] for i in self.indices]
+        self.thread_safe = getattr(ds, "thread_safe", False)
 
     def __len__(self) -> int:
         return len(self.indices)
@@ -212,8 +216,19 @@ def load_reference_dataset(cfg: RunConfig):
         from kokoro.data.dataset import RuslanDataset                 # type: ignore
         from kokoro.training.config import TrainingConfig             # type: ignore
     except ImportError as exc:
-        raise RuntimeError("a corpus run needs the reference package (`kokoro`) on PYTHONPATH for RuslanDataset; "
-                           "use --synthetic N for a corpus-free run") from exc
+        # no reference package: a corpus whose features the reference has already cached (<corpus>/.feature_cache/*.pt,
+        # dataset.py:412-414,849-866) can still be trained on — the cache files hold everything the step consumes
+        cache_dir = os.path.join(cfg.data_dir, ".feature_cache")
+        if os.path.isdir(cache_dir):
+            from .feature_cache import CachedFeatureDataset, FeatureCache
+            from .params import ModelConfig
+            ds = CachedFeatureDataset.scan(FeatureCache(cache_dir))
+            if len(ds) > 0:
+                top = max(int(ds.cache.load(s["audio_file"])["phoneme_indices"].max()) for s in ds.samples)
+                ds.vocab_size = max(ModelConfig().vocab_size, top + 1)
+                return ds
+        raise RuntimeError("a corpus run needs the reference package (`kokoro`) on PYTHONPATH for RuslanDataset, or a "
+                           "feature cache written by it under <corpus>/.feature_cache; use --synthetic N for a corpus-free run") from exc
     tc = TrainingConfig(data_dir=cfg.data_dir, output_dir=cfg.output_dir, batch_size=cfg.batch_size)
     ds = RuslanDataset(cfg.data_dir, tc)
     ds.vocab_size = len(ds.phoneme_processor.phoneme_to_id)
@@ -273,7 +288,8 @@ def resume(cfg: RunConfig, step, log: Callable[[str], None] = print) -> int:
         if path is None:
             log(f"--resume auto: no checkpoint in {cfg.output_dir}, starting from scratch")
             return 0
-    ck = torch.load(path, map_location="cpu", weights_only=False)
+    from .checkpoint import load_sharded
+    ck = load_sharded(path, map_location="cpu")       # a plain single-file checkpoint comes back as it is
     model_cfg = getattr(getattr(step, "engine", None), "cfg", None)
     if model_cfg is not None and hasattr(model_cfg, "hidden_dim"):
         from .checkpoint import check_model_metadata
@@ -314,7 +330,8 @@ def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
     best, best_epoch, since_best, saved = float("inf"), -1, 0, []
     os.makedirs(cfg.output_dir, exist_ok=True)
     writer = None
-    if cfg.async_checkpoints and rank == 0:
+    shard = (rank, world) if (cfg.sharded_checkpoints and world > 1) else None
+    if cfg.async_checkpoints and (rank == 0 or shard is not None):
         from .checkpoint import AsyncCheckpointWriter
         writer = AsyncCheckpointWriter()
     micro_batches_seen, skipped_seen = 0, 0
@@ -329,9 +346,14 @@ def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
             ds_sampler.set_epoch(epoch)
             batches = list(iter(ds_sampler))
         dev_losses = []
+        if getattr(train_ds, "thread_safe", False):   # cached corpus: the next batches are read and collated ahead of the step
+            from .feature_cache import BatchPrefetcher
+            collated = iter(BatchPrefetcher(train_ds, batches, collate_fn))
+        else:
+            collated = (collate_fn([train_ds[i] for i in b]) for b in batches)
         for win in accumulation_windows(len(batches), cfg.gradient_accumulation_steps):
             for k, bi in enumerate(win):
-                batch = collate_fn([train_ds[i] for i in batches[bi]])
+                batch = next(collated)                # windows cover 0 .. len(batches) - 1 in order
                 if epoch >= cfg.spec_augment_start_epoch:
                     B, T = batch["mel_specs"].shape[:2]
                     step.engine.set_spec_augment(AcousticEngine.draw_spec_spans(B, T, step.engine.D))
@@ -364,15 +386,15 @@ def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
                     rec.update({k: v for k, v in step.read_val_metrics(acc).items() if v is not None})
                 if vm[0] < best - cfg.early_stopping_min_delta:
                     best, best_epoch, since_best = vm[0], epoch, 0
-                    if rank == 0:
-                        saved.append(save_checkpoint(cfg, step, epoch, rec, best, best_epoch, writer))
+                    if rank == 0 or shard is not None:
+                        saved.append(save_checkpoint(cfg, step, epoch, rec, best, best_epoch, writer, shard))
                 else:
                     since_best += 1
         hist.append(rec)
         log(f"epoch {epoch + 1}/{cfg.num_epochs}: " + ", ".join(f"{k}={v:.4f}" for k, v in rec.items()
                                                                   if isinstance(v, float)))
-        if rank == 0 and cfg.save_every > 0 and (epoch + 1) % cfg.save_every == 0:
-            saved.append(save_checkpoint(cfg, step, epoch, rec, best, best_epoch, writer))
+        if (rank == 0 or shard is not None) and cfg.save_every > 0 and (epoch + 1) % cfg.save_every == 0:
+            saved.append(save_checkpoint(cfg, step, epoch, rec, best, best_epoch, writer, shard))
         if world > 1:
             # rank 0 alone may just have written a checkpoint (hundreds of MB through torch.save): the others must not
             # enter the next epoch's collective kernel and spin on it for the duration of one-sided host work
@@ -415,12 +437,15 @@ def _detector_state(step) -> Optional[Dict]:
     return {"ema_norm": c["ema_norm"], "ema_steps": c["ema_steps"], "skipped_total": c["skipped_total"]}
 
 
-def save_checkpoint(cfg: RunConfig, step, epoch: int, rec: Dict, best: float, best_epoch: int, writer=None) -> str:
-    """checkpoint_epoch_{N}.pth with the reference's key names (trainer.py:1994-2031) for what this path owns."""
+def save_checkpoint(cfg: RunConfig, step, epoch: int, rec: Dict, best: float, best_epoch: int, writer=None,
+                    shard: Optional[tuple] = None) -> str:
+    """checkpoint_epoch_{N}.pth with the reference's key names (trainer.py:1994-2031) for what this path owns.
+    shard = (rank, world): called by every rank, each writes its share (checkpoint.save_sharded)."""
     path = os.path.join(cfg.output_dir, f"checkpoint_epoch_{epoch + 1}.pth")
     st = step.store
-    ckpt = {"epoch": epoch, "model_state_dict": {k: v.detach().cpu() for k, v in step.state_dict().items()},
-            "ema_model_state_dict": ({k: v.detach().cpu() for k, v in st.state_dict(st.ema).items()}
+    host = (lambda v: v.detach()) if shard is not None else (lambda v: v.detach().cpu())   # sharded: only own tensors are copied
+    ckpt = {"epoch": epoch, "model_state_dict": {k: host(v) for k, v in step.state_dict().items()},
+            "ema_model_state_dict": ({k: host(v) for k, v in st.state_dict(st.ema).items()}
                                      if getattr(st, "ema", None) is not None else None),
             # counters: scheduler calls made / optimizer steps that really updated the weights (device-side counter: a
             # non-finite step is skipped on the device without a host sync) / micro-batches seen (trainer.py:1994-2031)
@@ -437,12 +462,15 @@ def save_checkpoint(cfg: RunConfig, step, epoch: int, rec: Dict, best: float, be
             "config": _picklable_config(cfg)}
     if hasattr(step, "opt"):                          # Adam moments + step in torch.optim.AdamW.state_dict() form
         from .checkpoint import optimizer_state_dict
-        ckpt["optimizer_state_dict"] = optimizer_state_dict(step.opt)
+        ckpt["optimizer_state_dict"] = optimizer_state_dict(step.opt, on_device=shard is not None)
     model_cfg = getattr(getattr(step, "engine", None), "cfg", None)
     if model_cfg is not None and hasattr(model_cfg, "hidden_dim"):
         from .checkpoint import build_model_metadata
         ckpt["model_metadata"] = build_model_metadata(model_cfg, cfg)
-    if writer is not None:
+    if shard is not None:
+        from .checkpoint import save_sharded
+        save_sharded(path, ckpt, shard[0], shard[1], writer)
+    elif writer is not None:
         writer.save(path, ckpt)                       # serialisation + file system on the writer thread
     else:
         torch.save(ckpt, path)

@@ -3,6 +3,7 @@ dumped from the live reference parser (tests/golden/make_golden_cli.py); the loo
 import argparse
 import json
 import os
+import sys
 
 import pytest
 import torch
@@ -320,3 +321,90 @@ def test_schedule_rewind_undoes_skipped_steps():
         b.advance()
     a.rewind(3)
     assert a.state_dict() == b.state_dict() and a.lrs() == b.lrs()
+
+
+def test_sharded_checkpoint_merges_to_the_single_file_payload(tmp_path):
+    """checkpoint.save_sharded / load_sharded: every rank of a data-parallel run writes its share of the
+    (replicated) tensors; the merged payload equals what a single torch.save would have held, a missing shard is an error, a
+    plain checkpoint passes through load_sharded unchanged, and the shares are balanced."""
+    import torch
+    from kokoro_ruslan_b200 import checkpoint as ck
+    g = torch.Generator().manual_seed(0)
+    payload = {"epoch": 3, "model_state_dict": {f"w{i}": torch.randn(10 + 7 * i, 4, generator=g) for i in range(9)},
+               "ema_model_state_dict": {f"w{i}": torch.randn(10 + 7 * i, 4, generator=g) for i in range(9)},
+               "optimizer_state_dict": {"state": {0: {"step": torch.tensor(5.0), "exp_avg": torch.randn(33, generator=g)}},
+                                        "param_groups": [{"lr": 1e-4, "params": [0], "betas": (0.9, 0.98)}]},
+               "config": {"a": 1}, "best_val_loss": 0.5, "scheduler_state_dict": {"step": 7}, "none": None}
+    world = 4
+    path = str(tmp_path / "checkpoint_epoch_4.pth")
+    written = []
+    for r in range(world):                                   # what the four ranks do, one after the other here
+        written += ck.save_sharded(path, payload, r, world)
+    assert sorted(os.path.basename(f) for f in written) == sorted(
+        ["checkpoint_epoch_4.pth"] + [f"checkpoint_epoch_4.pth.shard{r}of4" for r in range(world)])
+    merged = ck.load_sharded(path)
+
+    def same(a, b):
+        if isinstance(a, torch.Tensor):
+            return isinstance(b, torch.Tensor) and torch.equal(a, b)
+        if isinstance(a, dict):
+            return isinstance(b, dict) and list(a) == list(b) and all(same(a[k], b[k]) for k in a)
+        if isinstance(a, (list, tuple)):
+            return type(a) is type(b) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        return a == b
+    assert same(payload, merged)
+    table = ck.shard_assignment(payload, world)
+    load = [0] * world
+    for p_, t in ck._tensor_paths(payload):
+        load[table[p_]] += t.numel()
+    assert max(load) - min(load) <= max(t.numel() for _, t in ck._tensor_paths(payload))
+    head = torch.load(path, weights_only=False)
+    assert ck.is_sharded(head) and not list(ck._tensor_paths(head))       # the head file holds no tensor
+    os.remove(ck.shard_path(path, 2, world))
+    with pytest.raises(FileNotFoundError):
+        ck.load_sharded(path)
+    plain = str(tmp_path / "plain.pth")
+    torch.save(payload, plain)
+    assert same(payload, ck.load_sharded(plain))
+
+
+def test_cached_corpus_trains_through_the_prefetcher(tmp_path, monkeypatch):
+    """A corpus whose features sit in the reference's cache format (N4) is trained on without the reference package: the
+    CLI's dataset loader falls back to <corpus>/.feature_cache, and the epoch loop takes its batches from the read-ahead
+    prefetcher — the same batches, in the same order, as the synchronous loop."""
+    from kokoro_ruslan_b200 import cli
+    from kokoro_ruslan_b200.data import collate_fn
+    from kokoro_ruslan_b200.feature_cache import BatchPrefetcher, FeatureCache
+    corpus = tmp_path / "corpus"
+    cache = FeatureCache(corpus / ".feature_cache")
+    src = cli.SyntheticDataset(14, seed=5, min_frames=50, max_frames=110)
+    for i in range(len(src)):
+        it = dict(src[i])
+        it["mel_spec"] = it["mel_spec"] if "mel_spec" in it else it["mel"]
+        cache.save(f"utt{i:02d}", {k: v for k, v in it.items() if k in ("mel_spec", "phoneme_indices", "stress_indices",
+                                                                        "phoneme_durations", "stop_token_targets", "pitch",
+                                                                        "energy", "text", "mel_length", "phoneme_length")})
+    for name in ("kokoro", "kokoro.data", "kokoro.data.dataset", "kokoro.training", "kokoro.training.config"):
+        monkeypatch.setitem(sys.modules, name, None)         # the reference package is not importable
+    ds = cli.load_reference_dataset(cli.RunConfig(data_dir=str(corpus), output_dir=str(tmp_path)))
+    assert len(ds) == 14 and ds.vocab_size >= 59 and ds.thread_safe
+    train_ds, val_ds = cli.split_dataset(ds, 0.2, seed=1)
+    assert train_ds.thread_safe
+    cfg = cli.RunConfig(output_dir=str(tmp_path / "out"), num_epochs=2, max_frames_per_batch=300, min_batch_size=1, max_batch_size=4,
+                        save_every=0)
+    step = _StubStep([1.0, 0.9])
+    out = cli.train(cfg, train_ds, val_ds, step)
+    assert len(out["history"]) == 2 and sum(h["batches"] for h in out["history"]) == len(step.calls)
+    # the prefetcher yields exactly the synchronous batches
+    batches = [[0, 3], [1], [2, 4, 5]]
+    want = [collate_fn([train_ds[i] for i in b], pin_memory=False) for b in batches]
+    got = list(BatchPrefetcher(train_ds, batches, lambda items: collate_fn(items, pin_memory=False), depth=2, workers=2))
+    assert len(got) == 3
+    for a, b in zip(want, got):
+        assert sorted(a) == sorted(b) and all(torch.equal(a[k], b[k]) for k in a if isinstance(a[k], torch.Tensor))
+    with pytest.raises(ValueError):
+        BatchPrefetcher(cli.SyntheticDataset(2), [[0]], collate_fn)
+    empty = tmp_path / "nothing"
+    empty.mkdir()
+    with pytest.raises(RuntimeError):
+        cli.load_reference_dataset(cli.RunConfig(data_dir=str(empty), output_dir=str(tmp_path)))

@@ -67,3 +67,48 @@ def test_two_rank_gloo_protocol():
                   + (torch.tensor(p1).unsqueeze(0) - torch.tensor(t1).unsqueeze(1)).mean(0))
     assert torch.allclose(torch.tensor(g0), want, atol=1e-6)
     assert m0 == m1 == 2.0
+
+
+def _shard_worker(rank, world, port, out_dir, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from kokoro_ruslan_b200 import checkpoint as ck
+    from kokoro_ruslan_b200.parallel import broadcast_parameters, init_distributed
+    init_distributed("gloo")
+    flat = torch.arange(4096, dtype=torch.float32) * (rank + 1)      # different before the broadcast, identical after
+    broadcast_parameters(flat, src=0)
+    payload = {"epoch": 1, "model_state_dict": {f"p{i}": flat[i * 512:(i + 1) * 512].clone() for i in range(8)},
+               "optimizer_state_dict": {"state": {0: {"exp_avg": flat[:100] * 0.5}}, "param_groups": [{"lr": 1e-4}]}}
+    writer = ck.AsyncCheckpointWriter()                              # the async writer path, one writer per rank
+    path = os.path.join(out_dir, "checkpoint_epoch_2.pth")
+    files = ck.save_sharded(path, payload, rank, world, writer)
+    writer.wait()
+    dist.barrier()                                                    # every shard is on disk
+    merged = ck.load_sharded(path)
+    ok = all(torch.equal(merged["model_state_dict"][f"p{i}"], torch.arange(4096, dtype=torch.float32)[i * 512:(i + 1) * 512])
+             for i in range(8)) and torch.equal(merged["optimizer_state_dict"]["state"][0]["exp_avg"],
+                                                torch.arange(100, dtype=torch.float32) * 0.5)
+    q.put((rank, [os.path.basename(f) for f in files], ok, merged["epoch"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_checkpoint(tmp_path):
+    """Sharded checkpoints with two gloo ranks: each rank writes its share of the replicated state
+    through its own asynchronous writer, rank 0 adds the head file, and both ranks read the same merged payload back."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == ["checkpoint_epoch_2.pth.shard0of2", "checkpoint_epoch_2.pth"]
+    assert res[1][1] == ["checkpoint_epoch_2.pth.shard1of2"]
+    assert all(r[2] and r[3] == 1 for r in res)
+    sizes = [os.path.getsize(os.path.join(str(tmp_path), f"checkpoint_epoch_2.pth.shard{r}of2")) for r in range(2)]
+    assert abs(sizes[0] - sizes[1]) < 4096                             # balanced shares
