@@ -324,3 +324,58 @@ def load_sharded(path: str, map_location="cpu") -> Dict:
             return type(obj)(fill(v, prefix + (i,)) for i, v in enumerate(obj))
         return obj
     return fill(head["skeleton"], ())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Legacy checkpoints: the reference's strict-resume rules (training/checkpoint_manager.py:360-525) restated on state dicts.
+# ----------------------------------------------------------------------------------------------------------------------
+_NEW_VARIANCE_PREFIX = "duration_adaptor.variance_adaptor."       # sub-modules added in a later architecture revision
+_FFN_OUTPUT_NORM_SUFFIX = ".ff.output_norm.weight"                # enabled on a checkpoint trained without it
+_ALIBI_SUFFIX = ".alibi_slopes"                                   # buffers of the ALiBi decoder, gone with RoPE
+
+
+def extract_model_state_dict(ck) -> Dict[str, torch.Tensor]:
+    """`model_state_dict`, else `model`, else a raw state dict (checkpoint_manager.py:398-410)."""
+    if not isinstance(ck, dict):
+        raise RuntimeError("Checkpoint payload is not a dictionary.")
+    if "model_state_dict" in ck:
+        return ck["model_state_dict"]
+    if "model" in ck:
+        return ck["model"]
+    if ck and all(isinstance(v, torch.Tensor) for v in ck.values()):
+        return ck
+    raise RuntimeError("Checkpoint does not contain a recognized model state dictionary. "
+                       "Expected key 'model_state_dict' or 'model'.")
+
+
+def migrate_model_state_dict(saved: Dict[str, torch.Tensor], current: Dict[str, torch.Tensor],
+                             log: Callable[[str], None] = lambda s: None) -> Dict[str, torch.Tensor]:
+    """The state dict to load strictly into the current model, after the reference's known migrations
+    (checkpoint_manager.py:412-489): keys missing from `saved` are tolerated only under
+    `duration_adaptor.variance_adaptor.` or as `*.ff.output_norm.weight` — they keep the current (freshly initialised)
+    values; keys `saved` has in excess are tolerated only as `*.alibi_slopes` and are discarded.  Anything else, or a shape
+    mismatch, is the reference's "architecture/state mismatch" error."""
+    missing = [k for k in current if k not in saved]
+    unexpected = [k for k in saved if k not in current]
+    shapes = [k for k in current if k in saved and tuple(saved[k].shape) != tuple(current[k].shape)]
+    ok_missing = all(k.startswith(_NEW_VARIANCE_PREFIX) or k.endswith(_FFN_OUTPUT_NORM_SUFFIX) for k in missing)
+    ok_unexpected = all(k.endswith(_ALIBI_SUFFIX) for k in unexpected)
+    if shapes or not (ok_missing and ok_unexpected):
+        raise RuntimeError("Strict checkpoint model load failed due to architecture/state mismatch. "
+                           f"Missing: {[k for k in missing if not (k.startswith(_NEW_VARIANCE_PREFIX) or k.endswith(_FFN_OUTPUT_NORM_SUFFIX))]}, "
+                           f"unexpected: {[k for k in unexpected if not k.endswith(_ALIBI_SUFFIX)]}, shape mismatches: {shapes}")
+    if missing:
+        log(f"Checkpoint is missing {len(missing)} key(s) from expected architecture migrations (variance_adaptor / "
+            "ffn_output_norm). Loading shared weights and initialising missing keys from scratch.")
+    if unexpected:
+        log(f"Checkpoint contains {len(unexpected)} legacy ALiBi positional encoding buffer(s) (alibi_slopes) that are not "
+            "used by the current RoPE-based model.  These will be discarded.")
+    return {k: (saved[k] if k in saved else current[k].detach().clone()) for k in current}
+
+
+def check_resume_fields(ck: Dict, training: bool = True) -> None:
+    """Fields a training resume needs (checkpoint_manager.py:491-511): optimizer + scheduler state, epoch, loss."""
+    if training and ("optimizer_state_dict" not in ck or "scheduler_state_dict" not in ck):
+        raise RuntimeError("Checkpoint is missing optimizer/scheduler state required for training resume.")
+    if "epoch" not in ck or "loss" not in ck:
+        raise RuntimeError("Checkpoint is missing required 'epoch' or 'loss' fields.")

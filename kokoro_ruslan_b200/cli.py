@@ -296,12 +296,16 @@ def resume(cfg: RunConfig, step, log: Callable[[str], None] = print) -> int:
         bad = check_model_metadata(ck.get("model_metadata"), model_cfg)
         if bad:
             raise RuntimeError(f"checkpoint {path} was written for a different architecture: " + "; ".join(bad))
-    step.load_state_dict(ck["model_state_dict"])
+    from .checkpoint import check_resume_fields, extract_model_state_dict, migrate_model_state_dict
+    check_resume_fields(ck, training=hasattr(step, "opt"))
+    # the reference's known migrations (checkpoint_manager.py:412-489): later-added variance-adaptor / ffn output-norm
+    # weights keep their initial values, legacy ALiBi buffers are dropped; anything else is an architecture mismatch
+    step.load_state_dict(migrate_model_state_dict(extract_model_state_dict(ck), step.state_dict(), log))
     ema = ck.get("ema_model_state_dict")
     st = step.store
     if ema is not None and getattr(st, "ema", None) is not None:
         live = st.params.clone()
-        step.load_state_dict(ema)                 # route the EMA tensors through the same layout conversion ...
+        step.load_state_dict(migrate_model_state_dict(ema, step.state_dict()))   # same layout conversion + migrations ...
         st.ema.copy_(st.params)
         st.params.copy_(live)                     # ... then restore the live weights and their bf16 shadow
         st.refresh_shadow()

@@ -146,7 +146,7 @@ def test_resume_auto_picks_the_latest_checkpoint_and_continues(tmp_path):
     from kokoro_ruslan_b200 import cli
     for n in (1, 3, 12):
         torch.save({"epoch": n - 1, "model_state_dict": {"w": torch.full((2,), float(n))}, "ema_model_state_dict": None,
-                    "scheduler_state_dict": {"k": n}}, os.path.join(str(tmp_path), f"checkpoint_epoch_{n}.pth"))
+                    "scheduler_state_dict": {"k": n}, "loss": 1.0 / n}, os.path.join(str(tmp_path), f"checkpoint_epoch_{n}.pth"))
     assert cli.find_latest_checkpoint(str(tmp_path)).endswith("checkpoint_epoch_12.pth")
     assert cli.find_latest_checkpoint(str(tmp_path / "missing")) is None
     step = _StubStep([1.0])
@@ -408,3 +408,41 @@ def test_cached_corpus_trains_through_the_prefetcher(tmp_path, monkeypatch):
     empty.mkdir()
     with pytest.raises(RuntimeError):
         cli.load_reference_dataset(cli.RunConfig(data_dir=str(empty), output_dir=str(tmp_path)))
+
+
+def test_legacy_checkpoint_migrations_follow_the_reference_rules():
+    """checkpoint.migrate_model_state_dict / extract_model_state_dict / check_resume_fields restate the reference's
+    strict-resume rules (training/checkpoint_manager.py:360-525): only variance-adaptor and ffn output-norm keys may be
+    missing (they keep their initial values), only ALiBi buffers may be in excess (dropped); `model` and raw state dicts are
+    accepted as the model entry; optimizer / scheduler / epoch / loss are required for a training resume."""
+    from kokoro_ruslan_b200 import checkpoint as ck
+    cur = {"encoder.w": torch.zeros(3), "duration_adaptor.variance_adaptor.pitch_embedding.weight": torch.ones(4),
+           "decoder.layers.0.ff.output_norm.weight": torch.ones(2), "decoder.layers.0.ff.linear1.weight": torch.zeros(2, 2)}
+    legacy = {"encoder.w": torch.full((3,), 5.0), "decoder.layers.0.ff.linear1.weight": torch.full((2, 2), 7.0),
+              "decoder.layers.0.self_attn.alibi_slopes": torch.arange(8.0)}
+    logs = []
+    out = ck.migrate_model_state_dict(legacy, cur, logs.append)
+    assert list(out) == list(cur) and torch.equal(out["encoder.w"], legacy["encoder.w"])
+    assert torch.equal(out["duration_adaptor.variance_adaptor.pitch_embedding.weight"], torch.ones(4))
+    assert torch.equal(out["decoder.layers.0.ff.output_norm.weight"], torch.ones(2))
+    assert len(logs) == 2 and "alibi_slopes" in logs[1] and "missing 2 key(s)" in logs[0]
+    assert ck.migrate_model_state_dict(dict(cur), cur) .keys() == cur.keys()
+    for bad in (dict(legacy, **{"something.else": torch.zeros(1)}),                 # unexpected non-ALiBi key
+                {k: v for k, v in legacy.items() if k != "encoder.w"},              # a missing key outside the migrations
+                dict(legacy, **{"encoder.w": torch.zeros(4)})):                     # shape mismatch
+        with pytest.raises(RuntimeError, match="architecture/state mismatch"):
+            ck.migrate_model_state_dict(bad, cur)
+    assert ck.extract_model_state_dict({"model_state_dict": legacy}) is legacy
+    assert ck.extract_model_state_dict({"model": legacy}) is legacy
+    assert ck.extract_model_state_dict(legacy) is legacy                              # raw state dict
+    with pytest.raises(RuntimeError, match="recognized model state"):
+        ck.extract_model_state_dict({"epoch": 3, "weights": legacy})
+    with pytest.raises(RuntimeError, match="not a dictionary"):
+        ck.extract_model_state_dict([1, 2])
+    full = {"optimizer_state_dict": {}, "scheduler_state_dict": {}, "epoch": 1, "loss": 0.5}
+    ck.check_resume_fields(full)
+    with pytest.raises(RuntimeError, match="optimizer/scheduler"):
+        ck.check_resume_fields({"epoch": 1, "loss": 0.5})
+    with pytest.raises(RuntimeError, match="'epoch' or 'loss'"):
+        ck.check_resume_fields({"optimizer_state_dict": {}, "scheduler_state_dict": {}, "epoch": 1})
+    ck.check_resume_fields({"epoch": 1, "loss": 0.5}, training=False)
