@@ -219,18 +219,44 @@ __global__ void adapt_bwd_kernel(const float* __restrict__ dmem, const int* __re
 // ---------------------------------------------------------------------------------------------
 // GroupNorm(1) + ReLU on the padded layout
 // ---------------------------------------------------------------------------------------------
+// Group sums are accumulated per WARP over a contiguous run of rows and flushed (two double atomics) only when the group
+// changes or the run ends: a group is one (utterance, 512-frame chunk), i.e. hundreds of consecutive rows, and one atomic
+// pair per ROW onto the ~16 group addresses serialised in the L2 (12 us for 6400 rows, 26 us in the backward pass).
+struct GroupRun {
+  int g = -1;
+  double s = 0.0, q = 0.0;
+  __device__ __forceinline__ void add(int gr, float a, float b, double* out, int lane) {
+    if (gr != g) { flush(out, lane); g = gr; }
+    s += (double)a; q += (double)b;
+  }
+  __device__ __forceinline__ void flush(double* out, int lane) {
+    if (g >= 0 && lane == 0) { atomicAdd(out + 2 * g, s); atomicAdd(out + 2 * g + 1, q); }
+    s = 0.0; q = 0.0;
+  }
+};
+// contiguous rows [r0, r1) of warp `gw` out of `nw` warps
+__device__ __forceinline__ void warp_row_range(int R, int gw, int nw, int& r0, int& r1) {
+  const int per = (R + nw - 1) / nw;
+  r0 = min(R, gw * per);
+  r1 = min(R, r0 + per);
+}
+
 __global__ void gn_stats_kernel(const float* __restrict__ x, const int* __restrict__ row_group,
                                 double* __restrict__ stats, int R, int C) {
   kr::pdl_entry();
   const int lane = threadIdx.x & 31;
-  for (int r = blockIdx.x * WARPS + (threadIdx.x >> 5); r < R; r += gridDim.x * WARPS) {
+  int r0, r1;
+  warp_row_range(R, blockIdx.x * WARPS + (threadIdx.x >> 5), gridDim.x * WARPS, r0, r1);
+  GroupRun run;
+  for (int r = r0; r < r1; ++r) {
     const int g = row_group[r];
     if (g < 0) continue;
     float s = 0.f, q = 0.f;
     for (int c = lane; c < C; c += 32) { const float v = x[(long long)r * C + c]; s += v; q += v * v; }
     s = warp_sum(s); q = warp_sum(q);
-    if (lane == 0) { atomicAdd(stats + 2 * g, (double)s); atomicAdd(stats + 2 * g + 1, (double)q); }
+    run.add(g, s, q, stats, lane);
   }
+  run.flush(stats, lane);
 }
 
 __device__ __forceinline__ void gn_mean_rstd(const double* stats, const int* group_rows, int g, int C,
@@ -279,11 +305,15 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const float* __
   float ag[8], ab[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
-  for (int r = blockIdx.x * WARPS + warp; r < R; r += gridDim.x * WARPS) {
+  int r0, r1;
+  warp_row_range(R, blockIdx.x * WARPS + warp, gridDim.x * WARPS, r0, r1);
+  GroupRun run;
+  int g_cached = -1;
+  float mean = 0.f, rstd = 0.f;
+  for (int r = r0; r < r1; ++r) {
     const int g = row_group[r];
     if (g < 0) continue;
-    float mean, rstd;
-    gn_mean_rstd(stats, group_rows, g, C, mean, rstd);
+    if (g != g_cached) { gn_mean_rstd(stats, group_rows, g, C, mean, rstd); g_cached = g; }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -298,8 +328,9 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const float* __
       }
     }
     s1 = warp_sum(s1); s2 = warp_sum(s2);
-    if (lane == 0) { atomicAdd(gsum + 2 * g, (double)s1); atomicAdd(gsum + 2 * g + 1, (double)s2); }
+    run.add(g, s1, s2, gsum, lane);
   }
+  run.flush(gsum, lane);
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sm[0][warp][lane + 32 * i] = ag[i]; sm[1][warp][lane + 32 * i] = ab[i]; }
   __syncthreads();
@@ -517,7 +548,7 @@ extern "C" int kr_gn_fwd(const float* x, const int* row_group, const int* group_
   if (C > 256 || (C % 32)) { kr_set_error("kr_gn: C must be a multiple of 32, <= 256"); return KR_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * G, st) != cudaSuccess) { kr_set_error("memset failed"); return KR_ERR_CUDA; }
-  kr::launch(gn_stats_kernel, warp_blocks(R), WARPS * 32, 0, st, x, row_group, stats, R, C);
+  kr::launch(gn_stats_kernel, warp_blocks(R, 2), WARPS * 32, 0, st, x, row_group, stats, R, C);
   KR_CHECK_LAUNCH();
   kr::launch(gn_apply_relu_kernel, warp_blocks(R), WARPS * 32, 0, st, x, row_group, stats, group_rows, gamma, beta, (bf16*)out_bf16, R, C,
              kr_drop_to_device(drop));
