@@ -528,6 +528,22 @@ def run_ours(args):
     # ---- the kernels beside the step (features, decode): isolated subprocesses, after everything above ------
     if roof is not None:
         roof["top_ops"] = top_ops
+        roof["top_ops_note"] = ("event pairs around each C-ABI call in an EAGER multi-stream pass: a row's ms is the op's duration in "
+                                "situ, i.e. it includes the slow-down from kernels running concurrently on the side streams "
+                                "(weight gradients, encoder, predictors) and ~3 us of event overhead per launch; the rows therefore "
+                                "sum to far more than the graph-replayed step.  An op family's marginal cost ON the step's critical "
+                                "path is in marginal_in_step_ms")
+        try:   # tools/ablate_step.py: step time with one family's entry points turned into no-ops (committed capture)
+            marg = {}
+            with open(os.path.join(ROOT, "profiles", "r02_step_ablation.txt")) as f:
+                for line in f:
+                    parts = line.split()
+                    if len(parts) >= 5 and parts[0].startswith("kr_") and parts[2] == "ms":
+                        marg[parts[0]] = float(parts[4])
+            roof["marginal_in_step_ms"] = {"source": "profiles/r02_step_ablation.txt (tools/ablate_step.py on a B200, bench shape, "
+                                                     "graph replay; step(all) - step(without the family))", **marg}
+        except Exception:
+            pass
         roof["hifigan"] = hifi
         if world == 1 and not args.no_extras:
             try:
