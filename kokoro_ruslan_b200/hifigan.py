@@ -341,7 +341,9 @@ class HiFiGANGenerator:
             for name in ("h_act", "ya_act", "yb_act", "t_act", "x_act"):
                 b[f"{name}{i}"] = z(B, L + 2 * HALO, cp)
             # residual stream in fp32: bf16 here is the dominant error term (measured 1.0-1.3e-2 on the
-            # audio vs 0.75e-2 with fp32), the conv operands (the *_act tensors) stay bf16
+            # audio vs 0.75e-2 with fp32), the conv operands (the *_act tensors) stay bf16.  Re-measured at the end of
+            # round 2 per stage (2 x 800 frames, gate 1e-2): fp32 everywhere 0.91e-2; bf16 in the 256-channel stage only
+            # 0.94e-2; in the 256- and 128-channel stages 1.07e-2 — and neither was faster (13.7 / 15.4 vs 13.3 ms)
             for name in ("h_raw", "ya_raw", "yb_raw"):
                 b[f"{name}{i}"] = z(B, L + 2 * HALO, cp, dt=F32)
             b[f"xs{i}"] = z(B, L, c0 // 2 ** (i + 1), dt=F32)
