@@ -458,6 +458,23 @@ __global__ void conv_dgrad_shadow_kernel(const float* __restrict__ w2, bf16* __r
   }
 }
 
+// the same for up to 8 convs of one shape in ONE launch (blockIdx.y = conv): the optimizer step refreshes the four dgrad
+// shadows of the variance predictors at its very end, where four dependent ~10 us launches were 40 us of the step
+struct ShadowBatch { const float* w2[8]; bf16* wd[8]; };
+__global__ void conv_dgrad_shadow_multi_kernel(const ShadowBatch b, int Co, int Ci) {
+  kr::pdl_entry();
+  const float* __restrict__ w2 = b.w2[blockIdx.y];
+  bf16* __restrict__ wd = b.wd[blockIdx.y];
+  const long long total = (long long)Ci * 3 * Co;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % Co);
+    const int j = (int)((i / Co) % 3);
+    const int c = (int)(i / (3LL * Co));
+    wd[i] = __float2bfloat16(w2[((long long)o * 3 + (2 - j)) * Ci + c]);
+  }
+}
+
 inline int warp_blocks(long long rows, int cap_mult = 8) {
   long long b = (rows + WARPS - 1) / WARPS;
   const long long cap = (long long)kNumSMs * cap_mult;
@@ -596,6 +613,19 @@ extern "C" int kr_conv_dgrad_shadow(const float* w2, void* wd, int Co, int Ci, v
   const long long total = (long long)Ci * 3 * Co;
   long long b = (total + 255) / 256;
   kr::launch(conv_dgrad_shadow_kernel, (int)(b < 1184 ? b : 1184), 256, 0, (cudaStream_t)stream, w2, (bf16*)wd, Co, Ci);
+  KR_CHECK_LAUNCH();
+  return KR_OK;
+}
+
+extern "C" int kr_conv_dgrad_shadow_multi(const float* const* w2, void* const* wd, int n, int Co, int Ci, void* stream) {
+  if (n <= 0) return KR_OK;
+  if (n > 8) { kr_set_error("kr_conv_dgrad_shadow_multi: at most 8 convs per launch"); return KR_ERR_ARG; }
+  ShadowBatch b{};
+  for (int i = 0; i < n; ++i) { b.w2[i] = w2[i]; b.wd[i] = reinterpret_cast<bf16*>(wd[i]); }
+  const long long total = (long long)Ci * 3 * Co;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 296) blocks = 296;
+  kr::launch(conv_dgrad_shadow_multi_kernel, dim3((unsigned)blocks, (unsigned)n), 256, 0, (cudaStream_t)stream, b, Co, Ci);
   KR_CHECK_LAUNCH();
   return KR_OK;
 }

@@ -516,6 +516,14 @@ def conv_dgrad_shadow(w2, wd, Co: int, Ci: int):
     check(lib().kr_conv_dgrad_shadow(_ptr(w2), _ptr(wd), c_int(Co), c_int(Ci), _stream()), "kr_conv_dgrad_shadow")
 
 
+def conv_dgrad_shadow_multi(pairs, Co: int, Ci: int):
+    """pairs: up to 8 (master conv weight fp32, dgrad shadow bf16) tensors of one (Co, Ci) shape, refreshed in one launch."""
+    n = len(pairs)
+    w2 = (c_void_p * n)(*[p[0].data_ptr() for p in pairs])
+    wd = (c_void_p * n)(*[p[1].data_ptr() for p in pairs])
+    check(lib().kr_conv_dgrad_shadow_multi(w2, wd, c_int(n), c_int(Co), c_int(Ci), _stream()), "kr_conv_dgrad_shadow_multi")
+
+
 def stop_head_fwd(x, w, b, z):
     N, D = x.shape
     check(lib().kr_stop_head_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(z), c_int(N), c_int(D), _stream()),

@@ -226,11 +226,25 @@ class FusedAdamW:
                               _ptr(self.g_wd), _ptr(self.t_wnmax), _ptr(self.wsq), _ptr(self.ctrl),
                               c_float(c.adam_betas[0]), c_float(c.adam_betas[1]), c_float(c.adam_eps),
                               c_float(c.ema_decay), _stream()), "kr_adamw_step")
+        # the step's tail: the weight-norm projection (FFN matrices) and the dgrad shadows of the predictor convs read
+        # disjoint weights and both depend on the AdamW kernel only -> side by side (they were 65 serial us)
+        side = None
+        if self.n_wn_chunks and s.params.is_cuda:
+            import torch
+            if getattr(self, "_tail_stream", None) is None:
+                self._tail_stream = torch.cuda.Stream(device=s.params.device)
+            side, cur = self._tail_stream, torch.cuda.current_stream(s.params.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                s.refresh_conv_dgrad()
         if self.n_wn_chunks:
             check(L.kr_wn_project(_ptr(s.params), _ptr(s.shadow), _ptr(self.wn_chunks), c_int(self.n_wn_chunks),
                                   _ptr(self.chunk_tensor), _ptr(self.chunk_start), _ptr(self.chunk_len),
                                   _ptr(self.t_wnmax), _ptr(self.wsq), _ptr(self.ctrl), _stream()), "kr_wn_project")
-        s.refresh_conv_dgrad()
+        if side is not None:
+            cur.wait_stream(side)
+        else:
+            s.refresh_conv_dgrad()
 
     def write_detector_state(self, ema_norm: float, ema_steps: int) -> None:
         """Restores the explosion detector's norm EMA (checkpoint resume)."""

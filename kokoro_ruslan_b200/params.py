@@ -252,10 +252,15 @@ class ParamStore:
         self.refresh_conv_dgrad()
 
     def refresh_conv_dgrad(self) -> None:
+        """bf16 dgrad layouts of the variance predictors' conv weights: one launch per (Co, Ci) shape."""
         from . import ops
+        by_shape: Dict[Tuple[int, int], list] = {}
         for name, wd in self.conv_dgrad.items():
             co, ci, _ = self.entries[name].shape
-            ops.conv_dgrad_shadow(self.p(name), wd, co, ci)
+            by_shape.setdefault((co, ci), []).append((self.p(name), wd))
+        for (co, ci), pairs in by_shape.items():
+            for k in range(0, len(pairs), 8):
+                ops.conv_dgrad_shadow_multi(pairs[k:k + 8], co, ci)
 
     # ----- default initialisation (reference nn.Module defaults + explicit inits) ---------------
     def init_default(self, seed: int = 0) -> None:

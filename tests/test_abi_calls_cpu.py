@@ -59,7 +59,8 @@ def check_calls(calls):
         for i, (a, p) in enumerate(zip(args, params)):
             want = expected_ctype(p)
             if want == "pointer":
-                ok = a is None or isinstance(a, ctypes.c_void_p) or type(a).__name__ == "CArgObject"
+                ok = (a is None or isinstance(a, ctypes.c_void_p) or type(a).__name__ == "CArgObject"
+                      or isinstance(a, ctypes.Array))          # host arrays (pointer tables, block lists)
             else:
                 ok = isinstance(a, want)
             assert ok, f"{name}: argument {i} ({p!r}) got {type(a).__name__}"

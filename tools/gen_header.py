@@ -86,6 +86,7 @@ DOCS = {
     "kr_chunk_sqnorm": "Per-chunk squared sums of the flat gradient buffer (single-GPU first optimizer phase; deterministic, no atomics).",
     "kr_chunk_to_tensor_sq": "sq[t] = sum over the chunks of tensor t in chunk order (first_chunk[n_tensors + 1]); raises the control block's non-finite flag (training/trainer.py:1308-1313).",
     "kr_conv_dgrad_shadow": "bf16 tap-reversed transpose of a tap-major conv weight: the B operand of the conv data-gradient GEMM.",
+    "kr_conv_dgrad_shadow_multi": "kr_conv_dgrad_shadow for n <= 8 convs of one (Co, Ci) shape in one launch: w2 / wd are HOST arrays of n device pointers.",
 }
 
 STRUCTS = """/* Dropout / stochastic-depth descriptor of ONE site (HOST struct, passed by pointer; NULL or
