@@ -133,7 +133,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* v_full = k_full + FWD_STAGES;               // [FWD_STAGES] (tx)
   uint64_t* kv_empty = v_full + FWD_STAGES;             // [FWD_STAGES] commit: every MMA reading the stage is done
   uint64_t* s_full = kv_empty + FWD_STAGES;             // [2] commit: S_w(j) (and with it PV_w(j-1)) complete
-  uint64_t* p_ready = s_full + 2;                       // [2] 128 arrivals: P_w(j) (and a rescaled O_w) are in TMEM
+  uint64_t* p_ready = s_full + 2;                       // [2] one arrival per warp of the warpgroup: P_w(j) (and a rescaled O_w) are in TMEM
   uint64_t* o_final = p_ready + 2;                      // [2] commit: the last PV_w is complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
   uint32_t* mask_words = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [n_ktiles][4]
@@ -157,7 +157,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_bar, 1);
     for (int i = 0; i < FWD_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(&s_full[w], 1); mbar_init(&p_ready[w], 128); mbar_init(&o_final[w], 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(&s_full[w], 1); mbar_init(&p_ready[w], 4); mbar_init(&o_final[w], 1); }
     fence_barrier_init();
   }
   if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -352,7 +352,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_st_wait();
       }
       tc_fence_before();
-      mbar_arrive(&p_ready[w]);
+      __syncwarp();                                  // one elected arrival per warp (128 arrivals on one mbarrier word serialise)
+      if (lane == 0) mbar_arrive(&p_ready[w]);
     }
     if (nt > 0) {
       mbar_wait(&o_final[w], 0);
@@ -464,7 +465,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* s_bar = bars + 3;     // S(it) complete: the exp2 half of the softmax starts while dP is still in the tensor pipe
   uint64_t* dp_bar = bars + 4;    // dP(it) complete
   uint64_t* out_bar = bars + 5;
-  uint64_t* soft_bar = bars + 6;  // [2] one per half (128 threads each)
+  uint64_t* soft_bar = bars + 6;  // [2] one per half: one arrival per warp (4 each)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   uint32_t* mask_words = tmem_slot + 2;
 
@@ -487,7 +488,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     mbar_init(kv_bar, 1); mbar_init(&qdo_bar[0], 1); mbar_init(&qdo_bar[1], 1);
     mbar_init(s_bar, 1); mbar_init(dp_bar, 1); mbar_init(out_bar, 1);
-    mbar_init(&soft_bar[0], 128); mbar_init(&soft_bar[1], 128);
+    mbar_init(&soft_bar[0], 4); mbar_init(&soft_bar[1], 4);
     fence_barrier_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -717,7 +718,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&soft_bar[ch]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&soft_bar[ch]);
     }
     mbar_wait(out_bar, (n_it - 1) & 1);
     tc_fence_after();
