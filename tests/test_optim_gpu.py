@@ -133,3 +133,22 @@ def test_fused_step_matches_the_live_reference_trainer(case):
                 assert float(flat.double().norm()) == pytest.approx(float(fix[key + "_norms"][step][i]), rel=2e-4, abs=1e-6)
                 assert torch.allclose(got, osrc[n].detach(), rtol=2e-4, atol=2e-6), (step, n, key)
     assert opt.read_ctrl()["step"] == len(spec["gscale"]) - sum(1 for x in spec["special"] if x)
+
+
+def test_batched_conv_dgrad_shadows_equal_the_single_launches():
+    """kr_conv_dgrad_shadow_multi (the optimizer step's tail) writes exactly what one kr_conv_dgrad_shadow launch per conv
+    writes: Wd[c, j*Co + o] = W[o, 2 - j, c] in bf16."""
+    from kokoro_ruslan_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    Co, Ci = 256, 256
+    ws = [torch.randn(Co, 3, Ci, generator=g).cuda() for _ in range(4)]
+    single = [torch.zeros(Ci, 3 * Co, dtype=torch.bfloat16, device="cuda") for _ in ws]
+    multi = [torch.zeros(Ci, 3 * Co, dtype=torch.bfloat16, device="cuda") for _ in ws]
+    for w, wd in zip(ws, single):
+        ops.conv_dgrad_shadow(w, wd, Co, Ci)
+    ops.conv_dgrad_shadow_multi(list(zip(ws, multi)), Co, Ci)
+    torch.cuda.synchronize()
+    for w, a, b in zip(ws, single, multi):
+        assert torch.equal(a, b)
+        want = w.flip(1).permute(2, 1, 0).reshape(Ci, 3 * Co).to(torch.bfloat16)
+        assert torch.equal(b, want)
