@@ -268,3 +268,39 @@ def test_bench_shape_gradients_against_the_reference_autocast_noise_floor():
     assert p90_o <= max(6e-2, 1.25 * p90_r), (p90_o, p90_r)
     assert ours[0][0] <= max(0.15, 1.25 * refn[0][0]), ours[:5]
     assert min(r[1] for r in ours) > 0.99, sorted(ours, key=lambda r: r[1])[:5]
+
+
+def test_hifigan_config5_16x800_against_the_live_reference_generator():
+    """Config 5 at its full size — 16 mels x 800 frames -> 16 x 204800 samples — against the UNMODIFIED reference
+    HiFiGANGenerator (baseline/_ref, weight-normed modules, PyTorch fp32 on the same GPU) loaded with the same state dict."""
+    if not os.path.isdir(os.path.join(REF, "kokoro")):
+        pytest.skip("baseline/_ref (the installed reference) is not present")
+    from kokoro_ruslan_b200.hifigan import HiFiGANConfig, HiFiGANGenerator
+    from oracle import hifigan as oh
+    from oracle.ref_trainer import _import_reference
+    _import_reference()
+    from kokoro.inference.hifigan_vocoder import HiFiGANConfig as RefConfig, HiFiGANGenerator as RefGenerator
+    sd = oh.seeded_state_dict(oh.HifiConfig(), seed=0)
+    ref = RefGenerator(RefConfig.get_default_config())
+    ref.load_state_dict(sd, strict=True)
+    ref = ref.cuda().eval()
+    gen = HiFiGANGenerator(HiFiGANConfig.get_default_config())
+    gen.load_state_dict(sd)
+    mel = oh.synthetic_mel(16, 800, 9).cuda()
+    with torch.no_grad():
+        prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False      # a true fp32 reference
+        try:
+            want = ref(mel).float()
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ref_bf16 = ref(mel).float()                     # the reference's own mixed-precision run, for scale
+    got = gen(mel).float()
+    assert got.shape == want.shape == (16, 1, 204800)
+    err = _rel(got, want)
+    _record(f"hifigan config 5: the reference generator under bf16 autocast vs its fp32 run: {_rel(ref_bf16, want):.3e}")
+    per_item = [float((got[b] - want[b]).abs().max() / (want[b].abs().max() + 1e-12)) for b in range(16)]
+    _record(f"hifigan config 5 (16x800 frames) vs the live reference generator in fp32 on the GPU: max|a-b|/max|b| = {err:.3e} "
+            f"(per utterance {min(per_item):.3e} .. {max(per_item):.3e}; gate 1e-2)")
+    assert err < 1e-2, err
