@@ -30,7 +30,9 @@
 // Issue order  G1(0), G1(1), G2(0), G1(2), G2(1), ...: while one slot converts its t tile or writes its outputs, the tensor
 // pipe works for the other slot.  Weights that only fit next to ONE slot (k = 11 on 64 channels: 176 KB) run in one-slot mode:
 // the same issue order with a single slab, t tile and acc2 and four epilogue warps — acc1 stays double-buffered, so GEMM1 of
-// the next tile runs under the epilogues of the current one.
+// the next tile runs under the epilogues of the current one.  (Measured and dropped for that mode: a second MMA-issuing warp
+// for GEMM2 — 568 vs 510 us per k = 11 step, and 290 vs 266 us on the two-slot k = 3 steps; converting the t tile with both
+// warp sets — the second set has to wait for epilogue 2 of the previous tile, which stages in the t tile: 490 us.)
 // Channels-last activations [B, L + 2*halo, 64] with zero halos (halo >= h2 + conv1's reach); weights [64, n * 32] bf16.
 #include "kr_common.cuh"
 #include "kokoro_b200.h"
