@@ -10,11 +10,31 @@
 namespace {
 using namespace kr;
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// GELU (erf form, the reference's nn.GELU() default) and its derivative for the GLU kernels, which are bound by
+// instruction issue, not by memory (6400 x 1536 gates, operands in L2: erff alone is ~40 issue slots per element with both
+// of its branches predicated): Abramowitz-Stegun 7.1.26, erf(u) = 1 - (a1 t + ... + a5 t^5) exp(-u^2), t = 1 / (1 + p u),
+// |error| < 5e-7 in fp32 — three decimal orders below the bf16 resolution of the gated product — with ONE exponential shared
+// by the CDF and the PDF (exp(-u^2) = exp(-x^2 / 2)).
+struct GeluParts { float cdf, e; };      // cdf = Phi(x), e = exp(-x^2 / 2)
+__device__ __forceinline__ GeluParts gelu_parts(float x) {
+  const float u = fabsf(x) * 0.70710678118654752f;
+  float t;                                                          // 1 / (1 + p u): one MUFU.RCP (>= 22 good bits)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.f)));
+  const float e = __expf(-u * u);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.f);                 // erf(|x| / sqrt 2)
+  GeluParts r;
+  r.cdf = 0.5f * (1.f + copysignf(erf_abs, x));
+  r.e = e;
+  return r;
+}
+__device__ __forceinline__ float gelu_erf(float x) { return x * gelu_parts(x).cdf; }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const GeluParts g = gelu_parts(x);
+  return fmaf(x * 0.3989422804014327f, g.e, g.cdf);              // cdf + x * pdf
 }
 
 // dropout factors of the 8 consecutive elements starting at e0 (all 1 when disabled)
@@ -33,12 +53,14 @@ __global__ void glu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ u,
   kr::pdl_entry();
   DropCtx dc{};
   if (d.state != nullptr) dc = drop_ctx(d);
-  // one thread = 8 consecutive output columns
+  // one thread = 8 consecutive output columns; a block walks whole rows (threadIdx.x = the column vector, no per-element
+  // 64-bit division: it was ~5 of the ~50 issue slots per element of this instruction-bound kernel)
   const int vec_per_row = FF / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / vec_per_row;
-    const int c = (int)(i % vec_per_row) * 8;
+  const long long n_rows = n_vec / vec_per_row;
+  if ((int)threadIdx.x >= vec_per_row) return;
+  const int c = (int)threadIdx.x * 8;
+  for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const long long i = row * vec_per_row + threadIdx.x;
     const uint4 g = *reinterpret_cast<const uint4*>(h + row * 2 * FF + c);
     const uint4 l = *reinterpret_cast<const uint4*>(h + row * 2 * FF + FF + c);
     const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, lw[4] = {l.x, l.y, l.z, l.w};
@@ -60,10 +82,11 @@ __global__ void glu_bwd_kernel(const bf16* __restrict__ du, const bf16* __restri
   DropCtx dc{};
   if (drop.state != nullptr) dc = drop_ctx(drop);
   const int vec_per_row = FF / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / vec_per_row;
-    const int c = (int)(i % vec_per_row) * 8;
+  const long long n_rows = n_vec / vec_per_row;
+  if ((int)threadIdx.x >= vec_per_row) return;
+  const int c = (int)threadIdx.x * 8;
+  for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const long long i = row * vec_per_row + threadIdx.x;
     const uint4 g = *reinterpret_cast<const uint4*>(h + row * 2 * FF + c);
     const uint4 l = *reinterpret_cast<const uint4*>(h + row * 2 * FF + FF + c);
     const uint4 d = *reinterpret_cast<const uint4*>(du + row * FF + c);
@@ -76,8 +99,10 @@ __global__ void glu_bwd_kernel(const bf16* __restrict__ du, const bf16* __restri
       const float2 a = unpack_bf16(gw[k]), b = unpack_bf16(lw[k]);
       float2 e = unpack_bf16(dw[k]);
       e.x *= f[2 * k]; e.y *= f[2 * k + 1];
-      og[k] = pack_bf16(e.x * b.x * gelu_erf_grad(a.x), e.y * b.y * gelu_erf_grad(a.y));
-      ol[k] = pack_bf16(e.x * gelu_erf(a.x), e.y * gelu_erf(a.y));
+      const GeluParts px = gelu_parts(a.x), py = gelu_parts(a.y);
+      og[k] = pack_bf16(e.x * b.x * fmaf(a.x * 0.3989422804014327f, px.e, px.cdf),
+                        e.y * b.y * fmaf(a.y * 0.3989422804014327f, py.e, py.cdf));
+      ol[k] = pack_bf16(e.x * a.x * px.cdf, e.y * a.y * py.cdf);
     }
     *reinterpret_cast<uint4*>(dh + row * 2 * FF + c) = make_uint4(og[0], og[1], og[2], og[3]);
     *reinterpret_cast<uint4*>(dh + row * 2 * FF + FF + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
@@ -226,6 +251,10 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __r
   }
 }
 
+// GLU kernels: one block walks rows, threadIdx.x = column vector (FF / 8 of them, rounded up to a warp multiple)
+inline int glu_threads(int FF) { return ((FF / 8) + 31) / 32 * 32; }
+inline int glu_blocks(int N) { const int cap = kNumSMs * 8; return N < cap ? (N > 0 ? N : 1) : cap; }
+
 inline int ew_blocks(long long n, int threads = 256) {
   long long b = (n + threads - 1) / threads;
   const long long cap = (long long)kNumSMs * 16;
@@ -236,9 +265,9 @@ inline int ew_blocks(long long n, int threads = 256) {
 
 extern "C" int kr_glu_fwd(const void* h, void* u, int N, int FF, const kr_drop_spec* drop, void* stream) {
   if (N <= 0) return KR_OK;
-  if (FF % 8) { kr_set_error("kr_glu: FF must be a multiple of 8"); return KR_ERR_ARG; }
+  if (FF % 8 || FF > 8192) { kr_set_error("kr_glu: FF must be a multiple of 8, at most 8192"); return KR_ERR_ARG; }
   const long long n_vec = (long long)N * FF / 8;
-  kr::launch(glu_fwd_kernel, ew_blocks(n_vec), 256, 0, (cudaStream_t)stream, (const bf16*)h, (bf16*)u, n_vec, FF,
+  kr::launch(glu_fwd_kernel, glu_blocks(N), glu_threads(FF), 0, (cudaStream_t)stream, (const bf16*)h, (bf16*)u, n_vec, FF,
              kr_drop_to_device(drop));
   KR_CHECK_LAUNCH();
   return KR_OK;
@@ -246,9 +275,9 @@ extern "C" int kr_glu_fwd(const void* h, void* u, int N, int FF, const kr_drop_s
 extern "C" int kr_glu_bwd(const void* du, const void* h, void* dh, int N, int FF, const kr_drop_spec* drop,
                           void* stream) {
   if (N <= 0) return KR_OK;
-  if (FF % 8) { kr_set_error("kr_glu: FF must be a multiple of 8"); return KR_ERR_ARG; }
+  if (FF % 8 || FF > 8192) { kr_set_error("kr_glu: FF must be a multiple of 8, at most 8192"); return KR_ERR_ARG; }
   const long long n_vec = (long long)N * FF / 8;
-  kr::launch(glu_bwd_kernel, ew_blocks(n_vec), 256, 0, (cudaStream_t)stream, (const bf16*)du, (const bf16*)h, (bf16*)dh, n_vec, FF,
+  kr::launch(glu_bwd_kernel, glu_blocks(N), glu_threads(FF), 0, (cudaStream_t)stream, (const bf16*)du, (const bf16*)h, (bf16*)dh, n_vec, FF,
              kr_drop_to_device(drop));
   KR_CHECK_LAUNCH();
   return KR_OK;

@@ -48,7 +48,23 @@ def main():
     nrm = bf(N, 3 * D)
     t = bench(lambda: ops.qkv_prep_fwd(parts(raw), parts(nrm), g, 0b011, cos, sin, N, S, H))
     print(f"qkv_prep_fwd   3 parts: {t:6.1f} us  {N * 3 * D * 4 / t / 1e3:7.0f} GB/s")
+    FF = 1536
+    hff, u, du, dh = bf(N, 2 * FF), bf(N, FF), bf(N, FF), bf(N, 2 * FF)
+    dspec = ops.make_drop_spec(state, 7, 0.2)
+    for nm, sp in (("no dropout", None), ("dropout 0.2", dspec)):
+        t = bench(lambda: ops.glu_fwd(hff, u, drop=sp))
+        print(f"glu_fwd ({nm}): {t:6.1f} us  {(N * 3 * FF * 2) / t / 1e3:7.0f} GB/s")
+        t = bench(lambda: ops.glu_bwd(du, hff, dh, drop=sp))
+        print(f"glu_bwd ({nm}): {t:6.1f} us  {(N * 5 * FF * 2) / t / 1e3:7.0f} GB/s")
+    hb, mean2, rstd2 = bf(N, D), f32(N), f32(N)
+    t = bench(lambda: ops.layernorm_fwd(x, gam, dbet, hb, None, mean2, rstd2))
+    print(f"layernorm_fwd: {t:6.1f} us  {(N * D * 6) / t / 1e3:7.0f} GB/s")
     y, out = f32(N, D), f32(N, D)
+    t = bench(lambda: ops.rmsnorm_resid_fwd(y, gam, x, out))
+    print(f"rmsnorm_resid_fwd: {t:6.1f} us  {(N * D * 12) / t / 1e3:7.0f} GB/s")
+    cs = torch.zeros(2 * FF, device="cuda")
+    t = bench(lambda: ops.colsum_bf16(dh, cs))
+    print(f"colsum_bf16 [6400 x 3072]: {t:6.1f} us  {(N * 2 * FF * 2) / t / 1e3:7.0f} GB/s")
     dyb = bf(N, D)
     t = bench(lambda: ops.rmsnorm_resid_bwd(dy, y, gam, dyb, dgam))
     print(f"rmsnorm_resid_bwd: {t:6.1f} us  {(2 * N * D * 4 + N * D * 2) / t / 1e3:7.0f} GB/s")
