@@ -292,12 +292,15 @@ __device__ __forceinline__ void store16_bf16(bf16* p, const float* v) {
 // (4 lanes each) = one full 512-wide row when H = 8, i.e. 1 KB coalesced bf16 per warp access.
 struct PrepUnit { int row, col; bool valid; };
 __device__ __forceinline__ PrepUnit prep_unit(const PrepParams& p, long long w, int lane, long long total) {
-  long long u = w * 8 + (lane >> 2);
+  // 32-bit arithmetic (the launchers refuse N * H >= 2^31): two 64-bit divisions per 16 elements were ~a quarter of the
+  // instructions of these issue-bound kernels
+  unsigned u = (unsigned)w * 8u + (unsigned)(lane >> 2);
   PrepUnit r;
-  r.valid = u < total;
-  if (!r.valid) u = total - 1;
-  const int head = (int)(u % p.H);
-  r.row = (int)(u / p.H);
+  r.valid = u < (unsigned)total;
+  if (!r.valid) u = (unsigned)total - 1u;
+  const unsigned row = u / (unsigned)p.H;
+  const int head = (int)(u - row * (unsigned)p.H);
+  r.row = (int)row;
   r.col = head * 64 + (lane & 3) * 16;
   return r;
 }
@@ -506,6 +509,7 @@ extern "C" int kr_qkv_prep_fwd(const void* in0, const void* in1, const void* in2
     p.part[i].ld_in = ld_in; p.part[i].ld_out = ld_out; p.part[i].rope = (rope_mask >> i) & 1;
   }
   p.n_parts = n_parts; p.N = N; p.S = S; p.H = H; p.cos_t = cos_t; p.sin_t = sin_t; p.eps = FLT_EPSILON;
+  if ((long long)N * H >= (1LL << 31) - 8) { kr_set_error("kr_qkv_prep: N * H must stay below 2^31"); return KR_ERR_UNSUPPORTED; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long total = ((long long)N * H + 7) / 8;
   const long long nb_ = (total + WARPS - 1) / WARPS;
@@ -538,6 +542,7 @@ extern "C" int kr_qkv_prep_bwd(const void* in0, const void* in1, const void* in2
     p.part[i].grad_f32 = (grad_f32_mask >> i) & 1;
   }
   p.n_parts = n_parts; p.N = N; p.S = S; p.H = H; p.cos_t = cos_t; p.sin_t = sin_t; p.eps = FLT_EPSILON;
+  if ((long long)N * H >= (1LL << 31) - 8) { kr_set_error("kr_qkv_prep: N * H must stay below 2^31"); return KR_ERR_UNSUPPORTED; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long total = ((long long)N * H + 7) / 8;
   const long long nb_ = (total + WARPS - 1) / WARPS;
