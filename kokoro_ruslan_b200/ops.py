@@ -81,7 +81,7 @@ def _stream() -> c_void_p:
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major: bool = False,
          b_mn_major: bool = False, bias: Optional[torch.Tensor] = None,
          resid: Optional[torch.Tensor] = None, resid_mod: int = 0, alpha: float = 1.0,
-         accumulate: bool = False, splits: int = 1, drop: Optional[DropSpec] = None) -> torch.Tensor:
+         accumulate: bool = False, splits: int = 1, drop: Optional[DropSpec] = None, block_n: int = 0) -> torch.Tensor:
     """out[M,N] (+)= alpha * A @ B^T (+bias) (+resid) on tcgen05 (bf16 in, fp32 accumulate).
 
     A logical [M,K]: stored [M,K] (K-major) or, if a_mn_major, stored [K,M].
@@ -134,6 +134,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major: boo
             g.resid, g.resid_dtype, g.ldr, g.resid_mod = _p(resid), 0, ldr, resid_mod
         g.C, g.c_mode, g.ldc = _p(out), epi, o2.stride(0)
         g.splits = 1
+        g.force_block_n = block_n
         g.drop = ctypes.addressof(drop)
         check(lib().kr_gemm_ex(ctypes.byref(g), _stream()), "kr_gemm_ex")
         return out
