@@ -308,13 +308,19 @@ class AcousticEngine:
 
     def _attn_fwd(self, pre: str, x: torch.Tensor, B: int, S: int, norm: str, causal: bool,
                   key_mask: Optional[torch.Tensor], mem: Optional[torch.Tensor], Sk: int, sv: dict, kv_pre=None,
-                  drop: Optional[dict] = None):
+                  drop: Optional[dict] = None, pre_ln=None, next_ln=None):
+        """pre_ln = (h, mean, rstd): this sub-layer's LayerNorm was already produced by the tail kernel of the sub-layer
+        before it.  next_ln = (norm name, "bf16" | "f32"): the tail of THIS sub-layer (dropout + residual) also produces the
+        LayerNorm that follows — returns (out, (h, mean, rstd)) instead of out."""
         st, D, H = self.store, self.D, self.H
         N = B * S
         cross = mem is not None
-        h = self._empty(N, D, dtype=BF16)
-        mean, rstd = self._empty(N), self._empty(N)
-        ops.layernorm_fwd(x, st.p(norm + "weight"), st.p(norm + "bias"), h, None, mean, rstd)
+        if pre_ln is None:
+            h = self._empty(N, D, dtype=BF16)
+            mean, rstd = self._empty(N), self._empty(N)
+            ops.layernorm_fwd(x, st.p(norm + "weight"), st.p(norm + "bias"), h, None, mean, rstd)
+        else:
+            h, mean, rstd = pre_ln
         gq, gk, gv = st.p(pre + "q_norm.weight"), st.p(pre + "k_norm.weight"), st.p(pre + "v_norm.weight")
         if not cross:
             raw = self._empty(N, 3 * D, dtype=BF16)
@@ -345,9 +351,25 @@ class AcousticEngine:
         drop = drop or {"p": None, "out": None}
         ops.attn_fwd(q, k, v, o.view(B, S, H, 64), lse, key_mask, causal, 1.0 / 8.0, drop=drop["p"])
         out = self._empty(N, D)
-        ops.gemm(o, st.w(pre + "w_o.weight"), out, bias=st.p(pre + "w_o.bias"), resid=x, drop=drop["out"])
+        nxt = None
+        if next_ln is None:
+            ops.gemm(o, st.w(pre + "w_o.weight"), out, bias=st.p(pre + "w_o.bias"), resid=x, drop=drop["out"])
+        else:
+            # plain out-projection (its dropout / residual epilogue costs 8 us of an exposed single-tile epilogue), then ONE
+            # row-wise kernel: dropout + residual + the LayerNorm of the sub-layer that follows
+            yo = self._empty(N, D)
+            ops.gemm(o, st.w(pre + "w_o.weight"), yo, bias=st.p(pre + "w_o.bias"))
+            nxt = self._ln_out(N, next_ln)
+            ops.resid_drop_ln_fwd(yo, x, out, drop["out"], st.p(next_ln[0] + "weight"), st.p(next_ln[0] + "bias"), *nxt)
+            nxt = (nxt[0] if nxt[0] is not None else nxt[1], nxt[2], nxt[3])
         sv.update(x=x, h=h, mean=mean, rstd=rstd, o=o, lse=lse, q=q, k=k, v=v, drop=drop)
-        return out
+        return out if next_ln is None else (out, nxt)
+
+    def _ln_out(self, N: int, next_ln):
+        """(h_bf16 | None, h_f32 | None, mean, rstd) buffers of a fused following LayerNorm."""
+        bf = next_ln[1] == "bf16"
+        return (self._empty(N, self.D, dtype=BF16) if bf else None, None if bf else self._empty(N, self.D),
+                self._empty(N), self._empty(N))
 
     def _attn_bwd(self, pre: str, dout: torch.Tensor, dout_bf: torch.Tensor, B: int, S: int, norm: str,
                   causal: bool, key_mask, mem, Sk: int, sv: dict, dmem: Optional[torch.Tensor],
@@ -405,12 +427,17 @@ class AcousticEngine:
     # ------------------------------------------------------------------------------------------
     # GLU feed-forward sub-layer
     # ------------------------------------------------------------------------------------------
-    def _ffn_fwd(self, pre: str, x: torch.Tensor, norm: str, ff: int, sv: dict, drop: Optional[dict] = None):
+    def _ffn_fwd(self, pre: str, x: torch.Tensor, norm: str, ff: int, sv: dict, drop: Optional[dict] = None, pre_ln=None,
+                 next_ln=None):
+        """pre_ln / next_ln: as in _attn_fwd."""
         st, D = self.store, self.D
         N = x.shape[0]
-        h = self._empty(N, D, dtype=BF16)
-        mean, rstd = self._empty(N), self._empty(N)
-        ops.layernorm_fwd(x, st.p(norm + "weight"), st.p(norm + "bias"), h, None, mean, rstd)
+        if pre_ln is None:
+            h = self._empty(N, D, dtype=BF16)
+            mean, rstd = self._empty(N), self._empty(N)
+            ops.layernorm_fwd(x, st.p(norm + "weight"), st.p(norm + "bias"), h, None, mean, rstd)
+        else:
+            h, mean, rstd = pre_ln
         hff = self._empty(N, 2 * ff, dtype=BF16)
         ops.gemm(h, st.w(pre + "linear1.weight"), hff, bias=st.p(pre + "linear1.bias"))
         u = self._empty(N, ff, dtype=BF16)
@@ -419,9 +446,16 @@ class AcousticEngine:
         y = self._empty(N, D)
         ops.gemm(u, st.w(pre + "linear2.weight"), y, bias=st.p(pre + "linear2.bias"))
         out = self._empty(N, D)
-        ops.rmsnorm_resid_fwd(y, st.p(pre + "output_norm.weight"), x, out, drop=drop["out"])
+        nxt = None
+        if next_ln is None:
+            ops.rmsnorm_resid_fwd(y, st.p(pre + "output_norm.weight"), x, out, drop=drop["out"])
+        else:
+            nxt = self._ln_out(N, next_ln)
+            ops.rmsnorm_resid_ln_fwd(y, st.p(pre + "output_norm.weight"), x, out, drop["out"], st.p(next_ln[0] + "weight"),
+                                     st.p(next_ln[0] + "bias"), *nxt)
+            nxt = (nxt[0] if nxt[0] is not None else nxt[1], nxt[2], nxt[3])
         sv.update(x=x, h=h, mean=mean, rstd=rstd, hff=hff, u=u, y=y, drop=drop)
-        return out
+        return out if next_ln is None else (out, nxt)
 
     def _ffn_bwd(self, pre: str, dout: torch.Tensor, norm: str, ff: int, sv: dict, next_drop=None, next_dbias=None):
         st, D = self.store, self.D
@@ -535,9 +569,9 @@ class AcousticEngine:
             ops.dec_in_drop(t_in, st.pe[:T], y, T, spec, scale_a)
         s1: dict = {}
         pre = "decoder.layers.0."
-        y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, ctx["mel_pad"], None, T, s1,
-                           drop=self._branch_specs("dec.0.self", p_dec, T, False))
-        return melshift, y, s1
+        y, ln = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, ctx["mel_pad"], None, T, s1,
+                               drop=self._branch_specs("dec.0.self", p_dec, T, False), next_ln=(pre + "norm2.", "bf16"))
+        return melshift, (y, ln), s1
 
     # ------------------------------------------------------------------------------------------
     # forward
@@ -589,17 +623,19 @@ class AcousticEngine:
             text_pad = self._empty(B, P, dtype=torch.uint8)
             ops.eq_mask(idx, 0, text_pad)
         enc_saved = []
+        ln = None                             # LayerNorm of the next sub-layer, produced by the previous sub-layer's tail kernel
         for i in range(cfg.n_encoder_layers):
             pre = f"transformer_encoder_layers.{i}."
             s1, s2 = {}, {}
-            x = self._attn_fwd(pre + "self_attn.", x, B, P, pre + "norm1.", False, text_pad, None, P, s1,
-                               drop=self._branch_specs(f"enc.{i}.attn", p_enc, P, False))
-            x = self._ffn_fwd(pre + "ff.", x, pre + "norm2.", cfg.encoder_ff_dim, s2,
-                              drop=self._branch_specs(f"enc.{i}.ffn", p_enc, P, True))
+            x, ln = self._attn_fwd(pre + "self_attn.", x, B, P, pre + "norm1.", False, text_pad, None, P, s1,
+                                   drop=self._branch_specs(f"enc.{i}.attn", p_enc, P, False), pre_ln=ln,
+                                   next_ln=(pre + "norm2.", "bf16"))
+            last = i == cfg.n_encoder_layers - 1
+            x, ln = self._ffn_fwd(pre + "ff.", x, pre + "norm2.", cfg.encoder_ff_dim, s2,
+                                  drop=self._branch_specs(f"enc.{i}.ffn", p_enc, P, True), pre_ln=ln,
+                                  next_ln=("encoder_norm.", "f32") if last else (f"transformer_encoder_layers.{i + 1}.norm1.", "bf16"))
             enc_saved.append((s1, s2))
-        enc = self._empty(Ne, D)
-        enc_mean, enc_rstd = self._empty(Ne), self._empty(Ne)
-        ops.layernorm_fwd(x, st.p("encoder_norm.weight"), st.p("encoder_norm.bias"), None, enc, enc_mean, enc_rstd)
+        enc, enc_mean, enc_rstd = ln          # the final encoder norm (fp32) came out of the last FFN's tail
         ctx.update(idx=idx, stress=stress, text_pad=text_pad, enc_saved=enc_saved, enc_in=x,
                    enc_mean=enc_mean, enc_rstd=enc_rstd)
 
@@ -644,7 +680,7 @@ class AcousticEngine:
             dec_head = self._decoder_head(ctx, mel_specs, B, T, dcfg, p_enc, p_dec)
         else:
             self._join("d0")
-        melshift, y, s1_first = dec_head
+        melshift, (y, ln), s1_first = dec_head
         dec_saved = []
         kv_pre = [None] * cfg.n_decoder_layers
         if self.multi_stream:                 # all six cross-attention K/V projections depend on `mem` only
@@ -658,18 +694,20 @@ class AcousticEngine:
             pre = f"decoder.layers.{i}."
             s1, s2, s3 = {}, {}, {}
             if i == 0:
-                s1 = s1_first                 # already computed by _decoder_head
+                s1 = s1_first                 # already computed by _decoder_head (with norm2's LayerNorm)
             else:
-                y = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, mel_padding_mask, None, T, s1,
-                                   drop=self._branch_specs(f"dec.{i}.self", p_dec, T, False))
-            y = self._attn_fwd(pre + "cross_attn.", y, B, T, pre + "norm2.", False, fmask_t, mem, T, s2,
-                               kv_pre=kv_pre[i], drop=self._branch_specs(f"dec.{i}.cross", p_dec, T, False))
-            y = self._ffn_fwd(pre + "ff.", y, pre + "norm3.", cfg.decoder_ff_dim, s3,
-                              drop=self._branch_specs(f"dec.{i}.ffn", p_dec, T, True))
+                y, ln = self._attn_fwd(pre + "self_attn.", y, B, T, pre + "norm1.", True, mel_padding_mask, None, T, s1,
+                                       drop=self._branch_specs(f"dec.{i}.self", p_dec, T, False), pre_ln=ln,
+                                       next_ln=(pre + "norm2.", "bf16"))
+            y, ln = self._attn_fwd(pre + "cross_attn.", y, B, T, pre + "norm2.", False, fmask_t, mem, T, s2,
+                                   kv_pre=kv_pre[i], drop=self._branch_specs(f"dec.{i}.cross", p_dec, T, False), pre_ln=ln,
+                                   next_ln=(pre + "norm3.", "bf16"))
+            last = i == cfg.n_decoder_layers - 1
+            y, ln = self._ffn_fwd(pre + "ff.", y, pre + "norm3.", cfg.decoder_ff_dim, s3,
+                                  drop=self._branch_specs(f"dec.{i}.ffn", p_dec, T, True), pre_ln=ln,
+                                  next_ln=("decoder.norm.", "bf16") if last else (f"decoder.layers.{i + 1}.norm1.", "bf16"))
             dec_saved.append((s1, s2, s3))
-        yn = self._empty(Nd, D, dtype=BF16)
-        dn_mean, dn_rstd = self._empty(Nd), self._empty(Nd)
-        ops.layernorm_fwd(y, st.p("decoder.norm.weight"), st.p("decoder.norm.bias"), yn, None, dn_mean, dn_rstd)
+        yn, dn_mean, dn_rstd = ln             # decoder.norm came out of the last FFN's tail
         mel_pred = self._empty(Nd, cfg.mel_dim)
         ops.gemm(yn, st.w("mel_projection_out.weight"), mel_pred, bias=st.p("mel_projection_out.bias"))
         stop = self._empty(Nd)

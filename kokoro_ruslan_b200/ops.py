@@ -321,6 +321,23 @@ def rmsnorm_resid_fwd(y, gain, resid, out, drop: Optional[DropSpec] = None):
           "kr_rmsnorm_resid_fwd")
 
 
+def resid_drop_ln_fwd(y, resid, out, drop: Optional[DropSpec], gamma, beta, h_bf16, h_f32, mean, rstd, eps: float = 1e-5):
+    """out = resid + dropout(y); h = LayerNorm(out) (csrc/kr_norm.cu resid_drop_ln_fwd_kernel)."""
+    N, D = y.shape
+    check(lib().kr_resid_drop_ln_fwd(_ptr(y), _ptr(resid), _ptr(out), c_int(N), c_int(D), _dref(drop), _ptr(gamma), _ptr(beta),
+                                     _ptr(h_bf16), _ptr(h_f32), _ptr(mean), _ptr(rstd), c_float(eps), _stream()),
+          "kr_resid_drop_ln_fwd")
+
+
+def rmsnorm_resid_ln_fwd(y, gain, resid, out, drop: Optional[DropSpec], gamma, beta, h_bf16, h_f32, mean, rstd,
+                         eps: float = 1e-5):
+    """rmsnorm_resid_fwd + the LayerNorm that follows it, one kernel."""
+    N, D = y.shape
+    check(lib().kr_rmsnorm_resid_ln_fwd(_ptr(y), _ptr(gain), _ptr(resid), _ptr(out), c_int(N), c_int(D), _dref(drop), _ptr(gamma),
+                                        _ptr(beta), _ptr(h_bf16), _ptr(h_f32), _ptr(mean), _ptr(rstd), c_float(eps), _stream()),
+          "kr_rmsnorm_resid_ln_fwd")
+
+
 def rmsnorm_resid_bwd(dout, y, gain, dy_bf16, dgain, drop: Optional[DropSpec] = None,
                       dcol: Optional[torch.Tensor] = None):
     """dcol [D] += column sums of dy (the bias gradient of the Linear that produced y)."""

@@ -49,6 +49,8 @@ DOCS = {
     "kr_layernorm_fwd": "LayerNorm over the last dim (D in {128,256,512}), fp32 in, bf16 and/or fp32 out, saves mean/rstd. model/transformers.py:478,485,564,572,581,660; model/model.py:122.",
     "kr_layernorm_bwd": "LayerNorm backward fused with the residual-gradient add (dx = dres + ...), optional bf16 copy of dx (with the dropout / stochastic-depth factors of the residual branch it feeds, and its column sums = that branch's output-bias gradient accumulated into dcol_bf16), dgamma/dbeta accumulated with atomics.",
     "kr_rmsnorm_resid_fwd": "FFN output RMSNorm(eps = fp32 finfo.eps) + residual add, model/transformers.py:94,109-111.",
+    "kr_resid_drop_ln_fwd": "Tail of an attention sub-layer fused with the LayerNorm that follows it: out = resid + dropout(y) (y = the out-projection's fp32 output incl. bias; the dropout / stochastic-depth factors and their element index row * D + col are those of kr_gemm_ex's dropout epilogue, model/transformers.py:482-483,569,578) and h = LayerNorm(out) (bf16 and / or fp32 copy, mean / rstd saved for the backward), model/transformers.py:474,563 pre-norm blocks. Bit-identical to the GEMM epilogue + kr_layernorm_fwd it replaces.",
+    "kr_rmsnorm_resid_ln_fwd": "kr_rmsnorm_resid_fwd fused with the LayerNorm of the next sub-layer (or the final norm): out as there, h = LayerNorm(out), mean / rstd saved.",
     "kr_rmsnorm_resid_bwd": "Backward of kr_rmsnorm_resid_fwd w.r.t. y (bf16) and the gain; dcol += column sums of dy (bias gradient of linear2).",
     "kr_qkv_prep_fwd": "Per-head RMSNorm(64) with learned gain on up to three column blocks (q|k|v) + rotate-half RoPE on the blocks selected by rope_mask; position = row % S. model/transformers.py:145-148,260-272; model/positional_encoding.py:196-209.",
     "kr_qkv_prep_bwd": "Backward of kr_qkv_prep_fwd: incoming gradients may be fp32 (grad_f32_mask) or bf16; writes d(raw projection) bf16 and accumulates the gain gradients.",
