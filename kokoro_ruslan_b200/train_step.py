@@ -34,6 +34,8 @@ from .params import ModelConfig
 
 BATCH_KEYS = ("phoneme_indices", "stress_indices", "phoneme_durations", "mel_specs", "pitches", "energies",
               "stop_token_targets", "mel_lengths", "phoneme_lengths")
+PACKED_KEYS = tuple(k for k in BATCH_KEYS if k != "mel_specs")      # the small fields: one packed H2D copy per step
+PACK_RING = 4                                                       # pinned host images in flight (guarded by events)
 
 
 @dataclass
@@ -173,6 +175,13 @@ class _Staged:
     launches: int = 0
     warm: List[int] = field(default_factory=lambda: [0] * 4)
     last_used: int = 0
+    # every batch field except the mel lives in ONE device allocation (dev[k] are views at 256-byte offsets), filled from a
+    # ring of pinned host images by ONE copy: a step's host batch costs two H2D transfers (this + the mel) instead of nine
+    pack_dev: Optional[torch.Tensor] = None
+    pack_host: Optional[torch.Tensor] = None                       # [PACK_RING, bytes] pinned
+    pack_views: List[Dict[str, torch.Tensor]] = field(default_factory=list)
+    pack_done: List[Optional[torch.cuda.Event]] = field(default_factory=list)
+    pack_i: int = 0
 
 
 class TrainStep:
@@ -278,6 +287,23 @@ class TrainStep:
             out["phoneme_lengths"] = batch["phoneme_lengths"].clamp(max=cap)
         return out
 
+    def _new_staged(self, batch: Dict[str, torch.Tensor]) -> _Staged:
+        """Static device buffers of one batch shape: the mel on its own, everything else as views of one packed allocation."""
+        offs, off = {}, 0
+        for k in PACKED_KEYS:
+            offs[k] = off
+            off = (off + batch[k].numel() * batch[k].element_size() + 255) & ~255
+        pack_dev = torch.empty(max(off, 256), dtype=torch.uint8, device=self.device)
+        pack_host = torch.empty(PACK_RING, pack_dev.numel(), dtype=torch.uint8).pin_memory()
+
+        def views(base: torch.Tensor) -> Dict[str, torch.Tensor]:
+            return {k: base[offs[k]:offs[k] + batch[k].numel() * batch[k].element_size()].view(batch[k].dtype).view(batch[k].shape)
+                    for k in PACKED_KEYS}
+        dev = views(pack_dev)
+        dev["mel_specs"] = torch.empty(batch["mel_specs"].shape, dtype=batch["mel_specs"].dtype, device=self.device)
+        return _Staged(dev=dev, pack_dev=pack_dev, pack_host=pack_host, pack_views=[views(pack_host[i]) for i in range(PACK_RING)],
+                       pack_done=[None] * PACK_RING)
+
     def stage(self, batch: Dict[str, torch.Tensor], divisor: int = 1) -> Tuple[_Staged, Tuple[int, int, int, int, bool]]:
         """Host-side prologue: shape key, stabiliser scalars, async H2D into the static buffers.
         divisor = the accumulation divisor of this micro-batch (trainer.py:2284-2294)."""
@@ -302,16 +328,28 @@ class TrainStep:
             if len(self._staged) >= self.max_cached_shapes:
                 victim = min(self._staged, key=lambda k: self._staged[k].last_used)
                 del self._staged[victim]          # drops the graph and its private memory pool
-            dev = {}
-            for k in BATCH_KEYS:
-                src = batch[k]
-                dev[k] = torch.empty(src.shape, dtype=src.dtype, device=self.device)
-            st = _Staged(dev=dev)
+            st = self._new_staged(batch)
             self._staged[key] = st
         st.last_used = self._tick
         nbytes = 0
+        packed = on_host and all(not batch[k].is_cuda and batch[k].dtype == st.dev[k].dtype for k in PACKED_KEYS)
+        if packed:
+            i = st.pack_i % PACK_RING
+            st.pack_i += 1
+            if st.pack_done[i] is not None:
+                st.pack_done[i].synchronize()     # the copy that last read this pinned image has finished (PACK_RING steps ago)
+            for k, view in st.pack_views[i].items():
+                view.copy_(batch[k])
+            st.pack_dev.copy_(st.pack_host[i], non_blocking=True)
+            if st.pack_dev.is_cuda:
+                if st.pack_done[i] is None:
+                    st.pack_done[i] = torch.cuda.Event()
+                st.pack_done[i].record()
+            nbytes += sum(v.numel() * v.element_size() for v in st.pack_views[i].values())
         for k in BATCH_KEYS:
             src = batch[k]
+            if packed and k in PACKED_KEYS:
+                continue
             if src.data_ptr() != st.dev[k].data_ptr():
                 st.dev[k].copy_(src, non_blocking=True)
                 if not src.is_cuda:

@@ -82,3 +82,29 @@ for g, p, n in gaps[:14]:
 print("  last 8 activities of the step:")
 for e in sorted(step, key=lambda e: e["ts"] + e["dur"])[-8:]:
     print(f"    ends {(e['ts'] + e['dur'] - t0) / 1e3:6.3f} ms  dur {e['dur']:7.1f} us  stream {e['args'].get('stream')}  {e['name'][:70]}")
+# the forward chain: the side stream that carries the most busy time before the main stream resumes
+if gaps:
+    g0, p0, n0 = gaps[0]
+    fwd_end = n0["ts"]
+    cand = {s: sum(e["dur"] for e in es_ if e["ts"] < fwd_end) for s, es_ in by.items() if s != main}
+    fs = max(cand, key=cand.get)
+    chain = [e for e in by[fs] if e["ts"] < fwd_end]
+    print(f"  forward chain on stream {fs}: {len(chain)} kernels, busy {sum(e['dur'] for e in chain) / 1e3:.3f} ms, "
+          f"span {(chain[-1]['ts'] + chain[-1]['dur'] - chain[0]['ts']) / 1e3:.3f} ms")
+    fam = defaultdict(lambda: [0, 0.0, 0.0])
+    prev_end = chain[0]["ts"]
+    for e in chain:
+        k = e["name"].replace("(anonymous namespace)::", "").replace("void ", "")[:44]
+        fam[k][0] += 1
+        fam[k][1] += e["dur"]
+        fam[k][2] += max(0.0, e["ts"] - prev_end)
+        prev_end = e["ts"] + e["dur"]
+    print("    kernel family                                   n   busy us  gap-before us")
+    for k, (n, d, g) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
+        print(f"    {k:44s} {n:4d} {d:9.1f} {g:9.1f}")
+    if os.environ.get("KR_TIMELINE_CHAIN"):
+        prev_end = chain[0]["ts"]
+        for e in chain:
+            print(f"      +{(e['ts'] - t0) / 1e3:6.3f} ms gap {e['ts'] - prev_end:5.1f} dur {e['dur']:6.1f}  "
+                  f"{e['name'].replace('(anonymous namespace)::', '')[:60]} grid {e['args'].get('grid')}")
+            prev_end = e["ts"] + e["dur"]
