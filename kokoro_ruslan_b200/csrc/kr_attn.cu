@@ -140,9 +140,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_qtiles = (p.Sq + TQ - 1) / TQ;
-  // causal: the last pair attends to the most keys -> schedule the heavy pairs first
-  const int pair = CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
+  // 1-D grid, pair of query tiles OUTERMOST: CTAs are handed out in blockIdx order, so the whole machine takes the heavy
+  // pairs first (longest-processing-time order).  Causal: the last pair attends to the most keys; otherwise the last pair
+  // (often a single, partly filled tile) is the light one and goes last.  With the pair innermost (round 1-2: a 3-D grid)
+  // every (head, batch) group put one heavy CTA at the END of the schedule: 13 vs 10 key-tile times for T = 800.
+  const int per_pair = p.H * p.B;
+  const int pi = (int)blockIdx.x / per_pair, hb = (int)blockIdx.x - pi * per_pair;
+  const int pair = CAUSAL ? (n_qtiles + 1) / 2 - 1 - pi : pi;
+  const int h = hb % p.H, b = hb / p.H;
   const int n_ktiles = (p.Sk + TK - 1) / TK;
   int n_w[2];
 #pragma unroll
@@ -810,7 +815,7 @@ extern "C" int kr_attn_fwd(const void* q, long long q_ss, long long q_bs, const 
     attr = true;
   }
   const int n_qtiles = (Sq + TQ - 1) / TQ;
-  dim3 grid((n_qtiles + 1) / 2, H, B);          // one CTA per PAIR of query tiles
+  dim3 grid(((n_qtiles + 1) / 2) * H * B, 1, 1);   // one CTA per PAIR of query tiles, pair outermost (LPT order)
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool dr = p.drop.state != nullptr;
   if (causal && dr)  kr::launch(attn_fwd_kernel<true, true>, grid, FWD_THREADS, FWD_SMEM, st, tq, tk, tv, p);
