@@ -88,15 +88,20 @@ class PadGeom:
         self.group_rows = torch.tensor(group_rows, **i32)
 
 
-_WGRAD_TARGET = int(__import__("os").environ.get("KR_WGRAD_TARGET", "96"))
-_WGRAD_MIN_KB = int(__import__("os").environ.get("KR_WGRAD_MIN_KB", "12"))
+# Weight-gradient GEMM policy, fixed by sweeps on B200 at the bench shape (tools/gpu_ab.sh history in DESIGN.md §7):
+# 128 x 256 output tiles (one N = 256 MMA per K step reads fewer operand bytes per flop than two N = 128 ones), split-K
+# until a GEMM has about _WGRAD_TARGET CTAs, never fewer than _WGRAD_MIN_KB 64-row K blocks per split.
+_WGRAD_TARGET = 112
+_WGRAD_MIN_KB = 12
+_WGRAD_BLOCK_N = 256
 
 
 def _auto_splits(tiles: int, k_blocks: int, target: int = 0) -> int:
     """Split-K factor of a weight-gradient GEMM.  Every split pays a full fp32-atomic epilogue of its output tile
     and the weight gradients run on side streams next to the critical chain, so FEWER, longer CTAs win: measured
     on B200 (tools/wgrad_ab.sh) 296 CTAs / no minimum = 7.36 ms per step, 96 CTAs with >= 12 K blocks (768 rows)
-    per split = 7.07-7.16 ms."""
+    per split = 7.07-7.16 ms.  Round 2, 128 x 256 tiles, step in ms at target 96 / 112 / 128 / 148 / 192 CTAs:
+    6.19 / 6.14 / 6.16 / 6.21 / 6.20 (128 x 128 tiles at 96 / 128: 6.19 / 6.20)."""
     target = target or _WGRAD_TARGET
     s = max(1, min(k_blocks, (target + tiles - 1) // tiles))
     return max(1, min(s, k_blocks // max(1, _WGRAD_MIN_KB)))
@@ -285,11 +290,12 @@ class AcousticEngine:
         """gw[N_out, K_in] += dy[tok, N_out]^T x[tok, K_in] (split-K, fp32 atomics) and, when gb is
         given, gb[N_out] += column sums of dy (bias gradient) — both on a weight-gradient stream."""
         n_out, k_in = gw.shape
-        tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128)
+        bn = _WGRAD_BLOCK_N if k_in % _WGRAD_BLOCK_N == 0 else 0          # 0: the library picks the tile width
+        tiles = ((n_out + 127) // 128) * ((k_in + (bn or 128) - 1) // (bn or 128))
         kb = (dy.shape[0] + 63) // 64
         with self._on_w():
             ops.gemm(dy, x, gw, a_mn_major=True, b_mn_major=True, accumulate=True,
-                     splits=_auto_splits(tiles, kb))
+                     splits=_auto_splits(tiles, kb), block_n=bn)
             if gb is not None:
                 ops.colsum_bf16(dy, gb)
 

@@ -1,2 +1,4 @@
-# A/B of the weight-gradient split-K policy (KR_WGRAD_TARGET = CTAs per GEMM, KR_WGRAD_MIN_KB = min 64-row K blocks per split)
-for cfg in ${WGRAD_CFGS:-"96 12" "64 16" "48 20" "74 12" "96 25" "32 25"}; do set -- $cfg; KR_WGRAD_TARGET=$1 KR_WGRAD_MIN_KB=$2 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-hifigan 2>/dev/null | python -c "import sys,json; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('target $1 min_kb $2:', round(d['ms_per_step'],3))"; done
+# Round-1 A/B of the weight-gradient split-K policy.  The knobs it swept (CTAs per GEMM, minimum 64-row K blocks per split)
+# are now the constants _WGRAD_TARGET / _WGRAD_MIN_KB / _WGRAD_BLOCK_N in kokoro_ruslan_b200/engine.py; to sweep again,
+# edit them and run tools/gpu_ab.sh.  Results: engine._auto_splits docstring, DESIGN.md §7.
+echo "see kokoro_ruslan_b200/engine.py:_auto_splits"
