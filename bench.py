@@ -419,8 +419,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        l = ts.train_step(host)
-        l_host = l.cpu()                      # D2H read of the step's result (synchronises)
+        l_host = ts.train_step_host(host)     # host batch in, the step's six losses out as Python floats (D2H inside the step)
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
@@ -563,7 +562,11 @@ def run_ours(args):
             "config": bench_config(world, args.dropout, comm),
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": frames_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d_bytes + 8 + 40, "d2h_bytes_per_step": 24},
+                    "h2d_bytes_per_step": h2d_bytes + 12 + 40, "d2h_bytes_per_step": 28,
+                    "api": "TrainStep.train_step_host(host batch) -> six losses as Python floats, every step: the batch goes "
+                           "host -> device in two copies before the step's graph, the losses (+ a sequence id) come back by a "
+                           "D2H copy inside the step right after the loss kernel, so the host stages the next batch while the "
+                           "backward pass and optimizer run; the next step starts after this one has finished (stream order)"},
             "gpu_launches": launches_per_step * args.steps * 2, "launches_per_step": launches_per_step,
             "clocks": clocks, "losses_first": first_losses, "losses_last": final_losses, "lib": str(_lib.LIB_PATH)}
     print(json.dumps(line), flush=True)

@@ -129,7 +129,7 @@ class AcousticEngine:
         if os.environ.get("KR_STREAMS", "1") == "0":
             multi_stream = False
         self.multi_stream = multi_stream
-        self._side = {k: torch.cuda.Stream(device=self.device) for k in ("w0", "w1", "vp", "enc", "kv", "d0", "comm", "z")} if multi_stream else {}
+        self._side = {k: torch.cuda.Stream(device=self.device) for k in ("w0", "w1", "vp", "enc", "kv", "d0", "comm", "z", "l")} if multi_stream else {}
         # data parallel: callable(split_layer) that all-reduces early_grad_ranges(split_layer); backward_parts() runs it on
         # the "comm" side stream once those ranges are final, underneath the rest of the backward (TrainStep installs it)
         self.early_reduce_hook = None

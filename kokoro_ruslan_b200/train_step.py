@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import math
 import os
+import time
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -249,11 +250,16 @@ class TrainStep:
         self._opt_warm = 0
         self._opt_launches = 0
         # [loss scale / world, clip norm] for the current step: one pinned ring slot -> one H2D copy
-        self._scal_ring = torch.empty(64, 2, dtype=torch.float32).pin_memory()
+        # (+ the sequence id of the step, which travels back with the losses: train_step_host())
+        self._scal_ring = torch.zeros(64, 3, dtype=torch.float32).pin_memory()
         self._scal_i = 0
-        self._scal_dev = torch.tensor([1.0, self.opt.cfg.max_grad_norm], dtype=torch.float32, device=self.device)
+        self._scal_dev = torch.tensor([1.0, self.opt.cfg.max_grad_norm, 0.0], dtype=torch.float32, device=self.device)
         self.loss_scale = self._scal_dev[0:1]
         self.clip = self._scal_dev[1:2]
+        # losses[6] + the step's sequence id, written by a D2H copy that is part of the step right after the loss kernel (side
+        # stream "l"): the host can read a step's losses while its backward pass and optimizer are still running
+        self._loss_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._seq = 0
         self.launches_last_step = 0
         self.h2d_bytes_last_step = 0
 
@@ -359,8 +365,9 @@ class TrainStep:
         self._scal_i += 1
         slot[0] = scale / (self.world * max(1, divisor))
         slot[1] = clip
+        slot[2] = float(self._seq)
         self._scal_dev.copy_(slot, non_blocking=True)
-        self.h2d_bytes_last_step = nbytes + 8
+        self.h2d_bytes_last_step = nbytes + 12
         return st, key
 
     # ------------------------------------------------------------------------------------------
@@ -376,6 +383,9 @@ class TrainStep:
                                d["pitches"], d["energies"], d["mel_lengths"], d["phoneme_lengths"],
                                loss_scale=self.loss_scale)
         out.append(losses)
+        with eng._on("l"):                        # early D2H of the losses, then of the sequence id that marks them valid
+            self._loss_host[0:6].copy_(losses, non_blocking=True)
+            self._loss_host[6:7].copy_(self._scal_dev[2:3], non_blocking=True)
         if zero:
             eng._join("z")                        # every backward stream forks from here: the gradients are zero before any of them adds
         yield from eng.backward_parts(ctx, g, self.split_layer if getattr(self, "_early_on", False) else None)
@@ -512,6 +522,26 @@ class TrainStep:
     def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         """Full optimizer step on one micro-batch (gradient_accumulation_steps = 1)."""
         return self.micro_step(batch, True, True, 1)
+
+    def train_step_host(self, batch: Dict[str, torch.Tensor], timeout_s: float = 120.0) -> List[float]:
+        """train_step() for callers that log the losses of EVERY step (the reference trainer's progress bar,
+        trainer.py:2560-2600): returns the six un-scaled losses as Python floats as soon as the device has produced them —
+        right after the forward pass — while the backward pass and the optimizer of the step are still running; the host
+        stages the next batch in that time.  Stream order is unchanged: the next step starts after this one has finished."""
+        self._seq = self._seq % 1000000 + 1
+        want = float(self._seq)
+        self.micro_step(batch, True, True, 1)
+        flag = self._loss_host.numpy()
+        t0 = time.monotonic()
+        spins = 0
+        while flag[6] != want:                    # pinned memory: the copy engine's writes are visible to host loads
+            spins += 1
+            if (spins & 0xFFFF) == 0 and time.monotonic() - t0 > timeout_s:
+                torch.cuda.synchronize(self.device)
+                if flag[6] != want:
+                    raise RuntimeError("train_step_host: the losses of the step never arrived (sequence id %r, want %r)"
+                                       % (float(flag[6]), want))
+        return [float(v) for v in flag[:6]]
 
     def train_window(self, batches: List[Dict[str, torch.Tensor]]) -> List[torch.Tensor]:
         """One optimizer step over an accumulation window of len(batches) micro-batches; the divisor is the

@@ -163,3 +163,34 @@ def test_validation_forward_uses_ema_weights_and_no_dropout():
         assert torch.allclose(g, want, rtol=1.5e-2, atol=1e-4), (use_ema, g, want)
     ts.train_step(batch)                                                # training continues normally afterwards
     assert int(ts.engine.drop_state[1]) == rng_step + 1
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_train_step_host_returns_each_steps_losses_early(graphs):
+    """train_step_host() hands back the six losses of THE step it ran (sequence id check) — the numbers train_step()
+    leaves in its device tensor — for varying batches and shapes, and trains the same weights."""
+    from oracle import acoustic as oa
+    from kokoro_ruslan_b200.optim import OptimConfig
+    from kokoro_ruslan_b200.train_step import ScheduleConfig, TrainStep
+    ocfg, cfg = _tiny()
+    sd = oa.seeded_state_dict(ocfg, seed=0)
+    mk = lambda: TrainStep(cfg, OptimConfig(learning_rate=1e-3), ScheduleConfig(total_steps=1000), device="cuda", use_graphs=graphs)
+    a, b = mk(), mk()
+    a.load_state_dict(sd)
+    b.load_state_dict(sd)
+    batches = [{k: v.pin_memory() for k, v in oa.synthetic_batch(B=3, P=24, T=T, seed=s, ragged=True).items()}
+               for T, s in ((150, 11), (150, 12), (97, 13), (150, 11), (97, 14), (150, 15))]
+    for i, batch in enumerate(batches):
+        want = a.train_step(batch).cpu().tolist()
+        got = b.train_step_host(batch)
+        if i == 0:
+            assert got == want, (got, want)       # same weights, deterministic forward: the very same numbers
+        # later steps: the split-K weight gradients add with fp32 atomics, so two runs differ in the last bits
+        assert all(abs(g - w) <= 2e-3 * abs(w) + 1e-5 for g, w in zip(got, want)), (i, got, want)
+    torch.cuda.synchronize()
+    num = den = 0.0
+    mine, other = a.store.state_dict(), b.store.state_dict()
+    for n in a.store.order:
+        num += float((mine[n].float() - other[n].float()).pow(2).sum())
+        den += float((mine[n].float().cpu() - sd[n]).pow(2).sum())
+    assert (num / den) ** 0.5 < 0.15, (num / den) ** 0.5          # same gate as the oracle comparison above
