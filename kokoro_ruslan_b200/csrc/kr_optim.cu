@@ -128,6 +128,9 @@ struct AdamParams {
   float beta1, beta2, eps, ema_decay;
 };
 
+// A 38 B / element stream (5 reads, 4 writes + the bf16 shadow): 5.1 TB/s = 79 % of the measured copy bandwidth, 62 % of the
+// DRAM peak in ncu, occupancy capped at 4 blocks per SM by registers.  Tried in round 2 without any gain: two float4 positions
+// of all five arrays in flight per thread (160 B, 68 registers: 370 vs 365 us), 2048 / 8192 / 16384-element chunks.
 __global__ void adamw_kernel(const AdamParams a) {
   kr::pdl_entry();
   __shared__ float red[32];
