@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FAMILIES = ["", "kr_attn_bwd", "kr_attn_fwd", "kr_attn_bwd_prep", "kr_qkv_prep_bwd", "kr_qkv_prep_fwd", "kr_layernorm_bwd",
-            "kr_layernorm_fwd", "kr_glu_bwd", "kr_glu_fwd", "kr_rmsnorm_resid_bwd", "kr_rmsnorm_resid_fwd", "kr_colsum",
+            "kr_layernorm_fwd", "kr_glu_bwd", "kr_glu_fwd", "kr_rmsnorm_resid_bwd", "kr_rmsnorm_resid_ln_fwd", "kr_resid_drop_ln_fwd", "kr_colsum",
             "kr_gn_", "kr_adamw_step", "kr_gemm"]
 
 
