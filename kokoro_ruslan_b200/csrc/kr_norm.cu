@@ -534,6 +534,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) qkv_prep_bwd_kernel(const Pr
   if (threadIdx.x < 64 && pp.dgain != nullptr) atomicAdd(pp.dgain + threadIdx.x, sm[threadIdx.x]);
 }
 
+// Tried and dropped (round 2): ln_bwd with the next row's x / dy prefetched in registers and the three column accumulators
+// in per-warp shared memory rows (to free the registers): 14.9 vs 9.1 us at 6400 x 512 — the shared-memory read-modify-write
+// per row and 184 bytes of spills cost more than the overlapped load latency gains.
 // Launch geometry, fixed by sweeps on B200 (round 2, bench shape; the sweep knobs are gone):
 //   * ln_bwd runs at 2 blocks / SM (launch bounds): 3 blocks / SM would cap it at 80 registers and spill ~260 bytes since
 //     the dropout specs were added;

@@ -2,7 +2,7 @@
 # Serialised launch list of one eager training step with DRAM bytes per kernel (profiles/r02_step_traffic_*).
 mkdir -p gpurun_out
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/step_traffic.csv python tools/one_step.py 2 > gpurun_out/step_traffic.log 2>&1
-python tools/ncu_traffic.py gpurun_out/step_traffic.csv gpurun_out/r02_step_traffic_v2 | head -30
+python tools/ncu_traffic.py gpurun_out/step_traffic.csv gpurun_out/r02_step_traffic_v3 | head -30
 python - <<'PY'
 import csv
 from collections import defaultdict
