@@ -537,6 +537,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) qkv_prep_bwd_kernel(const Pr
 // Tried and dropped (round 2): ln_bwd with the next row's x / dy prefetched in registers and the three column accumulators
 // in per-warp shared memory rows (to free the registers): 14.9 vs 9.1 us at 6400 x 512 — the shared-memory read-modify-write
 // per row and 184 bytes of spills cost more than the overlapped load latency gains.
+// Also dropped: qkv_prep_fwd with gain / cos / sin fetched four values at a time at their use (60 registers, 4 blocks per SM,
+// instead of 80 / 3): 10.7 vs 9.9 us for the three-part self-attention call; at 48 / 40 registers the spills make it 14 - 17 us.
 // Launch geometry, fixed by sweeps on B200 (round 2, bench shape; the sweep knobs are gone):
 //   * ln_bwd runs at 2 blocks / SM (launch bounds): 3 blocks / SM would cap it at 80 registers and spill ~260 bytes since
 //     the dropout specs were added;
