@@ -260,6 +260,12 @@ class TrainStep:
         # stream "l"): the host can read a step's losses while its backward pass and optimizer are still running
         self._loss_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self._seq = 0
+        # The mel batch is read by the first forward kernel and by the loss kernel only.  Once train_step_host() has SEEN a
+        # step's losses on the host, that step is past its last reader, so the next batch's mel (2 MB, 40 us of PCIe — the one
+        # large input) is copied from a side stream while the backward pass and optimizer of the step still run.
+        self._mel_idle = False
+        self._copy_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._mel_copied: Optional[torch.cuda.Event] = None
         self.launches_last_step = 0
         self.h2d_bytes_last_step = 0
 
@@ -352,12 +358,21 @@ class TrainStep:
                     st.pack_done[i] = torch.cuda.Event()
                 st.pack_done[i].record()
             nbytes += sum(v.numel() * v.element_size() for v in st.pack_views[i].values())
+        mel_idle, self._mel_idle = self._mel_idle, False
         for k in BATCH_KEYS:
             src = batch[k]
             if packed and k in PACKED_KEYS:
                 continue
             if src.data_ptr() != st.dev[k].data_ptr():
-                st.dev[k].copy_(src, non_blocking=True)
+                if k == "mel_specs" and mel_idle and packed and self._copy_stream is not None:
+                    with torch.cuda.stream(self._copy_stream):
+                        st.dev[k].copy_(src, non_blocking=True)
+                        if self._mel_copied is None:
+                            self._mel_copied = torch.cuda.Event()
+                        self._mel_copied.record()
+                    torch.cuda.current_stream(self.device).wait_event(self._mel_copied)
+                else:
+                    st.dev[k].copy_(src, non_blocking=True)
                 if not src.is_cuda:
                     nbytes += src.numel() * src.element_size()
         scale, clip = adaptive_stabilisation(T, max_d, self.opt.cfg.max_grad_norm)
@@ -541,6 +556,7 @@ class TrainStep:
                 if flag[6] != want:
                     raise RuntimeError("train_step_host: the losses of the step never arrived (sequence id %r, want %r)"
                                        % (float(flag[6]), want))
+        self._mel_idle = True                     # this step is past the loss kernel, the last reader of the mel batch
         return [float(v) for v in flag[:6]]
 
     def train_window(self, batches: List[Dict[str, torch.Tensor]]) -> List[torch.Tensor]:
