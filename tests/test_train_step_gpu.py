@@ -179,7 +179,8 @@ def test_train_step_host_returns_each_steps_losses_early(graphs):
     a.load_state_dict(sd)
     b.load_state_dict(sd)
     batches = [{k: v.pin_memory() for k, v in oa.synthetic_batch(B=3, P=24, T=T, seed=s, ragged=True).items()}
-               for T, s in ((150, 11), (150, 12), (97, 13), (150, 11), (97, 14), (150, 15))]
+               for T, s in ((150, 11), (150, 12), (97, 13), (150, 11), (97, 14), (150, 15), (600, 16), (600, 17), (600, 16))]
+    # (same shape, different mels back to back: the next mel is copied from a side stream while the step still runs)
     for i, batch in enumerate(batches):
         want = a.train_step(batch).cpu().tolist()
         got = b.train_step_host(batch)
