@@ -15,4 +15,3 @@ print("HIFI", {k: v for k, v in d["roofline"].get("hifigan", {}).items() if not 
 print("CPU", {k: v for k, v in d.get("cpu_baseline", {}).items() if k != "sample"})
 PY
 timeout 300 python tools/step_timeline.py > gpurun_out/step_timeline.txt 2>&1; grep -A11 "step span" gpurun_out/step_timeline.txt | cut -c1-150
-timeout 400 python tools/ablate_step.py > gpurun_out/step_ablation.txt 2>&1; tail -20 gpurun_out/step_ablation.txt
