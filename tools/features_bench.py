@@ -51,17 +51,29 @@ def main():
     peak, src = peak_gbs()
     mel_tr = LogMelSpectrogram()
     mel = mel_tr(wav)
+    # algorithmic bytes AND flops per frame: these kernels run FFTs in shared memory (1024-point STFT + 513 x 80 mel filter
+    # bank; a 4096-point FFT pair for the autocorrelation), so the HBM fraction alone says little — the fp32 ALU figure is the
+    # nearer bound, and at 6400 frames per launch both are far from it: the kernels are latency-bound (one CTA per frame,
+    # ~24 barrier-separated butterfly stages), which is fine for a once-per-corpus preprocessing step.
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12            # TFLOP/s: SMs x FMA lanes x 2 x the SM clock under load
     rows = [
-        ("kr_mel_stft", lambda: mel_tr(wav), B * frames * (1024 + 320)),
-        ("kr_pitch_frames+track", lambda: PitchExtractor.extract_pitch(wav), B * frames * (1024 + 12 + 16)),
+        ("kr_mel_stft", lambda: mel_tr(wav), B * frames * (1024 + 320), B * frames * (5 * 1024 * 10 + 2 * 513 * 80)),
+        ("kr_pitch_frames+track", lambda: PitchExtractor.extract_pitch(wav), B * frames * (1024 + 12 + 16),
+         B * frames * (2 * 5 * 4096 * 12)),
         ("kr_energy_frames+norm", lambda: EnergyExtractor.extract_energy_from_mel(mel, False, channel_major=True,
-                                                                                  exp_input=True), B * frames * (320 + 12)),
+                                                                                  exp_input=True), B * frames * (320 + 12), 0),
     ]
-    for name, fn, nbytes in rows:
+    for name, fn, nbytes, flops in rows:
         t = bench(fn)
-        print(json.dumps({"kernel": name, "us": round(t * 1e6, 2), "frames_per_s": round(B * frames / t),
-                          "roofline": {"bound": "hbm", "achieved": round(nbytes / t / 1e9, 2), "peak": peak, "unit": "GB/s",
-                                       "frac": round(nbytes / t / 1e9 / peak, 4), "peak_source": src}}))
+        row = {"kernel": name, "us": round(t * 1e6, 2), "frames_per_s": round(B * frames / t),
+               "roofline": {"bound": "hbm", "achieved": round(nbytes / t / 1e9, 2), "peak": peak, "unit": "GB/s",
+                            "frac": round(nbytes / t / 1e9 / peak, 4), "peak_source": src}}
+        if flops:
+            row["roofline"]["bound"] = "latency (shared-memory FFT stages); nearest throughput bound: fp32 ALU"
+            row["roofline"]["fp32"] = {"achieved": round(flops / t / 1e12, 2), "peak": round(fp32_peak, 1), "unit": "TFLOP/s",
+                                       "frac": round(flops / t / 1e12 / fp32_peak, 4),
+                                       "peak_source": "nominal: 148 SMs x 128 FMA lanes x 2 x 1.965 GHz"}
+        print(json.dumps(row))
     pipe = FeaturePipeline()
     lens = torch.full((B,), n, dtype=torch.int64, device="cuda")      # device-resident: no H2D inside graph capture
     t = bench(lambda: pipe(wav, lens), iters=5)
