@@ -101,7 +101,8 @@ def _auto_splits(tiles: int, k_blocks: int, target: int = 0) -> int:
     and the weight gradients run on side streams next to the critical chain, so FEWER, longer CTAs win: measured
     on B200 (tools/wgrad_ab.sh) 296 CTAs / no minimum = 7.36 ms per step, 96 CTAs with >= 12 K blocks (768 rows)
     per split = 7.07-7.16 ms.  Round 2, 128 x 256 tiles, step in ms at target 96 / 112 / 128 / 148 / 192 CTAs:
-    6.19 / 6.14 / 6.16 / 6.21 / 6.20 (128 x 128 tiles at 96 / 128: 6.19 / 6.20)."""
+    6.19 / 6.14 / 6.16 / 6.21 / 6.20 (128 x 128 tiles at 96 / 128: 6.19 / 6.20); a finer sweep on the final tree: 104 / 112 /
+    120 CTAs = 6.140 / 6.144 - 6.150 / 6.150, minimum K blocks per split 8 / 12 / 16 = 6.186 / 6.144 / 6.158."""
     target = target or _WGRAD_TARGET
     s = max(1, min(k_blocks, (target + tiles - 1) // tiles))
     return max(1, min(s, k_blocks // max(1, _WGRAD_MIN_KB)))
