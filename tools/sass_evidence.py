@@ -38,8 +38,8 @@ def main() -> None:
     print("emitted as STG.E.128.STRONG.SYS on that address), MUFU.EX2 = ex2.approx, REDG / ATOMG = global reductions / atomics;")
     print("n = SASS instructions of the kernel\n")
     print(f"{'kernel':72s}" + "".join(f"{c:>10s}" for c in COLS) + f"{'n':>8s}")
-    for k, r in sorted(rows.items(), key=lambda kv: kv[0].lstrip("_ZN0123456789GLOBALab cdef_")):
-        name = re.sub(r"^_ZN\d+_GLOBAL__N__[0-9a-f]+_\d+_\w+?_cu_[0-9a-f]+", "", k)
+    for k, r in sorted(rows.items(), key=lambda kv: re.sub(r"^_ZN\d+_GLOBAL__N__[0-9a-f]+_\d+_\w+?_cu_[0-9a-f]{8}\d+", "", kv[0])):
+        name = re.sub(r"^_ZN\d+_GLOBAL__N__[0-9a-f]+_\d+_\w+?_cu_[0-9a-f]{8}\d+", "", k)
         print(f"{name[:72]:72s}" + "".join(f"{r[c]:10d}" for c in COLS) + f"{r['n']:8d}")
     print(f"\n{len(rows)} kernels; {sum(1 for r in rows.values() if r['UTCHMMA'])} issue tcgen05.mma, "
           f"{sum(1 for r in rows.values() if r['UTMALDG'])} load through TMA, {sum(1 for r in rows.values() if r['LDGMC'])} use multimem")
