@@ -24,7 +24,7 @@ def main() -> None:
             continue
         if cur is None or "/*" not in line:
             continue
-        m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        m = re.search(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if not m:
             continue
         op = m.group(1)
