@@ -100,6 +100,7 @@ class SymmetricGradReducer:
         arr = ctypes.c_void_p * self.world
         self._ptrs = [arr(*[int(p) for p in h.buffer_ptrs]) for h in self._h]
         store.grads = self.grads                  # every gradient view is taken from store.grads at call time
+        store._views.clear()                      # (cached views of the old buffer would keep its 198 MB alive)
         opt.sq_chunk = self.sq_chunk[:opt.n_chunks]
         self.clip_global = torch.zeros(1, dtype=torch.float32, device=dev)
         self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)

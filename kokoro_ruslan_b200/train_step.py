@@ -245,6 +245,13 @@ class TrainStep:
         # activations at the bench shape: dynamic batching produces many shapes, so the cache is LRU-bounded
         self.max_cached_shapes = max_cached_shapes
         self._tick = 0
+        # Dynamic batching (DynamicFrameBatchSampler re-packs its buckets every epoch) produces a new (B, P, T, T') shape almost
+        # every step: a graph captured for a shape that never comes back costs a device synchronisation, ~0.3 s of capture
+        # and, at eviction, the release of its ~4 GB pool — measured 24 - 52 ms per step against 14.5 ms for plain eager
+        # launches (tools/dynamic_bench.py).  So capturing is tied to the shape cache's hit rate: always during the first
+        # CAPTURE_PROBE steps (fixed-shape runs capture at once), afterwards only while at least CAPTURE_MIN_HIT of the
+        # steps arrive with a shape that is already cached.
+        self._shape_hits = 0
         self._staged: Dict[Tuple[int, int, int, int, bool], _Staged] = {}
         self._opt_graph: Optional[torch.cuda.CUDAGraph] = None
         self._opt_warm = 0
@@ -336,6 +343,7 @@ class TrainStep:
         key = (B, P, T, Tp, self.engine.spec_spans is not None)
         st = self._staged.get(key)
         self._tick += 1
+        self._shape_hits += st is not None
         if st is None:
             if len(self._staged) >= self.max_cached_shapes:
                 victim = min(self._staged, key=lambda k: self._staged[k].last_used)
@@ -428,7 +436,8 @@ class TrainStep:
             st.launches = launch_count() - n0
             return losses
         if st.graph[v] is None:
-            if st.warm[v] < 1:                    # eager warm-up (builds geometry tables, sets func attrs)
+            worth = self._tick <= self.CAPTURE_PROBE or self._shape_hits >= self.CAPTURE_MIN_HIT * self._tick
+            if st.warm[v] < 1 or not worth:       # eager: warm-up (geometry tables, func attrs) or shapes that do not recur
                 st.warm[v] += 1
                 n0 = launch_count()
                 losses = self._fwd_bwd(st.dev, Tp, zero)
@@ -445,6 +454,9 @@ class TrainStep:
         st.graph[v].replay()
         st.losses = st.graph_losses[v]
         return st.losses
+
+    CAPTURE_PROBE = 32       # steps during which every recurring shape is captured
+    CAPTURE_MIN_HIT = 0.5    # afterwards: fraction of steps whose shape must already be cached for capturing to go on
 
     def _run_optimizer(self) -> None:
         fused = self.reducer is not None and self.world > 1
