@@ -47,14 +47,14 @@ def main():
                                                                  "wait_event": lambda s, e: None})()
     torch.Tensor.pin_memory = lambda self, *a, **k: self
     engine_mod.AcousticEngine._empty = lambda self, *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype)
-    from oracle import acoustic as oa          # synthetic batch only (a tool, not the product path)
+    from bench import synthetic_batch
     from kokoro_ruslan_b200.params import ModelConfig
     from kokoro_ruslan_b200.train_step import ScheduleConfig, TrainStep
     from kokoro_ruslan_b200.engine import DropoutConfig
     cfg = ModelConfig()
     ts = TrainStep(cfg, sched_cfg=ScheduleConfig(total_steps=1000), device="cpu", use_graphs=False,
                    dropout=DropoutConfig.reference_training())
-    batch = oa.synthetic_batch(B=4, P=32, T=200, seed=1, ragged=True)
+    batch = synthetic_batch(4, 32, 200, cfg.mel_dim, cfg.vocab_size, 1)
     ts.train_step(batch)
     t0 = time.perf_counter()
     for _ in range(steps):
