@@ -295,3 +295,30 @@ def test_oracle_explicit_padding_masks_match_reference_golden():
     fix = np.load(os.path.join(HERE, "golden", "acoustic_masks.npz"))
     for k, o in zip(("mel", "log_dur", "stop", "pitch", "energy"), outs):
         assert np.abs(o.numpy() - fix[f"out_{k}"]).max() < 1e-4, k
+
+
+def test_param_views_are_cached_per_buffer_and_follow_repointed_buffers():
+    """ParamStore.p / g / w hand out cached internal-layout views; the flat buffers get re-pointed (EMA weights during
+    validation, symmetric-memory gradients under data parallelism) and the views must follow the buffer, not the name."""
+    import torch
+    from kokoro_ruslan_b200.params import ModelConfig, ParamStore
+    cfg = ModelConfig(hidden_dim=128, n_heads=2, n_encoder_layers=1, n_decoder_layers=1, encoder_ff_dim=256,
+                      decoder_ff_dim=256, variance_filter_size=64)
+    st = ParamStore(cfg, torch.device("cpu"), with_ema=True)
+    name = "transformer_encoder_layers.0.ff.linear1.weight"
+    conv = next(n for n in st.order if ".conv_layers.0.weight" in n)
+    assert st.p(name) is st.p(name) and st.g(name) is st.g(name) and st.w(name) is st.w(name)
+    assert st.p(name).data_ptr() == st.params.data_ptr() + 4 * st.entries[name].offset
+    co, ci, k = st.entries[conv].shape
+    assert tuple(st.p(conv).shape) == (co, k * ci)                      # internal conv layout [C_out, 3 * C_in]
+    old = st.g(name)
+    st.grads = torch.zeros_like(st.grads)                                # what parallel.SymmetricGradReducer does
+    new = st.g(name)
+    assert new is not old and new.data_ptr() == st.grads.data_ptr() + 4 * st.entries[name].offset
+    saved = st.params
+    st.params = st.ema                                                   # what TrainStep.eval_losses does
+    assert st.p(name).data_ptr() == st.ema.data_ptr() + 4 * st.entries[name].offset
+    st.params = saved
+    assert st.p(name).data_ptr() == saved.data_ptr() + 4 * st.entries[name].offset
+    st.p(name).fill_(3.0)
+    assert float(st.params[st.entries[name].offset]) == 3.0 and float(st.ema[st.entries[name].offset]) == 0.0
