@@ -436,8 +436,7 @@ class TrainStep:
             st.launches = launch_count() - n0
             return losses
         if st.graph[v] is None:
-            worth = self._tick <= self.CAPTURE_PROBE or self._shape_hits >= self.CAPTURE_MIN_HIT * self._tick
-            if st.warm[v] < 1 or not worth:       # eager: warm-up (geometry tables, func attrs) or shapes that do not recur
+            if st.warm[v] < 1 or not self._capture_worth():   # eager: warm-up (geometry tables, func attrs) or shapes that do not recur
                 st.warm[v] += 1
                 n0 = launch_count()
                 losses = self._fwd_bwd(st.dev, Tp, zero)
@@ -457,6 +456,10 @@ class TrainStep:
 
     CAPTURE_PROBE = 32       # steps during which every recurring shape is captured
     CAPTURE_MIN_HIT = 0.5    # afterwards: fraction of steps whose shape must already be cached for capturing to go on
+
+    def _capture_worth(self) -> bool:
+        """Graph capture pays only if shapes come back: see the comment at _shape_hits."""
+        return self._tick <= self.CAPTURE_PROBE or self._shape_hits >= self.CAPTURE_MIN_HIT * self._tick
 
     def _run_optimizer(self) -> None:
         fused = self.reducer is not None and self.world > 1

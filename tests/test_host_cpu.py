@@ -322,3 +322,23 @@ def test_param_views_are_cached_per_buffer_and_follow_repointed_buffers():
     assert st.p(name).data_ptr() == saved.data_ptr() + 4 * st.entries[name].offset
     st.p(name).fill_(3.0)
     assert float(st.params[st.entries[name].offset]) == 3.0 and float(st.ema[st.entries[name].offset]) == 0.0
+
+
+def test_graph_capture_follows_the_shape_cache_hit_rate():
+    """Fixed shapes are captured at once; after the probe window capturing goes on only while shapes keep coming back
+    (dynamic batching produces a new shape almost every step: tools/dynamic_bench.py)."""
+    from kokoro_ruslan_b200.train_step import TrainStep
+    ts = TrainStep.__new__(TrainStep)
+    probe = TrainStep.CAPTURE_PROBE
+    ts._tick, ts._shape_hits = 2, 1                       # second step of a fixed-shape run
+    assert ts._capture_worth()
+    ts._tick, ts._shape_hits = probe, 0                   # still probing: a recurring shape is captured
+    assert ts._capture_worth()
+    ts._tick, ts._shape_hits = probe + 1, 1               # dynamic batching: 1 hit in 33 steps
+    assert not ts._capture_worth()
+    ts._tick, ts._shape_hits = 10 * probe, 9 * probe      # fixed shape, long run
+    assert ts._capture_worth()
+    ts._tick, ts._shape_hits = 1000, 499
+    assert not ts._capture_worth()
+    ts._tick, ts._shape_hits = 1000, 500
+    assert ts._capture_worth()
