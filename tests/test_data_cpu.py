@@ -110,3 +110,50 @@ def test_collate_contract():
         assert torch.equal(out["stop_token_targets"][i, :T], it["stop_token_targets"])
     assert out["texts"] == ["t50", "t31", "t64"]
     assert build_stop_token_targets(5, 2).tolist() == [0.0, 0.0, 0.25, 0.5, 1.0]
+
+
+# ---- edge cases against the INSTALLED reference (baseline/_ref), run side by side with the same RNG state -------------------
+EDGE_CASES = [
+    ("empty corpus", [], dict(max_frames=8000, min_batch_size=4, max_batch_size=32, drop_last=False, shuffle=True)),
+    ("single utterance", [512], dict(max_frames=8000, min_batch_size=4, max_batch_size=32, drop_last=False, shuffle=True)),
+    ("single utterance, drop_last", [512], dict(max_frames=8000, min_batch_size=4, max_batch_size=32, drop_last=True, shuffle=True)),
+    ("every utterance over the budget", [9000, 12000, 8500, 8001], dict(max_frames=8000, min_batch_size=1, max_batch_size=32,
+                                                                       drop_last=False, shuffle=True)),
+    ("identical lengths", [700] * 37, dict(max_frames=8000, min_batch_size=4, max_batch_size=8, drop_last=False, shuffle=True)),
+    ("identical lengths, no shuffle", [700] * 37, dict(max_frames=8000, min_batch_size=4, max_batch_size=8, drop_last=True,
+                                                        shuffle=False)),
+    ("max_batch_size 1", [300, 900, 450, 1200, 610], dict(max_frames=20000, min_batch_size=1, max_batch_size=1, drop_last=False,
+                                                         shuffle=True)),
+    ("long-utterance stress (config 4)", [1990, 2010, 1800, 2200, 1500, 1999, 2001], dict(max_frames=8000, min_batch_size=1,
+                                                                                         max_batch_size=32, drop_last=False,
+                                                                                         shuffle=True)),
+]
+
+
+@pytest.mark.parametrize("label,lengths,kwargs", EDGE_CASES, ids=[c[0] for c in EDGE_CASES])
+def test_dynamic_sampler_edge_cases_equal_the_installed_reference(label, lengths, kwargs):
+    """Empty / single / over-budget / degenerate corpora (the reference's tests/unit/test_dynamic_frame_batch_sampler.py covers
+    only the regular case): the reference sampler and this one are built and iterated twice under the same `random` state and
+    must produce the same batch lists — or fail the same way."""
+    import logging
+    import sys
+    root = os.path.dirname(HERE)
+    sys.path.insert(0, root)
+    from oracle import ref_trainer
+    if not ref_trainer.reference_available():
+        pytest.skip("baseline/_ref is not installed")
+    ref_trainer._import_reference()
+    logging.getLogger("kokoro").setLevel(logging.CRITICAL)
+    from kokoro.data.dataset import DynamicFrameBatchSampler as RefSampler
+    from kokoro_ruslan_b200.data import DynamicFrameBatchSampler
+
+    def run(cls):
+        random.seed(1234)
+        try:
+            s = cls(DummyDataset(lengths), **kwargs)
+            return ("ok", [list(map(int, b)) for b in s.batches], [list(map(int, b)) for b in s],
+                    [list(map(int, b)) for b in s], len(s))
+        except Exception as e:          # noqa: BLE001 — the point is that both fail alike
+            return ("raises", type(e).__name__)
+    want, got = run(RefSampler), run(DynamicFrameBatchSampler)
+    assert got == want, (label, got, want)
