@@ -157,3 +157,38 @@ def test_dynamic_sampler_edge_cases_equal_the_installed_reference(label, lengths
             return ("raises", type(e).__name__)
     want, got = run(RefSampler), run(DynamicFrameBatchSampler)
     assert got == want, (label, got, want)
+
+
+@pytest.mark.parametrize("shapes", [[(40, 6)], [(50, 7), (31, 12), (64, 3)], [(1, 1), (2, 1)], [(2000, 250), (3, 2), (777, 90), (12, 12)]],
+                         ids=["batch of one", "ragged", "one-frame utterances", "long-utterance stress"])
+def test_collate_equals_the_installed_reference(shapes):
+    """collate_fn side by side with the reference's (data/dataset.py:871-921) on batches of one, ragged batches, one-frame
+    utterances and the 2000-frame stress case: same keys, dtypes, shapes and values."""
+    import logging
+    import sys
+    root = os.path.dirname(HERE)
+    sys.path.insert(0, root)
+    from oracle import ref_trainer
+    if not ref_trainer.reference_available():
+        pytest.skip("baseline/_ref is not installed")
+    ref_trainer._import_reference()
+    logging.getLogger("kokoro").setLevel(logging.CRITICAL)
+    from kokoro.data.dataset import collate_fn as ref_collate
+    from kokoro_ruslan_b200.data import build_stop_token_targets, collate_fn
+    g = torch.Generator().manual_seed(3)
+    items = []
+    for T, P in shapes:
+        items.append({"mel_spec": torch.randn(80, T, generator=g), "pitch": torch.rand(T, generator=g),
+                      "energy": torch.rand(T, generator=g), "stop_token_targets": build_stop_token_targets(T),
+                      "phoneme_indices": torch.randint(1, 59, (P,), generator=g),
+                      "phoneme_durations": torch.randint(1, 9, (P,), generator=g),
+                      "stress_indices": torch.randint(0, 3, (P,), generator=g), "mel_length": T, "phoneme_length": P,
+                      "text": f"t{T}", "audio_file": f"a{T}.wav"})
+    want = ref_collate([dict(it) for it in items])
+    got = collate_fn([dict(it) for it in items], pin_memory=False)
+    assert set(got) == set(want)
+    for k, w in want.items():
+        if torch.is_tensor(w):
+            assert got[k].dtype == w.dtype and got[k].shape == w.shape and torch.equal(got[k], w), k
+        else:
+            assert list(got[k]) == list(w), k
