@@ -125,3 +125,38 @@ def test_half_block_lists_equal_the_conv():
             n1 = len(G._half_blocks(torch.zeros(32, 32, k), dil, True)[1])
             n2 = len(G._half_blocks(torch.zeros(32, 32, k), 1, True)[1])
             assert n1 + n2 <= 35, (k, dil, n1, n2)
+
+
+def test_oracle_equals_the_installed_reference_on_edge_shapes():
+    """Side by side with the installed reference generator (baseline/_ref) on shapes the fixture does not hold: one frame, an
+    odd handful of frames, a batch of one and of three, an unbatched (80, T) mel, loud / silent inputs."""
+    import logging
+    import sys
+    import pytest
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import hifigan as oh
+    from oracle import ref_trainer
+    if not ref_trainer.reference_available():
+        pytest.skip("baseline/_ref is not installed")
+    ref_trainer._import_reference()
+    logging.getLogger("kokoro").setLevel(logging.CRITICAL)
+    from kokoro.inference.hifigan_vocoder import HiFiGANConfig, HiFiGANGenerator
+    cfg = oh.HifiConfig()
+    ref = HiFiGANGenerator(HiFiGANConfig.get_default_config()).eval()
+    sd = oh.seeded_state_dict(cfg, seed=0)
+    ref.load_state_dict(sd, strict=True)
+    cases = {"one frame": oh.synthetic_mel(1, 1, 5), "seven frames, three utterances": oh.synthetic_mel(3, 7, 6),
+             "unbatched (T, 80)": oh.synthetic_mel(1, 9, 7)[0].t(), "silence": torch.full((1, 80, 5), -11.5),
+             "loud": oh.synthetic_mel(2, 6, 8) + 6.0}
+    for label, mel in cases.items():
+        with torch.no_grad():
+            want = ref(mel)
+        got = oh.generator_forward(sd, cfg, mel)
+        assert got.shape == want.shape, (label, got.shape, want.shape)
+        assert float((got - want).abs().max()) < 2e-6, (label, float((got - want).abs().max()))
+    # a 2-D input is ALWAYS read as (time, mel) (hifigan_vocoder.py:115-117): (80, T) is an error on both sides
+    wrong = oh.synthetic_mel(1, 9, 7)[0]
+    with pytest.raises(RuntimeError):
+        ref(wrong)
+    with pytest.raises(RuntimeError):
+        oh.generator_forward(sd, cfg, wrong)
