@@ -98,7 +98,7 @@ def _cross_attn_step(sd, pre: str, cfg, x: Tensor, k_raw: Tensor, v: Tensor, mem
     k = oa._rms(k_raw, sd[pre + "k_norm.weight"])
     s = (q @ k.transpose(-1, -2)) / math.sqrt(dk)
     s = s.masked_fill(mem_pad.view(mem_pad.shape[0], 1, 1, -1), float("-inf"))
-    o = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(x.shape[0], 1, -1)
+    o = (oa.softmax_rows(s) @ v).transpose(1, 2).reshape(x.shape[0], 1, -1)     # an all-padding memory gives a zero context
     return o @ sd[pre + "w_o.weight"].t() + sd[pre + "w_o.bias"]
 
 
