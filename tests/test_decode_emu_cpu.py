@@ -333,3 +333,33 @@ def test_query_rotation_fix_makes_decode_equal_the_causal_training_forward(emu):
     assert float((outs[True] - causal).abs().max()) / scale < 1e-2                         # fixed decode == training pass
     assert float((outs[False][:, :1] - causal[:, :1]).abs().max()) / scale < 1e-2          # frame 0: position 0 either way
     assert float((outs[False][:, 4:] - causal[:, 4:]).abs().max()) / scale > 3e-2          # the reference's mismatch
+
+
+def test_all_padding_memory_gives_a_zero_cross_attention_context(emu):
+    """A single phoneme whose predicted duration rounds to zero: the 3-frame minimum memory is ALL padding
+    (variance_predictor.py:357-359), torch's SDPA gives the query zero weights and the reference decodes on
+    (tests/test_inference_cpu.py pins the oracle to the installed reference on exactly this case).  The decode kernel's
+    own source (phase C of dec_attn_body: L > 0 ? o / L : 0) must do the same — no NaN, same frames, same stop step."""
+    from oracle import acoustic as oa
+    from oracle import inference as oi
+    cfg = oa.AcousticConfig(hidden_dim=128, n_heads=2, n_encoder_layers=1, n_decoder_layers=2, ff_dim=128, variance_filter=64,
+                            max_len=1200)
+    sd = oa.seeded_state_dict(cfg, seed=6)
+    sd["duration_adaptor.variance_adaptor.duration_predictor.linear.bias"] = torch.tensor([1.2])
+    sd["stop_token_predictor.bias"] = torch.tensor([-1.0])
+    g = torch.Generator().manual_seed(31)
+    torch.randint(1, cfg.vocab_size, (3, 10), generator=g)             # same draw order as the reference-side test
+    idx = torch.randint(1, cfg.vocab_size, (1, 1), generator=g)
+    mem, mem_pad, _ = oi.encode_and_expand(sd, cfg, idx, None)
+    assert mem.shape[1] == 3 and bool(mem_pad.all())                    # the case this test is about
+    want, want_p, raw = oi.forward_inference(sd, cfg, idx, None, return_raw=True)
+    assert torch.isfinite(want).all() and want.shape[1] == 13           # what the installed reference generates
+    loop, be, lo, hi, Tp = _loop(emu, sd, cfg, idx, None)
+    n = want.shape[1]
+    forced = torch.zeros(1, hi, cfg.mel_dim)
+    forced[:, 1:n] = raw[:, :n - 1]
+    got, probs = loop.run(lo, hi, Tp, forced=forced, poll=5)
+    assert torch.isfinite(got).all() and torch.isfinite(probs).all()
+    assert got.shape[1] == n, (got.shape, want.shape)
+    assert float((got - want).abs().max()) / float(want.abs().max()) < 1e-2
+    assert float((probs - torch.tensor(want_p)).abs().max()) < 2e-2
