@@ -363,3 +363,37 @@ def test_all_padding_memory_gives_a_zero_cross_attention_context(emu):
     assert got.shape[1] == n, (got.shape, want.shape)
     assert float((got - want).abs().max()) / float(want.abs().max()) < 1e-2
     assert float((probs - torch.tensor(want_p)).abs().max()) < 2e-2
+
+
+@pytest.mark.parametrize("label,dur_bias,stop_bias,shape,kw", [
+    ("stop never fires", 0.8, -30.0, (1, 6), {}),
+    ("stop fires at once", 0.8, 30.0, (1, 6), {}),
+    ("small max_len", 1.5, -30.0, (1, 12), dict(max_len=20)),
+], ids=["never", "at once", "small max_len"])
+def test_generation_bounds_on_the_kernel_source(emu, label, dur_bias, stop_bias, shape, kw):
+    """The stop rules of dec_finish_body at the edges the reference-side test pins the oracle on: a stop head that never
+    fires ends at the upper bound, one that fires at once ends right after the lower bound, a small max_len caps the run.
+    Teacher-forced with the oracle's frames; the kernel source must stop on the same step."""
+    from oracle import acoustic as oa
+    from oracle import inference as oi
+    from kokoro_ruslan_b200.inference import DecodeLoop, generation_bounds
+    cfg = oa.AcousticConfig(hidden_dim=128, n_heads=2, n_encoder_layers=1, n_decoder_layers=2, ff_dim=128, variance_filter=64,
+                            max_len=1200)
+    sd = oa.seeded_state_dict(cfg, seed=6)
+    sd["duration_adaptor.variance_adaptor.duration_predictor.linear.bias"] = torch.tensor([dur_bias])
+    sd["stop_token_predictor.bias"] = torch.tensor([stop_bias])
+    idx = torch.randint(1, cfg.vocab_size, shape, generator=torch.Generator().manual_seed(17))
+    want, want_p, raw = oi.forward_inference(sd, cfg, idx, None, return_raw=True, **kw)
+    cross, mem_pad, Tp = _memory(sd, cfg, idx, None)
+    lo, hi = generation_bounds(Tp, **kw)
+    assert (lo, hi) == oi.generation_bounds(Tp, **kw)
+    n = want.shape[1]
+    assert n == (hi if stop_bias < 0 else lo + 1), (label, n, lo, hi)   # the edge this case is about
+    t_cap = ((hi + 63) // 64) * 64
+    loop = DecodeLoop(EmuBackend(emu, sd, cfg.max_len), cfg.n_decoder_layers, cfg.hidden_dim, cfg.n_heads, cfg.ff_dim,
+                      cfg.mel_dim, idx.shape[0], Tp, t_cap, cross, mem_pad)
+    forced = torch.zeros(shape[0], hi, cfg.mel_dim)
+    forced[:, 1:n] = raw[:, :n - 1]
+    got, probs = loop.run(lo, hi, Tp, forced=forced, poll=9)
+    assert got.shape[1] == n, (label, got.shape, want.shape)
+    assert float((got - want).abs().max()) / float(want.abs().max()) < 1e-2
