@@ -64,3 +64,31 @@ def test_reference_quirks_are_reproduced(emu):
     # durations past the last frame: tokens 1 and 2 pile their labels (1 + 2 = 3 >= P) onto frame T-1, which drops out
     got = run(emu, torch.tensor([[1.0, 2, 3, 4]]), torch.tensor([[3, 2, 5]]))
     assert torch.allclose(got, torch.tensor([[2.0, 0.0, 0.0]]))
+
+
+def test_kernel_source_equals_the_installed_reference_on_edge_durations(emu):
+    """kr_average_by_duration's own source side by side with the installed reference function (utils/lengths.py:156-208) on
+    zero / negative / single / huge durations, durations running past the frame axis, and masked phonemes: bit-identical."""
+    import logging
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import ref_trainer
+    if not ref_trainer.reference_available():
+        pytest.skip("baseline/_ref is not installed")
+    ref_trainer._import_reference()
+    logging.getLogger("kokoro").setLevel(logging.CRITICAL)
+    from kokoro.utils.lengths import average_by_duration
+    g = torch.Generator().manual_seed(9)
+    cases = {"all zero": torch.zeros(2, 5, dtype=torch.long), "one row zero": torch.tensor([[0, 0, 0, 0], [3, 0, 2, 1]]),
+             "single token": torch.tensor([[7]]), "negative durations": torch.tensor([[2, -3, 4], [-1, -1, 5]]),
+             "ragged": torch.randint(0, 9, (3, 11), generator=g), "long utterance": torch.randint(1, 16, (2, 260), generator=g),
+             "one huge duration": torch.tensor([[1, 1500, 1], [2, 2, 2]])}
+    for label, dur in cases.items():
+        B, P = dur.shape
+        total = int(dur.clamp(min=0).sum(1).max())
+        for T in sorted({max(1, total - 2), max(1, total), total + 3}):     # frame axis shorter than / equal to / longer than the durations
+            vals = torch.rand(B, T, generator=g)
+            for mask in (None, torch.rand(B, P, generator=g) > 0.3):
+                want = average_by_duration(vals, dur, mask)
+                got = run(emu, vals, dur, mask)
+                assert got.shape == want.shape and torch.equal(got, want), (label, T, mask is None, got, want)
