@@ -271,7 +271,8 @@ class TrainStep:
         # step's losses on the host, that step is past its last reader, so the next batch's mel (2 MB, 40 us of PCIe — the one
         # large input) is copied from a side stream while the backward pass and optimizer of the step still run.
         self._mel_idle = False
-        self._copy_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._copy_stream = (torch.cuda.Stream(device=self.device)
+                             if self.device.type == "cuda" and self.engine.multi_stream else None)   # KR_STREAMS=0: one stream
         self._mel_copied: Optional[torch.cuda.Event] = None
         self.launches_last_step = 0
         self.h2d_bytes_last_step = 0
