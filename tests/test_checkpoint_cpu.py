@@ -252,3 +252,65 @@ def test_the_installed_references_own_loader_accepts_a_checkpoint_written_here(t
             assert torch.equal(st["exp_avg_sq"], store.ref_view(store.exp_avg_sq, n).cpu()), n
             n_params += 1
     assert n_params == 132 and len(tr.optimizer.param_groups) == 10
+
+
+def test_resume_from_a_checkpoint_written_by_the_installed_reference_trainer(tmp_path):
+    """The other direction: the UNMODIFIED reference trainer takes two AdamW steps and writes its own checkpoint
+    (trainer.py:1994-2031, save_checkpoint_with_scaler: pickled TrainingConfig, model_metadata, OneCycleLR state, EMA);
+    cli.resume loads it — weights, the Adam moments of every parameter and the step count arrive bit-identical, and training
+    continues at the next epoch."""
+    import logging
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import ref_trainer as harness
+    if not harness.reference_available():
+        pytest.skip("baseline/_ref is not installed")
+    from kokoro_ruslan_b200 import cli
+    from kokoro_ruslan_b200.optim import CTRL_FIELDS
+    from kokoro_ruslan_b200.params import ModelConfig
+    over = dict(n_mels=80, hidden_dim=128, n_heads=2, n_encoder_layers=2, n_decoder_layers=2, encoder_ff_dim=256,
+                decoder_ff_dim=256, max_decoder_seq_len=400, variance_filter_size=64, n_variance_bins=256, num_epochs=3,
+                output_dir=str(tmp_path))
+    tr = harness.build_trainer(None, torch.device("cpu"), 59, over)
+    tr._setup_scheduler()
+    logging.getLogger("kokoro").setLevel(logging.CRITICAL)
+    g = torch.Generator().manual_seed(5)
+    for p in tr.model.parameters():
+        p.grad = torch.randn(p.shape, generator=g) * 0.01
+    tr.optimizer.step()
+    tr.optimizer.step()
+    tr.current_optimizer_step = tr.optimizer_steps_completed = tr.ema_updates = 2
+    tr.save_checkpoint_with_scaler(2, 0.9, val_loss=1.1, best_val_loss=1.0, best_val_epoch=1)
+    path = os.path.join(str(tmp_path), "checkpoint_epoch_3.pth")
+    store, opt = _tiny()
+    store.ema = None                                  # (the EMA restore path refreshes the bf16 shadow: a device op)
+    mc = ModelConfig(vocab_size=59, mel_dim=80, hidden_dim=128, n_encoder_layers=2, n_heads=2, encoder_ff_dim=256,
+                     n_decoder_layers=2, decoder_ff_dim=256, max_decoder_seq_len=400, variance_filter_size=64, n_variance_bins=256)
+
+    class Step:
+        def __init__(self):
+            self.store, self.opt = store, opt
+            self.engine = type("E", (), {"cfg": mc})()
+            self.sched = type("S", (), {"current_optimizer_step": 0, "state_dict": lambda s: {},
+                                        "load_state_dict": lambda s, sd: None})()
+
+        def state_dict(self):
+            return self.store.state_dict()
+
+        def load_state_dict(self, sd):
+            for n in self.store.order:
+                self.store.ref_view(self.store.params, n).copy_(sd[n])
+
+    cfg = cli.RunConfig(output_dir=str(tmp_path))
+    cfg.resume_checkpoint = path
+    assert cli.resume(cfg, Step(), log=lambda s: None) == 3
+    theirs, mine = tr.model.state_dict(), store.state_dict()
+    for k in mine:
+        assert torch.equal(theirs[k], mine[k]), k
+    names = {id(p): n for n, p in tr.model.named_parameters()}
+    for grp in tr.optimizer.param_groups:
+        for p in grp["params"]:
+            n, st = names[id(p)], tr.optimizer.state[p]
+            assert torch.equal(st["exp_avg"], store.ref_view(store.exp_avg, n)), n
+            assert torch.equal(st["exp_avg_sq"], store.ref_view(store.exp_avg_sq, n)), n
+    assert int(opt.ctrl[CTRL_FIELDS.index("step")]) == 2
