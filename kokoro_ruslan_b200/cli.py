@@ -324,6 +324,25 @@ def resume(cfg: RunConfig, step, log: Callable[[str], None] = print) -> int:
     return int(ck.get("epoch", -1)) + 1
 
 
+def save_phoneme_processor(dataset, output_dir: str, log: Callable[[str], None] = print) -> Optional[str]:
+    """<output_dir>/phoneme_processor.pkl = pickle of processor.to_dict(), as the reference trainer writes it at the start of
+    training (trainer.py:2828, checkpoint_manager.py:244-249): the reference's resume / inference read the phoneme table from
+    that file (checkpoint_manager.py:252-259, 527-530).  The processor itself belongs to the phoneme front-end (out of scope):
+    it is whatever object the corpus dataset carries; datasets without one (--synthetic, cached corpora) write nothing."""
+    ds = dataset
+    while ds is not None and not hasattr(ds, "phoneme_processor"):
+        ds = getattr(ds, "ds", None)                # _Subset wrappers of the train / validation split
+    proc = getattr(ds, "phoneme_processor", None)
+    if proc is None or not hasattr(proc, "to_dict"):
+        return None
+    import pickle
+    path = os.path.join(output_dir, "phoneme_processor.pkl")
+    with open(path, "wb") as f:
+        pickle.dump(proc.to_dict(), f)
+    log(f"phoneme processor saved: {path}")
+    return path
+
+
 def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
           log: Callable[[str], None] = print, start_epoch: int = 0) -> Dict:
     """Runs the epochs on an already constructed step object (TrainStep API: micro_step, eval_losses, engine,
@@ -333,6 +352,8 @@ def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
     hist: List[Dict] = []
     best, best_epoch, since_best, saved = float("inf"), -1, 0, []
     os.makedirs(cfg.output_dir, exist_ok=True)
+    if rank == 0:
+        save_phoneme_processor(train_ds, cfg.output_dir, log)
     writer = None
     shard = (rank, world) if (cfg.sharded_checkpoints and world > 1) else None
     if cfg.async_checkpoints and (rank == 0 or shard is not None):

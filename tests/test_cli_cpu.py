@@ -446,3 +446,31 @@ def test_legacy_checkpoint_migrations_follow_the_reference_rules():
     with pytest.raises(RuntimeError, match="'epoch' or 'loss'"):
         ck.check_resume_fields({"optimizer_state_dict": {}, "scheduler_state_dict": {}, "epoch": 1})
     ck.check_resume_fields({"epoch": 1, "loss": 0.5}, training=False)
+
+
+def test_phoneme_processor_pickle_is_read_by_the_references_loader(tmp_path):
+    """cli.save_phoneme_processor writes what the reference trainer writes at the start of training (trainer.py:2828): the
+    installed reference's load_phoneme_processor reads it back into an equal processor; datasets without a processor (the
+    synthetic one) write nothing; the train / validation _Subset wrappers are looked through."""
+    import logging
+    sys.path.insert(0, os.path.dirname(HERE))
+    from kokoro_ruslan_b200 import cli
+    assert cli.save_phoneme_processor(cli.SyntheticDataset(2), str(tmp_path), log=lambda s: None) is None
+    assert not (tmp_path / "phoneme_processor.pkl").exists()
+    from oracle import ref_trainer as harness
+    if not harness.reference_available():
+        pytest.skip("baseline/_ref is not installed")
+    harness._import_reference()
+    logging.getLogger("kokoro").setLevel(logging.CRITICAL)
+    from kokoro.data.russian_phoneme_processor import RussianPhonemeProcessor
+    from kokoro.training.checkpoint_manager import load_phoneme_processor
+    proc = RussianPhonemeProcessor()
+    corpus = type("Corpus", (), {"phoneme_processor": proc, "samples": [{"audio_length": 10}] * 3,
+                                 "__len__": lambda s: 3, "__getitem__": lambda s, i: {}})()
+    wrapped = cli._Subset(corpus, [0, 2])
+    path = cli.save_phoneme_processor(wrapped, str(tmp_path), log=lambda s: None)
+    assert path == str(tmp_path / "phoneme_processor.pkl")
+    back = load_phoneme_processor(str(tmp_path))
+    assert back.phoneme_to_id == proc.phoneme_to_id and back.get_vocab_size() == proc.get_vocab_size()
+    norm = lambda d: {k: (sorted(v) if isinstance(v, list) else v) for k, v in d.items()}      # noqa: E731 — sets travel as lists
+    assert norm(back.to_dict()) == norm(proc.to_dict())
