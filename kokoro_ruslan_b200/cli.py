@@ -431,7 +431,8 @@ def train(cfg: RunConfig, train_ds, val_ds, step, rank: int = 0, world: int = 1,
             break
     if writer is not None:
         writer.wait()                                 # every file is on disk (or the failure is raised) before returning
-    return {"history": hist, "best_val_loss": best, "best_val_epoch": best_epoch, "checkpoints": saved}
+    final = save_final_model(cfg, step) if rank == 0 else None
+    return {"history": hist, "best_val_loss": best, "best_val_epoch": best_epoch, "checkpoints": saved, "final_model": final}
 
 
 def _steps_completed(step) -> int:
@@ -460,6 +461,23 @@ def _detector_state(step) -> Optional[Dict]:
         return None
     c = opt.read_ctrl()
     return {"ema_norm": c["ema_norm"], "ema_steps": c["ema_steps"], "skipped_total": c["skipped_total"]}
+
+
+def save_final_model(cfg: RunConfig, step) -> Optional[str]:
+    """<output_dir>/kokoro_russian_final.pth = {model_state_dict, config, model_metadata}, what the reference trainer writes
+    when training ends (trainer.py:3013, checkpoint_manager.py:916-926) and what its inference loads first
+    (inference/inference.py:111-128)."""
+    if not hasattr(step, "state_dict"):
+        return None
+    path = os.path.join(cfg.output_dir, "kokoro_russian_final.pth")
+    payload = {"model_state_dict": {k: v.detach().cpu() for k, v in step.state_dict().items()},
+               "config": _picklable_config(cfg)}
+    model_cfg = getattr(getattr(step, "engine", None), "cfg", None)
+    if model_cfg is not None and hasattr(model_cfg, "hidden_dim"):
+        from .checkpoint import build_model_metadata
+        payload["model_metadata"] = build_model_metadata(model_cfg, cfg)
+    torch.save(payload, path)
+    return path
 
 
 def save_checkpoint(cfg: RunConfig, step, epoch: int, rec: Dict, best: float, best_epoch: int, writer=None,

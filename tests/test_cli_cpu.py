@@ -474,3 +474,45 @@ def test_phoneme_processor_pickle_is_read_by_the_references_loader(tmp_path):
     assert back.phoneme_to_id == proc.phoneme_to_id and back.get_vocab_size() == proc.get_vocab_size()
     norm = lambda d: {k: (sorted(v) if isinstance(v, list) else v) for k, v in d.items()}      # noqa: E731 — sets travel as lists
     assert norm(back.to_dict()) == norm(proc.to_dict())
+
+
+def test_the_references_inference_loads_the_final_model_written_here(tmp_path):
+    """The output directory of cli.train is what the reference's inference expects: KokoroTTS._load_phoneme_processor and
+    KokoroTTS._load_model (inference/inference.py:85-330, unmodified, installed in baseline/_ref) read phoneme_processor.pkl
+    and kokoro_russian_final.pth written by cli.save_phoneme_processor / cli.save_final_model, build the reference model from
+    the metadata and end up with the very same 135 tensors."""
+    import logging
+    from pathlib import Path
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import ref_trainer as harness
+    if not harness.reference_available():
+        pytest.skip("baseline/_ref is not installed")
+    harness._import_reference()
+    logging.getLogger("kokoro").setLevel(logging.CRITICAL)
+    from kokoro.data.russian_phoneme_processor import RussianPhonemeProcessor
+    from kokoro.inference.inference import KokoroTTS
+    from kokoro_ruslan_b200 import cli
+    from kokoro_ruslan_b200.params import ModelConfig, ParamStore
+    proc = RussianPhonemeProcessor()
+    mc = ModelConfig(vocab_size=len(proc.phoneme_to_id), mel_dim=80, hidden_dim=128, n_encoder_layers=2, n_heads=2,
+                     encoder_ff_dim=256, n_decoder_layers=2, decoder_ff_dim=256, max_decoder_seq_len=400,
+                     variance_filter_size=64, n_variance_bins=256)
+    store = ParamStore(mc, torch.device("cpu"), with_ema=False)
+    store.params.copy_(torch.randn(store.total, generator=torch.Generator().manual_seed(0)) * 0.05)
+    step = type("Step", (), {"store": store, "engine": type("E", (), {"cfg": mc})(), "state_dict": lambda s: store.state_dict()})()
+    cfg = cli.RunConfig(output_dir=str(tmp_path))
+    assert cli.save_final_model(cfg, step) == str(tmp_path / "kokoro_russian_final.pth")
+    cli.save_phoneme_processor(type("Corpus", (), {"phoneme_processor": proc})(), str(tmp_path), log=lambda s: None)
+    tts = KokoroTTS.__new__(KokoroTTS)
+    tts.model_dir, tts.device, tts.weights_preference, tts.enable_profiling = Path(tmp_path), torch.device("cpu"), "auto", False
+    for k in ("inference_max_len", "inference_stop_threshold", "inference_min_len_ratio", "inference_min_len_floor"):
+        setattr(tts, k, None)
+        setattr(tts, "_explicit_" + k, False)
+    tts.phoneme_processor = tts._load_phoneme_processor()
+    assert tts.phoneme_processor.phoneme_to_id == proc.phoneme_to_id
+    model = tts._load_model()
+    mine, theirs = store.state_dict(), model.state_dict()
+    assert len(mine) == 135 and set(mine) <= set(theirs)
+    for k, v in mine.items():
+        assert torch.equal(theirs[k], v), k
+    assert tts.inference_max_len is not None and tts.inference_stop_threshold is not None     # controls came from the metadata
